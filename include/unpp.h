@@ -1,0 +1,188 @@
+/* unpp.h — C ABI of libunpp.so, the sm_100a kernel library behind the UNet_Nested (UNet++) drop-in.
+ *
+ * Boundary contract: plain pointers and sizes only, no torch types.  The caller
+ * (PyTorch) owns ALL device memory — activations, workspaces, packed weights and the flat gradient
+ * buffer are torch tensors whose data_ptr() is passed in.  Every entry point enqueues work on the
+ * cudaStream_t it is given and never synchronises; it returns 0 on success and a negative code on
+ * failure, with a thread-local message available from unpp_last_error().  The library keeps no
+ * global mutable state apart from per-device immutable caches (SM count, driver entry points).
+ *
+ * What each entry point replaces in the reference (file:line into the reference repository):
+ *   unpp_conv_tc        nn.Conv2d 3x3 + [BatchNorm2d eval-folded] + ReLU of unetConv2 (models/unet.py:132-134,140-141),
+ *                       torch.cat of unetUp.forward (unet.py:199-201) as a K-loop over source tensors,
+ *                       nn.ConvTranspose2d k2 s2 of unetUp (unet.py:187) in pointwise+scatter mode,
+ *                       the 1x1 heads + sigmoid (unet.py:242-244,283-286) fused into the epilogue,
+ *                       and — with flipped packed weights — the dgrad of all of the above.
+ *   unpp_pack_weights   (no reference counterpart: OIHW fp32 state_dict -> bf16 UMMA operand layout)
+ *   unpp_nchw_to_nhwc   layout change at the API edge (reference is NCHW fp32 throughout)
+ *   unpp_maxpool2x2     nn.MaxPool2d(2) (unet.py:219,258,260,262)
+ *   unpp_argmax_peaks   the arg-max core of Heatmap.extract_points_ (tools/misc/heatmap.py:173-178)
+ *   unpp_wgrad, unpp_bn_*, unpp_maxpool2x2_bwd, unpp_head_bwd   the autograd backward of unet.py:255-300
+ *   unpp_adamw          tools/optimizers/adamw.py:38-100 (AdamW.step) over one flat buffer
+ */
+#ifndef UNPP_H_
+#define UNPP_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* unpp_stream_t; /* cudaStream_t */
+
+enum {
+  UNPP_OK = 0,
+  UNPP_ERR_BAD_ARG = -1,
+  UNPP_ERR_CUDA = -2,
+  UNPP_ERR_UNSUPPORTED = -3,
+};
+
+#define UNPP_MAX_SRC 6
+
+/* conv modes */
+#define UNPP_MODE_CONV 0    /* out[N,H,W,n_total]                                             */
+#define UNPP_MODE_DECONV 1  /* out[N,2H,2W,n_total/4]; GEMM column = (2p+q)*Cout + co          */
+
+typedef struct UnppConvArgs {
+  int32_t N, H, W;              /* pixel grid of the sources (all sources share it)             */
+  int32_t nsrc;                 /* number of concatenated source tensors (K loop walks them)    */
+  const void* src[UNPP_MAX_SRC];/* NHWC bf16, C = src_C[i] in {16,32,64,128}                     */
+  int32_t src_C[UNPP_MAX_SRC];
+  /* src_step[i] in {0,1}: dense [N,H,W,C].  2: the tensor is [N,2H,2W,C] and pixel (y,x) of the grid
+   * reads (2y+src_oy[i], 2x+src_ox[i]) — the four taps of the k2s2 transposed-conv dgrad.        */
+  int32_t src_step[UNPP_MAX_SRC], src_oy[UNPP_MAX_SRC], src_ox[UNPP_MAX_SRC];
+  int32_t taps;                 /* 9 = 3x3 stride 1 pad 1;  1 = pointwise                        */
+  int32_t n_total;              /* GEMM N: Cout (conv) or 4*Cout (deconv)                        */
+  int32_t n_tile;               /* columns per CTA; divides n_total; multiple of 16; <= 256      */
+  const void* wpacked;          /* bf16 [n_total/n_tile][taps][K/8][n_tile][8]  (unpp_pack_weights) */
+  const float* bias;            /* fp32 [Cout] or NULL                                           */
+  int32_t mode;                 /* UNPP_MODE_*                                                   */
+  int32_t relu;                 /* apply max(.,0) after bias                                     */
+  void* out;                    /* NHWC bf16 or NULL (head-only)                                 */
+  /* fused 1x1 head + sigmoid: requires mode conv, n_total == n_tile == 16 */
+  const float* head_w;          /* fp32 [classes][16] or NULL                                    */
+  const float* head_b;          /* fp32 [classes]                                                */
+  float* heat;                  /* fp32 NCHW [N,classes,H,W]                                     */
+  float* logit;                 /* optional fp32 NCHW pre-sigmoid output (training) or NULL       */
+  int32_t head_classes;         /* <= 8                                                          */
+  /* head dropout (training): keep-mask u8 NHWC [N,H,W,16] or NULL; scale = 1/(1-p) */
+  const uint8_t* drop_mask;
+  float drop_scale;
+  /* backward-only epilogue inputs, both NHWC bf16 shaped like `out` (conv mode) */
+  const void* addend;           /* added to the accumulator before masking, or NULL              */
+  const void* relu_mask_src;    /* forward activation y: result is zeroed where y <= 0, or NULL   */
+  /* per-channel reductions of the fp32 result over all pixels (BN batch stats / bias grads):
+   * stats[0..Cout) += sum(v), stats[Cout..2Cout) += sum(v*v) or sum(v*aux) ; fp32 atomics into a
+   * [gridDim][2][Cout] partial buffer, reduced deterministically by unpp_reduce_partials. */
+  float* stats_partial;         /* fp32 [unpp_conv_grid()][2][Cout] or NULL                       */
+  const void* stats_aux;        /* NHWC bf16 like out, or NULL (then second stat = sum v*v)       */
+  const float* aux_mean;        /* with stats_aux: second stat = sum v * (aux - mean[c]) * istd[c]*/
+  const float* aux_istd;
+} UnppConvArgs;
+
+const char* unpp_last_error(void);
+int unpp_version(void);
+int unpp_num_sms(void);
+
+/* Fused implicit-GEMM convolution on tcgen05 tensor cores (TMA-staged NHWC bf16 halo tiles). */
+int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream);
+/* Number of CTAs unpp_conv_tc will launch for these args (size of stats_partial's leading dim). */
+int unpp_conv_grid(const UnppConvArgs* a);
+
+/* Weight packing into the UMMA B-operand layout [n_total/n_tile][taps][K/8][n_tile][8] (bf16).
+ *  kind 0: forward conv   B[n=co][tap][k=ci]   = W[co][k_begin+ci][tap] * (scale ? scale[co] : 1)
+ *          src = OIHW fp32 [Cout][Cin_total][kh][kw]; K = k_count channels starting at k_begin
+ *  kind 1: dgrad of conv  B[n=ci][tap][k=co]   = W[co][n_begin+ci][taps-1-tap]  (flipped taps)
+ *          n_total = number of input channels of the slice, K = Cout
+ *  kind 2: deconv forward B[n=(2p+q)*Cout+co][0][k=ci] = Wd[ci][co][p][q]; src [Cin][Cout][2][2]
+ *  kind 3: deconv dgrad   (one pointwise GEMM per (p,q) tap over the up-resolution gradient)
+ *          B[n=ci][tap=2p+q][k=co] = Wd[ci][co][p][q]
+ * k_dst8 places the K range at 8-channel chunk offset k_dst8 inside a K/8 = k8_total wide buffer,
+ * so that several sources (concat) or several consumers (dgrad gather) share one packed tensor. */
+typedef struct UnppPackArgs {
+  const float* src;
+  void* dst;            /* bf16 */
+  const float* scale;   /* per output channel (BN fold), kind 0 only, or NULL */
+  int32_t kind;
+  int32_t src_O, src_I; /* dims 0 and 1 of the source weight tensor */
+  int32_t taps;
+  int32_t n_total, n_tile;
+  int32_t n_begin;      /* kind 1: first input channel of the slice */
+  int32_t k_begin, k_count;
+  int32_t k8_total, k_dst8;
+} UnppPackArgs;
+int unpp_pack_weights(const UnppPackArgs* a, unpp_stream_t stream);
+
+/* fp32 NCHW [N,C,H,W] -> bf16 NHWC [N,H,W,Cpad] (channels >= C zero-filled). */
+int unpp_nchw_to_nhwc(const float* x, void* out, int N, int C, int H, int W, int Cpad, unpp_stream_t stream);
+/* bf16 NHWC 2x2/2 max pooling (H, W even). */
+int unpp_maxpool2x2(const void* x, void* out, int N, int H, int W, int C, unpp_stream_t stream);
+/* Per-plane arg-max of fp32 NCHW heatmaps: first maximum in row-major order -> xy[b][c] = {x, y},
+ * val[b][c] = the maximum (val may be NULL). One CTA per plane, warp-shuffle reduction. */
+int unpp_argmax_peaks(const float* heat, int planes, int H, int W, int32_t* xy, float* val, unpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Training step.  Reference counterparts: autograd of models/unet.py:255-300 (cuDNN dgrad/wgrad,
+ * BatchNorm / MaxPool / Dropout / sigmoid backward), nn.MSELoss (trainer/trainer.py:427) and
+ * tools/optimizers/adamw.py:38-100.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Weight gradient dW[tap][ci][co] = sum_pixels X[pix + tap][ci] * dZ[pix][co] as per-CTA partials
+ * fp32 [unpp_wgrad_grid()][taps][sum src_C][cout], reduced by unpp_wgrad_reduce. */
+typedef struct UnppWgradArgs {
+  int32_t N, H, W;               /* pixel grid */
+  int32_t nsrc;
+  const void* src[UNPP_MAX_SRC]; /* forward inputs of the conv (virtual concat), NHWC bf16 dense    */
+  int32_t src_C[UNPP_MAX_SRC];
+  const void* dz;                /* NHWC bf16 [N, H*dz_step, W*dz_step, cout]                        */
+  int32_t cout;
+  int32_t dz_step, dz_oy, dz_ox; /* 1,0,0 = dense; 2,p,q = tap (p,q) of a k2s2 transposed conv       */
+  int32_t taps;                  /* 9 or 1 */
+  float* partial;
+} UnppWgradArgs;
+int unpp_wgrad(const UnppWgradArgs* a, unpp_stream_t stream);
+int unpp_wgrad_grid(const UnppWgradArgs* a);
+/* dst[co*s_co + ci*s_ci + tap*s_tap] = scale * sum_p partial[p][tap][ci_begin+ci][co], ci < ci_count */
+int unpp_wgrad_reduce(const float* partial, int nparts, int taps, int cin_total, int cout, float* dst, int ci_begin, int ci_count,
+                      long s_co, long s_ci, long s_tap, float scale, unpp_stream_t stream);
+/* out[i] (+)= scale * sum_p partial[p*stride + i], i < n (fixed order: deterministic) */
+int unpp_reduce_partials(const float* partial, int nparts, long stride, int n, float scale, float* out, int accumulate,
+                         unpp_stream_t stream);
+
+/* BatchNorm2d batch statistics from the conv epilogue partials [nparts][2][C] (sum, sum of squares):
+ * mean, inverse std (biased variance, eps), fused affine scale = gamma*istd, shift = beta - mean*scale,
+ * and the running-stat update with the unbiased variance (running_* may be NULL). */
+int unpp_bn_finalize(const float* partial, int nparts, int C, float count, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, float* mean, float* istd, float* scale, float* shift,
+                     unpp_stream_t stream);
+/* y = relu(z*scale + shift) on NHWC bf16; pooled (optional) = 2x2/2 max pool of y. */
+int unpp_bn_relu(const void* z, const float* scale, const float* shift, void* y, void* pooled, int N, int H, int W, int C,
+                 unpp_stream_t stream);
+/* MaxPool2d(2) backward: dx[N,H,W,C] from dpooled[N,H/2,W/2,C] and the forward input x (first max wins). */
+int unpp_maxpool2x2_bwd(const void* x, const void* dpooled, void* dx, int N, int H, int W, int C, unpp_stream_t stream);
+/* BatchNorm backward apply: dz = gamma*istd*(dyh - sums[c]/count - xhat*sums[C+c]/count), xhat=(z-mean)*istd. */
+int unpp_bn_bwd_apply(const void* dyh, const void* z, const float* mean, const float* istd, const float* gamma, const float* sums,
+                      float count, void* dz, int N, int H, int W, int C, unpp_stream_t stream);
+/* Head backward (sigmoid' + 1x1 conv dgrad/wgrad + dropout mask).  Exactly one of dheat (upstream
+ * gradient, fp32 NCHW) and target (fused MSE: dheat = coef*(heat-target), loss partial = sum (heat-target)^2)
+ * is non-NULL.  partial: fp32 [unpp_head_bwd_grid()][classes*16 + classes + 1] = dW, db, loss. */
+int unpp_head_bwd(const float* heat, const float* dheat, const float* target, float coef, const void* x, const uint8_t* drop_mask,
+                  float drop_scale, const float* head_w, int classes, void* dx, float* partial, int N, int H, int W,
+                  unpp_stream_t stream);
+int unpp_head_bwd_grid(int N, int H, int W);
+/* The reference's AdamW on a flat fp32 buffer (decay = weight_decay * p_old, not scaled by lr);
+ * step is the 1-based step count; gradients are multiplied by grad_scale first (1/world for DP). */
+int unpp_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+               int step, float grad_scale, unpp_stream_t stream);
+/* u8 keep-mask for nn.Dropout(p): mask[i] = 1 with probability 1-p (counter-based hash of seed, i). */
+int unpp_dropout_mask(uint8_t* mask, long n, float p_drop, uint64_t seed, unpp_stream_t stream);
+
+/* sizeof() of the argument structs as the C compiler sees them (binding self-check). */
+int unpp_sizeof_conv_args(void);
+int unpp_sizeof_pack_args(void);
+int unpp_sizeof_wgrad_args(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNPP_H_ */

@@ -1,0 +1,87 @@
+"""CPU: the drop-in boundary — constructor, state_dict layout, seeded init stream,
+error behaviour, and the exported C ABI."""
+import ctypes
+import hashlib
+import os
+import re
+
+import pytest
+import torch
+
+import unet_nested4tiny_objects_keypoints_b200 as pkg
+from unet_nested4tiny_objects_keypoints_b200 import _lib, models
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _sha(sd):
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode() + v.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def test_constructed_with_no_arguments_like_the_trainer():
+    m = getattr(models, "UNet_Nested")()  # trainer/trainer.py:337,340
+    assert (m.in_channels, m.n_classes, m.feature_scale, m.is_deconv, m.is_batchnorm, m.is_ds) == (3, 4, 2, True, True, True)
+    assert models.count_param(m) == 553260
+
+
+def test_state_dict_layout_and_seeded_init_equal_the_reference(golden):
+    _, meta = golden
+    torch.manual_seed(0)
+    m = pkg.UNet_Nested()
+    sd = m.state_dict()
+    assert [[k, list(v.shape), str(v.dtype)] for k, v in sd.items()] == meta["state_dict_keys"]
+    assert sum(v.numel() * v.element_size() for v in sd.values()) == 2216944
+    # same parameter-holder tree + same three init passes => same RNG stream as the reference
+    assert _sha(sd) == meta["init_seed0_sha256"]
+
+
+def test_state_dict_round_trip():
+    from oracle import unetpp_oracle as O
+    m = pkg.UNet_Nested()
+    sd = O.synth_state_dict(seed=5)
+    missing, unexpected = m.load_state_dict(sd)
+    assert not missing and not unexpected
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_dataparallel_wrapper_exposes_module_state_dict():
+    m = pkg.UNet_Nested()
+    dp = torch.nn.DataParallel(m)  # trainer/trainer.py:338; .module.state_dict() at 240
+    assert list(dp.module.state_dict().keys()) == list(m.state_dict().keys())
+
+
+def test_no_cpu_fallback():
+    m = pkg.UNet_Nested().eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 3, 32, 32))
+    with pytest.raises(ValueError):
+        m(torch.zeros(3, 32, 32))
+
+
+def test_unknown_init_type_raises_like_the_reference():
+    with pytest.raises(NotImplementedError):
+        models.init_weights(torch.nn.Conv2d(1, 1, 1), init_type="normal")  # unet.py:163
+
+
+def test_library_exports_every_symbol_declared_in_the_header():
+    hdr = open(os.path.join(ROOT, "include", "unpp.h")).read()
+    declared = set(re.findall(r"\b(unpp_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found in include/unpp.h"
+    assert declared == set(_lib.exported_symbols())
+    lib = ctypes.CDLL(_lib.LIB_PATH)  # loading must work without a GPU
+    for name in declared:
+        assert hasattr(lib, name), name
+    loaded = _lib.load()
+    assert loaded.unpp_version() >= 1
+    assert isinstance(loaded.unpp_last_error(), bytes)
+
+
+def test_struct_layouts_match_the_header():
+    # sizes computed by the C compiler are embedded in the library (unpp_sizeof_*)
+    lib = _lib.load()
+    assert lib.unpp_sizeof_conv_args() == ctypes.sizeof(_lib.ConvArgs)
+    assert lib.unpp_sizeof_pack_args() == ctypes.sizeof(_lib.PackArgs)

@@ -1,0 +1,81 @@
+"""GPU: the drop-in UNet_Nested (eval mode) against the committed reference outputs and the oracle.
+
+Stated bf16 bound (DESIGN.md "Numerics"): activations are stored in bf16 between the fused kernels
+(fp32 accumulation in TMEM), so post-sigmoid heat maps agree with the fp32 reference to
+max |err| <= 2e-2 absolute (typically 3e-3); keypoint arg-max indices are bit-exact on identical
+heat maps (test_kernels_gpu.py::test_argmax_bit_exact)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import unet_nested4tiny_objects_keypoints_b200 as pkg  # noqa: E402
+from oracle import unetpp_oracle as O  # noqa: E402
+
+HEAT_ATOL = 2e-2
+
+
+def make_model(seed=1):
+    m = pkg.UNet_Nested()
+    m.load_state_dict(O.synth_state_dict(seed=seed))
+    return m.to("cuda").eval()
+
+
+def test_eval_forward_matches_reference_golden(golden):
+    arr, _ = golden
+    m = make_model(1)
+    with torch.no_grad():
+        outs = m(torch.from_numpy(arr["eval_x"]).cuda())
+    assert isinstance(outs, tuple) and len(outs) == 3
+    for i, o in enumerate(outs):
+        assert o.dtype == torch.float32 and o.shape == (2, 4, 32, 32)
+        err = np.abs(o.cpu().numpy() - arr[f"eval_out{i}"]).max()
+        assert err <= HEAT_ATOL, (i, err)
+    with torch.no_grad():
+        o2 = m(torch.from_numpy(arr["eval2_x"]).cuda())[2]
+    assert np.abs(o2.cpu().numpy() - arr["eval2_out2"]).max() <= HEAT_ATOL
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 256, 256), (3, 64, 96), (2, 8, 8), (1, 72, 40)])
+def test_eval_forward_matches_oracle(B, H, W):
+    sd = O.synth_state_dict(seed=3)
+    m = make_model(3)
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    x = torch.randn(B, 3, H, W, generator=g)
+    ref = O.forward(sd, x)
+    with torch.no_grad():
+        outs = m(x.cuda())
+    for r, o in zip(ref, outs):
+        assert float((o.cpu() - r).abs().max()) <= HEAT_ATOL
+
+
+def test_uniform_image_input_and_predict_keypoints():
+    sd = O.synth_state_dict(seed=4)
+    m = make_model(4)
+    x = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(7))  # un-normalised ToTensor-style images
+    ref = O.forward(sd, x)
+    xy, val, heats = m.predict_keypoints(x.cuda(), head=2)
+    assert float((heats[2].cpu() - ref[2]).abs().max()) <= HEAT_ATOL
+    # the fused pipeline's arg-max equals the oracle's arg-max of the SAME heat maps, bit-exactly
+    rxy, rval = O.argmax_keypoints(heats[2].cpu().numpy())
+    assert np.array_equal(xy.cpu().numpy(), rxy) and np.array_equal(val.cpu().numpy(), rval)
+
+
+def test_reference_error_behaviour_on_bad_sizes():
+    m = make_model(1)
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 36, 36, device="cuda"))  # not divisible by 8: the reference's torch.cat throws too
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 4, 32, 32, device="cuda"))
+
+
+def test_weights_are_repacked_after_load_state_dict():
+    m = make_model(1)
+    x = torch.randn(1, 3, 32, 32, generator=torch.Generator().manual_seed(1)).cuda()
+    with torch.no_grad():
+        a = m(x)[2].clone()
+        m.load_state_dict(O.synth_state_dict(seed=9))
+        b = m(x)[2]
+    ref = O.forward(O.synth_state_dict(seed=9), x.cpu())[2]
+    assert float((b.cpu() - ref).abs().max()) <= HEAT_ATOL and not torch.equal(a, b)

@@ -1,0 +1,361 @@
+"""GPU: each libunpp.so kernel, called through the C ABI (ops.py -> ctypes), against a plain
+torch-CPU fp32/fp64 restatement of the same op on the same bf16-rounded inputs.
+
+Tolerances: the kernels read bf16, accumulate in fp32 and store bf16, so against an fp64 reference
+on identical bf16 inputs the error is the output rounding (2^-9 relative) plus fp32 accumulation
+noise: |err| <= 6e-3 * max|ref| for bf16 outputs, 2e-3 for fp32 outputs.  Integer outputs (arg-max)
+are bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from unet_nested4tiny_objects_keypoints_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def bf(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def nhwc(t):  # NCHW fp32 cpu -> NHWC bf16 cuda
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(DEV)
+
+
+def nchw(t):  # NHWC bf16 cuda -> NCHW fp32 cpu
+    return t.float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def close(got, ref, rel, what=""):
+    ref = ref.double()
+    err = float((got.double() - ref).abs().max())
+    scale = float(ref.abs().max()) + 1e-30
+    assert err <= rel * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.3e} > {rel})"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+@pytest.mark.parametrize("N,H,W,cins,cout", [
+    (2, 24, 40, [16], 16),
+    (1, 16, 16, [64], 64),
+    (2, 8, 8, [128], 128),
+    (1, 40, 72, [32], 32),
+    (1, 32, 32, [16, 16, 16, 16], 16),
+    (2, 16, 24, [32, 32, 32], 32),
+    (1, 16, 16, [64, 64], 64),
+    (1, 8, 8, [64], 128),
+    (3, 64, 64, [16, 16], 16),
+    (1, 128, 128, [16], 16),
+])
+def test_conv3x3_bias_relu_virtual_concat(N, H, W, cins, cout):
+    cin = sum(cins)
+    xs = [bf(rnd(N, c, H, W, seed=i + 1)) for i, c in enumerate(cins)]
+    w = bf(rnd(cout, cin, 3, 3, seed=50, scale=(2.0 / (9 * cin)) ** 0.5))
+    b = rnd(cout, seed=51, scale=0.1)
+    ref = F.relu(F.conv2d(torch.cat(xs, 1).double(), w.double(), b.double(), padding=1))
+    nt = ops.pick_n_tile(cout, cin, 9)
+    wp = ops.pack_weights(w.to(DEV), 0, 9, cout, nt, cin)
+    out = torch.empty(N, H, W, cout, dtype=torch.bfloat16, device=DEV)
+    ops.conv([nhwc(x) for x in xs], N, H, W, wp, cout, nt, 9, bias=b.to(DEV), relu=True, out=out)
+    torch.cuda.synchronize()
+    close(nchw(out), ref, 6e-3, "conv3x3")
+
+
+@pytest.mark.parametrize("n_tile", [16, 32, 64])
+def test_conv3x3_n_tile_split(n_tile):
+    N, H, W, cin, cout = 1, 16, 24, 32, 64
+    x = bf(rnd(N, cin, H, W, seed=3))
+    w = bf(rnd(cout, cin, 3, 3, seed=4, scale=0.1))
+    ref = F.conv2d(x.double(), w.double(), padding=1)
+    wp = ops.pack_weights(w.to(DEV), 0, 9, cout, n_tile, cin)
+    out = torch.empty(N, H, W, cout, dtype=torch.bfloat16, device=DEV)
+    ops.conv([nhwc(x)], N, H, W, wp, cout, n_tile, 9, out=out)
+    close(nchw(out), ref, 6e-3, "conv n_tile")
+
+
+def test_bn_fold_scale_in_pack():
+    N, H, W, cin, cout = 1, 16, 16, 16, 32
+    x = bf(rnd(N, cin, H, W, seed=5))
+    w = rnd(cout, cin, 3, 3, seed=6, scale=0.1)
+    scale = torch.rand(cout) + 0.5
+    ref = F.conv2d(x.double(), bf(w * scale[:, None, None, None]).double(), padding=1)
+    wp = ops.pack_weights(w.to(DEV), 0, 9, cout, 32, cin, scale=scale.to(DEV))
+    out = torch.empty(N, H, W, cout, dtype=torch.bfloat16, device=DEV)
+    ops.conv([nhwc(x)], N, H, W, wp, cout, 32, 9, out=out)
+    close(nchw(out), ref, 6e-3, "bn fold")
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout", [(2, 8, 12, 32, 16), (1, 16, 16, 64, 32), (1, 4, 4, 128, 64), (1, 64, 64, 32, 16)])
+def test_deconv_k2s2(N, H, W, cin, cout):
+    x = bf(rnd(N, cin, H, W, seed=7))
+    w = bf(rnd(cin, cout, 2, 2, seed=8, scale=0.2))
+    b = rnd(cout, seed=9, scale=0.1)
+    ref = F.conv_transpose2d(x.double(), w.double(), b.double(), stride=2)
+    nt = ops.pick_n_tile(4 * cout, cin, 1, deconv=True)
+    wp = ops.pack_weights(w.to(DEV), 2, 1, 4 * cout, nt, cin)
+    out = torch.empty(N, 2 * H, 2 * W, cout, dtype=torch.bfloat16, device=DEV)
+    ops.conv([nhwc(x)], N, H, W, wp, 4 * cout, nt, 1, bias=b.to(DEV), mode=ops.MODE_DECONV, out=out)
+    close(nchw(out), ref, 6e-3, "deconv")
+
+
+@pytest.mark.parametrize("with_mask", [False, True])
+def test_fused_head_sigmoid_dropout(with_mask):
+    N, H, W = 2, 16, 24
+    x = bf(rnd(N, 16, H, W, seed=10))
+    w = bf(rnd(16, 16, 3, 3, seed=11, scale=0.12))
+    b = rnd(16, seed=12, scale=0.1)
+    hw, hb = rnd(4, 16, seed=13, scale=0.5), rnd(4, seed=14, scale=0.2)
+    y = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1))
+    mask = (torch.rand(N, 16, H, W, generator=torch.Generator().manual_seed(15)) >= 0.4)
+    yd = y * mask.double() / 0.6 if with_mask else y
+    logit = F.conv2d(yd, hw.double()[:, :, None, None], hb.double())
+    wp = ops.pack_weights(w.to(DEV), 0, 9, 16, 16, 16)
+    out = torch.empty(N, H, W, 16, dtype=torch.bfloat16, device=DEV)
+    heat = torch.empty(N, 4, H, W, device=DEV)
+    lg = torch.empty(N, 4, H, W, device=DEV)
+    m8 = mask.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(DEV) if with_mask else None
+    ops.conv([nhwc(x)], N, H, W, wp, 16, 16, 9, bias=b.to(DEV), relu=True, out=out,
+             head=(hw.to(DEV), hb.to(DEV), heat, lg, m8, 1 / 0.6 if with_mask else 1.0))
+    close(nchw(out), y, 6e-3, "head conv out")
+    close(lg.cpu(), logit, 2e-3, "logit")
+    close(heat.cpu(), torch.sigmoid(logit), 2e-3, "heat")
+
+
+def test_input_layout_and_maxpool():
+    x = rnd(2, 3, 16, 24, seed=16)
+    out = torch.empty(2, 16, 24, 16, dtype=torch.bfloat16, device=DEV)
+    ops.nchw_to_nhwc16(x.to(DEV), out)
+    got = nchw(out)
+    assert torch.equal(got[:, :3], bf(x)) and float(got[:, 3:].abs().max()) == 0.0
+    y = bf(rnd(2, 32, 16, 24, seed=17))
+    p = torch.empty(2, 8, 12, 32, dtype=torch.bfloat16, device=DEV)
+    ops.maxpool(nhwc(y), p)
+    assert torch.equal(nchw(p), F.max_pool2d(y, 2))
+
+
+def test_argmax_bit_exact(golden):
+    from oracle import unetpp_oracle as O
+    arr, _ = golden
+    for planes in (arr["peaks_planes"], arr["tie_plane"], np.random.default_rng(0).random((3, 4, 40, 56), dtype=np.float32)):
+        xy, val = ops.argmax_peaks(torch.from_numpy(planes).to(DEV))
+        rxy, rval = O.argmax_keypoints(planes)
+        assert np.array_equal(xy.cpu().numpy(), rxy)
+        assert np.array_equal(val.cpu().numpy(), rval)
+    assert np.array_equal(ops.argmax_peaks(torch.from_numpy(arr["peaks_planes"]).to(DEV))[0].cpu().numpy(), arr["peaks_xy"])
+    # plateau / constant / last-pixel / odd-size planes
+    z = np.zeros((1, 3, 9, 13), dtype=np.float32)
+    z[0, 1, 8, 12] = 1.0
+    z[0, 2, 3:6, 4:9] = 0.5
+    xy, _ = ops.argmax_peaks(torch.from_numpy(z).to(DEV))
+    assert xy.cpu().tolist() == [[[0, 0], [12, 8], [4, 3]]]
+
+
+# ---------------------------------------------------------------------------------------------- training kernels
+@pytest.mark.parametrize("N,H,W,cins,cout", [
+    (2, 16, 40, [16], 16),
+    (1, 24, 32, [16, 16, 16], 16),
+    (2, 16, 16, [32, 32], 32),
+    (1, 16, 16, [64], 64),
+    (2, 8, 8, [128], 128),
+    (1, 8, 8, [64, 64], 64),
+    (1, 8, 8, [64], 128),
+    (3, 64, 64, [16], 16),
+])
+def test_wgrad_conv3x3(N, H, W, cins, cout):
+    cin = sum(cins)
+    xs = [bf(rnd(N, c, H, W, seed=i + 20)) for i, c in enumerate(cins)]
+    dz = bf(rnd(N, cout, H, W, seed=30, scale=0.5))
+    ref = torch.nn.grad.conv2d_weight(torch.cat(xs, 1).double(), (cout, cin, 3, 3), dz.double(), padding=1)
+    g = ops.wgrad_grid(cins, N, H, W, cout, 9)
+    partial = torch.full((g, 9, cin, cout), float("nan"), device=DEV)
+    ops.wgrad([nhwc(x) for x in xs], N, H, W, nhwc(dz), cout, 9, partial)
+    dst = torch.zeros(cout, cin, 3, 3, device=DEV)
+    ops.wgrad_reduce(partial, g, 9, cin, cout, dst, 0, cin, cin * 9, 9, 1)
+    close(dst.cpu(), ref, 2e-3, "wgrad")
+
+
+def test_wgrad_deconv_strided_dz():
+    N, H, W, cin, cout = 2, 8, 12, 32, 16
+    x = bf(rnd(N, cin, H, W, seed=31))
+    du = bf(rnd(N, cout, 2 * H, 2 * W, seed=32))
+    w = torch.zeros(cin, cout, 2, 2, dtype=torch.double, requires_grad=True)
+    F.conv_transpose2d(x.double(), w, stride=2).backward(du.double())
+    dst = torch.zeros(cin, cout, 2, 2, device=DEV)
+    g = ops.wgrad_grid([cin], N, H, W, cout, 1)
+    partial = torch.empty(g, 1, cin, cout, device=DEV)
+    du_d = nhwc(du)
+    for pq in range(4):
+        ops.wgrad([nhwc(x)], N, H, W, du_d, cout, 1, partial, dz_view=(pq >> 1, pq & 1))
+        ops.wgrad_reduce(partial, g, 1, cin, cout, dst, 0, cin, 4, cout * 4, 0, dst_offset=pq)
+    close(dst.cpu(), w.grad, 2e-3, "deconv wgrad")
+
+
+@pytest.mark.parametrize("cins_consumers,c_t", [([16], 16), ([16, 16, 16], 16), ([32, 32], 32), ([64], 32), ([128], 64)])
+def test_dgrad_gather_with_relu_mask_and_stats(cins_consumers, c_t):
+    """dT = sum_k conv_transpose(dZ_k, W_k[:, slice]) (+ addend), masked by T > 0, with per-channel sums."""
+    N, H, W = 2, 16, 24
+    t_act = bf(F.relu(rnd(N, c_t, H, W, seed=40)))
+    dzs = [bf(rnd(N, c, H, W, seed=41 + i)) for i, c in enumerate(cins_consumers)]
+    ws = [bf(rnd(c, c_t + 16, 3, 3, seed=45 + i, scale=0.1)) for i, c in enumerate(cins_consumers)]  # consumer weights [co, ci_total, 3, 3]
+    addend = bf(rnd(N, c_t, H, W, seed=49, scale=0.3))
+    n_begin = 16  # T occupies input channels [16, 16 + c_t) of every consumer
+    ref = addend.double().clone()
+    for dz, w in zip(dzs, ws):
+        ref += F.conv_transpose2d(dz.double(), w.double()[:, n_begin:n_begin + c_t], padding=1)
+    ref = ref * (t_act > 0)
+    ktot = sum(cins_consumers)
+    nt = ops.pick_n_tile(c_t, ktot, 9)
+    wp = torch.zeros(c_t * 9 * ktot, dtype=torch.bfloat16, device=DEV)
+    k8 = 0
+    for c, w in zip(cins_consumers, ws):
+        ops.pack_weights(w.to(DEV), 1, 9, c_t, nt, c, n_begin=n_begin, dst=wp, k8_total=ktot // 8, k_dst8=k8)
+        k8 += c // 8
+    out = torch.empty(N, H, W, c_t, dtype=torch.bfloat16, device=DEV)
+    g = ops.conv_grid(cins_consumers, N, H, W, c_t, nt, 9)
+    stats = torch.full((g, 2, c_t), float("nan"), device=DEV)
+    ops.conv([nhwc(d) for d in dzs], N, H, W, wp, c_t, nt, 9, out=out, addend=nhwc(addend), relu_mask_src=nhwc(t_act), stats_partial=stats)
+    got = nchw(out)
+    close(got, ref, 6e-3, "dgrad gather")
+    sums = torch.empty(2 * c_t, device=DEV)
+    ops.reduce_partials(stats, g, 2 * c_t, 2 * c_t, sums)
+    close(sums[:c_t].cpu(), got.double().sum((0, 2, 3)), 1e-3, "sum v")
+    close(sums[c_t:].cpu(), (got.double() ** 2).sum((0, 2, 3)), 1e-3, "sum v^2")
+
+
+def test_deconv_dgrad_strided_sources():
+    N, H, W, cin, cout = 2, 8, 12, 32, 16  # high: [N,cin,H,W]; up: [N,cout,2H,2W]
+    du = bf(rnd(N, cout, 2 * H, 2 * W, seed=60))
+    w = bf(rnd(cin, cout, 2, 2, seed=61, scale=0.2))
+    x = torch.zeros(N, cin, H, W, dtype=torch.double, requires_grad=True)
+    F.conv_transpose2d(x, w.double(), stride=2).backward(du.double())
+    nt = ops.pick_n_tile(cin, 4 * cout, 1)
+    wp = ops.pack_weights(w.to(DEV), 3, 4, cin, nt, cout)  # [nt][tap=pq][k8][n][8]
+    # the kernel sees 4 sources (one per tap) and taps=1: K index = pq*cout + co, so repack tap-major into K
+    wp = wp.view(cin // nt, 4, cout // 8, nt, 8).reshape(cin // nt, 1, 4 * cout // 8, nt, 8).contiguous()
+    du_d = nhwc(du)
+    out = torch.empty(N, H, W, cin, dtype=torch.bfloat16, device=DEV)
+    ops.conv([du_d] * 4, N, H, W, wp, cin, nt, 1, out=out, strided=[(0, 0), (0, 1), (1, 0), (1, 1)])
+    close(nchw(out), x.grad, 6e-3, "deconv dgrad")
+
+
+def test_bn_train_forward_and_backward_kernels():
+    N, H, W, Cc = 2, 16, 24, 32
+    z = bf(rnd(N, Cc, H, W, seed=70) * 1.5 + 0.3)
+    gamma, beta = torch.rand(Cc) + 0.5, rnd(Cc, seed=71, scale=0.2)
+    rm, rv = rnd(Cc, seed=72, scale=0.1), torch.rand(Cc) + 0.5
+    dy = bf(rnd(N, Cc, H, W, seed=73))
+    zz = z.double().requires_grad_(True)
+    g64, b64 = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rm_ref, rv_ref = rm.double().clone(), rv.double().clone()
+    y_ref = F.relu(F.batch_norm(zz, rm_ref, rv_ref, g64, b64, training=True, momentum=0.1, eps=1e-5))
+    y_ref.backward(dy.double())
+    # statistics partials as the conv epilogue would emit them (two fake CTAs)
+    zd = nhwc(z)
+    half = z[:1].double(), z[1:].double()
+    partial = torch.stack([torch.stack([h.sum((0, 2, 3)), (h * h).sum((0, 2, 3))]) for h in half]).float().to(DEV)
+    count = N * H * W
+    mean, istd, scale, shift = (torch.empty(Cc, device=DEV) for _ in range(4))
+    rm_d, rv_d = rm.to(DEV), rv.to(DEV)
+    ops.bn_finalize(partial, 2, Cc, count, gamma.to(DEV), beta.to(DEV), rm_d, rv_d, 0.1, 1e-5, mean, istd, scale, shift)
+    close(rm_d.cpu(), rm_ref, 1e-5, "running_mean")
+    close(rv_d.cpu(), rv_ref, 1e-5, "running_var")
+    y = torch.empty_like(zd)
+    pooled = torch.empty(N, H // 2, W // 2, Cc, dtype=torch.bfloat16, device=DEV)
+    ops.bn_relu(zd, scale, shift, y, pooled)
+    close(nchw(y), y_ref.detach(), 6e-3, "bn relu")
+    assert torch.equal(nchw(pooled), F.max_pool2d(nchw(y), 2))
+    y2 = torch.empty_like(zd)
+    ops.bn_relu(zd, scale, shift, y2, None)
+    assert torch.equal(y2, y)
+    # backward: dyh = dy * (y > 0); sums = (sum dyh, sum dyh*xhat)
+    dyh = dy.double() * (y_ref.detach() > 0)
+    xhat = (z.double() - z.double().mean((0, 2, 3), keepdim=True)) / torch.sqrt(z.double().var((0, 2, 3), unbiased=False, keepdim=True) + 1e-5)
+    sums = torch.cat([dyh.sum((0, 2, 3)), (dyh * xhat).sum((0, 2, 3))]).float().to(DEV)
+    close(sums[:Cc].cpu(), b64.grad, 1e-4, "dbeta")
+    close(sums[Cc:].cpu(), g64.grad, 1e-4, "dgamma")
+    dz = torch.empty_like(zd)
+    ops.bn_bwd_apply(nhwc(dyh.float()), zd, mean, istd, gamma.to(DEV), sums, count, dz)
+    close(nchw(dz), zz.grad, 8e-3, "bn dz")
+
+
+def test_maxpool_backward_first_max_wins():
+    x = bf(F.relu(rnd(2, 16, 8, 12, seed=80)))  # many exact ties at 0
+    dp = bf(rnd(2, 16, 4, 6, seed=81))
+    xx = x.double().requires_grad_(True)
+    F.max_pool2d(xx, 2).backward(dp.double())
+    dx = torch.empty(2, 8, 12, 16, dtype=torch.bfloat16, device=DEV)
+    ops.maxpool_bwd(nhwc(x), nhwc(dp), dx)
+    assert torch.equal(nchw(dx).double(), xx.grad)
+
+
+@pytest.mark.parametrize("mode", ["upstream", "mse"])
+def test_head_backward(mode):
+    N, H, W = 2, 16, 24
+    x = bf(F.relu(rnd(N, 16, H, W, seed=90)))
+    hw, hb = rnd(4, 16, seed=91, scale=0.5), rnd(4, seed=92, scale=0.2)
+    mask = (torch.rand(N, 16, H, W, generator=torch.Generator().manual_seed(93)) >= 0.4)
+    xx = x.double().requires_grad_(True)
+    w64, b64 = hw.double().requires_grad_(True), hb.double().requires_grad_(True)
+    heat_ref = torch.sigmoid(F.conv2d(xx * mask.double() / 0.6, w64[:, :, None, None], b64))
+    heat = heat_ref.detach().float()
+    target = torch.rand(N, 4, H, W, generator=torch.Generator().manual_seed(94))
+    coef = 2.0 / (3 * heat.numel())
+    if mode == "mse":
+        (((heat_ref - target.double()) ** 2).sum() * coef / 2).backward()
+        dheat = None
+    else:
+        dheat = rnd(N, 4, H, W, seed=95)
+        heat_ref.backward(dheat.double())
+    g = ops.head_bwd_grid(N, H, W)
+    partial = torch.full((g, 4 * 16 + 4 + 1), float("nan"), device=DEV)
+    dx = torch.empty(N, H, W, 16, dtype=torch.bfloat16, device=DEV)
+    m8 = mask.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(DEV)
+    ops.head_bwd(heat.to(DEV), None if dheat is None else dheat.to(DEV), target.to(DEV) if mode == "mse" else None, coef, nhwc(x), m8, 1 / 0.6,
+                 hw.to(DEV), dx, partial)
+    close(nchw(dx), xx.grad, 6e-3, "head dx")
+    red = torch.empty(69, device=DEV)
+    ops.reduce_partials(partial, g, 69, 69, red)
+    close(red[:64].cpu().view(4, 16), w64.grad, 2e-3, "head dW")
+    close(red[64:68].cpu(), b64.grad, 2e-3, "head db")
+    if mode == "mse":
+        close(red[68:].cpu(), ((heat.double() - target.double()) ** 2).sum().reshape(1), 1e-4, "loss sum")
+
+
+def test_adamw_matches_reference_semantics(golden):
+    arr, meta = golden
+    h = meta["adamw_hyper"]
+    for j in range(2):
+        p = torch.from_numpy(arr[f"adamw_p0_{j}"]).reshape(-1).to(DEV)
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+        for s in range(3):
+            g = torch.from_numpy(arr[f"adamw_g{s}_{j}"]).reshape(-1).to(DEV)
+            ops.adamw(p, g, m, v, h["lr"], h["betas"][0], h["betas"][1], h["eps"], h["weight_decay"], s + 1)
+        assert np.allclose(p.cpu().numpy(), arr[f"adamw_p3_{j}"].reshape(-1), rtol=2e-6, atol=1e-7)
+
+
+def test_dropout_mask_rate_and_determinism():
+    m1 = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    m2 = torch.empty_like(m1)
+    ops.dropout_mask(m1, 0.4, 1234)
+    ops.dropout_mask(m2, 0.4, 1234)
+    assert torch.equal(m1, m2) and int(m1.max()) == 1
+    assert abs(float(m1.float().mean()) - 0.6) < 5e-3
+    ops.dropout_mask(m2, 0.4, 99)
+    assert not torch.equal(m1, m2)
+
+
+def test_bad_arguments_return_errors_not_crashes():
+    from unet_nested4tiny_objects_keypoints_b200._lib import UnppError
+    x = torch.zeros(1, 8, 8, 24, dtype=torch.bfloat16, device=DEV)  # 24 channels: unsupported
+    wp = torch.zeros(16 * 9 * 24, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(UnppError, match="16/32/64/128"):
+        ops.conv([x], 1, 8, 8, wp, 16, 16, 9, out=torch.empty(1, 8, 8, 16, dtype=torch.bfloat16, device=DEV))
+    with pytest.raises(UnppError):
+        ops.maxpool(torch.zeros(1, 7, 8, 16, dtype=torch.bfloat16, device=DEV), torch.zeros(1, 3, 4, 16, dtype=torch.bfloat16, device=DEV))

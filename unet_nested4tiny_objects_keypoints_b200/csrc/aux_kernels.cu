@@ -1,0 +1,192 @@
+// aux_kernels.cu — the memory-bound helpers around the tensor-core convolution:
+//   weight packing (fp32 OIHW state_dict -> bf16 UMMA B-operand layout),
+//   NCHW fp32 -> NHWC bf16 input conversion, 2x2 max-pool, and heat-map peak extraction.
+// All are plain coalesced/vectorised CUDA-core kernels (HBM-bound byte movers).
+#include "common.h"
+#include "../../include/unpp.h"
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// weight packing: one thread per packed 8-element K group (16 B store)
+__global__ void pack_weights_kernel(UnppPackArgs a) {
+  const int nt_count = a.n_total / a.n_tile;
+  const int k8_count = a.k_count / 8;
+  const long total = long(nt_count) * a.taps * k8_count * a.n_tile;
+  for (long idx = blockIdx.x * long(blockDim.x) + threadIdx.x; idx < total; idx += long(gridDim.x) * blockDim.x) {
+    long t = idx;
+    const int nl = int(t % a.n_tile);
+    t /= a.n_tile;
+    const int k8 = int(t % k8_count);
+    t /= k8_count;
+    const int tap = int(t % a.taps);
+    const int nt = int(t / a.taps);
+    const int n = nt * a.n_tile + nl;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int k = k8 * 8 + kk;
+      float w;
+      if (a.kind == 0) {  // B[n=co][tap][k=ci] = W[co][k_begin+ci][tap]
+        w = a.src[(size_t(n) * a.src_I + (a.k_begin + k)) * a.taps + tap];
+        if (a.scale) w *= a.scale[n];
+      } else if (a.kind == 1) {  // B[n=ci][tap][k=co] = W[co][n_begin+ci][taps-1-tap]
+        w = a.src[(size_t(a.k_begin + k) * a.src_I + (a.n_begin + n)) * a.taps + (a.taps - 1 - tap)];
+      } else if (a.kind == 2) {  // B[n=pq*Cout+co][0][k=ci] = Wd[ci][co][pq];  src [Cin][Cout][2][2]
+        const int cout = a.src_I, pq = n / cout, co = n % cout;
+        w = a.src[(size_t(a.k_begin + k) * cout + co) * 4 + pq];
+      } else {  // kind 3: B[n=ci][tap=pq][k=co] = Wd[ci][co][pq]
+        w = a.src[(size_t(a.n_begin + n) * a.src_I + (a.k_begin + k)) * 4 + tap];
+      }
+      v[kk] = __float2bfloat16_rn(w);
+    }
+    const size_t dst = (((size_t(nt) * a.taps + tap) * a.k8_total + a.k_dst8 + k8) * a.n_tile + nl) * 8;
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dst) + dst) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC bf16 with channel padding; one thread per pixel, reads coalesced per plane.
+template <int CPAD>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C, long HW) {
+  const long total = long(N) * HW;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const long n = i / HW, p = i % HW;
+    __align__(16) __nv_bfloat16 v[CPAD];
+#pragma unroll
+    for (int c = 0; c < CPAD; ++c) v[c] = __float2bfloat16_rn(c < C ? __ldg(x + (n * C + c) * HW + p) : 0.f);
+    uint4* o = reinterpret_cast<uint4*>(out + i * CPAD);
+#pragma unroll
+    for (int k = 0; k < CPAD / 8; ++k) o[k] = reinterpret_cast<const uint4*>(v)[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2x2 max pool on NHWC bf16, 8 channels (16 B) per thread.
+__device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
+  uint4 r;
+  __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&a);
+  __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+__global__ void maxpool2x2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int N, int H, int W, int C8) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long total = long(N) * Ho * Wo * C8;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    long t = i;
+    const int c = int(t % C8);
+    t /= C8;
+    const int xo = int(t % Wo);
+    t /= Wo;
+    const int yo = int(t % Ho);
+    const long n = t / Ho;
+    const uint4* r0 = x + ((n * H + 2 * yo) * W + 2 * xo) * C8 + c;
+    const uint4* r1 = r0 + long(W) * C8;
+    out[i] = max8(max8(__ldg(r0), __ldg(r0 + C8)), max8(__ldg(r1), __ldg(r1 + C8)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-plane arg-max with "first maximum in row-major order" tie-breaking
+// (np.where(h == h.max()) -> [0] of tools/misc/heatmap.py:173-176).  One CTA per plane; each
+// thread scans a strided set of float4s keeping (value, smallest index); warp-shuffle then
+// cross-warp reduction with the same total order: larger value wins, equal value -> smaller
+// index wins.  NaNs never win (comparison false), matching a max over finite sigmoid outputs.
+__device__ __forceinline__ void take(float& bv, int& bi, float v, int i) {
+  if (v > bv || (v == bv && i < bi)) bv = v, bi = i;
+}
+__global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ heat, int HW, int W, int32_t* __restrict__ xy,
+                                                     float* __restrict__ val) {
+  const float* h = heat + size_t(blockIdx.x) * HW;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  if ((HW & 3) == 0 && (reinterpret_cast<uintptr_t>(h) & 15) == 0) {
+    const float4* h4 = reinterpret_cast<const float4*>(h);
+    for (int i = threadIdx.x; i < HW / 4; i += blockDim.x) {
+      const float4 v = __ldg(h4 + i);
+      take(bv, bi, v.x, 4 * i), take(bv, bi, v.y, 4 * i + 1), take(bv, bi, v.z, 4 * i + 2), take(bv, bi, v.w, 4 * i + 3);
+    }
+  } else {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) take(bv, bi, __ldg(h + i), i);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    take(bv, bi, ov, oi);
+  }
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sv[warp] = bv, si[warp] = bi;
+  __syncthreads();
+  if (warp == 0) {
+    bv = lane < (blockDim.x >> 5) ? sv[lane] : -INFINITY;
+    bi = lane < (blockDim.x >> 5) ? si[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      take(bv, bi, ov, oi);
+    }
+    if (lane == 0) {
+      if (bi == 0x7fffffff) bi = 0;  // all-NaN / -inf plane: np.argmax would also report 0
+      xy[2 * blockIdx.x] = bi % W;      // x first (heatmap.py:178)
+      xy[2 * blockIdx.x + 1] = bi / W;  // then y
+      if (val) val[blockIdx.x] = bv;
+    }
+  }
+}
+
+inline int grid_for(long total, int block) {
+  long g = (total + block - 1) / block;
+  const long cap = long(unpp::num_sms()) * 16;
+  return int(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" int unpp_pack_weights(const UnppPackArgs* a, unpp_stream_t stream) {
+  if (!a || !a->src || !a->dst) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: null pointer");
+  if (a->kind < 0 || a->kind > 3) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: bad kind");
+  if (a->n_tile < 8 || a->n_total % a->n_tile || a->k_count % 8 || a->k_count < 8 || a->taps < 1)
+    return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: n_total %% n_tile, k_count %% 8 must be 0");
+  if (a->k_dst8 + a->k_count / 8 > a->k8_total) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: K range exceeds k8_total");
+  const long total = long(a->n_total) * a->taps * (a->k_count / 8);
+  pack_weights_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("pack_weights: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_nchw_to_nhwc(const float* x, void* out, int N, int C, int H, int W, int Cpad, unpp_stream_t stream) {
+  if (!x || !out || N < 1 || C < 1 || H < 1 || W < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "nchw_to_nhwc: bad argument");
+  if (Cpad != 16 || C > Cpad) return unpp::fail(UNPP_ERR_UNSUPPORTED, "nchw_to_nhwc: Cpad must be 16 and C <= 16");
+  const long total = long(N) * H * W;
+  nchw_to_nhwc_kernel<16><<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(out), N, C, long(H) * W);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("nchw_to_nhwc: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_maxpool2x2(const void* x, void* out, int N, int H, int W, int C, unpp_stream_t stream) {
+  if (!x || !out || N < 1 || H < 2 || W < 2 || (H & 1) || (W & 1) || C % 8) return unpp::fail(UNPP_ERR_BAD_ARG, "maxpool2x2: need even H, W and C %% 8 == 0");
+  const long total = long(N) * (H / 2) * (W / 2) * (C / 8);
+  maxpool2x2_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), N, H, W, C / 8);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("maxpool2x2: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_argmax_peaks(const float* heat, int planes, int H, int W, int32_t* xy, float* val, unpp_stream_t stream) {
+  if (!heat || !xy || planes < 0 || H < 1 || W < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "argmax_peaks: bad argument");
+  if (long(H) * W > 0x7ffffff0L) return unpp::fail(UNPP_ERR_UNSUPPORTED, "argmax_peaks: plane too large");
+  if (planes == 0) return UNPP_OK;
+  argmax_kernel<<<planes, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(heat, H * W, W, xy, val);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("argmax_peaks: launch");
+  return UNPP_OK;
+}

@@ -1,0 +1,46 @@
+// common.cu — error slot, device queries, version.
+#include "common.h"
+#include "../../include/unpp.h"
+
+namespace unpp {
+
+char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int fail_cuda(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  snprintf(last_error_buf(), 512, "%s: %s", what, cudaGetErrorString(e));
+  return UNPP_ERR_CUDA;
+}
+
+int num_sms() {
+  // Immutable per-device cache (indexed by device ordinal; written once with the same value).
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cache[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+
+}  // namespace unpp
+
+extern "C" const char* unpp_last_error(void) { return unpp::last_error_buf(); }
+extern "C" int unpp_version(void) { return 1; }
+extern "C" int unpp_num_sms(void) { return unpp::num_sms(); }
+extern "C" int unpp_sizeof_conv_args(void) { return int(sizeof(UnppConvArgs)); }
+extern "C" int unpp_sizeof_pack_args(void) { return int(sizeof(UnppPackArgs)); }
+extern "C" int unpp_sizeof_wgrad_args(void) { return int(sizeof(UnppWgradArgs)); }

@@ -1,0 +1,499 @@
+// conv_tc.cu — fused implicit-GEMM convolution for UNet++ on Blackwell tensor cores.
+//
+// One kernel serves every GEMM-shaped op of the network (3x3 conv of a virtual concat, the k2s2
+// transposed conv as a pointwise GEMM with a scatter epilogue, and all dgrads with flipped packed
+// weights):
+//
+//   * activations are NHWC bf16.  A persistent CTA walks 16-row x TW-column output tiles; for each
+//     tile and each <=64-channel chunk of each source tensor ONE TMA box load brings the
+//     (16+2) x (TW+2) halo tile into shared memory as pixel-major rows with the hardware swizzle
+//     that matches the chunk width (32/64/128 B).  The concat is never materialised: the K loop
+//     just walks the chunk table.
+//   * the nine filter taps are NOT nine copies: each tap is the same smem tile seen through a
+//     matrix descriptor whose start address is shifted by (r*P + s) pixels (P = TW+2) and whose
+//     stride-byte-offset is one tile row, so a 128-row MMA covers a 16x8 pixel patch
+//     (probe/umma_probe.cu m6/m7/m8 verify this addressing on B200).
+//   * tcgen05.mma (M=128, N=n_tile, K=16, bf16 -> fp32) accumulates in TMEM; two accumulator sets
+//     let the epilogue of tile i overlap the MMAs of tile i+1.
+//   * epilogue warps read TMEM (tcgen05.ld 32x32b), apply bias / ReLU / ReLU-mask / addend, the
+//     fused 1x1 head + sigmoid, and store NHWC bf16 (and NCHW fp32 heatmaps).
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
+#include "sm100.cuh"
+#include "common.h"
+#include "../../include/unpp.h"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int kMaxChunks = 8;
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;
+
+struct ConvTcParams {
+  CUtensorMap maps[UNPP_MAX_SRC];
+  int nchunk;
+  int ch_map[kMaxChunks];   // which tensor map
+  int ch_c0[kMaxChunks];    // first channel inside that source
+  int ch_span[kMaxChunks];  // bytes per pixel row of the chunk: 32 / 64 / 128
+  int ch_wk8[kMaxChunks];   // offset of the chunk in the packed-weight K axis, in 8-channel units
+  int N, H, W;
+  int TW, nsub, tiles_x, tiles_y, ntiles;
+  int taps, ncols, k8_total;
+  int stage_bytes, nstage, w_bytes, w_smem_bytes;
+  int tmem_cols;
+  const __nv_bfloat16* wpacked;
+  // epilogue
+  int mode, relu, cout;  // cout = channels of `out` (n_total for conv, n_total/4 for deconv)
+  const float* bias;
+  __nv_bfloat16* out;
+  const float* head_w;
+  const float* head_b;
+  float* heat;
+  float* logit;
+  int head_classes;
+  const uint8_t* drop_mask;
+  float drop_scale;
+  const __nv_bfloat16* addend;
+  const __nv_bfloat16* relu_mask_src;
+  float* stats_partial;
+  const __nv_bfloat16* stats_aux;
+  const float* aux_mean;
+  const float* aux_istd;
+};
+
+__device__ __forceinline__ uint32_t layout_type_of_span(int span) { return span == 128 ? 2u : span == 64 ? 4u : 6u; }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+// Sum over the 32 lanes of v[c] for c = lane >> 1, by recursive halving (16 shuffles instead of
+// 80): after the four exchange steps lane l holds channel (l >> 1) summed over 16 lanes; the last
+// step folds the two lanes that share a channel.
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+  float a8[8], a4[4], a2[2], a1;
+  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float mine = h4 ? v[8 + i] : v[i], other = h4 ? v[i] : v[8 + i];
+    a8[i] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float mine = h3 ? a8[4 + i] : a8[i], other = h3 ? a8[i] : a8[4 + i];
+    a4[i] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float mine = h2 ? a4[2 + i] : a4[i], other = h2 ? a4[i] : a4[2 + i];
+    a2[i] = mine + __shfl_xor_sync(0xffffffffu, other, 4);
+  }
+  {
+    const float mine = h1 ? a2[1] : a2[0], other = h1 ? a2[0] : a2[1];
+    a1 = mine + __shfl_xor_sync(0xffffffffu, other, 2);
+  }
+  return a1 + __shfl_xor_sync(0xffffffffu, a1, 1);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_acc_full[2], bar_acc_empty[2], bar_w;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_stats[4][2][256];  // per epilogue warp per-channel partial sums (training only)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntile_idx = blockIdx.y;  // which n_tile slice of the GEMM N axis this CTA owns
+  // the swizzle patterns of TMA and UMMA are functions of the absolute shared address: keep every
+  // stage 1024-aligned whatever the static shared footprint turns out to be
+  uint8_t* const w_smem = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  uint8_t* const stage0 = w_smem + p.w_smem_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nstage; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_acc_full[i], 1);
+      mbar_init(&bar_acc_empty[i], 4);
+    }
+    mbar_init(&bar_w, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < UNPP_MAX_SRC; ++i)
+      if (i < p.nchunk) tma_prefetch_desc(&p.maps[p.ch_map[i]]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int pad = p.taps == 9 ? 1 : 0;
+  const int P = p.TW + 2 * pad;    // tile pitch in pixels
+  const int rows = 16 + 2 * pad;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bar_w, p.w_bytes);
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpacked) + size_t(ntile_idx) * p.w_bytes;
+      for (int off = 0; off < p.w_bytes; off += 16384) {
+        int n = p.w_bytes - off < 16384 ? p.w_bytes - off : 16384;
+        bulk_load(w_smem + off, wsrc + off, n, &bar_w);
+      }
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+        for (int c = 0; c < p.nchunk; ++c, ++it) {
+          const int s = it % p.nstage, ph = (it / p.nstage) & 1;
+          mbar_wait(&bar_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&bar_full[s], rows * P * p.ch_span[c]);
+          tma_load_4d(&p.maps[p.ch_map[c]], &bar_full[s], stage0 + size_t(s) * p.stage_bytes, p.ch_c0[c], tx * p.TW - pad,
+                      ty * 16 - pad, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    mbar_wait(&bar_w, 0);
+    const uint32_t idesc = make_idesc_bf16(128, p.ncols);
+    const uint32_t w_addr = smem_u32(w_smem);
+    const uint32_t stage_addr0 = smem_u32(stage0);
+    int it = 0, tile_it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_it) {
+      const int b = tile_it & 1, aph = (tile_it >> 1) & 1;
+      mbar_wait(&bar_acc_empty[b], aph ^ 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + uint32_t(b * p.nsub * p.ncols);
+      for (int c = 0; c < p.nchunk; ++c, ++it) {
+        const int s = it % p.nstage, ph = (it / p.nstage) & 1;
+        mbar_wait(&bar_full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const int span = p.ch_span[c];
+          const int kslabs = span >> 5;
+          const uint64_t a0 = make_sdesc(stage_addr0 + uint32_t(s) * p.stage_bytes, 16, uint32_t(P * span), layout_type_of_span(span));
+          const uint32_t sub_step = uint32_t(8 * span) >> 4;  // next 8-pixel patch column, in 16 B units
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const int r = p.taps == 9 ? tap / 3 : 0, sft = p.taps == 9 ? tap % 3 : 0;
+            for (int ks = 0; ks < kslabs; ++ks) {
+              const uint64_t a_tap = a0 + uint64_t(uint32_t((r * P + sft) * span + ks * 32) >> 4);
+              const uint64_t bdesc =
+                  make_sdesc(w_addr + uint32_t(((tap * p.k8_total + p.ch_wk8[c] + 2 * ks) * p.ncols) * 16), uint32_t(p.ncols * 16), 128, 0);
+              const uint32_t accum = (c | tap | ks) ? 1u : 0u;
+              for (int j = 0; j < p.nsub; ++j) umma_bf16(acc + uint32_t(j * p.ncols), a_tap + uint64_t(j * sub_step), bdesc, idesc, accum);
+            }
+          }
+        }
+        __syncwarp();
+        if (elect_one()) umma_commit(&bar_empty[s]);
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&bar_acc_full[b]);
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;              // TMEM lane quadrant this warp may read
+    const int m = q * 32 + lane;         // accumulator row
+    const int pi = m >> 3, pj = m & 7;   // pixel inside the 16x8 patch
+    const int ew = warp - 2;
+    int tile_it = 0;
+    if (p.stats_partial)
+      for (int i = lane; i < 2 * 256; i += 32) (&s_stats[ew][0][0])[i] = 0.f;
+    __syncwarp();
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_it) {
+      const int b = tile_it & 1, aph = (tile_it >> 1) & 1;
+      const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+      mbar_wait(&bar_acc_full[b], aph);
+      tc_fence_after();
+      const int y = ty * 16 + pi;
+      for (int j = 0; j < p.nsub; ++j) {
+        const int x = tx * p.TW + j * 8 + pj;
+        const bool valid = (y < p.H) && (x < p.W);
+        for (int c0 = 0; c0 < p.ncols; c0 += 16) {
+          uint32_t raw[16];
+          tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t((b * p.nsub + j) * p.ncols + c0), raw);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(raw[k]);
+          const int gcol = ntile_idx * p.ncols + c0;  // GEMM column of v[0]
+          if (p.mode == UNPP_MODE_CONV) {
+            const size_t pix = (size_t(n) * p.H + y) * p.W + x;
+            if (p.bias) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) v[k] += __ldg(p.bias + gcol + k);
+            }
+            if (p.addend && valid) {
+              const uint4* ap = reinterpret_cast<const uint4*>(p.addend + pix * p.cout + gcol);
+              uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+              uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[2 * k] += bf16_lo(aw[k]), v[2 * k + 1] += bf16_hi(aw[k]);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
+            }
+            if (p.relu_mask_src && valid) {
+              const uint4* mp = reinterpret_cast<const uint4*>(p.relu_mask_src + pix * p.cout + gcol);
+              uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+              uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                if (!(bf16_lo(mw[k]) > 0.f)) v[2 * k] = 0.f;
+                if (!(bf16_hi(mw[k]) > 0.f)) v[2 * k + 1] = 0.f;
+              }
+            }
+            if (p.stats_partial) {
+              // Per-channel sums over this warp's 32 pixels (statistics of the bf16-rounded value
+              // that is stored; invalid pixels contribute 0).  Second statistic: v*v (BN batch
+              // variance) or v * xhat with xhat = (aux - mean) * istd (BN backward's dgamma).
+              float s1[16], s2[16];
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const float r = valid ? __bfloat162float(__float2bfloat16_rn(v[k])) : 0.f;
+                s1[k] = r, s2[k] = r * r;
+              }
+              if (p.stats_aux) {
+                uint32_t xw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (valid) {
+                  const uint4* xp = reinterpret_cast<const uint4*>(p.stats_aux + pix * p.cout + gcol);
+                  const uint4 x0 = __ldg(xp), x1 = __ldg(xp + 1);
+                  xw[0] = x0.x, xw[1] = x0.y, xw[2] = x0.z, xw[3] = x0.w, xw[4] = x1.x, xw[5] = x1.y, xw[6] = x1.z, xw[7] = x1.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  s2[2 * k] = s1[2 * k] * (bf16_lo(xw[k]) - __ldg(p.aux_mean + gcol + 2 * k)) * __ldg(p.aux_istd + gcol + 2 * k);
+                  s2[2 * k + 1] = s1[2 * k + 1] * (bf16_hi(xw[k]) - __ldg(p.aux_mean + gcol + 2 * k + 1)) * __ldg(p.aux_istd + gcol + 2 * k + 1);
+                }
+              }
+              const float r1 = warp_reduce16(s1, lane), r2 = warp_reduce16(s2, lane);
+              if ((lane & 1) == 0) {  // lane holds channel (lane >> 1); each warp owns its own slots
+                s_stats[ew][0][c0 + (lane >> 1)] += r1;
+                s_stats[ew][1][c0 + (lane >> 1)] += r2;
+              }
+            }
+            if (p.out && valid) {
+              uint4 o0, o1;
+              o0.x = pack_bf16x2(v[0], v[1]), o0.y = pack_bf16x2(v[2], v[3]), o0.z = pack_bf16x2(v[4], v[5]), o0.w = pack_bf16x2(v[6], v[7]);
+              o1.x = pack_bf16x2(v[8], v[9]), o1.y = pack_bf16x2(v[10], v[11]), o1.z = pack_bf16x2(v[12], v[13]),
+              o1.w = pack_bf16x2(v[14], v[15]);
+              uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.cout + gcol);
+              op[0] = o0;
+              op[1] = o1;
+            }
+            if (p.head_w && valid) {
+              if (p.drop_mask) {
+                const uint4 dm = __ldg(reinterpret_cast<const uint4*>(p.drop_mask + pix * 16));
+                const uint32_t dw[4] = {dm.x, dm.y, dm.z, dm.w};
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] = ((dw[k >> 2] >> (8 * (k & 3))) & 0xFF) ? v[k] * p.drop_scale : 0.f;
+              }
+              for (int cls = 0; cls < p.head_classes; ++cls) {
+                float acc = __ldg(p.head_b + cls);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) acc = fmaf(__ldg(p.head_w + cls * 16 + k), v[k], acc);
+                const size_t o = ((size_t(n) * p.head_classes + cls) * p.H + y) * p.W + x;
+                if (p.logit) p.logit[o] = acc;
+                p.heat[o] = 1.f / (1.f + __expf(-acc));
+              }
+            }
+          } else {  // UNPP_MODE_DECONV: column block -> (p,q) quadrant of the 2x upsampled output
+            const int pq = gcol / p.cout, co0 = gcol % p.cout;
+            if (valid) {
+              if (p.bias) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] += __ldg(p.bias + co0 + k);
+              }
+              const size_t opix = (size_t(n) * (2 * p.H) + (2 * y + (pq >> 1))) * (2 * p.W) + (2 * x + (pq & 1));
+              uint4 o0, o1;
+              o0.x = pack_bf16x2(v[0], v[1]), o0.y = pack_bf16x2(v[2], v[3]), o0.z = pack_bf16x2(v[4], v[5]), o0.w = pack_bf16x2(v[6], v[7]);
+              o1.x = pack_bf16x2(v[8], v[9]), o1.y = pack_bf16x2(v[10], v[11]), o1.z = pack_bf16x2(v[12], v[13]),
+              o1.w = pack_bf16x2(v[14], v[15]);
+              uint4* op = reinterpret_cast<uint4*>(p.out + opix * p.cout + co0);
+              op[0] = o0;
+              op[1] = o1;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (p.stats_partial) {
+    // partial layout [cta.x][2][n_total]; the four warp slots are summed in a fixed order so the
+    // result is deterministic for a given launch geometry.
+    for (int i = threadIdx.x; i < 2 * p.ncols; i += kThreads) {
+      const int st = i / p.ncols, ch = i % p.ncols;
+      const float t = ((s_stats[0][st][ch] + s_stats[1][st][ch]) + s_stats[2][st][ch]) + s_stats[3][st][ch];
+      p.stats_partial[(size_t(blockIdx.x) * 2 + st) * p.cout + ntile_idx * p.ncols + ch] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;  // immutable after first resolution
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct Plan {
+  int TW, nsub, nstage, stage_bytes, w_bytes, w_smem_bytes, tmem_cols, smem_total, grid_x, grid_y, tiles_x, tiles_y, ntiles;
+  int nchunk, k8_total;
+  int ch_map[kMaxChunks], ch_c0[kMaxChunks], ch_span[kMaxChunks], ch_wk8[kMaxChunks];
+};
+
+int make_plan(const UnppConvArgs* a, Plan* pl) {
+  if (!a || a->nsrc < 1 || a->nsrc > UNPP_MAX_SRC) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: nsrc out of range");
+  if (a->taps != 9 && a->taps != 1) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: taps must be 1 or 9");
+  if (a->N < 1 || a->H < 1 || a->W < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: empty pixel grid");
+  if (a->n_tile < 16 || a->n_tile > 256 || a->n_tile % 16 || a->n_total % a->n_tile)
+    return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: n_tile must be a multiple of 16 in [16,256] dividing n_total");
+  int nchunk = 0, k8 = 0, max_span = 0;
+  for (int i = 0; i < a->nsrc; ++i) {
+    const int C = a->src_C[i];
+    if (C != 16 && C != 32 && C != 64 && C != 128) return unpp::fail(UNPP_ERR_UNSUPPORTED, "conv_tc: source channels must be 16/32/64/128");
+    if (!a->src[i] || (reinterpret_cast<uintptr_t>(a->src[i]) & 15)) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: source pointer null or unaligned");
+    if (a->src_step[i] < 0 || a->src_step[i] > 2 || (a->src_step[i] == 2 && (a->taps != 1 || (a->src_oy[i] & ~1) || (a->src_ox[i] & ~1))))
+      return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: strided sources need taps=1 and offsets in {0,1}");
+    for (int c0 = 0; c0 < C; c0 += 64) {
+      if (nchunk >= kMaxChunks) return unpp::fail(UNPP_ERR_UNSUPPORTED, "conv_tc: too many K chunks");
+      const int w = C - c0 < 64 ? C - c0 : 64;
+      pl->ch_map[nchunk] = i, pl->ch_c0[nchunk] = c0, pl->ch_span[nchunk] = w * 2, pl->ch_wk8[nchunk] = k8;
+      k8 += w / 8;
+      if (w * 2 > max_span) max_span = w * 2;
+      ++nchunk;
+    }
+  }
+  pl->nchunk = nchunk, pl->k8_total = k8;
+  const int pad = a->taps == 9 ? 1 : 0;
+  pl->w_bytes = a->taps * k8 * a->n_tile * 16;
+  pl->w_smem_bytes = (pl->w_bytes + 1023) / 1024 * 1024;
+  const int smem_budget = 200 * 1024;
+  int TW = 64;
+  while (TW > 8 && (2 * (TW / 8) * a->n_tile > 512 || TW / 2 >= ((a->W + 7) / 8) * 8)) TW >>= 1;
+  for (;; TW >>= 1) {
+    pl->stage_bytes = ((16 + 2 * pad) * (TW + 2 * pad) * max_span + 1023) / 1024 * 1024;
+    pl->nstage = (smem_budget - pl->w_smem_bytes) / pl->stage_bytes;
+    if (pl->nstage >= 2 || TW == 8) break;
+  }
+  if (pl->nstage < 2) return unpp::fail(UNPP_ERR_UNSUPPORTED, "conv_tc: packed weights of one n_tile do not leave room for 2 stages; lower n_tile");
+  if (2 * (TW / 8) * a->n_tile > 512) return unpp::fail(UNPP_ERR_UNSUPPORTED, "conv_tc: n_tile too large for TMEM double buffering");
+  if (pl->nstage > kMaxStages) pl->nstage = kMaxStages;
+  pl->TW = TW, pl->nsub = TW / 8;
+  int cols = 2 * pl->nsub * a->n_tile, tc = 32;
+  while (tc < cols) tc <<= 1;
+  pl->tmem_cols = tc;
+  pl->smem_total = 1024 + pl->w_smem_bytes + pl->nstage * pl->stage_bytes;
+  pl->tiles_x = (a->W + TW - 1) / TW, pl->tiles_y = (a->H + 15) / 16;
+  pl->ntiles = pl->tiles_x * pl->tiles_y * a->N;
+  pl->grid_y = a->n_total / a->n_tile;
+  int gx = unpp::num_sms() / pl->grid_y;
+  if (gx < 1) gx = 1;
+  if (gx > pl->ntiles) gx = pl->ntiles;
+  pl->grid_x = gx;
+  return UNPP_OK;
+}
+
+}  // namespace
+
+extern "C" int unpp_conv_grid(const UnppConvArgs* a) {
+  Plan pl;
+  int rc = make_plan(a, &pl);
+  return rc ? rc : pl.grid_x;
+}
+
+extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  Plan pl;
+  if (int rc = make_plan(a, &pl)) return rc;
+  if (!a->wpacked) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: wpacked is null");
+  if (a->mode != UNPP_MODE_CONV && a->mode != UNPP_MODE_DECONV) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: bad mode");
+  if (a->mode == UNPP_MODE_DECONV && (a->taps != 1 || a->n_total % 4 || (a->n_total / 4) % 16 || !a->out))
+    return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: deconv mode needs taps=1, n_total=4*Cout with Cout%16==0 and an output");
+  if (a->head_w && (a->mode != UNPP_MODE_CONV || a->n_total != 16 || a->n_tile != 16 || !a->heat || !a->head_b || a->head_classes < 1 ||
+                    a->head_classes > 8))
+    return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: fused head needs conv mode, n_total=n_tile=16, heat/head_b and 1..8 classes");
+  if (!a->out && !a->head_w) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: nothing to write");
+  if (a->stats_partial && a->mode != UNPP_MODE_CONV) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: stats only in conv mode");
+  if (a->stats_aux && (!a->aux_mean || !a->aux_istd)) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: stats_aux needs aux_mean/aux_istd");
+
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return unpp::fail(UNPP_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled not available from the driver");
+
+  ConvTcParams p;
+  memset(&p, 0, sizeof p);
+  const int pad = a->taps == 9 ? 1 : 0;
+  for (int i = 0; i < a->nsrc; ++i) {
+    const cuuint64_t C = a->src_C[i];
+    const int box_c = C < 64 ? int(C) : 64;
+    const cuuint64_t st = a->src_step[i] == 2 ? 2 : 1, fullW = cuuint64_t(a->W) * st, fullH = cuuint64_t(a->H) * st;
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(a->src[i]);
+    if (st == 2) base += (size_t(a->src_oy[i]) * fullW + a->src_ox[i]) * C * 2;
+    cuuint64_t gd[4] = {C, cuuint64_t(a->W), cuuint64_t(a->H), cuuint64_t(a->N)};
+    cuuint64_t gs[3] = {C * 2 * st, fullW * C * 2 * st, fullH * fullW * C * 2};
+    cuuint32_t box[4] = {cuuint32_t(box_c), cuuint32_t(pl.TW + 2 * pad), cuuint32_t(16 + 2 * pad), 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUtensorMapSwizzle sw = box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = enc(&p.maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<uint8_t*>(base), gd, gs, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled failed (CUresult %d) for source %d", int(r), i);
+  }
+  p.nchunk = pl.nchunk;
+  for (int c = 0; c < pl.nchunk; ++c) p.ch_map[c] = pl.ch_map[c], p.ch_c0[c] = pl.ch_c0[c], p.ch_span[c] = pl.ch_span[c], p.ch_wk8[c] = pl.ch_wk8[c];
+  p.N = a->N, p.H = a->H, p.W = a->W;
+  p.TW = pl.TW, p.nsub = pl.nsub, p.tiles_x = pl.tiles_x, p.tiles_y = pl.tiles_y, p.ntiles = pl.ntiles;
+  p.taps = a->taps, p.ncols = a->n_tile, p.k8_total = pl.k8_total;
+  p.stage_bytes = pl.stage_bytes, p.nstage = pl.nstage, p.w_bytes = pl.w_bytes, p.w_smem_bytes = pl.w_smem_bytes;
+  p.tmem_cols = pl.tmem_cols;
+  p.wpacked = reinterpret_cast<const __nv_bfloat16*>(a->wpacked);
+  p.mode = a->mode, p.relu = a->relu;
+  p.cout = a->mode == UNPP_MODE_DECONV ? a->n_total / 4 : a->n_total;
+  p.bias = a->bias;
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  p.head_w = a->head_w, p.head_b = a->head_b, p.heat = a->heat, p.logit = a->logit, p.head_classes = a->head_classes;
+  p.drop_mask = a->drop_mask, p.drop_scale = a->drop_scale;
+  p.addend = reinterpret_cast<const __nv_bfloat16*>(a->addend);
+  p.relu_mask_src = reinterpret_cast<const __nv_bfloat16*>(a->relu_mask_src);
+  p.stats_partial = a->stats_partial;
+  p.stats_aux = reinterpret_cast<const __nv_bfloat16*>(a->stats_aux);
+  p.aux_mean = a->aux_mean, p.aux_istd = a->aux_istd;
+
+  static int smem_opted_in = 0;  // attribute is per-function, idempotent
+  if (!smem_opted_in) {
+    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024) != cudaSuccess)
+      return unpp::fail_cuda("conv_tc: cudaFuncSetAttribute");
+    smem_opted_in = 1;
+  }
+  conv_tc_kernel<<<dim3(pl.grid_x, pl.grid_y), kThreads, pl.smem_total, stream>>>(p);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("conv_tc: launch");
+  return UNPP_OK;
+}

@@ -1,0 +1,443 @@
+// train_kernels.cu — the memory-bound kernels of the training step that sit between the
+// tensor-core convolutions: BatchNorm batch statistics finalisation and apply (+ReLU, +2x2 pool),
+// BatchNorm / max-pool backward, the fused head backward (sigmoid' + 1x1 head dgrad/wgrad + dropout
+// mask, optionally with the MSE loss and its gradient computed in place), deterministic partial-sum
+// reductions, the flat-buffer AdamW of the reference, and the dropout keep-mask generator.
+// All are coalesced, vectorised (16 B per thread) CUDA-core kernels bounded by HBM bandwidth.
+#include "common.h"
+#include "../../include/unpp.h"
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace {
+
+inline int grid_for(long total, int block, int per_sm = 8) {
+  long g = (total + block - 1) / block;
+  const long cap = long(unpp::num_sms()) * per_sm;
+  return int(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf_lo(u.x), f[1] = bf_hi(u.x), f[2] = bf_lo(u.y), f[3] = bf_hi(u.y);
+  f[4] = bf_lo(u.z), f[5] = bf_hi(u.z), f[6] = bf_lo(u.w), f[7] = bf_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack2(f[0], f[1]), u.y = pack2(f[2], f[3]), u.z = pack2(f[4], f[5]), u.w = pack2(f[6], f[7]);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------
+// out[i] (+)= scale * sum_p partial[p * stride + i]  — fixed summation order => deterministic
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nparts, long stride, int n, float scale,
+                                       float* __restrict__ out, int accumulate) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += __ldg(partial + p * stride + i);
+    s *= scale;
+    out[i] = accumulate ? out[i] + s : s;
+  }
+}
+
+// wgrad partial [nparts][taps][cin_total][cout] -> dst[co*s_co + ci*s_ci + tap*s_tap] for ci < ci_count
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int taps, int cin_total, int cout, float* __restrict__ dst,
+                                    int ci_begin, int ci_count, long s_co, long s_ci, long s_tap, float scale) {
+  const int n = taps * ci_count * cout;
+  const long stride = long(taps) * cin_total * cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int co = i % cout, ci = (i / cout) % ci_count, tap = i / (cout * ci_count);
+    const float* p = partial + (long(tap) * cin_total + ci_begin + ci) * cout + co;
+    float s = 0.f;
+    for (int k = 0; k < nparts; ++k) s += __ldg(p + k * stride);
+    dst[co * s_co + ci * s_ci + tap * s_tap] = s * scale;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm2d training statistics (reference models/unet.py:133, nn.BatchNorm2d eps 1e-5 momentum 0.1):
+// reduce the per-CTA (sum, sum of squares) partials of the conv epilogue, produce mean / inverse std
+// and the fused affine (scale, shift), and update the running statistics (unbiased variance).
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nparts, int C, float count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float momentum, float eps, float* __restrict__ mean, float* __restrict__ istd, float* __restrict__ scale,
+                                   float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;  // 2*C*nparts values in total: double costs nothing here and removes the E[z^2]-m^2 cancellation
+  for (int p = 0; p < nparts; ++p) {
+    s1 += double(__ldg(partial + (size_t(p) * 2 + 0) * C + c));
+    s2 += double(__ldg(partial + (size_t(p) * 2 + 1) * C + c));
+  }
+  const double m = s1 / count;
+  double var = s2 / count - m * m;
+  if (var < 0.0) var = 0.0;
+  const float is = float(1.0 / sqrt(var + double(eps)));
+  mean[c] = float(m);
+  istd[c] = is;
+  const float sc = gamma[c] * is;
+  scale[c] = sc;
+  shift[c] = beta[c] - float(m) * sc;
+  if (running_mean) {
+    const double unbiased = count > 1.f ? var * double(count) / double(count - 1.f) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * float(m);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * float(unbiased);
+  }
+}
+
+// y = relu(z * scale[c] + shift[c]) (bf16 NHWC, 8 channels per thread); optional 2x2 max-pooled copy.
+__global__ void bn_relu_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift, uint4* __restrict__ y,
+                               long total, int C8) {
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int c0 = int(i % C8) * 8;
+    float f[8];
+    unpack8(__ldg(z + i), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], __ldg(scale + c0 + k), __ldg(shift + c0 + k)), 0.f);
+    y[i] = pack8(f);
+  }
+}
+__global__ void bn_relu_pool_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                                    uint4* __restrict__ y, uint4* __restrict__ pooled, int N, int H, int W, int C8) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long total = long(N) * Ho * Wo * C8;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    long t = i;
+    const int c8 = int(t % C8);
+    t /= C8;
+    const int xo = int(t % Wo);
+    t /= Wo;
+    const int yo = int(t % Ho);
+    const long n = t / Ho;
+    float sc[8], sh[8], mx[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sc[k] = __ldg(scale + c8 * 8 + k), sh[k] = __ldg(shift + c8 * 8 + k), mx[k] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long idx = ((n * H + 2 * yo + (q >> 1)) * W + 2 * xo + (q & 1)) * C8 + c8;
+      float f[8];
+      unpack8(__ldg(z + idx), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
+      const uint4 packed = pack8(f);
+      y[idx] = packed;
+      float r[8];
+      unpack8(packed, r);  // pool the bf16-rounded values, exactly what a pool over the stored y would see
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mx[k] = fmaxf(mx[k], r[k]);
+    }
+    pooled[i] = pack8(mx);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// MaxPool2d(2) backward: the gradient of each pooled element goes to the FIRST maximum of its 2x2
+// window in row-major order (what ATen's max_pool2d_with_indices records); the other three get 0.
+__global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dp, uint4* __restrict__ dx, int N, int H, int W, int C8) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long total = long(N) * Ho * Wo * C8;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    long t = i;
+    const int c8 = int(t % C8);
+    t /= C8;
+    const int xo = int(t % Wo);
+    t /= Wo;
+    const int yo = int(t % Ho);
+    const long n = t / Ho;
+    float v[4][8], g[8];
+    long idx[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      idx[q] = ((n * H + 2 * yo + (q >> 1)) * W + 2 * xo + (q & 1)) * C8 + c8;
+      unpack8(__ldg(x + idx[q]), v[q]);
+    }
+    unpack8(__ldg(dp + i), g);
+    float o[4][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int best = 0;
+      float bv = v[0][k];
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (v[q][k] > bv) bv = v[q][k], best = q;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q][k] = (q == best) ? g[k] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dx[idx[q]] = pack8(o[q]);
+  }
+}
+
+// BatchNorm backward, apply pass: dz = gamma*istd * (dyh - s1/M - xhat * s2/M), xhat = (z-mean)*istd,
+// with s1 = sum dyh (= dbeta), s2 = sum dyh*xhat (= dgamma) reduced beforehand (conv_tc epilogue stats).
+__global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dyh, const uint4* __restrict__ z, const float* __restrict__ mean,
+                                    const float* __restrict__ istd, const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count,
+                                    uint4* __restrict__ dz, long total, int C8) {
+  const int C = C8 * 8;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const int c0 = int(i % C8) * 8;
+    float g[8], zz[8], o[8];
+    unpack8(__ldg(dyh + i), g);
+    unpack8(__ldg(z + i), zz);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c0 + k;
+      const float is = __ldg(istd + c);
+      const float xh = (zz[k] - __ldg(mean + c)) * is;
+      o[k] = __ldg(gamma + c) * is * (g[k] - __ldg(sums + c) * inv_count - xh * __ldg(sums + C + c) * inv_count);
+    }
+    dz[i] = pack8(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Head backward.  Forward was heat = sigmoid(Wh . (x * mask * scale) + bh) with x = X_0k (bf16 NHWC,
+// 16 channels), reference models/unet.py:283-286.  Given either the upstream gradient dheat (fp32
+// NCHW) or — fused MSE mode — the target T (then dheat = coef * (p - T), loss += (p - T)^2), computes
+//   dlogit = dheat * p * (1 - p)
+//   dx[c]  = mask[c]*scale * sum_cls dlogit[cls] * Wh[cls][c]          (bf16 NHWC, to be masked by x>0 downstream)
+//   dWh[cls][c] += dlogit[cls] * x[c]*mask[c]*scale ;  dbh[cls] += dlogit[cls] ; loss partial
+// One thread per pixel; per-thread register accumulators, one shuffle+smem reduction per CTA at
+// the end, written to partial[blockIdx.x][NCLS*16 + NCLS + 1].
+template <int NCLS>
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ heat, const float* __restrict__ dheat, const float* __restrict__ target,
+                                                       float coef, const uint4* __restrict__ x, const uint4* __restrict__ mask, float drop_scale,
+                                                       const float* __restrict__ head_w, uint4* __restrict__ dx, float* __restrict__ partial,
+                                                       int N, long HW) {
+  constexpr int NACC = NCLS * 16 + NCLS + 1;
+  float acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+  float w[NCLS][16];
+#pragma unroll
+  for (int c = 0; c < NCLS; ++c)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w[c][k] = __ldg(head_w + c * 16 + k);
+  const long total = long(N) * HW;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+    const long n = i / HW, p = i % HW;
+    float dl[NCLS];
+#pragma unroll
+    for (int c = 0; c < NCLS; ++c) {
+      const long o = (n * NCLS + c) * HW + p;
+      const float pr = __ldg(heat + o);
+      float dh;
+      if (target) {
+        const float d = pr - __ldg(target + o);
+        acc[NACC - 1] += d * d;
+        dh = coef * d;
+      } else {
+        dh = __ldg(dheat + o);
+      }
+      dl[c] = dh * pr * (1.f - pr);
+      acc[NCLS * 16 + c] += dl[c];
+    }
+    float xv[16], keep[16];
+    unpack8(__ldg(x + 2 * i), *reinterpret_cast<float(*)[8]>(xv));
+    unpack8(__ldg(x + 2 * i + 1), *reinterpret_cast<float(*)[8]>(xv + 8));
+    if (mask) {
+      const uint4 m = __ldg(mask + i);
+      const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+      for (int k = 0; k < 16; ++k) keep[k] = ((mw[k >> 2] >> (8 * (k & 3))) & 0xFF) ? drop_scale : 0.f;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) keep[k] = 1.f;
+    }
+    float g[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float xd = xv[k] * keep[k];
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCLS; ++c) {
+        acc[c * 16 + k] = fmaf(dl[c], xd, acc[c * 16 + k]);
+        s = fmaf(dl[c], w[c][k], s);
+      }
+      g[k] = s * keep[k];
+    }
+    dx[2 * i] = pack8(*reinterpret_cast<float(*)[8]>(g));
+    dx[2 * i + 1] = pack8(*reinterpret_cast<float(*)[8]>(g + 8));
+  }
+  __shared__ float red[8][NACC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NACC; i += blockDim.x) {
+    float s = 0.f;
+    for (int wv = 0; wv < 8; ++wv) s += red[wv][i];
+    partial[size_t(blockIdx.x) * NACC + i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// The reference's AdamW (tools/optimizers/adamw.py:38-100), one pass over the flat parameter buffer:
+//   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p = p - step_size * m / (sqrt(v)+eps) - wd * p_old
+// (decay is NOT scaled by lr, and uses the pre-update p).  step_size is computed on the host in
+// double like the reference does in Python floats.
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n, float b1,
+                             float b2, float eps, float step_size, float wd, float grad_scale) {
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < n; i += long(gridDim.x) * blockDim.x) {
+    const float gr = g[i] * grad_scale;
+    const float mm = m[i] * b1 + (1.f - b1) * gr;
+    const float vv = v[i] * b2 + (1.f - b2) * gr * gr;
+    m[i] = mm, v[i] = vv;
+    const float denom = sqrtf(vv) + eps;
+    const float po = p[i];
+    float pn = po - step_size * (mm / denom);
+    if (wd != 0.f) pn -= po * wd;
+    p[i] = pn;
+  }
+}
+
+// Dropout keep-mask (nn.Dropout(p), models/unet.py:254): u8 1 = keep, counter-based hash RNG
+// (not torch's Philox stream: parity runs pass explicit masks; this serves throughput runs).
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16, x *= 0x7feb352du, x ^= x >> 15, x *= 0x846ca68bu, x ^= x >> 16;
+  return x;
+}
+__global__ void dropout_mask_kernel(uint4* __restrict__ out, long n16, uint32_t seed_lo, uint32_t seed_hi, uint32_t thresh16) {
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < n16; i += long(gridDim.x) * blockDim.x) {
+    uint32_t wds[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t packed = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t r = mix32(mix32(uint32_t(i) * 8u + q * 2 + h + seed_lo) ^ (uint32_t(i >> 29) + seed_hi));
+        packed |= ((r & 0xFFFF) >= thresh16 ? 1u : 0u) << (16 * h);
+        packed |= ((r >> 16) >= thresh16 ? 1u : 0u) << (16 * h + 8);
+      }
+      wds[q] = packed;
+    }
+    out[i] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+  }
+}
+
+}  // namespace
+
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int unpp_reduce_partials(const float* partial, int nparts, long stride, int n, float scale, float* out, int accumulate,
+                                    unpp_stream_t stream) {
+  if (!partial || !out || nparts < 1 || n < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "reduce_partials: bad argument");
+  reduce_partials_kernel<<<grid_for(n, 128), 128, 0, STREAM(stream)>>>(partial, nparts, stride, n, scale, out, accumulate);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("reduce_partials: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_wgrad_reduce(const float* partial, int nparts, int taps, int cin_total, int cout, float* dst, int ci_begin, int ci_count,
+                                 long s_co, long s_ci, long s_tap, float scale, unpp_stream_t stream) {
+  if (!partial || !dst || nparts < 1 || taps < 1 || ci_count < 1 || ci_begin < 0 || ci_begin + ci_count > cin_total || cout < 1)
+    return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad_reduce: bad argument");
+  const int n = taps * ci_count * cout;
+  wgrad_reduce_kernel<<<grid_for(n, 128), 128, 0, STREAM(stream)>>>(partial, nparts, taps, cin_total, cout, dst, ci_begin, ci_count, s_co, s_ci,
+                                                                   s_tap, scale);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("wgrad_reduce: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_bn_finalize(const float* partial, int nparts, int C, float count, const float* gamma, const float* beta, float* running_mean,
+                                float* running_var, float momentum, float eps, float* mean, float* istd, float* scale, float* shift,
+                                unpp_stream_t stream) {
+  if (!partial || !gamma || !beta || !mean || !istd || !scale || !shift || nparts < 1 || C < 1 || !(count >= 1.f))
+    return unpp::fail(UNPP_ERR_BAD_ARG, "bn_finalize: bad argument");
+  bn_finalize_kernel<<<(C + 63) / 64, 64, 0, STREAM(stream)>>>(partial, nparts, C, count, gamma, beta, running_mean, running_var, momentum, eps,
+                                                               mean, istd, scale, shift);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("bn_finalize: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_bn_relu(const void* z, const float* scale, const float* shift, void* y, void* pooled, int N, int H, int W, int C,
+                            unpp_stream_t stream) {
+  if (!z || !scale || !shift || !y || N < 1 || H < 1 || W < 1 || C % 8) return unpp::fail(UNPP_ERR_BAD_ARG, "bn_relu: bad argument");
+  if (pooled) {
+    if ((H & 1) || (W & 1)) return unpp::fail(UNPP_ERR_BAD_ARG, "bn_relu: pooling needs even H and W");
+    const long total = long(N) * (H / 2) * (W / 2) * (C / 8);
+    bn_relu_pool_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const uint4*>(z), scale, shift,
+                                                                          reinterpret_cast<uint4*>(y), reinterpret_cast<uint4*>(pooled), N, H, W,
+                                                                          C / 8);
+  } else {
+    const long total = long(N) * H * W * (C / 8);
+    bn_relu_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<uint4*>(y),
+                                                                     total, C / 8);
+  }
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("bn_relu: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_maxpool2x2_bwd(const void* x, const void* dpooled, void* dx, int N, int H, int W, int C, unpp_stream_t stream) {
+  if (!x || !dpooled || !dx || N < 1 || H < 2 || W < 2 || (H & 1) || (W & 1) || C % 8)
+    return unpp::fail(UNPP_ERR_BAD_ARG, "maxpool2x2_bwd: need even H, W and C %% 8 == 0");
+  const long total = long(N) * (H / 2) * (W / 2) * (C / 8);
+  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dpooled),
+                                                                       reinterpret_cast<uint4*>(dx), N, H, W, C / 8);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("maxpool2x2_bwd: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_bn_bwd_apply(const void* dyh, const void* z, const float* mean, const float* istd, const float* gamma, const float* sums,
+                                 float count, void* dz, int N, int H, int W, int C, unpp_stream_t stream) {
+  if (!dyh || !z || !mean || !istd || !gamma || !sums || !dz || N < 1 || H < 1 || W < 1 || C % 8 || !(count >= 1.f))
+    return unpp::fail(UNPP_ERR_BAD_ARG, "bn_bwd_apply: bad argument");
+  const long total = long(N) * H * W * (C / 8);
+  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const uint4*>(dyh), reinterpret_cast<const uint4*>(z), mean,
+                                                                        istd, gamma, sums, 1.f / count, reinterpret_cast<uint4*>(dz), total, C / 8);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("bn_bwd_apply: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_head_bwd_grid(int N, int H, int W) { return grid_for(long(N) * H * W, 256, 2); }
+
+extern "C" int unpp_head_bwd(const float* heat, const float* dheat, const float* target, float coef, const void* x, const uint8_t* drop_mask,
+                             float drop_scale, const float* head_w, int classes, void* dx, float* partial, int N, int H, int W,
+                             unpp_stream_t stream) {
+  if (!heat || (!dheat && !target) || !x || !head_w || !dx || !partial || N < 1 || H < 1 || W < 1)
+    return unpp::fail(UNPP_ERR_BAD_ARG, "head_bwd: bad argument");
+  const int grid = unpp_head_bwd_grid(N, H, W);
+  const long HW = long(H) * W;
+#define LAUNCH(NC)                                                                                                                        \
+  head_bwd_kernel<NC><<<grid, 256, 0, STREAM(stream)>>>(heat, dheat, target, coef, reinterpret_cast<const uint4*>(x),                      \
+                                                        reinterpret_cast<const uint4*>(drop_mask), drop_scale, head_w,                     \
+                                                        reinterpret_cast<uint4*>(dx), partial, N, HW)
+  switch (classes) {
+    case 1: LAUNCH(1); break;
+    case 2: LAUNCH(2); break;
+    case 3: LAUNCH(3); break;
+    case 4: LAUNCH(4); break;
+    default: return unpp::fail(UNPP_ERR_UNSUPPORTED, "head_bwd: 1..4 classes supported");
+  }
+#undef LAUNCH
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("head_bwd: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                          int step, float grad_scale, unpp_stream_t stream) {
+  if (!p || !g || !m || !v || n < 1 || step < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "adamw: bad argument");
+  const double bc1 = 1.0 - pow(double(beta1), step), bc2 = 1.0 - pow(double(beta2), step);
+  const float step_size = float(double(lr) * sqrt(bc2) / bc1);
+  adamw_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(p, g, m, v, n, beta1, beta2, eps, step_size, weight_decay, grad_scale);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("adamw: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_dropout_mask(uint8_t* mask, long n, float p_drop, uint64_t seed, unpp_stream_t stream) {
+  if (!mask || n < 16 || (n & 15) || !(p_drop >= 0.f) || !(p_drop < 1.f)) return unpp::fail(UNPP_ERR_BAD_ARG, "dropout_mask: n must be a positive multiple of 16, 0 <= p < 1");
+  const uint32_t thresh = uint32_t(double(p_drop) * 65536.0 + 0.5);
+  dropout_mask_kernel<<<grid_for(n / 16, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<uint4*>(mask), n / 16, uint32_t(seed), uint32_t(seed >> 32),
+                                                                         thresh);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("dropout_mask: launch");
+  return UNPP_OK;
+}

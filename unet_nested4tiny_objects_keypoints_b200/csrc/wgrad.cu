@@ -1,0 +1,266 @@
+// wgrad.cu — weight gradient of the 3x3 convs (and, with taps = 1 and a strided dZ view, of the
+// k2s2 transposed convs) as an implicit GEMM whose reduction dimension is the pixel grid:
+//
+//     dW[tap][ci][co] = sum_{n,y,x} X[n, y + r - 1, x + s - 1, ci] * dZ[n, y, x, co]
+//
+// Both operands are NHWC bf16 tiles brought in by TMA (zero-filled halo / out-of-image pixels, so
+// no masking anywhere).  A job = one <=64-channel chunk of one source tensor x one <=64-channel
+// slice of dZ; blockIdx.y enumerates the jobs, blockIdx.x strides over 8x32-pixel tiles.  Every
+// warp keeps its (tap, 16ci, 16co) accumulator fragments in registers across ALL the tiles of the
+// CTA (the output is tiny: 9*Cin*Cout), so HBM traffic is one read of X and dZ; the per-CTA result
+// goes to a partial buffer reduced in fixed order by unpp_wgrad_reduce (deterministic).
+//
+// Tensor-core path: warp-level mma (wmma m16n16k16 bf16 -> fp32).  The pixel dimension is K, so
+// the X tile [pixel][ci] is the column-major A operand and the dZ tile [pixel][co] the row-major
+// B operand — no transposes are materialised.
+#include "sm100.cuh"
+#include "common.h"
+#include "../../include/unpp.h"
+#include <mma.h>
+
+using namespace sm100;
+using namespace nvcuda;
+
+namespace {
+
+constexpr int kMaxJobs = 16;
+constexpr int TR = 8, TC = 32;  // tile rows / cols (pixels)
+constexpr int kThreads = 256;
+
+struct WgradParams {
+  CUtensorMap xmap[UNPP_MAX_SRC];
+  CUtensorMap zmap;
+  int njobs;
+  int job_map[kMaxJobs], job_c0[kMaxJobs], job_cs[kMaxJobs], job_cioff[kMaxJobs], job_co0[kMaxJobs], job_con[kMaxJobs];
+  int tiles_x, tiles_y, ntiles;
+  int pad, cin_total, cout;
+  int xstage_bytes, zstage_bytes;
+  float* partial;
+};
+
+template <int TAPS, int PPW>
+__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[2];
+  uint8_t* const smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int job = blockIdx.y;
+  const int cs = p.job_cs[job], con = p.job_con[job];
+  const int nco = con >> 4, npairs = (cs >> 4) * nco;
+  const int PX = TC + 2 * p.pad, PY = TR + 2 * p.pad;
+  const int stage_bytes = p.xstage_bytes + p.zstage_bytes;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_full[0], 1);
+    mbar_init(&bar_full[1], 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&p.xmap[p.job_map[job]]);
+    tma_prefetch_desc(&p.zmap);
+  }
+  __syncthreads();
+
+  auto issue = [&](int tile, int buf) {
+    const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+    uint8_t* xs = smem + size_t(buf) * stage_bytes;
+    uint8_t* zs = xs + p.xstage_bytes;
+    mbar_arrive_expect_tx(&bar_full[buf], uint32_t(PY * PX * cs * 2 + TR * TC * con * 2));
+    tma_load_4d(&p.xmap[p.job_map[job]], &bar_full[buf], xs, p.job_c0[job], tx * TC - p.pad, ty * TR - p.pad, n);
+    tma_load_4d(&p.zmap, &bar_full[buf], zs, p.job_co0[job], tx * TC, ty * TR, n);
+  };
+
+  // fragment ownership
+  int pair0, row0, row_step;
+  const int ppw_job = npairs >= 8 ? npairs / 8 : 1;  // <= PPW
+  if (npairs >= 8) {
+    pair0 = warp * ppw_job, row0 = 0, row_step = 1;
+  } else {
+    pair0 = warp % npairs, row0 = warp / npairs, row_step = 8 / npairs;
+  }
+
+  wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[PPW][TAPS];
+#pragma unroll
+  for (int j = 0; j < PPW; ++j)
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) wmma::fill_fragment(acc[j][t], 0.f);
+
+  if (threadIdx.x == 0 && int(blockIdx.x) < p.ntiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    if (threadIdx.x == 0 && tile + int(gridDim.x) < p.ntiles) issue(tile + gridDim.x, buf ^ 1);
+    mbar_wait(&bar_full[buf], (it >> 1) & 1);
+    const __nv_bfloat16* xs = reinterpret_cast<const __nv_bfloat16*>(smem + size_t(buf) * stage_bytes);
+    const __nv_bfloat16* zs = reinterpret_cast<const __nv_bfloat16*>(smem + size_t(buf) * stage_bytes + p.xstage_bytes);
+    for (int row = row0; row < TR; row += row_step) {
+#pragma unroll
+      for (int kk = 0; kk < TC / 16; ++kk) {
+        const int x0 = kk * 16;
+#pragma unroll
+        for (int j = 0; j < PPW; ++j) {
+          if (j >= ppw_job) break;
+          const int pair = pair0 + j, cb = pair / nco, ob = pair % nco;
+          wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fb;
+          wmma::load_matrix_sync(fb, zs + (row * TC + x0) * con + ob * 16, con);
+#pragma unroll
+          for (int t = 0; t < TAPS; ++t) {
+            const int r = TAPS == 9 ? t / 3 : 0, s = TAPS == 9 ? t % 3 : 0;
+            wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::col_major> fa;
+            wmma::load_matrix_sync(fa, xs + ((row + r) * PX + x0 + s) * cs + cb * 16, cs);
+            wmma::mma_sync(acc[j][t], fa, fb, acc[j][t]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with `buf` before it is refilled two iterations later
+  }
+
+  // stage the fragments in shared memory, then sum the warps that share a pair in a fixed order
+  float* stage_f = reinterpret_cast<float*>(smem);
+#pragma unroll
+  for (int j = 0; j < PPW; ++j)
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) wmma::store_matrix_sync(stage_f + ((warp * PPW + j) * TAPS + t) * 256, acc[j][t], 16, wmma::mem_row_major);
+  __syncthreads();
+  const int nout = TAPS * cs * con;
+  const int wpp = npairs >= 8 ? 1 : 8 / npairs;
+  for (int i = threadIdx.x; i < nout; i += kThreads) {
+    const int col = i % con, cil = (i / con) % cs, t = i / (con * cs);
+    const int pair = (cil >> 4) * nco + (col >> 4);
+    const int e = (cil & 15) * 16 + (col & 15);
+    float s = 0.f;
+    if (npairs >= 8) {
+      const int w = pair / ppw_job, j = pair % ppw_job;
+      s = stage_f[((w * PPW + j) * TAPS + t) * 256 + e];
+    } else {
+      for (int k = 0; k < wpp; ++k) s += stage_f[(((pair + k * npairs) * PPW) * TAPS + t) * 256 + e];
+    }
+    p.partial[((size_t(blockIdx.x) * TAPS + t) * p.cin_total + p.job_cioff[job] + cil) * p.cout + p.job_co0[job] + col] = s;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult r;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) != cudaSuccess || !q) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(q);
+  }
+  return fn;
+}
+
+struct Plan {
+  int njobs, ppw, pad, cin_total, tiles_x, tiles_y, ntiles, grid_x, xstage_bytes, zstage_bytes, smem_total;
+  int job_map[kMaxJobs], job_c0[kMaxJobs], job_cs[kMaxJobs], job_cioff[kMaxJobs], job_co0[kMaxJobs], job_con[kMaxJobs];
+};
+
+int make_plan(const UnppWgradArgs* a, Plan* pl) {
+  if (!a || a->nsrc < 1 || a->nsrc > UNPP_MAX_SRC) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: nsrc out of range");
+  if (a->taps != 9 && a->taps != 1) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: taps must be 1 or 9");
+  if (a->N < 1 || a->H < 1 || a->W < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: empty pixel grid");
+  if (a->cout != 16 && a->cout != 32 && a->cout != 64 && a->cout != 128) return unpp::fail(UNPP_ERR_UNSUPPORTED, "wgrad: cout must be 16/32/64/128");
+  if (a->dz_step != 1 && a->dz_step != 2) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: dz_step must be 1 or 2");
+  int nj = 0, ci_off = 0, max_cs = 0, max_con = 0, max_pairs = 0;
+  for (int i = 0; i < a->nsrc; ++i) {
+    const int C = a->src_C[i];
+    if (C != 16 && C != 32 && C != 64 && C != 128) return unpp::fail(UNPP_ERR_UNSUPPORTED, "wgrad: source channels must be 16/32/64/128");
+    if (!a->src[i] || (reinterpret_cast<uintptr_t>(a->src[i]) & 15)) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: source pointer null or unaligned");
+    for (int c0 = 0; c0 < C; c0 += 64) {
+      const int cs = C - c0 < 64 ? C - c0 : 64;
+      for (int co0 = 0; co0 < a->cout; co0 += 64) {
+        const int con = a->cout - co0 < 64 ? a->cout - co0 : 64;
+        if (nj >= kMaxJobs) return unpp::fail(UNPP_ERR_UNSUPPORTED, "wgrad: too many jobs");
+        pl->job_map[nj] = i, pl->job_c0[nj] = c0, pl->job_cs[nj] = cs, pl->job_cioff[nj] = ci_off + c0, pl->job_co0[nj] = co0, pl->job_con[nj] = con;
+        const int pairs = (cs / 16) * (con / 16);
+        if (pairs != 1 && pairs != 2 && pairs != 4 && pairs != 8 && pairs != 16)
+          return unpp::fail(UNPP_ERR_UNSUPPORTED, "wgrad: (chunk/16)*(cout slice/16) must be a power of two <= 16");
+        if (cs > max_cs) max_cs = cs;
+        if (con > max_con) max_con = con;
+        if (pairs > max_pairs) max_pairs = pairs;
+        ++nj;
+      }
+    }
+    ci_off += C;
+  }
+  pl->njobs = nj, pl->cin_total = ci_off;
+  pl->ppw = max_pairs > 8 ? 2 : 1;
+  pl->pad = a->taps == 9 ? 1 : 0;
+  const int PX = TC + 2 * pl->pad, PY = TR + 2 * pl->pad;
+  pl->xstage_bytes = (PY * PX * max_cs * 2 + 127) / 128 * 128;
+  pl->zstage_bytes = (TR * TC * max_con * 2 + 127) / 128 * 128;
+  const int pipe = 2 * (pl->xstage_bytes + pl->zstage_bytes);
+  const int staging = 8 * pl->ppw * a->taps * 256 * 4;
+  pl->smem_total = 128 + (pipe > staging ? pipe : staging);
+  pl->tiles_x = (a->W + TC - 1) / TC, pl->tiles_y = (a->H + TR - 1) / TR;
+  pl->ntiles = pl->tiles_x * pl->tiles_y * a->N;
+  int gx = unpp::num_sms() / nj;
+  if (gx < 1) gx = 1;
+  if (gx > pl->ntiles) gx = pl->ntiles;
+  pl->grid_x = gx;
+  return UNPP_OK;
+}
+
+template <int TAPS, int PPW>
+int launch(const WgradParams& p, const Plan& pl, cudaStream_t stream) {
+  if (cudaFuncSetAttribute(wgrad_kernel<TAPS, PPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
+    return unpp::fail_cuda("wgrad: cudaFuncSetAttribute");
+  wgrad_kernel<TAPS, PPW><<<dim3(pl.grid_x, pl.njobs), kThreads, pl.smem_total, stream>>>(p);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("wgrad: launch");
+  return UNPP_OK;
+}
+
+}  // namespace
+
+extern "C" int unpp_wgrad_grid(const UnppWgradArgs* a) {
+  Plan pl;
+  int rc = make_plan(a, &pl);
+  return rc ? rc : pl.grid_x;
+}
+
+extern "C" int unpp_wgrad(const UnppWgradArgs* a, unpp_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  Plan pl;
+  if (int rc = make_plan(a, &pl)) return rc;
+  if (!a->dz || !a->partial) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: dz / partial is null");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return unpp::fail(UNPP_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled not available from the driver");
+  WgradParams p;
+  memset(&p, 0, sizeof p);
+  const int PX = TC + 2 * pl.pad, PY = TR + 2 * pl.pad;
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < a->nsrc; ++i) {
+    const cuuint64_t C = a->src_C[i];
+    cuuint64_t gd[4] = {C, cuuint64_t(a->W), cuuint64_t(a->H), cuuint64_t(a->N)};
+    cuuint64_t gs[3] = {C * 2, cuuint64_t(a->W) * C * 2, cuuint64_t(a->H) * a->W * C * 2};
+    cuuint32_t box[4] = {cuuint32_t(C < 64 ? C : 64), cuuint32_t(PX), cuuint32_t(PY), 1};
+    CUresult r = enc(&p.xmap[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->src[i]), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled failed (CUresult %d) for source %d", int(r), i);
+  }
+  {
+    // dZ may be a stride-2 view of a [N, 2H, 2W, cout] tensor (transposed-conv weight gradient)
+    const cuuint64_t C = a->cout, st = a->dz_step, fullW = cuuint64_t(a->W) * st, fullH = cuuint64_t(a->H) * st;
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(a->dz) + (size_t(a->dz_oy) * fullW + a->dz_ox) * C * 2;
+    cuuint64_t gd[4] = {C, cuuint64_t(a->W), cuuint64_t(a->H), cuuint64_t(a->N)};
+    cuuint64_t gs[3] = {C * 2 * st, fullW * C * 2 * st, fullH * fullW * C * 2};
+    const int con = a->cout < 64 ? a->cout : 64;
+    cuuint32_t box[4] = {cuuint32_t(con), cuuint32_t(TC), cuuint32_t(TR), 1};
+    CUresult r = enc(&p.zmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<uint8_t*>(base), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled failed (CUresult %d) for dZ", int(r));
+  }
+  p.njobs = pl.njobs;
+  for (int j = 0; j < pl.njobs; ++j) {
+    p.job_map[j] = pl.job_map[j], p.job_c0[j] = pl.job_c0[j], p.job_cs[j] = pl.job_cs[j];
+    p.job_cioff[j] = pl.job_cioff[j], p.job_co0[j] = pl.job_co0[j], p.job_con[j] = pl.job_con[j];
+  }
+  p.tiles_x = pl.tiles_x, p.tiles_y = pl.tiles_y, p.ntiles = pl.ntiles;
+  p.pad = pl.pad, p.cin_total = pl.cin_total, p.cout = a->cout;
+  p.xstage_bytes = pl.xstage_bytes, p.zstage_bytes = pl.zstage_bytes;
+  p.partial = a->partial;
+  if (a->taps == 9) return pl.ppw == 2 ? launch<9, 2>(p, pl, stream) : launch<9, 1>(p, pl, stream);
+  return pl.ppw == 2 ? launch<1, 2>(p, pl, stream) : launch<1, 1>(p, pl, stream);
+}

@@ -1,0 +1,204 @@
+"""Host-side engine: drives libunpp.so (C ABI, include/unpp.h) for one UNet_Nested on one device.
+
+The reference executes ``UNet_Nested.forward`` (models/unet.py:255-300) as ~80 ATen/cuDNN launches
+on NCHW fp32 tensors.  Here the same DAG runs as 27 launches of hand-written sm_100a kernels on
+NHWC bf16 tensors with fp32 accumulation:
+
+  * every 3x3 conv (+bias / folded BatchNorm, + ReLU) is one ``unpp_conv_tc`` call whose K loop walks
+    the list of source tensors, so ``torch.cat`` (unet.py:199-201) is never materialised;
+  * ``ConvTranspose2d(k2,s2)`` (unet.py:187) is a pointwise tensor-core GEMM with a scatter epilogue;
+  * the 1x1 heads + sigmoid (unet.py:242-244,283-286) ride in the epilogue of the node's second conv;
+  * eval-mode BatchNorm (unet.py:133) is folded into the packed bf16 weights and the fp32 bias.
+
+PyTorch owns all device memory (activation arena, packed weights); this module only passes
+``data_ptr()``s and the current CUDA stream across the C ABI.  There is no fallback path.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .ops import MODE_CONV, MODE_DECONV, pick_n_tile
+
+ENCODER = ("conv00", "conv10", "conv20", "conv30")
+# name -> (high-resolution source node, low sources in concat order, level)   (unet.py:268-277)
+DECODER = {
+    "up_concat01": ("X10", ("X00",), 0),
+    "up_concat11": ("X20", ("X10",), 1),
+    "up_concat21": ("X30", ("X20",), 2),
+    "up_concat02": ("X11", ("X00", "X01"), 0),
+    "up_concat12": ("X21", ("X10", "X11"), 1),
+    "up_concat03": ("X12", ("X00", "X01", "X02"), 0),
+}
+DECODER_ORDER = ("up_concat01", "up_concat11", "up_concat21", "up_concat02", "up_concat12", "up_concat03")
+HEAD_OF = {"up_concat01": "final_1", "up_concat02": "final_2", "up_concat03": "final_3"}
+
+
+class Engine:
+    def __init__(self, model, device: torch.device):
+        if device.type != "cuda":
+            raise RuntimeError("the B200-native UNet_Nested engine needs a CUDA device")
+        if not model.is_deconv:
+            raise ValueError("is_deconv=False (bilinear upsample) is not implemented by the sm_100a engine yet")
+        if not model.is_batchnorm:
+            raise ValueError("is_batchnorm=False is not implemented by the sm_100a engine yet")
+        f = [int(c / model.feature_scale) for c in (32, 64, 128, 256)]
+        if f != [16, 32, 64, 128] or model.n_classes > 8 or model.in_channels > 16:
+            raise ValueError("the sm_100a engine supports feature_scale=2, n_classes<=8, in_channels<=16")
+        self.model = model
+        self.device = device
+        self.filters = f
+        ops.lib()  # fail now if libunpp.so is missing: there is no other execution path
+        self._packed_eval = None
+        self._packed_key = None
+        self._arena: Dict[Tuple, Dict[str, torch.Tensor]] = {}
+        self._keep: List = []
+
+    # ------------------------------------------------------------------------------ weights
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self.model.parameters()) + list(self.model.buffers()))
+
+    def _conv_seq(self, name: str, n: int):
+        m = self.model
+        for part in name.split("."):
+            m = getattr(m, part)
+        return getattr(m, "conv%d" % n)
+
+    def packed_eval(self):
+        """bf16 UMMA-layout weights with eval-mode BatchNorm folded in (unet.py:133), cached until a
+        parameter or buffer changes."""
+        key = self._param_key()
+        if self._packed_eval is not None and self._packed_key == key:
+            return self._packed_eval
+        P: Dict[str, Dict] = {}
+        with torch.no_grad():
+            for name in ENCODER:
+                for n in (1, 2):
+                    seq = self._conv_seq(name, n)
+                    conv, bn = seq[0], seq[1]
+                    scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
+                    bias = ((conv.bias - bn.running_mean) * scale + bn.bias).float().contiguous()
+                    P[f"{name}.c{n}"] = self._pack_fwd_conv(conv.weight, scale, bias)
+            for name in DECODER_ORDER:
+                up = getattr(self.model, name)
+                for n in (1, 2):
+                    conv = self._conv_seq(name + ".conv", n)[0]
+                    P[f"{name}.c{n}"] = self._pack_fwd_conv(conv.weight, None, conv.bias.detach().float().contiguous())
+                cin, cout = up.up.weight.shape[0], up.up.weight.shape[1]
+                nt = pick_n_tile(4 * cout, cin, 1, deconv=True)
+                P[f"{name}.up"] = dict(w=ops.pack_weights(up.up.weight.float(), 2, 1, 4 * cout, nt, cin), bias=up.up.bias.detach().float().contiguous(),
+                                       n_total=4 * cout, n_tile=nt, cout=cout)
+            for h in ("final_1", "final_2", "final_3"):
+                m = getattr(self.model, h)
+                P[h] = dict(w=m.weight.detach().float().reshape(m.weight.shape[0], -1).contiguous(), b=m.bias.detach().float().contiguous())
+        self._packed_eval, self._packed_key = P, key
+        return P
+
+    def _pack_fwd_conv(self, weight: torch.Tensor, scale, bias):
+        w = weight.detach().float()
+        cout, cin = w.shape[0], w.shape[1]
+        if cin % 16:  # first layer: 3 input channels live in a 16-channel zero-padded NHWC tensor
+            wp = torch.zeros(cout, 16 * ((cin + 15) // 16), 3, 3, dtype=torch.float32, device=w.device)
+            wp[:, :cin] = w
+            w, cin = wp, wp.shape[1]
+        nt = pick_n_tile(cout, cin, 9)
+        return dict(w=ops.pack_weights(w, 0, 9, cout, nt, cin, scale=scale), bias=bias, n_total=cout, n_tile=nt)
+
+    # ------------------------------------------------------------------------------ activations
+    def arena(self, B: int, H: int, W: int, kind: str) -> Dict[str, torch.Tensor]:
+        key = (B, H, W, kind)
+        a = self._arena.get(key)
+        if a is None:
+            f = self.filters
+            bf = dict(dtype=torch.bfloat16, device=self.device)
+            a = {"x16": torch.empty(B, H, W, 16, **bf)}
+            for lvl, (node, c) in enumerate(zip(ENCODER, f)):
+                h, w = H >> lvl, W >> lvl
+                a[f"{node}.a"] = torch.empty(B, h, w, c, **bf)
+                a[f"X{lvl}0"] = torch.empty(B, h, w, c, **bf)
+                if lvl < 3:
+                    a[f"P{lvl}0"] = torch.empty(B, h // 2, w // 2, c, **bf)
+            for name in DECODER_ORDER:
+                _, _, lvl = DECODER[name]
+                h, w, c = H >> lvl, W >> lvl, f[lvl]
+                tag = name[-2:]
+                a[f"U{tag}"] = torch.empty(B, h, w, c, **bf)
+                a[f"{name}.a"] = torch.empty(B, h, w, c, **bf)
+                a[f"X{tag}"] = torch.empty(B, h, w, c, **bf)
+            if len(self._arena) >= 4:
+                self._arena.pop(next(iter(self._arena)))
+            self._arena[key] = a
+        return a
+
+    # ------------------------------------------------------------------------------ forward
+    def _check_input(self, x: torch.Tensor):
+        if x.dtype != torch.float32:
+            raise ValueError("UNet_Nested expects float32 input (the reference runs fp32 NCHW)")
+        B, Cin, H, W = x.shape
+        if Cin != self.model.in_channels:
+            raise ValueError(f"expected {self.model.in_channels} input channels, got {Cin}")
+        if H % 8 or W % 8 or H < 8 or W < 8:
+            # the reference's torch.cat throws for sizes not divisible by 8 (no pad logic in unetUp, unet.py:198-202)
+            raise ValueError("UNet_Nested needs H and W divisible by 8")
+        if x.device != self.device:
+            raise RuntimeError("input is on a different device than the engine")
+        return B, H, W
+
+    def forward(self, x: torch.Tensor):
+        if self.model.training:
+            from .training import run_autograd
+            return run_autograd(self, x)
+        # eval mode (trainer/trainer.py:200-210 runs it under set_grad_enabled(False)): inference kernels, no graph
+        return self.forward_eval(x)
+
+    def forward_eval(self, x: torch.Tensor, heads: Sequence[int] = (0, 1, 2)):
+        """Inference forward (BN folded, dropout off).  Returns the three sigmoid heat maps
+        (fp32 NCHW) — ``None`` for heads not requested."""
+        B, H, W = self._check_input(x)
+        x = x.contiguous()
+        P = self.packed_eval()
+        A = self.arena(B, H, W, "eval")
+        ncls = self.model.n_classes
+        ops.nchw_to_nhwc16(x, A["x16"])
+        src = A["x16"]
+        for lvl, name in enumerate(ENCODER):
+            h, w = H >> lvl, W >> lvl
+            p1, p2 = P[f"{name}.c1"], P[f"{name}.c2"]
+            ops.conv([src], B, h, w, p1["w"], p1["n_total"], p1["n_tile"], 9, bias=p1["bias"], relu=True, out=A[f"{name}.a"])
+            ops.conv([A[f"{name}.a"]], B, h, w, p2["w"], p2["n_total"], p2["n_tile"], 9, bias=p2["bias"], relu=True, out=A[f"X{lvl}0"])
+            if lvl < 3:
+                ops.maxpool(A[f"X{lvl}0"], A[f"P{lvl}0"])
+                src = A[f"P{lvl}0"]
+        heats: List[Optional[torch.Tensor]] = [None, None, None]
+        for name in DECODER_ORDER:
+            high, lows, lvl = DECODER[name]
+            tag = name[-2:]
+            h, w = H >> lvl, W >> lvl
+            pu, p1, p2 = P[f"{name}.up"], P[f"{name}.c1"], P[f"{name}.c2"]
+            ops.conv([A[high]], B, h // 2, w // 2, pu["w"], pu["n_total"], pu["n_tile"], 1, bias=pu["bias"], mode=MODE_DECONV, out=A[f"U{tag}"])
+            ops.conv([A[f"U{tag}"]] + [A[l] for l in lows], B, h, w, p1["w"], p1["n_total"], p1["n_tile"], 9, bias=p1["bias"], relu=True,
+                      out=A[f"{name}.a"])
+            head = None
+            out = A[f"X{tag}"]
+            if name in HEAD_OF:
+                k = int(HEAD_OF[name][-1]) - 1
+                if k in heads:
+                    ph = P[HEAD_OF[name]]
+                    heats[k] = torch.empty(B, ncls, H, W, dtype=torch.float32, device=self.device)
+                    head = (ph["w"], ph["b"], heats[k], None, None, 1.0)
+                if name == "up_concat03":
+                    out = None  # X03 has no consumer besides its head
+                    if head is None:
+                        continue
+            ops.conv([A[f"{name}.a"]], B, h, w, p2["w"], p2["n_total"], p2["n_tile"], 9, bias=p2["bias"], relu=True, out=out, head=head)
+        return tuple(heats)
+
+    @torch.no_grad()
+    def predict_keypoints(self, x: torch.Tensor, head: int = 2):
+        if head not in (0, 1, 2):
+            raise ValueError("head must be 0, 1 or 2")
+        heats = self.forward_eval(x, heads=(head,))
+        xy, val = ops.argmax_peaks(heats[head])
+        return xy, val, heats

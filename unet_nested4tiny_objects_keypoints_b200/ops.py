@@ -1,0 +1,218 @@
+"""Thin tensor-level wrappers over the C ABI of libunpp.so (include/unpp.h).
+
+Every function takes CUDA torch tensors (PyTorch owns the memory), passes raw pointers and the
+current CUDA stream across the boundary, and raises ``UnppError`` on a non-zero return code.
+Nothing here computes anything in PyTorch: a missing library or a failing kernel is an exception,
+never a fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, PackArgs, WgradArgs, MODE_CONV, MODE_DECONV  # noqa: F401
+
+W_SMEM_BUDGET = 96 * 1024  # packed weights of one n_tile kept resident in shared memory
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def lib():
+    return _lib.load()
+
+
+def pick_n_tile(n_total: int, k_total: int, taps: int, deconv: bool = False) -> int:
+    """Largest multiple of 16 dividing n_total whose packed weights fit the shared-memory budget."""
+    best = 16
+    for nt in range(16, min(n_total, 256) + 1, 16):
+        if n_total % nt:
+            continue
+        if taps * (k_total // 8) * nt * 16 > W_SMEM_BUDGET:
+            continue
+        if deconv and nt > 64:
+            continue
+        best = nt
+    return best
+
+
+def pack_weights(src: torch.Tensor, kind: int, taps: int, n_total: int, n_tile: int, k_count: int, *, scale=None, n_begin: int = 0,
+                 k_begin: int = 0, dst: Optional[torch.Tensor] = None, k8_total: Optional[int] = None, k_dst8: int = 0) -> torch.Tensor:
+    """fp32 weights -> bf16 UMMA B-operand layout [n_total/n_tile][taps][k8_total][n_tile][8] (see unpp.h)."""
+    src = src.detach()
+    if not src.is_contiguous():
+        src = src.contiguous()
+    assert src.dtype == torch.float32 and src.is_cuda
+    k8_total = k_count // 8 if k8_total is None else k8_total
+    if dst is None:
+        dst = torch.zeros(n_total * taps * k8_total * 8, dtype=torch.bfloat16, device=src.device)
+    a = PackArgs()
+    a.src, a.dst, a.scale = src.data_ptr(), dst.data_ptr(), _ptr(scale)
+    a.kind, a.src_O, a.src_I, a.taps = kind, src.shape[0], src.shape[1], taps
+    a.n_total, a.n_tile, a.n_begin = n_total, n_tile, n_begin
+    a.k_begin, a.k_count, a.k8_total, a.k_dst8 = k_begin, k_count, k8_total, k_dst8
+    _lib.check(lib().unpp_pack_weights(C.byref(a), _stream()), "unpp_pack_weights")
+    return dst
+
+
+def _conv_args(srcs, N, H, W, n_total, n_tile, taps, strided=None) -> ConvArgs:
+    a = ConvArgs()
+    a.N, a.H, a.W, a.nsrc = N, H, W, len(srcs)
+    for i, s in enumerate(srcs):
+        if isinstance(s, torch.Tensor):
+            a.src[i] = s.data_ptr()
+            a.src_C[i] = s.shape[-1]
+        else:  # geometry-only query: channel count
+            a.src[i] = 16
+            a.src_C[i] = int(s)
+        if strided is not None:
+            a.src_step[i], a.src_oy[i], a.src_ox[i] = 2, strided[i][0], strided[i][1]
+    a.taps, a.n_total, a.n_tile = taps, n_total, n_tile
+    return a
+
+
+def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Tensor, n_total: int, n_tile: int, taps: int, *, bias=None,
+         relu=False, mode=MODE_CONV, out=None, head=None, addend=None, relu_mask_src=None, stats_partial=None, stats_aux=None, aux_mean=None,
+         aux_istd=None, strided=None) -> None:
+    """One unpp_conv_tc launch.  ``srcs``: NHWC bf16 tensors (virtual concat along K).
+    ``head`` = (w fp32 [cls,16], b fp32 [cls], heat fp32 NCHW, logit|None, drop_mask u8 NHWC|None, drop_scale).
+    ``strided`` = [(oy, ox), ...]: every source is a [N,2H,2W,C] tensor read at (2y+oy, 2x+ox)."""
+    a = _conv_args(srcs, N, H, W, n_total, n_tile, taps, strided)
+    a.wpacked, a.bias = wpacked.data_ptr(), _ptr(bias)
+    a.mode, a.relu = mode, int(relu)
+    a.out = _ptr(out)
+    if head is not None:
+        hw, hb, heat, logit, dmask, dscale = head
+        a.head_w, a.head_b, a.heat, a.logit = hw.data_ptr(), hb.data_ptr(), heat.data_ptr(), _ptr(logit)
+        a.head_classes = hw.shape[0]
+        a.drop_mask, a.drop_scale = _ptr(dmask), float(dscale)
+    a.addend, a.relu_mask_src = _ptr(addend), _ptr(relu_mask_src)
+    a.stats_partial, a.stats_aux, a.aux_mean, a.aux_istd = _ptr(stats_partial), _ptr(stats_aux), _ptr(aux_mean), _ptr(aux_istd)
+    _lib.check(lib().unpp_conv_tc(C.byref(a), _stream()), "unpp_conv_tc")
+
+
+def conv_grid(srcs_C: Sequence[int], N: int, H: int, W: int, n_total: int, n_tile: int, taps: int) -> int:
+    a = _conv_args(list(srcs_C), N, H, W, n_total, n_tile, taps)
+    g = lib().unpp_conv_grid(C.byref(a))
+    if g < 0:
+        _lib.check(g, "unpp_conv_grid")
+    return g
+
+
+def nchw_to_nhwc16(x: torch.Tensor, out: torch.Tensor) -> None:
+    B, Cin, H, W = x.shape
+    _lib.check(lib().unpp_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, Cin, H, W, 16, _stream()), "unpp_nchw_to_nhwc")
+
+
+def maxpool(x: torch.Tensor, out: torch.Tensor) -> None:
+    B, H, W, Cc = x.shape
+    _lib.check(lib().unpp_maxpool2x2(x.data_ptr(), out.data_ptr(), B, H, W, Cc, _stream()), "unpp_maxpool2x2")
+
+
+def argmax_peaks(heat: torch.Tensor):
+    """fp32 [B,C,H,W] -> (xy int32 [B,C,2] as [x,y], peak fp32 [B,C]); reference tools/misc/heatmap.py:173-178."""
+    if heat.dtype != torch.float32 or not heat.is_cuda or heat.dim() != 4:
+        raise ValueError("argmax_peaks expects an fp32 CUDA tensor [B,C,H,W]")
+    heat = heat.contiguous()
+    B, Cc, H, W = heat.shape
+    xy = torch.empty(B, Cc, 2, dtype=torch.int32, device=heat.device)
+    val = torch.empty(B, Cc, dtype=torch.float32, device=heat.device)
+    _lib.check(lib().unpp_argmax_peaks(heat.data_ptr(), B * Cc, H, W, xy.data_ptr(), val.data_ptr(), _stream()), "unpp_argmax_peaks")
+    return xy, val
+
+
+# ---------------------------------------------------------------------------------------------- training
+def _wgrad_args(srcs, N, H, W, dz, cout, taps, dz_view=None) -> WgradArgs:
+    a = WgradArgs()
+    a.N, a.H, a.W, a.nsrc = N, H, W, len(srcs)
+    for i, s in enumerate(srcs):
+        if isinstance(s, torch.Tensor):
+            a.src[i], a.src_C[i] = s.data_ptr(), s.shape[-1]
+        else:
+            a.src[i], a.src_C[i] = 16, int(s)
+    a.dz = 16 if dz is None else dz.data_ptr()
+    a.cout, a.taps = cout, taps
+    if dz_view is None:
+        a.dz_step, a.dz_oy, a.dz_ox = 1, 0, 0
+    else:
+        a.dz_step, a.dz_oy, a.dz_ox = 2, dz_view[0], dz_view[1]
+    return a
+
+
+def wgrad_grid(srcs_C: Sequence[int], N: int, H: int, W: int, cout: int, taps: int) -> int:
+    a = _wgrad_args(list(srcs_C), N, H, W, None, cout, taps)
+    g = lib().unpp_wgrad_grid(C.byref(a))
+    if g < 0:
+        _lib.check(g, "unpp_wgrad_grid")
+    return g
+
+
+def wgrad(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, dz: torch.Tensor, cout: int, taps: int, partial: torch.Tensor, dz_view=None) -> None:
+    a = _wgrad_args(srcs, N, H, W, dz, cout, taps, dz_view)
+    a.partial = partial.data_ptr()
+    _lib.check(lib().unpp_wgrad(C.byref(a), _stream()), "unpp_wgrad")
+
+
+def wgrad_reduce(partial: torch.Tensor, nparts: int, taps: int, cin_total: int, cout: int, dst: torch.Tensor, ci_begin: int, ci_count: int,
+                 s_co: int, s_ci: int, s_tap: int, scale: float = 1.0, dst_offset: int = 0) -> None:
+    _lib.check(lib().unpp_wgrad_reduce(partial.data_ptr(), nparts, taps, cin_total, cout, dst.data_ptr() + 4 * dst_offset, ci_begin, ci_count,
+                                       s_co, s_ci, s_tap, scale, _stream()), "unpp_wgrad_reduce")
+
+
+def reduce_partials(partial: torch.Tensor, nparts: int, stride: int, n: int, out: torch.Tensor, scale: float = 1.0, accumulate: bool = False,
+                    partial_offset: int = 0, out_offset: int = 0) -> None:
+    _lib.check(lib().unpp_reduce_partials(partial.data_ptr() + 4 * partial_offset, nparts, stride, n, scale, out.data_ptr() + 4 * out_offset,
+                                          int(accumulate), _stream()), "unpp_reduce_partials")
+
+
+def bn_finalize(partial, nparts, Cc, count, gamma, beta, running_mean, running_var, momentum, eps, mean, istd, scale, shift) -> None:
+    _lib.check(lib().unpp_bn_finalize(partial.data_ptr(), nparts, Cc, float(count), gamma.data_ptr(), beta.data_ptr(), _ptr(running_mean),
+                                      _ptr(running_var), float(momentum), float(eps), mean.data_ptr(), istd.data_ptr(), scale.data_ptr(),
+                                      shift.data_ptr(), _stream()), "unpp_bn_finalize")
+
+
+def bn_relu(z, scale, shift, y, pooled=None) -> None:
+    N, H, W, Cc = z.shape
+    _lib.check(lib().unpp_bn_relu(z.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), _ptr(pooled), N, H, W, Cc, _stream()), "unpp_bn_relu")
+
+
+def maxpool_bwd(x, dpooled, dx) -> None:
+    N, H, W, Cc = x.shape
+    _lib.check(lib().unpp_maxpool2x2_bwd(x.data_ptr(), dpooled.data_ptr(), dx.data_ptr(), N, H, W, Cc, _stream()), "unpp_maxpool2x2_bwd")
+
+
+def bn_bwd_apply(dyh, z, mean, istd, gamma, sums, count, dz) -> None:
+    N, H, W, Cc = z.shape
+    _lib.check(lib().unpp_bn_bwd_apply(dyh.data_ptr(), z.data_ptr(), mean.data_ptr(), istd.data_ptr(), gamma.data_ptr(), sums.data_ptr(),
+                                       float(count), dz.data_ptr(), N, H, W, Cc, _stream()), "unpp_bn_bwd_apply")
+
+
+def head_bwd_grid(N: int, H: int, W: int) -> int:
+    return lib().unpp_head_bwd_grid(N, H, W)
+
+
+def head_bwd(heat, dheat, target, coef, x, drop_mask, drop_scale, head_w, dx, partial) -> None:
+    N, ncls, H, W = heat.shape
+    _lib.check(lib().unpp_head_bwd(heat.data_ptr(), _ptr(dheat), _ptr(target), float(coef), x.data_ptr(), _ptr(drop_mask), float(drop_scale),
+                                   head_w.data_ptr(), ncls, dx.data_ptr(), partial.data_ptr(), N, H, W, _stream()), "unpp_head_bwd")
+
+
+def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0) -> None:
+    """tools/optimizers/adamw.py:38-100 on flat fp32 buffers (in place)."""
+    for t in (p, g, m, v):
+        assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous() and t.numel() == p.numel()
+    _lib.check(lib().unpp_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+                                float(weight_decay), int(step), float(grad_scale), _stream()), "unpp_adamw")
+
+
+def dropout_mask(mask: torch.Tensor, p_drop: float, seed: int) -> None:
+    assert mask.dtype == torch.uint8 and mask.is_cuda and mask.is_contiguous()
+    _lib.check(lib().unpp_dropout_mask(mask.data_ptr(), mask.numel(), float(p_drop), int(seed) & (2**64 - 1), _stream()), "unpp_dropout_mask")
