@@ -165,7 +165,8 @@ int unpp_bn_bwd_apply(const void* dyh, const void* z, const float* mean, const f
                       float count, void* dz, int N, int H, int W, int C, unpp_stream_t stream);
 /* Head backward (sigmoid' + 1x1 conv dgrad/wgrad + dropout mask).  Exactly one of dheat (upstream
  * gradient, fp32 NCHW) and target (fused MSE: dheat = coef*(heat-target), loss partial = sum (heat-target)^2)
- * is non-NULL.  partial: fp32 [unpp_head_bwd_grid()][classes*16 + classes + 1] = dW, db, loss. */
+ * is non-NULL.  dx is already multiplied by the ReLU mask [x > 0] of the conv that produced x.
+ * partial: fp32 [unpp_head_bwd_grid()][classes*16 + classes + 1 + 16] = dW, db, loss, per-channel sum of dx. */
 int unpp_head_bwd(const float* heat, const float* dheat, const float* target, float coef, const void* x, const uint8_t* drop_mask,
                   float drop_scale, const float* head_w, int classes, void* dx, float* partial, int N, int H, int W,
                   unpp_stream_t stream);

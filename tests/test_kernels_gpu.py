@@ -298,7 +298,7 @@ def test_maxpool_backward_first_max_wins():
 @pytest.mark.parametrize("mode", ["upstream", "mse"])
 def test_head_backward(mode):
     N, H, W = 2, 16, 24
-    x = bf(F.relu(rnd(N, 16, H, W, seed=90)))
+    x = bf(F.relu(rnd(N, 16, H, W, seed=90)))  # output of a ReLU conv: the kernel also applies that ReLU's mask
     hw, hb = rnd(4, 16, seed=91, scale=0.5), rnd(4, seed=92, scale=0.2)
     mask = (torch.rand(N, 16, H, W, generator=torch.Generator().manual_seed(93)) >= 0.4)
     xx = x.double().requires_grad_(True)
@@ -314,18 +314,20 @@ def test_head_backward(mode):
         dheat = rnd(N, 4, H, W, seed=95)
         heat_ref.backward(dheat.double())
     g = ops.head_bwd_grid(N, H, W)
-    partial = torch.full((g, 4 * 16 + 4 + 1), float("nan"), device=DEV)
+    partial = torch.full((g, 4 * 16 + 4 + 1 + 16), float("nan"), device=DEV)
     dx = torch.empty(N, H, W, 16, dtype=torch.bfloat16, device=DEV)
     m8 = mask.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(DEV)
     ops.head_bwd(heat.to(DEV), None if dheat is None else dheat.to(DEV), target.to(DEV) if mode == "mse" else None, coef, nhwc(x), m8, 1 / 0.6,
                  hw.to(DEV), dx, partial)
-    close(nchw(dx), xx.grad, 6e-3, "head dx")
-    red = torch.empty(69, device=DEV)
-    ops.reduce_partials(partial, g, 69, 69, red)
+    dx_ref = xx.grad * (x > 0)
+    close(nchw(dx), dx_ref, 6e-3, "head dx")
+    red = torch.empty(85, device=DEV)
+    ops.reduce_partials(partial, g, 85, 85, red)
+    close(red[69:].cpu(), nchw(dx).double().sum((0, 2, 3)), 1e-4, "dx channel sums")
     close(red[:64].cpu().view(4, 16), w64.grad, 2e-3, "head dW")
     close(red[64:68].cpu(), b64.grad, 2e-3, "head db")
     if mode == "mse":
-        close(red[68:].cpu(), ((heat.double() - target.double()) ** 2).sum().reshape(1), 1e-4, "loss sum")
+        close(red[68:69].cpu(), ((heat.double() - target.double()) ** 2).sum().reshape(1), 1e-4, "loss sum")
 
 
 def test_adamw_matches_reference_semantics(golden):

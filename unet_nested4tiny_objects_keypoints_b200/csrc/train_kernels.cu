@@ -200,16 +200,17 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dyh, const uint4* 
 // 16 channels), reference models/unet.py:283-286.  Given either the upstream gradient dheat (fp32
 // NCHW) or — fused MSE mode — the target T (then dheat = coef * (p - T), loss += (p - T)^2), computes
 //   dlogit = dheat * p * (1 - p)
-//   dx[c]  = mask[c]*scale * sum_cls dlogit[cls] * Wh[cls][c]          (bf16 NHWC, to be masked by x>0 downstream)
+//   dx[c]  = [x[c] > 0] * mask[c]*scale * sum_cls dlogit[cls] * Wh[cls][c]   (bf16 NHWC; x = relu(.) so the ReLU mask of the
+//            producing conv is applied here) ;  dxsum[c] += dx[c]  (bias gradient of that conv when the head is its only consumer)
 //   dWh[cls][c] += dlogit[cls] * x[c]*mask[c]*scale ;  dbh[cls] += dlogit[cls] ; loss partial
 // One thread per pixel; per-thread register accumulators, one shuffle+smem reduction per CTA at
-// the end, written to partial[blockIdx.x][NCLS*16 + NCLS + 1].
+// the end, written to partial[blockIdx.x][NCLS*16 + NCLS + 1 + 16] = dW, db, loss, dxsum.
 template <int NCLS>
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ heat, const float* __restrict__ dheat, const float* __restrict__ target,
                                                        float coef, const uint4* __restrict__ x, const uint4* __restrict__ mask, float drop_scale,
                                                        const float* __restrict__ head_w, uint4* __restrict__ dx, float* __restrict__ partial,
                                                        int N, long HW) {
-  constexpr int NACC = NCLS * 16 + NCLS + 1;
+  constexpr int NACC = NCLS * 16 + NCLS + 1 + 16, LOSS = NCLS * 16 + NCLS;
   float acc[NACC];
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       float dh;
       if (target) {
         const float d = pr - __ldg(target + o);
-        acc[NACC - 1] += d * d;
+        acc[LOSS] += d * d;
         dh = coef * d;
       } else {
         dh = __ldg(dheat + o);
@@ -259,7 +260,9 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
         acc[c * 16 + k] = fmaf(dl[c], xd, acc[c * 16 + k]);
         s = fmaf(dl[c], w[c][k], s);
       }
-      g[k] = s * keep[k];
+      g[k] = xv[k] > 0.f ? s * keep[k] : 0.f;
+      g[k] = __bfloat162float(__float2bfloat16_rn(g[k]));  // sum exactly what is stored
+      acc[LOSS + 1 + k] += g[k];
     }
     dx[2 * i] = pack8(*reinterpret_cast<float(*)[8]>(g));
     dx[2 * i + 1] = pack8(*reinterpret_cast<float(*)[8]>(g + 8));
