@@ -175,8 +175,13 @@ int unpp_head_bwd_grid(int N, int H, int W);
  * step is the 1-based step count; gradients are multiplied by grad_scale first (1/world for DP). */
 int unpp_adamw(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps, float weight_decay,
                int step, float grad_scale, unpp_stream_t stream);
-/* u8 keep-mask for nn.Dropout(p): mask[i] = 1 with probability 1-p (counter-based hash of seed, i). */
-int unpp_dropout_mask(uint8_t* mask, long n, float p_drop, uint64_t seed, unpp_stream_t stream);
+/* Same, with the step count kept on the device (CUDA-graph friendly): increments *step_counter,
+ * derives the bias-corrected step size from it into *step_size_scratch, then updates. */
+int unpp_adamw_dev(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, uint64_t* step_counter, float* step_size_scratch, float grad_scale, unpp_stream_t stream);
+/* u8 keep-mask for nn.Dropout(p): mask[i] = 1 with probability 1-p (counter-based hash of seed, i and,
+ * when step_counter is not NULL, of the device step counter so that graph replays draw new masks). */
+int unpp_dropout_mask(uint8_t* mask, long n, float p_drop, uint64_t seed, const uint64_t* step_counter, unpp_stream_t stream);
 
 /* sizeof() of the argument structs as the C compiler sees them (binding self-check). */
 int unpp_sizeof_conv_args(void);

@@ -1,0 +1,89 @@
+"""GPU: the CUDA-graph sessions (fused.py) — inference + keypoints, and the fused training step
+(forward, MSE fused into the head backward, backward, reference AdamW on the flat buffer)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import unet_nested4tiny_objects_keypoints_b200 as pkg  # noqa: E402
+from unet_nested4tiny_objects_keypoints_b200 import fused  # noqa: E402
+from oracle import unetpp_oracle as O  # noqa: E402
+from test_training_gpu import check_grads  # noqa: E402
+
+
+def test_inference_session_graph_equals_eager_and_oracle():
+    sd = O.synth_state_dict(seed=31)
+    m = pkg.UNet_Nested()
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    x = torch.randn(3, 3, 64, 64, generator=torch.Generator().manual_seed(2))
+    sess = fused.InferenceSession(m, 3, 64, 64, head=2)
+    assert sess.graph is not None
+    xy, val = sess.run(x.pin_memory())
+    torch.cuda.synchronize()
+    xy2, val2, heats = m.predict_keypoints(x.cuda(), head=2)
+    assert torch.equal(xy, xy2) and torch.equal(val, val2) and torch.equal(sess.heat, heats[2])
+    ref = O.forward(sd, x)[2]
+    assert float((sess.heat.cpu() - ref).abs().max()) <= 3e-2
+    rxy, _ = O.argmax_keypoints(sess.heat.cpu().numpy())
+    assert np.array_equal(xy.cpu().numpy(), rxy)
+    # a second batch through the same graph
+    x2 = torch.randn(3, 3, 64, 64, generator=torch.Generator().manual_seed(3))
+    sess.run(x2.pin_memory())
+    torch.cuda.synchronize()
+    assert float((sess.heat.cpu() - O.forward(sd, x2)[2]).abs().max()) <= 3e-2
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_train_step_loss_grads_and_adamw_update(use_graph):
+    sd = O.synth_state_dict(seed=32)
+    m = pkg.UNet_Nested()
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    m.drop_out.p = 0.0
+    B, H, W = 2, 32, 32
+    hyper = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    step = fused.FusedTrainStep(m, B, H, W, use_graph=use_graph, **hyper)
+    # construction (warm-up + capture) must leave weights, buffers and optimizer state untouched
+    for k, v in m.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, 3, H, W, generator=g)
+    target = torch.rand(B, 4, H, W, generator=g)
+    p_old = step.flat_p.clone()
+    loss = step.step(x.pin_memory(), target.pin_memory())
+    torch.cuda.synchronize()
+    rl, _, rg, rstats = O.train_step_grads(sd, x, target, dropout_masks=None)
+    assert abs(float(loss) - float(rl)) <= 1e-2 * float(rl)
+    grads = {k: step.flat_g[off:off + n].view_as(p) for (k, p), (off, n) in zip(m.named_parameters(), step.ts.lay.values())}
+    check_grads(grads, rg)
+    # the update is the reference AdamW (decay = wd * p_old, not scaled by lr) applied to OUR gradient
+    p_exp, _, _ = O.adamw_reference_step(p_old.cpu(), step.flat_g.cpu(), torch.zeros_like(p_old.cpu()), torch.zeros_like(p_old.cpu()), 1, **hyper)
+    assert torch.allclose(step.flat_p.cpu(), p_exp, rtol=1e-5, atol=1e-7)
+    assert int(step.step_counter.item()) == 1
+    # parameters are views of the flat buffer: the module sees the update, and so does state_dict()
+    assert torch.equal(m.state_dict()["final_1.weight"].reshape(-1), step.flat_p[step.ts.lay["final_1.weight"][0]:][:64])
+    for k, v in rstats.items():
+        got = m.state_dict()[k].cpu()
+        if k.endswith("num_batches_tracked"):
+            assert int(got) == 1
+        else:
+            assert float((got - v).abs().max()) <= 1e-2 * float(v.abs().max()), k
+    # second step: Adam moments and the device step counter advance
+    step.step(x.pin_memory(), target.pin_memory())
+    torch.cuda.synchronize()
+    assert int(step.step_counter.item()) == 2 and float(step.flat_v.abs().max()) > 0
+
+
+def test_fused_train_step_dropout_masks_change_every_replay():
+    m = pkg.UNet_Nested().cuda().train()
+    step = fused.FusedTrainStep(m, 1, 32, 32)
+    x = torch.randn(1, 3, 32, 32).pin_memory()
+    t = torch.rand(1, 4, 32, 32).pin_memory()
+    step.step(x, t)
+    m1 = step.ts.t["mask0"].clone()
+    step.step(x, t)
+    m2 = step.ts.t["mask0"].clone()
+    assert not torch.equal(m1, m2)
+    assert abs(float(m1.float().mean()) - 0.6) < 0.05

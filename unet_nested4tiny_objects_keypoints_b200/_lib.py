@@ -101,7 +101,9 @@ _SIGNATURES = {
     "unpp_head_bwd_grid": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "unpp_adamw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                              C.c_int, C.c_float, C.c_void_p]),
-    "unpp_dropout_mask": (C.c_int, [C.c_void_p, C.c_long, C.c_float, C.c_uint64, C.c_void_p]),
+    "unpp_adamw_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                 C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+    "unpp_dropout_mask": (C.c_int, [C.c_void_p, C.c_long, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p]),
     "unpp_sizeof_conv_args": (C.c_int, []),
     "unpp_sizeof_pack_args": (C.c_int, []),
     "unpp_sizeof_wgrad_args": (C.c_int, []),

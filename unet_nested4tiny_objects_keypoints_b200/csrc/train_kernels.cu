@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 // (decay is NOT scaled by lr, and uses the pre-update p).  step_size is computed on the host in
 // double like the reference does in Python floats.
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n, float b1,
-                             float b2, float eps, float step_size, float wd, float grad_scale) {
+                             float b2, float eps, float step_size, const float* __restrict__ step_size_dev, float wd, float grad_scale) {
+  if (step_size_dev) step_size = *step_size_dev;
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < n; i += long(gridDim.x) * blockDim.x) {
     const float gr = g[i] * grad_scale;
     const float mm = m[i] * b1 + (1.f - b1) * gr;
@@ -304,13 +305,27 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// Device-side step bookkeeping so that a whole training step can live in one CUDA graph: bumps the
+// step counter and derives AdamW's bias-corrected step size from it (adamw.py:86-88).
+__global__ void adamw_prep_kernel(unsigned long long* counter, float lr, float b1, float b2, float* step_size) {
+  const unsigned long long t = *counter + 1ull;
+  *counter = t;
+  const double bc1 = 1.0 - pow(double(b1), double(t)), bc2 = 1.0 - pow(double(b2), double(t));
+  *step_size = float(double(lr) * sqrt(bc2) / bc1);
+}
+
 // Dropout keep-mask (nn.Dropout(p), models/unet.py:254): u8 1 = keep, counter-based hash RNG
 // (not torch's Philox stream: parity runs pass explicit masks; this serves throughput runs).
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16, x *= 0x7feb352du, x ^= x >> 15, x *= 0x846ca68bu, x ^= x >> 16;
   return x;
 }
-__global__ void dropout_mask_kernel(uint4* __restrict__ out, long n16, uint32_t seed_lo, uint32_t seed_hi, uint32_t thresh16) {
+__global__ void dropout_mask_kernel(uint4* __restrict__ out, long n16, uint32_t seed_lo, uint32_t seed_hi, uint32_t thresh16,
+                                    const unsigned long long* __restrict__ counter) {
+  if (counter) {  // per-step stream: fold the device step counter into the seed
+    const unsigned long long c = (*counter + 1ull) * 0x9E3779B97F4A7C15ull;
+    seed_lo ^= uint32_t(c), seed_hi ^= uint32_t(c >> 32);
+  }
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < n16; i += long(gridDim.x) * blockDim.x) {
     uint32_t wds[4];
 #pragma unroll
@@ -431,16 +446,25 @@ extern "C" int unpp_adamw(float* p, const float* g, float* m, float* v, long n, 
   if (!p || !g || !m || !v || n < 1 || step < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "adamw: bad argument");
   const double bc1 = 1.0 - pow(double(beta1), step), bc2 = 1.0 - pow(double(beta2), step);
   const float step_size = float(double(lr) * sqrt(bc2) / bc1);
-  adamw_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(p, g, m, v, n, beta1, beta2, eps, step_size, weight_decay, grad_scale);
+  adamw_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(p, g, m, v, n, beta1, beta2, eps, step_size, nullptr, weight_decay, grad_scale);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("adamw: launch");
   return UNPP_OK;
 }
 
-extern "C" int unpp_dropout_mask(uint8_t* mask, long n, float p_drop, uint64_t seed, unpp_stream_t stream) {
+extern "C" int unpp_adamw_dev(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, uint64_t* step_counter, float* step_size_scratch, float grad_scale, unpp_stream_t stream) {
+  if (!p || !g || !m || !v || n < 1 || !step_counter || !step_size_scratch) return unpp::fail(UNPP_ERR_BAD_ARG, "adamw_dev: bad argument");
+  adamw_prep_kernel<<<1, 1, 0, STREAM(stream)>>>(reinterpret_cast<unsigned long long*>(step_counter), lr, beta1, beta2, step_size_scratch);
+  adamw_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(p, g, m, v, n, beta1, beta2, eps, 0.f, step_size_scratch, weight_decay, grad_scale);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("adamw_dev: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_dropout_mask(uint8_t* mask, long n, float p_drop, uint64_t seed, const uint64_t* step_counter, unpp_stream_t stream) {
   if (!mask || n < 16 || (n & 15) || !(p_drop >= 0.f) || !(p_drop < 1.f)) return unpp::fail(UNPP_ERR_BAD_ARG, "dropout_mask: n must be a positive multiple of 16, 0 <= p < 1");
   const uint32_t thresh = uint32_t(double(p_drop) * 65536.0 + 0.5);
   dropout_mask_kernel<<<grid_for(n / 16, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<uint4*>(mask), n / 16, uint32_t(seed), uint32_t(seed >> 32),
-                                                                         thresh);
+                                                                         thresh, reinterpret_cast<const unsigned long long*>(step_counter));
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("dropout_mask: launch");
   return UNPP_OK;
 }

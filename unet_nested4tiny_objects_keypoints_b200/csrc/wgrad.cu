@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ uint64_t bar_full[2];
   uint8_t* const smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   const int job = blockIdx.y;
   const int cs = p.job_cs[job], con = p.job_con[job];
   const int nco = con >> 4, npairs = (cs >> 4) * nco;
@@ -205,8 +205,12 @@ int make_plan(const UnppWgradArgs* a, Plan* pl) {
 
 template <int TAPS, int PPW>
 int launch(const WgradParams& p, const Plan& pl, cudaStream_t stream) {
-  if (cudaFuncSetAttribute(wgrad_kernel<TAPS, PPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
-    return unpp::fail_cuda("wgrad: cudaFuncSetAttribute");
+  static bool opted_in = false;  // per instantiation; the attribute is idempotent
+  if (!opted_in) {
+    if (cudaFuncSetAttribute(wgrad_kernel<TAPS, PPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
+      return unpp::fail_cuda("wgrad: cudaFuncSetAttribute");
+    opted_in = true;
+  }
   wgrad_kernel<TAPS, PPW><<<dim3(pl.grid_x, pl.njobs), kThreads, pl.smem_total, stream>>>(p);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("wgrad: launch");
   return UNPP_OK;

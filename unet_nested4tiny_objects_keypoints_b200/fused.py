@@ -1,0 +1,206 @@
+"""Whole-step sessions on top of the engine: the hot loops of the reference trainer with every
+launch of a step captured in one CUDA graph.
+
+  * ``InferenceSession``  — ``val_epoch_`` core (trainer/trainer.py:209-220): forward in eval mode +
+    heat-map arg-max keypoints (tools/misc/heatmap.py:173-178), host tensors in, keypoints out.
+  * ``FusedTrainStep``    — ``train_epoch_`` core (trainer/trainer.py:115-136): zero_grad, forward,
+    mean-of-three-heads MSE (nn.MSELoss, trainer.py:427) with its gradient fused into the head
+    backward, backward, [data-parallel all-reduce], the reference's AdamW (tools/optimizers/
+    adamw.py:38-100) over one flat parameter buffer.  Where the reference makes three D2H copies, a
+    CPU loss and one H2D gradient copy per step (trainer.py:127-135), nothing leaves the device here.
+
+Data parallelism: one process per GPU, full replica each, local batch =
+global / world; the only exchange is ONE ``all_reduce(SUM)`` of the flat 553 260-element fp32
+gradient buffer per step (NCCL over NVLink; gloo in the CPU tests of the host logic), followed by
+the same AdamW update on every rank with ``grad_scale = 1/world``.  BatchNorm statistics stay
+per-rank like ``nn.DataParallel`` (trainer.py:338) keeps them per replica.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import ops
+from .training import TrainState, backward_train, flat_layout, forward_train, pack_train
+
+
+def _device(device) -> torch.device:
+    d = torch.device(device)
+    return torch.device("cuda", torch.cuda.current_device()) if d.type == "cuda" and d.index is None else d
+
+
+def _engine(model, device):
+    return model._engine(_device(device))
+
+
+class InferenceSession:
+    """Fixed-shape inference + keypoint extraction.  ``run(x_host)`` copies the batch to the device,
+    replays the captured forward + arg-max and returns ``(xy int32 [B,C,2], peak fp32 [B,C])`` on the
+    device; ``heat`` holds the heat maps of the selected head."""
+
+    def __init__(self, model, B: int, H: int, W: int, head: int = 2, device="cuda", use_graph: bool = True):
+        self.model, self.head = model, head
+        self.dev = _device(device)
+        self.eng = _engine(model, self.dev)
+        if model.training:
+            raise RuntimeError("InferenceSession needs model.eval()")
+        self.x = torch.zeros(B, model.in_channels, H, W, dtype=torch.float32, device=self.dev)
+        self.graph = None
+        self.launches = 0
+        with torch.no_grad(), torch.cuda.device(self.dev):
+            self._body()  # warm-up: packs weights, allocates the activation arena
+            torch.cuda.synchronize()
+            if use_graph:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._body()
+                torch.cuda.current_stream().wait_stream(s)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._body()
+                self.graph = g
+        # nchw->nhwc, 8 encoder convs, 3 pools, 6 x (deconv + 2 convs), arg-max
+        self.launches = 1 + 8 + 3 + 18 + 1
+
+    def _body(self):
+        heats = self.eng.forward_eval(self.x, heads=(self.head,))
+        self.heat = heats[self.head]
+        self.xy, self.val = ops.argmax_peaks(self.heat)
+
+    def run_device(self):
+        """Inputs already in ``self.x`` (device): one pass of the hot path."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            with torch.no_grad():
+                self._body()
+        return self.xy, self.val
+
+    def run(self, x_host: torch.Tensor):
+        self.x.copy_(x_host, non_blocking=True)
+        return self.run_device()
+
+
+class FusedTrainStep:
+    def __init__(self, model, B: int, H: int, W: int, lr: float = 3e-6, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-4, device="cuda", use_graph: bool = True, process_group=None, seed: int = 0):
+        """Defaults follow the reference CLI: ``--optimizer adamw --lr 3e-6 --weight-decay 1e-4`` (train.py:38-45)."""
+        self.model = model
+        self.dev = _device(device)
+        if not model.training:
+            raise RuntimeError("FusedTrainStep needs model.train()")
+        self.eng = _engine(model, self.dev)
+        self.hyper = dict(lr=lr, b1=betas[0], b2=betas[1], eps=eps, wd=weight_decay)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.ts = TrainState(self.eng, B, H, W)
+        ts = self.ts
+        p_drop = float(model.drop_out.p)
+        ts.use_masks, ts.drop_scale = p_drop > 0.0, (1.0 / (1.0 - p_drop) if p_drop > 0 else 1.0)
+        self.p_drop, self.seed = p_drop, seed
+        # flat fp32 parameter storage: every nn.Parameter becomes a view into one buffer (state_dict unchanged)
+        lay, n = flat_layout(model)
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=self.dev)
+        with torch.no_grad():
+            for name, p in model.named_parameters():
+                off, cnt = lay[name]
+                self.flat_p[off:off + cnt].copy_(p.detach().reshape(-1))
+                p.data = self.flat_p[off:off + cnt].view_as(p)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        self.flat_m = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        self.flat_v = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.step_size = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.x = torch.zeros(B, model.in_channels, H, W, dtype=torch.float32, device=self.dev)
+        self.target = torch.zeros(B, model.n_classes, H, W, dtype=torch.float32, device=self.dev)
+        self.numel_head = B * model.n_classes * H * W
+        self.coef = 2.0 / (3.0 * self.numel_head)  # d/dp of (1/3) sum_k mean((p_k - T)^2)
+        self.graph_a = self.graph_b = None
+        self.steps_done = 0
+        with torch.cuda.device(self.dev):
+            snapshot = (self.flat_p.clone(), [b.clone() for b in model.buffers()])
+            self._fwd_bwd()  # warm-up (allocates scratch); undone below
+            self._update()
+            torch.cuda.synchronize()
+            if use_graph:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._fwd_bwd()
+                    self._update()
+                torch.cuda.current_stream().wait_stream(s)
+                ga = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga):
+                    self._fwd_bwd()
+                    if self.world == 1:
+                        self._update()
+                self.graph_a = ga
+                if self.world > 1:
+                    gb = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gb):
+                        self._update()
+                    self.graph_b = gb
+            # restore the state the warm-up / capture passes touched
+            self.flat_p.copy_(snapshot[0])
+            for b, b0 in zip(model.buffers(), snapshot[1]):
+                b.copy_(b0)
+            self.flat_m.zero_()
+            self.flat_v.zero_()
+            self.step_counter.zero_()
+            torch.cuda.synchronize()
+
+    # one step = these two pieces; every launch in them is a libunpp.so kernel except the int64
+    # num_batches_tracked increments of the eight BatchNorm layers
+    def _fwd_bwd(self):
+        ts = self.ts
+        pack_train(ts)
+        if ts.use_masks:
+            for k in range(3):
+                ops.dropout_mask(ts.t[f"mask{k}"].view(-1), self.p_drop, self.seed * 7919 + k, self.step_counter)
+        forward_train(ts, self.x)
+        backward_train(ts, self.flat_g, target=self.target, coef=self.coef)
+        nacc, ncls = ts.head_nacc, self.model.n_classes
+        ops.reduce_partials(ts.t["head_red"], 3, nacc, 1, self.loss, scale=1.0 / (3.0 * self.numel_head), partial_offset=ncls * 17)
+
+    def _update(self):
+        h = self.hyper
+        ops.adamw_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, h["lr"], h["b1"], h["b2"], h["eps"], h["wd"], self.step_counter,
+                      self.step_size, grad_scale=1.0 / self.world)
+
+    def step_device(self) -> torch.Tensor:
+        """Inputs already in ``self.x`` / ``self.target``.  Returns the (device) loss of this rank's batch."""
+        if self.graph_a is not None:
+            self.graph_a.replay()
+        else:
+            self._fwd_bwd()
+            if self.world == 1:
+                self._update()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            if self.graph_b is not None:
+                self.graph_b.replay()
+            else:
+                self._update()
+        self.steps_done += 1
+        self.eng._packed_key = None  # parameters changed through raw pointers: eval-mode packed weights are stale
+        return self.loss
+
+    def step(self, x_host: torch.Tensor, target_host: torch.Tensor) -> torch.Tensor:
+        self.x.copy_(x_host, non_blocking=True)
+        self.target.copy_(target_host, non_blocking=True)
+        return self.step_device()
+
+    @property
+    def heats(self):
+        return self.ts.heats
+
+
+def broadcast_parameters(model, src: int = 0, process_group=None) -> None:
+    """Initial weight/buffer sync of the replicas (what nn.DataParallel's per-forward replicate does, trainer.py:338)."""
+    for t in list(model.parameters()) + list(model.buffers()):
+        torch.distributed.broadcast(t.data, src=src, group=process_group)

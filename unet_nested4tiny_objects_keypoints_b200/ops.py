@@ -18,8 +18,34 @@ from ._lib import ConvArgs, PackArgs, WgradArgs, MODE_CONV, MODE_DECONV  # noqa:
 W_SMEM_BUDGET = 96 * 1024  # packed weights of one n_tile kept resident in shared memory
 
 
+launch_count = 0   # kernels of libunpp.so enqueued through this module (bench.py reads it for "gpu_launches")
+trace = None       # when a list: conv()/wgrad() append (label, start_event, end_event, algorithmic_bytes, flops)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+class _Traced:
+    """Brackets one launch with CUDA events on the current stream when tracing is on."""
+
+    def __init__(self, label, nbytes, flops):
+        self.label, self.nbytes, self.flops = label, nbytes, flops
+
+    def __enter__(self):
+        if trace is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if trace is not None:
+            self.e1.record()
+            trace.append((self.label, self.e0, self.e1, self.nbytes, self.flops))
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -59,6 +85,7 @@ def pack_weights(src: torch.Tensor, kind: int, taps: int, n_total: int, n_tile: 
     a.kind, a.src_O, a.src_I, a.taps = kind, src.shape[0], src.shape[1], taps
     a.n_total, a.n_tile, a.n_begin = n_total, n_tile, n_begin
     a.k_begin, a.k_count, a.k8_total, a.k_dst8 = k_begin, k_count, k8_total, k_dst8
+    _count()
     _lib.check(lib().unpp_pack_weights(C.byref(a), _stream()), "unpp_pack_weights")
     return dst
 
@@ -96,7 +123,25 @@ def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Te
         a.drop_mask, a.drop_scale = _ptr(dmask), float(dscale)
     a.addend, a.relu_mask_src = _ptr(addend), _ptr(relu_mask_src)
     a.stats_partial, a.stats_aux, a.aux_mean, a.aux_istd = _ptr(stats_partial), _ptr(stats_aux), _ptr(aux_mean), _ptr(aux_istd)
-    _lib.check(lib().unpp_conv_tc(C.byref(a), _stream()), "unpp_conv_tc")
+    _count()
+    if trace is None:
+        _lib.check(lib().unpp_conv_tc(C.byref(a), _stream()), "unpp_conv_tc")
+        return
+    # algorithmic traffic: every source once, the output once, weights once; heat maps fp32
+    k_total = sum(s.shape[-1] for s in srcs)
+    px = N * H * W
+    nbytes = px * k_total * 2 + wpacked.numel() * 2
+    if out is not None:
+        nbytes += px * n_total * 2
+    if head is not None:
+        nbytes += px * head[0].shape[0] * 4 + (px * 16 if head[4] is not None else 0)
+    for extra in (addend, relu_mask_src, stats_aux):
+        if extra is not None:
+            nbytes += extra.numel() * 2
+    flops = 2 * px * k_total * n_total * taps
+    label = "conv_tc %s taps%d K%d N%d %dx%d" % ("deconv" if mode == MODE_DECONV else "conv", taps, k_total, n_total, H, W)
+    with _Traced(label, nbytes, flops):
+        _lib.check(lib().unpp_conv_tc(C.byref(a), _stream()), "unpp_conv_tc")
 
 
 def conv_grid(srcs_C: Sequence[int], N: int, H: int, W: int, n_total: int, n_tile: int, taps: int) -> int:
@@ -109,11 +154,13 @@ def conv_grid(srcs_C: Sequence[int], N: int, H: int, W: int, n_total: int, n_til
 
 def nchw_to_nhwc16(x: torch.Tensor, out: torch.Tensor) -> None:
     B, Cin, H, W = x.shape
+    _count()
     _lib.check(lib().unpp_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, Cin, H, W, 16, _stream()), "unpp_nchw_to_nhwc")
 
 
 def maxpool(x: torch.Tensor, out: torch.Tensor) -> None:
     B, H, W, Cc = x.shape
+    _count()
     _lib.check(lib().unpp_maxpool2x2(x.data_ptr(), out.data_ptr(), B, H, W, Cc, _stream()), "unpp_maxpool2x2")
 
 
@@ -125,6 +172,7 @@ def argmax_peaks(heat: torch.Tensor):
     B, Cc, H, W = heat.shape
     xy = torch.empty(B, Cc, 2, dtype=torch.int32, device=heat.device)
     val = torch.empty(B, Cc, dtype=torch.float32, device=heat.device)
+    _count()
     _lib.check(lib().unpp_argmax_peaks(heat.data_ptr(), B * Cc, H, W, xy.data_ptr(), val.data_ptr(), _stream()), "unpp_argmax_peaks")
     return xy, val
 
@@ -158,22 +206,29 @@ def wgrad_grid(srcs_C: Sequence[int], N: int, H: int, W: int, cout: int, taps: i
 def wgrad(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, dz: torch.Tensor, cout: int, taps: int, partial: torch.Tensor, dz_view=None) -> None:
     a = _wgrad_args(srcs, N, H, W, dz, cout, taps, dz_view)
     a.partial = partial.data_ptr()
-    _lib.check(lib().unpp_wgrad(C.byref(a), _stream()), "unpp_wgrad")
+    _count()
+    k_total = sum(s.shape[-1] for s in srcs)
+    px = N * H * W
+    with _Traced("wgrad taps%d K%d N%d %dx%d" % (taps, k_total, cout, H, W), px * (k_total + cout) * 2, 2 * px * k_total * cout * taps):
+        _lib.check(lib().unpp_wgrad(C.byref(a), _stream()), "unpp_wgrad")
 
 
 def wgrad_reduce(partial: torch.Tensor, nparts: int, taps: int, cin_total: int, cout: int, dst: torch.Tensor, ci_begin: int, ci_count: int,
                  s_co: int, s_ci: int, s_tap: int, scale: float = 1.0, dst_offset: int = 0) -> None:
+    _count()
     _lib.check(lib().unpp_wgrad_reduce(partial.data_ptr(), nparts, taps, cin_total, cout, dst.data_ptr() + 4 * dst_offset, ci_begin, ci_count,
                                        s_co, s_ci, s_tap, scale, _stream()), "unpp_wgrad_reduce")
 
 
 def reduce_partials(partial: torch.Tensor, nparts: int, stride: int, n: int, out: torch.Tensor, scale: float = 1.0, accumulate: bool = False,
                     partial_offset: int = 0, out_offset: int = 0) -> None:
+    _count()
     _lib.check(lib().unpp_reduce_partials(partial.data_ptr() + 4 * partial_offset, nparts, stride, n, scale, out.data_ptr() + 4 * out_offset,
                                           int(accumulate), _stream()), "unpp_reduce_partials")
 
 
 def bn_finalize(partial, nparts, Cc, count, gamma, beta, running_mean, running_var, momentum, eps, mean, istd, scale, shift) -> None:
+    _count()
     _lib.check(lib().unpp_bn_finalize(partial.data_ptr(), nparts, Cc, float(count), gamma.data_ptr(), beta.data_ptr(), _ptr(running_mean),
                                       _ptr(running_var), float(momentum), float(eps), mean.data_ptr(), istd.data_ptr(), scale.data_ptr(),
                                       shift.data_ptr(), _stream()), "unpp_bn_finalize")
@@ -181,16 +236,19 @@ def bn_finalize(partial, nparts, Cc, count, gamma, beta, running_mean, running_v
 
 def bn_relu(z, scale, shift, y, pooled=None) -> None:
     N, H, W, Cc = z.shape
+    _count()
     _lib.check(lib().unpp_bn_relu(z.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), _ptr(pooled), N, H, W, Cc, _stream()), "unpp_bn_relu")
 
 
 def maxpool_bwd(x, dpooled, dx) -> None:
     N, H, W, Cc = x.shape
+    _count()
     _lib.check(lib().unpp_maxpool2x2_bwd(x.data_ptr(), dpooled.data_ptr(), dx.data_ptr(), N, H, W, Cc, _stream()), "unpp_maxpool2x2_bwd")
 
 
 def bn_bwd_apply(dyh, z, mean, istd, gamma, sums, count, dz) -> None:
     N, H, W, Cc = z.shape
+    _count()
     _lib.check(lib().unpp_bn_bwd_apply(dyh.data_ptr(), z.data_ptr(), mean.data_ptr(), istd.data_ptr(), gamma.data_ptr(), sums.data_ptr(),
                                        float(count), dz.data_ptr(), N, H, W, Cc, _stream()), "unpp_bn_bwd_apply")
 
@@ -201,6 +259,7 @@ def head_bwd_grid(N: int, H: int, W: int) -> int:
 
 def head_bwd(heat, dheat, target, coef, x, drop_mask, drop_scale, head_w, dx, partial) -> None:
     N, ncls, H, W = heat.shape
+    _count()
     _lib.check(lib().unpp_head_bwd(heat.data_ptr(), _ptr(dheat), _ptr(target), float(coef), x.data_ptr(), _ptr(drop_mask), float(drop_scale),
                                    head_w.data_ptr(), ncls, dx.data_ptr(), partial.data_ptr(), N, H, W, _stream()), "unpp_head_bwd")
 
@@ -209,10 +268,24 @@ def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0)
     """tools/optimizers/adamw.py:38-100 on flat fp32 buffers (in place)."""
     for t in (p, g, m, v):
         assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous() and t.numel() == p.numel()
+    _count()
     _lib.check(lib().unpp_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
                                 float(weight_decay), int(step), float(grad_scale), _stream()), "unpp_adamw")
 
 
-def dropout_mask(mask: torch.Tensor, p_drop: float, seed: int) -> None:
+def adamw_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_counter, step_size_scratch, grad_scale=1.0) -> None:
+    """Same update with the step counter (int64 [1]) and step size (fp32 [1]) living on the device."""
+    for t in (p, g, m, v):
+        assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous() and t.numel() == p.numel()
+    assert step_counter.dtype == torch.int64 and step_size_scratch.dtype == torch.float32
+    _count(2)
+    _lib.check(lib().unpp_adamw_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr), float(beta1), float(beta2),
+                                    float(eps), float(weight_decay), step_counter.data_ptr(), step_size_scratch.data_ptr(), float(grad_scale),
+                                    _stream()), "unpp_adamw_dev")
+
+
+def dropout_mask(mask: torch.Tensor, p_drop: float, seed: int, step_counter: Optional[torch.Tensor] = None) -> None:
     assert mask.dtype == torch.uint8 and mask.is_cuda and mask.is_contiguous()
-    _lib.check(lib().unpp_dropout_mask(mask.data_ptr(), mask.numel(), float(p_drop), int(seed) & (2**64 - 1), _stream()), "unpp_dropout_mask")
+    _count()
+    _lib.check(lib().unpp_dropout_mask(mask.data_ptr(), mask.numel(), float(p_drop), int(seed) & (2**64 - 1), _ptr(step_counter), _stream()),
+               "unpp_dropout_mask")

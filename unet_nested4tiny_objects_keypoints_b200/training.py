@@ -195,6 +195,8 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
     eng, t, P, m = ts.eng, ts.t, ts.packed, ts.eng.model
     B, H, W = ts.B, ts.H, ts.W
     ncls = m.n_classes
+    if update_running_stats:
+        eng._packed_key = None  # running statistics change below without a torch version bump: drop the eval-mode fold cache
     ops.nchw_to_nhwc16(x, t["x16"])
     src = t["x16"]
     for lvl, name in enumerate(ENCODER):
