@@ -61,6 +61,9 @@ def check_grads(named_grads, ref):
         if _is_pre_bn_bias(k):
             assert gmax <= 1e-6 + 10 * scale, k
             continue
+        if scale == 0.0:  # e.g. a head that does not contribute to the loss: both must be exactly zero
+            assert gmax == 0.0, k
+            continue
         max_rel, min_cos = _bounds(k)
         assert rel <= max_rel, f"{k}: rel err {rel:.3e} > {max_rel} (scale {scale:.3e}, cos {cos:.5f})"
         assert cos >= min_cos, f"{k}: cosine {cos:.5f} < {min_cos}"

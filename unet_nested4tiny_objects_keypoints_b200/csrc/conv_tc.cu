@@ -18,7 +18,9 @@
 //   * epilogue warps read TMEM (tcgen05.ld 32x32b), apply bias / ReLU / ReLU-mask / addend, the
 //     fused 1x1 head + sigmoid, and store NHWC bf16 (and NCHW fp32 heatmaps).
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue
+// (two per TMEM lane quadrant).  The kernel is compiled per epilogue variant (conv / deconv scatter,
+// fused head, training extras) so that the inference epilogue carries no run-time feature tests.
 #include "sm100.cuh"
 #include "common.h"
 #include "../../include/unpp.h"
@@ -29,7 +31,8 @@ namespace {
 
 constexpr int kMaxChunks = 8;
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + epilogue warps
 
 struct ConvTcParams {
   CUtensorMap maps[UNPP_MAX_SRC];
@@ -100,11 +103,147 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
   return a1 + __shfl_xor_sync(0xffffffffu, a1, 1);
 }
 
+// Epilogue of one 16-column group of one 8x16-pixel... rather 128-pixel sub-tile: v[16] are the fp32
+// accumulators of this thread's pixel for GEMM columns [gcol, gcol+16).
+// Register-resident copy of the epilogue parameters (read once from the parameter bank).
+struct EpiArgs {
+  int H, W, cout, head_classes;
+  __nv_bfloat16* out;
+  float* heat;
+  float* logit;
+  const uint8_t* drop_mask;
+  float drop_scale;
+  const __nv_bfloat16* addend;
+  const __nv_bfloat16* relu_mask_src;
+  float* stats_partial;
+  const __nv_bfloat16* stats_aux;
+  const float* aux_mean;
+  const float* aux_istd;
+};
+
+template <bool DECONV, bool HEAD, bool TRAIN>
+__device__ __forceinline__ void epilogue_group(const EpiArgs& p, float (&v)[16], int n, int y, int x, bool valid, int gcol, int c0,
+                                               const float* s_bias, const float* s_head, float relu_floor, float* s_stats1, float* s_stats2,
+                                               int lane) {
+  {
+    const float4* b4 = reinterpret_cast<const float4*>(s_bias + (DECONV ? gcol % p.cout : c0));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 b = b4[k];
+      v[4 * k] += b.x, v[4 * k + 1] += b.y, v[4 * k + 2] += b.z, v[4 * k + 3] += b.w;
+    }
+  }
+  if constexpr (DECONV) {
+    if (valid) {
+      const int pq = gcol / p.cout, co0 = gcol % p.cout;
+      const size_t opix = (size_t(n) * (2 * p.H) + (2 * y + (pq >> 1))) * (2 * p.W) + (2 * x + (pq & 1));
+      uint4 o0, o1;
+      o0.x = pack_bf16x2(v[0], v[1]), o0.y = pack_bf16x2(v[2], v[3]), o0.z = pack_bf16x2(v[4], v[5]), o0.w = pack_bf16x2(v[6], v[7]);
+      o1.x = pack_bf16x2(v[8], v[9]), o1.y = pack_bf16x2(v[10], v[11]), o1.z = pack_bf16x2(v[12], v[13]), o1.w = pack_bf16x2(v[14], v[15]);
+      uint4* op = reinterpret_cast<uint4*>(p.out + opix * p.cout + co0);
+      op[0] = o0;
+      op[1] = o1;
+    }
+    return;
+  }
+  const size_t pix = (size_t(n) * p.H + y) * p.W + x;
+  if constexpr (TRAIN) {
+    if (p.addend && valid) {
+      const uint4* ap = reinterpret_cast<const uint4*>(p.addend + pix * p.cout + gcol);
+      uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+      uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[2 * k] += bf16_lo(aw[k]), v[2 * k + 1] += bf16_hi(aw[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], relu_floor);
+  if constexpr (TRAIN) {
+    if (p.relu_mask_src && valid) {
+      const uint4* mp = reinterpret_cast<const uint4*>(p.relu_mask_src + pix * p.cout + gcol);
+      uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+      uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (!(bf16_lo(mw[k]) > 0.f)) v[2 * k] = 0.f;
+        if (!(bf16_hi(mw[k]) > 0.f)) v[2 * k + 1] = 0.f;
+      }
+    }
+    if (p.stats_partial) {
+      // Per-channel sums over this warp's 32 pixels (statistics of the bf16-rounded value that is
+      // stored; invalid pixels contribute 0).  Second statistic: v*v (BN batch variance) or
+      // v * xhat with xhat = (aux - mean) * istd (BN backward's dgamma).
+      float s1[16], s2[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float r = valid ? __bfloat162float(__float2bfloat16_rn(v[k])) : 0.f;
+        s1[k] = r, s2[k] = r * r;
+      }
+      if (p.stats_aux) {
+        uint32_t xw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (valid) {
+          const uint4* xp = reinterpret_cast<const uint4*>(p.stats_aux + pix * p.cout + gcol);
+          const uint4 x0 = __ldg(xp), x1 = __ldg(xp + 1);
+          xw[0] = x0.x, xw[1] = x0.y, xw[2] = x0.z, xw[3] = x0.w, xw[4] = x1.x, xw[5] = x1.y, xw[6] = x1.z, xw[7] = x1.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s2[2 * k] = s1[2 * k] * (bf16_lo(xw[k]) - __ldg(p.aux_mean + gcol + 2 * k)) * __ldg(p.aux_istd + gcol + 2 * k);
+          s2[2 * k + 1] = s1[2 * k + 1] * (bf16_hi(xw[k]) - __ldg(p.aux_mean + gcol + 2 * k + 1)) * __ldg(p.aux_istd + gcol + 2 * k + 1);
+        }
+      }
+      const float r1 = warp_reduce16(s1, lane), r2 = warp_reduce16(s2, lane);
+      if ((lane & 1) == 0) {  // lane holds channel (lane >> 1); each warp owns its own slots
+        s_stats1[c0 + (lane >> 1)] += r1;
+        s_stats2[c0 + (lane >> 1)] += r2;
+      }
+    }
+  }
+  if (p.out && valid) {
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(v[0], v[1]), o0.y = pack_bf16x2(v[2], v[3]), o0.z = pack_bf16x2(v[4], v[5]), o0.w = pack_bf16x2(v[6], v[7]);
+    o1.x = pack_bf16x2(v[8], v[9]), o1.y = pack_bf16x2(v[10], v[11]), o1.z = pack_bf16x2(v[12], v[13]), o1.w = pack_bf16x2(v[14], v[15]);
+    uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.cout + gcol);
+    op[0] = o0;
+    op[1] = o1;
+  }
+  if constexpr (HEAD) {
+    if (valid) {
+      if constexpr (TRAIN) {
+        if (p.drop_mask) {
+          const uint4 dm = __ldg(reinterpret_cast<const uint4*>(p.drop_mask + pix * 16));
+          const uint32_t dw[4] = {dm.x, dm.y, dm.z, dm.w};
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = ((dw[k >> 2] >> (8 * (k & 3))) & 0xFF) ? v[k] * p.drop_scale : 0.f;
+        }
+      }
+      const size_t plane = size_t(p.H) * p.W;
+      size_t o = size_t(n) * p.head_classes * plane + size_t(y) * p.W + x;
+      for (int cls = 0; cls < p.head_classes; ++cls, o += plane) {
+        const float4* w4 = reinterpret_cast<const float4*>(s_head + cls * 16);
+        float acc = s_head[8 * 16 + cls];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 w = w4[k];
+          acc = fmaf(w.x, v[4 * k], acc), acc = fmaf(w.y, v[4 * k + 1], acc), acc = fmaf(w.z, v[4 * k + 2], acc), acc = fmaf(w.w, v[4 * k + 3], acc);
+        }
+        if constexpr (TRAIN) {
+          if (p.logit) p.logit[o] = acc;
+        }
+        p.heat[o] = 1.f / (1.f + __expf(-acc));
+      }
+    }
+  }
+}
+
+template <bool DECONV, bool HEAD, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_acc_full[2], bar_acc_empty[2], bar_w;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_stats[4][2][256];  // per epilogue warp per-channel partial sums (training only)
+  __shared__ __align__(16) float s_bias[256];
+  __shared__ __align__(16) float s_head[8 * 16 + 8];
+  __shared__ float s_stats[TRAIN ? kEpiWarps : 1][2][TRAIN ? 256 : 1];  // per epilogue warp per-channel partial sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntile_idx = blockIdx.y;  // which n_tile slice of the GEMM N axis this CTA owns
@@ -120,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_acc_full[i], 1);
-      mbar_init(&bar_acc_empty[i], 4);
+      mbar_init(&bar_acc_empty[i], kEpiWarps);
     }
     mbar_init(&bar_w, 1);
     fence_mbar_init();
@@ -132,6 +271,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < UNPP_MAX_SRC; ++i)
       if (i < p.nchunk) tma_prefetch_desc(&p.maps[p.ch_map[i]]);
+  }
+  // stage the per-column bias (conv: this CTA's n_tile slice; deconv: all Cout) and the 1x1 head
+  {
+    const int nb = DECONV ? p.cout : p.ncols;
+    for (int i = threadIdx.x; i < nb; i += kThreads) s_bias[i] = p.bias ? __ldg(p.bias + (DECONV ? 0 : ntile_idx * p.ncols) + i) : 0.f;
+    if constexpr (HEAD) {
+      for (int i = threadIdx.x; i < p.head_classes * 16; i += kThreads) s_head[i] = __ldg(p.head_w + i);
+      for (int i = threadIdx.x; i < p.head_classes; i += kThreads) s_head[8 * 16 + i] = __ldg(p.head_b + i);
+    }
+    if constexpr (TRAIN) {
+      for (int i = threadIdx.x; i < kEpiWarps * 2 * 256; i += kThreads) (&s_stats[0][0][0])[i] = 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -165,33 +316,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    // every kernel parameter used below is copied to a register first: the loop must not touch
+    // the parameter bank between MMA issues
     mbar_wait(&bar_w, 0);
-    const uint32_t idesc = make_idesc_bf16(128, p.ncols);
+    const int ncols = p.ncols, nsub = p.nsub, taps = p.taps, k8_total = p.k8_total, nchunk = p.nchunk, nstage = p.nstage;
+    const int ntiles = p.ntiles, stage_bytes = p.stage_bytes;
+    const uint32_t idesc = make_idesc_bf16(128, ncols);
     const uint32_t w_addr = smem_u32(w_smem);
     const uint32_t stage_addr0 = smem_u32(stage0);
+    int spans[kMaxChunks], wk8s[kMaxChunks];
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) spans[c] = p.ch_span[c], wk8s[c] = p.ch_wk8[c];
     int it = 0, tile_it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_it) {
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
       const int b = tile_it & 1, aph = (tile_it >> 1) & 1;
       mbar_wait(&bar_acc_empty[b], aph ^ 1);
       tc_fence_after();
-      const uint32_t acc = tmem_base + uint32_t(b * p.nsub * p.ncols);
-      for (int c = 0; c < p.nchunk; ++c, ++it) {
-        const int s = it % p.nstage, ph = (it / p.nstage) & 1;
+      const uint32_t acc = tmem_base + uint32_t(b * nsub * ncols);
+#pragma unroll 1
+      for (int c = 0; c < nchunk; ++c, ++it) {
+        const int s = it % nstage, ph = (it / nstage) & 1;
+        int span = spans[0], wk8 = wk8s[0];
+#pragma unroll
+        for (int cc = 1; cc < kMaxChunks; ++cc)
+          if (cc == c) span = spans[cc], wk8 = wk8s[cc];
         mbar_wait(&bar_full[s], ph);
         tc_fence_after();
         if (elect_one()) {
-          const int span = p.ch_span[c];
           const int kslabs = span >> 5;
-          const uint64_t a0 = make_sdesc(stage_addr0 + uint32_t(s) * p.stage_bytes, 16, uint32_t(P * span), layout_type_of_span(span));
+          const uint64_t a0 = make_sdesc(stage_addr0 + uint32_t(s) * stage_bytes, 16, uint32_t(P * span), layout_type_of_span(span));
           const uint32_t sub_step = uint32_t(8 * span) >> 4;  // next 8-pixel patch column, in 16 B units
-          for (int tap = 0; tap < p.taps; ++tap) {
-            const int r = p.taps == 9 ? tap / 3 : 0, sft = p.taps == 9 ? tap % 3 : 0;
+          const uint64_t b0 = make_sdesc(w_addr + uint32_t(wk8 * ncols * 16), uint32_t(ncols * 16), 128, 0);
+          const uint32_t b_tap_step = uint32_t(k8_total * ncols * 16) >> 4, b_ks_step = uint32_t(2 * ncols * 16) >> 4;
+          for (int tap = 0; tap < taps; ++tap) {
+            const int r = taps == 9 ? tap / 3 : 0, sft = taps == 9 ? tap % 3 : 0;
+            const uint64_t a_row = a0 + uint64_t(uint32_t((r * P + sft) * span) >> 4);
+            const uint64_t b_row = b0 + uint64_t(tap * b_tap_step);
             for (int ks = 0; ks < kslabs; ++ks) {
-              const uint64_t a_tap = a0 + uint64_t(uint32_t((r * P + sft) * span + ks * 32) >> 4);
-              const uint64_t bdesc =
-                  make_sdesc(w_addr + uint32_t(((tap * p.k8_total + p.ch_wk8[c] + 2 * ks) * p.ncols) * 16), uint32_t(p.ncols * 16), 128, 0);
+              const uint64_t a_tap = a_row + uint64_t(ks * 2), bdesc = b_row + uint64_t(ks * b_ks_step);
               const uint32_t accum = (c | tap | ks) ? 1u : 0u;
-              for (int j = 0; j < p.nsub; ++j) umma_bf16(acc + uint32_t(j * p.ncols), a_tap + uint64_t(j * sub_step), bdesc, idesc, accum);
+              for (int j = 0; j < nsub; ++j) umma_bf16(acc + uint32_t(j * ncols), a_tap + uint64_t(j * sub_step), bdesc, idesc, accum);
             }
           }
         }
@@ -203,131 +367,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM lane quadrant; the (sub-tile, 16-column group) units of a tile alternate
+    // between them.  The TMEM load of the next unit is in flight while the current one is processed.
+    const int ew = warp - 2;
     const int q = warp & 3;              // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;
     const int m = q * 32 + lane;         // accumulator row
     const int pi = m >> 3, pj = m & 7;   // pixel inside the 16x8 patch
-    const int ew = warp - 2;
+    const int ncb = p.ncols >> 4, units = p.nsub * ncb;
+    const float relu_floor = p.relu ? 0.f : -INFINITY;
+    EpiArgs e;
+    e.H = p.H, e.W = p.W, e.cout = p.cout, e.head_classes = p.head_classes, e.out = p.out, e.heat = p.heat, e.logit = p.logit;
+    e.drop_mask = p.drop_mask, e.drop_scale = p.drop_scale, e.addend = p.addend, e.relu_mask_src = p.relu_mask_src;
+    e.stats_partial = p.stats_partial, e.stats_aux = p.stats_aux, e.aux_mean = p.aux_mean, e.aux_istd = p.aux_istd;
+    const int TW = p.TW, ncols = p.ncols, nsub = p.nsub, ntiles = p.ntiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y;
+    float* const st1 = TRAIN ? &s_stats[TRAIN ? ew : 0][0][0] : nullptr;
+    float* const st2 = TRAIN ? &s_stats[TRAIN ? ew : 0][1][0] : nullptr;
     int tile_it = 0;
-    if (p.stats_partial)
-      for (int i = lane; i < 2 * 256; i += 32) (&s_stats[ew][0][0])[i] = 0.f;
-    __syncwarp();
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_it) {
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
       const int b = tile_it & 1, aph = (tile_it >> 1) & 1;
-      const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+      const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
       mbar_wait(&bar_acc_full[b], aph);
       tc_fence_after();
       const int y = ty * 16 + pi;
-      for (int j = 0; j < p.nsub; ++j) {
-        const int x = tx * p.TW + j * 8 + pj;
-        const bool valid = (y < p.H) && (x < p.W);
-        for (int c0 = 0; c0 < p.ncols; c0 += 16) {
-          uint32_t raw[16];
-          tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t((b * p.nsub + j) * p.ncols + c0), raw);
-          tmem_ld_wait();
-          float v[16];
+      const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * nsub * ncols);
+      uint32_t raw[16];
+      int u = half;
+      if (u < units) tmem_ld16(tbase + uint32_t(u * 16), raw);  // unit u covers columns [16u, 16u+16) of this accumulator set
+      for (; u < units; u += 2) {
+        tmem_ld_wait16(raw);
+        float v[16];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(raw[k]);
-          const int gcol = ntile_idx * p.ncols + c0;  // GEMM column of v[0]
-          if (p.mode == UNPP_MODE_CONV) {
-            const size_t pix = (size_t(n) * p.H + y) * p.W + x;
-            if (p.bias) {
-#pragma unroll
-              for (int k = 0; k < 16; ++k) v[k] += __ldg(p.bias + gcol + k);
-            }
-            if (p.addend && valid) {
-              const uint4* ap = reinterpret_cast<const uint4*>(p.addend + pix * p.cout + gcol);
-              uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
-              uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-              for (int k = 0; k < 8; ++k) v[2 * k] += bf16_lo(aw[k]), v[2 * k + 1] += bf16_hi(aw[k]);
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
-            }
-            if (p.relu_mask_src && valid) {
-              const uint4* mp = reinterpret_cast<const uint4*>(p.relu_mask_src + pix * p.cout + gcol);
-              uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-              uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                if (!(bf16_lo(mw[k]) > 0.f)) v[2 * k] = 0.f;
-                if (!(bf16_hi(mw[k]) > 0.f)) v[2 * k + 1] = 0.f;
-              }
-            }
-            if (p.stats_partial) {
-              // Per-channel sums over this warp's 32 pixels (statistics of the bf16-rounded value
-              // that is stored; invalid pixels contribute 0).  Second statistic: v*v (BN batch
-              // variance) or v * xhat with xhat = (aux - mean) * istd (BN backward's dgamma).
-              float s1[16], s2[16];
-#pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const float r = valid ? __bfloat162float(__float2bfloat16_rn(v[k])) : 0.f;
-                s1[k] = r, s2[k] = r * r;
-              }
-              if (p.stats_aux) {
-                uint32_t xw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                if (valid) {
-                  const uint4* xp = reinterpret_cast<const uint4*>(p.stats_aux + pix * p.cout + gcol);
-                  const uint4 x0 = __ldg(xp), x1 = __ldg(xp + 1);
-                  xw[0] = x0.x, xw[1] = x0.y, xw[2] = x0.z, xw[3] = x0.w, xw[4] = x1.x, xw[5] = x1.y, xw[6] = x1.z, xw[7] = x1.w;
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  s2[2 * k] = s1[2 * k] * (bf16_lo(xw[k]) - __ldg(p.aux_mean + gcol + 2 * k)) * __ldg(p.aux_istd + gcol + 2 * k);
-                  s2[2 * k + 1] = s1[2 * k + 1] * (bf16_hi(xw[k]) - __ldg(p.aux_mean + gcol + 2 * k + 1)) * __ldg(p.aux_istd + gcol + 2 * k + 1);
-                }
-              }
-              const float r1 = warp_reduce16(s1, lane), r2 = warp_reduce16(s2, lane);
-              if ((lane & 1) == 0) {  // lane holds channel (lane >> 1); each warp owns its own slots
-                s_stats[ew][0][c0 + (lane >> 1)] += r1;
-                s_stats[ew][1][c0 + (lane >> 1)] += r2;
-              }
-            }
-            if (p.out && valid) {
-              uint4 o0, o1;
-              o0.x = pack_bf16x2(v[0], v[1]), o0.y = pack_bf16x2(v[2], v[3]), o0.z = pack_bf16x2(v[4], v[5]), o0.w = pack_bf16x2(v[6], v[7]);
-              o1.x = pack_bf16x2(v[8], v[9]), o1.y = pack_bf16x2(v[10], v[11]), o1.z = pack_bf16x2(v[12], v[13]),
-              o1.w = pack_bf16x2(v[14], v[15]);
-              uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.cout + gcol);
-              op[0] = o0;
-              op[1] = o1;
-            }
-            if (p.head_w && valid) {
-              if (p.drop_mask) {
-                const uint4 dm = __ldg(reinterpret_cast<const uint4*>(p.drop_mask + pix * 16));
-                const uint32_t dw[4] = {dm.x, dm.y, dm.z, dm.w};
-#pragma unroll
-                for (int k = 0; k < 16; ++k) v[k] = ((dw[k >> 2] >> (8 * (k & 3))) & 0xFF) ? v[k] * p.drop_scale : 0.f;
-              }
-              for (int cls = 0; cls < p.head_classes; ++cls) {
-                float acc = __ldg(p.head_b + cls);
-#pragma unroll
-                for (int k = 0; k < 16; ++k) acc = fmaf(__ldg(p.head_w + cls * 16 + k), v[k], acc);
-                const size_t o = ((size_t(n) * p.head_classes + cls) * p.H + y) * p.W + x;
-                if (p.logit) p.logit[o] = acc;
-                p.heat[o] = 1.f / (1.f + __expf(-acc));
-              }
-            }
-          } else {  // UNPP_MODE_DECONV: column block -> (p,q) quadrant of the 2x upsampled output
-            const int pq = gcol / p.cout, co0 = gcol % p.cout;
-            if (valid) {
-              if (p.bias) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) v[k] += __ldg(p.bias + co0 + k);
-              }
-              const size_t opix = (size_t(n) * (2 * p.H) + (2 * y + (pq >> 1))) * (2 * p.W) + (2 * x + (pq & 1));
-              uint4 o0, o1;
-              o0.x = pack_bf16x2(v[0], v[1]), o0.y = pack_bf16x2(v[2], v[3]), o0.z = pack_bf16x2(v[4], v[5]), o0.w = pack_bf16x2(v[6], v[7]);
-              o1.x = pack_bf16x2(v[8], v[9]), o1.y = pack_bf16x2(v[10], v[11]), o1.z = pack_bf16x2(v[12], v[13]),
-              o1.w = pack_bf16x2(v[14], v[15]);
-              uint4* op = reinterpret_cast<uint4*>(p.out + opix * p.cout + co0);
-              op[0] = o0;
-              op[1] = o1;
-            }
-          }
-        }
+        for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(raw[k]);
+        if (u + 2 < units) tmem_ld16(tbase + uint32_t((u + 2) * 16), raw);
+        const int j = u / ncb, c0 = (u % ncb) * 16;
+        const int x = tx * TW + j * 8 + pj;
+        const bool valid = (y < e.H) && (x < e.W);
+        epilogue_group<DECONV, HEAD, TRAIN>(e, v, n, y, x, valid, ntile_idx * ncols + c0, c0, s_bias, s_head, relu_floor, st1, st2, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -338,13 +415,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
-  if (p.stats_partial) {
-    // partial layout [cta.x][2][n_total]; the four warp slots are summed in a fixed order so the
-    // result is deterministic for a given launch geometry.
-    for (int i = threadIdx.x; i < 2 * p.ncols; i += kThreads) {
-      const int st = i / p.ncols, ch = i % p.ncols;
-      const float t = ((s_stats[0][st][ch] + s_stats[1][st][ch]) + s_stats[2][st][ch]) + s_stats[3][st][ch];
-      p.stats_partial[(size_t(blockIdx.x) * 2 + st) * p.cout + ntile_idx * p.ncols + ch] = t;
+  if constexpr (TRAIN) {
+    if (p.stats_partial) {
+      // partial layout [cta.x][2][n_total]; the warp slots are summed in a fixed order so the
+      // result is deterministic for a given launch geometry.
+      for (int i = threadIdx.x; i < 2 * p.ncols; i += kThreads) {
+        const int st = i / p.ncols, ch = i % p.ncols;
+        float t = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < kEpiWarps; ++wv) t += s_stats[TRAIN ? wv : 0][st][TRAIN ? ch : 0];
+        p.stats_partial[(size_t(blockIdx.x) * 2 + st) * p.cout + ntile_idx * p.ncols + ch] = t;
+      }
     }
   }
 }
@@ -397,7 +478,7 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
   const int pad = a->taps == 9 ? 1 : 0;
   pl->w_bytes = a->taps * k8 * a->n_tile * 16;
   pl->w_smem_bytes = (pl->w_bytes + 1023) / 1024 * 1024;
-  const int smem_budget = 200 * 1024;
+  const int smem_budget = 196 * 1024;
   int TW = 64;
   while (TW > 8 && (2 * (TW / 8) * a->n_tile > 512 || TW / 2 >= ((a->W + 7) / 8) * 8)) TW >>= 1;
   for (;; TW >>= 1) {
@@ -487,13 +568,27 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   p.stats_aux = reinterpret_cast<const __nv_bfloat16*>(a->stats_aux);
   p.aux_mean = a->aux_mean, p.aux_istd = a->aux_istd;
 
-  static int smem_opted_in = 0;  // attribute is per-function, idempotent
-  if (!smem_opted_in) {
-    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024) != cudaSuccess)
-      return unpp::fail_cuda("conv_tc: cudaFuncSetAttribute");
-    smem_opted_in = 1;
-  }
-  conv_tc_kernel<<<dim3(pl.grid_x, pl.grid_y), kThreads, pl.smem_total, stream>>>(p);
+  const bool deconv = a->mode == UNPP_MODE_DECONV, head = a->head_w != nullptr;
+  const bool train = a->addend || a->relu_mask_src || a->stats_partial || a->logit || a->drop_mask;
+  if (deconv && train) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: deconv mode has no training epilogue");
+  if (deconv && a->n_total / 4 > 256) return unpp::fail(UNPP_ERR_UNSUPPORTED, "conv_tc: deconv Cout > 256");
+  const dim3 grid(pl.grid_x, pl.grid_y);
+#define UNPP_LAUNCH(D, Hd, T)                                                                                                         \
+  do {                                                                                                                                \
+    static int opted_in = 0; /* attribute is per-function, idempotent */                                                              \
+    if (!opted_in) {                                                                                                                  \
+      if (cudaFuncSetAttribute(conv_tc_kernel<D, Hd, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024) != cudaSuccess)     \
+        return unpp::fail_cuda("conv_tc: cudaFuncSetAttribute");                                                                      \
+      opted_in = 1;                                                                                                                   \
+    }                                                                                                                                 \
+    conv_tc_kernel<D, Hd, T><<<grid, kThreads, pl.smem_total, stream>>>(p);                                                           \
+  } while (0)
+  if (deconv) UNPP_LAUNCH(true, false, false);
+  else if (head && train) UNPP_LAUNCH(false, true, true);
+  else if (head) UNPP_LAUNCH(false, true, false);
+  else if (train) UNPP_LAUNCH(false, false, true);
+  else UNPP_LAUNCH(false, false, false);
+#undef UNPP_LAUNCH
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("conv_tc: launch");
   return UNPP_OK;
 }

@@ -111,8 +111,9 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
+  // no "memory" clobber on purpose: the operands were made visible by the mbarrier wait (which has
+  // one); a clobber here would force every kernel parameter to be re-read after each MMA issue.
 }
 // Arrive on an mbarrier when all previously issued MMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
@@ -127,8 +128,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
+      : "r"(taddr));
+}
+// Wait for the outstanding TMEM loads; the registers are passed through the asm so that no use of
+// them can be scheduled above the wait.
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                 "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
 }
 
 // ----------------------------------------------------------------------------- descriptors
