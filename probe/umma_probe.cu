@@ -604,6 +604,85 @@ static void p2_case(int lt, int N, long long* dc) {
          NACC, double(c) / (NIT * 16));
 }
 
+
+// p3: does the SS-mode MMA rate depend on the ALIGNMENT of the A start address relative to the
+// swizzle atom (8 rows x span)?  The production conv shifts the start by whole pixels (= span bytes)
+// and whole tile rows (P*span bytes) to select a filter tap; B is the no-swizzle packed weight tile.
+__global__ void __launch_bounds__(128, 1) k_mma_rate3(uint32_t idesc, int n_iter, uint32_t a_off, uint32_t sbo, uint32_t lt, uint32_t j_step,
+                                                      int ncol, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  for (int i = threadIdx.x * 16; i < 128 * 1024; i += blockDim.x * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 32) {
+    tmem_alloc(&tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base, base = smem_u32(smem);
+  if (threadIdx.x < 32) {
+    const uint64_t bdesc = make_sdesc(base + 96 * 1024, uint32_t(ncol * 16), 128, 0);
+    const uint64_t adesc0 = make_sdesc(base + a_off, 16, sbo, lt);
+    long long t0 = clock64();
+    for (int it = 0; it < n_iter; ++it) {
+      if (elect_one()) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) umma_bf16(tb + u * ncol, adesc0 + uint64_t((u * j_step) >> 4), bdesc, idesc, it > 0 ? 1u : 0u);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0 && threadIdx.x == 0) *cycles = t1 - t0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tb, 512);
+}
+
+static void test_p3() {
+  long long* dc;
+  CK(cudaMalloc(&dc, 8));
+  CK(cudaFuncSetAttribute(k_mma_rate3, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  const int NIT = 512;
+  struct Case { const char* name; int span; uint32_t a_off, sbo; int N; };
+  const Case cases[] = {
+      {"swz32 aligned dense (sbo=256)", 32, 0, 256, 16},        {"swz32 start+32B dense", 32, 32, 256, 16},
+      {"swz32 start+128B dense", 32, 128, 256, 16},              {"swz32 aligned sbo=66px", 32, 0, 66 * 32, 16},
+      {"swz32 start+1px sbo=66px", 32, 32, 66 * 32, 16},         {"swz32 aligned sbo=72px", 32, 0, 72 * 32, 16},
+      {"swz32 start+1px sbo=72px", 32, 32, 72 * 32, 16},         {"swz32 aligned sbo=72px N=48", 32, 0, 72 * 32, 48},
+      {"swz64 aligned dense (sbo=512)", 64, 0, 512, 32},         {"swz64 start+1px dense", 64, 64, 512, 32},
+      {"swz64 start+1px sbo=66px", 64, 64, 66 * 64, 32},         {"swz64 aligned sbo=72px", 64, 0, 72 * 64, 32},
+      {"swz128 aligned dense (sbo=1024)", 128, 0, 1024, 64},     {"swz128 start+1px dense", 128, 128, 1024, 64},
+      {"swz128 start+1px sbo=34px", 128, 128, 34 * 128, 64},     {"swz128 aligned sbo=40px", 128, 0, 40 * 128, 64},
+      {"swz128 aligned sbo=40px N=192", 128, 0, 40 * 128, 192},  {"swz128 aligned dense N=128", 128, 0, 1024, 128},
+  };
+  for (const Case& c : cases) {
+    const uint32_t lt = c.span == 128 ? 2 : c.span == 64 ? 4 : 6;
+    if (8 * c.N > 512) {
+      continue;
+    }
+    k_mma_rate3<<<148, 128, 128 * 1024>>>(make_idesc_bf16(128, c.N), NIT, c.a_off, c.sbo, lt, 8 * c.span, c.N, dc);
+    CK(cudaGetLastError());
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("RESULT p3 %s launch error %s FAIL\n", c.name, cudaGetErrorString(e));
+      exit(1);
+    }
+    long long cyc;
+    CK(cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost));
+    printf("RESULT p3 %-36s N=%3d  %.1f cycles/MMA (128xNx16)  PASS\n", c.name, c.N, double(cyc) / (NIT * 8));
+  }
+}
+
 static void test_p2() {
   long long* dc;
   CK(cudaMalloc(&dc, 8));
@@ -689,6 +768,7 @@ int main(int argc, char** argv) {
   else if (t == "t6") test_tma("t6(4d C=16 swizzle32 dst+128)", 6);
   else if (t == "p1") test_p1();
   else if (t == "p2") test_p2();
+  else if (t == "p3") test_p3();
   else if (t == "m8") {
     test_m8(32);
     test_m8(64);

@@ -18,9 +18,10 @@
 //   * epilogue warps read TMEM (tcgen05.ld 32x32b), apply bias / ReLU / ReLU-mask / addend, the
 //     fused 1x1 head + sigmoid, and store NHWC bf16 (and NCHW fp32 heatmaps).
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue
+// Warp roles: warp 0 = TMA producer, warps 1,10,11,12 = MMA issuers (warp 1 also allocates TMEM), warps 2..9 = epilogue
 // (two per TMEM lane quadrant).  The kernel is compiled per epilogue variant (conv / deconv scatter,
 // fused head, training extras) so that the inference epilogue carries no run-time feature tests.
+#include <cstdlib>
 #include "sm100.cuh"
 #include "common.h"
 #include "../../include/unpp.h"
@@ -32,7 +33,8 @@ namespace {
 constexpr int kMaxChunks = 8;
 constexpr int kMaxStages = 8;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + epilogue warps
+constexpr int kMmaWarps = 4;  // issuing threads: each owns the sub-tile accumulators j = i, i+4, ... (disjoint TMEM columns)
+constexpr int kThreads = 64 + 32 * kEpiWarps + 32 * (kMmaWarps - 1);  // TMA warp + MMA warp + epilogue warps + extra MMA warps
 
 struct ConvTcParams {
   CUtensorMap maps[UNPP_MAX_SRC];
@@ -64,6 +66,7 @@ struct ConvTcParams {
   const __nv_bfloat16* stats_aux;
   const float* aux_mean;
   const float* aux_istd;
+  int dbg;  // UNPP_DBG experiment bits (0 in production): 1 = epilogue skips its work, 2 = no MMAs issued, 4 = no TMA tile loads
 };
 
 __device__ __forceinline__ uint32_t layout_type_of_span(int span) { return span == 128 ? 2u : span == 64 ? 4u : 6u; }
@@ -255,10 +258,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nstage; ++i) {
       mbar_init(&bar_full[i], 1);
-      mbar_init(&bar_empty[i], 1);
+      mbar_init(&bar_empty[i], kMmaWarps);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_acc_full[i], 1);
+      mbar_init(&bar_acc_full[i], kMmaWarps);
       mbar_init(&bar_acc_empty[i], kEpiWarps);
     }
     mbar_init(&bar_w, 1);
@@ -308,19 +311,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int c = 0; c < p.nchunk; ++c, ++it) {
           const int s = it % p.nstage, ph = (it / p.nstage) & 1;
           mbar_wait(&bar_empty[s], ph ^ 1);
+          if (p.dbg & 4) {
+            mbar_arrive(&bar_full[s]);
+            continue;
+          }
           mbar_arrive_expect_tx(&bar_full[s], rows * P * p.ch_span[c]);
           tma_load_4d(&p.maps[p.ch_map[c]], &bar_full[s], stage0 + size_t(s) * p.stage_bytes, p.ch_c0[c], tx * p.TW - pad,
                       ty * 16 - pad, n);
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 || warp >= 2 + kEpiWarps) {
+    // ------------------------------------------------------------------ MMA issuers (warps 1, 10, 11, 12)
+    // One thread can only sustain ~1 MMA per 85 cycles through the uniform datapath (measured: the
+    // tensor pipe takes ~40); four issuing threads, each with its own accumulators, remove that limit.
+    const int mw = warp == 1 ? 0 : warp - (1 + kEpiWarps);
+    const bool has0 = mw < p.nsub, has1 = mw + kMmaWarps < p.nsub;
     // every kernel parameter used below is copied to a register first: the loop must not touch
     // the parameter bank between MMA issues
     mbar_wait(&bar_w, 0);
     const int ncols = p.ncols, nsub = p.nsub, taps = p.taps, k8_total = p.k8_total, nchunk = p.nchunk, nstage = p.nstage;
-    const int ntiles = p.ntiles, stage_bytes = p.stage_bytes;
+    const int ntiles = p.ntiles, stage_bytes = p.stage_bytes, dbg = p.dbg;
     const uint32_t idesc = make_idesc_bf16(128, ncols);
     const uint32_t w_addr = smem_u32(w_smem);
     const uint32_t stage_addr0 = smem_u32(stage0);
@@ -342,20 +353,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (cc == c) span = spans[cc], wk8 = wk8s[cc];
         mbar_wait(&bar_full[s], ph);
         tc_fence_after();
-        if (elect_one()) {
+        if (elect_one() && !(dbg & 2)) {
+          // descriptor arithmetic is incremental (adds of loop-invariant 16-byte-unit offsets): the
+          // issue rate of this single thread is what bounds the small-N layers
           const int kslabs = span >> 5;
-          const uint64_t a0 = make_sdesc(stage_addr0 + uint32_t(s) * stage_bytes, 16, uint32_t(P * span), layout_type_of_span(span));
-          const uint32_t sub_step = uint32_t(8 * span) >> 4;  // next 8-pixel patch column, in 16 B units
-          const uint64_t b0 = make_sdesc(w_addr + uint32_t(wk8 * ncols * 16), uint32_t(ncols * 16), 128, 0);
+          const uint32_t px_step = uint32_t(span) >> 4, row_step = uint32_t(P * span) >> 4;
           const uint32_t b_tap_step = uint32_t(k8_total * ncols * 16) >> 4, b_ks_step = uint32_t(2 * ncols * 16) >> 4;
-          for (int tap = 0; tap < taps; ++tap) {
-            const int r = taps == 9 ? tap / 3 : 0, sft = taps == 9 ? tap % 3 : 0;
-            const uint64_t a_row = a0 + uint64_t(uint32_t((r * P + sft) * span) >> 4);
-            const uint64_t b_row = b0 + uint64_t(tap * b_tap_step);
-            for (int ks = 0; ks < kslabs; ++ks) {
-              const uint64_t a_tap = a_row + uint64_t(ks * 2), bdesc = b_row + uint64_t(ks * b_ks_step);
-              const uint32_t accum = (c | tap | ks) ? 1u : 0u;
-              for (int j = 0; j < nsub; ++j) umma_bf16(acc + uint32_t(j * ncols), a_tap + uint64_t(j * sub_step), bdesc, idesc, accum);
+          const uint32_t sub_step = uint32_t(8 * span) >> 4;  // next 8-pixel patch column, in 16 B units
+          const uint64_t a0 = make_sdesc(stage_addr0 + uint32_t(s) * stage_bytes, 16, uint32_t(P * span), layout_type_of_span(span));
+          const uint64_t a_j0 = a0 + uint64_t(mw * sub_step), a_j1 = a0 + uint64_t((mw + kMmaWarps) * sub_step);
+          const uint32_t acc0 = acc + uint32_t(mw * ncols), acc1 = acc + uint32_t((mw + kMmaWarps) * ncols);
+          uint64_t b_t = make_sdesc(w_addr + uint32_t(wk8 * ncols * 16), uint32_t(ncols * 16), 128, 0);
+          const int R = taps == 9 ? 3 : 1;
+          uint32_t accum = c ? 1u : 0u;
+          uint32_t a_r = 0;
+          for (int r = 0; r < R; ++r, a_r += row_step) {
+            uint32_t a_t = a_r;
+            for (int sft = 0; sft < R; ++sft, a_t += px_step, b_t += b_tap_step) {
+              uint32_t a_k = a_t;
+              uint64_t b_k = b_t;
+              for (int ks = 0; ks < kslabs; ++ks, a_k += 2, b_k += b_ks_step) {
+                if (has0) umma_bf16(acc0, a_j0 + a_k, b_k, idesc, accum);
+                if (has1) umma_bf16(acc1, a_j1 + a_k, b_k, idesc, accum);
+                accum = 1u;
+              }
             }
           }
         }
@@ -366,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (elect_one()) umma_commit(&bar_acc_full[b]);
       __syncwarp();
     }
-  } else {
+  } else if (warp < 2 + kEpiWarps) {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
     // Two warps per TMEM lane quadrant; the (sub-tile, 16-column group) units of a tile alternate
     // between them.  The TMEM load of the next unit is in flight while the current one is processed.
@@ -381,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     e.H = p.H, e.W = p.W, e.cout = p.cout, e.head_classes = p.head_classes, e.out = p.out, e.heat = p.heat, e.logit = p.logit;
     e.drop_mask = p.drop_mask, e.drop_scale = p.drop_scale, e.addend = p.addend, e.relu_mask_src = p.relu_mask_src;
     e.stats_partial = p.stats_partial, e.stats_aux = p.stats_aux, e.aux_mean = p.aux_mean, e.aux_istd = p.aux_istd;
-    const int TW = p.TW, ncols = p.ncols, nsub = p.nsub, ntiles = p.ntiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y;
+    const int TW = p.TW, ncols = p.ncols, nsub = p.nsub, ntiles = p.ntiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y, dbg = p.dbg;
     float* const st1 = TRAIN ? &s_stats[TRAIN ? ew : 0][0][0] : nullptr;
     float* const st2 = TRAIN ? &s_stats[TRAIN ? ew : 0][1][0] : nullptr;
     int tile_it = 0;
@@ -393,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int y = ty * 16 + pi;
       const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * nsub * ncols);
       uint32_t raw[16];
-      int u = half;
+      int u = (dbg & 1) ? units : half;
       if (u < units) tmem_ld16(tbase + uint32_t(u * 16), raw);  // unit u covers columns [16u, 16u+16) of this accumulator set
       for (; u < units; u += 2) {
         tmem_ld_wait16(raw);
@@ -567,6 +588,10 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   p.stats_partial = a->stats_partial;
   p.stats_aux = reinterpret_cast<const __nv_bfloat16*>(a->stats_aux);
   p.aux_mean = a->aux_mean, p.aux_istd = a->aux_istd;
+  {
+    const char* d = getenv("UNPP_DBG");
+    p.dbg = d ? atoi(d) : 0;
+  }
 
   const bool deconv = a->mode == UNPP_MODE_DECONV, head = a->head_w != nullptr;
   const bool train = a->addend || a->relu_mask_src || a->stats_partial || a->logit || a->drop_mask;
