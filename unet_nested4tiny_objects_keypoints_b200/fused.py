@@ -21,7 +21,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from . import ops
+from . import ops, parallel
 from .training import TrainState, backward_train, flat_layout, forward_train, pack_train
 
 
@@ -181,7 +181,7 @@ class FusedTrainStep:
             if self.world == 1:
                 self._update()
         if self.world > 1:
-            torch.distributed.all_reduce(self.flat_g, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            parallel.allreduce_gradients(self.flat_g, self.pg)  # the step's only collective: 2.2 MB flat fp32 buffer
             if self.graph_b is not None:
                 self.graph_b.replay()
             else:
@@ -200,7 +200,4 @@ class FusedTrainStep:
         return self.ts.heats
 
 
-def broadcast_parameters(model, src: int = 0, process_group=None) -> None:
-    """Initial weight/buffer sync of the replicas (what nn.DataParallel's per-forward replicate does, trainer.py:338)."""
-    for t in list(model.parameters()) + list(model.buffers()):
-        torch.distributed.broadcast(t.data, src=src, group=process_group)
+broadcast_parameters = parallel.broadcast_parameters
