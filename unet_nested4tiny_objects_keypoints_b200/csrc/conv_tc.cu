@@ -18,7 +18,7 @@
 //   * epilogue warps read TMEM (tcgen05.ld 32x32b), apply bias / ReLU / ReLU-mask / addend, the
 //     fused 1x1 head + sigmoid, and store NHWC bf16 (and NCHW fp32 heatmaps).
 //
-// Warp roles: warp 0 = TMA producer, warps 1,10,11,12 = MMA issuers (warp 1 also allocates TMEM), warps 2..9 = epilogue
+// Warp roles: warp 0 = TMA producer, warps 1,10.. = MMA issuers (warp 1 also allocates TMEM), warps 2..9 = epilogue
 // (two per TMEM lane quadrant).  The kernel is compiled per epilogue variant (conv / deconv scatter,
 // fused head, training extras) so that the inference epilogue carries no run-time feature tests.
 #include <cstdlib>
@@ -33,8 +33,11 @@ namespace {
 constexpr int kMaxChunks = 8;
 constexpr int kMaxStages = 8;
 constexpr int kEpiWarps = 8;
-constexpr int kMmaWarps = 4;  // issuing threads: each owns the sub-tile accumulators j = i, i+4, ... (disjoint TMEM columns)
-constexpr int kThreads = 64 + 32 * kEpiWarps + 32 * (kMmaWarps - 1);  // TMA warp + MMA warp + epilogue warps + extra MMA warps
+// Issuing threads: each owns the sub-tile accumulators j = i, i+n, i+2n (disjoint TMEM columns).  The inference
+// variants (<= 108 registers) run four of them (416 threads); the training variants need up to 168 registers
+// and run three (384 threads).
+constexpr int mma_warps(bool train) { return train ? 3 : 4; }
+constexpr int block_threads(bool train) { return 64 + 32 * kEpiWarps + 32 * (mma_warps(train) - 1); }
 
 struct ConvTcParams {
   CUtensorMap maps[UNPP_MAX_SRC];
@@ -124,10 +127,41 @@ struct EpiArgs {
   const float* aux_istd;
 };
 
+// Training-only operands of one unit, fetched from global memory BEFORE the TMEM load is waited for.
+struct TrainOperands {
+  uint4 a0, a1, m0, m1, x0, x1;
+};
+template <bool TRAIN>
+__device__ __forceinline__ void prefetch_train(const EpiArgs& p, TrainOperands& t, size_t pix, int gcol, bool valid) {
+  if constexpr (TRAIN) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    t.a0 = t.a1 = t.m0 = t.m1 = t.x0 = t.x1 = z;
+    if (valid) {
+      const size_t off = pix * p.cout + gcol;
+      if (p.addend) {
+        const uint4* q = reinterpret_cast<const uint4*>(p.addend + off);
+        t.a0 = __ldg(q), t.a1 = __ldg(q + 1);
+      }
+      if (p.relu_mask_src) {
+        const uint4* q = reinterpret_cast<const uint4*>(p.relu_mask_src + off);
+        t.m0 = __ldg(q), t.m1 = __ldg(q + 1);
+      }
+      if (p.stats_aux) {
+        const uint4* q = reinterpret_cast<const uint4*>(p.stats_aux + off);
+        t.x0 = __ldg(q), t.x1 = __ldg(q + 1);
+      }
+    }
+  }
+}
+
+// Epilogue of one unit = one 16-column group of one 128-pixel sub-tile: v[16] are the fp32 accumulators
+// of this thread's pixel for GEMM columns [gcol, gcol+16).  Statistics (training): sa1 += value,
+// sa2 += value^2 or value*aux, per thread when reg_stats (reduced over the warp once per kernel),
+// else reduced over the warp here into the warp's shared-memory slots.
 template <bool DECONV, bool HEAD, bool TRAIN>
-__device__ __forceinline__ void epilogue_group(const EpiArgs& p, float (&v)[16], int n, int y, int x, bool valid, int gcol, int c0,
-                                               const float* s_bias, const float* s_head, float relu_floor, float* s_stats1, float* s_stats2,
-                                               int lane) {
+__device__ __forceinline__ void epilogue_group(const EpiArgs& p, float (&v)[16], const TrainOperands& t, int n, int y, int x, bool valid,
+                                               int gcol, int c0, const float* s_bias, const float* s_head, float relu_floor, bool reg_stats,
+                                               float (&sa1)[16], float (&sa2)[16], float* s_stats1, float* s_stats2, int lane) {
   {
     const float4* b4 = reinterpret_cast<const float4*>(s_bias + (DECONV ? gcol % p.cout : c0));
 #pragma unroll
@@ -151,10 +185,8 @@ __device__ __forceinline__ void epilogue_group(const EpiArgs& p, float (&v)[16],
   }
   const size_t pix = (size_t(n) * p.H + y) * p.W + x;
   if constexpr (TRAIN) {
-    if (p.addend && valid) {
-      const uint4* ap = reinterpret_cast<const uint4*>(p.addend + pix * p.cout + gcol);
-      uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
-      uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    if (p.addend) {
+      const uint32_t aw[8] = {t.a0.x, t.a0.y, t.a0.z, t.a0.w, t.a1.x, t.a1.y, t.a1.z, t.a1.w};
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[2 * k] += bf16_lo(aw[k]), v[2 * k + 1] += bf16_hi(aw[k]);
     }
@@ -162,10 +194,8 @@ __device__ __forceinline__ void epilogue_group(const EpiArgs& p, float (&v)[16],
 #pragma unroll
   for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], relu_floor);
   if constexpr (TRAIN) {
-    if (p.relu_mask_src && valid) {
-      const uint4* mp = reinterpret_cast<const uint4*>(p.relu_mask_src + pix * p.cout + gcol);
-      uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-      uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    if (p.relu_mask_src) {
+      const uint32_t mw[8] = {t.m0.x, t.m0.y, t.m0.z, t.m0.w, t.m1.x, t.m1.y, t.m1.z, t.m1.w};
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         if (!(bf16_lo(mw[k]) > 0.f)) v[2 * k] = 0.f;
@@ -173,32 +203,26 @@ __device__ __forceinline__ void epilogue_group(const EpiArgs& p, float (&v)[16],
       }
     }
     if (p.stats_partial) {
-      // Per-channel sums over this warp's 32 pixels (statistics of the bf16-rounded value that is
-      // stored; invalid pixels contribute 0).  Second statistic: v*v (BN batch variance) or
-      // v * xhat with xhat = (aux - mean) * istd (BN backward's dgamma).
+      // statistics of the bf16-rounded value that is stored; invalid pixels contribute 0.  Second
+      // statistic: v*v (BN batch variance) or v*aux (BN backward: sum dyh*z, turned into
+      // sum dyh*xhat = istd*(sum dyh*z - mean*sum dyh) when the CTA writes its partials).
       float s1[16], s2[16];
+      const uint32_t xw[8] = {t.x0.x, t.x0.y, t.x0.z, t.x0.w, t.x1.x, t.x1.y, t.x1.z, t.x1.w};
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const float r = valid ? __bfloat162float(__float2bfloat16_rn(v[k])) : 0.f;
-        s1[k] = r, s2[k] = r * r;
+        const float aux = (k & 1) ? bf16_hi(xw[k >> 1]) : bf16_lo(xw[k >> 1]);
+        s1[k] = r, s2[k] = r * (p.stats_aux ? aux : r);
       }
-      if (p.stats_aux) {
-        uint32_t xw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (valid) {
-          const uint4* xp = reinterpret_cast<const uint4*>(p.stats_aux + pix * p.cout + gcol);
-          const uint4 x0 = __ldg(xp), x1 = __ldg(xp + 1);
-          xw[0] = x0.x, xw[1] = x0.y, xw[2] = x0.z, xw[3] = x0.w, xw[4] = x1.x, xw[5] = x1.y, xw[6] = x1.z, xw[7] = x1.w;
-        }
+      if (reg_stats) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          s2[2 * k] = s1[2 * k] * (bf16_lo(xw[k]) - __ldg(p.aux_mean + gcol + 2 * k)) * __ldg(p.aux_istd + gcol + 2 * k);
-          s2[2 * k + 1] = s1[2 * k + 1] * (bf16_hi(xw[k]) - __ldg(p.aux_mean + gcol + 2 * k + 1)) * __ldg(p.aux_istd + gcol + 2 * k + 1);
+        for (int k = 0; k < 16; ++k) sa1[k] += s1[k], sa2[k] += s2[k];
+      } else {
+        const float r1 = warp_reduce16(s1, lane), r2 = warp_reduce16(s2, lane);
+        if ((lane & 1) == 0) {  // lane holds channel (lane >> 1); each warp owns its own slots
+          s_stats1[c0 + (lane >> 1)] += r1;
+          s_stats2[c0 + (lane >> 1)] += r2;
         }
-      }
-      const float r1 = warp_reduce16(s1, lane), r2 = warp_reduce16(s2, lane);
-      if ((lane & 1) == 0) {  // lane holds channel (lane >> 1); each warp owns its own slots
-        s_stats1[c0 + (lane >> 1)] += r1;
-        s_stats2[c0 + (lane >> 1)] += r2;
       }
     }
   }
@@ -240,7 +264,8 @@ __device__ __forceinline__ void epilogue_group(const EpiArgs& p, float (&v)[16],
 }
 
 template <bool DECONV, bool HEAD, bool TRAIN>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+__global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  constexpr int kMmaWarps = mma_warps(TRAIN), kThreads = block_threads(TRAIN);
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_acc_full[2], bar_acc_empty[2], bar_w;
   __shared__ uint32_t tmem_base_slot;
@@ -322,11 +347,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
   } else if (warp == 1 || warp >= 2 + kEpiWarps) {
-    // ------------------------------------------------------------------ MMA issuers (warps 1, 10, 11, 12)
+    // ------------------------------------------------------------------ MMA issuers (warp 1 and warps 10..)
     // One thread can only sustain ~1 MMA per 85 cycles through the uniform datapath (measured: the
-    // tensor pipe takes ~40); four issuing threads, each with its own accumulators, remove that limit.
+    // tensor pipe takes ~40); three or four issuing threads, each with its own accumulators, remove that limit.
     const int mw = warp == 1 ? 0 : warp - (1 + kEpiWarps);
-    const bool has0 = mw < p.nsub, has1 = mw + kMmaWarps < p.nsub;
+    const bool has0 = mw < p.nsub, has1 = mw + kMmaWarps < p.nsub, has2 = mw + 2 * kMmaWarps < p.nsub;
     // every kernel parameter used below is copied to a register first: the loop must not touch
     // the parameter bank between MMA issues
     mbar_wait(&bar_w, 0);
@@ -361,8 +386,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const uint32_t b_tap_step = uint32_t(k8_total * ncols * 16) >> 4, b_ks_step = uint32_t(2 * ncols * 16) >> 4;
           const uint32_t sub_step = uint32_t(8 * span) >> 4;  // next 8-pixel patch column, in 16 B units
           const uint64_t a0 = make_sdesc(stage_addr0 + uint32_t(s) * stage_bytes, 16, uint32_t(P * span), layout_type_of_span(span));
-          const uint64_t a_j0 = a0 + uint64_t(mw * sub_step), a_j1 = a0 + uint64_t((mw + kMmaWarps) * sub_step);
-          const uint32_t acc0 = acc + uint32_t(mw * ncols), acc1 = acc + uint32_t((mw + kMmaWarps) * ncols);
+          const uint64_t a_j0 = a0 + uint64_t(mw * sub_step), a_j1 = a0 + uint64_t((mw + kMmaWarps) * sub_step),
+                         a_j2 = a0 + uint64_t((mw + 2 * kMmaWarps) * sub_step);
+          const uint32_t acc0 = acc + uint32_t(mw * ncols), acc1 = acc + uint32_t((mw + kMmaWarps) * ncols),
+                         acc2 = acc + uint32_t((mw + 2 * kMmaWarps) * ncols);
           uint64_t b_t = make_sdesc(w_addr + uint32_t(wk8 * ncols * 16), uint32_t(ncols * 16), 128, 0);
           const int R = taps == 9 ? 3 : 1;
           uint32_t accum = c ? 1u : 0u;
@@ -375,6 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               for (int ks = 0; ks < kslabs; ++ks, a_k += 2, b_k += b_ks_step) {
                 if (has0) umma_bf16(acc0, a_j0 + a_k, b_k, idesc, accum);
                 if (has1) umma_bf16(acc1, a_j1 + a_k, b_k, idesc, accum);
+                if (has2) umma_bf16(acc2, a_j2 + a_k, b_k, idesc, accum);
                 accum = 1u;
               }
             }
@@ -405,6 +433,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int TW = p.TW, ncols = p.ncols, nsub = p.nsub, ntiles = p.ntiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y, dbg = p.dbg;
     float* const st1 = TRAIN ? &s_stats[TRAIN ? ew : 0][0][0] : nullptr;
     float* const st2 = TRAIN ? &s_stats[TRAIN ? ew : 0][1][0] : nullptr;
+    // with <= 2 column groups every unit of this warp has the same 16 channels: keep the statistics in registers
+    const bool reg_stats = TRAIN && ncb <= 2;
+    float sa1[16], sa2[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sa1[k] = 0.f, sa2[k] = 0.f;
     int tile_it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
       const int b = tile_it & 1, aph = (tile_it >> 1) & 1;
@@ -417,19 +450,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       int u = (dbg & 1) ? units : half;
       if (u < units) tmem_ld16(tbase + uint32_t(u * 16), raw);  // unit u covers columns [16u, 16u+16) of this accumulator set
       for (; u < units; u += 2) {
+        const int j = u / ncb, c0 = (u % ncb) * 16;
+        const int x = tx * TW + j * 8 + pj;
+        const bool valid = (y < e.H) && (x < e.W);
+        TrainOperands tops;
+        prefetch_train<TRAIN>(e, tops, (size_t(n) * e.H + y) * e.W + x, ntile_idx * ncols + c0, valid);
         tmem_ld_wait16(raw);
         float v[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(raw[k]);
         if (u + 2 < units) tmem_ld16(tbase + uint32_t((u + 2) * 16), raw);
-        const int j = u / ncb, c0 = (u % ncb) * 16;
-        const int x = tx * TW + j * 8 + pj;
-        const bool valid = (y < e.H) && (x < e.W);
-        epilogue_group<DECONV, HEAD, TRAIN>(e, v, n, y, x, valid, ntile_idx * ncols + c0, c0, s_bias, s_head, relu_floor, st1, st2, lane);
+        epilogue_group<DECONV, HEAD, TRAIN>(e, v, tops, n, y, x, valid, ntile_idx * ncols + c0, c0, s_bias, s_head, relu_floor, reg_stats, sa1, sa2,
+                                            st1, st2, lane);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+    }
+    if constexpr (TRAIN) {
+      if (reg_stats && e.stats_partial) {
+        const int c0w = (half % ncb) * 16;  // u = half + 2i  =>  u % ncb is constant for ncb in {1, 2}
+        const float r1 = warp_reduce16(sa1, lane), r2 = warp_reduce16(sa2, lane);
+        if ((lane & 1) == 0) st1[c0w + (lane >> 1)] += r1, st2[c0w + (lane >> 1)] += r2;
+      }
     }
   }
 
@@ -445,6 +488,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         float t = 0.f;
 #pragma unroll
         for (int wv = 0; wv < kEpiWarps; ++wv) t += s_stats[TRAIN ? wv : 0][st][TRAIN ? ch : 0];
+        if (st == 1 && p.stats_aux) {  // sum dyh*xhat = istd * (sum dyh*z - mean * sum dyh)
+          float t1 = 0.f;
+#pragma unroll
+          for (int wv = 0; wv < kEpiWarps; ++wv) t1 += s_stats[TRAIN ? wv : 0][0][TRAIN ? ch : 0];
+          const int gc = ntile_idx * p.ncols + ch;
+          t = __ldg(p.aux_istd + gc) * (t - __ldg(p.aux_mean + gc) * t1);
+        }
         p.stats_partial[(size_t(blockIdx.x) * 2 + st) * p.cout + ntile_idx * p.ncols + ch] = t;
       }
     }
@@ -606,7 +656,7 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
         return unpp::fail_cuda("conv_tc: cudaFuncSetAttribute");                                                                      \
       opted_in = 1;                                                                                                                   \
     }                                                                                                                                 \
-    conv_tc_kernel<D, Hd, T><<<grid, kThreads, pl.smem_total, stream>>>(p);                                                           \
+    conv_tc_kernel<D, Hd, T><<<grid, block_threads(T), pl.smem_total, stream>>>(p);                                                           \
   } while (0)
   if (deconv) UNPP_LAUNCH(true, false, false);
   else if (head && train) UNPP_LAUNCH(false, true, true);

@@ -10,16 +10,15 @@
 // CTA (the output is tiny: 9*Cin*Cout), so HBM traffic is one read of X and dZ; the per-CTA result
 // goes to a partial buffer reduced in fixed order by unpp_wgrad_reduce (deterministic).
 //
-// Tensor-core path: warp-level mma (wmma m16n16k16 bf16 -> fp32).  The pixel dimension is K, so
-// the X tile [pixel][ci] is the column-major A operand and the dZ tile [pixel][co] the row-major
-// B operand — no transposes are materialised.
+// Tensor-core path: warp-level mma.sync m16n8k16 (bf16 -> fp32).  The pixel dimension is K, so both
+// operands are needed 'transposed' relative to the NHWC tiles: ldmatrix.trans delivers the X tile
+// [pixel][ci] as the A fragment and the dZ tile [pixel][co] as the B fragment straight from the
+// swizzled TMA tiles — no transposes are materialised and the loads are bank-conflict free.
 #include "sm100.cuh"
 #include "common.h"
 #include "../../include/unpp.h"
-#include <mma.h>
 
 using namespace sm100;
-using namespace nvcuda;
 
 namespace {
 
@@ -38,17 +37,30 @@ struct WgradParams {
   float* partial;
 };
 
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// TMA writes the tiles with the hardware swizzle of their row width (conflict-free ldmatrix):
+// the 16-byte chunk index inside a row is XORed with address bits [7, 7+log2(span/16)).
+__device__ __forceinline__ uint32_t swz(uint32_t addr, uint32_t mask) { return addr ^ (((addr >> 7) & mask) << 4); }
+
 template <int TAPS, int PPW>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ uint64_t bar_full[2];
-  uint8_t* const smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  const int warp = threadIdx.x >> 5;
+  uint8_t* const smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int job = blockIdx.y;
   const int cs = p.job_cs[job], con = p.job_con[job];
   const int nco = con >> 4, npairs = (cs >> 4) * nco;
-  const int PX = TC + 2 * p.pad, PY = TR + 2 * p.pad;
-  const int stage_bytes = p.xstage_bytes + p.zstage_bytes;
+  const int pad = p.pad, PX = TC + 2 * pad, PY = TR + 2 * pad;
+  const int stage_bytes = p.xstage_bytes + p.zstage_bytes, xstage_bytes = p.xstage_bytes;
+  const int ntiles = p.ntiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y;
 
   if (threadIdx.x == 0) {
     mbar_init(&bar_full[0], 1);
@@ -60,15 +72,15 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   __syncthreads();
 
   auto issue = [&](int tile, int buf) {
-    const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
     uint8_t* xs = smem + size_t(buf) * stage_bytes;
-    uint8_t* zs = xs + p.xstage_bytes;
+    uint8_t* zs = xs + xstage_bytes;
     mbar_arrive_expect_tx(&bar_full[buf], uint32_t(PY * PX * cs * 2 + TR * TC * con * 2));
-    tma_load_4d(&p.xmap[p.job_map[job]], &bar_full[buf], xs, p.job_c0[job], tx * TC - p.pad, ty * TR - p.pad, n);
+    tma_load_4d(&p.xmap[p.job_map[job]], &bar_full[buf], xs, p.job_c0[job], tx * TC - pad, ty * TR - pad, n);
     tma_load_4d(&p.zmap, &bar_full[buf], zs, p.job_co0[job], tx * TC, ty * TR, n);
   };
 
-  // fragment ownership
+  // fragment ownership: a warp owns ppw_job (tap x 16ci x 16co) fragment sets that share the ci block
   int pair0, row0, row_step;
   const int ppw_job = npairs >= 8 ? npairs / 8 : 1;  // <= PPW
   if (npairs >= 8) {
@@ -76,37 +88,52 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   } else {
     pair0 = warp % npairs, row0 = warp / npairs, row_step = 8 / npairs;
   }
+  const int cb = pair0 / nco, ob0 = pair0 % nco;  // pairs pair0 .. pair0+ppw_job-1 have the same cb (nco is even when ppw_job = 2)
 
-  wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[PPW][TAPS];
+  // per-lane ldmatrix row addresses (bytes inside a tile, before the row / tap / k-step offsets)
+  const int lt = lane >> 3, li = lane & 7;
+  const uint32_t a_lane = uint32_t((li + 8 * (lt >> 1)) * cs + cb * 16 + 8 * (lt & 1)) * 2;      // A = X^T: k = pixel, m = ci
+  const uint32_t b_lane = uint32_t((li + 8 * (lt & 1)) * con + ob0 * 16 + 8 * (lt >> 1)) * 2;   // B = dZ:  k = pixel, n = co
+  const uint32_t xmask = uint32_t(cs * 2 / 16 - 1) & 7u, zmask = uint32_t(con * 2 / 16 - 1) & 7u;
+  const uint32_t x_px = uint32_t(cs * 2), z_px = uint32_t(con * 2);
+  const uint32_t smem_base = smem_u32(smem);
+
+  float acc[PPW][TAPS][2][4];
 #pragma unroll
   for (int j = 0; j < PPW; ++j)
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) wmma::fill_fragment(acc[j][t], 0.f);
+    for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][t][h][e] = 0.f;
 
-  if (threadIdx.x == 0 && int(blockIdx.x) < p.ntiles) issue(blockIdx.x, 0);
+  if (threadIdx.x == 0 && int(blockIdx.x) < ntiles) issue(blockIdx.x, 0);
   int it = 0;
-  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
-    if (threadIdx.x == 0 && tile + int(gridDim.x) < p.ntiles) issue(tile + gridDim.x, buf ^ 1);
+    if (threadIdx.x == 0 && tile + int(gridDim.x) < ntiles) issue(tile + gridDim.x, buf ^ 1);
     mbar_wait(&bar_full[buf], (it >> 1) & 1);
-    const __nv_bfloat16* xs = reinterpret_cast<const __nv_bfloat16*>(smem + size_t(buf) * stage_bytes);
-    const __nv_bfloat16* zs = reinterpret_cast<const __nv_bfloat16*>(smem + size_t(buf) * stage_bytes + p.xstage_bytes);
+    const uint32_t xs = smem_base + uint32_t(buf) * stage_bytes, zs = xs + xstage_bytes;
     for (int row = row0; row < TR; row += row_step) {
 #pragma unroll
       for (int kk = 0; kk < TC / 16; ++kk) {
         const int x0 = kk * 16;
+        uint32_t fb[PPW][4];
 #pragma unroll
-        for (int j = 0; j < PPW; ++j) {
-          if (j >= ppw_job) break;
-          const int pair = pair0 + j, cb = pair / nco, ob = pair % nco;
-          wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fb;
-          wmma::load_matrix_sync(fb, zs + (row * TC + x0) * con + ob * 16, con);
+        for (int j = 0; j < PPW; ++j)
+          if (j < ppw_job) ldsm_x4_trans(swz(zs + uint32_t(row * TC + x0) * z_px + b_lane + uint32_t(j * 32), zmask), fb[j]);
 #pragma unroll
-          for (int t = 0; t < TAPS; ++t) {
-            const int r = TAPS == 9 ? t / 3 : 0, s = TAPS == 9 ? t % 3 : 0;
-            wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::col_major> fa;
-            wmma::load_matrix_sync(fa, xs + ((row + r) * PX + x0 + s) * cs + cb * 16, cs);
-            wmma::mma_sync(acc[j][t], fa, fb, acc[j][t]);
+        for (int t = 0; t < TAPS; ++t) {
+          const int r = TAPS == 9 ? t / 3 : 0, s = TAPS == 9 ? t % 3 : 0;
+          uint32_t fa[4];
+          ldsm_x4_trans(swz(xs + uint32_t((row + r) * PX + x0 + s) * x_px + a_lane, xmask), fa);
+#pragma unroll
+          for (int j = 0; j < PPW; ++j) {
+            if (j < ppw_job) {
+              mma_16816(acc[j][t][0], fa, fb[j][0], fb[j][1]);
+              mma_16816(acc[j][t][1], fa, fb[j][2], fb[j][3]);
+            }
           }
         }
       }
@@ -114,12 +141,22 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     __syncthreads();  // everyone is done with `buf` before it is refilled two iterations later
   }
 
-  // stage the fragments in shared memory, then sum the warps that share a pair in a fixed order
+  // stage the fragments in shared memory ([frag][16 ci][16 co] fp32), then sum the warps that share a pair in a fixed order
   float* stage_f = reinterpret_cast<float*>(smem);
+  {
+    const int g = lane >> 2, c2 = (lane & 3) * 2;
 #pragma unroll
-  for (int j = 0; j < PPW; ++j)
+    for (int j = 0; j < PPW; ++j)
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) wmma::store_matrix_sync(stage_f + ((warp * PPW + j) * TAPS + t) * 256, acc[j][t], 16, wmma::mem_row_major);
+      for (int t = 0; t < TAPS; ++t) {
+        float* f = stage_f + ((warp * PPW + j) * TAPS + t) * 256;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          *reinterpret_cast<float2*>(f + g * 16 + h * 8 + c2) = make_float2(acc[j][t][h][0], acc[j][t][h][1]);
+          *reinterpret_cast<float2*>(f + (g + 8) * 16 + h * 8 + c2) = make_float2(acc[j][t][h][2], acc[j][t][h][3]);
+        }
+      }
+  }
   __syncthreads();
   const int nout = TAPS * cs * con;
   const int wpp = npairs >= 8 ? 1 : 8 / npairs;
@@ -189,11 +226,11 @@ int make_plan(const UnppWgradArgs* a, Plan* pl) {
   pl->ppw = max_pairs > 8 ? 2 : 1;
   pl->pad = a->taps == 9 ? 1 : 0;
   const int PX = TC + 2 * pl->pad, PY = TR + 2 * pl->pad;
-  pl->xstage_bytes = (PY * PX * max_cs * 2 + 127) / 128 * 128;
-  pl->zstage_bytes = (TR * TC * max_con * 2 + 127) / 128 * 128;
+  pl->xstage_bytes = (PY * PX * max_cs * 2 + 1023) / 1024 * 1024;  // 1 KB granules keep every tile on the swizzle pattern period
+  pl->zstage_bytes = (TR * TC * max_con * 2 + 1023) / 1024 * 1024;
   const int pipe = 2 * (pl->xstage_bytes + pl->zstage_bytes);
   const int staging = 8 * pl->ppw * a->taps * 256 * 4;
-  pl->smem_total = 128 + (pipe > staging ? pipe : staging);
+  pl->smem_total = 1024 + (pipe > staging ? pipe : staging);
   pl->tiles_x = (a->W + TC - 1) / TC, pl->tiles_y = (a->H + TR - 1) / TR;
   pl->ntiles = pl->tiles_x * pl->tiles_y * a->N;
   int gx = unpp::num_sms() / nj;
@@ -239,9 +276,10 @@ extern "C" int unpp_wgrad(const UnppWgradArgs* a, unpp_stream_t stream_) {
     const cuuint64_t C = a->src_C[i];
     cuuint64_t gd[4] = {C, cuuint64_t(a->W), cuuint64_t(a->H), cuuint64_t(a->N)};
     cuuint64_t gs[3] = {C * 2, cuuint64_t(a->W) * C * 2, cuuint64_t(a->H) * a->W * C * 2};
-    cuuint32_t box[4] = {cuuint32_t(C < 64 ? C : 64), cuuint32_t(PX), cuuint32_t(PY), 1};
+    const int bc = C < 64 ? int(C) : 64;
+    cuuint32_t box[4] = {cuuint32_t(bc), cuuint32_t(PX), cuuint32_t(PY), 1};
     CUresult r = enc(&p.xmap[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->src[i]), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     bc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled failed (CUresult %d) for source %d", int(r), i);
   }
   {
@@ -253,7 +291,7 @@ extern "C" int unpp_wgrad(const UnppWgradArgs* a, unpp_stream_t stream_) {
     const int con = a->cout < 64 ? a->cout : 64;
     cuuint32_t box[4] = {cuuint32_t(con), cuuint32_t(TC), cuuint32_t(TR), 1};
     CUresult r = enc(&p.zmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<uint8_t*>(base), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     con == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : con == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled failed (CUresult %d) for dZ", int(r));
   }
   p.njobs = pl.njobs;

@@ -37,7 +37,9 @@ def _engine(model, device):
 class InferenceSession:
     """Fixed-shape inference + keypoint extraction.  ``run(x_host)`` copies the batch to the device,
     replays the captured forward + arg-max and returns ``(xy int32 [B,C,2], peak fp32 [B,C])`` on the
-    device; ``heat`` holds the heat maps of the selected head."""
+    device; ``heat`` holds the heat maps of the selected head.  ``run_many`` streams a sequence of
+    host batches through two input buffers so that the H2D copy of batch k+1 overlaps the kernels
+    of batch k (the activation arena is shared: compute is serial on one stream)."""
 
     def __init__(self, model, B: int, H: int, W: int, head: int = 2, device="cuda", use_graph: bool = True):
         self.model, self.head = model, head
@@ -45,42 +47,106 @@ class InferenceSession:
         self.eng = _engine(model, self.dev)
         if model.training:
             raise RuntimeError("InferenceSession needs model.eval()")
-        self.x = torch.zeros(B, model.in_channels, H, W, dtype=torch.float32, device=self.dev)
-        self.graph = None
-        self.launches = 0
+        self.B = B
+        self.xs = [torch.zeros(B, model.in_channels, H, W, dtype=torch.float32, device=self.dev) for _ in range(2)]
+        self.out = [None, None]
+        self.graphs = [None, None]
         with torch.no_grad(), torch.cuda.device(self.dev):
-            self._body()  # warm-up: packs weights, allocates the activation arena
+            n0 = ops.launch_count
+            self._body(0)  # warm-up: packs weights, allocates the activation arena
+            self.launches = ops.launch_count - n0 - self._pack_launches
             torch.cuda.synchronize()
             if use_graph:
                 s = torch.cuda.Stream()
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
-                    self._body()
+                    self._body(0)
                 torch.cuda.current_stream().wait_stream(s)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._body()
-                self.graph = g
-        # nchw->nhwc, 8 encoder convs, 3 pools, 6 x (deconv + 2 convs), arg-max
-        self.launches = 1 + 8 + 3 + 18 + 1
+                for i in range(2):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._body(i)
+                    self.graphs[i] = g
+            else:
+                self._body(1)
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
 
-    def _body(self):
-        heats = self.eng.forward_eval(self.x, heads=(self.head,))
-        self.heat = heats[self.head]
-        self.xy, self.val = ops.argmax_peaks(self.heat)
+    # kernels per pass: nchw->nhwc, 8 encoder convs, 3 pools, 6 x (deconv + 2 convs), arg-max = 31
+    def _body(self, i: int):
+        n0 = ops.launch_count
+        P = self.eng.packed_eval()
+        self._pack_launches = ops.launch_count - n0
+        heats = self.eng.forward_eval(self.xs[i], heads=(self.head,))
+        xy, val = ops.argmax_peaks(heats[self.head])
+        self.out[i] = (xy, val, heats[self.head])
 
-    def run_device(self):
-        """Inputs already in ``self.x`` (device): one pass of the hot path."""
-        if self.graph is not None:
-            self.graph.replay()
+    @property
+    def x(self):
+        return self.xs[0]
+
+    @property
+    def graph(self):
+        return self.graphs[0]
+
+    @property
+    def heat(self):
+        return self.out[0][2]
+
+    @property
+    def xy(self):
+        return self.out[0][0]
+
+    @property
+    def val(self):
+        return self.out[0][1]
+
+    def run_device(self, i: int = 0):
+        """Inputs already in ``self.xs[i]`` (device): one pass of the hot path."""
+        if self.graphs[i] is not None:
+            self.graphs[i].replay()
         else:
             with torch.no_grad():
-                self._body()
-        return self.xy, self.val
+                self._body(i)
+        return self.out[i][0], self.out[i][1]
 
     def run(self, x_host: torch.Tensor):
-        self.x.copy_(x_host, non_blocking=True)
-        return self.run_device()
+        self.xs[0].copy_(x_host, non_blocking=True)
+        return self.run_device(0)
+
+    def run_many(self, host_batches, xy_host=None, val_host=None):
+        """Pipelined: for every (pinned) host batch, H2D -> forward + arg-max -> D2H of the keypoints.
+        ``xy_host`` / ``val_host``: optional lists of pinned host tensors receiving the results.
+        Returns after everything is enqueued; the caller synchronises the current stream."""
+        cur = torch.cuda.current_stream(self.dev)
+        cs = self.copy_stream
+        cs.wait_stream(cur)
+        h2d = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [None, None]
+        n = len(host_batches)
+
+        def prefetch(k):
+            i = k & 1
+            with torch.cuda.stream(cs):
+                if done[i] is not None:
+                    cs.wait_event(done[i])  # the graph that last read this buffer has finished
+                self.xs[i].copy_(host_batches[k], non_blocking=True)
+                h2d[i].record(cs)
+
+        if n:
+            prefetch(0)
+        for k in range(n):
+            i = k & 1
+            if k + 1 < n:
+                prefetch(k + 1)
+            cur.wait_event(h2d[i])
+            xy, val = self.run_device(i)
+            if xy_host is not None:
+                xy_host[k].copy_(xy, non_blocking=True)
+            if val_host is not None:
+                val_host[k].copy_(val, non_blocking=True)
+            done[i] = torch.cuda.Event()
+            done[i].record(cur)
+        return n
 
 
 class FusedTrainStep:
