@@ -78,6 +78,10 @@ typedef struct UnppConvArgs {
   const void* stats_aux;        /* NHWC bf16 like out, or NULL (then second stat = sum v*v)       */
   const float* aux_mean;        /* with stats_aux: second stat = sum v * (aux - mean[c]) * istd[c]*/
   const float* aux_istd;
+  /* 2x2 output blocking (3x3 conv, every source C = 16, n_total = 16, even H and W): one GEMM row is a
+   * 2x2 pixel block, N = 4*16, K walks the 4x4 input window -> 16 instead of 36 MMAs per 512 pixels.
+   * wpacked must then be packed with kind 4 (forward) or 5 (dgrad), taps = 16, n_total = n_tile = 64. */
+  int32_t block2x2;
 } UnppConvArgs;
 
 const char* unpp_last_error(void);
@@ -97,6 +101,9 @@ int unpp_conv_grid(const UnppConvArgs* a);
  *  kind 2: deconv forward B[n=(2p+q)*Cout+co][0][k=ci] = Wd[ci][co][p][q]; src [Cin][Cout][2][2]
  *  kind 3: deconv dgrad   (one pointwise GEMM per (p,q) tap over the up-resolution gradient)
  *          B[n=ci][tap=2p+q][k=co] = Wd[ci][co][p][q]
+ *  kind 4: 2x2-blocked forward conv (taps = 16 window positions dy*4+dx, n = (2*jy+jx)*16 + co):
+ *          B[n][pos][k=ci] = W[co][k_begin+ci][dy-jy][dx-jx] * scale[co] if both offsets are in 0..2, else 0
+ *  kind 5: 2x2-blocked dgrad: B[n=(2*jy+jx)*16+ci][pos][k=co] = W[k_begin+co][n_begin+ci][2-(dy-jy)][2-(dx-jx)] or 0
  * k_dst8 places the K range at 8-channel chunk offset k_dst8 inside a K/8 = k8_total wide buffer,
  * so that several sources (concat) or several consumers (dgrad gather) share one packed tensor. */
 typedef struct UnppPackArgs {

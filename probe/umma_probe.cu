@@ -609,7 +609,7 @@ static void p2_case(int lt, int N, long long* dc) {
 // swizzle atom (8 rows x span)?  The production conv shifts the start by whole pixels (= span bytes)
 // and whole tile rows (P*span bytes) to select a filter tap; B is the no-swizzle packed weight tile.
 __global__ void __launch_bounds__(128, 1) k_mma_rate3(uint32_t idesc, int n_iter, uint32_t a_off, uint32_t sbo, uint32_t lt, uint32_t j_step,
-                                                      int ncol, long long* cycles) {
+                                                      int ncol, long long* cycles, uint32_t b_step = 0, int nacc = 8, uint32_t b_off = 64 * 1024) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
@@ -628,13 +628,14 @@ __global__ void __launch_bounds__(128, 1) k_mma_rate3(uint32_t idesc, int n_iter
   tc_fence_after();
   const uint32_t tb = tmem_base, base = smem_u32(smem);
   if (threadIdx.x < 32) {
-    const uint64_t bdesc = make_sdesc(base + 96 * 1024, uint32_t(ncol * 16), 128, 0);
+    const uint64_t bdesc = make_sdesc(base + b_off, uint32_t(ncol * 16), 128, 0);
     const uint64_t adesc0 = make_sdesc(base + a_off, 16, sbo, lt);
     long long t0 = clock64();
     for (int it = 0; it < n_iter; ++it) {
       if (elect_one()) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) umma_bf16(tb + u * ncol, adesc0 + uint64_t((u * j_step) >> 4), bdesc, idesc, it > 0 ? 1u : 0u);
+        for (int u = 0; u < 8; ++u)
+          umma_bf16(tb + (u % nacc) * ncol, adesc0 + uint64_t((u * j_step) >> 4), bdesc + uint64_t((u * b_step) >> 4), idesc, (it > 0 || u >= nacc) ? 1u : 0u);
       }
       __syncwarp();
     }
@@ -646,6 +647,24 @@ __global__ void __launch_bounds__(128, 1) k_mma_rate3(uint32_t idesc, int n_iter
   }
   __syncthreads();
   if (threadIdx.x < 32) tmem_dealloc(tb, 512);
+}
+
+static void test_p4() {
+  long long* dc;
+  CK(cudaMalloc(&dc, 8));
+  CK(cudaFuncSetAttribute(k_mma_rate3, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int NIT = 256;
+  for (int N : {16, 64})
+    for (uint32_t a_off : {0u, 40u * 1024u, 100u * 1024u})
+      for (uint32_t b_off : {48u * 1024u, 64u * 1024u, 80u * 1024u, 96u * 1024u, 97u * 1024u, 112u * 1024u, 160u * 1024u}) {
+        const int span = N == 16 ? 32 : 64;
+        k_mma_rate3<<<148, 128, 200 * 1024>>>(make_idesc_bf16(128, N), NIT, a_off, span == 32 ? 66 * 32 : 2304, span == 32 ? 6 : 4, 8 * span, N, dc, N == 64 ? 2048u : 512u, N == 64 ? 2 : 8, b_off);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        long long cy;
+        CK(cudaMemcpy(&cy, dc, 8, cudaMemcpyDeviceToHost));
+        printf("RESULT p4 N=%2d A at %3u KB, B at %3u KB (B steps per MMA): %.1f cycles/MMA PASS\n", N, a_off / 1024, b_off / 1024, double(cy) / (NIT * 8));
+      }
 }
 
 static void test_p3() {
@@ -663,7 +682,10 @@ static void test_p3() {
       {"swz64 start+1px sbo=66px", 64, 64, 66 * 64, 32},         {"swz64 aligned sbo=72px", 64, 0, 72 * 64, 32},
       {"swz128 aligned dense (sbo=1024)", 128, 0, 1024, 64},     {"swz128 start+1px dense", 128, 128, 1024, 64},
       {"swz128 start+1px sbo=34px", 128, 128, 34 * 128, 64},     {"swz128 aligned sbo=40px", 128, 0, 40 * 128, 64},
-      {"swz128 aligned sbo=40px N=192", 128, 0, 40 * 128, 192},  {"swz128 aligned dense N=128", 128, 0, 1024, 128},
+      {"swz64 aligned dense N=64", 64, 0, 512, 64},              {"swz64 half-row start dense N=64", 64, 32, 512, 64},
+      {"swz64 aligned sbo=2304 N=64", 64, 0, 2304, 64},          {"swz64 half-row sbo=2304 N=64", 64, 32, 2304, 64},
+      {"swz64 half-row sbo=2368 N=64", 64, 32, 2368, 64},        {"swz64 half-row sbo=2304 N=32", 64, 32, 2304, 32},
+      {"swz32 aligned dense N=64", 32, 0, 256, 64},              {"swz32 sbo=66px N=64", 32, 32, 66 * 32, 64},
   };
   for (const Case& c : cases) {
     const uint32_t lt = c.span == 128 ? 2 : c.span == 64 ? 4 : 6;
@@ -671,6 +693,17 @@ static void test_p3() {
       continue;
     }
     k_mma_rate3<<<148, 128, 128 * 1024>>>(make_idesc_bf16(128, c.N), NIT, c.a_off, c.sbo, lt, 8 * c.span, c.N, dc);
+    if (c.N == 64 && c.span == 64 && c.a_off == 32 && c.sbo == 2304) {  // the 2x2-blocked production pattern: B changes every MMA, 2 accumulators
+      for (int variant = 0; variant < 3; ++variant) {
+        CK(cudaDeviceSynchronize());
+        k_mma_rate3<<<148, 128, 128 * 1024>>>(make_idesc_bf16(128, 64), NIT, 32, 2304, lt, variant == 2 ? 32u : 8 * 64u, 64, dc, variant >= 1 ? 2048u : 0u, 2);
+        CK(cudaDeviceSynchronize());
+        long long cy;
+        CK(cudaMemcpy(&cy, dc, 8, cudaMemcpyDeviceToHost));
+        printf("RESULT p3   variant %d (B step %s, 2 accumulators, A step %s)  %.1f cycles/MMA  PASS\n", variant, variant >= 1 ? "2KB" : "0", variant == 2 ? "32B" : "512B",
+               double(cy) / (NIT * 8));
+      }
+    }
     CK(cudaGetLastError());
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -769,6 +802,7 @@ int main(int argc, char** argv) {
   else if (t == "p1") test_p1();
   else if (t == "p2") test_p2();
   else if (t == "p3") test_p3();
+  else if (t == "p4") test_p4();
   else if (t == "m8") {
     test_m8(32);
     test_m8(64);

@@ -361,3 +361,67 @@ def test_bad_arguments_return_errors_not_crashes():
         ops.conv([x], 1, 8, 8, wp, 16, 16, 9, out=torch.empty(1, 8, 8, 16, dtype=torch.bfloat16, device=DEV))
     with pytest.raises(UnppError):
         ops.maxpool(torch.zeros(1, 7, 8, 16, dtype=torch.bfloat16, device=DEV), torch.zeros(1, 3, 4, 16, dtype=torch.bfloat16, device=DEV))
+
+
+# ---------------------------------------------------------------------------------------------- 2x2 output-blocked conv (16-channel levels)
+@pytest.mark.parametrize("N,H,W,nsrc", [(2, 32, 32, 1), (1, 24, 40, 2), (3, 64, 64, 3), (1, 8, 8, 4), (2, 16, 48, 4), (1, 128, 96, 1)])
+def test_conv3x3_block2x2_forward(N, H, W, nsrc):
+    cin = 16 * nsrc
+    xs = [bf(rnd(N, 16, H, W, seed=i + 101)) for i in range(nsrc)]
+    w = bf(rnd(16, cin, 3, 3, seed=150, scale=(2.0 / (9 * cin)) ** 0.5))
+    b = rnd(16, seed=151, scale=0.1)
+    ref = F.relu(F.conv2d(torch.cat(xs, 1).double(), w.double(), b.double(), padding=1))
+    wp = ops.pack_weights_b2(w.to(DEV), False, cin)
+    out = torch.empty(N, H, W, 16, dtype=torch.bfloat16, device=DEV)
+    ops.conv([nhwc(x) for x in xs], N, H, W, wp, 16, 16, 9, bias=b.to(DEV), relu=True, out=out, b2=True)
+    torch.cuda.synchronize()
+    close(nchw(out), ref, 6e-3, "conv3x3 2x2-blocked")
+
+
+def test_block2x2_fused_head_and_bn_fold():
+    N, H, W = 2, 32, 48
+    x = bf(rnd(N, 16, H, W, seed=160))
+    w = rnd(16, 16, 3, 3, seed=161, scale=0.12)
+    scale = torch.rand(16) + 0.5
+    b = rnd(16, seed=162, scale=0.1)
+    hw, hb = rnd(4, 16, seed=163, scale=0.5), rnd(4, seed=164, scale=0.2)
+    y = F.relu(F.conv2d(x.double(), bf(w * scale[:, None, None, None]).double(), b.double(), padding=1))
+    logit = F.conv2d(y, hw.double()[:, :, None, None], hb.double())
+    wp = ops.pack_weights_b2(w.to(DEV), False, 16, scale=scale.to(DEV))
+    out = torch.empty(N, H, W, 16, dtype=torch.bfloat16, device=DEV)
+    heat = torch.empty(N, 4, H, W, device=DEV)
+    ops.conv([nhwc(x)], N, H, W, wp, 16, 16, 9, bias=b.to(DEV), relu=True, out=out, head=(hw.to(DEV), hb.to(DEV), heat, None, None, 1.0), b2=True)
+    close(nchw(out), y, 6e-3, "b2 head conv out")
+    close(heat.cpu(), torch.sigmoid(logit), 2e-3, "b2 heat")
+
+
+@pytest.mark.parametrize("ncons", [1, 3])
+def test_block2x2_dgrad_gather_mask_stats(ncons):
+    N, H, W = 2, 32, 40
+    t_act = bf(F.relu(rnd(N, 16, H, W, seed=170)))
+    dzs = [bf(rnd(N, 16, H, W, seed=171 + i)) for i in range(ncons)]
+    ws = [bf(rnd(16, 48, 3, 3, seed=175 + i, scale=0.1)) for i in range(ncons)]
+    addend = bf(rnd(N, 16, H, W, seed=179, scale=0.3))
+    aux = bf(rnd(N, 16, H, W, seed=180))
+    mean, istd = rnd(16, seed=181, scale=0.2), torch.rand(16) + 0.5
+    n_begin = 16
+    ref = addend.double().clone()
+    for dz, w in zip(dzs, ws):
+        ref += F.conv_transpose2d(dz.double(), w.double()[:, n_begin:n_begin + 16], padding=1)
+    ref = ref * (t_act > 0)
+    ktot = 16 * ncons
+    wp = torch.zeros(64 * 16 * ktot, dtype=torch.bfloat16, device=DEV)
+    for i, w in enumerate(ws):
+        ops.pack_weights_b2(w.to(DEV), True, 16, n_begin=n_begin, dst=wp, k8_total=ktot // 8, k_dst8=2 * i)
+    out = torch.empty(N, H, W, 16, dtype=torch.bfloat16, device=DEV)
+    g = ops.conv_grid([16] * ncons, N, H, W, 16, 16, 9, b2=True)
+    stats = torch.full((g, 2, 16), float("nan"), device=DEV)
+    ops.conv([nhwc(d) for d in dzs], N, H, W, wp, 16, 16, 9, out=out, addend=nhwc(addend), relu_mask_src=nhwc(t_act), stats_partial=stats,
+             stats_aux=nhwc(aux), aux_mean=mean.to(DEV), aux_istd=istd.to(DEV), b2=True)
+    got = nchw(out)
+    close(got, ref, 6e-3, "b2 dgrad gather")
+    sums = torch.empty(32, device=DEV)
+    ops.reduce_partials(stats, g, 32, 32, sums)
+    close(sums[:16].cpu(), got.double().sum((0, 2, 3)), 1e-3, "sum v")
+    xhat = (aux.double() - mean.double()[None, :, None, None]) * istd.double()[None, :, None, None]
+    close(sums[16:].cpu(), (got.double() * xhat).sum((0, 2, 3)), 2e-3, "sum v*xhat")

@@ -50,6 +50,7 @@ class ConvArgs(C.Structure):
         ("stats_aux", C.c_void_p),
         ("aux_mean", C.c_void_p),
         ("aux_istd", C.c_void_p),
+        ("block2x2", C.c_int32),
     ]
 
 

@@ -37,8 +37,19 @@ __global__ void pack_weights_kernel(UnppPackArgs a) {
       } else if (a.kind == 2) {  // B[n=pq*Cout+co][0][k=ci] = Wd[ci][co][pq];  src [Cin][Cout][2][2]
         const int cout = a.src_I, pq = n / cout, co = n % cout;
         w = a.src[(size_t(a.k_begin + k) * cout + co) * 4 + pq];
-      } else {  // kind 3: B[n=ci][tap=pq][k=co] = Wd[ci][co][pq]
+      } else if (a.kind == 3) {  // B[n=ci][tap=pq][k=co] = Wd[ci][co][pq]
         w = a.src[(size_t(a.n_begin + n) * a.src_I + (a.k_begin + k)) * 4 + tap];
+      } else {  // kinds 4 / 5: 2x2 output blocks; tap = window position dy*4+dx, n = (2*jy+jx)*16 + c
+        const int q = n >> 4, c = n & 15, r = (tap >> 2) - (q >> 1), s = (tap & 3) - (q & 1);
+        w = 0.f;
+        if (r >= 0 && r <= 2 && s >= 0 && s <= 2) {
+          if (a.kind == 4) {
+            w = a.src[(size_t(c) * a.src_I + (a.k_begin + k)) * 9 + r * 3 + s];
+            if (a.scale) w *= a.scale[c];
+          } else {
+            w = a.src[(size_t(a.k_begin + k) * a.src_I + (a.n_begin + c)) * 9 + (2 - r) * 3 + (2 - s)];
+          }
+        }
       }
       v[kk] = __float2bfloat16_rn(w);
     }
@@ -153,7 +164,9 @@ inline int grid_for(long total, int block) {
 
 extern "C" int unpp_pack_weights(const UnppPackArgs* a, unpp_stream_t stream) {
   if (!a || !a->src || !a->dst) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: null pointer");
-  if (a->kind < 0 || a->kind > 3) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: bad kind");
+  if (a->kind < 0 || a->kind > 5) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: bad kind");
+  if (a->kind >= 4 && (a->taps != 16 || a->n_total != 64 || a->n_tile != 64))
+    return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: 2x2-blocked kinds need taps=16, n_total=n_tile=64");
   if (a->n_tile < 8 || a->n_total % a->n_tile || a->k_count % 8 || a->k_count < 8 || a->taps < 1)
     return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: n_total %% n_tile, k_count %% 8 must be 0");
   if (a->k_dst8 + a->k_count / 8 > a->k8_total) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: K range exceeds k8_total");

@@ -69,6 +69,7 @@ struct ConvTcParams {
   const __nv_bfloat16* stats_aux;
   const float* aux_mean;
   const float* aux_istd;
+  int b2, b2_P;  // 2x2 output blocking: flag, pixel PAIRS per staged tile row (TW/2 + 2)
   int dbg;  // UNPP_DBG experiment bits (0 in production): 1 = epilogue skips its work, 2 = no MMAs issued, 4 = no TMA tile loads
 };
 
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
   }
   // stage the per-column bias (conv: this CTA's n_tile slice; deconv: all Cout) and the 1x1 head
   {
-    const int nb = DECONV ? p.cout : p.ncols;
+    const int nb = (DECONV || p.b2) ? p.cout : p.ncols;
     for (int i = threadIdx.x; i < nb; i += kThreads) s_bias[i] = p.bias ? __ldg(p.bias + (DECONV ? 0 : ntile_idx * p.ncols) + i) : 0.f;
     if constexpr (HEAD) {
       for (int i = threadIdx.x; i < p.head_classes * 16; i += kThreads) s_head[i] = __ldg(p.head_w + i);
@@ -340,6 +341,11 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
             mbar_arrive(&bar_full[s]);
             continue;
           }
+          if (p.b2) {  // pixel-pair rows (64 B), 34 image rows x (TW/2 + 2) pairs around a 32 x TW output tile
+            mbar_arrive_expect_tx(&bar_full[s], 34 * p.b2_P * 64);
+            tma_load_4d(&p.maps[p.ch_map[c]], &bar_full[s], stage0 + size_t(s) * p.stage_bytes, 0, tx * (p.TW >> 1) - 1, ty * 32 - 1, n);
+            continue;
+          }
           mbar_arrive_expect_tx(&bar_full[s], rows * P * p.ch_span[c]);
           tma_load_4d(&p.maps[p.ch_map[c]], &bar_full[s], stage0 + size_t(s) * p.stage_bytes, p.ch_c0[c], tx * p.TW - pad,
                       ty * 16 - pad, n);
@@ -351,12 +357,12 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     // One thread can only sustain ~1 MMA per 85 cycles through the uniform datapath (measured: the
     // tensor pipe takes ~40); three or four issuing threads, each with its own accumulators, remove that limit.
     const int mw = warp == 1 ? 0 : warp - (1 + kEpiWarps);
-    const bool has0 = mw < p.nsub, has1 = mw + kMmaWarps < p.nsub, has2 = mw + 2 * kMmaWarps < p.nsub;
+    const bool has0 = mw < p.nsub, has1 = mw + kMmaWarps < p.nsub, has2 = kMmaWarps < 4 && mw + 2 * kMmaWarps < p.nsub;  // (8 sub-tiles at most: a third slot only exists with three issuers)
     // every kernel parameter used below is copied to a register first: the loop must not touch
     // the parameter bank between MMA issues
     mbar_wait(&bar_w, 0);
     const int ncols = p.ncols, nsub = p.nsub, taps = p.taps, k8_total = p.k8_total, nchunk = p.nchunk, nstage = p.nstage;
-    const int ntiles = p.ntiles, stage_bytes = p.stage_bytes, dbg = p.dbg;
+    const int ntiles = p.ntiles, stage_bytes = p.stage_bytes, dbg = p.dbg, b2 = p.b2, b2_P = p.b2_P;
     const uint32_t idesc = make_idesc_bf16(128, ncols);
     const uint32_t w_addr = smem_u32(w_smem);
     const uint32_t stage_addr0 = smem_u32(stage0);
@@ -378,34 +384,67 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
           if (cc == c) span = spans[cc], wk8 = wk8s[cc];
         mbar_wait(&bar_full[s], ph);
         tc_fence_after();
-        if (elect_one() && !(dbg & 2)) {
-          // descriptor arithmetic is incremental (adds of loop-invariant 16-byte-unit offsets): the
-          // issue rate of this single thread is what bounds the small-N layers
+        // Issue loops: fully unrolled over the window positions / taps, descriptors formed from a constant high
+        // word and a 32-bit low word (start address + LBO) so that every MMA costs two independent adds, not a
+        // serial chain through the uniform datapath (the single issuing thread is the limiter at small N).
+        if (b2) {
+          if (elect_one() && !(dbg & 2)) {
+            // 2x2 output blocks: GEMM row = block (8 consecutive pixel pairs = 8 rows of 64 B, next row group two
+            // image rows down), K walks the 4x4 input window: pixel (dy, dx) of the window is 32 B into / past the
+            // pair row, i.e. a start-address shift of (dy * pairs_per_row * 4 + (dx + 1) * 2) 16-byte units.
+            const uint64_t ad = make_sdesc(stage_addr0 + uint32_t(s) * stage_bytes, 16, uint32_t(2 * b2_P * 64), 4);
+            const uint64_t bd = make_sdesc(w_addr + uint32_t(wk8 * 64 * 16), 64 * 16, 128, 0);
+            const uint32_t a_hi = uint32_t(ad >> 32), b_hi = uint32_t(bd >> 32), b_lo = uint32_t(bd);
+            const uint32_t a_lo0 = uint32_t(ad) + 2u + uint32_t(mw * 32), a_lo1 = a_lo0 + uint32_t(kMmaWarps * 32);
+            const uint32_t acc0 = acc + uint32_t(mw * 64), acc1 = acc + uint32_t((mw + kMmaWarps) * 64);
+            const uint32_t b_pos_step = uint32_t(k8_total * 64 * 16) >> 4, row_step = uint32_t(b2_P * 4);
+            const uint32_t first = c ? 1u : 0u;
+#pragma unroll
+            for (int dy = 0; dy < 4; ++dy) {
+#pragma unroll
+              for (int dx = 0; dx < 4; ++dx) {
+                const uint32_t ao = uint32_t(dy) * row_step + uint32_t(dx * 2), bo = uint32_t(dy * 4 + dx) * b_pos_step;
+                const uint64_t bdesc = (uint64_t(b_hi) << 32) | (b_lo + bo);
+                const uint32_t accum = (dy | dx) ? 1u : first;
+                if (has0) umma_bf16(acc0, (uint64_t(a_hi) << 32) | (a_lo0 + ao), bdesc, idesc, accum);
+                if (has1) umma_bf16(acc1, (uint64_t(a_hi) << 32) | (a_lo1 + ao), bdesc, idesc, accum);
+              }
+            }
+          }
+        } else if (elect_one() && !(dbg & 2)) {
           const int kslabs = span >> 5;
           const uint32_t px_step = uint32_t(span) >> 4, row_step = uint32_t(P * span) >> 4;
           const uint32_t b_tap_step = uint32_t(k8_total * ncols * 16) >> 4, b_ks_step = uint32_t(2 * ncols * 16) >> 4;
           const uint32_t sub_step = uint32_t(8 * span) >> 4;  // next 8-pixel patch column, in 16 B units
-          const uint64_t a0 = make_sdesc(stage_addr0 + uint32_t(s) * stage_bytes, 16, uint32_t(P * span), layout_type_of_span(span));
-          const uint64_t a_j0 = a0 + uint64_t(mw * sub_step), a_j1 = a0 + uint64_t((mw + kMmaWarps) * sub_step),
-                         a_j2 = a0 + uint64_t((mw + 2 * kMmaWarps) * sub_step);
+          const uint64_t ad = make_sdesc(stage_addr0 + uint32_t(s) * stage_bytes, 16, uint32_t(P * span), layout_type_of_span(span));
+          const uint64_t bd = make_sdesc(w_addr + uint32_t(wk8 * ncols * 16), uint32_t(ncols * 16), 128, 0);
+          const uint32_t a_hi = uint32_t(ad >> 32), b_hi = uint32_t(bd >> 32), b_lo = uint32_t(bd);
+          const uint32_t a_lo0 = uint32_t(ad) + uint32_t(mw) * sub_step, a_lo1 = a_lo0 + uint32_t(kMmaWarps) * sub_step,
+                         a_lo2 = a_lo1 + uint32_t(kMmaWarps) * sub_step;
           const uint32_t acc0 = acc + uint32_t(mw * ncols), acc1 = acc + uint32_t((mw + kMmaWarps) * ncols),
                          acc2 = acc + uint32_t((mw + 2 * kMmaWarps) * ncols);
-          uint64_t b_t = make_sdesc(w_addr + uint32_t(wk8 * ncols * 16), uint32_t(ncols * 16), 128, 0);
-          const int R = taps == 9 ? 3 : 1;
-          uint32_t accum = c ? 1u : 0u;
-          uint32_t a_r = 0;
-          for (int r = 0; r < R; ++r, a_r += row_step) {
-            uint32_t a_t = a_r;
-            for (int sft = 0; sft < R; ++sft, a_t += px_step, b_t += b_tap_step) {
-              uint32_t a_k = a_t;
-              uint64_t b_k = b_t;
-              for (int ks = 0; ks < kslabs; ++ks, a_k += 2, b_k += b_ks_step) {
-                if (has0) umma_bf16(acc0, a_j0 + a_k, b_k, idesc, accum);
-                if (has1) umma_bf16(acc1, a_j1 + a_k, b_k, idesc, accum);
-                if (has2) umma_bf16(acc2, a_j2 + a_k, b_k, idesc, accum);
-                accum = 1u;
+          const uint32_t first = c ? 1u : 0u;
+          auto issue_tap = [&](uint32_t ao, uint32_t bo, bool first_tap) {
+#pragma unroll 4
+            for (int ks = 0; ks < kslabs; ++ks) {
+              const uint32_t aok = ao + uint32_t(ks * 2);
+              const uint64_t bdesc = (uint64_t(b_hi) << 32) | (b_lo + bo + uint32_t(ks) * b_ks_step);
+              const uint32_t accum = (first_tap && ks == 0) ? first : 1u;
+              if (has0) umma_bf16(acc0, (uint64_t(a_hi) << 32) | (a_lo0 + aok), bdesc, idesc, accum);
+              if (has1) umma_bf16(acc1, (uint64_t(a_hi) << 32) | (a_lo1 + aok), bdesc, idesc, accum);
+              if constexpr (kMmaWarps < 4) {
+                if (has2) umma_bf16(acc2, (uint64_t(a_hi) << 32) | (a_lo2 + aok), bdesc, idesc, accum);
               }
             }
+          };
+          if (taps == 9) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+              for (int sft = 0; sft < 3; ++sft) issue_tap(uint32_t(r) * row_step + uint32_t(sft) * px_step, uint32_t(r * 3 + sft) * b_tap_step, (r | sft) == 0);
+            }
+          } else {
+            issue_tap(0u, 0u, true);
           }
         }
         __syncwarp();
@@ -430,11 +469,11 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     e.H = p.H, e.W = p.W, e.cout = p.cout, e.head_classes = p.head_classes, e.out = p.out, e.heat = p.heat, e.logit = p.logit;
     e.drop_mask = p.drop_mask, e.drop_scale = p.drop_scale, e.addend = p.addend, e.relu_mask_src = p.relu_mask_src;
     e.stats_partial = p.stats_partial, e.stats_aux = p.stats_aux, e.aux_mean = p.aux_mean, e.aux_istd = p.aux_istd;
-    const int TW = p.TW, ncols = p.ncols, nsub = p.nsub, ntiles = p.ntiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y, dbg = p.dbg;
+    const int TW = p.TW, ncols = p.ncols, nsub = p.nsub, ntiles = p.ntiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y, dbg = p.dbg, b2 = p.b2;
     float* const st1 = TRAIN ? &s_stats[TRAIN ? ew : 0][0][0] : nullptr;
     float* const st2 = TRAIN ? &s_stats[TRAIN ? ew : 0][1][0] : nullptr;
     // with <= 2 column groups every unit of this warp has the same 16 channels: keep the statistics in registers
-    const bool reg_stats = TRAIN && ncb <= 2;
+    const bool reg_stats = TRAIN && (ncb <= 2 || b2);  // (2x2 blocking: the four column groups are four pixels of the same 16 channels)
     float sa1[16], sa2[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) sa1[k] = 0.f, sa2[k] = 0.f;
@@ -444,24 +483,26 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
       mbar_wait(&bar_acc_full[b], aph);
       tc_fence_after();
-      const int y = ty * 16 + pi;
+      const int y = b2 ? ty * 32 + 2 * pi : ty * 16 + pi;
       const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * nsub * ncols);
       uint32_t raw[16];
       int u = (dbg & 1) ? units : half;
       if (u < units) tmem_ld16(tbase + uint32_t(u * 16), raw);  // unit u covers columns [16u, 16u+16) of this accumulator set
       for (; u < units; u += 2) {
-        const int j = u / ncb, c0 = (u % ncb) * 16;
-        const int x = tx * TW + j * 8 + pj;
-        const bool valid = (y < e.H) && (x < e.W);
+        // classic: unit = (8-pixel-wide sub-tile j, 16-column group); 2x2: unit = (16-pixel-wide sub-tile, pixel of the block)
+        const int j = b2 ? (u >> 2) : u / ncb, c0 = b2 ? 0 : (u % ncb) * 16;
+        const int yy = b2 ? y + ((u >> 1) & 1) : y;
+        const int x = b2 ? tx * TW + j * 16 + 2 * pj + (u & 1) : tx * TW + j * 8 + pj;
+        const bool valid = (yy < e.H) && (x < e.W);
         TrainOperands tops;
-        prefetch_train<TRAIN>(e, tops, (size_t(n) * e.H + y) * e.W + x, ntile_idx * ncols + c0, valid);
+        prefetch_train<TRAIN>(e, tops, (size_t(n) * e.H + yy) * e.W + x, ntile_idx * ncols * (b2 ? 0 : 1) + c0, valid);
         tmem_ld_wait16(raw);
         float v[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(raw[k]);
         if (u + 2 < units) tmem_ld16(tbase + uint32_t((u + 2) * 16), raw);
-        epilogue_group<DECONV, HEAD, TRAIN>(e, v, tops, n, y, x, valid, ntile_idx * ncols + c0, c0, s_bias, s_head, relu_floor, reg_stats, sa1, sa2,
-                                            st1, st2, lane);
+        epilogue_group<DECONV, HEAD, TRAIN>(e, v, tops, n, yy, x, valid, b2 ? 0 : ntile_idx * ncols + c0, c0, s_bias, s_head, relu_floor, reg_stats,
+                                            sa1, sa2, st1, st2, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -469,7 +510,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     }
     if constexpr (TRAIN) {
       if (reg_stats && e.stats_partial) {
-        const int c0w = (half % ncb) * 16;  // u = half + 2i  =>  u % ncb is constant for ncb in {1, 2}
+        const int c0w = b2 ? 0 : (half % ncb) * 16;  // u = half + 2i  =>  u % ncb is constant for ncb in {1, 2}
         const float r1 = warp_reduce16(sa1, lane), r2 = warp_reduce16(sa2, lane);
         if ((lane & 1) == 0) st1[c0w + (lane >> 1)] += r1, st2[c0w + (lane >> 1)] += r2;
       }
@@ -483,8 +524,9 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     if (p.stats_partial) {
       // partial layout [cta.x][2][n_total]; the warp slots are summed in a fixed order so the
       // result is deterministic for a given launch geometry.
-      for (int i = threadIdx.x; i < 2 * p.ncols; i += kThreads) {
-        const int st = i / p.ncols, ch = i % p.ncols;
+      const int nch = p.b2 ? p.cout : p.ncols;
+      for (int i = threadIdx.x; i < 2 * nch; i += kThreads) {
+        const int st = i / nch, ch = i % nch;
         float t = 0.f;
 #pragma unroll
         for (int wv = 0; wv < kEpiWarps; ++wv) t += s_stats[TRAIN ? wv : 0][st][TRAIN ? ch : 0];
@@ -492,10 +534,10 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
           float t1 = 0.f;
 #pragma unroll
           for (int wv = 0; wv < kEpiWarps; ++wv) t1 += s_stats[TRAIN ? wv : 0][0][TRAIN ? ch : 0];
-          const int gc = ntile_idx * p.ncols + ch;
+          const int gc = ntile_idx * nch + ch;
           t = __ldg(p.aux_istd + gc) * (t - __ldg(p.aux_mean + gc) * t1);
         }
-        p.stats_partial[(size_t(blockIdx.x) * 2 + st) * p.cout + ntile_idx * p.ncols + ch] = t;
+        p.stats_partial[(size_t(blockIdx.x) * 2 + st) * p.cout + ntile_idx * nch + ch] = t;
       }
     }
   }
@@ -519,9 +561,11 @@ EncodeTiledFn get_encode() {
 
 struct Plan {
   int TW, nsub, nstage, stage_bytes, w_bytes, w_smem_bytes, tmem_cols, smem_total, grid_x, grid_y, tiles_x, tiles_y, ntiles;
-  int nchunk, k8_total;
+  int nchunk, k8_total, b2, b2_P, ncols;
   int ch_map[kMaxChunks], ch_c0[kMaxChunks], ch_span[kMaxChunks], ch_wk8[kMaxChunks];
 };
+
+inline bool is_train(const UnppConvArgs* a) { return a->addend || a->relu_mask_src || a->stats_partial || a->logit || a->drop_mask; }
 
 int make_plan(const UnppConvArgs* a, Plan* pl) {
   if (!a || a->nsrc < 1 || a->nsrc > UNPP_MAX_SRC) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: nsrc out of range");
@@ -546,10 +590,43 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
     }
   }
   pl->nchunk = nchunk, pl->k8_total = k8;
+  pl->b2 = 0, pl->b2_P = 0, pl->ncols = a->n_tile;
+  // static shared memory: 18 KB in the training variants (statistics slots), 2 KB otherwise; 227 KB per CTA in total
+  const int smem_budget = (is_train(a) ? 196 : 220) * 1024;
+  if (a->block2x2) {
+    // 2x2 output blocking: every source is one 16-channel chunk staged as 64-byte pixel-pair rows; N = 4 x 16
+    if (a->taps != 9 || a->mode != UNPP_MODE_CONV || a->n_total != 16 || a->n_tile != 16 || (a->H & 1) || (a->W & 1))
+      return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: block2x2 needs a 3x3 conv with n_total = n_tile = 16 and even H, W");
+    for (int i = 0; i < a->nsrc; ++i) {
+      if (a->src_C[i] != 16 || a->src_step[i] == 2) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: block2x2 needs dense 16-channel sources");
+      pl->ch_span[i] = 64, pl->ch_wk8[i] = 2 * i;
+    }
+    pl->b2 = 1, pl->ncols = 64;
+    pl->w_bytes = 16 * k8 * 64 * 16;
+    pl->w_smem_bytes = (pl->w_bytes + 1023) / 1024 * 1024;
+    int TW = a->W > 16 ? 32 : 16;
+    for (;; TW >>= 1) {
+      pl->b2_P = TW / 2 + 2;
+      pl->stage_bytes = (34 * pl->b2_P * 64 + 1023) / 1024 * 1024;
+      pl->nstage = (smem_budget - pl->w_smem_bytes) / pl->stage_bytes;
+      if (pl->nstage >= 2 || TW == 16) break;
+    }
+    if (pl->nstage < 2) return unpp::fail(UNPP_ERR_UNSUPPORTED, "conv_tc: block2x2 weights leave no room for 2 stages (too many sources)");
+    if (pl->nstage > kMaxStages) pl->nstage = kMaxStages;
+    pl->TW = TW, pl->nsub = TW / 16;
+    pl->tmem_cols = 2 * pl->nsub * 64;
+    pl->smem_total = 1024 + pl->w_smem_bytes + pl->nstage * pl->stage_bytes;
+    pl->tiles_x = (a->W + TW - 1) / TW, pl->tiles_y = (a->H + 31) / 32;
+    pl->ntiles = pl->tiles_x * pl->tiles_y * a->N;
+    pl->grid_y = 1;
+    int gx = unpp::num_sms();
+    if (gx > pl->ntiles) gx = pl->ntiles;
+    pl->grid_x = gx;
+    return UNPP_OK;
+  }
   const int pad = a->taps == 9 ? 1 : 0;
   pl->w_bytes = a->taps * k8 * a->n_tile * 16;
   pl->w_smem_bytes = (pl->w_bytes + 1023) / 1024 * 1024;
-  const int smem_budget = 196 * 1024;
   int TW = 64;
   while (TW > 8 && (2 * (TW / 8) * a->n_tile > 512 || TW / 2 >= ((a->W + 7) / 8) * 8)) TW >>= 1;
   for (;; TW >>= 1) {
@@ -615,6 +692,12 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
     cuuint32_t box[4] = {cuuint32_t(box_c), cuuint32_t(pl.TW + 2 * pad), cuuint32_t(16 + 2 * pad), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUtensorMapSwizzle sw = box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    if (pl.b2) {  // the [N,H,W,16] tensor seen as [N,H,W/2,32]: one row = a horizontal pixel pair (64 B)
+      gd[0] = 32, gd[1] = cuuint64_t(a->W / 2);
+      gs[0] = 64;
+      box[0] = 32, box[1] = cuuint32_t(pl.b2_P), box[2] = 34;
+      sw = CU_TENSOR_MAP_SWIZZLE_64B;
+    }
     CUresult r = enc(&p.maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<uint8_t*>(base), gd, gs, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled failed (CUresult %d) for source %d", int(r), i);
@@ -623,7 +706,8 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   for (int c = 0; c < pl.nchunk; ++c) p.ch_map[c] = pl.ch_map[c], p.ch_c0[c] = pl.ch_c0[c], p.ch_span[c] = pl.ch_span[c], p.ch_wk8[c] = pl.ch_wk8[c];
   p.N = a->N, p.H = a->H, p.W = a->W;
   p.TW = pl.TW, p.nsub = pl.nsub, p.tiles_x = pl.tiles_x, p.tiles_y = pl.tiles_y, p.ntiles = pl.ntiles;
-  p.taps = a->taps, p.ncols = a->n_tile, p.k8_total = pl.k8_total;
+  p.taps = a->taps, p.ncols = pl.ncols, p.k8_total = pl.k8_total;
+  p.b2 = pl.b2, p.b2_P = pl.b2_P;
   p.stage_bytes = pl.stage_bytes, p.nstage = pl.nstage, p.w_bytes = pl.w_bytes, p.w_smem_bytes = pl.w_smem_bytes;
   p.tmem_cols = pl.tmem_cols;
   p.wpacked = reinterpret_cast<const __nv_bfloat16*>(a->wpacked);
@@ -644,7 +728,7 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   }
 
   const bool deconv = a->mode == UNPP_MODE_DECONV, head = a->head_w != nullptr;
-  const bool train = a->addend || a->relu_mask_src || a->stats_partial || a->logit || a->drop_mask;
+  const bool train = is_train(a);
   if (deconv && train) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: deconv mode has no training epilogue");
   if (deconv && a->n_total / 4 > 256) return unpp::fail(UNPP_ERR_UNSUPPORTED, "conv_tc: deconv Cout > 256");
   const dim3 grid(pl.grid_x, pl.grid_y);
@@ -652,7 +736,7 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   do {                                                                                                                                \
     static int opted_in = 0; /* attribute is per-function, idempotent */                                                              \
     if (!opted_in) {                                                                                                                  \
-      if (cudaFuncSetAttribute(conv_tc_kernel<D, Hd, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024) != cudaSuccess)     \
+      if (cudaFuncSetAttribute(conv_tc_kernel<D, Hd, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (T ? 204 : 224) * 1024) != cudaSuccess) \
         return unpp::fail_cuda("conv_tc: cudaFuncSetAttribute");                                                                      \
       opted_in = 1;                                                                                                                   \
     }                                                                                                                                 \

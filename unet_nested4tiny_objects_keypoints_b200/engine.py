@@ -103,6 +103,9 @@ class Engine:
             wp = torch.zeros(cout, 16 * ((cin + 15) // 16), 3, 3, dtype=torch.float32, device=w.device)
             wp[:, :cin] = w
             w, cin = wp, wp.shape[1]
+        if cout == 16 and cin % 16 == 0 and cin <= 64:
+            # full-resolution level (every source has 16 channels): 2x2 output-blocked kernel path
+            return dict(w=ops.pack_weights_b2(w, False, cin, scale=scale), bias=bias, n_total=cout, n_tile=ops.NTile(16, b2=True))
         nt = pick_n_tile(cout, cin, 9)
         return dict(w=ops.pack_weights(w, 0, 9, cout, nt, cin, scale=scale), bias=bias, n_total=cout, n_tile=nt)
 

@@ -56,6 +56,23 @@ def lib():
     return _lib.load()
 
 
+class NTile(int):
+    """n_tile of a conv launch; ``NTile(16, b2=True)`` selects the 2x2 output-blocked kernel path
+    (weights packed with pack_weights_b2) wherever an ``n_tile`` is passed to conv() / conv_grid()."""
+
+    def __new__(cls, value, b2=False):
+        obj = super().__new__(cls, value)
+        obj.b2 = b2
+        return obj
+
+
+def pack_weights_b2(src: torch.Tensor, dgrad: bool, k_count: int, *, scale=None, n_begin: int = 0, k_begin: int = 0, dst=None, k8_total=None,
+                    k_dst8: int = 0) -> torch.Tensor:
+    """Weights of a 16-output-channel 3x3 conv for the 2x2 output-blocked kernel (unpp.h kinds 4 / 5)."""
+    return pack_weights(src, 5 if dgrad else 4, 16, 64, 64, k_count, scale=scale, n_begin=n_begin, k_begin=k_begin, dst=dst, k8_total=k8_total,
+                        k_dst8=k_dst8)
+
+
 def pick_n_tile(n_total: int, k_total: int, taps: int, deconv: bool = False) -> int:
     """Largest multiple of 16 dividing n_total whose packed weights fit the shared-memory budget."""
     best = 16
@@ -90,7 +107,7 @@ def pack_weights(src: torch.Tensor, kind: int, taps: int, n_total: int, n_tile: 
     return dst
 
 
-def _conv_args(srcs, N, H, W, n_total, n_tile, taps, strided=None) -> ConvArgs:
+def _conv_args(srcs, N, H, W, n_total, n_tile, taps, strided=None, b2=False) -> ConvArgs:
     a = ConvArgs()
     a.N, a.H, a.W, a.nsrc = N, H, W, len(srcs)
     for i, s in enumerate(srcs):
@@ -102,17 +119,18 @@ def _conv_args(srcs, N, H, W, n_total, n_tile, taps, strided=None) -> ConvArgs:
             a.src_C[i] = int(s)
         if strided is not None:
             a.src_step[i], a.src_oy[i], a.src_ox[i] = 2, strided[i][0], strided[i][1]
-    a.taps, a.n_total, a.n_tile = taps, n_total, n_tile
+    a.taps, a.n_total, a.n_tile = taps, n_total, int(n_tile)
+    a.block2x2 = int(b2 or getattr(n_tile, "b2", False))
     return a
 
 
 def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Tensor, n_total: int, n_tile: int, taps: int, *, bias=None,
          relu=False, mode=MODE_CONV, out=None, head=None, addend=None, relu_mask_src=None, stats_partial=None, stats_aux=None, aux_mean=None,
-         aux_istd=None, strided=None) -> None:
+         aux_istd=None, strided=None, b2=False) -> None:
     """One unpp_conv_tc launch.  ``srcs``: NHWC bf16 tensors (virtual concat along K).
     ``head`` = (w fp32 [cls,16], b fp32 [cls], heat fp32 NCHW, logit|None, drop_mask u8 NHWC|None, drop_scale).
     ``strided`` = [(oy, ox), ...]: every source is a [N,2H,2W,C] tensor read at (2y+oy, 2x+ox)."""
-    a = _conv_args(srcs, N, H, W, n_total, n_tile, taps, strided)
+    a = _conv_args(srcs, N, H, W, n_total, n_tile, taps, strided, b2)
     a.wpacked, a.bias = wpacked.data_ptr(), _ptr(bias)
     a.mode, a.relu = mode, int(relu)
     a.out = _ptr(out)
@@ -139,13 +157,13 @@ def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Te
         if extra is not None:
             nbytes += extra.numel() * 2
     flops = 2 * px * k_total * n_total * taps
-    label = "conv_tc %s taps%d K%d N%d %dx%d" % ("deconv" if mode == MODE_DECONV else "conv", taps, k_total, n_total, H, W)
+    label = "conv_tc %s taps%d K%d N%d %dx%d" % ("deconv" if mode == MODE_DECONV else ("conv2x2" if a.block2x2 else "conv"), taps, k_total, n_total, H, W)
     with _Traced(label, nbytes, flops):
         _lib.check(lib().unpp_conv_tc(C.byref(a), _stream()), "unpp_conv_tc")
 
 
-def conv_grid(srcs_C: Sequence[int], N: int, H: int, W: int, n_total: int, n_tile: int, taps: int) -> int:
-    a = _conv_args(list(srcs_C), N, H, W, n_total, n_tile, taps)
+def conv_grid(srcs_C: Sequence[int], N: int, H: int, W: int, n_total: int, n_tile: int, taps: int, b2: bool = False) -> int:
+    a = _conv_args(list(srcs_C), N, H, W, n_total, n_tile, taps, None, b2)
     g = lib().unpp_conv_grid(C.byref(a))
     if g < 0:
         _lib.check(g, "unpp_conv_grid")

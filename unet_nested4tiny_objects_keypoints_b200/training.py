@@ -146,6 +146,14 @@ def pack_train(ts: TrainState) -> None:
         nt = kw.pop("n_tile")
         dst = P.get(key)
         k8_total = kw.get("k8_total", k_count // 8)
+        b2 = kind in (0, 1) and taps == 9 and n_total == 16 and k_count % 16 == 0 and src.shape[0] == 16 and k8_total <= 8
+        if b2:  # 16-channel full-resolution level: 2x2 output-blocked kernel path (unpp.h kinds 4 / 5)
+            if dst is None:
+                dst = P[key] = torch.zeros(64 * 16 * k8_total * 8, dtype=torch.bfloat16, device=dev)
+                P[key + ".nt"] = ops.NTile(16, b2=True)
+            kw.pop("k8_total", None)
+            ops.pack_weights_b2(src, kind == 1, k_count, dst=dst, k8_total=k8_total, **kw)
+            return
         if dst is None:
             dst = P[key] = torch.zeros(n_total * taps * k8_total * 8, dtype=torch.bfloat16, device=dev)
             P[key + ".nt"] = nt
