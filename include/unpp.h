@@ -96,6 +96,7 @@ int unpp_conv_grid(const UnppConvArgs* a);
 /* Weight packing into the UMMA B-operand layout [n_total/n_tile][taps][K/8][n_tile][8] (bf16).
  *  kind 0: forward conv   B[n=co][tap][k=ci]   = W[co][k_begin+ci][tap] * (scale ? scale[co] : 1)
  *          src = OIHW fp32 [Cout][Cin_total][kh][kw]; K = k_count channels starting at k_begin
+ *          (channels >= Cin_total pack as zero: the 3-channel first layer reads a 16-channel padded input)
  *  kind 1: dgrad of conv  B[n=ci][tap][k=co]   = W[co][n_begin+ci][taps-1-tap]  (flipped taps)
  *          n_total = number of input channels of the slice, K = Cout
  *  kind 2: deconv forward B[n=(2p+q)*Cout+co][0][k=ci] = Wd[ci][co][p][q]; src [Cin][Cout][2][2]
@@ -119,6 +120,9 @@ typedef struct UnppPackArgs {
   int32_t k8_total, k_dst8;
 } UnppPackArgs;
 int unpp_pack_weights(const UnppPackArgs* a, unpp_stream_t stream);
+/* The same for a whole table of n jobs resident in DEVICE memory (entries are not validated): one launch
+ * re-packs every weight of a training step after the optimizer update. */
+int unpp_pack_weights_batched(const UnppPackArgs* table_dev, int n, unpp_stream_t stream);
 
 /* fp32 NCHW [N,C,H,W] -> bf16 NHWC [N,H,W,Cpad] (channels >= C zero-filled). */
 int unpp_nchw_to_nhwc(const float* x, void* out, int N, int C, int H, int W, int Cpad, unpp_stream_t stream);

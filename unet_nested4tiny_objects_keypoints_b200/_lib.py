@@ -83,6 +83,7 @@ _SIGNATURES = {
     "unpp_conv_tc": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "unpp_conv_grid": (C.c_int, [C.POINTER(ConvArgs)]),
     "unpp_pack_weights": (C.c_int, [C.POINTER(PackArgs), C.c_void_p]),
+    "unpp_pack_weights_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "unpp_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "unpp_maxpool2x2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "unpp_argmax_peaks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

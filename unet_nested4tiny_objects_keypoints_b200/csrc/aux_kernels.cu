@@ -11,7 +11,7 @@ namespace {
 
 // ------------------------------------------------------------------------------------------
 // weight packing: one thread per packed 8-element K group (16 B store)
-__global__ void pack_weights_kernel(UnppPackArgs a) {
+__device__ __forceinline__ void pack_entry(const UnppPackArgs& a) {
   const int nt_count = a.n_total / a.n_tile;
   const int k8_count = a.k_count / 8;
   const long total = long(nt_count) * a.taps * k8_count * a.n_tile;
@@ -29,8 +29,8 @@ __global__ void pack_weights_kernel(UnppPackArgs a) {
     for (int kk = 0; kk < 8; ++kk) {
       const int k = k8 * 8 + kk;
       float w;
-      if (a.kind == 0) {  // B[n=co][tap][k=ci] = W[co][k_begin+ci][tap]
-        w = a.src[(size_t(n) * a.src_I + (a.k_begin + k)) * a.taps + tap];
+      if (a.kind == 0) {  // B[n=co][tap][k=ci] = W[co][k_begin+ci][tap]; input channels beyond src_I are zero padding
+        w = (a.k_begin + k) < a.src_I ? a.src[(size_t(n) * a.src_I + (a.k_begin + k)) * a.taps + tap] : 0.f;
         if (a.scale) w *= a.scale[n];
       } else if (a.kind == 1) {  // B[n=ci][tap][k=co] = W[co][n_begin+ci][taps-1-tap]
         w = a.src[(size_t(a.k_begin + k) * a.src_I + (a.n_begin + n)) * a.taps + (a.taps - 1 - tap)];
@@ -44,7 +44,7 @@ __global__ void pack_weights_kernel(UnppPackArgs a) {
         w = 0.f;
         if (r >= 0 && r <= 2 && s >= 0 && s <= 2) {
           if (a.kind == 4) {
-            w = a.src[(size_t(c) * a.src_I + (a.k_begin + k)) * 9 + r * 3 + s];
+            w = (a.k_begin + k) < a.src_I ? a.src[(size_t(c) * a.src_I + (a.k_begin + k)) * 9 + r * 3 + s] : 0.f;
             if (a.scale) w *= a.scale[c];
           } else {
             w = a.src[(size_t(a.k_begin + k) * a.src_I + (a.n_begin + c)) * 9 + (2 - r) * 3 + (2 - s)];
@@ -56,6 +56,13 @@ __global__ void pack_weights_kernel(UnppPackArgs a) {
     const size_t dst = (((size_t(nt) * a.taps + tap) * a.k8_total + a.k_dst8 + k8) * a.n_tile + nl) * 8;
     *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dst) + dst) = *reinterpret_cast<const uint4*>(v);
   }
+}
+
+__global__ void pack_weights_kernel(UnppPackArgs a) { pack_entry(a); }
+// one launch for a whole table of pack jobs (device-resident): blockIdx.y selects the job
+__global__ void pack_weights_batched_kernel(const UnppPackArgs* __restrict__ table) {
+  const UnppPackArgs a = table[blockIdx.y];
+  pack_entry(a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -173,6 +180,13 @@ extern "C" int unpp_pack_weights(const UnppPackArgs* a, unpp_stream_t stream) {
   const long total = long(a->n_total) * a->taps * (a->k_count / 8);
   pack_weights_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("pack_weights: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_pack_weights_batched(const UnppPackArgs* table_dev, int n, unpp_stream_t stream) {
+  if (!table_dev || n < 1 || n > 65535) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights_batched: bad argument");
+  pack_weights_batched_kernel<<<dim3(8, n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table_dev);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("pack_weights_batched: launch");
   return UNPP_OK;
 }
 

@@ -69,6 +69,7 @@ struct ConvTcParams {
   const __nv_bfloat16* stats_aux;
   const float* aux_mean;
   const float* aux_istd;
+  int nacc;      // accumulator sets in TMEM (2 or 4): the epilogue of tile i overlaps the MMAs of tiles i+1 .. i+nacc-1
   int b2, b2_P;  // 2x2 output blocking: flag, pixel PAIRS per staged tile row (TW/2 + 2)
   int dbg;  // UNPP_DBG experiment bits (0 in production): 1 = epilogue skips its work, 2 = no MMAs issued, 4 = no TMA tile loads
 };
@@ -268,7 +269,7 @@ template <bool DECONV, bool HEAD, bool TRAIN>
 __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   constexpr int kMmaWarps = mma_warps(TRAIN), kThreads = block_threads(TRAIN);
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_acc_full[2], bar_acc_empty[2], bar_w;
+  __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_acc_full[4], bar_acc_empty[4], bar_w;
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_bias[256];
   __shared__ __align__(16) float s_head[8 * 16 + 8];
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], kMmaWarps);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&bar_acc_full[i], kMmaWarps);
       mbar_init(&bar_acc_empty[i], kEpiWarps);
     }
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     // the parameter bank between MMA issues
     mbar_wait(&bar_w, 0);
     const int ncols = p.ncols, nsub = p.nsub, taps = p.taps, k8_total = p.k8_total, nchunk = p.nchunk, nstage = p.nstage;
-    const int ntiles = p.ntiles, stage_bytes = p.stage_bytes, dbg = p.dbg, b2 = p.b2, b2_P = p.b2_P;
+    const int ntiles = p.ntiles, stage_bytes = p.stage_bytes, dbg = p.dbg, b2 = p.b2, b2_P = p.b2_P, nacc = p.nacc;
     const uint32_t idesc = make_idesc_bf16(128, ncols);
     const uint32_t w_addr = smem_u32(w_smem);
     const uint32_t stage_addr0 = smem_u32(stage0);
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     for (int c = 0; c < kMaxChunks; ++c) spans[c] = p.ch_span[c], wk8s[c] = p.ch_wk8[c];
     int it = 0, tile_it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
-      const int b = tile_it & 1, aph = (tile_it >> 1) & 1;
+      const int b = tile_it % nacc, aph = (tile_it / nacc) & 1;
       mbar_wait(&bar_acc_empty[b], aph ^ 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + uint32_t(b * nsub * ncols);
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     e.H = p.H, e.W = p.W, e.cout = p.cout, e.head_classes = p.head_classes, e.out = p.out, e.heat = p.heat, e.logit = p.logit;
     e.drop_mask = p.drop_mask, e.drop_scale = p.drop_scale, e.addend = p.addend, e.relu_mask_src = p.relu_mask_src;
     e.stats_partial = p.stats_partial, e.stats_aux = p.stats_aux, e.aux_mean = p.aux_mean, e.aux_istd = p.aux_istd;
-    const int TW = p.TW, ncols = p.ncols, nsub = p.nsub, ntiles = p.ntiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y, dbg = p.dbg, b2 = p.b2;
+    const int TW = p.TW, ncols = p.ncols, nsub = p.nsub, ntiles = p.ntiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y, dbg = p.dbg, b2 = p.b2, nacc = p.nacc;
     float* const st1 = TRAIN ? &s_stats[TRAIN ? ew : 0][0][0] : nullptr;
     float* const st2 = TRAIN ? &s_stats[TRAIN ? ew : 0][1][0] : nullptr;
     // with <= 2 column groups every unit of this warp has the same 16 channels: keep the statistics in registers
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     for (int k = 0; k < 16; ++k) sa1[k] = 0.f, sa2[k] = 0.f;
     int tile_it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
-      const int b = tile_it & 1, aph = (tile_it >> 1) & 1;
+      const int b = tile_it % nacc, aph = (tile_it / nacc) & 1;
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
       mbar_wait(&bar_acc_full[b], aph);
       tc_fence_after();
@@ -561,7 +562,7 @@ EncodeTiledFn get_encode() {
 
 struct Plan {
   int TW, nsub, nstage, stage_bytes, w_bytes, w_smem_bytes, tmem_cols, smem_total, grid_x, grid_y, tiles_x, tiles_y, ntiles;
-  int nchunk, k8_total, b2, b2_P, ncols;
+  int nchunk, k8_total, b2, b2_P, ncols, nacc;
   int ch_map[kMaxChunks], ch_c0[kMaxChunks], ch_span[kMaxChunks], ch_wk8[kMaxChunks];
 };
 
@@ -614,7 +615,8 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
     if (pl->nstage < 2) return unpp::fail(UNPP_ERR_UNSUPPORTED, "conv_tc: block2x2 weights leave no room for 2 stages (too many sources)");
     if (pl->nstage > kMaxStages) pl->nstage = kMaxStages;
     pl->TW = TW, pl->nsub = TW / 16;
-    pl->tmem_cols = 2 * pl->nsub * 64;
+    pl->nacc = 4 * pl->nsub * 64 <= 512 ? 4 : 2;
+    pl->tmem_cols = pl->nacc * pl->nsub * 64;
     pl->smem_total = 1024 + pl->w_smem_bytes + pl->nstage * pl->stage_bytes;
     pl->tiles_x = (a->W + TW - 1) / TW, pl->tiles_y = (a->H + 31) / 32;
     pl->ntiles = pl->tiles_x * pl->tiles_y * a->N;
@@ -638,7 +640,8 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
   if (2 * (TW / 8) * a->n_tile > 512) return unpp::fail(UNPP_ERR_UNSUPPORTED, "conv_tc: n_tile too large for TMEM double buffering");
   if (pl->nstage > kMaxStages) pl->nstage = kMaxStages;
   pl->TW = TW, pl->nsub = TW / 8;
-  int cols = 2 * pl->nsub * a->n_tile, tc = 32;
+  pl->nacc = 4 * pl->nsub * a->n_tile <= 512 ? 4 : 2;
+  int cols = pl->nacc * pl->nsub * a->n_tile, tc = 32;
   while (tc < cols) tc <<= 1;
   pl->tmem_cols = tc;
   pl->smem_total = 1024 + pl->w_smem_bytes + pl->nstage * pl->stage_bytes;
@@ -707,7 +710,7 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   p.N = a->N, p.H = a->H, p.W = a->W;
   p.TW = pl.TW, p.nsub = pl.nsub, p.tiles_x = pl.tiles_x, p.tiles_y = pl.tiles_y, p.ntiles = pl.ntiles;
   p.taps = a->taps, p.ncols = pl.ncols, p.k8_total = pl.k8_total;
-  p.b2 = pl.b2, p.b2_P = pl.b2_P;
+  p.b2 = pl.b2, p.b2_P = pl.b2_P, p.nacc = pl.nacc;
   p.stage_bytes = pl.stage_bytes, p.nstage = pl.nstage, p.w_bytes = pl.w_bytes, p.w_smem_bytes = pl.w_smem_bytes;
   p.tmem_cols = pl.tmem_cols;
   p.wpacked = reinterpret_cast<const __nv_bfloat16*>(a->wpacked);

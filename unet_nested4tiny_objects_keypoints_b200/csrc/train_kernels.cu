@@ -34,28 +34,48 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------
-// out[i] (+)= scale * sum_p partial[p * stride + i]  — fixed summation order => deterministic
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nparts, long stride, int n, float scale,
-                                       float* __restrict__ out, int accumulate) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += __ldg(partial + p * stride + i);
-    s *= scale;
-    out[i] = accumulate ? out[i] + s : s;
+// Deterministic partial-sum reductions.  A block of 256 threads owns 32 consecutive outputs; its 8
+// warps sum disjoint, interleaved slices of the partials (p = w, w+8, ...), the 8 slice sums are then
+// added in a fixed order — 8x more loads in flight than one thread per output, same result every run.
+template <typename F>
+__device__ __forceinline__ float sliced_sum(int nparts, F load) {
+  __shared__ float red[8][32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  float s = 0.f;
+  for (int p = w; p < nparts; p += 8) s += load(p);
+  red[w][l] = s;
+  __syncthreads();
+  float t = 0.f;
+  if (w == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][l];
+  }
+  __syncthreads();
+  return t;  // valid in warp 0
+}
+
+// out[i] (+)= scale * sum_p partial[p * stride + i]
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nparts, long stride, int n, float scale,
+                                                              float* __restrict__ out, int accumulate) {
+  for (int base = blockIdx.x * 32; base < n; base += gridDim.x * 32) {
+    const int i = base + (threadIdx.x & 31);
+    const float t = sliced_sum(nparts, [&](int p) { return i < n ? __ldg(partial + p * stride + i) : 0.f; });
+    if (threadIdx.x < 32 && i < n) out[i] = accumulate ? out[i] + t * scale : t * scale;
   }
 }
 
 // wgrad partial [nparts][taps][cin_total][cout] -> dst[co*s_co + ci*s_ci + tap*s_tap] for ci < ci_count
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int taps, int cin_total, int cout, float* __restrict__ dst,
-                                    int ci_begin, int ci_count, long s_co, long s_ci, long s_tap, float scale) {
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int taps, int cin_total, int cout,
+                                                           float* __restrict__ dst, int ci_begin, int ci_count, long s_co, long s_ci, long s_tap,
+                                                           float scale) {
   const int n = taps * ci_count * cout;
   const long stride = long(taps) * cin_total * cout;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int base = blockIdx.x * 32; base < n; base += gridDim.x * 32) {
+    const int i = base + (threadIdx.x & 31);
     const int co = i % cout, ci = (i / cout) % ci_count, tap = i / (cout * ci_count);
-    const float* p = partial + (long(tap) * cin_total + ci_begin + ci) * cout + co;
-    float s = 0.f;
-    for (int k = 0; k < nparts; ++k) s += __ldg(p + k * stride);
-    dst[co * s_co + ci * s_ci + tap * s_tap] = s * scale;
+    const float* q = partial + (long(tap) * cin_total + ci_begin + ci) * cout + co;
+    const float t = sliced_sum(nparts, [&](int p) { return i < n ? __ldg(q + p * stride) : 0.f; });
+    if (threadIdx.x < 32 && i < n) dst[co * s_co + ci * s_ci + tap * s_tap] = t * scale;
   }
 }
 
@@ -63,17 +83,27 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int npart
 // BatchNorm2d training statistics (reference models/unet.py:133, nn.BatchNorm2d eps 1e-5 momentum 0.1):
 // reduce the per-CTA (sum, sum of squares) partials of the conv epilogue, produce mean / inverse std
 // and the fused affine (scale, shift), and update the running statistics (unbiased variance).
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nparts, int C, float count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float momentum, float eps, float* __restrict__ mean, float* __restrict__ istd, float* __restrict__ scale,
-                                   float* __restrict__ shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;  // 2*C*nparts values in total: double costs nothing here and removes the E[z^2]-m^2 cancellation
-  for (int p = 0; p < nparts; ++p) {
-    s1 += double(__ldg(partial + (size_t(p) * 2 + 0) * C + c));
-    s2 += double(__ldg(partial + (size_t(p) * 2 + 1) * C + c));
-  }
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int nparts, int C, float count,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps,
+                                                          float* __restrict__ mean, float* __restrict__ istd, float* __restrict__ scale,
+                                                          float* __restrict__ shift) {
+  // block = 32 channels x 8 slices of the partials; sums in double (2*C*nparts values: free, and it removes the
+  // E[z^2]-m^2 cancellation); fixed summation order
+  __shared__ double r1[8][32], r2[8][32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, c = blockIdx.x * 32 + l;
+  double s1 = 0.0, s2 = 0.0;
+  if (c < C)
+    for (int p = w; p < nparts; p += 8) {
+      s1 += double(__ldg(partial + (size_t(p) * 2 + 0) * C + c));
+      s2 += double(__ldg(partial + (size_t(p) * 2 + 1) * C + c));
+    }
+  r1[w][l] = s1, r2[w][l] = s2;
+  __syncthreads();
+  if (w != 0 || c >= C) return;
+  s1 = 0.0, s2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1 += r1[k][l], s2 += r2[k][l];
   const double m = s1 / count;
   double var = s2 / count - m * m;
   if (var < 0.0) var = 0.0;
@@ -350,7 +380,7 @@ __global__ void dropout_mask_kernel(uint4* __restrict__ out, long n16, uint32_t 
 extern "C" int unpp_reduce_partials(const float* partial, int nparts, long stride, int n, float scale, float* out, int accumulate,
                                     unpp_stream_t stream) {
   if (!partial || !out || nparts < 1 || n < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "reduce_partials: bad argument");
-  reduce_partials_kernel<<<grid_for(n, 128), 128, 0, STREAM(stream)>>>(partial, nparts, stride, n, scale, out, accumulate);
+  reduce_partials_kernel<<<grid_for((long(n) + 31) / 32 * 256, 256), 256, 0, STREAM(stream)>>>(partial, nparts, stride, n, scale, out, accumulate);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("reduce_partials: launch");
   return UNPP_OK;
 }
@@ -360,7 +390,7 @@ extern "C" int unpp_wgrad_reduce(const float* partial, int nparts, int taps, int
   if (!partial || !dst || nparts < 1 || taps < 1 || ci_count < 1 || ci_begin < 0 || ci_begin + ci_count > cin_total || cout < 1)
     return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad_reduce: bad argument");
   const int n = taps * ci_count * cout;
-  wgrad_reduce_kernel<<<grid_for(n, 128), 128, 0, STREAM(stream)>>>(partial, nparts, taps, cin_total, cout, dst, ci_begin, ci_count, s_co, s_ci,
+  wgrad_reduce_kernel<<<grid_for((long(n) + 31) / 32 * 256, 256), 256, 0, STREAM(stream)>>>(partial, nparts, taps, cin_total, cout, dst, ci_begin, ci_count, s_co, s_ci,
                                                                    s_tap, scale);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("wgrad_reduce: launch");
   return UNPP_OK;
@@ -371,7 +401,7 @@ extern "C" int unpp_bn_finalize(const float* partial, int nparts, int C, float c
                                 unpp_stream_t stream) {
   if (!partial || !gamma || !beta || !mean || !istd || !scale || !shift || nparts < 1 || C < 1 || !(count >= 1.f))
     return unpp::fail(UNPP_ERR_BAD_ARG, "bn_finalize: bad argument");
-  bn_finalize_kernel<<<(C + 63) / 64, 64, 0, STREAM(stream)>>>(partial, nparts, C, count, gamma, beta, running_mean, running_var, momentum, eps,
+  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, STREAM(stream)>>>(partial, nparts, C, count, gamma, beta, running_mean, running_var, momentum, eps,
                                                                mean, istd, scale, shift);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("bn_finalize: launch");
   return UNPP_OK;

@@ -99,10 +99,8 @@ class Engine:
     def _pack_fwd_conv(self, weight: torch.Tensor, scale, bias):
         w = weight.detach().float()
         cout, cin = w.shape[0], w.shape[1]
-        if cin % 16:  # first layer: 3 input channels live in a 16-channel zero-padded NHWC tensor
-            wp = torch.zeros(cout, 16 * ((cin + 15) // 16), 3, 3, dtype=torch.float32, device=w.device)
-            wp[:, :cin] = w
-            w, cin = wp, wp.shape[1]
+        if cin % 16:  # first layer: 3 input channels live in a 16-channel zero-padded NHWC tensor (the pack kernel zero-fills)
+            cin = 16 * ((cin + 15) // 16)
         if cout == 16 and cin % 16 == 0 and cin <= 64:
             # full-resolution level (every source has 16 channels): 2x2 output-blocked kernel path
             return dict(w=ops.pack_weights_b2(w, False, cin, scale=scale), bias=bias, n_total=cout, n_tile=ops.NTile(16, b2=True))

@@ -18,6 +18,7 @@ from ._lib import ConvArgs, PackArgs, WgradArgs, MODE_CONV, MODE_DECONV  # noqa:
 W_SMEM_BUDGET = 96 * 1024  # packed weights of one n_tile kept resident in shared memory
 
 
+pack_record = None  # when a list: pack_weights() appends its validated PackArgs instead of launching (see pack_batched)
 launch_count = 0   # kernels of libunpp.so enqueued through this module (bench.py reads it for "gpu_launches")
 trace = None       # when a list: conv()/wgrad() append (label, start_event, end_event, algorithmic_bytes, flops)
 
@@ -102,9 +103,23 @@ def pack_weights(src: torch.Tensor, kind: int, taps: int, n_total: int, n_tile: 
     a.kind, a.src_O, a.src_I, a.taps = kind, src.shape[0], src.shape[1], taps
     a.n_total, a.n_tile, a.n_begin = n_total, n_tile, n_begin
     a.k_begin, a.k_count, a.k8_total, a.k_dst8 = k_begin, k_count, k8_total, k_dst8
+    if pack_record is not None:
+        pack_record.append((a, src))  # keep the source tensor alive with its job
+        return dst
     _count()
     _lib.check(lib().unpp_pack_weights(C.byref(a), _stream()), "unpp_pack_weights")
     return dst
+
+
+def make_pack_table(jobs, device) -> torch.Tensor:
+    """Device-resident table of PackArgs (for pack_batched) from the jobs recorded through ``pack_record``."""
+    raw = b"".join(bytes(a) for a, _ in jobs)
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+
+def pack_batched(table: torch.Tensor, n: int) -> None:
+    _count()
+    _lib.check(lib().unpp_pack_weights_batched(table.data_ptr(), n, _stream()), "unpp_pack_weights_batched")
 
 
 def _conv_args(srcs, N, H, W, n_total, n_tile, taps, strided=None, b2=False) -> ConvArgs:

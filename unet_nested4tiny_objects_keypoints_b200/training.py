@@ -138,7 +138,26 @@ def consumers_of(node: str) -> List[Tuple[str, int]]:
 
 def pack_train(ts: TrainState) -> None:
     """(Re)pack every weight the step needs from the current fp32 parameters: forward operands,
-    flipped/transposed dgrad operands, and the gather operands of the fan-out activations."""
+    flipped/transposed dgrad operands, and the gather operands of the fan-out activations.
+    The ~60 pack jobs are recorded once into a device-resident table (source pointers are the
+    parameters' storage, which stays put) and replayed with ONE launch per step."""
+    m = ts.eng.model
+    key = tuple(p.data_ptr() for p in m.parameters())
+    if getattr(ts, "_pack_key", None) == key:
+        ops.pack_batched(ts._pack_table, ts._pack_n)
+        return
+    ops.pack_record = []
+    try:
+        _pack_train_jobs(ts)
+        jobs = ops.pack_record
+    finally:
+        ops.pack_record = None
+    ts._pack_jobs = jobs  # keeps the source views alive
+    ts._pack_table, ts._pack_n, ts._pack_key = ops.make_pack_table(jobs, ts.eng.device), len(jobs), key
+    ops.pack_batched(ts._pack_table, ts._pack_n)
+
+
+def _pack_train_jobs(ts: TrainState) -> None:
     m, P = ts.eng.model, ts.packed
     dev = ts.eng.device
 
@@ -165,11 +184,7 @@ def pack_train(ts: TrainState) -> None:
                 w = conv.weight.detach()
                 cout, cin = w.shape[0], w.shape[1]
                 if cin % 16:
-                    wp = ts.scratch.get("w_in_pad")
-                    if wp is None:
-                        wp = ts.scratch["w_in_pad"] = torch.zeros(cout, 16, 3, 3, dtype=torch.float32, device=dev)
-                    wp[:, :cin] = w
-                    w, cin = wp, 16
+                    cin = 16 * ((cin + 15) // 16)  # first layer: the pack kernel zero-fills input channels >= 3
                 put(f"{name}.c{n}.fwd", w, 0, 9, cout, cin, n_tile=pick_n_tile(cout, cin, 9))
             w2 = _w2(m, name).weight.detach()
             c = w2.shape[0]
