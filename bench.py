@@ -274,6 +274,12 @@ def bench_infer(args, rank, world, local):
         roof = roofline_from_trace(agg, reps, "conv_tc", pk)
         step_ms = ms / args.steps
         roof["share_of_step"] = round(roof["ms_per_step_in_kernel"] / step_ms, 3)
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+            with open(tpath) as f:
+                tj = json.load(f)
+            roof["traffic"] = round(tj["traffic_bytes_per_launch_avg"])
+            roof["traffic_source"] = tj["source"]
         whole = {"algorithmic_bytes_per_image": ALGO_BYTES_PER_IMG_INFER, "achieved_gbs": round(ALGO_BYTES_PER_IMG_INFER * INFER_B / (step_ms * 1e-3) / 1e9, 1),
                  "frac_of_hbm_peak": round(ALGO_BYTES_PER_IMG_INFER * INFER_B / (step_ms * 1e-3) / 1e9 / pk["hbm"], 4),
                  "tflops": round(ALGO_FLOPS_PER_IMG_INFER * INFER_B / (step_ms * 1e-3) / 1e12, 1)}
