@@ -36,6 +36,7 @@ TRAIN_B1 = 32
 TRAIN_GLOBAL = 256
 ALGO_BYTES_PER_IMG_INFER = 62.05e6   # fused plan, bf16 activations, 256x256
 ALGO_FLOPS_PER_IMG_INFER = 8.789e9
+CONFIG_TAG = "configs[1]"
 
 
 def peaks():
@@ -222,7 +223,7 @@ def metric_name(workload):
 
 def config_of(workload, world):
     if workload == "infer":
-        return {"workload": f"configs[1]: UNet_Nested eval forward, batch {INFER_B}/GPU, 3x{S}x{S} fp32 in, fused head + heat-map arg-max keypoints",
+        return {"workload": f"{CONFIG_TAG}: UNet_Nested eval forward, batch {INFER_B}/GPU, 3x{S}x{S} fp32 in, fused head + heat-map arg-max keypoints",
                 "batch_per_gpu": INFER_B, "image": [3, S, S], "l2": "activation working set (>= 268 MB per level-0 tensor) is larger than the 126 MB L2; no flush needed",
                 "parallelism": f"dp{world} (independent shards, no collective)", "cuda_graph": True}
     b = TRAIN_B1 if world == 1 else TRAIN_GLOBAL // world
@@ -353,9 +354,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="infer", choices=["infer", "train"])
+    ap.add_argument("--workload", default="infer", choices=["infer", "train", "infer1024"])
     ap.add_argument("--no-extra", action="store_true", help="skip the cpu_baseline leg and the extra training measurement")
     args = ap.parse_args()
+    if args.workload == "infer1024":  # BASELINE.json configs[4]: high-resolution inference, batch 16 at 1024x1024
+        global S, INFER_B, ALGO_BYTES_PER_IMG_INFER, ALGO_FLOPS_PER_IMG_INFER, CONFIG_TAG
+        S, INFER_B, ALGO_BYTES_PER_IMG_INFER, ALGO_FLOPS_PER_IMG_INFER, CONFIG_TAG = 1024, 16, 976.3e6, 140.63e9, "configs[4]"
+        args.workload, args.no_extra = "infer", True
 
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))

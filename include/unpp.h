@@ -175,10 +175,12 @@ int unpp_maxpool2x2_bwd(const void* x, const void* dpooled, void* dx, int N, int
 int unpp_bn_bwd_apply(const void* dyh, const void* z, const float* mean, const float* istd, const float* gamma, const float* sums,
                       float count, void* dz, int N, int H, int W, int C, unpp_stream_t stream);
 /* Head backward (sigmoid' + 1x1 conv dgrad/wgrad + dropout mask).  Exactly one of dheat (upstream
- * gradient, fp32 NCHW) and target (fused MSE: dheat = coef*(heat-target), loss partial = sum (heat-target)^2)
- * is non-NULL.  dx is already multiplied by the ReLU mask [x > 0] of the conv that produced x.
+ * gradient, fp32 NCHW) and target is non-NULL.  With target the loss gradient is fused:
+ *   loss_kind 0, nn.MSELoss (trainer/trainer.py:427): dheat = coef*(heat-target), loss partial = sum (heat-target)^2
+ *   loss_kind 1, FocalLoss_BCE_2d (tools/losses/focal_loss.py:264-301, the criterion the trainer ships, trainer.py:426):
+ *                a = |heat-target|, e = 1-a+1e-20, loss partial = sum -a^gamma*log(e), dheat = coef * d/dheat of that term  dx is already multiplied by the ReLU mask [x > 0] of the conv that produced x.
  * partial: fp32 [unpp_head_bwd_grid()][classes*16 + classes + 1 + 16] = dW, db, loss, per-channel sum of dx. */
-int unpp_head_bwd(const float* heat, const float* dheat, const float* target, float coef, const void* x, const uint8_t* drop_mask,
+int unpp_head_bwd(const float* heat, const float* dheat, const float* target, int loss_kind, float gamma, float coef, const void* x, const uint8_t* drop_mask,
                   float drop_scale, const float* head_w, int classes, void* dx, float* partial, int N, int H, int W,
                   unpp_stream_t stream);
 int unpp_head_bwd_grid(int N, int H, int W);

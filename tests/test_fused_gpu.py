@@ -87,3 +87,39 @@ def test_fused_train_step_dropout_masks_change_every_replay():
     m2 = step.ts.t["mask0"].clone()
     assert not torch.equal(m1, m2)
     assert abs(float(m1.float().mean()) - 0.6) < 0.05
+
+
+def test_fused_train_step_with_the_shipped_focal_criterion():
+    """trainer.py:426 ships FocalLoss_BCE_2d(gamma=3); fused into the head backward like the MSE."""
+    sd = O.synth_state_dict(seed=33)
+    m = pkg.UNet_Nested()
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    m.drop_out.p = 0.0
+    B, H, W = 2, 32, 32
+    step = fused.FusedTrainStep(m, B, H, W, loss="focal", lr=1e-4)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(B, 3, H, W, generator=g)
+    target = torch.rand(B, 4, H, W, generator=g)
+    loss = step.step(x.pin_memory(), target.pin_memory())
+    torch.cuda.synchronize()
+    rl, _, rg, _ = O.train_step_grads(sd, x, target, dropout_masks=None, loss="focal")
+    assert abs(float(loss) - float(rl)) <= 2e-2 * abs(float(rl))
+    grads = {k: step.flat_g[off:off + n].view_as(p) for (k, p), (off, n) in zip(m.named_parameters(), step.ts.lay.values())}
+    check_grads(grads, rg)
+
+
+def test_reference_adamw_dropin_optimizer_matches_reference_semantics(golden):
+    from unet_nested4tiny_objects_keypoints_b200.optimizers import AdamW
+    arr, meta = golden
+    h = meta["adamw_hyper"]
+    params = [torch.nn.Parameter(torch.from_numpy(arr[f"adamw_p0_{j}"]).cuda()) for j in range(2)]
+    opt = AdamW(params, lr=h["lr"], betas=tuple(h["betas"]), eps=h["eps"], weight_decay=h["weight_decay"])
+    for s in range(3):
+        for j, p in enumerate(params):
+            p.grad = torch.from_numpy(arr[f"adamw_g{s}_{j}"]).cuda()
+        opt.step()
+    for j, p in enumerate(params):
+        assert np.allclose(p.detach().cpu().numpy(), arr[f"adamw_p3_{j}"], rtol=2e-6, atol=1e-7)
+    with pytest.raises(NotImplementedError):
+        AdamW(params, amsgrad=True)

@@ -295,7 +295,7 @@ def test_maxpool_backward_first_max_wins():
     assert torch.equal(nchw(dx).double(), xx.grad)
 
 
-@pytest.mark.parametrize("mode", ["upstream", "mse"])
+@pytest.mark.parametrize("mode", ["upstream", "mse", "focal"])
 def test_head_backward(mode):
     N, H, W = 2, 16, 24
     x = bf(F.relu(rnd(N, 16, H, W, seed=90)))  # output of a ReLU conv: the kernel also applies that ReLU's mask
@@ -310,6 +310,11 @@ def test_head_backward(mode):
     if mode == "mse":
         (((heat_ref - target.double()) ** 2).sum() * coef / 2).backward()
         dheat = None
+    elif mode == "focal":  # FocalLoss_BCE_2d(gamma=3), mean over 3 heads (oracle restatement pinned to the reference)
+        from oracle import unetpp_oracle as O
+        coef = 1.0 / (3 * N * 4)
+        (O.focal_loss_bce_2d(heat_ref, target.double(), gamma=3.0) / 3).backward()
+        dheat = None
     else:
         dheat = rnd(N, 4, H, W, seed=95)
         heat_ref.backward(dheat.double())
@@ -317,8 +322,8 @@ def test_head_backward(mode):
     partial = torch.full((g, 4 * 16 + 4 + 1 + 16), float("nan"), device=DEV)
     dx = torch.empty(N, H, W, 16, dtype=torch.bfloat16, device=DEV)
     m8 = mask.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(DEV)
-    ops.head_bwd(heat.to(DEV), None if dheat is None else dheat.to(DEV), target.to(DEV) if mode == "mse" else None, coef, nhwc(x), m8, 1 / 0.6,
-                 hw.to(DEV), dx, partial)
+    ops.head_bwd(heat.to(DEV), None if dheat is None else dheat.to(DEV), target.to(DEV) if mode != "upstream" else None, coef, nhwc(x), m8, 1 / 0.6,
+                 hw.to(DEV), dx, partial, loss_kind=1 if mode == "focal" else 0, gamma=3.0)
     dx_ref = xx.grad * (x > 0)
     close(nchw(dx), dx_ref, 6e-3, "head dx")
     red = torch.empty(85, device=DEV)
@@ -326,6 +331,9 @@ def test_head_backward(mode):
     close(red[69:].cpu(), nchw(dx).double().sum((0, 2, 3)), 1e-4, "dx channel sums")
     close(red[:64].cpu().view(4, 16), w64.grad, 2e-3, "head dW")
     close(red[64:68].cpu(), b64.grad, 2e-3, "head db")
+    if mode == "focal":
+        a = (heat.double() - target.double()).abs()
+        close(red[68:69].cpu(), (-(a ** 3) * torch.log(1 - a + 1e-20)).sum().reshape(1), 1e-4, "focal loss sum")
     if mode == "mse":
         close(red[68:69].cpu(), ((heat.double() - target.double()) ** 2).sum().reshape(1), 1e-4, "loss sum")
 

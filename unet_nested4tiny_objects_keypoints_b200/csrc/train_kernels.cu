@@ -237,7 +237,7 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dyh, const uint4* 
 // the end, written to partial[blockIdx.x][NCLS*16 + NCLS + 1 + 16] = dW, db, loss, dxsum.
 template <int NCLS>
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ heat, const float* __restrict__ dheat, const float* __restrict__ target,
-                                                       float coef, const uint4* __restrict__ x, const uint4* __restrict__ mask, float drop_scale,
+                                                       int loss_kind, float gamma, float coef, const uint4* __restrict__ x, const uint4* __restrict__ mask, float drop_scale,
                                                        const float* __restrict__ head_w, uint4* __restrict__ dx, float* __restrict__ partial,
                                                        int N, long HW) {
   constexpr int NACC = NCLS * 16 + NCLS + 1 + 16, LOSS = NCLS * 16 + NCLS;
@@ -260,8 +260,15 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       float dh;
       if (target) {
         const float d = pr - __ldg(target + o);
-        acc[LOSS] += d * d;
-        dh = coef * d;
+        if (loss_kind == 0) {  // MSE: loss += d^2, d loss / d p = coef * d
+          acc[LOSS] += d * d;
+          dh = coef * d;
+        } else {  // FocalLoss_BCE_2d (tools/losses/focal_loss.py:264-301): a = |p-t|, e = 1-a+1e-20, loss += -a^gamma * log(e)
+          const float a = fabsf(d), e = 1.f - a + 1e-20f;
+          const float le = logf(e), pg1 = a > 0.f ? powf(a, gamma - 1.f) : 0.f;
+          acc[LOSS] += -(pg1 * a) * le;
+          dh = coef * copysignf(-gamma * pg1 * le + (pg1 * a) / e, d);
+        }
       } else {
         dh = __ldg(dheat + o);
       }
@@ -448,15 +455,16 @@ extern "C" int unpp_bn_bwd_apply(const void* dyh, const void* z, const float* me
 
 extern "C" int unpp_head_bwd_grid(int N, int H, int W) { return grid_for(long(N) * H * W, 256, 2); }
 
-extern "C" int unpp_head_bwd(const float* heat, const float* dheat, const float* target, float coef, const void* x, const uint8_t* drop_mask,
+extern "C" int unpp_head_bwd(const float* heat, const float* dheat, const float* target, int loss_kind, float gamma, float coef, const void* x, const uint8_t* drop_mask,
                              float drop_scale, const float* head_w, int classes, void* dx, float* partial, int N, int H, int W,
                              unpp_stream_t stream) {
   if (!heat || (!dheat && !target) || !x || !head_w || !dx || !partial || N < 1 || H < 1 || W < 1)
     return unpp::fail(UNPP_ERR_BAD_ARG, "head_bwd: bad argument");
+  if (loss_kind != 0 && loss_kind != 1) return unpp::fail(UNPP_ERR_BAD_ARG, "head_bwd: loss_kind must be 0 (MSE) or 1 (focal BCE)");
   const int grid = unpp_head_bwd_grid(N, H, W);
   const long HW = long(H) * W;
 #define LAUNCH(NC)                                                                                                                        \
-  head_bwd_kernel<NC><<<grid, 256, 0, STREAM(stream)>>>(heat, dheat, target, coef, reinterpret_cast<const uint4*>(x),                      \
+  head_bwd_kernel<NC><<<grid, 256, 0, STREAM(stream)>>>(heat, dheat, target, loss_kind, gamma, coef, reinterpret_cast<const uint4*>(x),                      \
                                                         reinterpret_cast<const uint4*>(drop_mask), drop_scale, head_w,                     \
                                                         reinterpret_cast<uint4*>(dx), partial, N, HW)
   switch (classes) {

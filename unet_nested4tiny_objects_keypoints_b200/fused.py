@@ -151,7 +151,8 @@ class InferenceSession:
 
 class FusedTrainStep:
     def __init__(self, model, B: int, H: int, W: int, lr: float = 3e-6, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-4, device="cuda", use_graph: bool = True, process_group=None, seed: int = 0):
+                 weight_decay: float = 1e-4, device="cuda", use_graph: bool = True, process_group=None, seed: int = 0, loss: str = "mse",
+                 focal_gamma: float = 3.0):
         """Defaults follow the reference CLI: ``--optimizer adamw --lr 3e-6 --weight-decay 1e-4`` (train.py:38-45)."""
         self.model = model
         self.dev = _device(device)
@@ -185,7 +186,14 @@ class FusedTrainStep:
         self.x = torch.zeros(B, model.in_channels, H, W, dtype=torch.float32, device=self.dev)
         self.target = torch.zeros(B, model.n_classes, H, W, dtype=torch.float32, device=self.dev)
         self.numel_head = B * model.n_classes * H * W
-        self.coef = 2.0 / (3.0 * self.numel_head)  # d/dp of (1/3) sum_k mean((p_k - T)^2)
+        if loss == "mse":      # (1/3) sum_k mean((p_k - T)^2): nn.MSELoss per head (trainer.py:427), mean of the heads (trainer.py:125-134)
+            self.loss_kind, self.coef, self.loss_scale = 0, 2.0 / (3.0 * self.numel_head), 1.0 / (3.0 * self.numel_head)
+        elif loss == "focal":  # (1/3) sum_k FocalLoss_BCE_2d(gamma)(p_k, T): sum over pixels / (B*C) (focal_loss.py:282,301; trainer.py:426)
+            self.loss_kind = 1
+            self.coef = self.loss_scale = 1.0 / (3.0 * B * model.n_classes)
+        else:
+            raise ValueError("loss must be 'mse' or 'focal'")
+        self.focal_gamma = focal_gamma
         self.graph_a = self.graph_b = None
         self.steps_done = 0
         with torch.cuda.device(self.dev):
@@ -229,9 +237,9 @@ class FusedTrainStep:
             for k in range(3):
                 ops.dropout_mask(ts.t[f"mask{k}"].view(-1), self.p_drop, self.seed * 7919 + k, self.step_counter)
         forward_train(ts, self.x)
-        backward_train(ts, self.flat_g, target=self.target, coef=self.coef)
+        backward_train(ts, self.flat_g, target=self.target, coef=self.coef, loss_kind=self.loss_kind, gamma=self.focal_gamma)
         nacc, ncls = ts.head_nacc, self.model.n_classes
-        ops.reduce_partials(ts.t["head_red"], 3, nacc, 1, self.loss, scale=1.0 / (3.0 * self.numel_head), partial_offset=ncls * 17)
+        ops.reduce_partials(ts.t["head_red"], 3, nacc, 1, self.loss, scale=self.loss_scale, partial_offset=ncls * 17)
 
     def _update(self):
         h = self.hyper

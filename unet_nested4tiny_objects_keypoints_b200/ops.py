@@ -290,10 +290,10 @@ def head_bwd_grid(N: int, H: int, W: int) -> int:
     return lib().unpp_head_bwd_grid(N, H, W)
 
 
-def head_bwd(heat, dheat, target, coef, x, drop_mask, drop_scale, head_w, dx, partial) -> None:
+def head_bwd(heat, dheat, target, coef, x, drop_mask, drop_scale, head_w, dx, partial, loss_kind: int = 0, gamma: float = 3.0) -> None:
     N, ncls, H, W = heat.shape
     _count()
-    _lib.check(lib().unpp_head_bwd(heat.data_ptr(), _ptr(dheat), _ptr(target), float(coef), x.data_ptr(), _ptr(drop_mask), float(drop_scale),
+    _lib.check(lib().unpp_head_bwd(heat.data_ptr(), _ptr(dheat), _ptr(target), int(loss_kind), float(gamma), float(coef), x.data_ptr(), _ptr(drop_mask), float(drop_scale),
                                    head_w.data_ptr(), ncls, dx.data_ptr(), partial.data_ptr(), N, H, W, _stream()), "unpp_head_bwd")
 
 

@@ -270,7 +270,7 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
 
 # ---------------------------------------------------------------------------------------------- backward
 def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Optional[torch.Tensor]]] = None, target: Optional[torch.Tensor] = None,
-                   coef: float = 0.0) -> None:
+                   coef: float = 0.0, loss_kind: int = 0, gamma: float = 3.0) -> None:
     """Fills the flat fp32 gradient buffer ``G`` (layout ``ts.lay``).  Either ``dheats`` (upstream
     gradients of the three heat maps, fp32 NCHW; ``None`` entries mean zero) or ``target`` + ``coef``
     (fused MSE: d heat = coef * (heat - target); the summed squared error lands in
@@ -325,7 +325,7 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
             dh = torch.zeros_like(ts.heats[k])
         if True:
             ops.head_bwd(ts.heats[k], dh, target if dh is None else None, coef, t[f"X{name[-2:]}"], t[f"mask{k}"] if ts.use_masks else None,
-                         ts.drop_scale, hm.weight.view(ncls, -1), t[f"dXh{k}"], part)
+                         ts.drop_scale, hm.weight.view(ncls, -1), t[f"dXh{k}"], part, loss_kind=loss_kind, gamma=gamma)
             ops.reduce_partials(part, ts.head_grid, ts.head_nacc, ts.head_nacc, t["head_red"][k])
         ops.reduce_partials(t["head_red"], 1, 0, ncls * 16, G, out_offset=goff(hname + ".weight"), partial_offset=k * ts.head_nacc)
         ops.reduce_partials(t["head_red"], 1, 0, ncls, G, out_offset=goff(hname + ".bias"), partial_offset=k * ts.head_nacc + ncls * 16)
