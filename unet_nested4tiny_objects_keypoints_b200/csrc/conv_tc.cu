@@ -211,10 +211,11 @@ __device__ __forceinline__ void epilogue_group(const EpiArgs& p, float (&v)[16],
       float s1[16], s2[16];
       const uint32_t xw[8] = {t.x0.x, t.x0.y, t.x0.z, t.x0.w, t.x1.x, t.x1.y, t.x1.z, t.x1.w};
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float r = valid ? __bfloat162float(__float2bfloat16_rn(v[k])) : 0.f;
-        const float aux = (k & 1) ? bf16_hi(xw[k >> 1]) : bf16_lo(xw[k >> 1]);
-        s1[k] = r, s2[k] = r * (p.stats_aux ? aux : r);
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t pk = valid ? pack_bf16x2(v[2 * k], v[2 * k + 1]) : 0u;  // exactly the two bf16 values that get stored
+        const float r0 = bf16_lo(pk), r1 = bf16_hi(pk);
+        s1[2 * k] = r0, s1[2 * k + 1] = r1;
+        s2[2 * k] = r0 * (p.stats_aux ? bf16_lo(xw[k]) : r0), s2[2 * k + 1] = r1 * (p.stats_aux ? bf16_hi(xw[k]) : r1);
       }
       if (reg_stats) {
 #pragma unroll
@@ -487,9 +488,14 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
       const int y = b2 ? ty * 32 + 2 * pi : ty * 16 + pi;
       const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * nsub * ncols);
       uint32_t raw[16];
-      int u = (dbg & 1) ? units : half;
-      if (u < units) tmem_ld16(tbase + uint32_t(u * 16), raw);  // unit u covers columns [16u, 16u+16) of this accumulator set
-      for (; u < units; u += 2) {
+      // classic: this warp takes units half, half+2, ...; 2x2: it takes block row jy = half and walks (sub-tile, jx), so
+      // that the two horizontally adjacent pixels of a block (64 contiguous bytes) are read / written back to back
+      const bool pair_order = TRAIN && b2;  // (the plain inference epilogue measured slightly faster with the interleaved split)
+      const int nit = (dbg & 1) ? 0 : (pair_order ? nsub * 2 : (units - half + 1) / 2);
+      auto unit_of = [&](int it) { return pair_order ? ((it >> 1) * 4 + half * 2 + (it & 1)) : half + 2 * it; };
+      if (nit > 0) tmem_ld16(tbase + uint32_t(unit_of(0) * 16), raw);  // unit u covers columns [16u, 16u+16) of this accumulator set
+      for (int it = 0; it < nit; ++it) {
+        const int u = unit_of(it);
         // classic: unit = (8-pixel-wide sub-tile j, 16-column group); 2x2: unit = (16-pixel-wide sub-tile, pixel of the block)
         const int j = b2 ? (u >> 2) : u / ncb, c0 = b2 ? 0 : (u % ncb) * 16;
         const int yy = b2 ? y + ((u >> 1) & 1) : y;
@@ -501,7 +507,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
         float v[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(raw[k]);
-        if (u + 2 < units) tmem_ld16(tbase + uint32_t((u + 2) * 16), raw);
+        if (it + 1 < nit) tmem_ld16(tbase + uint32_t(unit_of(it + 1) * 16), raw);
         epilogue_group<DECONV, HEAD, TRAIN>(e, v, tops, n, yy, x, valid, b2 ? 0 : ntile_idx * ncols + c0, c0, s_bias, s_head, relu_floor, reg_stats,
                                             sa1, sa2, st1, st2, lane);
       }
