@@ -71,7 +71,8 @@ struct ConvTcParams {
   const float* aux_istd;
   int nacc;      // accumulator sets in TMEM (2 or 4): the epilogue of tile i overlaps the MMAs of tiles i+1 .. i+nacc-1
   int b2, b2_P;  // 2x2 output blocking: flag, pixel PAIRS per staged tile row (TW/2 + 2)
-  int dbg;  // UNPP_DBG experiment bits (0 in production): 1 = epilogue skips its work, 2 = no MMAs issued, 4 = no TMA tile loads
+  int dbg;  // UNPP_DBG experiment bits (0 in production): 1 = epilogue skips its work, 2 = no MMAs issued, 4 = no TMA tile loads,
+            // 8 = epilogue does not store its bf16 output, 16 = epilogue does not read TMEM
 };
 
 __device__ __forceinline__ uint32_t layout_type_of_span(int span) { return span == 128 ? 2u : span == 64 ? 4u : 6u; }
@@ -115,7 +116,7 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
 // accumulators of this thread's pixel for GEMM columns [gcol, gcol+16).
 // Register-resident copy of the epilogue parameters (read once from the parameter bank).
 struct EpiArgs {
-  int H, W, cout, head_classes;
+  int H, W, cout, head_classes, dbg;
   __nv_bfloat16* out;
   float* heat;
   float* logit;
@@ -229,7 +230,7 @@ __device__ __forceinline__ void epilogue_group(const EpiArgs& p, float (&v)[16],
       }
     }
   }
-  if (p.out && valid) {
+  if (p.out && valid && !(p.dbg & 8)) {
     uint4 o0, o1;
     o0.x = pack_bf16x2(v[0], v[1]), o0.y = pack_bf16x2(v[2], v[3]), o0.z = pack_bf16x2(v[4], v[5]), o0.w = pack_bf16x2(v[6], v[7]);
     o1.x = pack_bf16x2(v[8], v[9]), o1.y = pack_bf16x2(v[10], v[11]), o1.z = pack_bf16x2(v[12], v[13]), o1.w = pack_bf16x2(v[14], v[15]);
@@ -468,6 +469,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     const int ncb = p.ncols >> 4, units = p.nsub * ncb;
     const float relu_floor = p.relu ? 0.f : -INFINITY;
     EpiArgs e;
+    e.dbg = p.dbg;
     e.H = p.H, e.W = p.W, e.cout = p.cout, e.head_classes = p.head_classes, e.out = p.out, e.heat = p.heat, e.logit = p.logit;
     e.drop_mask = p.drop_mask, e.drop_scale = p.drop_scale, e.addend = p.addend, e.relu_mask_src = p.relu_mask_src;
     e.stats_partial = p.stats_partial, e.stats_aux = p.stats_aux, e.aux_mean = p.aux_mean, e.aux_istd = p.aux_istd;
@@ -493,7 +495,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
       const bool pair_order = TRAIN && b2;  // (the plain inference epilogue measured slightly faster with the interleaved split)
       const int nit = (dbg & 1) ? 0 : (pair_order ? nsub * 2 : (units - half + 1) / 2);
       auto unit_of = [&](int it) { return pair_order ? ((it >> 1) * 4 + half * 2 + (it & 1)) : half + 2 * it; };
-      if (nit > 0) tmem_ld16(tbase + uint32_t(unit_of(0) * 16), raw);  // unit u covers columns [16u, 16u+16) of this accumulator set
+      if (nit > 0 && !(dbg & 16)) tmem_ld16(tbase + uint32_t(unit_of(0) * 16), raw);  // unit u covers columns [16u, 16u+16) of this accumulator set
       for (int it = 0; it < nit; ++it) {
         const int u = unit_of(it);
         // classic: unit = (8-pixel-wide sub-tile j, 16-column group); 2x2: unit = (16-pixel-wide sub-tile, pixel of the block)
@@ -503,11 +505,11 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
         const bool valid = (yy < e.H) && (x < e.W);
         TrainOperands tops;
         prefetch_train<TRAIN>(e, tops, (size_t(n) * e.H + yy) * e.W + x, ntile_idx * ncols * (b2 ? 0 : 1) + c0, valid);
-        tmem_ld_wait16(raw);
+        if (!(dbg & 16)) tmem_ld_wait16(raw);
         float v[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(raw[k]);
-        if (it + 1 < nit) tmem_ld16(tbase + uint32_t(unit_of(it + 1) * 16), raw);
+        if (it + 1 < nit && !(dbg & 16)) tmem_ld16(tbase + uint32_t(unit_of(it + 1) * 16), raw);
         epilogue_group<DECONV, HEAD, TRAIN>(e, v, tops, n, yy, x, valid, b2 ? 0 : ntile_idx * ncols + c0, c0, s_bias, s_head, relu_floor, reg_stats,
                                             sa1, sa2, st1, st2, lane);
       }
@@ -611,7 +613,8 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
     pl->b2 = 1, pl->ncols = 64;
     pl->w_bytes = 16 * k8 * 64 * 16;
     pl->w_smem_bytes = (pl->w_bytes + 1023) / 1024 * 1024;
-    int TW = a->W > 16 ? 32 : 16;
+    // widest tile that leaves room for two stages: fewer tiles (less per-tile handshake), more sub-tiles (more issuers busy)
+    int TW = a->W > 32 ? 64 : a->W > 16 ? 32 : 16;
     for (;; TW >>= 1) {
       pl->b2_P = TW / 2 + 2;
       pl->stage_bytes = (34 * pl->b2_P * 64 + 1023) / 1024 * 1024;
