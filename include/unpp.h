@@ -82,6 +82,16 @@ typedef struct UnppConvArgs {
    * 2x2 pixel block, N = 4*16, K walks the 4x4 input window -> 16 instead of 36 MMAs per 512 pixels.
    * wpacked must then be packed with kind 4 (forward) or 5 (dgrad), taps = 16, n_total = n_tile = 64. */
   int32_t block2x2;
+  /* Fused transposed conv (inference, with block2x2): conv3x3(cat[ConvTranspose2d_k2s2(low), src...]) — the k2s2
+   * upsample never overlaps, so its branch collapses into a 3x3 conv over the LOW-resolution tensor with
+   * composed weights whose 64 GEMM columns are (pixel of the 2x2 block, co): one more K chunk of the same
+   * accumulators.  lowres_src: NHWC bf16 [N, H/2, W/2, lowres_C] (lowres_C = 32); lowres_wpacked: kind-0 packing
+   * of the composed [64][lowres_C][3][3] weight (taps 9, n_total = n_tile = 64).  The upsample bias reaches
+   * fewer taps at the image border: bias is then a [9][16] table indexed by (row class, column class). */
+  const void* lowres_src;
+  const void* lowres_wpacked;
+  int32_t lowres_C;
+  int32_t bias_classes;         /* 0/1: bias[Cout]; 9: bias[3*rowclass+colclass][16], class 0 first, 1 interior, 2 last */
 } UnppConvArgs;
 
 const char* unpp_last_error(void);
@@ -90,7 +100,8 @@ int unpp_num_sms(void);
 
 /* Fused implicit-GEMM convolution on tcgen05 tensor cores (TMA-staged NHWC bf16 halo tiles). */
 int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream);
-/* Number of CTAs unpp_conv_tc will launch for these args (size of stats_partial's leading dim). */
+/* Number of CTAs unpp_conv_tc will launch for these args (size of stats_partial's leading dim).  The tiling depends
+ * on which epilogue variant runs, so query with the SAME args as the launch (in particular a non-NULL stats_partial). */
 int unpp_conv_grid(const UnppConvArgs* a);
 
 /* Weight packing into the UMMA B-operand layout [n_total/n_tile][taps][K/8][n_tile][8] (bf16).

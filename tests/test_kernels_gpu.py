@@ -433,3 +433,26 @@ def test_block2x2_dgrad_gather_mask_stats(ncons):
     close(sums[:16].cpu(), got.double().sum((0, 2, 3)), 1e-3, "sum v")
     xhat = (aux.double() - mean.double()[None, :, None, None]) * istd.double()[None, :, None, None]
     close(sums[16:].cpu(), (got.double() * xhat).sum((0, 2, 3)), 2e-3, "sum v*xhat")
+
+
+@pytest.mark.parametrize("N,H,W,nlows", [(2, 32, 32, 1), (1, 24, 40, 2), (2, 64, 64, 3), (1, 8, 8, 1), (1, 128, 64, 2)])
+def test_fused_transposed_conv_into_block2x2_conv(N, H, W, nlows):
+    """conv3x3(cat[ConvTranspose2d_k2s2(x_low), lows...]) + bias + ReLU in ONE launch, the upsampled tensor never exists."""
+    from unet_nested4tiny_objects_keypoints_b200.engine import compose_deconv_conv
+    xlow = bf(rnd(N, 32, H // 2, W // 2, seed=200))
+    lows = [bf(rnd(N, 16, H, W, seed=201 + i)) for i in range(nlows)]
+    w_up = rnd(32, 16, 2, 2, seed=210, scale=0.2)
+    b_up = rnd(16, seed=211, scale=0.3)
+    cin = 16 * (1 + nlows)
+    w = rnd(16, cin, 3, 3, seed=212, scale=(2.0 / (9 * cin)) ** 0.5)
+    b = rnd(16, seed=213, scale=0.1)
+    up = F.conv_transpose2d(xlow.double(), w_up.double(), b_up.double(), stride=2)
+    ref = F.relu(F.conv2d(torch.cat([up] + [l.double() for l in lows], 1), w.double(), b.double(), padding=1))
+    comp, table = compose_deconv_conv(w[:, :16].to(DEV), w_up.to(DEV), b_up.to(DEV), b.to(DEV))
+    wp = ops.pack_weights_b2(w.to(DEV), False, 16 * nlows, k_begin=16)
+    lw = ops.pack_weights(comp, 0, 9, 64, 64, 32)
+    out = torch.empty(N, H, W, 16, dtype=torch.bfloat16, device=DEV)
+    ops.conv([nhwc(l) for l in lows], N, H, W, wp, 16, ops.NTile(16, b2=True), 9, bias=table, bias_classes=9, relu=True, out=out,
+             lowres=(nhwc(xlow), lw))
+    torch.cuda.synchronize()
+    close(nchw(out), ref, 8e-3, "fused transposed conv")

@@ -51,6 +51,10 @@ class ConvArgs(C.Structure):
         ("aux_mean", C.c_void_p),
         ("aux_istd", C.c_void_p),
         ("block2x2", C.c_int32),
+        ("lowres_src", C.c_void_p),
+        ("lowres_wpacked", C.c_void_p),
+        ("lowres_C", C.c_int32),
+        ("bias_classes", C.c_int32),
     ]
 
 

@@ -71,6 +71,11 @@ struct ConvTcParams {
   const float* aux_istd;
   int nacc;      // accumulator sets in TMEM (2 or 4): the epilogue of tile i overlaps the MMAs of tiles i+1 .. i+nacc-1
   int b2, b2_P;  // 2x2 output blocking: flag, pixel PAIRS per staged tile row (TW/2 + 2)
+  // fused transposed conv (with b2): one extra K chunk per tile read from the low-resolution tensor
+  CUtensorMap lowmap;
+  int low_on, low_P, low_k8, low_w_off, low_w_bytes;  // low_P = low-res pixels per staged tile row (TW/2 + 2); offsets in bytes
+  const __nv_bfloat16* low_wpacked;
+  int bias9;     // bias is a [9][16] (row class, column class) table
   int dbg;  // UNPP_DBG experiment bits (0 in production): 1 = epilogue skips its work, 2 = no MMAs issued, 4 = no TMA tile loads,
             // 8 = epilogue does not store its bf16 output, 16 = epilogue does not read TMEM
 };
@@ -116,7 +121,7 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
 // accumulators of this thread's pixel for GEMM columns [gcol, gcol+16).
 // Register-resident copy of the epilogue parameters (read once from the parameter bank).
 struct EpiArgs {
-  int H, W, cout, head_classes, dbg;
+  int H, W, cout, head_classes, dbg, bias9;
   __nv_bfloat16* out;
   float* heat;
   float* logit;
@@ -166,7 +171,9 @@ __device__ __forceinline__ void epilogue_group(const EpiArgs& p, float (&v)[16],
                                                int gcol, int c0, const float* s_bias, const float* s_head, float relu_floor, bool reg_stats,
                                                float (&sa1)[16], float (&sa2)[16], float* s_stats1, float* s_stats2, int lane) {
   {
-    const float4* b4 = reinterpret_cast<const float4*>(s_bias + (DECONV ? gcol % p.cout : c0));
+    int boff = DECONV ? gcol % p.cout : c0;
+    if (!DECONV && p.bias9) boff = (((y == 0) ? 0 : (y == p.H - 1 ? 2 : 1)) * 3 + ((x == 0) ? 0 : (x == p.W - 1 ? 2 : 1))) * 16;
+    const float4* b4 = reinterpret_cast<const float4*>(s_bias + boff);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float4 b = b4[k];
@@ -303,10 +310,11 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < UNPP_MAX_SRC; ++i)
       if (i < p.nchunk) tma_prefetch_desc(&p.maps[p.ch_map[i]]);
+    if (p.low_on) tma_prefetch_desc(&p.lowmap);
   }
   // stage the per-column bias (conv: this CTA's n_tile slice; deconv: all Cout) and the 1x1 head
   {
-    const int nb = (DECONV || p.b2) ? p.cout : p.ncols;
+    const int nb = p.bias9 ? 9 * 16 : ((DECONV || p.b2) ? p.cout : p.ncols);
     for (int i = threadIdx.x; i < nb; i += kThreads) s_bias[i] = p.bias ? __ldg(p.bias + (DECONV ? 0 : ntile_idx * p.ncols) + i) : 0.f;
     if constexpr (HEAD) {
       for (int i = threadIdx.x; i < p.head_classes * 16; i += kThreads) s_head[i] = __ldg(p.head_w + i);
@@ -328,20 +336,32 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bar_w, p.w_bytes);
+      mbar_arrive_expect_tx(&bar_w, p.w_bytes + (p.low_on ? p.low_w_bytes : 0));
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpacked) + size_t(ntile_idx) * p.w_bytes;
       for (int off = 0; off < p.w_bytes; off += 16384) {
         int n = p.w_bytes - off < 16384 ? p.w_bytes - off : 16384;
         bulk_load(w_smem + off, wsrc + off, n, &bar_w);
       }
+      if (p.low_on) {
+        const uint8_t* lsrc = reinterpret_cast<const uint8_t*>(p.low_wpacked);
+        for (int off = 0; off < p.low_w_bytes; off += 16384) {
+          int n = p.low_w_bytes - off < 16384 ? p.low_w_bytes - off : 16384;
+          bulk_load(w_smem + p.low_w_off + off, lsrc + off, n, &bar_w);
+        }
+      }
       int it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
-        for (int c = 0; c < p.nchunk; ++c, ++it) {
+        for (int c = 0; c < p.nchunk + p.low_on; ++c, ++it) {
           const int s = it % p.nstage, ph = (it / p.nstage) & 1;
           mbar_wait(&bar_empty[s], ph ^ 1);
           if (p.dbg & 4) {
             mbar_arrive(&bar_full[s]);
+            continue;
+          }
+          if (c == p.nchunk) {  // low-resolution halo tile of the fused transposed conv: 18 rows x (TW/2 + 2) pixels of 64 B
+            mbar_arrive_expect_tx(&bar_full[s], 18 * p.low_P * 64);
+            tma_load_4d(&p.lowmap, &bar_full[s], stage0 + size_t(s) * p.stage_bytes, 0, tx * (p.TW >> 1) - 1, ty * 16 - 1, n);
             continue;
           }
           if (p.b2) {  // pixel-pair rows (64 B), 34 image rows x (TW/2 + 2) pairs around a 32 x TW output tile
@@ -366,6 +386,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     mbar_wait(&bar_w, 0);
     const int ncols = p.ncols, nsub = p.nsub, taps = p.taps, k8_total = p.k8_total, nchunk = p.nchunk, nstage = p.nstage;
     const int ntiles = p.ntiles, stage_bytes = p.stage_bytes, dbg = p.dbg, b2 = p.b2, b2_P = p.b2_P, nacc = p.nacc;
+    const int low_on = p.low_on, low_P = p.low_P, low_k8 = p.low_k8, low_w_off = p.low_w_off;
     const uint32_t idesc = make_idesc_bf16(128, ncols);
     const uint32_t w_addr = smem_u32(w_smem);
     const uint32_t stage_addr0 = smem_u32(stage0);
@@ -379,7 +400,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
       tc_fence_after();
       const uint32_t acc = tmem_base + uint32_t(b * nsub * ncols);
 #pragma unroll 1
-      for (int c = 0; c < nchunk; ++c, ++it) {
+      for (int c = 0; c < nchunk + low_on; ++c, ++it) {
         const int s = it % nstage, ph = (it / nstage) & 1;
         int span = spans[0], wk8 = wk8s[0];
 #pragma unroll
@@ -390,7 +411,33 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
         // Issue loops: fully unrolled over the window positions / taps, descriptors formed from a constant high
         // word and a 32-bit low word (start address + LBO) so that every MMA costs two independent adds, not a
         // serial chain through the uniform datapath (the single issuing thread is the limiter at small N).
-        if (b2) {
+        if (c == nchunk) {
+          if (elect_one() && !(dbg & 2)) {
+            // fused transposed conv: GEMM row = block = one LOW-resolution pixel (8 consecutive pixels = 8 rows of 64 B,
+            // next row group one low-res row down); classic 3x3 taps over the low-res halo tile, two K=16 slabs per
+            // tap (32 channels), the 64 columns are (pixel of the 2x2 block, co) with composed weights.
+            const uint64_t ad = make_sdesc(stage_addr0 + uint32_t(s) * stage_bytes, 16, uint32_t(low_P * 64), 4);
+            const uint64_t bd = make_sdesc(w_addr + uint32_t(low_w_off), 64 * 16, 128, 0);
+            const uint32_t a_hi = uint32_t(ad >> 32), b_hi = uint32_t(bd >> 32), b_lo = uint32_t(bd);
+            const uint32_t a_lo0 = uint32_t(ad) + uint32_t(mw * 32), a_lo1 = a_lo0 + uint32_t(kMmaWarps * 32);
+            const uint32_t acc0 = acc + uint32_t(mw * 64), acc1 = acc + uint32_t((mw + kMmaWarps) * 64);
+            const uint32_t b_tap_step = uint32_t(low_k8 * 64 * 16) >> 4, b_ks_step = uint32_t(2 * 64 * 16) >> 4, row_step = uint32_t(low_P * 4);
+            const int kslabs = low_k8 >> 1;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+              for (int sft = 0; sft < 3; ++sft) {
+                for (int ks = 0; ks < kslabs; ++ks) {
+                  const uint32_t ao = uint32_t(r) * row_step + uint32_t(sft * 4 + ks * 2);
+                  const uint64_t bdesc = (uint64_t(b_hi) << 32) | (b_lo + uint32_t(r * 3 + sft) * b_tap_step + uint32_t(ks) * b_ks_step);
+                  const uint32_t accum = (c | r | sft | ks) ? 1u : 0u;
+                  if (has0) umma_bf16(acc0, (uint64_t(a_hi) << 32) | (a_lo0 + ao), bdesc, idesc, accum);
+                  if (has1) umma_bf16(acc1, (uint64_t(a_hi) << 32) | (a_lo1 + ao), bdesc, idesc, accum);
+                }
+              }
+            }
+          }
+        } else if (b2) {
           if (elect_one() && !(dbg & 2)) {
             // 2x2 output blocks: GEMM row = block (8 consecutive pixel pairs = 8 rows of 64 B, next row group two
             // image rows down), K walks the 4x4 input window: pixel (dy, dx) of the window is 32 B into / past the
@@ -469,7 +516,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     const int ncb = p.ncols >> 4, units = p.nsub * ncb;
     const float relu_floor = p.relu ? 0.f : -INFINITY;
     EpiArgs e;
-    e.dbg = p.dbg;
+    e.dbg = p.dbg, e.bias9 = p.bias9;
     e.H = p.H, e.W = p.W, e.cout = p.cout, e.head_classes = p.head_classes, e.out = p.out, e.heat = p.heat, e.logit = p.logit;
     e.drop_mask = p.drop_mask, e.drop_scale = p.drop_scale, e.addend = p.addend, e.relu_mask_src = p.relu_mask_src;
     e.stats_partial = p.stats_partial, e.stats_aux = p.stats_aux, e.aux_mean = p.aux_mean, e.aux_istd = p.aux_istd;
@@ -570,7 +617,7 @@ EncodeTiledFn get_encode() {
 
 struct Plan {
   int TW, nsub, nstage, stage_bytes, w_bytes, w_smem_bytes, tmem_cols, smem_total, grid_x, grid_y, tiles_x, tiles_y, ntiles;
-  int nchunk, k8_total, b2, b2_P, ncols, nacc;
+  int nchunk, k8_total, b2, b2_P, ncols, nacc, low_on, low_w_off, low_w_bytes;
   int ch_map[kMaxChunks], ch_c0[kMaxChunks], ch_span[kMaxChunks], ch_wk8[kMaxChunks];
 };
 
@@ -599,7 +646,9 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
     }
   }
   pl->nchunk = nchunk, pl->k8_total = k8;
-  pl->b2 = 0, pl->b2_P = 0, pl->ncols = a->n_tile;
+  pl->b2 = 0, pl->b2_P = 0, pl->ncols = a->n_tile, pl->low_on = 0, pl->low_w_off = 0, pl->low_w_bytes = 0;
+  if (a->lowres_src && !a->block2x2) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: lowres_src (fused transposed conv) needs block2x2");
+  if (a->bias_classes != 0 && a->bias_classes != 1 && a->bias_classes != 9) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: bias_classes must be 0, 1 or 9");
   // static shared memory: 18 KB in the training variants (statistics slots), 2 KB otherwise; 227 KB per CTA in total
   const int smem_budget = (is_train(a) ? 196 : 220) * 1024;
   if (a->block2x2) {
@@ -613,6 +662,13 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
     pl->b2 = 1, pl->ncols = 64;
     pl->w_bytes = 16 * k8 * 64 * 16;
     pl->w_smem_bytes = (pl->w_bytes + 1023) / 1024 * 1024;
+    if (a->lowres_src) {
+      if (a->lowres_C != 32 || !a->lowres_wpacked || (a->H & 3) || (a->W & 3) || is_train(a) || (reinterpret_cast<uintptr_t>(a->lowres_src) & 15))
+        return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: fused transposed conv needs a 32-channel low-res source, its composed weights, H and W "
+                                            "divisible by 4, and the inference epilogue");
+      pl->low_on = 1, pl->low_w_off = pl->w_smem_bytes, pl->low_w_bytes = 9 * (a->lowres_C / 8) * 64 * 16;
+      pl->w_smem_bytes += (pl->low_w_bytes + 1023) / 1024 * 1024;
+    }
     // widest tile that leaves room for two stages: fewer tiles (less per-tile handshake), more sub-tiles (more issuers busy)
     int TW = a->W > 32 ? 64 : a->W > 16 ? 32 : 16;
     for (;; TW >>= 1) {
@@ -720,6 +776,19 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   p.TW = pl.TW, p.nsub = pl.nsub, p.tiles_x = pl.tiles_x, p.tiles_y = pl.tiles_y, p.ntiles = pl.ntiles;
   p.taps = a->taps, p.ncols = pl.ncols, p.k8_total = pl.k8_total;
   p.b2 = pl.b2, p.b2_P = pl.b2_P, p.nacc = pl.nacc;
+  p.bias9 = a->bias_classes == 9;
+  if (pl.low_on) {
+    const cuuint64_t C = a->lowres_C, lw = a->W / 2, lh = a->H / 2;
+    cuuint64_t gd[4] = {C, lw, lh, cuuint64_t(a->N)};
+    cuuint64_t gs[3] = {C * 2, lw * C * 2, lh * lw * C * 2};
+    cuuint32_t box[4] = {cuuint32_t(C), cuuint32_t(pl.TW / 2 + 2), 18, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&p.lowmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->lowres_src), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled failed (CUresult %d) for the low-res source", int(r));
+    p.low_on = 1, p.low_P = pl.TW / 2 + 2, p.low_k8 = a->lowres_C / 8, p.low_w_off = pl.low_w_off, p.low_w_bytes = pl.low_w_bytes;
+    p.low_wpacked = reinterpret_cast<const __nv_bfloat16*>(a->lowres_wpacked);
+  }
   p.stage_bytes = pl.stage_bytes, p.nstage = pl.nstage, p.w_bytes = pl.w_bytes, p.w_smem_bytes = pl.w_smem_bytes;
   p.tmem_cols = pl.tmem_cols;
   p.wpacked = reinterpret_cast<const __nv_bfloat16*>(a->wpacked);

@@ -36,6 +36,37 @@ DECODER_ORDER = ("up_concat01", "up_concat11", "up_concat21", "up_concat02", "up
 HEAD_OF = {"up_concat01": "final_1", "up_concat02": "final_2", "up_concat03": "final_3"}
 
 
+def compose_deconv_conv(w_conv_u: torch.Tensor, w_up: torch.Tensor, b_up: torch.Tensor, b_conv: torch.Tensor):
+    """conv3x3(ConvTranspose2d_k2s2(x)) as ONE 3x3 conv over the low-resolution x (the k2s2 upsample never overlaps).
+
+    w_conv_u [Co, Cu, 3, 3]: the slice of the consuming conv's weight that multiplies the upsampled tensor (unet.py:199-201:
+    the first Cu input channels); w_up [Ci, Cu, 2, 2], b_up [Cu]: the transposed conv (unet.py:187); b_conv [Co].
+    Returns (composed weight [4*Co, Ci, 3, 3] whose output channel is (2*jy+jx)*Co + co for pixel (jy, jx) of the 2x2 output
+    block, and whose taps are offsets -1..1 on the low-res grid; bias table [9, Co] indexed by 3*rowclass + colclass,
+    class 0 = first row/column, 1 = interior, 2 = last: zero padding is applied AFTER the upsample, so border pixels see
+    fewer taps of the upsample bias)."""
+    co, cu = w_conv_u.shape[0], w_conv_u.shape[1]
+    ci = w_up.shape[0]
+    wc, wd = w_conv_u.double(), w_up.double()
+    comp = torch.zeros(4 * co, ci, 3, 3, dtype=torch.float64, device=wc.device)
+    for jy in range(2):
+        for jx in range(2):
+            for r in range(3):
+                for s in range(3):
+                    uy, ux = jy + r - 1, jx + s - 1          # position in the upsampled grid relative to the block origin
+                    dyl, p_ = uy // 2, uy % 2                # low-res row offset (-1, 0, 1) and row parity of that upsampled pixel
+                    dxl, q_ = ux // 2, ux % 2
+                    blk = (2 * jy + jx) * co
+                    comp[blk:blk + co, :, dyl + 1, dxl + 1] += wc[:, :, r, s] @ wd[:, :, p_, q_].t()
+    t = torch.einsum("ocrs,c->rso", wc, b_up.double())       # contribution of the upsample bias through tap (r, s)
+    valid = {0: (1, 2), 1: (0, 1, 2), 2: (0, 1)}              # taps that stay inside the image for first / interior / last row
+    table = torch.zeros(9, co, dtype=torch.float64, device=wc.device)
+    for rc in range(3):
+        for cc in range(3):
+            table[3 * rc + cc] = b_conv.double() + sum(t[r, s] for r in valid[rc] for s in valid[cc])
+    return comp.float().contiguous(), table.float().contiguous()
+
+
 class Engine:
     def __init__(self, model, device: torch.device):
         if device.type != "cuda":
@@ -55,6 +86,7 @@ class Engine:
         self._packed_key = None
         self._arena: Dict[Tuple, Dict[str, torch.Tensor]] = {}
         self._keep: List = []
+        self.fuse_deconv = True  # inference: fold the k2s2 transposed conv of the full-resolution nodes into the consuming conv
 
     # ------------------------------------------------------------------------------ weights
     def _param_key(self):
@@ -86,6 +118,15 @@ class Engine:
                 for n in (1, 2):
                     conv = self._conv_seq(name + ".conv", n)[0]
                     P[f"{name}.c{n}"] = self._pack_fwd_conv(conv.weight, None, conv.bias.detach().float().contiguous())
+                conv1 = self._conv_seq(name + ".conv", 1)[0]
+                cu = up.up.weight.shape[1]
+                if cu == 16 and up.up.weight.shape[0] == 32 and conv1.weight.shape[1] - cu <= 48:
+                    # full-resolution node: the transposed conv is folded into the consuming conv (no U tensor, no deconv launch)
+                    comp, table = compose_deconv_conv(conv1.weight.detach().float()[:, :cu], up.up.weight.detach().float(), up.up.bias.detach().float(),
+                                                      conv1.bias.detach().float())
+                    klow = conv1.weight.shape[1] - cu
+                    P[f"{name}.c1.fused"] = dict(w=ops.pack_weights_b2(conv1.weight.detach().float(), False, klow, k_begin=cu), bias=table,
+                                                 low_w=ops.pack_weights(comp, 0, 9, 64, 64, 32), n_total=16, n_tile=ops.NTile(16, b2=True))
                 cin, cout = up.up.weight.shape[0], up.up.weight.shape[1]
                 nt = pick_n_tile(4 * cout, cin, 1, deconv=True)
                 P[f"{name}.up"] = dict(w=ops.pack_weights(up.up.weight.float(), 2, 1, 4 * cout, nt, cin), bias=up.up.bias.detach().float().contiguous(),
@@ -178,9 +219,14 @@ class Engine:
             tag = name[-2:]
             h, w = H >> lvl, W >> lvl
             pu, p1, p2 = P[f"{name}.up"], P[f"{name}.c1"], P[f"{name}.c2"]
-            ops.conv([A[high]], B, h // 2, w // 2, pu["w"], pu["n_total"], pu["n_tile"], 1, bias=pu["bias"], mode=MODE_DECONV, out=A[f"U{tag}"])
-            ops.conv([A[f"U{tag}"]] + [A[l] for l in lows], B, h, w, p1["w"], p1["n_total"], p1["n_tile"], 9, bias=p1["bias"], relu=True,
-                      out=A[f"{name}.a"])
+            pf = P.get(f"{name}.c1.fused")
+            if pf is not None and self.fuse_deconv:
+                ops.conv([A[l] for l in lows], B, h, w, pf["w"], 16, pf["n_tile"], 9, bias=pf["bias"], bias_classes=9, relu=True, out=A[f"{name}.a"],
+                         lowres=(A[high], pf["low_w"]))
+            else:
+                ops.conv([A[high]], B, h // 2, w // 2, pu["w"], pu["n_total"], pu["n_tile"], 1, bias=pu["bias"], mode=MODE_DECONV, out=A[f"U{tag}"])
+                ops.conv([A[f"U{tag}"]] + [A[l] for l in lows], B, h, w, p1["w"], p1["n_total"], p1["n_tile"], 9, bias=p1["bias"], relu=True,
+                          out=A[f"{name}.a"])
             head = None
             out = A[f"X{tag}"]
             if name in HEAD_OF:

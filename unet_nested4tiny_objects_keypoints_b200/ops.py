@@ -141,7 +141,7 @@ def _conv_args(srcs, N, H, W, n_total, n_tile, taps, strided=None, b2=False) -> 
 
 def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Tensor, n_total: int, n_tile: int, taps: int, *, bias=None,
          relu=False, mode=MODE_CONV, out=None, head=None, addend=None, relu_mask_src=None, stats_partial=None, stats_aux=None, aux_mean=None,
-         aux_istd=None, strided=None, b2=False) -> None:
+         aux_istd=None, strided=None, b2=False, lowres=None, bias_classes=0) -> None:
     """One unpp_conv_tc launch.  ``srcs``: NHWC bf16 tensors (virtual concat along K).
     ``head`` = (w fp32 [cls,16], b fp32 [cls], heat fp32 NCHW, logit|None, drop_mask u8 NHWC|None, drop_scale).
     ``strided`` = [(oy, ox), ...]: every source is a [N,2H,2W,C] tensor read at (2y+oy, 2x+ox)."""
@@ -154,6 +154,9 @@ def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Te
         a.head_w, a.head_b, a.heat, a.logit = hw.data_ptr(), hb.data_ptr(), heat.data_ptr(), _ptr(logit)
         a.head_classes = hw.shape[0]
         a.drop_mask, a.drop_scale = _ptr(dmask), float(dscale)
+    if lowres is not None:  # (low-resolution tensor [N,H/2,W/2,C], composed packed weights): fused transposed conv
+        a.lowres_src, a.lowres_wpacked, a.lowres_C = lowres[0].data_ptr(), lowres[1].data_ptr(), lowres[0].shape[-1]
+    a.bias_classes = bias_classes
     a.addend, a.relu_mask_src = _ptr(addend), _ptr(relu_mask_src)
     a.stats_partial, a.stats_aux, a.aux_mean, a.aux_istd = _ptr(stats_partial), _ptr(stats_aux), _ptr(aux_mean), _ptr(aux_istd)
     _count()
@@ -164,6 +167,8 @@ def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Te
     k_total = sum(s.shape[-1] for s in srcs)
     px = N * H * W
     nbytes = px * k_total * 2 + wpacked.numel() * 2
+    if lowres is not None:
+        nbytes += lowres[0].numel() * 2 + lowres[1].numel() * 2
     if out is not None:
         nbytes += px * n_total * 2
     if head is not None:
@@ -172,6 +177,8 @@ def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Te
         if extra is not None:
             nbytes += extra.numel() * 2
     flops = 2 * px * k_total * n_total * taps
+    if lowres is not None:  # count the unfused arithmetic it replaces: the k2s2 transposed conv + its 3x3 taps
+        flops += 2 * px * lowres[0].shape[-1] * n_total + 2 * px * n_total * n_total * taps
     label = "conv_tc %s taps%d K%d N%d %dx%d" % ("deconv" if mode == MODE_DECONV else ("conv2x2" if a.block2x2 else "conv"), taps, k_total, n_total, H, W)
     with _Traced(label, nbytes, flops):
         _lib.check(lib().unpp_conv_tc(C.byref(a), _stream()), "unpp_conv_tc")
@@ -179,6 +186,7 @@ def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Te
 
 def conv_grid(srcs_C: Sequence[int], N: int, H: int, W: int, n_total: int, n_tile: int, taps: int, b2: bool = False) -> int:
     a = _conv_args(list(srcs_C), N, H, W, n_total, n_tile, taps, None, b2)
+    a.stats_partial = 16  # the grid is asked for to size a statistics buffer: plan like the training-epilogue launch that will fill it
     g = lib().unpp_conv_grid(C.byref(a))
     if g < 0:
         _lib.check(g, "unpp_conv_grid")
