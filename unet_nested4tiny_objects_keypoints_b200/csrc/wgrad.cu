@@ -25,6 +25,7 @@ namespace {
 constexpr int kMaxJobs = 16;
 constexpr int TR = 8, TC = 32;  // tile rows / cols (pixels)
 constexpr int kThreads = 256;
+constexpr int kMaxStages = 8;  // TMA tiles in flight per CTA: the loop is latency-bound with fewer (8x32-pixel tiles are small)
 
 struct WgradParams {
   CUtensorMap xmap[UNPP_MAX_SRC];
@@ -33,7 +34,7 @@ struct WgradParams {
   int job_map[kMaxJobs], job_c0[kMaxJobs], job_cs[kMaxJobs], job_cioff[kMaxJobs], job_co0[kMaxJobs], job_con[kMaxJobs];
   int tiles_x, tiles_y, ntiles;
   int pad, cin_total, cout;
-  int xstage_bytes, zstage_bytes;
+  int xstage_bytes, zstage_bytes, nstage;
   float* partial;
 };
 
@@ -52,7 +53,7 @@ __device__ __forceinline__ uint32_t swz(uint32_t addr, uint32_t mask) { return a
 template <int TAPS, int PPW>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ uint64_t bar_full[2];
+  __shared__ uint64_t bar_full[kMaxStages];
   uint8_t* const smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int job = blockIdx.y;
@@ -60,11 +61,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   const int nco = con >> 4, npairs = (cs >> 4) * nco;
   const int pad = p.pad, PX = TC + 2 * pad, PY = TR + 2 * pad;
   const int stage_bytes = p.xstage_bytes + p.zstage_bytes, xstage_bytes = p.xstage_bytes;
-  const int ntiles = p.ntiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y;
+  const int ntiles = p.ntiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y, nstage = p.nstage;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bar_full[0], 1);
-    mbar_init(&bar_full[1], 1);
+    for (int i = 0; i < kMaxStages; ++i) mbar_init(&bar_full[i], 1);
     fence_mbar_init();
     tma_prefetch_desc(&p.xmap[p.job_map[job]]);
     tma_prefetch_desc(&p.zmap);
@@ -108,12 +108,16 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[j][t][h][e] = 0.f;
 
-  if (threadIdx.x == 0 && int(blockIdx.x) < ntiles) issue(blockIdx.x, 0);
+  // prologue: fill the ring (tile k of this CTA goes to buffer k % nstage)
+  if (threadIdx.x == 0)
+    for (int k = 0; k < nstage; ++k) {
+      const int tile = blockIdx.x + k * int(gridDim.x);
+      if (tile < ntiles) issue(tile, k);
+    }
   int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    if (threadIdx.x == 0 && tile + int(gridDim.x) < ntiles) issue(tile + gridDim.x, buf ^ 1);
-    mbar_wait(&bar_full[buf], (it >> 1) & 1);
+    const int buf = it % nstage;
+    mbar_wait(&bar_full[buf], (it / nstage) & 1);
     const uint32_t xs = smem_base + uint32_t(buf) * stage_bytes, zs = xs + xstage_bytes;
     for (int row = row0; row < TR; row += row_step) {
 #pragma unroll
@@ -138,7 +142,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         }
       }
     }
-    __syncthreads();  // everyone is done with `buf` before it is refilled two iterations later
+    __syncthreads();  // everyone is done with `buf`: refill it with the tile nstage iterations ahead
+    if (threadIdx.x == 0) {
+      const int nxt = tile + nstage * int(gridDim.x);
+      if (nxt < ntiles) issue(nxt, buf);
+    }
   }
 
   // stage the fragments in shared memory ([frag][16 ci][16 co] fp32), then sum the warps that share a pair in a fixed order
@@ -190,7 +198,7 @@ EncodeTiledFn get_encode() {
 }
 
 struct Plan {
-  int njobs, ppw, pad, cin_total, tiles_x, tiles_y, ntiles, grid_x, xstage_bytes, zstage_bytes, smem_total;
+  int njobs, ppw, pad, cin_total, tiles_x, tiles_y, ntiles, grid_x, xstage_bytes, zstage_bytes, smem_total, nstage;
   int job_map[kMaxJobs], job_c0[kMaxJobs], job_cs[kMaxJobs], job_cioff[kMaxJobs], job_co0[kMaxJobs], job_con[kMaxJobs];
 };
 
@@ -228,7 +236,11 @@ int make_plan(const UnppWgradArgs* a, Plan* pl) {
   const int PX = TC + 2 * pl->pad, PY = TR + 2 * pl->pad;
   pl->xstage_bytes = (PY * PX * max_cs * 2 + 1023) / 1024 * 1024;  // 1 KB granules keep every tile on the swizzle pattern period
   pl->zstage_bytes = (TR * TC * max_con * 2 + 1023) / 1024 * 1024;
-  const int pipe = 2 * (pl->xstage_bytes + pl->zstage_bytes);
+  const int stage = pl->xstage_bytes + pl->zstage_bytes;
+  pl->nstage = (200 * 1024) / stage;
+  if (pl->nstage > kMaxStages) pl->nstage = kMaxStages;
+  if (pl->nstage < 2) return unpp::fail(UNPP_ERR_UNSUPPORTED, "wgrad: tile does not fit twice in shared memory");
+  const int pipe = pl->nstage * stage;
   const int staging = 8 * pl->ppw * a->taps * 256 * 4;
   pl->smem_total = 1024 + (pipe > staging ? pipe : staging);
   pl->tiles_x = (a->W + TC - 1) / TC, pl->tiles_y = (a->H + TR - 1) / TR;
@@ -301,7 +313,7 @@ extern "C" int unpp_wgrad(const UnppWgradArgs* a, unpp_stream_t stream_) {
   }
   p.tiles_x = pl.tiles_x, p.tiles_y = pl.tiles_y, p.ntiles = pl.ntiles;
   p.pad = pl.pad, p.cin_total = pl.cin_total, p.cout = a->cout;
-  p.xstage_bytes = pl.xstage_bytes, p.zstage_bytes = pl.zstage_bytes;
+  p.xstage_bytes = pl.xstage_bytes, p.zstage_bytes = pl.zstage_bytes, p.nstage = pl.nstage;
   p.partial = a->partial;
   if (a->taps == 9) return pl.ppw == 2 ? launch<9, 2>(p, pl, stream) : launch<9, 1>(p, pl, stream);
   return pl.ppw == 2 ? launch<1, 2>(p, pl, stream) : launch<1, 1>(p, pl, stream);
