@@ -235,9 +235,10 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dyh, const uint4* 
 //   dWh[cls][c] += dlogit[cls] * x[c]*mask[c]*scale ;  dbh[cls] += dlogit[cls] ; loss partial
 // One thread per pixel; per-thread register accumulators, one shuffle+smem reduction per CTA at
 // the end, written to partial[blockIdx.x][NCLS*16 + NCLS + 1 + 16] = dW, db, loss, dxsum.
-template <int NCLS>
+// FOCAL is a compile-time switch: the powf/logf path costs registers and instructions the MSE / upstream path must not pay.
+template <int NCLS, bool FOCAL>
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ heat, const float* __restrict__ dheat, const float* __restrict__ target,
-                                                       int loss_kind, float gamma, float coef, const uint4* __restrict__ x, const uint4* __restrict__ mask, float drop_scale,
+                                                       float gamma, float coef, const uint4* __restrict__ x, const uint4* __restrict__ mask, float drop_scale,
                                                        const float* __restrict__ head_w, uint4* __restrict__ dx, float* __restrict__ partial,
                                                        int N, long HW) {
   constexpr int NACC = NCLS * 16 + NCLS + 1 + 16, LOSS = NCLS * 16 + NCLS;
@@ -260,12 +261,13 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       float dh;
       if (target) {
         const float d = pr - __ldg(target + o);
-        if (loss_kind == 0) {  // MSE: loss += d^2, d loss / d p = coef * d
+        if constexpr (!FOCAL) {  // MSE: loss += d^2, d loss / d p = coef * d
           acc[LOSS] += d * d;
           dh = coef * d;
         } else {  // FocalLoss_BCE_2d (tools/losses/focal_loss.py:264-301): a = |p-t|, e = 1-a+1e-20, loss += -a^gamma * log(e)
           const float a = fabsf(d), e = 1.f - a + 1e-20f;
-          const float le = logf(e), pg1 = a > 0.f ? powf(a, gamma - 1.f) : 0.f;
+          // gamma = 3 (the trainer's setting, trainer.py:426) needs no pow; log through the fast intrinsic (rel. error ~1e-6)
+          const float le = __logf(e), pg1 = gamma == 3.f ? a * a : (a > 0.f ? __powf(a, gamma - 1.f) : 0.f);
           acc[LOSS] += -(pg1 * a) * le;
           dh = coef * copysignf(-gamma * pg1 * le + (pg1 * a) / e, d);
         }
@@ -464,7 +466,12 @@ extern "C" int unpp_head_bwd(const float* heat, const float* dheat, const float*
   const int grid = unpp_head_bwd_grid(N, H, W);
   const long HW = long(H) * W;
 #define LAUNCH(NC)                                                                                                                        \
-  head_bwd_kernel<NC><<<grid, 256, 0, STREAM(stream)>>>(heat, dheat, target, loss_kind, gamma, coef, reinterpret_cast<const uint4*>(x),                      \
+  if (loss_kind == 1)                                                                                                                     \
+    head_bwd_kernel<NC, true><<<grid, 256, 0, STREAM(stream)>>>(heat, dheat, target, gamma, coef, reinterpret_cast<const uint4*>(x),           \
+                                                        reinterpret_cast<const uint4*>(drop_mask), drop_scale, head_w,                     \
+                                                        reinterpret_cast<uint4*>(dx), partial, N, HW);                                     \
+  else                                                                                                                                    \
+    head_bwd_kernel<NC, false><<<grid, 256, 0, STREAM(stream)>>>(heat, dheat, target, gamma, coef, reinterpret_cast<const uint4*>(x),                      \
                                                         reinterpret_cast<const uint4*>(drop_mask), drop_scale, head_w,                     \
                                                         reinterpret_cast<uint4*>(dx), partial, N, HW)
   switch (classes) {
