@@ -19,6 +19,7 @@
  *   unpp_argmax_peaks   the arg-max core of Heatmap.extract_points_ (tools/misc/heatmap.py:173-178)
  *   unpp_wgrad, unpp_bn_*, unpp_maxpool2x2_bwd, unpp_head_bwd   the autograd backward of unet.py:255-300
  *   unpp_adamw          tools/optimizers/adamw.py:38-100 (AdamW.step) over one flat buffer
+ *   unpp_create_heatmap tools/misc/helper.py:87-172 (target synthesis the trainer runs on the CPU every step)
  */
 #ifndef UNPP_H_
 #define UNPP_H_
@@ -206,6 +207,11 @@ int unpp_adamw_dev(float* p, const float* g, float* m, float* v, long n, float l
 /* u8 keep-mask for nn.Dropout(p): mask[i] = 1 with probability 1-p (counter-based hash of seed, i and,
  * when step_counter is not NULL, of the device step counter so that graph replays draw new masks). */
 int unpp_dropout_mask(uint8_t* mask, long n, float p_drop, uint64_t seed, const uint64_t* step_counter, unpp_stream_t stream);
+
+/* Target heat maps from key points, the trainer's per-step CPU routine (tools/misc/helper.py:87-172, called at
+ * trainer/trainer.py:122-123): keypoints fp32 [N][npts][2] as (x, y) -> out fp32 [N][4][H][W]; point groups
+ * {0}, {1,2,3}, {4}, {5..npts-1}; exp(-0.5*distance/3) in float64; multi-point planes divided by their maximum. */
+int unpp_create_heatmap(const float* keypoints, int N, int npts, int H, int W, float* out, unpp_stream_t stream);
 
 /* sizeof() of the argument structs as the C compiler sees them (binding self-check). */
 int unpp_sizeof_conv_args(void);

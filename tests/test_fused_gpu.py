@@ -123,3 +123,22 @@ def test_reference_adamw_dropin_optimizer_matches_reference_semantics(golden):
         assert np.allclose(p.detach().cpu().numpy(), arr[f"adamw_p3_{j}"], rtol=2e-6, atol=1e-7)
     with pytest.raises(NotImplementedError):
         AdamW(params, amsgrad=True)
+
+
+def test_fused_train_step_from_keypoints_builds_targets_on_the_device():
+    sd = O.synth_state_dict(seed=34)
+    m = pkg.UNet_Nested()
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    m.drop_out.p = 0.0
+    B, H, W = 2, 32, 32
+    step = fused.FusedTrainStep(m, B, H, W)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, 3, H, W, generator=g)
+    kp = (torch.rand(B, 7, 2, generator=g) * 28 + 2).float()
+    loss = step.step_keypoints(x.pin_memory(), kp.pin_memory())
+    torch.cuda.synchronize()
+    target = torch.from_numpy(O.create_heatmap(kp.numpy(), H, W))  # trainer.py:122-123
+    assert float((step.target.cpu() - target).abs().max()) <= 2e-6
+    rl, _, _, _ = O.train_step_grads(sd, x, target, dropout_masks=None)
+    assert abs(float(loss) - float(rl)) <= 1e-2 * float(rl)

@@ -456,3 +456,16 @@ def test_fused_transposed_conv_into_block2x2_conv(N, H, W, nlows):
              lowres=(nhwc(xlow), lw))
     torch.cuda.synchronize()
     close(nchw(out), ref, 8e-3, "fused transposed conv")
+
+
+def test_target_heatmap_synthesis_matches_reference(golden):
+    """tools/misc/helper.py:87-172 on the device: against the reference output in the fixture and the oracle on new points."""
+    from oracle import unetpp_oracle as O
+    arr, _ = golden
+    got = ops.create_heatmap(torch.from_numpy(arr["hm_keypoints"]).to(DEV), 48, 48)
+    assert np.allclose(got.cpu().numpy(), arr["hm_target"], rtol=0, atol=2e-6)
+    kp = (torch.rand(3, 7, 2, generator=torch.Generator().manual_seed(5)) * torch.tensor([70.0, 38.0]) + 1).float()
+    got = ops.create_heatmap(kp.to(DEV), 40, 72).cpu().numpy()
+    ref = O.create_heatmap(kp.numpy(), 40, 72)
+    assert got.shape == ref.shape == (3, 4, 40, 72) and np.allclose(got, ref, rtol=0, atol=2e-6)
+    assert np.allclose(got[:, [1, 3]].max(axis=(2, 3)), 1.0)  # multi-point planes are max-normalised

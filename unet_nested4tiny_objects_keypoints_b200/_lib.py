@@ -110,6 +110,7 @@ _SIGNATURES = {
     "unpp_adamw_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                  C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     "unpp_dropout_mask": (C.c_int, [C.c_void_p, C.c_long, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "unpp_create_heatmap": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "unpp_sizeof_conv_args": (C.c_int, []),
     "unpp_sizeof_pack_args": (C.c_int, []),
     "unpp_sizeof_wgrad_args": (C.c_int, []),

@@ -161,6 +161,46 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ h
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Target heat-map synthesis of the reference trainer (tools/misc/helper.py:87-172, called on the CPU every
+// step at trainer/trainer.py:122-123): 7 key points -> 4 planes, point groups {0}, {1,2,3}, {4}, {5..};
+// per point exp(-0.5 * dist / 3) with the Euclidean DISTANCE (not squared) in float64; single-point
+// planes are assigned, multi-point planes are summed (float32 += float64) and divided by their maximum.
+// One CTA per (n, channel) plane: pass 1 writes the sums and reduces the plane maximum, pass 2 normalises.
+__global__ void __launch_bounds__(256) create_heatmap_kernel(const float* __restrict__ kp, int npts, int H, int W, float* __restrict__ out) {
+  const int n = blockIdx.x >> 2, ch = blockIdx.x & 3;
+  const int p0 = ch == 0 ? 0 : ch == 1 ? 1 : ch == 2 ? 4 : 5, p1 = ch == 0 ? 1 : ch == 1 ? 4 : ch == 2 ? 5 : npts;
+  float* plane = out + size_t(blockIdx.x) * H * W;
+  double cx[4], cy[4];
+  const int np = p1 - p0;
+  for (int i = 0; i < 4; ++i) {
+    cx[i] = i < np ? double(kp[(size_t(n) * npts + p0 + i) * 2]) : 0.0;
+    cy[i] = i < np ? double(kp[(size_t(n) * npts + p0 + i) * 2 + 1]) : 0.0;
+  }
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+    const double x = double(i % W), y = double(i / W);
+    float acc = 0.f;
+    for (int k = 0; k < np && k < 4; ++k) {
+      const double d = sqrt((x - cx[k]) * (x - cx[k]) + (y - cy[k]) * (y - cy[k]));
+      const double g = exp(-0.5 * d / 3.0);
+      acc = np == 1 ? float(g) : float(double(acc) + g);
+    }
+    plane[i] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  if (np <= 1) return;
+  __shared__ float smax[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = smax[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) mx = fmaxf(mx, smax[k]);
+  for (int i = threadIdx.x; i < H * W; i += blockDim.x) plane[i] = plane[i] / mx;  // each thread re-reads only what it wrote
+}
+
 inline int grid_for(long total, int block) {
   long g = (total + block - 1) / block;
   const long cap = long(unpp::num_sms()) * 16;
@@ -206,6 +246,14 @@ extern "C" int unpp_maxpool2x2(const void* x, void* out, int N, int H, int W, in
   maxpool2x2_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), N, H, W, C / 8);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("maxpool2x2: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_create_heatmap(const float* keypoints, int N, int npts, int H, int W, float* out, unpp_stream_t stream) {
+  if (!keypoints || !out || N < 1 || H < 1 || W < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "create_heatmap: bad argument");
+  if (npts < 6 || npts > 9) return unpp::fail(UNPP_ERR_UNSUPPORTED, "create_heatmap: the reference's grouping needs 6..9 key points (7 in the trainer)");
+  create_heatmap_kernel<<<N * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(keypoints, npts, H, W, out);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("create_heatmap: launch");
   return UNPP_OK;
 }
 

@@ -269,6 +269,15 @@ class FusedTrainStep:
         self.target.copy_(target_host, non_blocking=True)
         return self.step_device()
 
+    def step_keypoints(self, x_host: torch.Tensor, keypoints_host: torch.Tensor) -> torch.Tensor:
+        """The trainer's step with its target synthesis on the device: where trainer/trainer.py:122-123 builds the
+        heat-map targets on the CPU with numpy every iteration (helper.create_heatmap), the key points [B,7,2] go
+        H2D (56 bytes per image) and ``unpp_create_heatmap`` writes the targets straight into the step's buffer."""
+        self.x.copy_(x_host, non_blocking=True)
+        kp = keypoints_host.to(self.dev, non_blocking=True).float()
+        ops.create_heatmap(kp, self.target.shape[2], self.target.shape[3], out=self.target)
+        return self.step_device()
+
     @property
     def heats(self):
         return self.ts.heats

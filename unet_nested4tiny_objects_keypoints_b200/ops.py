@@ -330,3 +330,16 @@ def dropout_mask(mask: torch.Tensor, p_drop: float, seed: int, step_counter: Opt
     _count()
     _lib.check(lib().unpp_dropout_mask(mask.data_ptr(), mask.numel(), float(p_drop), int(seed) & (2**64 - 1), _ptr(step_counter), _stream()),
                "unpp_dropout_mask")
+
+
+def create_heatmap(keypoints: torch.Tensor, H: int, W: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Target heat maps on the device (reference tools/misc/helper.py:87-172): keypoints fp32 [N, 7, 2] as (x, y) -> fp32 [N, 4, H, W]."""
+    if keypoints.dtype != torch.float32 or not keypoints.is_cuda or keypoints.dim() != 3 or keypoints.shape[2] != 2:
+        raise ValueError("create_heatmap expects an fp32 CUDA tensor [N, points, 2]")
+    keypoints = keypoints.contiguous()
+    N, npts = keypoints.shape[0], keypoints.shape[1]
+    if out is None:
+        out = torch.empty(N, 4, H, W, dtype=torch.float32, device=keypoints.device)
+    _count()
+    _lib.check(lib().unpp_create_heatmap(keypoints.data_ptr(), N, npts, H, W, out.data_ptr(), _stream()), "unpp_create_heatmap")
+    return out
