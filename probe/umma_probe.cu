@@ -716,6 +716,49 @@ static void test_p3() {
   }
 }
 
+
+// m9: the wgrad scheme on swizzled NHWC tiles.  Both operands MN-major (the contiguous dimension of a [pixel][channel]
+// tile is the GEMM M/N dimension, pixels are K).  A atoms (C channels each) are x-SHIFTED copies of the same tile:
+// LBO = one pixel (= span bytes), SBO = 8 pixels.  D[(j, ci), co] = sum_{p<16} X[p0 + p + j][ci] * G[p0 + p][co].
+static void test_m9(int C, int M) {
+  const int span = C * 2, N = C < 64 ? C : 64, NPIX = 96, atoms = M / C;
+  std::vector<float> X(NPIX * C), G(NPIX * N);
+  for (auto& v : X) v = frand();
+  for (auto& v : G) v = frand();
+  std::vector<uint8_t> img;
+  for (int p = 0; p < NPIX; ++p)
+    for (int c = 0; c < C; ++c) put_bf(img, swz(p * span + c * 2, span), X[p * C + c]);
+  const int gbase = (NPIX * span + 1023) / 1024 * 1024;
+  const int gspan = N * 2;
+  for (int p = 0; p < NPIX; ++p)
+    for (int c = 0; c < N; ++c) put_bf(img, gbase + swz(p * gspan + c * 2, gspan), G[p * N + c]);
+  const uint32_t lt = span == 128 ? 2 : span == 64 ? 4 : 6, glt = gspan == 128 ? 2 : gspan == 64 ? 4 : 6;
+  const int p0 = 5;  // unaligned pixel start on purpose (taps shift the start by whole pixels)
+  MmaJob j{};
+  j.adesc = make_sdesc(p0 * span, span /*LBO: next atom = next pixel*/, 8 * span, lt);
+  j.bdesc = make_sdesc(gbase + p0 * gspan, gspan, 8 * gspan, glt);
+  j.accumulate = 0;
+  std::vector<float> exp(128 * N, 0.f);
+  for (int a = 0; a < atoms; ++a)
+    for (int ci = 0; ci < C; ++ci)
+      for (int co = 0; co < N; ++co) {
+        float s = 0;
+        for (int p = 0; p < 16; ++p) s += X[(p0 + p + a) * C + ci] * G[(p0 + p) * N + co];
+        exp[(a * C + ci) * N + co] = s;
+      }
+  char name[128];
+  snprintf(name, sizeof name, "m9(mn-major swz%d, %d x-shifted atoms via LBO=1px, M=%d N=%d)", span, atoms, M, N);
+  if (M == 128) {
+    run_mma(name, img, {j}, make_idesc_bf16(128, N, 1, 1), N, exp);
+  } else {
+    // M = 64: find out which TMEM lanes hold rows 0..63 (rows beyond M were poisoned with NaN bytes by run_mma)
+    std::vector<float> e2(128 * N, 0.f);
+    for (int m = 0; m < 64; ++m)
+      for (int n = 0; n < N; ++n) e2[m * N + n] = exp[m * N + n];
+    run_mma(name, img, {j}, make_idesc_bf16(64, N, 1, 1), N, e2);
+  }
+}
+
 static void test_p2() {
   long long* dc;
   CK(cudaMalloc(&dc, 8));
@@ -801,7 +844,12 @@ int main(int argc, char** argv) {
   else if (t == "t6") test_tma("t6(4d C=16 swizzle32 dst+128)", 6);
   else if (t == "p1") test_p1();
   else if (t == "p2") test_p2();
-  else if (t == "p3") test_p3();
+  else if (t == "m9") {
+    test_m9(16, 128);
+    test_m9(32, 128);
+    test_m9(64, 128);
+    test_m9(16, 64);
+  } else if (t == "p3") test_p3();
   else if (t == "p4") test_p4();
   else if (t == "m8") {
     test_m8(32);
