@@ -16,5 +16,9 @@ def run(cins, cout, H, N=32, reps=10):
     for _ in range(reps): ops.wgrad(srcs, N, H, H, dz, cout, 9, part)
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps, g
-for cins, cout, H in (([128], 128, 32), ([64], 128, 32), ([64, 64], 64, 64), ([64], 64, 64), ([16], 16, 256), ([16] * 4, 16, 256), ([32] * 3, 32, 128)):
-    print(cins, cout, H, "ms %.4f grid %d" % run(cins, cout, H), flush=True)
+print("UNPP_WGRAD_LEGACY =", os.environ.get("UNPP_WGRAD_LEGACY"))
+for cins, cout, H in (([128], 128, 32), ([64, 64], 64, 64), ([16], 16, 256), ([16] * 2, 16, 256), ([16] * 3, 16, 256), ([16] * 5, 16, 256), ([16], 32, 128),
+                      ([32], 32, 128), ([32] * 2, 32, 128), ([32] * 3, 32, 128)):
+    ms, g = run(cins, cout, H)
+    px = 32 * H * H
+    print(cins, cout, H, "ms %.4f grid %d  algorithmic GB/s %.0f" % (ms, g, px * (sum(cins) + cout) * 2 / ms / 1e6), flush=True)

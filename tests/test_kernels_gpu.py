@@ -167,6 +167,15 @@ def test_argmax_bit_exact(golden):
     (1, 8, 8, [64, 64], 64),
     (1, 8, 8, [64], 128),
     (3, 64, 64, [16], 16),
+    # tcgen05 path (16/32-channel sources and outputs): ragged tiles, mixed widths, every accumulator split
+    (1, 8, 8, [16], 16),
+    (2, 40, 72, [16, 16], 16),
+    (1, 48, 96, [16, 16, 16, 16, 16], 16),
+    (2, 24, 40, [16], 32),
+    (1, 32, 64, [32], 32),
+    (2, 24, 56, [32, 32, 32], 32),
+    (1, 16, 32, [32, 16], 16),
+    (5, 128, 128, [16, 16, 16, 16], 16),
 ])
 def test_wgrad_conv3x3(N, H, W, cins, cout):
     cin = sum(cins)

@@ -17,6 +17,7 @@
 #include "sm100.cuh"
 #include "common.h"
 #include "../../include/unpp.h"
+#include "wgrad_tc.h"
 
 using namespace sm100;
 
@@ -270,6 +271,7 @@ int launch(const WgradParams& p, const Plan& pl, cudaStream_t stream) {
 extern "C" int unpp_wgrad_grid(const UnppWgradArgs* a) {
   Plan pl;
   int rc = make_plan(a, &pl);
+  if (!rc && unpp::wgrad_tc_eligible(a)) return unpp::wgrad_tc_grid(a);
   return rc ? rc : pl.grid_x;
 }
 
@@ -278,6 +280,8 @@ extern "C" int unpp_wgrad(const UnppWgradArgs* a, unpp_stream_t stream_) {
   Plan pl;
   if (int rc = make_plan(a, &pl)) return rc;
   if (!a->dz || !a->partial) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: dz / partial is null");
+  if ((reinterpret_cast<uintptr_t>(a->dz) & 15)) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: dz pointer unaligned");
+  if (unpp::wgrad_tc_eligible(a)) return unpp::wgrad_tc_launch(a, stream);  // tcgen05 path (16/32-channel levels)
   EncodeTiledFn enc = get_encode();
   if (!enc) return unpp::fail(UNPP_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled not available from the driver");
   WgradParams p;

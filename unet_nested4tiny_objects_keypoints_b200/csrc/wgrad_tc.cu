@@ -1,0 +1,317 @@
+// wgrad_tc.cu — weight gradient of the 3x3 convs of the 16/32-channel levels on tcgen05 tensor cores.
+//
+//     dW[r][s][ci][co] = sum_{n,y,x} X[n, y + r - 1, x + s - 1, ci] * dZ[n, y, x, co]
+//
+// The reduction dimension of this GEMM is the pixel grid, so BOTH operands are "MN-major" for the
+// tensor core: in an NHWC tile [pixel][channel] the contiguous dimension is the GEMM M (ci) / N (co)
+// dimension and the pixels are K.  tcgen05.mma reads such tiles directly (descriptor major bits), with
+// the hardware swizzle TMA wrote them with, so nothing is transposed or copied:
+//
+//   * A = one row of the X tile.  M = 128 = (128 / C) "atoms" of C channels; the leading-dimension
+//     byte offset of the descriptor is ONE PIXEL, so atom j is the same row shifted by j pixels:
+//     rows (j, ci) of the accumulator are the filter column s = j (j < 3 is used, the rest of the
+//     M = 128 the instruction insists on is discarded — the tensor pipe is idle anyway).
+//   * B = three rows of the dZ tile.  N = 3 * Cout; the leading-dimension byte offset is one tile
+//     row, so atom i is dZ one row further down: columns (i, co) are the filter row r = 2 - i.
+//   * one MMA (K = 16 pixels) therefore accumulates all nine taps of a 16-pixel row segment:
+//     D[(j, ci)][(i, co)] += sum_p X[Y][x0 - 1 + p + j][ci] * dZ[Y - 1 + i][x0 + p][co].
+//     (probe/umma_probe.cu m9 verifies the descriptor form on B200.)
+//
+// Work is partitioned by X rows / dZ columns: a tile is TR rows x TW columns; its X box has a one
+// pixel halo in x only, its dZ box a one-row halo in y only, and TMA zero-fills everything outside
+// the image, so every (pixel, tap) pair is counted exactly once and nothing is masked.  The
+// accumulators ([128 lanes] x [3 * Cout] fp32 per source, up to four row-interleaved copies so that
+// four issuing threads work in parallel) stay in TMEM for the whole kernel; each CTA writes one
+// partial [9][Cin_total][Cout] at the end, reduced in fixed order by unpp_wgrad_reduce (deterministic).
+//
+// Shared-memory operand traffic per MMA is 4 KB (A) + 96 * Cout B (B) for 16 pixels, i.e. 352 B per
+// pixel and 16-channel source at the full-resolution level against 64 B of HBM traffic: the two
+// limits (128 B/clk/SM shared memory, 6.5 TB/s HBM) are within 5 % of each other there.
+#include <cstdlib>
+#include "sm100.cuh"
+#include "common.h"
+#include "wgrad_tc.h"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int TR = 16, TW = 32, PX = TW + 2;
+constexpr int kIssuers = 4;
+constexpr int kThreads = 256;  // warp 0: TMA producer, warps 1..4: MMA issuers, all eight: final TMEM read-out
+constexpr int kMaxX = 8, kMaxZ = 4;
+
+struct Params {
+  CUtensorMap xmap[UNPP_MAX_SRC];
+  CUtensorMap zmap;
+  int nsrc;
+  int src_C[UNPP_MAX_SRC], cioff[UNPP_MAX_SRC];
+  int tiles_x, tiles_y, ntiles;
+  int cin_total, cout;
+  int xslot, zslot, nx, nz;  // ring geometry: bytes per slot, slots
+  int nsplit, ncols, tmem_cols;
+  float* partial;
+};
+
+__device__ __forceinline__ uint32_t layout_of_span(int span) { return span == 128 ? 2u : span == 64 ? 4u : 6u; }
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t x_full[kMaxX], x_empty[kMaxX], z_full[kMaxZ], z_empty[kMaxZ], bar_done;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* const zring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* const xring = zring + p.nz * p.zslot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxX; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], kIssuers);
+    for (int i = 0; i < kMaxZ; ++i) mbar_init(&z_full[i], 1), mbar_init(&z_empty[i], kIssuers);
+    mbar_init(&bar_done, kIssuers);
+    fence_mbar_init();
+    for (int u = 0; u < p.nsrc; ++u) tma_prefetch_desc(&p.xmap[u]);
+    tma_prefetch_desc(&p.zmap);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int nsrc = p.nsrc, ntiles = p.ntiles, nx = p.nx, nz = p.nz, nsplit = p.nsplit, ncols = p.ncols;
+  const int zspan = p.cout * 2;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int xi = 0, zi = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+        {
+          const int s = zi % nz;
+          mbar_wait(&z_empty[s], ((zi / nz) & 1) ^ 1);
+          mbar_arrive_expect_tx(&z_full[s], uint32_t((TR + 2) * TW * zspan));
+          tma_load_4d(&p.zmap, &z_full[s], zring + size_t(s) * p.zslot, 0, tx * TW, ty * TR - 1, n);
+          ++zi;
+        }
+        for (int u = 0; u < nsrc; ++u, ++xi) {
+          const int s = xi % nx;
+          mbar_wait(&x_empty[s], ((xi / nx) & 1) ^ 1);
+          mbar_arrive_expect_tx(&x_full[s], uint32_t(TR * PX * p.src_C[u] * 2));
+          tma_load_4d(&p.xmap[u], &x_full[s], xring + size_t(s) * p.xslot, 0, tx * TW - 1, ty * TR, n);
+        }
+      }
+    }
+  } else if (warp <= kIssuers) {
+    // ------------------------------------------------------------------ MMA issuers
+    // Accumulator a = u * nsplit + h (source u, rows h, h + nsplit, ... of every tile) belongs to issuer a % kIssuers.
+    const int w = warp - 1;
+    const uint32_t idesc = make_idesc_bf16(128, ncols, 1, 1);
+    const uint32_t zring_a = smem_u32(zring), xring_a = smem_u32(xring);
+    const uint32_t zslot = uint32_t(p.zslot), xslot = uint32_t(p.xslot);
+    int spans[UNPP_MAX_SRC];
+#pragma unroll
+    for (int u = 0; u < UNPP_MAX_SRC; ++u) spans[u] = p.src_C[u] * 2;
+    const uint32_t z_row = uint32_t(TW * zspan) >> 4, z_seg = uint32_t(16 * zspan) >> 4;
+    int xi = 0, zi = 0, tile_it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it, ++zi) {
+      const int zs = zi % nz;
+      mbar_wait(&z_full[zs], (zi / nz) & 1);
+      const uint64_t bd = make_sdesc(zring_a + uint32_t(zs) * zslot, uint32_t(TW * zspan), uint32_t(8 * zspan), layout_of_span(zspan));
+      const uint32_t b_hi = uint32_t(bd >> 32), b_lo = uint32_t(bd);
+#pragma unroll 1
+      for (int u = 0; u < nsrc; ++u, ++xi) {
+        const int xs = xi % nx;
+        int span = spans[0];
+#pragma unroll
+        for (int k = 1; k < UNPP_MAX_SRC; ++k)
+          if (k == u) span = spans[k];
+        mbar_wait(&x_full[xs], (xi / nx) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ad = make_sdesc(xring_a + uint32_t(xs) * xslot, uint32_t(span), uint32_t(8 * span), layout_of_span(span));
+          const uint32_t a_hi = uint32_t(ad >> 32), a_lo = uint32_t(ad);
+          const uint32_t x_row = uint32_t(PX * span) >> 4, x_seg = uint32_t(16 * span) >> 4;
+          for (int h = 0; h < nsplit; ++h) {
+            const int a = u * nsplit + h;
+            if (a % kIssuers != w) continue;
+            const uint32_t acc = tmem_base + uint32_t(a * ncols);
+            uint32_t accum = tile_it ? 1u : 0u;
+            for (int row = h; row < TR; row += nsplit) {
+              const uint32_t ar = a_lo + uint32_t(row) * x_row, br = b_lo + uint32_t(row) * z_row;
+#pragma unroll
+              for (int seg = 0; seg < TW / 16; ++seg) {
+                umma_bf16(acc, (uint64_t(a_hi) << 32) | (ar + uint32_t(seg) * x_seg), (uint64_t(b_hi) << 32) | (br + uint32_t(seg) * z_seg), idesc,
+                          accum);
+                accum = 1u;
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (elect_one()) umma_commit(&x_empty[xs]);
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&z_empty[zs]);
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(&bar_done);
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------ read-out: TMEM -> this CTA's partial
+  __syncthreads();  // idle warps sleep here instead of polling the barrier
+  mbar_wait(&bar_done, 0);
+  tc_fence_after();
+  {
+    const int q = warp & 3, half = warp >> 2;
+    const int m = q * 32 + lane;
+    const int ngroups = ncols >> 4;
+    float* const part = p.partial + size_t(blockIdx.x) * 9 * p.cin_total * p.cout;
+    for (int u = 0; u < nsrc; ++u) {
+      const int C = p.src_C[u];
+      if (q * 32 >= 3 * C) continue;  // warp-uniform: this lane quadrant only holds discarded shifts
+      const int j = m / C, ci = m % C;
+      for (int g = half; g < ngroups; g += 2) {
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = 0.f;
+        for (int h = 0; h < nsplit; ++h) {  // fixed order: deterministic
+          uint32_t raw[16];
+          tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t((u * nsplit + h) * ncols + g * 16), raw);
+          tmem_ld_wait16(raw);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] += __uint_as_float(raw[k]);
+        }
+        if (j < 3) {
+          const int i = (g * 16) / p.cout, co0 = (g * 16) % p.cout;
+          const int tap = (2 - i) * 3 + j;
+          float4* dst = reinterpret_cast<float4*>(part + (size_t(tap) * p.cin_total + p.cioff[u] + ci) * p.cout + co0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult r;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) != cudaSuccess || !q) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(q);
+  }
+  return fn;
+}
+
+struct Plan {
+  int cin_total, max_C, xslot, zslot, nx, nz, nsplit, ncols, tmem_cols, smem_total, tiles_x, tiles_y, ntiles, grid_x;
+  int cioff[UNPP_MAX_SRC];
+};
+
+void make_plan(const UnppWgradArgs* a, Plan* pl) {
+  int off = 0, maxc = 0;
+  for (int i = 0; i < a->nsrc; ++i) {
+    pl->cioff[i] = off;
+    off += a->src_C[i];
+    if (a->src_C[i] > maxc) maxc = a->src_C[i];
+  }
+  pl->cin_total = off, pl->max_C = maxc;
+  pl->ncols = 3 * a->cout;
+  int ns = 512 / (a->nsrc * pl->ncols);
+  pl->nsplit = ns > kIssuers ? kIssuers : ns;
+  int need = a->nsrc * pl->nsplit * pl->ncols, tc = 32;
+  while (tc < need) tc <<= 1;
+  pl->tmem_cols = tc;
+  pl->xslot = (TR * PX * maxc * 2 + 1023) / 1024 * 1024;
+  pl->zslot = ((TR + 2) * TW * a->cout * 2 + 1023) / 1024 * 1024;
+  const int budget = 212 * 1024;
+  pl->nz = a->cout == 16 ? 3 : 2;
+  pl->nx = (budget - pl->nz * pl->zslot) / pl->xslot;
+  if (pl->nx > kMaxX) pl->nx = kMaxX;
+  pl->smem_total = 1024 + pl->nz * pl->zslot + pl->nx * pl->xslot + 1024;  // tail: the discarded shifts of the last row read past the slot
+  pl->tiles_x = (a->W + TW - 1) / TW, pl->tiles_y = (a->H + TR - 1) / TR;
+  pl->ntiles = pl->tiles_x * pl->tiles_y * a->N;
+  const int sms = unpp::num_sms();
+  pl->grid_x = pl->ntiles < sms ? pl->ntiles : sms;
+}
+
+}  // namespace
+
+namespace unpp {
+
+bool wgrad_tc_eligible(const UnppWgradArgs* a) {
+  if (a->taps != 9 || a->dz_step != 1) return false;
+  if (a->cout != 16 && a->cout != 32) return false;
+  for (int i = 0; i < a->nsrc; ++i)
+    if (a->src_C[i] != 16 && a->src_C[i] != 32) return false;
+  if (a->nsrc * 3 * a->cout > 512) return false;
+  static int legacy = -1;  // UNPP_WGRAD_LEGACY=1 forces the mma.sync kernel (A/B measurements); read once
+  if (legacy < 0) {
+    const char* e = getenv("UNPP_WGRAD_LEGACY");
+    legacy = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !legacy;
+}
+
+int wgrad_tc_grid(const UnppWgradArgs* a) {
+  Plan pl;
+  make_plan(a, &pl);
+  return pl.grid_x;
+}
+
+int wgrad_tc_launch(const UnppWgradArgs* a, cudaStream_t stream) {
+  Plan pl;
+  make_plan(a, &pl);
+  if (pl.nx < 2) return unpp::fail(UNPP_ERR_UNSUPPORTED, "wgrad_tc: tiles do not fit twice in shared memory");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return unpp::fail(UNPP_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled not available from the driver");
+  Params p;
+  memset(&p, 0, sizeof p);
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < a->nsrc; ++i) {
+    const cuuint64_t C = a->src_C[i];
+    cuuint64_t gd[4] = {C, cuuint64_t(a->W), cuuint64_t(a->H), cuuint64_t(a->N)};
+    cuuint64_t gs[3] = {C * 2, cuuint64_t(a->W) * C * 2, cuuint64_t(a->H) * a->W * C * 2};
+    cuuint32_t box[4] = {cuuint32_t(C), cuuint32_t(PX), cuuint32_t(TR), 1};
+    CUresult r = enc(&p.xmap[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->src[i]), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled failed (CUresult %d) for source %d", int(r), i);
+    p.src_C[i] = a->src_C[i], p.cioff[i] = pl.cioff[i];
+  }
+  {
+    const cuuint64_t C = a->cout;
+    cuuint64_t gd[4] = {C, cuuint64_t(a->W), cuuint64_t(a->H), cuuint64_t(a->N)};
+    cuuint64_t gs[3] = {C * 2, cuuint64_t(a->W) * C * 2, cuuint64_t(a->H) * a->W * C * 2};
+    cuuint32_t box[4] = {cuuint32_t(C), cuuint32_t(TW), cuuint32_t(TR + 2), 1};
+    CUresult r = enc(&p.zmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->dz), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled failed (CUresult %d) for dZ", int(r));
+  }
+  p.nsrc = a->nsrc;
+  p.tiles_x = pl.tiles_x, p.tiles_y = pl.tiles_y, p.ntiles = pl.ntiles;
+  p.cin_total = pl.cin_total, p.cout = a->cout;
+  p.xslot = pl.xslot, p.zslot = pl.zslot, p.nx = pl.nx, p.nz = pl.nz;
+  p.nsplit = pl.nsplit, p.ncols = pl.ncols, p.tmem_cols = pl.tmem_cols;
+  p.partial = a->partial;
+  static bool opted_in = false;  // the attribute is idempotent
+  if (!opted_in) {
+    if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess)
+      return unpp::fail_cuda("wgrad_tc: cudaFuncSetAttribute");
+    opted_in = true;
+  }
+  wgrad_tc_kernel<<<pl.grid_x, kThreads, pl.smem_total, stream>>>(p);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("wgrad_tc: launch");
+  return UNPP_OK;
+}
+
+}  // namespace unpp
