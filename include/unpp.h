@@ -159,7 +159,8 @@ typedef struct UnppWgradArgs {
   int32_t src_C[UNPP_MAX_SRC];
   const void* dz;                /* NHWC bf16 [N, H*dz_step, W*dz_step, cout]                        */
   int32_t cout;
-  int32_t dz_step, dz_oy, dz_ox; /* 1,0,0 = dense; 2,p,q = tap (p,q) of a k2s2 transposed conv       */
+  int32_t dz_step, dz_oy, dz_ox; /* 1,0,0 = dense; 2,p,q = tap (p,q) of a k2s2 transposed conv;
+                                    2,-1,-1 = all four taps in one launch: partial is [4 (2p+q)][grid][1][cin][cout] */
   int32_t taps;                  /* 9 or 1 */
   float* partial;
 } UnppWgradArgs;
@@ -168,6 +169,21 @@ int unpp_wgrad_grid(const UnppWgradArgs* a);
 /* dst[co*s_co + ci*s_ci + tap*s_tap] = scale * sum_p partial[p][tap][ci_begin+ci][co], ci < ci_count */
 int unpp_wgrad_reduce(const float* partial, int nparts, int taps, int cin_total, int cout, float* dst, int ci_begin, int ci_count,
                       long s_co, long s_ci, long s_tap, float scale, unpp_stream_t stream);
+/* Many reductions of the two kinds above in ONE launch (the training step defers every reduction whose
+ * result is only needed by the optimizer): job j writes
+ *   dst[co*s_co + ci*s_ci + tap*s_tap] = scale * sum_p partial[p*stride + (tap*cin_total + ci_begin + ci)*cout + co]
+ * for tap < taps, ci < ci_count, co < cout, with the same fixed summation order as the single-job kernels.
+ * `table` is a DEVICE array of njobs jobs; block_end = exclusive running total of ceil(outputs/32) blocks. */
+typedef struct UnppReduceJob {
+  const float* partial;
+  float* dst;
+  int64_t stride, s_co, s_ci, s_tap;
+  int32_t nparts, taps, cin_total, cout, ci_begin, ci_count;
+  float scale;
+  int32_t block_end;
+} UnppReduceJob;
+int unpp_reduce_batched(const UnppReduceJob* table, int njobs, int total_blocks, unpp_stream_t stream);
+int unpp_sizeof_reduce_job(void);
 /* out[i] (+)= scale * sum_p partial[p*stride + i], i < n (fixed order: deterministic) */
 int unpp_reduce_partials(const float* partial, int nparts, long stride, int n, float scale, float* out, int accumulate,
                          unpp_stream_t stream);

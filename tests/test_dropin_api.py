@@ -85,3 +85,5 @@ def test_struct_layouts_match_the_header():
     lib = _lib.load()
     assert lib.unpp_sizeof_conv_args() == ctypes.sizeof(_lib.ConvArgs)
     assert lib.unpp_sizeof_pack_args() == ctypes.sizeof(_lib.PackArgs)
+    assert lib.unpp_sizeof_wgrad_args() == ctypes.sizeof(_lib.WgradArgs)
+    assert lib.unpp_sizeof_reduce_job() == ctypes.sizeof(_lib.ReduceJob)

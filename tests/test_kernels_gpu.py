@@ -204,6 +204,22 @@ def test_wgrad_deconv_strided_dz():
         ops.wgrad([nhwc(x)], N, H, W, du_d, cout, 1, partial, dz_view=(pq >> 1, pq & 1))
         ops.wgrad_reduce(partial, g, 1, cin, cout, dst, 0, cin, 4, cout * 4, 0, dst_offset=pq)
     close(dst.cpu(), w.grad, 2e-3, "deconv wgrad")
+    # the four taps in one launch, reduced through the deferred (batched) reduction queue
+    g4 = ops.wgrad_grid([cin], N, H, W, cout, 1, dz_view="all4")
+    partial4 = torch.full((4, g4, 1, cin, cout), float("nan"), device=DEV)
+    ops.wgrad([nhwc(x)], N, H, W, du_d, cout, 1, partial4, dz_view="all4")
+    dst4 = torch.zeros(cin, cout, 2, 2, device=DEV)
+    bias_part = torch.randn(7, 2 * cout, device=DEV)
+    bias_out = torch.zeros(cout, device=DEV)
+    ops.reduce_queue = []
+    for pq in range(4):
+        ops.wgrad_reduce(partial4, g4, 1, cin, cout, dst4, 0, cin, 4, cout * 4, 0, dst_offset=pq, partial_offset=pq * g4 * cin * cout, defer=True)
+    ops.reduce_partials(bias_part, 7, 2 * cout, cout, bias_out, scale=0.5, defer=True)
+    assert float(dst4.abs().max()) == 0.0  # nothing ran yet
+    ops.flush_reduce_queue({}, DEV)
+    assert ops.reduce_queue is None
+    close(dst4.cpu(), w.grad, 2e-3, "deconv wgrad (4 taps, batched reduce)")
+    close(bias_out.cpu(), 0.5 * bias_part[:, :cout].double().sum(0).cpu(), 1e-5, "batched flat reduce")
 
 
 @pytest.mark.parametrize("cins_consumers,c_t", [([16], 16), ([16, 16, 16], 16), ([32, 32], 32), ([64], 32), ([128], 64)])

@@ -79,6 +79,15 @@ class WgradArgs(C.Structure):
     ]
 
 
+class ReduceJob(C.Structure):
+    _fields_ = [
+        ("partial", C.c_void_p), ("dst", C.c_void_p),
+        ("stride", C.c_int64), ("s_co", C.c_int64), ("s_ci", C.c_int64), ("s_tap", C.c_int64),
+        ("nparts", C.c_int32), ("taps", C.c_int32), ("cin_total", C.c_int32), ("cout", C.c_int32), ("ci_begin", C.c_int32), ("ci_count", C.c_int32),
+        ("scale", C.c_float), ("block_end", C.c_int32),
+    ]
+
+
 # Every symbol include/unpp.h declares, with its ctypes signature (tests check the export list).
 _SIGNATURES = {
     "unpp_last_error": (C.c_char_p, []),
@@ -95,6 +104,8 @@ _SIGNATURES = {
     "unpp_wgrad_grid": (C.c_int, [C.POINTER(WgradArgs)]),
     "unpp_wgrad_reduce": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_long, C.c_long, C.c_long,
                                     C.c_float, C.c_void_p]),
+    "unpp_reduce_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "unpp_sizeof_reduce_job": (C.c_int, []),
     "unpp_reduce_partials": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "unpp_bn_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

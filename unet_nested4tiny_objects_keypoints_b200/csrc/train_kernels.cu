@@ -79,6 +79,21 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+// All deferred reductions of a training step in one launch: block b owns 32 outputs of the job whose
+// block range contains b (the table is small: a linear scan of the running totals).
+__global__ void __launch_bounds__(256) reduce_batched_kernel(const UnppReduceJob* __restrict__ table, int njobs) {
+  int j = 0;
+  while (j < njobs - 1 && int(blockIdx.x) >= __ldg(&table[j].block_end)) ++j;
+  const UnppReduceJob job = table[j];
+  const int first = j ? __ldg(&table[j - 1].block_end) : 0;
+  const int n = job.taps * job.ci_count * job.cout;
+  const int i = (int(blockIdx.x) - first) * 32 + (threadIdx.x & 31);
+  const int co = i % job.cout, ci = (i / job.cout) % job.ci_count, tap = i / (job.cout * job.ci_count);
+  const float* q = job.partial + (long(tap) * job.cin_total + job.ci_begin + ci) * job.cout + co;
+  const float t = sliced_sum(job.nparts, [&](int p) { return i < n ? __ldg(q + p * job.stride) : 0.f; });
+  if (threadIdx.x < 32 && i < n) job.dst[co * job.s_co + ci * job.s_ci + tap * job.s_tap] = t * job.scale;
+}
+
 // ------------------------------------------------------------------------------------------
 // BatchNorm2d training statistics (reference models/unet.py:133, nn.BatchNorm2d eps 1e-5 momentum 0.1):
 // reduce the per-CTA (sum, sum of squares) partials of the conv epilogue, produce mean / inverse std
@@ -393,6 +408,14 @@ extern "C" int unpp_reduce_partials(const float* partial, int nparts, long strid
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("reduce_partials: launch");
   return UNPP_OK;
 }
+
+extern "C" int unpp_reduce_batched(const UnppReduceJob* table, int njobs, int total_blocks, unpp_stream_t stream) {
+  if (!table || njobs < 1 || total_blocks < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "reduce_batched: bad argument");
+  reduce_batched_kernel<<<total_blocks, 256, 0, STREAM(stream)>>>(table, njobs);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("reduce_batched: launch");
+  return UNPP_OK;
+}
+extern "C" int unpp_sizeof_reduce_job(void) { return int(sizeof(UnppReduceJob)); }
 
 extern "C" int unpp_wgrad_reduce(const float* partial, int nparts, int taps, int cin_total, int cout, float* dst, int ci_begin, int ci_count,
                                  long s_co, long s_ci, long s_tap, float scale, unpp_stream_t stream) {

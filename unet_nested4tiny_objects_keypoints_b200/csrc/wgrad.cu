@@ -30,7 +30,7 @@ constexpr int kMaxStages = 8;  // TMA tiles in flight per CTA: the loop is laten
 
 struct WgradParams {
   CUtensorMap xmap[UNPP_MAX_SRC];
-  CUtensorMap zmap;
+  CUtensorMap zmap[4];  // dense dZ: [0]; transposed-conv taps: one strided view per (p, q), selected by blockIdx.z
   int njobs;
   int job_map[kMaxJobs], job_c0[kMaxJobs], job_cs[kMaxJobs], job_cioff[kMaxJobs], job_co0[kMaxJobs], job_con[kMaxJobs];
   int tiles_x, tiles_y, ntiles;
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     for (int i = 0; i < kMaxStages; ++i) mbar_init(&bar_full[i], 1);
     fence_mbar_init();
     tma_prefetch_desc(&p.xmap[p.job_map[job]]);
-    tma_prefetch_desc(&p.zmap);
+    tma_prefetch_desc(&p.zmap[blockIdx.z]);
   }
   __syncthreads();
 
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     uint8_t* zs = xs + xstage_bytes;
     mbar_arrive_expect_tx(&bar_full[buf], uint32_t(PY * PX * cs * 2 + TR * TC * con * 2));
     tma_load_4d(&p.xmap[p.job_map[job]], &bar_full[buf], xs, p.job_c0[job], tx * TC - pad, ty * TR - pad, n);
-    tma_load_4d(&p.zmap, &bar_full[buf], zs, p.job_co0[job], tx * TC, ty * TR, n);
+    tma_load_4d(&p.zmap[blockIdx.z], &bar_full[buf], zs, p.job_co0[job], tx * TC, ty * TR, n);
   };
 
   // fragment ownership: a warp owns ppw_job (tap x 16ci x 16co) fragment sets that share the ci block
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     } else {
       for (int k = 0; k < wpp; ++k) s += stage_f[(((pair + k * npairs) * PPW) * TAPS + t) * 256 + e];
     }
-    p.partial[((size_t(blockIdx.x) * TAPS + t) * p.cin_total + p.job_cioff[job] + cil) * p.cout + p.job_co0[job] + col] = s;
+    p.partial[((size_t(blockIdx.z * gridDim.x + blockIdx.x) * TAPS + t) * p.cin_total + p.job_cioff[job] + cil) * p.cout + p.job_co0[job] + col] = s;
   }
 }
 
@@ -199,7 +199,7 @@ EncodeTiledFn get_encode() {
 }
 
 struct Plan {
-  int njobs, ppw, pad, cin_total, tiles_x, tiles_y, ntiles, grid_x, xstage_bytes, zstage_bytes, smem_total, nstage;
+  int njobs, ppw, pad, cin_total, tiles_x, tiles_y, ntiles, grid_x, grid_z, xstage_bytes, zstage_bytes, smem_total, nstage;
   int job_map[kMaxJobs], job_c0[kMaxJobs], job_cs[kMaxJobs], job_cioff[kMaxJobs], job_co0[kMaxJobs], job_con[kMaxJobs];
 };
 
@@ -209,6 +209,9 @@ int make_plan(const UnppWgradArgs* a, Plan* pl) {
   if (a->N < 1 || a->H < 1 || a->W < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: empty pixel grid");
   if (a->cout != 16 && a->cout != 32 && a->cout != 64 && a->cout != 128) return unpp::fail(UNPP_ERR_UNSUPPORTED, "wgrad: cout must be 16/32/64/128");
   if (a->dz_step != 1 && a->dz_step != 2) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: dz_step must be 1 or 2");
+  const bool all4 = a->dz_step == 2 && a->dz_oy < 0;
+  if (all4 && a->taps != 1) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: the four-tap transposed-conv form needs taps = 1");
+  pl->grid_z = all4 ? 4 : 1;
   int nj = 0, ci_off = 0, max_cs = 0, max_con = 0, max_pairs = 0;
   for (int i = 0; i < a->nsrc; ++i) {
     const int C = a->src_C[i];
@@ -246,7 +249,7 @@ int make_plan(const UnppWgradArgs* a, Plan* pl) {
   pl->smem_total = 1024 + (pipe > staging ? pipe : staging);
   pl->tiles_x = (a->W + TC - 1) / TC, pl->tiles_y = (a->H + TR - 1) / TR;
   pl->ntiles = pl->tiles_x * pl->tiles_y * a->N;
-  int gx = unpp::num_sms() / nj;
+  int gx = unpp::num_sms() / (nj * pl->grid_z);
   if (gx < 1) gx = 1;
   if (gx > pl->ntiles) gx = pl->ntiles;
   pl->grid_x = gx;
@@ -261,7 +264,7 @@ int launch(const WgradParams& p, const Plan& pl, cudaStream_t stream) {
       return unpp::fail_cuda("wgrad: cudaFuncSetAttribute");
     opted_in = true;
   }
-  wgrad_kernel<TAPS, PPW><<<dim3(pl.grid_x, pl.njobs), kThreads, pl.smem_total, stream>>>(p);
+  wgrad_kernel<TAPS, PPW><<<dim3(pl.grid_x, pl.njobs, pl.grid_z), kThreads, pl.smem_total, stream>>>(p);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("wgrad: launch");
   return UNPP_OK;
 }
@@ -298,15 +301,16 @@ extern "C" int unpp_wgrad(const UnppWgradArgs* a, unpp_stream_t stream_) {
                      bc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled failed (CUresult %d) for source %d", int(r), i);
   }
-  {
-    // dZ may be a stride-2 view of a [N, 2H, 2W, cout] tensor (transposed-conv weight gradient)
+  for (int z = 0; z < pl.grid_z; ++z) {
+    // dZ may be a stride-2 view of a [N, 2H, 2W, cout] tensor (transposed-conv weight gradient): tap (p, q) = (oy, ox)
+    const int oy = pl.grid_z == 4 ? (z >> 1) : a->dz_oy, ox = pl.grid_z == 4 ? (z & 1) : a->dz_ox;
     const cuuint64_t C = a->cout, st = a->dz_step, fullW = cuuint64_t(a->W) * st, fullH = cuuint64_t(a->H) * st;
-    const uint8_t* base = reinterpret_cast<const uint8_t*>(a->dz) + (size_t(a->dz_oy) * fullW + a->dz_ox) * C * 2;
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(a->dz) + (size_t(oy) * fullW + ox) * C * 2;
     cuuint64_t gd[4] = {C, cuuint64_t(a->W), cuuint64_t(a->H), cuuint64_t(a->N)};
     cuuint64_t gs[3] = {C * 2 * st, fullW * C * 2 * st, fullH * fullW * C * 2};
     const int con = a->cout < 64 ? a->cout : 64;
     cuuint32_t box[4] = {cuuint32_t(con), cuuint32_t(TC), cuuint32_t(TR), 1};
-    CUresult r = enc(&p.zmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<uint8_t*>(base), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(&p.zmap[z], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<uint8_t*>(base), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      con == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : con == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled failed (CUresult %d) for dZ", int(r));
   }

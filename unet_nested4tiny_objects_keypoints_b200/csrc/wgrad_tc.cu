@@ -24,9 +24,16 @@
 // four issuing threads work in parallel) stay in TMEM for the whole kernel; each CTA writes one
 // partial [9][Cin_total][Cout] at the end, reduced in fixed order by unpp_wgrad_reduce (deterministic).
 //
-// Shared-memory operand traffic per MMA is 4 KB (A) + 96 * Cout B (B) for 16 pixels, i.e. 352 B per
-// pixel and 16-channel source at the full-resolution level against 64 B of HBM traffic: the two
-// limits (128 B/clk/SM shared memory, 6.5 TB/s HBM) are within 5 % of each other there.
+// Pixel-pair view (all sources and the output 16 channels wide — the full-resolution level): the
+// [N,H,W,16] tensors are read as [N,H,W/2,32], i.e. a K row is a horizontal pixel PAIR (64 B TMA rows
+// move at ~5.8 TB/s, 32 B rows only at ~4.4) and the M / N element inside an atom is (parity e, channel).
+// With the X box starting one pair left of the dZ box, D[(j, e, ci)][(i, e', co)] is the tap with
+// x-offset e - e' + 2j - 1 (in {0,1,2} for six of the sixteen (j, e, e') combinations): every tap is the
+// sum of exactly two accumulator entries, which the read-out writes to two partial "slots" (the grid
+// query reports 2 partials per CTA), so the fixed-order reduction stays as it is.
+//
+// Shared-memory operand traffic per MMA: 4 KB (A) + 96 * Cout B (B) for 16 K rows, i.e. 224 B per
+// pixel and 16-channel source in the pair view (352 B without it) against 64 B of HBM traffic.
 #include <cstdlib>
 #include "sm100.cuh"
 #include "common.h"
@@ -36,7 +43,7 @@ using namespace sm100;
 
 namespace {
 
-constexpr int TR = 16, TW = 32, PX = TW + 2;
+constexpr int TW = 32, PX = TW + 2;  // K rows (pixels or pixel pairs) per tile row; tile rows TR = 8 or 16 (plan)
 constexpr int kIssuers = 4;
 constexpr int kThreads = 256;  // warp 0: TMA producer, warps 1..4: MMA issuers, all eight: final TMEM read-out
 constexpr int kMaxX = 8, kMaxZ = 4;
@@ -48,6 +55,9 @@ struct Params {
   int src_C[UNPP_MAX_SRC], cioff[UNPP_MAX_SRC];
   int tiles_x, tiles_y, ntiles;
   int cin_total, cout;
+  int TR;                    // tile rows
+  int pair;                  // pixel-pair view: src_C / zspan below are the EFFECTIVE widths (32), cout the real one (16)
+  int zspan;                 // bytes per K row of the dZ tile
   int xslot, zslot, nx, nz;  // ring geometry: bytes per slot, slots
   int nsplit, ncols, tmem_cols;
   float* partial;
@@ -80,7 +90,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   const int nsrc = p.nsrc, ntiles = p.ntiles, nx = p.nx, nz = p.nz, nsplit = p.nsplit, ncols = p.ncols;
-  const int zspan = p.cout * 2;
+  const int zspan = p.zspan, TR = p.TR;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -168,11 +178,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     const int q = warp & 3, half = warp >> 2;
     const int m = q * 32 + lane;
     const int ngroups = ncols >> 4;
-    float* const part = p.partial + size_t(blockIdx.x) * 9 * p.cin_total * p.cout;
+    const int cout = p.cout, pair = p.pair;
+    const size_t part_elems = size_t(9) * p.cin_total * cout;
+    float* const part = p.partial + size_t(blockIdx.x) * (pair ? 2 : 1) * part_elems;
     for (int u = 0; u < nsrc; ++u) {
-      const int C = p.src_C[u];
+      const int C = p.src_C[u];  // effective width of an atom
       if (q * 32 >= 3 * C) continue;  // warp-uniform: this lane quadrant only holds discarded shifts
-      const int j = m / C, ci = m % C;
+      const int j = m / C;
+      const int e = pair ? ((m >> 4) & 1) : 0, ci = pair ? (m & 15) : m % C;
       for (int g = half; g < ngroups; g += 2) {
         float v[16];
 #pragma unroll
@@ -184,10 +197,18 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
 #pragma unroll
           for (int k = 0; k < 16; ++k) v[k] += __uint_as_float(raw[k]);
         }
-        if (j < 3) {
-          const int i = (g * 16) / p.cout, co0 = (g * 16) % p.cout;
-          const int tap = (2 - i) * 3 + j;
-          float4* dst = reinterpret_cast<float4*>(part + (size_t(tap) * p.cin_total + p.cioff[u] + ci) * p.cout + co0);
+        int i, co0, sft, slot = 0;
+        if (pair) {  // column group = (dZ row shift i, parity e'); tap column = e - e' + 2j - 1
+          i = g >> 1;
+          co0 = 0;
+          sft = e - (g & 1) + 2 * j - 1;
+          slot = sft == 1 ? e : 1 - e;
+        } else {
+          i = (g * 16) / cout, co0 = (g * 16) % cout, sft = j;
+        }
+        if (j < 3 && sft >= 0 && sft < 3) {
+          const int tap = (2 - i) * 3 + sft;
+          float4* dst = reinterpret_cast<float4*>(part + slot * part_elems + (size_t(tap) * p.cin_total + p.cioff[u] + ci) * cout + co0);
 #pragma unroll
           for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
         }
@@ -215,31 +236,43 @@ EncodeTiledFn get_encode() {
 
 struct Plan {
   int cin_total, max_C, xslot, zslot, nx, nz, nsplit, ncols, tmem_cols, smem_total, tiles_x, tiles_y, ntiles, grid_x;
-  int cioff[UNPP_MAX_SRC];
+  int TR, pair, ecout, We;  // tile rows; pixel-pair view: effective output width, K rows per image row
+  int cioff[UNPP_MAX_SRC], eC[UNPP_MAX_SRC];
 };
 
 void make_plan(const UnppWgradArgs* a, Plan* pl) {
   int off = 0, maxc = 0;
+  pl->pair = (a->cout == 16 && !(a->W & 1) && a->nsrc * 96 <= 512) ? 1 : 0;
+  for (int i = 0; i < a->nsrc; ++i)
+    if (a->src_C[i] != 16) pl->pair = 0;
+  pl->ecout = pl->pair ? 32 : a->cout, pl->We = pl->pair ? a->W / 2 : a->W;
   for (int i = 0; i < a->nsrc; ++i) {
     pl->cioff[i] = off;
     off += a->src_C[i];
-    if (a->src_C[i] > maxc) maxc = a->src_C[i];
+    pl->eC[i] = pl->pair ? 32 : a->src_C[i];
+    if (pl->eC[i] > maxc) maxc = pl->eC[i];
   }
   pl->cin_total = off, pl->max_C = maxc;
-  pl->ncols = 3 * a->cout;
+  pl->ncols = 3 * pl->ecout;
+  int TR = 16;
+  {
+    const char* e = getenv("UNPP_WGRAD_TR");
+    if (e && atoi(e) == 8) TR = 8;
+  }
+  pl->TR = TR;
   int ns = 512 / (a->nsrc * pl->ncols);
   pl->nsplit = ns > kIssuers ? kIssuers : ns;
   int need = a->nsrc * pl->nsplit * pl->ncols, tc = 32;
   while (tc < need) tc <<= 1;
   pl->tmem_cols = tc;
   pl->xslot = (TR * PX * maxc * 2 + 1023) / 1024 * 1024;
-  pl->zslot = ((TR + 2) * TW * a->cout * 2 + 1023) / 1024 * 1024;
+  pl->zslot = ((TR + 2) * TW * pl->ecout * 2 + 1023) / 1024 * 1024;
   const int budget = 212 * 1024;
-  pl->nz = a->cout == 16 ? 3 : 2;
+  pl->nz = (pl->ecout == 16 || TR == 8) ? 3 : 2;
   pl->nx = (budget - pl->nz * pl->zslot) / pl->xslot;
   if (pl->nx > kMaxX) pl->nx = kMaxX;
   pl->smem_total = 1024 + pl->nz * pl->zslot + pl->nx * pl->xslot + 1024;  // tail: the discarded shifts of the last row read past the slot
-  pl->tiles_x = (a->W + TW - 1) / TW, pl->tiles_y = (a->H + TR - 1) / TR;
+  pl->tiles_x = (pl->We + TW - 1) / TW, pl->tiles_y = (a->H + TR - 1) / TR;
   pl->ntiles = pl->tiles_x * pl->tiles_y * a->N;
   const int sms = unpp::num_sms();
   pl->grid_x = pl->ntiles < sms ? pl->ntiles : sms;
@@ -266,7 +299,7 @@ bool wgrad_tc_eligible(const UnppWgradArgs* a) {
 int wgrad_tc_grid(const UnppWgradArgs* a) {
   Plan pl;
   make_plan(a, &pl);
-  return pl.grid_x;
+  return pl.grid_x * (pl.pair ? 2 : 1);  // partials written (the pair view writes two per CTA)
 }
 
 int wgrad_tc_launch(const UnppWgradArgs* a, cudaStream_t stream) {
@@ -279,20 +312,20 @@ int wgrad_tc_launch(const UnppWgradArgs* a, cudaStream_t stream) {
   memset(&p, 0, sizeof p);
   cuuint32_t es[4] = {1, 1, 1, 1};
   for (int i = 0; i < a->nsrc; ++i) {
-    const cuuint64_t C = a->src_C[i];
-    cuuint64_t gd[4] = {C, cuuint64_t(a->W), cuuint64_t(a->H), cuuint64_t(a->N)};
-    cuuint64_t gs[3] = {C * 2, cuuint64_t(a->W) * C * 2, cuuint64_t(a->H) * a->W * C * 2};
-    cuuint32_t box[4] = {cuuint32_t(C), cuuint32_t(PX), cuuint32_t(TR), 1};
+    const cuuint64_t C = pl.eC[i];
+    cuuint64_t gd[4] = {C, cuuint64_t(pl.We), cuuint64_t(a->H), cuuint64_t(a->N)};
+    cuuint64_t gs[3] = {C * 2, cuuint64_t(pl.We) * C * 2, cuuint64_t(a->H) * pl.We * C * 2};
+    cuuint32_t box[4] = {cuuint32_t(C), cuuint32_t(PX), cuuint32_t(pl.TR), 1};
     CUresult r = enc(&p.xmap[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->src[i]), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled failed (CUresult %d) for source %d", int(r), i);
-    p.src_C[i] = a->src_C[i], p.cioff[i] = pl.cioff[i];
+    p.src_C[i] = pl.eC[i], p.cioff[i] = pl.cioff[i];
   }
   {
-    const cuuint64_t C = a->cout;
-    cuuint64_t gd[4] = {C, cuuint64_t(a->W), cuuint64_t(a->H), cuuint64_t(a->N)};
-    cuuint64_t gs[3] = {C * 2, cuuint64_t(a->W) * C * 2, cuuint64_t(a->H) * a->W * C * 2};
-    cuuint32_t box[4] = {cuuint32_t(C), cuuint32_t(TW), cuuint32_t(TR + 2), 1};
+    const cuuint64_t C = pl.ecout;
+    cuuint64_t gd[4] = {C, cuuint64_t(pl.We), cuuint64_t(a->H), cuuint64_t(a->N)};
+    cuuint64_t gs[3] = {C * 2, cuuint64_t(pl.We) * C * 2, cuuint64_t(a->H) * pl.We * C * 2};
+    cuuint32_t box[4] = {cuuint32_t(C), cuuint32_t(TW), cuuint32_t(pl.TR + 2), 1};
     CUresult r = enc(&p.zmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->dz), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled failed (CUresult %d) for dZ", int(r));
@@ -300,6 +333,7 @@ int wgrad_tc_launch(const UnppWgradArgs* a, cudaStream_t stream) {
   p.nsrc = a->nsrc;
   p.tiles_x = pl.tiles_x, p.tiles_y = pl.tiles_y, p.ntiles = pl.ntiles;
   p.cin_total = pl.cin_total, p.cout = a->cout;
+  p.pair = pl.pair, p.zspan = pl.ecout * 2, p.TR = pl.TR;
   p.xslot = pl.xslot, p.zslot = pl.zslot, p.nx = pl.nx, p.nz = pl.nz;
   p.nsplit = pl.nsplit, p.ncols = pl.ncols, p.tmem_cols = pl.tmem_cols;
   p.partial = a->partial;

@@ -13,13 +13,14 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ConvArgs, PackArgs, WgradArgs, MODE_CONV, MODE_DECONV  # noqa: F401
+from ._lib import ConvArgs, PackArgs, ReduceJob, WgradArgs, MODE_CONV, MODE_DECONV  # noqa: F401
 
 W_SMEM_BUDGET = 96 * 1024  # packed weights of one n_tile kept resident in shared memory
 
 
 pack_record = None  # when a list: pack_weights() appends its validated PackArgs instead of launching (see pack_batched)
 launch_count = 0   # kernels of libunpp.so enqueued through this module (bench.py reads it for "gpu_launches")
+reduce_queue = None  # when a list: reductions called with defer=True are queued for ONE unpp_reduce_batched launch (flush_reduce_queue)
 trace = None       # when a list: conv()/wgrad() append (label, start_event, end_event, algorithmic_bytes, flops)
 
 
@@ -107,7 +108,8 @@ def pack_weights(src: torch.Tensor, kind: int, taps: int, n_total: int, n_tile: 
         pack_record.append((a, src))  # keep the source tensor alive with its job
         return dst
     _count()
-    _lib.check(lib().unpp_pack_weights(C.byref(a), _stream()), "unpp_pack_weights")
+    with _Traced("pack_weights", 0, 0):
+        _lib.check(lib().unpp_pack_weights(C.byref(a), _stream()), "unpp_pack_weights")
     return dst
 
 
@@ -119,7 +121,8 @@ def make_pack_table(jobs, device) -> torch.Tensor:
 
 def pack_batched(table: torch.Tensor, n: int) -> None:
     _count()
-    _lib.check(lib().unpp_pack_weights_batched(table.data_ptr(), n, _stream()), "unpp_pack_weights_batched")
+    with _Traced("pack_weights_batched", 0, 0):
+        _lib.check(lib().unpp_pack_weights_batched(table.data_ptr(), n, _stream()), "unpp_pack_weights_batched")
 
 
 def _conv_args(srcs, N, H, W, n_total, n_tile, taps, strided=None, b2=False) -> ConvArgs:
@@ -180,6 +183,9 @@ def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Te
     if lowres is not None:  # count the unfused arithmetic it replaces: the k2s2 transposed conv + its 3x3 taps
         flops += 2 * px * lowres[0].shape[-1] * n_total + 2 * px * n_total * n_total * taps
     label = "conv_tc %s taps%d K%d N%d %dx%d" % ("deconv" if mode == MODE_DECONV else ("conv2x2" if a.block2x2 else "conv"), taps, k_total, n_total, H, W)
+    flags = [n for n, v in (("st", stats_partial), ("aux", stats_aux), ("mask", relu_mask_src), ("add", addend), ("head", head), ("s2", strided), ("low", lowres)) if v is not None]
+    if flags:
+        label += " +" + "+".join(flags)
     with _Traced(label, nbytes, flops):
         _lib.check(lib().unpp_conv_tc(C.byref(a), _stream()), "unpp_conv_tc")
 
@@ -196,13 +202,15 @@ def conv_grid(srcs_C: Sequence[int], N: int, H: int, W: int, n_total: int, n_til
 def nchw_to_nhwc16(x: torch.Tensor, out: torch.Tensor) -> None:
     B, Cin, H, W = x.shape
     _count()
-    _lib.check(lib().unpp_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, Cin, H, W, 16, _stream()), "unpp_nchw_to_nhwc")
+    with _Traced("nchw_to_nhwc", 0, 0):
+        _lib.check(lib().unpp_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, Cin, H, W, 16, _stream()), "unpp_nchw_to_nhwc")
 
 
 def maxpool(x: torch.Tensor, out: torch.Tensor) -> None:
     B, H, W, Cc = x.shape
     _count()
-    _lib.check(lib().unpp_maxpool2x2(x.data_ptr(), out.data_ptr(), B, H, W, Cc, _stream()), "unpp_maxpool2x2")
+    with _Traced("maxpool2x2", 0, 0):
+        _lib.check(lib().unpp_maxpool2x2(x.data_ptr(), out.data_ptr(), B, H, W, Cc, _stream()), "unpp_maxpool2x2")
 
 
 def argmax_peaks(heat: torch.Tensor):
@@ -214,7 +222,8 @@ def argmax_peaks(heat: torch.Tensor):
     xy = torch.empty(B, Cc, 2, dtype=torch.int32, device=heat.device)
     val = torch.empty(B, Cc, dtype=torch.float32, device=heat.device)
     _count()
-    _lib.check(lib().unpp_argmax_peaks(heat.data_ptr(), B * Cc, H, W, xy.data_ptr(), val.data_ptr(), _stream()), "unpp_argmax_peaks")
+    with _Traced("argmax_peaks", 0, 0):
+        _lib.check(lib().unpp_argmax_peaks(heat.data_ptr(), B * Cc, H, W, xy.data_ptr(), val.data_ptr(), _stream()), "unpp_argmax_peaks")
     return xy, val
 
 
@@ -231,13 +240,15 @@ def _wgrad_args(srcs, N, H, W, dz, cout, taps, dz_view=None) -> WgradArgs:
     a.cout, a.taps = cout, taps
     if dz_view is None:
         a.dz_step, a.dz_oy, a.dz_ox = 1, 0, 0
+    elif dz_view == "all4":  # the four taps of a k2s2 transposed conv in one launch: partial [4][grid][1][cin][cout]
+        a.dz_step, a.dz_oy, a.dz_ox = 2, -1, -1
     else:
         a.dz_step, a.dz_oy, a.dz_ox = 2, dz_view[0], dz_view[1]
     return a
 
 
-def wgrad_grid(srcs_C: Sequence[int], N: int, H: int, W: int, cout: int, taps: int) -> int:
-    a = _wgrad_args(list(srcs_C), N, H, W, None, cout, taps)
+def wgrad_grid(srcs_C: Sequence[int], N: int, H: int, W: int, cout: int, taps: int, dz_view=None) -> int:
+    a = _wgrad_args(list(srcs_C), N, H, W, None, cout, taps, dz_view)
     g = lib().unpp_wgrad_grid(C.byref(a))
     if g < 0:
         _lib.check(g, "unpp_wgrad_grid")
@@ -250,27 +261,68 @@ def wgrad(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, dz: torch.Tensor
     _count()
     k_total = sum(s.shape[-1] for s in srcs)
     px = N * H * W
-    with _Traced("wgrad taps%d K%d N%d %dx%d" % (taps, k_total, cout, H, W), px * (k_total + cout) * 2, 2 * px * k_total * cout * taps):
+    nz = 4 if dz_view == "all4" else 1
+    with _Traced("wgrad taps%d K%d N%d %dx%d%s" % (taps, k_total, cout, H, W, " x4" if nz == 4 else ""), px * (k_total + nz * cout) * 2,
+                 2 * px * k_total * cout * taps * nz):
         _lib.check(lib().unpp_wgrad(C.byref(a), _stream()), "unpp_wgrad")
 
 
-def wgrad_reduce(partial: torch.Tensor, nparts: int, taps: int, cin_total: int, cout: int, dst: torch.Tensor, ci_begin: int, ci_count: int,
-                 s_co: int, s_ci: int, s_tap: int, scale: float = 1.0, dst_offset: int = 0) -> None:
+def _queue_reduce(partial_ptr, dst_ptr, stride, s_co, s_ci, s_tap, nparts, taps, cin_total, cout, ci_begin, ci_count, scale, keep) -> None:
+    j = ReduceJob()
+    j.partial, j.dst, j.stride, j.s_co, j.s_ci, j.s_tap = partial_ptr, dst_ptr, stride, s_co, s_ci, s_tap
+    j.nparts, j.taps, j.cin_total, j.cout, j.ci_begin, j.ci_count, j.scale = nparts, taps, cin_total, cout, ci_begin, ci_count, scale
+    reduce_queue.append((j, keep))
+
+
+def flush_reduce_queue(cache: dict, device) -> None:
+    """Launch every queued reduction as one unpp_reduce_batched and switch queueing off.  The device-resident job
+    table is cached by content (pointers are stable across steps), so a captured step replays without host work."""
+    global reduce_queue
+    jobs, reduce_queue = reduce_queue, None
+    if not jobs:
+        return
+    blocks = 0
+    for j, _ in jobs:
+        blocks += (j.taps * j.ci_count * j.cout + 31) // 32
+        j.block_end = blocks
+    raw = b"".join(bytes(j) for j, _ in jobs)
+    table = cache.get(raw)
+    if table is None:
+        if len(cache) >= 8:  # the autograd path may see a new gradient buffer address per call
+            cache.clear()
+        table = cache[raw] = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
     _count()
-    _lib.check(lib().unpp_wgrad_reduce(partial.data_ptr(), nparts, taps, cin_total, cout, dst.data_ptr() + 4 * dst_offset, ci_begin, ci_count,
+    with _Traced("reduce_batched", 0, 0):
+        _lib.check(lib().unpp_reduce_batched(table.data_ptr(), len(jobs), blocks, _stream()), "unpp_reduce_batched")
+
+
+def wgrad_reduce(partial: torch.Tensor, nparts: int, taps: int, cin_total: int, cout: int, dst: torch.Tensor, ci_begin: int, ci_count: int,
+                 s_co: int, s_ci: int, s_tap: int, scale: float = 1.0, dst_offset: int = 0, partial_offset: int = 0, defer: bool = False) -> None:
+    if defer and reduce_queue is not None:
+        _queue_reduce(partial.data_ptr() + 4 * partial_offset, dst.data_ptr() + 4 * dst_offset, taps * cin_total * cout, s_co, s_ci, s_tap, nparts, taps,
+                      cin_total, cout, ci_begin, ci_count, scale, (partial, dst))
+        return
+    _count()
+    with _Traced("wgrad_reduce", 0, 0):
+        _lib.check(lib().unpp_wgrad_reduce(partial.data_ptr() + 4 * partial_offset, nparts, taps, cin_total, cout, dst.data_ptr() + 4 * dst_offset, ci_begin, ci_count,
                                        s_co, s_ci, s_tap, scale, _stream()), "unpp_wgrad_reduce")
 
 
 def reduce_partials(partial: torch.Tensor, nparts: int, stride: int, n: int, out: torch.Tensor, scale: float = 1.0, accumulate: bool = False,
-                    partial_offset: int = 0, out_offset: int = 0) -> None:
+                    partial_offset: int = 0, out_offset: int = 0, defer: bool = False) -> None:
+    if defer and reduce_queue is not None and not accumulate:
+        _queue_reduce(partial.data_ptr() + 4 * partial_offset, out.data_ptr() + 4 * out_offset, stride, 1, 0, 0, nparts, 1, 1, n, 0, 1, scale, (partial, out))
+        return
     _count()
-    _lib.check(lib().unpp_reduce_partials(partial.data_ptr() + 4 * partial_offset, nparts, stride, n, scale, out.data_ptr() + 4 * out_offset,
+    with _Traced("reduce_partials", 0, 0):
+        _lib.check(lib().unpp_reduce_partials(partial.data_ptr() + 4 * partial_offset, nparts, stride, n, scale, out.data_ptr() + 4 * out_offset,
                                           int(accumulate), _stream()), "unpp_reduce_partials")
 
 
 def bn_finalize(partial, nparts, Cc, count, gamma, beta, running_mean, running_var, momentum, eps, mean, istd, scale, shift) -> None:
     _count()
-    _lib.check(lib().unpp_bn_finalize(partial.data_ptr(), nparts, Cc, float(count), gamma.data_ptr(), beta.data_ptr(), _ptr(running_mean),
+    with _Traced("bn_finalize", 0, 0):
+        _lib.check(lib().unpp_bn_finalize(partial.data_ptr(), nparts, Cc, float(count), gamma.data_ptr(), beta.data_ptr(), _ptr(running_mean),
                                       _ptr(running_var), float(momentum), float(eps), mean.data_ptr(), istd.data_ptr(), scale.data_ptr(),
                                       shift.data_ptr(), _stream()), "unpp_bn_finalize")
 
@@ -278,19 +330,22 @@ def bn_finalize(partial, nparts, Cc, count, gamma, beta, running_mean, running_v
 def bn_relu(z, scale, shift, y, pooled=None) -> None:
     N, H, W, Cc = z.shape
     _count()
-    _lib.check(lib().unpp_bn_relu(z.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), _ptr(pooled), N, H, W, Cc, _stream()), "unpp_bn_relu")
+    with _Traced("bn_relu", 0, 0):
+        _lib.check(lib().unpp_bn_relu(z.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), _ptr(pooled), N, H, W, Cc, _stream()), "unpp_bn_relu")
 
 
 def maxpool_bwd(x, dpooled, dx) -> None:
     N, H, W, Cc = x.shape
     _count()
-    _lib.check(lib().unpp_maxpool2x2_bwd(x.data_ptr(), dpooled.data_ptr(), dx.data_ptr(), N, H, W, Cc, _stream()), "unpp_maxpool2x2_bwd")
+    with _Traced("maxpool2x2_bwd", 0, 0):
+        _lib.check(lib().unpp_maxpool2x2_bwd(x.data_ptr(), dpooled.data_ptr(), dx.data_ptr(), N, H, W, Cc, _stream()), "unpp_maxpool2x2_bwd")
 
 
 def bn_bwd_apply(dyh, z, mean, istd, gamma, sums, count, dz) -> None:
     N, H, W, Cc = z.shape
     _count()
-    _lib.check(lib().unpp_bn_bwd_apply(dyh.data_ptr(), z.data_ptr(), mean.data_ptr(), istd.data_ptr(), gamma.data_ptr(), sums.data_ptr(),
+    with _Traced("bn_bwd_apply", 0, 0):
+        _lib.check(lib().unpp_bn_bwd_apply(dyh.data_ptr(), z.data_ptr(), mean.data_ptr(), istd.data_ptr(), gamma.data_ptr(), sums.data_ptr(),
                                        float(count), dz.data_ptr(), N, H, W, Cc, _stream()), "unpp_bn_bwd_apply")
 
 
@@ -301,7 +356,8 @@ def head_bwd_grid(N: int, H: int, W: int) -> int:
 def head_bwd(heat, dheat, target, coef, x, drop_mask, drop_scale, head_w, dx, partial, loss_kind: int = 0, gamma: float = 3.0) -> None:
     N, ncls, H, W = heat.shape
     _count()
-    _lib.check(lib().unpp_head_bwd(heat.data_ptr(), _ptr(dheat), _ptr(target), int(loss_kind), float(gamma), float(coef), x.data_ptr(), _ptr(drop_mask), float(drop_scale),
+    with _Traced("head_bwd", 0, 0):
+        _lib.check(lib().unpp_head_bwd(heat.data_ptr(), _ptr(dheat), _ptr(target), int(loss_kind), float(gamma), float(coef), x.data_ptr(), _ptr(drop_mask), float(drop_scale),
                                    head_w.data_ptr(), ncls, dx.data_ptr(), partial.data_ptr(), N, H, W, _stream()), "unpp_head_bwd")
 
 
@@ -310,7 +366,8 @@ def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0)
     for t in (p, g, m, v):
         assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous() and t.numel() == p.numel()
     _count()
-    _lib.check(lib().unpp_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+    with _Traced("adamw", 0, 0):
+        _lib.check(lib().unpp_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
                                 float(weight_decay), int(step), float(grad_scale), _stream()), "unpp_adamw")
 
 
@@ -328,7 +385,8 @@ def adamw_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_counter, ste
 def dropout_mask(mask: torch.Tensor, p_drop: float, seed: int, step_counter: Optional[torch.Tensor] = None) -> None:
     assert mask.dtype == torch.uint8 and mask.is_cuda and mask.is_contiguous()
     _count()
-    _lib.check(lib().unpp_dropout_mask(mask.data_ptr(), mask.numel(), float(p_drop), int(seed) & (2**64 - 1), _ptr(step_counter), _stream()),
+    with _Traced("create_heatmap", 0, 0):
+        _lib.check(lib().unpp_dropout_mask(mask.data_ptr(), mask.numel(), float(p_drop), int(seed) & (2**64 - 1), _ptr(step_counter), _stream()),
                "unpp_dropout_mask")
 
 

@@ -222,6 +222,7 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
         eng._packed_key = None  # running statistics change below without a torch version bump: drop the eval-mode fold cache
     ops.nchw_to_nhwc16(x, t["x16"])
     src = t["x16"]
+    tracked: List[torch.Tensor] = []
     for lvl, name in enumerate(ENCODER):
         h, w, c = H >> lvl, W >> lvl, eng.filters[lvl]
         count = B * h * w
@@ -241,13 +242,15 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
                             bn.running_var if update_running_stats else None, mom, bn.eps, t[pre + ".mean"], t[pre + ".istd"], t[pre + ".scale"],
                             t[pre + ".shift"])
             if update_running_stats:
-                bn.num_batches_tracked += 1
+                tracked.append(bn.num_batches_tracked)
             if n == 1:
                 ops.bn_relu(z, t[pre + ".scale"], t[pre + ".shift"], t[f"{name}.a"])
                 src = t[f"{name}.a"]
             else:
                 ops.bn_relu(z, t[pre + ".scale"], t[pre + ".shift"], t[f"X{lvl}0"], t[f"P{lvl}0"] if lvl < 3 else None)
                 src = t[f"P{lvl}0"] if lvl < 3 else None
+    if tracked:
+        torch._foreach_add_(tracked, 1)  # the eight int64 num_batches_tracked counters: one launch
     heats: List[torch.Tensor] = [None, None, None]
     for name in DECODER_ORDER:
         high, lows, lvl = DECODER[name]
@@ -283,29 +286,33 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
     def goff(pname):
         return lay[pname][0]
 
-    def stats_buf(srcs_C, n_total, nt, taps, h, w):
+    # Reductions whose result only the optimizer reads (weight / bias gradients) are queued and run as ONE batched
+    # launch at the end of the backward pass; each therefore owns its partial buffer (keyed by the parameter name).
+    ops.reduce_queue = []
+
+    def stats_buf(srcs_C, n_total, nt, taps, h, w, key="stats"):
         g = ops.conv_grid(srcs_C, B, h, w, n_total, nt, taps)
-        return g, ts.scratch_f32("stats", g * 2 * n_total)
+        return g, ts.scratch_f32(key, g * 2 * n_total)
 
     def bias_from_stats(part, g, c, pname):
-        ops.reduce_partials(part, g, 2 * c, c, G, out_offset=goff(pname))
+        ops.reduce_partials(part, g, 2 * c, c, G, out_offset=goff(pname), defer=True)
 
     def wgrad_conv(srcs, dz, h, w, pname, ci_count=None):
         cins = [s.shape[-1] for s in srcs]
         cin, cout = sum(cins), dz.shape[-1]
         g = ops.wgrad_grid(cins, B, h, w, cout, 9)
-        part = ts.scratch_f32("wgrad", g * 9 * cin * cout)
+        part = ts.scratch_f32("wgrad:" + pname, g * 9 * cin * cout)
         ops.wgrad(srcs, B, h, w, dz, cout, 9, part)
         real = cin if ci_count is None else ci_count
-        ops.wgrad_reduce(part, g, 9, cin, cout, G, 0, real, real * 9, 9, 1, dst_offset=goff(pname))
+        ops.wgrad_reduce(part, g, 9, cin, cout, G, 0, real, real * 9, 9, 1, dst_offset=goff(pname), defer=True)
 
-    def wgrad_deconv(xhigh, dU, h2, w2, pname):  # xhigh [B,h2,w2,cin], dU [B,2h2,2w2,cout]
+    def wgrad_deconv(xhigh, dU, h2, w2, pname):  # xhigh [B,h2,w2,cin], dU [B,2h2,2w2,cout]; the four taps in one launch
         cin, cout = xhigh.shape[-1], dU.shape[-1]
-        g = ops.wgrad_grid([cin], B, h2, w2, cout, 1)
-        part = ts.scratch_f32("wgrad", g * cin * cout)
-        for pq, (p_, q_) in enumerate(PQ):
-            ops.wgrad([xhigh], B, h2, w2, dU, cout, 1, part, dz_view=(p_, q_))
-            ops.wgrad_reduce(part, g, 1, cin, cout, G, 0, cin, 4, cout * 4, 0, dst_offset=goff(pname) + pq)
+        g = ops.wgrad_grid([cin], B, h2, w2, cout, 1, dz_view="all4")
+        part = ts.scratch_f32("wgrad:" + pname, 4 * g * cin * cout)
+        ops.wgrad([xhigh], B, h2, w2, dU, cout, 1, part, dz_view="all4")
+        for pq in range(4):
+            ops.wgrad_reduce(part, g, 1, cin, cout, G, 0, cin, 4, cout * 4, 0, dst_offset=goff(pname) + pq, partial_offset=pq * g * cin * cout, defer=True)
 
     def deconv_dgrad(dname, h2, w2, out, addend=None, mask=None, stats=None):
         """grad wrt the high-resolution... rather LOW-resolution input of decoder ``dname``'s transposed conv."""
@@ -327,8 +334,8 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
             ops.head_bwd(ts.heats[k], dh, target if dh is None else None, coef, t[f"X{name[-2:]}"], t[f"mask{k}"] if ts.use_masks else None,
                          ts.drop_scale, hm.weight.view(ncls, -1), t[f"dXh{k}"], part, loss_kind=loss_kind, gamma=gamma)
             ops.reduce_partials(part, ts.head_grid, ts.head_nacc, ts.head_nacc, t["head_red"][k])
-        ops.reduce_partials(t["head_red"], 1, 0, ncls * 16, G, out_offset=goff(hname + ".weight"), partial_offset=k * ts.head_nacc)
-        ops.reduce_partials(t["head_red"], 1, 0, ncls, G, out_offset=goff(hname + ".bias"), partial_offset=k * ts.head_nacc + ncls * 16)
+        ops.reduce_partials(t["head_red"], 1, 0, ncls * 16, G, out_offset=goff(hname + ".weight"), partial_offset=k * ts.head_nacc, defer=True)
+        ops.reduce_partials(t["head_red"], 1, 0, ncls, G, out_offset=goff(hname + ".bias"), partial_offset=k * ts.head_nacc + ncls * 16, defer=True)
 
     def decoder_node_backward(name, dZ2_ready_bias_done):
         """Given dZ2 (grad at the pre-ReLU output of the node's second conv), produce dZ1, dU and all
@@ -340,12 +347,12 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
         pre = f"{name}.conv"
         wgrad_conv([t[f"{name}.a"]], dZ2, h, w, f"{pre}.conv2.0.weight")
         key = f"{name}.c2.dgrad"
-        g, part = stats_buf([c], c, P[key + ".nt"], 9, h, w)
+        g, part = stats_buf([c], c, P[key + ".nt"], 9, h, w, key=f"stats:{pre}.conv1.0.bias")
         ops.conv([dZ2], B, h, w, P[key], c, P[key + ".nt"], 9, out=dZ1, relu_mask_src=t[f"{name}.a"], stats_partial=part)
         bias_from_stats(part, g, c, f"{pre}.conv1.0.bias")
         wgrad_conv([t[f"U{tag}"]] + [t[l] for l in lows], dZ1, h, w, f"{pre}.conv1.0.weight")
         key = f"{name}.c1.dgradU"
-        g, part = stats_buf([c], c, P[key + ".nt"], 9, h, w)
+        g, part = stats_buf([c], c, P[key + ".nt"], 9, h, w, key=f"stats:{name}.up.bias")
         ops.conv([dZ1], B, h, w, P[key], c, P[key + ".nt"], 9, out=dU, stats_partial=part)
         bias_from_stats(part, g, c, f"{name}.up.bias")
         wgrad_deconv(t[high], dU, h // 2, w // 2, f"{name}.up.weight")
@@ -358,7 +365,7 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
 
     # ---- decoder, deepest nesting first.  X03's only consumer is head 3: dZ2_03 = dXh2 (already masked)
     c0 = eng.filters[0]
-    ops.reduce_partials(t["head_red"], 1, 0, c0, G, out_offset=goff("up_concat03.conv.conv2.0.bias"), partial_offset=2 * ts.head_nacc + ncls * 17 + 1)
+    ops.reduce_partials(t["head_red"], 1, 0, c0, G, out_offset=goff("up_concat03.conv.conv2.0.bias"), partial_offset=2 * ts.head_nacc + ncls * 17 + 1, defer=True)
     decoder_node_backward("up_concat03", True)
 
     def x_node_decoder(node, dname, addend, extra_deconv_from=None):
@@ -374,11 +381,11 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
                 tmp = t["tmpX11"]
                 deconv_dgrad(extra_deconv_from, h, w, tmp, addend=addend)
                 add = tmp
-            g, part = stats_buf([c] * len(cons), c, P[key_for_stats + ".nt"], 9, h, w)
+            g, part = stats_buf([c] * len(cons), c, P[key_for_stats + ".nt"], 9, h, w, key=f"stats:{dname}.conv.conv2.0.bias")
             gather(node, h, w, out, add, t[node], dict(stats_partial=part))
         else:
             cin_up = t[f"dU{extra_deconv_from[-2:]}"].shape[-1]
-            g, part = stats_buf([cin_up] * 4, c, P[key_for_stats + ".nt"], 1, h, w)
+            g, part = stats_buf([cin_up] * 4, c, P[key_for_stats + ".nt"], 1, h, w, key=f"stats:{dname}.conv.conv2.0.bias")
             deconv_dgrad(extra_deconv_from, h, w, out, addend=addend, mask=t[node], stats=dict(stats_partial=part))
         bias_from_stats(part, g, c, f"{dname}.conv.conv2.0.bias")
         decoder_node_backward(dname, True)
@@ -419,8 +426,8 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
             deconv_dgrad(deconv_into[lvl], h, w, dyh2, addend=addend, mask=t[node], stats=dict(stats_partial=part, **aux2))
         # BatchNorm 2 backward: sums = (dbeta, dgamma); dz = gamma*istd*(dyh - s1/M - xhat*s2/M)
         ops.reduce_partials(part, g, 2 * c, 2 * c, t[bn2 + ".sums"])
-        ops.reduce_partials(t[bn2 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv2.1.bias"))
-        ops.reduce_partials(t[bn2 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv2.1.weight"), partial_offset=c)
+        ops.reduce_partials(t[bn2 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv2.1.bias"), defer=True)
+        ops.reduce_partials(t[bn2 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv2.1.weight"), partial_offset=c, defer=True)
         # {name}.conv2.0.bias: a bias in front of BatchNorm has an exactly zero gradient; G is zero-initialised and never written there
         dz2 = t[f"{name}.dz2"]
         ops.bn_bwd_apply(dyh2, t[f"{name}.z2"], t[bn2 + ".mean"], t[bn2 + ".istd"], seq2[1].weight, t[bn2 + ".sums"], count, dz2)
@@ -432,8 +439,8 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
         ops.conv([dz2], B, h, w, P[key], c, P[key + ".nt"], 9, out=dyh1, relu_mask_src=t[f"{name}.a"], stats_partial=part, stats_aux=t[f"{name}.z1"],
                  aux_mean=t[bn1 + ".mean"], aux_istd=t[bn1 + ".istd"])
         ops.reduce_partials(part, g, 2 * c, 2 * c, t[bn1 + ".sums"])
-        ops.reduce_partials(t[bn1 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv1.1.bias"))
-        ops.reduce_partials(t[bn1 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv1.1.weight"), partial_offset=c)
+        ops.reduce_partials(t[bn1 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv1.1.bias"), defer=True)
+        ops.reduce_partials(t[bn1 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv1.1.weight"), partial_offset=c, defer=True)
         dz1 = t[f"{name}.dz1"]
         ops.bn_bwd_apply(dyh1, t[f"{name}.z1"], t[bn1 + ".mean"], t[bn1 + ".istd"], seq1[1].weight, t[bn1 + ".sums"], count, dz1)
         if lvl == 0:
@@ -445,6 +452,7 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
             cprev = eng.filters[lvl - 1]
             ops.conv([dz1], B, h, w, P[key], cprev, P[key + ".nt"], 9, out=t[f"dP{lvl - 1}0"])
             ops.maxpool_bwd(t[f"X{lvl - 1}0"], t[f"dP{lvl - 1}0"], t[f"dpool{lvl - 1}"])
+    ops.flush_reduce_queue(ts.__dict__.setdefault("_reduce_tables", {}), eng.device)
 
 
 # ---------------------------------------------------------------------------------------------- autograd boundary
