@@ -173,7 +173,7 @@ int unpp_wgrad_reduce(const float* partial, int nparts, int taps, int cin_total,
  * result is only needed by the optimizer): job j writes
  *   dst[co*s_co + ci*s_ci + tap*s_tap] = scale * sum_p partial[p*stride + (tap*cin_total + ci_begin + ci)*cout + co]
  * for tap < taps, ci < ci_count, co < cout, with the same fixed summation order as the single-job kernels.
- * `table` is a DEVICE array of njobs jobs; block_end = exclusive running total of ceil(outputs/32) blocks. */
+ * `table` is a DEVICE array of njobs jobs; block_end = exclusive running total of ceil(outputs/128) blocks. */
 typedef struct UnppReduceJob {
   const float* partial;
   float* dst;

@@ -17,7 +17,7 @@ def run(cins, cout, H, N=32, reps=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps, g
 print("UNPP_WGRAD_LEGACY =", os.environ.get("UNPP_WGRAD_LEGACY"))
-for cins, cout, H in (([128], 128, 32), ([64, 64], 64, 64), ([16], 16, 256), ([16] * 2, 16, 256), ([16] * 3, 16, 256), ([16] * 5, 16, 256), ([16], 32, 128),
+for cins, cout, H in (([128], 128, 32), ([64], 128, 32), ([64, 64], 64, 64), ([64], 64, 64), ([32], 64, 64), ([16], 16, 256), ([16] * 2, 16, 256), ([16] * 3, 16, 256), ([16] * 5, 16, 256), ([16], 32, 128),
                       ([32], 32, 128), ([32] * 2, 32, 128), ([32] * 3, 32, 128)):
     ms, g = run(cins, cout, H)
     px = 32 * H * H

@@ -176,6 +176,12 @@ def test_argmax_bit_exact(golden):
     (2, 24, 56, [32, 32, 32], 32),
     (1, 16, 32, [32, 16], 16),
     (5, 128, 128, [16, 16, 16, 16], 16),
+    # wide layers: (<= 64-channel chunk, <= 64-channel output slice) jobs, two MMAs per K step for 64-channel chunks
+    (1, 24, 40, [32], 64),
+    (2, 16, 48, [64, 128], 64),
+    (3, 32, 32, [128], 128),
+    (2, 16, 16, [64], 32),
+    (32, 32, 32, [128], 128),
 ])
 def test_wgrad_conv3x3(N, H, W, cins, cout):
     cin = sum(cins)

@@ -79,19 +79,46 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
-// All deferred reductions of a training step in one launch: block b owns 32 outputs of the job whose
-// block range contains b (the table is small: a linear scan of the running totals).
+// All deferred reductions of a training step in one launch: block b owns 128 consecutive outputs (32 lanes x float4
+// along co; jobs whose partials are not 16-byte aligned fall back to 32 scalar outputs per block pass) of the job
+// whose block range contains b (the table is small: a linear scan of the running totals).  The eight warps sum
+// interleaved slices of the partials, the slice sums are added in a fixed order: deterministic.
 __global__ void __launch_bounds__(256) reduce_batched_kernel(const UnppReduceJob* __restrict__ table, int njobs) {
+  __shared__ float4 red4[8][32];
   int j = 0;
   while (j < njobs - 1 && int(blockIdx.x) >= __ldg(&table[j].block_end)) ++j;
   const UnppReduceJob job = table[j];
   const int first = j ? __ldg(&table[j - 1].block_end) : 0;
   const int n = job.taps * job.ci_count * job.cout;
-  const int i = (int(blockIdx.x) - first) * 32 + (threadIdx.x & 31);
-  const int co = i % job.cout, ci = (i / job.cout) % job.ci_count, tap = i / (job.cout * job.ci_count);
-  const float* q = job.partial + (long(tap) * job.cin_total + job.ci_begin + ci) * job.cout + co;
-  const float t = sliced_sum(job.nparts, [&](int p) { return i < n ? __ldg(q + p * job.stride) : 0.f; });
-  if (threadIdx.x < 32 && i < n) job.dst[co * job.s_co + ci * job.s_ci + tap * job.s_tap] = t * job.scale;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const bool vec = !(job.cout & 3) && !(job.stride & 3) && !(reinterpret_cast<uintptr_t>(job.partial) & 15);
+  for (int sub = 0; sub < (vec ? 1 : 4); ++sub) {
+    const int i = (int(blockIdx.x) - first) * 128 + (vec ? l * 4 : sub * 32 + l);
+    const int co = i % job.cout, ci = (i / job.cout) % job.ci_count, tap = i / (job.cout * job.ci_count);
+    const float* q = job.partial + (long(tap) * job.cin_total + job.ci_begin + ci) * job.cout + co;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) {
+      if (vec) {
+        for (int p = w; p < job.nparts; p += 8) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(q + p * job.stride));
+          s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+        }
+      } else {
+        for (int p = w; p < job.nparts; p += 8) s.x += __ldg(q + p * job.stride);
+      }
+    }
+    red4[w][l] = s;
+    __syncthreads();
+    if (w == 0 && i < n) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t.x += red4[k][l].x, t.y += red4[k][l].y, t.z += red4[k][l].z, t.w += red4[k][l].w;
+      float* d = job.dst + co * job.s_co + ci * job.s_ci + tap * job.s_tap;
+      d[0] = t.x * job.scale;
+      if (vec) d[job.s_co] = t.y * job.scale, d[2 * job.s_co] = t.z * job.scale, d[3 * job.s_co] = t.w * job.scale;
+    }
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------------------------------

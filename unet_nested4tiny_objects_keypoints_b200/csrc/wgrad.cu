@@ -272,19 +272,23 @@ int launch(const WgradParams& p, const Plan& pl, cudaStream_t stream) {
 }  // namespace
 
 extern "C" int unpp_wgrad_grid(const UnppWgradArgs* a) {
+  if (a && a->nsrc >= 1 && a->nsrc <= UNPP_MAX_SRC && a->N >= 1 && a->H >= 1 && a->W >= 1 && unpp::wgrad_tc_eligible(a)) return unpp::wgrad_tc_grid(a);
   Plan pl;
   int rc = make_plan(a, &pl);
-  if (!rc && unpp::wgrad_tc_eligible(a)) return unpp::wgrad_tc_grid(a);
   return rc ? rc : pl.grid_x;
 }
 
 extern "C" int unpp_wgrad(const UnppWgradArgs* a, unpp_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  Plan pl;
-  if (int rc = make_plan(a, &pl)) return rc;
+  if (!a || a->nsrc < 1 || a->nsrc > UNPP_MAX_SRC) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: nsrc out of range");
+  if (a->N < 1 || a->H < 1 || a->W < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: empty pixel grid");
   if (!a->dz || !a->partial) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: dz / partial is null");
   if ((reinterpret_cast<uintptr_t>(a->dz) & 15)) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: dz pointer unaligned");
-  if (unpp::wgrad_tc_eligible(a)) return unpp::wgrad_tc_launch(a, stream);  // tcgen05 path (16/32-channel levels)
+  for (int i = 0; i < a->nsrc; ++i)
+    if (!a->src[i] || (reinterpret_cast<uintptr_t>(a->src[i]) & 15)) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: source pointer null or unaligned");
+  if (unpp::wgrad_tc_eligible(a)) return unpp::wgrad_tc_launch(a, stream);  // tcgen05 path (every dense 3x3 shape of the network)
+  Plan pl;
+  if (int rc = make_plan(a, &pl)) return rc;
   EncodeTiledFn enc = get_encode();
   if (!enc) return unpp::fail(UNPP_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled not available from the driver");
   WgradParams p;

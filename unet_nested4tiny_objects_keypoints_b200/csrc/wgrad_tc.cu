@@ -32,6 +32,12 @@
 // sum of exactly two accumulator entries, which the read-out writes to two partial "slots" (the grid
 // query reports 2 partials per CTA), so the fixed-order reduction stays as it is.
 //
+// Wide layers (a source or the output 64 / 128 channels wide): sources are cut into <= 64-channel chunks and
+// the output into <= 64-channel slices; blockIdx.y enumerates the (chunk, slice) jobs, each CTA accumulating one
+// of them over its share of the tiles (8-row tiles there: a 64-channel tile row is 128 B per pixel).  A
+// 64-channel chunk has only two atoms in M = 128, so it takes two MMAs per K step: start shifts 0 (filter
+// columns 0, 1) and +2 pixels (column 2).
+//
 // Shared-memory operand traffic per MMA: 4 KB (A) + 96 * Cout B (B) for 16 K rows, i.e. 224 B per
 // pixel and 16-channel source in the pair view (352 B without it) against 64 B of HBM traffic.
 #include <cstdlib>
@@ -47,17 +53,19 @@ constexpr int TW = 32, PX = TW + 2;  // K rows (pixels or pixel pairs) per tile 
 constexpr int kIssuers = 4;
 constexpr int kThreads = 256;  // warp 0: TMA producer, warps 1..4: MMA issuers, all eight: final TMEM read-out
 constexpr int kMaxX = 8, kMaxZ = 4;
+constexpr int kMaxChunks = 2 * UNPP_MAX_SRC, kMaxJobs = 16;
 
 struct Params {
   CUtensorMap xmap[UNPP_MAX_SRC];
   CUtensorMap zmap;
-  int nsrc;
-  int src_C[UNPP_MAX_SRC], cioff[UNPP_MAX_SRC];
+  // K chunks (<= 64 channels of one source) and jobs (a run of chunks x one output slice); blockIdx.y = job
+  int ch_map[kMaxChunks], ch_c0[kMaxChunks], ch_C[kMaxChunks], ch_cioff[kMaxChunks];  // ch_C: EFFECTIVE atom width (32 in the pair view)
+  int job_ch0[kMaxJobs], job_nch[kMaxJobs], job_co0[kMaxJobs];
   int tiles_x, tiles_y, ntiles;
-  int cin_total, cout;
+  int cin_total, cout;       // real widths of the partial [9][cin_total][cout]
   int TR;                    // tile rows
-  int pair;                  // pixel-pair view: src_C / zspan below are the EFFECTIVE widths (32), cout the real one (16)
-  int zspan;                 // bytes per K row of the dZ tile
+  int pair;                  // pixel-pair view
+  int zspan;                 // bytes per K row of the dZ tile (= effective slice width * 2)
   int xslot, zslot, nx, nz;  // ring geometry: bytes per slot, slots
   int nsplit, ncols, tmem_cols;
   float* partial;
@@ -72,13 +80,15 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   uint8_t* const zring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* const xring = zring + p.nz * p.zslot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int job = blockIdx.y;
+  const int ch0 = p.job_ch0[job], nch = p.job_nch[job], co0 = p.job_co0[job];
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxX; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], kIssuers);
     for (int i = 0; i < kMaxZ; ++i) mbar_init(&z_full[i], 1), mbar_init(&z_empty[i], kIssuers);
     mbar_init(&bar_done, kIssuers);
     fence_mbar_init();
-    for (int u = 0; u < p.nsrc; ++u) tma_prefetch_desc(&p.xmap[u]);
+    for (int k = 0; k < nch; ++k) tma_prefetch_desc(&p.xmap[p.ch_map[ch0 + k]]);
     tma_prefetch_desc(&p.zmap);
   }
   if (warp == 1) {
@@ -89,7 +99,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  const int nsrc = p.nsrc, ntiles = p.ntiles, nx = p.nx, nz = p.nz, nsplit = p.nsplit, ncols = p.ncols;
+  const int ntiles = p.ntiles, nx = p.nx, nz = p.nz, nsplit = p.nsplit, ncols = p.ncols;
   const int zspan = p.zspan, TR = p.TR;
 
   if (warp == 0) {
@@ -102,27 +112,28 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
           const int s = zi % nz;
           mbar_wait(&z_empty[s], ((zi / nz) & 1) ^ 1);
           mbar_arrive_expect_tx(&z_full[s], uint32_t((TR + 2) * TW * zspan));
-          tma_load_4d(&p.zmap, &z_full[s], zring + size_t(s) * p.zslot, 0, tx * TW, ty * TR - 1, n);
+          tma_load_4d(&p.zmap, &z_full[s], zring + size_t(s) * p.zslot, p.pair ? 0 : co0, tx * TW, ty * TR - 1, n);
           ++zi;
         }
-        for (int u = 0; u < nsrc; ++u, ++xi) {
-          const int s = xi % nx;
+        for (int k = 0; k < nch; ++k, ++xi) {
+          const int s = xi % nx, c = ch0 + k;
           mbar_wait(&x_empty[s], ((xi / nx) & 1) ^ 1);
-          mbar_arrive_expect_tx(&x_full[s], uint32_t(TR * PX * p.src_C[u] * 2));
-          tma_load_4d(&p.xmap[u], &x_full[s], xring + size_t(s) * p.xslot, 0, tx * TW - 1, ty * TR, n);
+          mbar_arrive_expect_tx(&x_full[s], uint32_t(TR * PX * p.ch_C[c] * 2));
+          tma_load_4d(&p.xmap[p.ch_map[c]], &x_full[s], xring + size_t(s) * p.xslot, p.ch_c0[c], tx * TW - 1, ty * TR, n);
         }
       }
     }
   } else if (warp <= kIssuers) {
     // ------------------------------------------------------------------ MMA issuers
-    // Accumulator a = u * nsplit + h (source u, rows h, h + nsplit, ... of every tile) belongs to issuer a % kIssuers.
+    // Accumulator a = (acc0(chunk) + mi) * nsplit + h (chunk, MMA of the K step, rows h, h + nsplit, ... of every tile)
+    // belongs to issuer a % kIssuers.
     const int w = warp - 1;
     const uint32_t idesc = make_idesc_bf16(128, ncols, 1, 1);
     const uint32_t zring_a = smem_u32(zring), xring_a = smem_u32(xring);
     const uint32_t zslot = uint32_t(p.zslot), xslot = uint32_t(p.xslot);
-    int spans[UNPP_MAX_SRC];
+    int spans[kMaxChunks];
 #pragma unroll
-    for (int u = 0; u < UNPP_MAX_SRC; ++u) spans[u] = p.src_C[u] * 2;
+    for (int k = 0; k < kMaxChunks; ++k) spans[k] = ch0 + k < kMaxChunks ? p.ch_C[ch0 + k] * 2 : 0;
     const uint32_t z_row = uint32_t(TW * zspan) >> 4, z_seg = uint32_t(16 * zspan) >> 4;
     int xi = 0, zi = 0, tile_it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it, ++zi) {
@@ -130,35 +141,41 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       mbar_wait(&z_full[zs], (zi / nz) & 1);
       const uint64_t bd = make_sdesc(zring_a + uint32_t(zs) * zslot, uint32_t(TW * zspan), uint32_t(8 * zspan), layout_of_span(zspan));
       const uint32_t b_hi = uint32_t(bd >> 32), b_lo = uint32_t(bd);
+      int acc0 = 0;
 #pragma unroll 1
-      for (int u = 0; u < nsrc; ++u, ++xi) {
+      for (int k = 0; k < nch; ++k, ++xi) {
         const int xs = xi % nx;
         int span = spans[0];
 #pragma unroll
-        for (int k = 1; k < UNPP_MAX_SRC; ++k)
-          if (k == u) span = spans[k];
+        for (int kk = 1; kk < kMaxChunks; ++kk)
+          if (kk == k) span = spans[kk];
+        const int nm = span == 128 ? 2 : 1;  // 64-channel chunk: two atoms per MMA, two MMAs per K step
         mbar_wait(&x_full[xs], (xi / nx) & 1);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t ad = make_sdesc(xring_a + uint32_t(xs) * xslot, uint32_t(span), uint32_t(8 * span), layout_of_span(span));
           const uint32_t a_hi = uint32_t(ad >> 32), a_lo = uint32_t(ad);
           const uint32_t x_row = uint32_t(PX * span) >> 4, x_seg = uint32_t(16 * span) >> 4;
-          for (int h = 0; h < nsplit; ++h) {
-            const int a = u * nsplit + h;
-            if (a % kIssuers != w) continue;
-            const uint32_t acc = tmem_base + uint32_t(a * ncols);
-            uint32_t accum = tile_it ? 1u : 0u;
-            for (int row = h; row < TR; row += nsplit) {
-              const uint32_t ar = a_lo + uint32_t(row) * x_row, br = b_lo + uint32_t(row) * z_row;
+          for (int mi = 0; mi < nm; ++mi) {
+            for (int h = 0; h < nsplit; ++h) {
+              const int a = (acc0 + mi) * nsplit + h;
+              if (a % kIssuers != w) continue;
+              const uint32_t acc = tmem_base + uint32_t(a * ncols);
+              const uint32_t a_mi = a_lo + (uint32_t(mi * 2 * span) >> 4);  // second MMA: the row shifted by two more pixels
+              uint32_t accum = tile_it ? 1u : 0u;
+              for (int row = h; row < TR; row += nsplit) {
+                const uint32_t ar = a_mi + uint32_t(row) * x_row, br = b_lo + uint32_t(row) * z_row;
 #pragma unroll
-              for (int seg = 0; seg < TW / 16; ++seg) {
-                umma_bf16(acc, (uint64_t(a_hi) << 32) | (ar + uint32_t(seg) * x_seg), (uint64_t(b_hi) << 32) | (br + uint32_t(seg) * z_seg), idesc,
-                          accum);
-                accum = 1u;
+                for (int seg = 0; seg < TW / 16; ++seg) {
+                  umma_bf16(acc, (uint64_t(a_hi) << 32) | (ar + uint32_t(seg) * x_seg), (uint64_t(b_hi) << 32) | (br + uint32_t(seg) * z_seg), idesc,
+                            accum);
+                  accum = 1u;
+                }
               }
             }
           }
         }
+        acc0 += nm;
         __syncwarp();
         if (elect_one()) umma_commit(&x_empty[xs]);
         __syncwarp();
@@ -179,40 +196,49 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     const int m = q * 32 + lane;
     const int ngroups = ncols >> 4;
     const int cout = p.cout, pair = p.pair;
+    const int ecout = zspan >> 1;  // effective slice width
     const size_t part_elems = size_t(9) * p.cin_total * cout;
     float* const part = p.partial + size_t(blockIdx.x) * (pair ? 2 : 1) * part_elems;
-    for (int u = 0; u < nsrc; ++u) {
-      const int C = p.src_C[u];  // effective width of an atom
-      if (q * 32 >= 3 * C) continue;  // warp-uniform: this lane quadrant only holds discarded shifts
-      const int j = m / C;
-      const int e = pair ? ((m >> 4) & 1) : 0, ci = pair ? (m & 15) : m % C;
-      for (int g = half; g < ngroups; g += 2) {
-        float v[16];
+    int acc0 = 0;
+    for (int k = 0; k < nch; ++k) {
+      const int c = ch0 + k;
+      const int C = p.ch_C[c];  // effective width of an atom
+      const int nm = C == 64 ? 2 : 1;
+      for (int mi = 0; mi < nm; ++mi) {
+        const int a0 = (acc0 + mi) * nsplit;
+        const int j = m / C + 2 * mi;   // filter column (pair view: pair shift)
+        const int lanes_used = nm == 2 ? (mi ? 64 : 128) : 3 * C;
+        if (q * 32 >= lanes_used) continue;  // warp-uniform: this lane quadrant only holds discarded shifts
+        const int e = pair ? ((m >> 4) & 1) : 0, ci = pair ? (m & 15) : m % C;
+        for (int g = half; g < ngroups; g += 2) {
+          float v[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = 0.f;
-        for (int h = 0; h < nsplit; ++h) {  // fixed order: deterministic
-          uint32_t raw[16];
-          tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t((u * nsplit + h) * ncols + g * 16), raw);
-          tmem_ld_wait16(raw);
+          for (int t = 0; t < 16; ++t) v[t] = 0.f;
+          for (int h = 0; h < nsplit; ++h) {  // fixed order: deterministic
+            uint32_t raw[16];
+            tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t((a0 + h) * ncols + g * 16), raw);
+            tmem_ld_wait16(raw);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] += __uint_as_float(raw[k]);
-        }
-        int i, co0, sft, slot = 0;
-        if (pair) {  // column group = (dZ row shift i, parity e'); tap column = e - e' + 2j - 1
-          i = g >> 1;
-          co0 = 0;
-          sft = e - (g & 1) + 2 * j - 1;
-          slot = sft == 1 ? e : 1 - e;
-        } else {
-          i = (g * 16) / cout, co0 = (g * 16) % cout, sft = j;
-        }
-        if (j < 3 && sft >= 0 && sft < 3) {
-          const int tap = (2 - i) * 3 + sft;
-          float4* dst = reinterpret_cast<float4*>(part + slot * part_elems + (size_t(tap) * p.cin_total + p.cioff[u] + ci) * cout + co0);
+            for (int t = 0; t < 16; ++t) v[t] += __uint_as_float(raw[t]);
+          }
+          int i, col0, sft, slot = 0;
+          if (pair) {  // column group = (dZ row shift i, parity e'); tap column = e - e' + 2j - 1
+            i = g >> 1;
+            col0 = 0;
+            sft = e - (g & 1) + 2 * j - 1;
+            slot = sft == 1 ? e : 1 - e;
+          } else {
+            i = (g * 16) / ecout, col0 = (g * 16) % ecout, sft = j;
+          }
+          if (j < 3 && sft >= 0 && sft < 3) {
+            const int tap = (2 - i) * 3 + sft;
+            float4* dst = reinterpret_cast<float4*>(part + slot * part_elems + (size_t(tap) * p.cin_total + p.ch_cioff[c] + ci) * cout + co0 + col0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            for (int t = 0; t < 4; ++t) dst[t] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+          }
         }
       }
+      acc0 += nm;
     }
   }
   tc_fence_before();
@@ -235,47 +261,84 @@ EncodeTiledFn get_encode() {
 }
 
 struct Plan {
-  int cin_total, max_C, xslot, zslot, nx, nz, nsplit, ncols, tmem_cols, smem_total, tiles_x, tiles_y, ntiles, grid_x;
-  int TR, pair, ecout, We;  // tile rows; pixel-pair view: effective output width, K rows per image row
-  int cioff[UNPP_MAX_SRC], eC[UNPP_MAX_SRC];
+  bool ok;
+  int cin_total, xslot, zslot, nx, nz, nsplit, ncols, tmem_cols, smem_total, tiles_x, tiles_y, ntiles, grid_x;
+  int TR, pair, ecout, We;  // tile rows; pixel-pair view; effective output slice width; K rows per image row
+  int nchunks, njobs;
+  int box_C[UNPP_MAX_SRC];  // channels per TMA box of each source (effective)
+  int ch_map[kMaxChunks], ch_c0[kMaxChunks], ch_C[kMaxChunks], ch_cioff[kMaxChunks];
+  int job_ch0[kMaxJobs], job_nch[kMaxJobs], job_co0[kMaxJobs];
 };
 
+CUtensorMapSwizzle swizzle_of(int channels) { return channels == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : channels == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B; }
+
 void make_plan(const UnppWgradArgs* a, Plan* pl) {
-  int off = 0, maxc = 0;
-  pl->pair = (a->cout == 16 && !(a->W & 1) && a->nsrc * 96 <= 512) ? 1 : 0;
-  for (int i = 0; i < a->nsrc; ++i)
-    if (a->src_C[i] != 16) pl->pair = 0;
-  pl->ecout = pl->pair ? 32 : a->cout, pl->We = pl->pair ? a->W / 2 : a->W;
+  pl->ok = false;
+  if (a->taps != 9 || a->dz_step != 1) return;
+  if (a->cout != 16 && a->cout != 32 && a->cout != 64 && a->cout != 128) return;
+  bool all16 = a->cout == 16, wide = a->cout > 32;
   for (int i = 0; i < a->nsrc; ++i) {
-    pl->cioff[i] = off;
-    off += a->src_C[i];
-    pl->eC[i] = pl->pair ? 32 : a->src_C[i];
-    if (pl->eC[i] > maxc) maxc = pl->eC[i];
+    const int C = a->src_C[i];
+    if (C != 16 && C != 32 && C != 64 && C != 128) return;
+    all16 = all16 && C == 16;
+    wide = wide || C > 32;
   }
-  pl->cin_total = off, pl->max_C = maxc;
+  pl->pair = (all16 && !(a->W & 1) && a->nsrc * 96 <= 512) ? 1 : 0;
+  pl->ecout = pl->pair ? 32 : (a->cout > 64 ? 64 : a->cout);
+  pl->We = pl->pair ? a->W / 2 : a->W;
   pl->ncols = 3 * pl->ecout;
-  int TR = 16;
-  {
-    const char* e = getenv("UNPP_WGRAD_TR");
-    if (e && atoi(e) == 8) TR = 8;
+  // chunks
+  int off = 0, nchunks = 0, maxc = 0;
+  for (int i = 0; i < a->nsrc; ++i) {
+    const int C = a->src_C[i];
+    pl->box_C[i] = pl->pair ? 32 : (C > 64 ? 64 : C);
+    for (int c0 = 0; c0 < C; c0 += 64) {
+      if (nchunks >= kMaxChunks) return;
+      pl->ch_map[nchunks] = i, pl->ch_c0[nchunks] = c0, pl->ch_C[nchunks] = pl->box_C[i], pl->ch_cioff[nchunks] = off + c0;
+      if (pl->box_C[i] > maxc) maxc = pl->box_C[i];
+      ++nchunks;
+    }
+    off += C;
   }
-  pl->TR = TR;
-  int ns = 512 / (a->nsrc * pl->ncols);
+  pl->cin_total = off, pl->nchunks = nchunks;
+  // jobs: narrow layers = one job with every chunk; wide layers = one job per (chunk, output slice)
+  int njobs = 0, max_acc = 0;
+  if (!wide) {
+    pl->job_ch0[0] = 0, pl->job_nch[0] = nchunks, pl->job_co0[0] = 0;
+    njobs = 1, max_acc = nchunks;
+  } else {
+    for (int c = 0; c < nchunks; ++c)
+      for (int co0 = 0; co0 < a->cout; co0 += 64) {
+        if (njobs >= kMaxJobs) return;
+        pl->job_ch0[njobs] = c, pl->job_nch[njobs] = 1, pl->job_co0[njobs] = co0;
+        ++njobs;
+        const int nm = pl->ch_C[c] == 64 ? 2 : 1;
+        if (nm > max_acc) max_acc = nm;
+      }
+  }
+  pl->njobs = njobs;
+  if (max_acc * pl->ncols > 512) return;
+  int ns = 512 / (max_acc * pl->ncols);
   pl->nsplit = ns > kIssuers ? kIssuers : ns;
-  int need = a->nsrc * pl->nsplit * pl->ncols, tc = 32;
+  int need = max_acc * pl->nsplit * pl->ncols, tc = 32;
   while (tc < need) tc <<= 1;
   pl->tmem_cols = tc;
+  const int TR = (maxc == 64 || pl->ecout == 64) ? 8 : 16;
+  pl->TR = TR;
   pl->xslot = (TR * PX * maxc * 2 + 1023) / 1024 * 1024;
   pl->zslot = ((TR + 2) * TW * pl->ecout * 2 + 1023) / 1024 * 1024;
   const int budget = 212 * 1024;
-  pl->nz = (pl->ecout == 16 || TR == 8) ? 3 : 2;
+  pl->nz = pl->zslot <= 20 * 1024 ? 3 : 2;
   pl->nx = (budget - pl->nz * pl->zslot) / pl->xslot;
   if (pl->nx > kMaxX) pl->nx = kMaxX;
+  if (pl->nx < 2) return;
   pl->smem_total = 1024 + pl->nz * pl->zslot + pl->nx * pl->xslot + 1024;  // tail: the discarded shifts of the last row read past the slot
   pl->tiles_x = (pl->We + TW - 1) / TW, pl->tiles_y = (a->H + TR - 1) / TR;
   pl->ntiles = pl->tiles_x * pl->tiles_y * a->N;
-  const int sms = unpp::num_sms();
-  pl->grid_x = pl->ntiles < sms ? pl->ntiles : sms;
+  int gx = unpp::num_sms() / njobs;
+  if (gx < 1) gx = 1;
+  pl->grid_x = pl->ntiles < gx ? pl->ntiles : gx;
+  pl->ok = true;
 }
 
 }  // namespace
@@ -283,17 +346,15 @@ void make_plan(const UnppWgradArgs* a, Plan* pl) {
 namespace unpp {
 
 bool wgrad_tc_eligible(const UnppWgradArgs* a) {
-  if (a->taps != 9 || a->dz_step != 1) return false;
-  if (a->cout != 16 && a->cout != 32) return false;
-  for (int i = 0; i < a->nsrc; ++i)
-    if (a->src_C[i] != 16 && a->src_C[i] != 32) return false;
-  if (a->nsrc * 3 * a->cout > 512) return false;
   static int legacy = -1;  // UNPP_WGRAD_LEGACY=1 forces the mma.sync kernel (A/B measurements); read once
   if (legacy < 0) {
     const char* e = getenv("UNPP_WGRAD_LEGACY");
     legacy = (e && e[0] == '1') ? 1 : 0;
   }
-  return !legacy;
+  if (legacy) return false;
+  Plan pl;
+  make_plan(a, &pl);
+  return pl.ok;
 }
 
 int wgrad_tc_grid(const UnppWgradArgs* a) {
@@ -305,32 +366,32 @@ int wgrad_tc_grid(const UnppWgradArgs* a) {
 int wgrad_tc_launch(const UnppWgradArgs* a, cudaStream_t stream) {
   Plan pl;
   make_plan(a, &pl);
-  if (pl.nx < 2) return unpp::fail(UNPP_ERR_UNSUPPORTED, "wgrad_tc: tiles do not fit twice in shared memory");
+  if (!pl.ok) return unpp::fail(UNPP_ERR_UNSUPPORTED, "wgrad_tc: shape not supported by the tcgen05 path");
   EncodeTiledFn enc = get_encode();
   if (!enc) return unpp::fail(UNPP_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled not available from the driver");
   Params p;
   memset(&p, 0, sizeof p);
   cuuint32_t es[4] = {1, 1, 1, 1};
   for (int i = 0; i < a->nsrc; ++i) {
-    const cuuint64_t C = pl.eC[i];
+    const cuuint64_t C = pl.pair ? 32 : a->src_C[i];  // channels per K row of the tensor as TMA sees it
     cuuint64_t gd[4] = {C, cuuint64_t(pl.We), cuuint64_t(a->H), cuuint64_t(a->N)};
     cuuint64_t gs[3] = {C * 2, cuuint64_t(pl.We) * C * 2, cuuint64_t(a->H) * pl.We * C * 2};
-    cuuint32_t box[4] = {cuuint32_t(C), cuuint32_t(PX), cuuint32_t(pl.TR), 1};
+    cuuint32_t box[4] = {cuuint32_t(pl.box_C[i]), cuuint32_t(PX), cuuint32_t(pl.TR), 1};
     CUresult r = enc(&p.xmap[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->src[i]), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     swizzle_of(pl.box_C[i]), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled failed (CUresult %d) for source %d", int(r), i);
-    p.src_C[i] = pl.eC[i], p.cioff[i] = pl.cioff[i];
   }
   {
-    const cuuint64_t C = pl.ecout;
+    const cuuint64_t C = pl.pair ? 32 : a->cout;
     cuuint64_t gd[4] = {C, cuuint64_t(pl.We), cuuint64_t(a->H), cuuint64_t(a->N)};
     cuuint64_t gs[3] = {C * 2, cuuint64_t(pl.We) * C * 2, cuuint64_t(a->H) * pl.We * C * 2};
-    cuuint32_t box[4] = {cuuint32_t(C), cuuint32_t(TW), cuuint32_t(pl.TR + 2), 1};
+    cuuint32_t box[4] = {cuuint32_t(pl.ecout), cuuint32_t(TW), cuuint32_t(pl.TR + 2), 1};
     CUresult r = enc(&p.zmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->dz), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     swizzle_of(pl.ecout), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled failed (CUresult %d) for dZ", int(r));
   }
-  p.nsrc = a->nsrc;
+  for (int c = 0; c < pl.nchunks; ++c) p.ch_map[c] = pl.ch_map[c], p.ch_c0[c] = pl.ch_c0[c], p.ch_C[c] = pl.ch_C[c], p.ch_cioff[c] = pl.ch_cioff[c];
+  for (int j = 0; j < pl.njobs; ++j) p.job_ch0[j] = pl.job_ch0[j], p.job_nch[j] = pl.job_nch[j], p.job_co0[j] = pl.job_co0[j];
   p.tiles_x = pl.tiles_x, p.tiles_y = pl.tiles_y, p.ntiles = pl.ntiles;
   p.cin_total = pl.cin_total, p.cout = a->cout;
   p.pair = pl.pair, p.zspan = pl.ecout * 2, p.TR = pl.TR;
@@ -343,7 +404,7 @@ int wgrad_tc_launch(const UnppWgradArgs* a, cudaStream_t stream) {
       return unpp::fail_cuda("wgrad_tc: cudaFuncSetAttribute");
     opted_in = true;
   }
-  wgrad_tc_kernel<<<pl.grid_x, kThreads, pl.smem_total, stream>>>(p);
+  wgrad_tc_kernel<<<dim3(pl.grid_x, pl.njobs), kThreads, pl.smem_total, stream>>>(p);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("wgrad_tc: launch");
   return UNPP_OK;
 }

@@ -283,7 +283,7 @@ def flush_reduce_queue(cache: dict, device) -> None:
         return
     blocks = 0
     for j, _ in jobs:
-        blocks += (j.taps * j.ci_count * j.cout + 31) // 32
+        blocks += (j.taps * j.ci_count * j.cout + 127) // 128
         j.block_end = blocks
     raw = b"".join(bytes(j) for j, _ in jobs)
     table = cache.get(raw)
