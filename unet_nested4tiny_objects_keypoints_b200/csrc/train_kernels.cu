@@ -280,21 +280,29 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dyh, const uint4* 
 // FOCAL is a compile-time switch: the powf/logf path costs registers and instructions the MSE / upstream path must not pay.
 template <int NCLS, bool FOCAL>
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ heat, const float* __restrict__ dheat, const float* __restrict__ target,
-                                                       float gamma, float coef, const uint4* __restrict__ x, const uint4* __restrict__ mask, float drop_scale,
-                                                       const float* __restrict__ head_w, uint4* __restrict__ dx, float* __restrict__ partial,
+                                                       float gamma, float coef, const uint2* __restrict__ x, const uint32_t* __restrict__ mask, float drop_scale,
+                                                       const float* __restrict__ head_w, uint2* __restrict__ dx, float* __restrict__ partial,
                                                        int N, long HW) {
+  // Four threads per pixel, each owning four of the 16 channels (8 B of x / dx, 4 B of the keep-mask): 25 accumulators
+  // per thread instead of 85, so three blocks per SM are resident and enough loads are in flight to stream at HBM speed.
+  // The four lanes of a pixel read the same heat / target words (one broadcast transaction).
   constexpr int NACC = NCLS * 16 + NCLS + 1 + 16, LOSS = NCLS * 16 + NCLS;
-  float acc[NACC];
+  const int sub = threadIdx.x & 3;
+  const float lead = sub == 0 ? 1.f : 0.f;  // per-pixel sums (bias gradient, loss) are counted by one lane of the four
+  float accw[NCLS][4], accb[NCLS], accx[4], accl = 0.f, w[NCLS][4];
 #pragma unroll
-  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
-  float w[NCLS][16];
+  for (int c = 0; c < NCLS; ++c) {
+    accb[c] = 0.f;
 #pragma unroll
-  for (int c = 0; c < NCLS; ++c)
+    for (int k = 0; k < 4; ++k) accw[c][k] = 0.f, w[c][k] = __ldg(head_w + c * 16 + 4 * sub + k);
+  }
 #pragma unroll
-    for (int k = 0; k < 16; ++k) w[c][k] = __ldg(head_w + c * 16 + k);
+  for (int k = 0; k < 4; ++k) accx[k] = 0.f;
   const long total = long(N) * HW;
-  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+  for (long i = blockIdx.x * 64L + (threadIdx.x >> 2); i < total; i += long(gridDim.x) * 64L) {
     const long n = i / HW, p = i % HW;
+    const uint2 xr = __ldg(x + 4 * i + sub);
+    const uint32_t mw = mask ? __ldg(mask + 4 * i + sub) : 0x01010101u;
     float dl[NCLS];
 #pragma unroll
     for (int c = 0; c < NCLS; ++c) {
@@ -304,58 +312,65 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       if (target) {
         const float d = pr - __ldg(target + o);
         if constexpr (!FOCAL) {  // MSE: loss += d^2, d loss / d p = coef * d
-          acc[LOSS] += d * d;
+          accl = fmaf(lead * d, d, accl);
           dh = coef * d;
         } else {  // FocalLoss_BCE_2d (tools/losses/focal_loss.py:264-301): a = |p-t|, e = 1-a+1e-20, loss += -a^gamma * log(e)
           const float a = fabsf(d), e = 1.f - a + 1e-20f;
           // gamma = 3 (the trainer's setting, trainer.py:426) needs no pow; log through the fast intrinsic (rel. error ~1e-6)
           const float le = __logf(e), pg1 = gamma == 3.f ? a * a : (a > 0.f ? __powf(a, gamma - 1.f) : 0.f);
-          acc[LOSS] += -(pg1 * a) * le;
+          accl += lead * (-(pg1 * a) * le);
           dh = coef * copysignf(-gamma * pg1 * le + (pg1 * a) / e, d);
         }
       } else {
         dh = __ldg(dheat + o);
       }
       dl[c] = dh * pr * (1.f - pr);
-      acc[NCLS * 16 + c] += dl[c];
+      accb[c] = fmaf(lead, dl[c], accb[c]);
     }
-    float xv[16], keep[16];
-    unpack8(__ldg(x + 2 * i), *reinterpret_cast<float(*)[8]>(xv));
-    unpack8(__ldg(x + 2 * i + 1), *reinterpret_cast<float(*)[8]>(xv + 8));
-    if (mask) {
-      const uint4 m = __ldg(mask + i);
-      const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+    const float xv[4] = {bf_lo(xr.x), bf_hi(xr.x), bf_lo(xr.y), bf_hi(xr.y)};
+    float g[4];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) keep[k] = ((mw[k >> 2] >> (8 * (k & 3))) & 0xFF) ? drop_scale : 0.f;
-    } else {
-#pragma unroll
-      for (int k = 0; k < 16; ++k) keep[k] = 1.f;
-    }
-    float g[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float xd = xv[k] * keep[k];
+    for (int k = 0; k < 4; ++k) {
+      const float keep = mask ? (((mw >> (8 * k)) & 0xFF) ? drop_scale : 0.f) : 1.f;
+      const float xd = xv[k] * keep;
       float s = 0.f;
 #pragma unroll
       for (int c = 0; c < NCLS; ++c) {
-        acc[c * 16 + k] = fmaf(dl[c], xd, acc[c * 16 + k]);
+        accw[c][k] = fmaf(dl[c], xd, accw[c][k]);
         s = fmaf(dl[c], w[c][k], s);
       }
-      g[k] = xv[k] > 0.f ? s * keep[k] : 0.f;
+      g[k] = xv[k] > 0.f ? s * keep : 0.f;
       g[k] = __bfloat162float(__float2bfloat16_rn(g[k]));  // sum exactly what is stored
-      acc[LOSS + 1 + k] += g[k];
+      accx[k] += g[k];
     }
-    dx[2 * i] = pack8(*reinterpret_cast<float(*)[8]>(g));
-    dx[2 * i + 1] = pack8(*reinterpret_cast<float(*)[8]>(g + 8));
+    dx[4 * i + sub] = make_uint2(pack2(g[0], g[1]), pack2(g[2], g[3]));
   }
+  // fixed-order reduction: lanes of equal channel group (xor 4, 8, 16), then the eight warps
   __shared__ float red[8][NACC];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto lanes = [](float v) {
 #pragma unroll
-  for (int i = 0; i < NACC; ++i) {
-    float v = acc[i];
+    for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red[warp][i] = v;
+  for (int c = 0; c < NCLS; ++c) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float v = lanes(accw[c][k]);
+      if (lane < 4) red[warp][c * 16 + 4 * sub + k] = v;
+    }
+    const float b = lanes(accb[c]);
+    if (lane == 0) red[warp][NCLS * 16 + c] = b;
+  }
+  {
+    const float l = lanes(accl);
+    if (lane == 0) red[warp][LOSS] = l;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float v = lanes(accx[k]);
+    if (lane < 4) red[warp][LOSS + 1 + 4 * sub + k] = v;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < NACC; i += blockDim.x) {
@@ -505,7 +520,7 @@ extern "C" int unpp_bn_bwd_apply(const void* dyh, const void* z, const float* me
   return UNPP_OK;
 }
 
-extern "C" int unpp_head_bwd_grid(int N, int H, int W) { return grid_for(long(N) * H * W, 256, 2); }
+extern "C" int unpp_head_bwd_grid(int N, int H, int W) { return grid_for(long(N) * H * W * 4, 256, 3); }
 
 extern "C" int unpp_head_bwd(const float* heat, const float* dheat, const float* target, int loss_kind, float gamma, float coef, const void* x, const uint8_t* drop_mask,
                              float drop_scale, const float* head_w, int classes, void* dx, float* partial, int N, int H, int W,
@@ -517,13 +532,13 @@ extern "C" int unpp_head_bwd(const float* heat, const float* dheat, const float*
   const long HW = long(H) * W;
 #define LAUNCH(NC)                                                                                                                        \
   if (loss_kind == 1)                                                                                                                     \
-    head_bwd_kernel<NC, true><<<grid, 256, 0, STREAM(stream)>>>(heat, dheat, target, gamma, coef, reinterpret_cast<const uint4*>(x),           \
-                                                        reinterpret_cast<const uint4*>(drop_mask), drop_scale, head_w,                     \
-                                                        reinterpret_cast<uint4*>(dx), partial, N, HW);                                     \
+    head_bwd_kernel<NC, true><<<grid, 256, 0, STREAM(stream)>>>(heat, dheat, target, gamma, coef, reinterpret_cast<const uint2*>(x),           \
+                                                        reinterpret_cast<const uint32_t*>(drop_mask), drop_scale, head_w,                  \
+                                                        reinterpret_cast<uint2*>(dx), partial, N, HW);                                     \
   else                                                                                                                                    \
-    head_bwd_kernel<NC, false><<<grid, 256, 0, STREAM(stream)>>>(heat, dheat, target, gamma, coef, reinterpret_cast<const uint4*>(x),                      \
-                                                        reinterpret_cast<const uint4*>(drop_mask), drop_scale, head_w,                     \
-                                                        reinterpret_cast<uint4*>(dx), partial, N, HW)
+    head_bwd_kernel<NC, false><<<grid, 256, 0, STREAM(stream)>>>(heat, dheat, target, gamma, coef, reinterpret_cast<const uint2*>(x),          \
+                                                        reinterpret_cast<const uint32_t*>(drop_mask), drop_scale, head_w,                  \
+                                                        reinterpret_cast<uint2*>(dx), partial, N, HW)
   switch (classes) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;
