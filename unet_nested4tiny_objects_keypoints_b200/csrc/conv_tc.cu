@@ -274,6 +274,150 @@ __device__ __forceinline__ void epilogue_group(const EpiArgs& p, float (&v)[16],
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Epilogue of the 2x2 output-blocked path.  A thread owns one 2x2 block (accumulator row); the two warps of a lane
+// quadrant take the upper / lower pixel row of the blocks (dy), so one step = the 32 accumulator columns of the two
+// horizontally adjacent pixels (x0, x0 + 1) = 64 contiguous bytes of every NHWC16 operand and of the output.
+struct B2Operands {  // training-only operands of the two pixels, fetched BEFORE the TMEM load is waited for
+  uint4 a[4], m[4], x[4], d[2];
+};
+template <bool HEAD, bool TRAIN>
+__device__ __forceinline__ void b2_prefetch(const EpiArgs& p, B2Operands& t, size_t pix0, bool valid) {
+  if constexpr (TRAIN) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t.a[i] = t.m[i] = t.x[i] = z;
+    t.d[0] = t.d[1] = z;
+    if (valid) {
+      const size_t off = pix0 * 16;
+      if (p.addend) {
+        const uint4* q = reinterpret_cast<const uint4*>(p.addend + off);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t.a[i] = __ldg(q + i);
+      }
+      if (p.relu_mask_src) {
+        const uint4* q = reinterpret_cast<const uint4*>(p.relu_mask_src + off);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t.m[i] = __ldg(q + i);
+      }
+      if (p.stats_aux) {
+        const uint4* q = reinterpret_cast<const uint4*>(p.stats_aux + off);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t.x[i] = __ldg(q + i);
+      }
+      if constexpr (HEAD) {
+        if (p.drop_mask) {
+          const uint4* q = reinterpret_cast<const uint4*>(p.drop_mask + off);
+          t.d[0] = __ldg(q), t.d[1] = __ldg(q + 1);
+        }
+      }
+    }
+  }
+}
+
+template <bool HEAD, bool TRAIN>
+__device__ __forceinline__ void b2_finish(const EpiArgs& p, const uint32_t (&raw)[32], const B2Operands& t, const float (&bias_r)[16], const float* s_bias,
+                                          const float* s_head, bool relu, size_t pix0, bool valid, int n, int yy, int x0, float (&sa1)[16],
+                                          float (&sa2)[16]) {
+  uint32_t words[16];
+  float hv[2][16];  // post-activation values of the two pixels (fused head only)
+#pragma unroll
+  for (int px = 0; px < 2; ++px) {
+    float v[16];
+    if (p.bias9) {  // (row class, column class) bias table of the fused transposed conv
+      const int x = x0 + px;
+      const int boff = (((yy == 0) ? 0 : (yy == p.H - 1 ? 2 : 1)) * 3 + ((x == 0) ? 0 : (x == p.W - 1 ? 2 : 1))) * 16;
+      const float4* b4 = reinterpret_cast<const float4*>(s_bias + boff);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 b = b4[k];
+        v[4 * k] = __uint_as_float(raw[16 * px + 4 * k]) + b.x, v[4 * k + 1] = __uint_as_float(raw[16 * px + 4 * k + 1]) + b.y;
+        v[4 * k + 2] = __uint_as_float(raw[16 * px + 4 * k + 2]) + b.z, v[4 * k + 3] = __uint_as_float(raw[16 * px + 4 * k + 3]) + b.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(raw[16 * px + k]) + bias_r[k];
+    }
+    if constexpr (!TRAIN && !HEAD) {
+      // plain inference epilogue: the ReLU clamp is folded into the bf16 conversion
+#pragma unroll
+      for (int k = 0; k < 8; ++k) words[8 * px + k] = relu ? cvt_bf16x2_relu(v[2 * k], v[2 * k + 1]) : cvt_bf16x2(v[2 * k], v[2 * k + 1]);
+    } else {
+      if constexpr (TRAIN) {
+        if (p.addend) {
+          const uint32_t aw[8] = {t.a[2 * px].x, t.a[2 * px].y, t.a[2 * px].z, t.a[2 * px].w, t.a[2 * px + 1].x, t.a[2 * px + 1].y, t.a[2 * px + 1].z, t.a[2 * px + 1].w};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[2 * k] += bf16_lo(aw[k]), v[2 * k + 1] += bf16_hi(aw[k]);
+        }
+      }
+      if (relu) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
+      }
+      if constexpr (TRAIN) {
+        if (p.relu_mask_src) {
+          const uint32_t mw[8] = {t.m[2 * px].x, t.m[2 * px].y, t.m[2 * px].z, t.m[2 * px].w, t.m[2 * px + 1].x, t.m[2 * px + 1].y, t.m[2 * px + 1].z, t.m[2 * px + 1].w};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (!(bf16_lo(mw[k]) > 0.f)) v[2 * k] = 0.f;
+            if (!(bf16_hi(mw[k]) > 0.f)) v[2 * k + 1] = 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) words[8 * px + k] = cvt_bf16x2(v[2 * k], v[2 * k + 1]);
+      if constexpr (TRAIN) {
+        if (p.stats_partial && valid) {
+          // statistics of the bf16-rounded values that are stored; second statistic v*v (BN batch variance) or v*aux (BN backward)
+          const uint32_t xw[8] = {t.x[2 * px].x, t.x[2 * px].y, t.x[2 * px].z, t.x[2 * px].w, t.x[2 * px + 1].x, t.x[2 * px + 1].y, t.x[2 * px + 1].z, t.x[2 * px + 1].w};
+          const bool aux = p.stats_aux != nullptr;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float r0 = bf16_lo(words[8 * px + k]), r1 = bf16_hi(words[8 * px + k]);
+            sa1[2 * k] += r0, sa1[2 * k + 1] += r1;
+            sa2[2 * k] = fmaf(r0, aux ? bf16_lo(xw[k]) : r0, sa2[2 * k]), sa2[2 * k + 1] = fmaf(r1, aux ? bf16_hi(xw[k]) : r1, sa2[2 * k + 1]);
+          }
+        }
+      }
+      if constexpr (HEAD) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) hv[px][k] = v[k];
+        if constexpr (TRAIN) {
+          if (p.drop_mask) {
+            const uint32_t dw[4] = {t.d[px].x, t.d[px].y, t.d[px].z, t.d[px].w};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) hv[px][k] = ((dw[k >> 2] >> (8 * (k & 3))) & 0xFF) ? v[k] * p.drop_scale : 0.f;
+          }
+        }
+      }
+    }
+  }
+  if (!valid) return;
+  if (p.out) {
+    uint8_t* op = reinterpret_cast<uint8_t*>(p.out + pix0 * 16);
+    st_global_v8(op, words);
+    st_global_v8(op + 32, words + 8);
+  }
+  if constexpr (HEAD) {
+    const size_t plane = size_t(p.H) * p.W;
+    size_t o = size_t(n) * p.head_classes * plane + size_t(yy) * p.W + x0;
+    for (int cls = 0; cls < p.head_classes; ++cls, o += plane) {
+      const float4* w4 = reinterpret_cast<const float4*>(s_head + cls * 16);
+      float a0 = s_head[8 * 16 + cls], a1 = a0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 w = w4[k];
+        a0 = fmaf(w.x, hv[0][4 * k], a0), a0 = fmaf(w.y, hv[0][4 * k + 1], a0), a0 = fmaf(w.z, hv[0][4 * k + 2], a0), a0 = fmaf(w.w, hv[0][4 * k + 3], a0);
+        a1 = fmaf(w.x, hv[1][4 * k], a1), a1 = fmaf(w.y, hv[1][4 * k + 1], a1), a1 = fmaf(w.z, hv[1][4 * k + 2], a1), a1 = fmaf(w.w, hv[1][4 * k + 3], a1);
+      }
+      if constexpr (TRAIN) {
+        if (p.logit) *reinterpret_cast<float2*>(p.logit + o) = make_float2(a0, a1);
+      }
+      *reinterpret_cast<float2*>(p.heat + o) = make_float2(1.f / (1.f + __expf(-a0)), 1.f / (1.f + __expf(-a1)));
+    }
+  }
+}
+
 template <bool DECONV, bool HEAD, bool TRAIN>
 __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   constexpr int kMmaWarps = mma_warps(TRAIN), kThreads = block_threads(TRAIN);
@@ -529,6 +673,55 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
 #pragma unroll
     for (int k = 0; k < 16; ++k) sa1[k] = 0.f, sa2[k] = 0.f;
     int tile_it = 0;
+    if (b2) {
+      // 2x2 output blocks: this warp takes pixel row dy = half of every block; one step = two adjacent pixels (32 columns)
+      float bias_r[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) bias_r[k] = e.bias9 ? 0.f : s_bias[k];
+      const bool relu = p.relu != 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+        const int b = tile_it % nacc, aph = (tile_it / nacc) & 1;
+        const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+        mbar_wait(&bar_acc_full[b], aph);
+        tc_fence_after();
+        const int yy = ty * 32 + 2 * pi + half, xb = tx * TW + 2 * pj;
+        const bool row_ok = yy < e.H;
+        const size_t rowpix = (size_t(n) * e.H + yy) * e.W;
+        const uint32_t tcol = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * nsub * 64 + half * 32);
+        if (!(dbg & 1)) {
+          if constexpr (TRAIN || HEAD) {  // one TMEM buffer (registers): operands of the step are in flight while the load is waited for
+            uint32_t A[32];
+            for (int j = 0; j < nsub; ++j) {
+              const int x0 = xb + j * 16;
+              const bool valid = row_ok && x0 < e.W;
+              B2Operands tops;
+              tmem_ld32(tcol + uint32_t(j * 64), A);
+              b2_prefetch<HEAD, TRAIN>(e, tops, rowpix + x0, valid);
+              tmem_ld_wait32(A);
+              b2_finish<HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, rowpix + x0, valid, n, yy, x0, sa1, sa2);
+            }
+          } else {  // two TMEM buffers: the load of the next step is in flight while this one is finished
+            uint32_t A[32], B[32];
+            B2Operands tops;
+            tmem_ld32(tcol, A);
+            for (int j = 0; j < nsub; j += 2) {
+              const int x0 = xb + j * 16;
+              tmem_ld_wait32(A);
+              if (j + 1 < nsub) tmem_ld32(tcol + uint32_t((j + 1) * 64), B);
+              b2_finish<HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, rowpix + x0, row_ok && x0 < e.W, n, yy, x0, sa1, sa2);
+              if (j + 1 < nsub) {
+                tmem_ld_wait32(B);
+                if (j + 2 < nsub) tmem_ld32(tcol + uint32_t((j + 2) * 64), A);
+                b2_finish<HEAD, TRAIN>(e, B, tops, bias_r, s_bias, s_head, relu, rowpix + x0 + 16, row_ok && x0 + 16 < e.W, n, yy, x0 + 16, sa1, sa2);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+      }
+    } else
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
       const int b = tile_it % nacc, aph = (tile_it / nacc) & 1;
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);

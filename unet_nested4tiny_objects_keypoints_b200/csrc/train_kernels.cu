@@ -298,52 +298,73 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) accx[k] = 0.f;
-  const long total = long(N) * HW;
-  for (long i = blockIdx.x * 64L + (threadIdx.x >> 2); i < total; i += long(gridDim.x) * 64L) {
-    const long n = i / HW, p = i % HW;
-    const uint2 xr = __ldg(x + 4 * i + sub);
-    const uint32_t mw = mask ? __ldg(mask + 4 * i + sub) : 0x01010101u;
-    float dl[NCLS];
+  // One step of a lane quad = four consecutive pixels (HW % 4 == 0, so they share an image): the heat / target words of
+  // a class are ONE float4, and all 16 loads of the step are issued before any is used (the kernel is latency-bound).
+  const long quads = long(N) * HW / 4, step = long(gridDim.x) * 64L, HW4 = HW / 4;
+  long i4 = blockIdx.x * 64L + (threadIdx.x >> 2);
+  long n = i4 / HW4, p4 = i4 % HW4;  // (image, pixel quad) advanced incrementally: no 64-bit division in the loop
+  const long step_n = step / HW4, step_p = step % HW4;
+  for (; i4 < quads; i4 += step, n += step_n, p4 += step_p) {
+    if (p4 >= HW4) p4 -= HW4, ++n;
+    float4 hh[NCLS], tt[NCLS];
 #pragma unroll
     for (int c = 0; c < NCLS; ++c) {
-      const long o = (n * NCLS + c) * HW + p;
-      const float pr = __ldg(heat + o);
-      float dh;
-      if (target) {
-        const float d = pr - __ldg(target + o);
-        if constexpr (!FOCAL) {  // MSE: loss += d^2, d loss / d p = coef * d
-          accl = fmaf(lead * d, d, accl);
-          dh = coef * d;
-        } else {  // FocalLoss_BCE_2d (tools/losses/focal_loss.py:264-301): a = |p-t|, e = 1-a+1e-20, loss += -a^gamma * log(e)
-          const float a = fabsf(d), e = 1.f - a + 1e-20f;
-          // gamma = 3 (the trainer's setting, trainer.py:426) needs no pow; log through the fast intrinsic (rel. error ~1e-6)
-          const float le = __logf(e), pg1 = gamma == 3.f ? a * a : (a > 0.f ? __powf(a, gamma - 1.f) : 0.f);
-          accl += lead * (-(pg1 * a) * le);
-          dh = coef * copysignf(-gamma * pg1 * le + (pg1 * a) / e, d);
-        }
-      } else {
-        dh = __ldg(dheat + o);
-      }
-      dl[c] = dh * pr * (1.f - pr);
-      accb[c] = fmaf(lead, dl[c], accb[c]);
+      const long o = (n * NCLS + c) * HW + 4 * p4;
+      hh[c] = __ldg(reinterpret_cast<const float4*>(heat + o));
+      tt[c] = __ldg(reinterpret_cast<const float4*>((target ? target : dheat) + o));
     }
-    const float xv[4] = {bf_lo(xr.x), bf_hi(xr.x), bf_lo(xr.y), bf_hi(xr.y)};
-    float g[4];
+    uint2 xq[4];
+    uint32_t mq[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float keep = mask ? (((mw >> (8 * k)) & 0xFF) ? drop_scale : 0.f) : 1.f;
-      const float xd = xv[k] * keep;
-      float s = 0.f;
+    for (int u = 0; u < 4; ++u) {
+      xq[u] = __ldg(x + 4 * (4 * i4 + u) + sub);
+      mq[u] = mask ? __ldg(mask + 4 * (4 * i4 + u) + sub) : 0x01010101u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint2 xr = xq[u];
+      const uint32_t mw = mq[u];
+      float dl[NCLS];
 #pragma unroll
       for (int c = 0; c < NCLS; ++c) {
-        accw[c][k] = fmaf(dl[c], xd, accw[c][k]);
-        s = fmaf(dl[c], w[c][k], s);
+        const float pr = (&hh[c].x)[u], tv = (&tt[c].x)[u];
+        float dh;
+        if (target) {
+          const float d = pr - tv;
+          if constexpr (!FOCAL) {  // MSE: loss += d^2, d loss / d p = coef * d
+            accl = fmaf(lead * d, d, accl);
+            dh = coef * d;
+          } else {  // FocalLoss_BCE_2d (tools/losses/focal_loss.py:264-301): a = |p-t|, e = 1-a+1e-20, loss += -a^gamma * log(e)
+            const float a = fabsf(d), e = 1.f - a + 1e-20f;
+            // gamma = 3 (the trainer's setting, trainer.py:426) needs no pow; log through the fast intrinsic (rel. error ~1e-6)
+            const float le = __logf(e), pg1 = gamma == 3.f ? a * a : (a > 0.f ? __powf(a, gamma - 1.f) : 0.f);
+            accl += lead * (-(pg1 * a) * le);
+            dh = coef * copysignf(-gamma * pg1 * le + (pg1 * a) / e, d);
+          }
+        } else {
+          dh = tv;  // upstream gradient
+        }
+        dl[c] = dh * pr * (1.f - pr);
+        accb[c] = fmaf(lead, dl[c], accb[c]);
       }
-      g[k] = xv[k] > 0.f ? s * keep : 0.f;
-      g[k] = __bfloat162float(__float2bfloat16_rn(g[k]));  // sum exactly what is stored
-      accx[k] += g[k];
+      const float xv[4] = {bf_lo(xr.x), bf_hi(xr.x), bf_lo(xr.y), bf_hi(xr.y)};
+      float g[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float keep = mask ? (((mw >> (8 * k)) & 0xFF) ? drop_scale : 0.f) : 1.f;
+        const float xd = xv[k] * keep;
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCLS; ++c) {
+          accw[c][k] = fmaf(dl[c], xd, accw[c][k]);
+          s = fmaf(dl[c], w[c][k], s);
+        }
+        g[k] = xv[k] > 0.f ? s * keep : 0.f;
+        g[k] = __bfloat162float(__float2bfloat16_rn(g[k]));  // sum exactly what is stored
+        accx[k] += g[k];
+      }
+      dx[4 * (4 * i4 + u) + sub] = make_uint2(pack2(g[0], g[1]), pack2(g[2], g[3]));
     }
-    dx[4 * i + sub] = make_uint2(pack2(g[0], g[1]), pack2(g[2], g[3]));
   }
   // fixed-order reduction: lanes of equal channel group (xor 4, 8, 16), then the eight warps
   __shared__ float red[8][NACC];
@@ -520,7 +541,7 @@ extern "C" int unpp_bn_bwd_apply(const void* dyh, const void* z, const float* me
   return UNPP_OK;
 }
 
-extern "C" int unpp_head_bwd_grid(int N, int H, int W) { return grid_for(long(N) * H * W * 4, 256, 3); }
+extern "C" int unpp_head_bwd_grid(int N, int H, int W) { return grid_for(long(N) * H * W, 256, 2); }
 
 extern "C" int unpp_head_bwd(const float* heat, const float* dheat, const float* target, int loss_kind, float gamma, float coef, const void* x, const uint8_t* drop_mask,
                              float drop_scale, const float* head_w, int classes, void* dx, float* partial, int N, int H, int W,
@@ -528,6 +549,8 @@ extern "C" int unpp_head_bwd(const float* heat, const float* dheat, const float*
   if (!heat || (!dheat && !target) || !x || !head_w || !dx || !partial || N < 1 || H < 1 || W < 1)
     return unpp::fail(UNPP_ERR_BAD_ARG, "head_bwd: bad argument");
   if (loss_kind != 0 && loss_kind != 1) return unpp::fail(UNPP_ERR_BAD_ARG, "head_bwd: loss_kind must be 0 (MSE) or 1 (focal BCE)");
+  if ((long(H) * W) % 4 || ((reinterpret_cast<uintptr_t>(heat) | reinterpret_cast<uintptr_t>(target ? target : dheat)) & 15))
+    return unpp::fail(UNPP_ERR_BAD_ARG, "head_bwd: H*W must be a multiple of 4 and heat / target / dheat 16-byte aligned");
   const int grid = unpp_head_bwd_grid(N, H, W);
   const long HW = long(H) * W;
 #define LAUNCH(NC)                                                                                                                        \
