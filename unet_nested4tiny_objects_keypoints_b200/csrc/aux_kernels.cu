@@ -58,9 +58,13 @@ __device__ __forceinline__ void pack_entry(const UnppPackArgs& a) {
   }
 }
 
-__global__ void pack_weights_kernel(UnppPackArgs a) { pack_entry(a); }
+__global__ void pack_weights_kernel(UnppPackArgs a) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger(); pack_entry(a); }
 // one launch for a whole table of pack jobs (device-resident): blockIdx.y selects the job
 __global__ void pack_weights_batched_kernel(const UnppPackArgs* __restrict__ table) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   const UnppPackArgs a = table[blockIdx.y];
   pack_entry(a);
 }
@@ -69,6 +73,8 @@ __global__ void pack_weights_batched_kernel(const UnppPackArgs* __restrict__ tab
 // NCHW fp32 -> NHWC bf16 with channel padding; one thread per pixel, reads coalesced per plane.
 template <int CPAD>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C, long HW) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   const long total = long(N) * HW;
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
     const long n = i / HW, p = i % HW;
@@ -93,6 +99,8 @@ __device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
   return r;
 }
 __global__ void maxpool2x2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int N, int H, int W, int C8) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   const int Ho = H / 2, Wo = W / 2;
   const long total = long(N) * Ho * Wo * C8;
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
@@ -120,6 +128,8 @@ __device__ __forceinline__ void take(float& bv, int& bi, float v, int i) {
 }
 __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ heat, int HW, int W, int32_t* __restrict__ xy,
                                                      float* __restrict__ val) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   const float* h = heat + size_t(blockIdx.x) * HW;
   float bv = -INFINITY;
   int bi = 0x7fffffff;
@@ -168,6 +178,8 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ h
 // planes are assigned, multi-point planes are summed (float32 += float64) and divided by their maximum.
 // One CTA per (n, channel) plane: pass 1 writes the sums and reduces the plane maximum, pass 2 normalises.
 __global__ void __launch_bounds__(256) create_heatmap_kernel(const float* __restrict__ kp, int npts, int H, int W, float* __restrict__ out) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   const int n = blockIdx.x >> 2, ch = blockIdx.x & 3;
   const int p0 = ch == 0 ? 0 : ch == 1 ? 1 : ch == 2 ? 4 : 5, p1 = ch == 0 ? 1 : ch == 1 ? 4 : ch == 2 ? 5 : npts;
   float* plane = out + size_t(blockIdx.x) * H * W;
@@ -218,14 +230,14 @@ extern "C" int unpp_pack_weights(const UnppPackArgs* a, unpp_stream_t stream) {
     return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: n_total %% n_tile, k_count %% 8 must be 0");
   if (a->k_dst8 + a->k_count / 8 > a->k8_total) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: K range exceeds k8_total");
   const long total = long(a->n_total) * a->taps * (a->k_count / 8);
-  pack_weights_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+  unpp::launch(pack_weights_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), *a);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("pack_weights: launch");
   return UNPP_OK;
 }
 
 extern "C" int unpp_pack_weights_batched(const UnppPackArgs* table_dev, int n, unpp_stream_t stream) {
   if (!table_dev || n < 1 || n > 65535) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights_batched: bad argument");
-  pack_weights_batched_kernel<<<dim3(8, n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table_dev);
+  unpp::launch(pack_weights_batched_kernel, dim3(8, n), 256, 0, reinterpret_cast<cudaStream_t>(stream), table_dev);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("pack_weights_batched: launch");
   return UNPP_OK;
 }
@@ -234,7 +246,7 @@ extern "C" int unpp_nchw_to_nhwc(const float* x, void* out, int N, int C, int H,
   if (!x || !out || N < 1 || C < 1 || H < 1 || W < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "nchw_to_nhwc: bad argument");
   if (Cpad != 16 || C > Cpad) return unpp::fail(UNPP_ERR_UNSUPPORTED, "nchw_to_nhwc: Cpad must be 16 and C <= 16");
   const long total = long(N) * H * W;
-  nchw_to_nhwc_kernel<16><<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  unpp::launch(nchw_to_nhwc_kernel<16>, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       x, reinterpret_cast<__nv_bfloat16*>(out), N, C, long(H) * W);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("nchw_to_nhwc: launch");
   return UNPP_OK;
@@ -243,7 +255,7 @@ extern "C" int unpp_nchw_to_nhwc(const float* x, void* out, int N, int C, int H,
 extern "C" int unpp_maxpool2x2(const void* x, void* out, int N, int H, int W, int C, unpp_stream_t stream) {
   if (!x || !out || N < 1 || H < 2 || W < 2 || (H & 1) || (W & 1) || C % 8) return unpp::fail(UNPP_ERR_BAD_ARG, "maxpool2x2: need even H, W and C %% 8 == 0");
   const long total = long(N) * (H / 2) * (W / 2) * (C / 8);
-  maxpool2x2_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  unpp::launch(maxpool2x2_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), N, H, W, C / 8);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("maxpool2x2: launch");
   return UNPP_OK;
@@ -252,7 +264,7 @@ extern "C" int unpp_maxpool2x2(const void* x, void* out, int N, int H, int W, in
 extern "C" int unpp_create_heatmap(const float* keypoints, int N, int npts, int H, int W, float* out, unpp_stream_t stream) {
   if (!keypoints || !out || N < 1 || H < 1 || W < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "create_heatmap: bad argument");
   if (npts < 6 || npts > 9) return unpp::fail(UNPP_ERR_UNSUPPORTED, "create_heatmap: the reference's grouping needs 6..9 key points (7 in the trainer)");
-  create_heatmap_kernel<<<N * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(keypoints, npts, H, W, out);
+  unpp::launch(create_heatmap_kernel, N * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream), keypoints, npts, H, W, out);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("create_heatmap: launch");
   return UNPP_OK;
 }
@@ -261,7 +273,7 @@ extern "C" int unpp_argmax_peaks(const float* heat, int planes, int H, int W, in
   if (!heat || !xy || planes < 0 || H < 1 || W < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "argmax_peaks: bad argument");
   if (long(H) * W > 0x7ffffff0L) return unpp::fail(UNPP_ERR_UNSUPPORTED, "argmax_peaks: plane too large");
   if (planes == 0) return UNPP_OK;
-  argmax_kernel<<<planes, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(heat, H * W, W, xy, val);
+  unpp::launch(argmax_kernel, planes, 256, 0, reinterpret_cast<cudaStream_t>(stream), heat, H * W, W, xy, val);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("argmax_peaks: launch");
   return UNPP_OK;
 }

@@ -12,5 +12,28 @@ char* last_error_buf();
 int fail(int code, const char* fmt, ...);
 int fail_cuda(const char* what);  // formats cudaGetLastError() and returns UNPP_ERR_CUDA
 int num_sms();
+bool pdl_enabled();  // programmatic dependent launch for every libunpp kernel (UNPP_PDL=1 switches it on)
+
+// With UNPP_PDL=1 every libunpp kernel is launched with the programmatic-stream-serialization attribute and runs
+//   [on-chip prologue]  pdl_wait();  pdl_trigger();  [work]
+// so the launch latency and the prologue (barrier init, TMEM allocation, descriptor prefetch) of kernel k+1
+// overlap the tail of kernel k.  pdl_wait() returns when the preceding kernel has COMPLETED and its writes are
+// visible; since every kernel passes its own wait before it triggers, everything older is complete as well.
+// Nothing before pdl_wait() may touch global memory other kernels of the stream write.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... P, typename... A>
+inline cudaError_t launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+#endif
 
 }  // namespace unpp

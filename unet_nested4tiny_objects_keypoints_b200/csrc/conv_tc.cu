@@ -456,6 +456,10 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
       if (i < p.nchunk) tma_prefetch_desc(&p.maps[p.ch_map[i]]);
     if (p.low_on) tma_prefetch_desc(&p.lowmap);
   }
+  // Everything above is on-chip set-up and overlaps the tail of the preceding kernel (programmatic dependent launch);
+  // from here on global memory written by earlier kernels is read.
+  unpp::pdl_wait();
+  unpp::pdl_trigger();
   // stage the per-column bias (conv: this CTA's n_tile slice; deconv: all Cout) and the 1x1 head
   {
     const int nb = p.bias9 ? 9 * 16 : ((DECONV || p.b2) ? p.cout : p.ncols);
@@ -1014,7 +1018,7 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
         return unpp::fail_cuda("conv_tc: cudaFuncSetAttribute");                                                                      \
       opted_in = 1;                                                                                                                   \
     }                                                                                                                                 \
-    conv_tc_kernel<D, Hd, T><<<grid, block_threads(T), pl.smem_total, stream>>>(p);                                                           \
+    unpp::launch(conv_tc_kernel<D, Hd, T>, grid, block_threads(T), pl.smem_total, stream, p);                                                           \
   } while (0)
   if (deconv) UNPP_LAUNCH(true, false, false);
   else if (head && train) UNPP_LAUNCH(false, true, true);

@@ -57,6 +57,8 @@ __device__ __forceinline__ float sliced_sum(int nparts, F load) {
 // out[i] (+)= scale * sum_p partial[p * stride + i]
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nparts, long stride, int n, float scale,
                                                               float* __restrict__ out, int accumulate) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   for (int base = blockIdx.x * 32; base < n; base += gridDim.x * 32) {
     const int i = base + (threadIdx.x & 31);
     const float t = sliced_sum(nparts, [&](int p) { return i < n ? __ldg(partial + p * stride + i) : 0.f; });
@@ -68,6 +70,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int taps, int cin_total, int cout,
                                                            float* __restrict__ dst, int ci_begin, int ci_count, long s_co, long s_ci, long s_tap,
                                                            float scale) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   const int n = taps * ci_count * cout;
   const long stride = long(taps) * cin_total * cout;
   for (int base = blockIdx.x * 32; base < n; base += gridDim.x * 32) {
@@ -84,6 +88,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 // whose block range contains b (the table is small: a linear scan of the running totals).  The eight warps sum
 // interleaved slices of the partials, the slice sums are added in a fixed order: deterministic.
 __global__ void __launch_bounds__(256) reduce_batched_kernel(const UnppReduceJob* __restrict__ table, int njobs) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   __shared__ float4 red4[8][32];
   int j = 0;
   while (j < njobs - 1 && int(blockIdx.x) >= __ldg(&table[j].block_end)) ++j;
@@ -130,6 +136,8 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
                                                           float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps,
                                                           float* __restrict__ mean, float* __restrict__ istd, float* __restrict__ scale,
                                                           float* __restrict__ shift) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   // block = 32 channels x 8 slices of the partials; sums in double (2*C*nparts values: free, and it removes the
   // E[z^2]-m^2 cancellation); fixed summation order
   __shared__ double r1[8][32], r2[8][32];
@@ -165,6 +173,8 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
 // y = relu(z * scale[c] + shift[c]) (bf16 NHWC, 8 channels per thread); optional 2x2 max-pooled copy.
 __global__ void bn_relu_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift, uint4* __restrict__ y,
                                long total, int C8) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
     const int c0 = int(i % C8) * 8;
     float f[8];
@@ -176,6 +186,8 @@ __global__ void bn_relu_kernel(const uint4* __restrict__ z, const float* __restr
 }
 __global__ void bn_relu_pool_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                                     uint4* __restrict__ y, uint4* __restrict__ pooled, int N, int H, int W, int C8) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   const int Ho = H / 2, Wo = W / 2;
   const long total = long(N) * Ho * Wo * C8;
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
@@ -211,6 +223,8 @@ __global__ void bn_relu_pool_kernel(const uint4* __restrict__ z, const float* __
 // MaxPool2d(2) backward: the gradient of each pooled element goes to the FIRST maximum of its 2x2
 // window in row-major order (what ATen's max_pool2d_with_indices records); the other three get 0.
 __global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dp, uint4* __restrict__ dx, int N, int H, int W, int C8) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   const int Ho = H / 2, Wo = W / 2;
   const long total = long(N) * Ho * Wo * C8;
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
@@ -250,6 +264,8 @@ __global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __r
 __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dyh, const uint4* __restrict__ z, const float* __restrict__ mean,
                                     const float* __restrict__ istd, const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count,
                                     uint4* __restrict__ dz, long total, int C8) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   const int C = C8 * 8;
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
     const int c0 = int(i % C8) * 8;
@@ -283,6 +299,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
                                                        float gamma, float coef, const uint2* __restrict__ x, const uint32_t* __restrict__ mask, float drop_scale,
                                                        const float* __restrict__ head_w, uint2* __restrict__ dx, float* __restrict__ partial,
                                                        int N, long HW) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   // Four threads per pixel, each owning four of the 16 channels (8 B of x / dx, 4 B of the keep-mask): 25 accumulators
   // per thread instead of 85, so three blocks per SM are resident and enough loads are in flight to stream at HBM speed.
   // The four lanes of a pixel read the same heat / target words (one broadcast transaction).
@@ -408,6 +426,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 // double like the reference does in Python floats.
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n, float b1,
                              float b2, float eps, float step_size, const float* __restrict__ step_size_dev, float wd, float grad_scale) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   if (step_size_dev) step_size = *step_size_dev;
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < n; i += long(gridDim.x) * blockDim.x) {
     const float gr = g[i] * grad_scale;
@@ -425,6 +445,8 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 // Device-side step bookkeeping so that a whole training step can live in one CUDA graph: bumps the
 // step counter and derives AdamW's bias-corrected step size from it (adamw.py:86-88).
 __global__ void adamw_prep_kernel(unsigned long long* counter, float lr, float b1, float b2, float* step_size) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   const unsigned long long t = *counter + 1ull;
   *counter = t;
   const double bc1 = 1.0 - pow(double(b1), double(t)), bc2 = 1.0 - pow(double(b2), double(t));
@@ -439,6 +461,8 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 }
 __global__ void dropout_mask_kernel(uint4* __restrict__ out, long n16, uint32_t seed_lo, uint32_t seed_hi, uint32_t thresh16,
                                     const unsigned long long* __restrict__ counter) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
   if (counter) {  // per-step stream: fold the device step counter into the seed
     const unsigned long long c = (*counter + 1ull) * 0x9E3779B97F4A7C15ull;
     seed_lo ^= uint32_t(c), seed_hi ^= uint32_t(c >> 32);
@@ -467,14 +491,14 @@ __global__ void dropout_mask_kernel(uint4* __restrict__ out, long n16, uint32_t 
 extern "C" int unpp_reduce_partials(const float* partial, int nparts, long stride, int n, float scale, float* out, int accumulate,
                                     unpp_stream_t stream) {
   if (!partial || !out || nparts < 1 || n < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "reduce_partials: bad argument");
-  reduce_partials_kernel<<<grid_for((long(n) + 31) / 32 * 256, 256), 256, 0, STREAM(stream)>>>(partial, nparts, stride, n, scale, out, accumulate);
+  unpp::launch(reduce_partials_kernel, grid_for((long(n) + 31) / 32 * 256, 256), 256, 0, STREAM(stream), partial, nparts, stride, n, scale, out, accumulate);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("reduce_partials: launch");
   return UNPP_OK;
 }
 
 extern "C" int unpp_reduce_batched(const UnppReduceJob* table, int njobs, int total_blocks, unpp_stream_t stream) {
   if (!table || njobs < 1 || total_blocks < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "reduce_batched: bad argument");
-  reduce_batched_kernel<<<total_blocks, 256, 0, STREAM(stream)>>>(table, njobs);
+  unpp::launch(reduce_batched_kernel, total_blocks, 256, 0, STREAM(stream), table, njobs);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("reduce_batched: launch");
   return UNPP_OK;
 }
@@ -485,7 +509,7 @@ extern "C" int unpp_wgrad_reduce(const float* partial, int nparts, int taps, int
   if (!partial || !dst || nparts < 1 || taps < 1 || ci_count < 1 || ci_begin < 0 || ci_begin + ci_count > cin_total || cout < 1)
     return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad_reduce: bad argument");
   const int n = taps * ci_count * cout;
-  wgrad_reduce_kernel<<<grid_for((long(n) + 31) / 32 * 256, 256), 256, 0, STREAM(stream)>>>(partial, nparts, taps, cin_total, cout, dst, ci_begin, ci_count, s_co, s_ci,
+  unpp::launch(wgrad_reduce_kernel, grid_for((long(n) + 31) / 32 * 256, 256), 256, 0, STREAM(stream), partial, nparts, taps, cin_total, cout, dst, ci_begin, ci_count, s_co, s_ci,
                                                                    s_tap, scale);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("wgrad_reduce: launch");
   return UNPP_OK;
@@ -496,7 +520,7 @@ extern "C" int unpp_bn_finalize(const float* partial, int nparts, int C, float c
                                 unpp_stream_t stream) {
   if (!partial || !gamma || !beta || !mean || !istd || !scale || !shift || nparts < 1 || C < 1 || !(count >= 1.f))
     return unpp::fail(UNPP_ERR_BAD_ARG, "bn_finalize: bad argument");
-  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, STREAM(stream)>>>(partial, nparts, C, count, gamma, beta, running_mean, running_var, momentum, eps,
+  unpp::launch(bn_finalize_kernel, (C + 31) / 32, 256, 0, STREAM(stream), partial, nparts, C, count, gamma, beta, running_mean, running_var, momentum, eps,
                                                                mean, istd, scale, shift);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("bn_finalize: launch");
   return UNPP_OK;
@@ -508,12 +532,12 @@ extern "C" int unpp_bn_relu(const void* z, const float* scale, const float* shif
   if (pooled) {
     if ((H & 1) || (W & 1)) return unpp::fail(UNPP_ERR_BAD_ARG, "bn_relu: pooling needs even H and W");
     const long total = long(N) * (H / 2) * (W / 2) * (C / 8);
-    bn_relu_pool_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const uint4*>(z), scale, shift,
+    unpp::launch(bn_relu_pool_kernel, grid_for(total, 256), 256, 0, STREAM(stream), reinterpret_cast<const uint4*>(z), scale, shift,
                                                                           reinterpret_cast<uint4*>(y), reinterpret_cast<uint4*>(pooled), N, H, W,
                                                                           C / 8);
   } else {
     const long total = long(N) * H * W * (C / 8);
-    bn_relu_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<uint4*>(y),
+    unpp::launch(bn_relu_kernel, grid_for(total, 256), 256, 0, STREAM(stream), reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<uint4*>(y),
                                                                      total, C / 8);
   }
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("bn_relu: launch");
@@ -524,7 +548,7 @@ extern "C" int unpp_maxpool2x2_bwd(const void* x, const void* dpooled, void* dx,
   if (!x || !dpooled || !dx || N < 1 || H < 2 || W < 2 || (H & 1) || (W & 1) || C % 8)
     return unpp::fail(UNPP_ERR_BAD_ARG, "maxpool2x2_bwd: need even H, W and C %% 8 == 0");
   const long total = long(N) * (H / 2) * (W / 2) * (C / 8);
-  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dpooled),
+  unpp::launch(maxpool_bwd_kernel, grid_for(total, 256), 256, 0, STREAM(stream), reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dpooled),
                                                                        reinterpret_cast<uint4*>(dx), N, H, W, C / 8);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("maxpool2x2_bwd: launch");
   return UNPP_OK;
@@ -535,7 +559,7 @@ extern "C" int unpp_bn_bwd_apply(const void* dyh, const void* z, const float* me
   if (!dyh || !z || !mean || !istd || !gamma || !sums || !dz || N < 1 || H < 1 || W < 1 || C % 8 || !(count >= 1.f))
     return unpp::fail(UNPP_ERR_BAD_ARG, "bn_bwd_apply: bad argument");
   const long total = long(N) * H * W * (C / 8);
-  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const uint4*>(dyh), reinterpret_cast<const uint4*>(z), mean,
+  unpp::launch(bn_bwd_apply_kernel, grid_for(total, 256), 256, 0, STREAM(stream), reinterpret_cast<const uint4*>(dyh), reinterpret_cast<const uint4*>(z), mean,
                                                                         istd, gamma, sums, 1.f / count, reinterpret_cast<uint4*>(dz), total, C / 8);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("bn_bwd_apply: launch");
   return UNPP_OK;
@@ -555,11 +579,11 @@ extern "C" int unpp_head_bwd(const float* heat, const float* dheat, const float*
   const long HW = long(H) * W;
 #define LAUNCH(NC)                                                                                                                        \
   if (loss_kind == 1)                                                                                                                     \
-    head_bwd_kernel<NC, true><<<grid, 256, 0, STREAM(stream)>>>(heat, dheat, target, gamma, coef, reinterpret_cast<const uint2*>(x),           \
+    unpp::launch(head_bwd_kernel<NC, true>, grid, 256, 0, STREAM(stream), heat, dheat, target, gamma, coef, reinterpret_cast<const uint2*>(x),           \
                                                         reinterpret_cast<const uint32_t*>(drop_mask), drop_scale, head_w,                  \
                                                         reinterpret_cast<uint2*>(dx), partial, N, HW);                                     \
   else                                                                                                                                    \
-    head_bwd_kernel<NC, false><<<grid, 256, 0, STREAM(stream)>>>(heat, dheat, target, gamma, coef, reinterpret_cast<const uint2*>(x),          \
+    unpp::launch(head_bwd_kernel<NC, false>, grid, 256, 0, STREAM(stream), heat, dheat, target, gamma, coef, reinterpret_cast<const uint2*>(x),          \
                                                         reinterpret_cast<const uint32_t*>(drop_mask), drop_scale, head_w,                  \
                                                         reinterpret_cast<uint2*>(dx), partial, N, HW)
   switch (classes) {
@@ -579,7 +603,7 @@ extern "C" int unpp_adamw(float* p, const float* g, float* m, float* v, long n, 
   if (!p || !g || !m || !v || n < 1 || step < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "adamw: bad argument");
   const double bc1 = 1.0 - pow(double(beta1), step), bc2 = 1.0 - pow(double(beta2), step);
   const float step_size = float(double(lr) * sqrt(bc2) / bc1);
-  adamw_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(p, g, m, v, n, beta1, beta2, eps, step_size, nullptr, weight_decay, grad_scale);
+  unpp::launch(adamw_kernel, grid_for(n, 256), 256, 0, STREAM(stream), p, g, m, v, n, beta1, beta2, eps, step_size, nullptr, weight_decay, grad_scale);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("adamw: launch");
   return UNPP_OK;
 }
@@ -587,8 +611,8 @@ extern "C" int unpp_adamw(float* p, const float* g, float* m, float* v, long n, 
 extern "C" int unpp_adamw_dev(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
                               float weight_decay, uint64_t* step_counter, float* step_size_scratch, float grad_scale, unpp_stream_t stream) {
   if (!p || !g || !m || !v || n < 1 || !step_counter || !step_size_scratch) return unpp::fail(UNPP_ERR_BAD_ARG, "adamw_dev: bad argument");
-  adamw_prep_kernel<<<1, 1, 0, STREAM(stream)>>>(reinterpret_cast<unsigned long long*>(step_counter), lr, beta1, beta2, step_size_scratch);
-  adamw_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(p, g, m, v, n, beta1, beta2, eps, 0.f, step_size_scratch, weight_decay, grad_scale);
+  unpp::launch(adamw_prep_kernel, 1, 1, 0, STREAM(stream), reinterpret_cast<unsigned long long*>(step_counter), lr, beta1, beta2, step_size_scratch);
+  unpp::launch(adamw_kernel, grid_for(n, 256), 256, 0, STREAM(stream), p, g, m, v, n, beta1, beta2, eps, 0.f, step_size_scratch, weight_decay, grad_scale);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("adamw_dev: launch");
   return UNPP_OK;
 }
@@ -596,7 +620,7 @@ extern "C" int unpp_adamw_dev(float* p, const float* g, float* m, float* v, long
 extern "C" int unpp_dropout_mask(uint8_t* mask, long n, float p_drop, uint64_t seed, const uint64_t* step_counter, unpp_stream_t stream) {
   if (!mask || n < 16 || (n & 15) || !(p_drop >= 0.f) || !(p_drop < 1.f)) return unpp::fail(UNPP_ERR_BAD_ARG, "dropout_mask: n must be a positive multiple of 16, 0 <= p < 1");
   const uint32_t thresh = uint32_t(double(p_drop) * 65536.0 + 0.5);
-  dropout_mask_kernel<<<grid_for(n / 16, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<uint4*>(mask), n / 16, uint32_t(seed), uint32_t(seed >> 32),
+  unpp::launch(dropout_mask_kernel, grid_for(n / 16, 256), 256, 0, STREAM(stream), reinterpret_cast<uint4*>(mask), n / 16, uint32_t(seed), uint32_t(seed >> 32),
                                                                          thresh, reinterpret_cast<const unsigned long long*>(step_counter));
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("dropout_mask: launch");
   return UNPP_OK;

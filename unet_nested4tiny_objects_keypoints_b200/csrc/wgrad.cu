@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     tma_prefetch_desc(&p.zmap[blockIdx.z]);
   }
   __syncthreads();
+  unpp::pdl_wait();  // see common.h: the set-up above overlaps the tail of the preceding kernel
+  unpp::pdl_trigger();
 
   auto issue = [&](int tile, int buf) {
     const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
@@ -264,7 +266,7 @@ int launch(const WgradParams& p, const Plan& pl, cudaStream_t stream) {
       return unpp::fail_cuda("wgrad: cudaFuncSetAttribute");
     opted_in = true;
   }
-  wgrad_kernel<TAPS, PPW><<<dim3(pl.grid_x, pl.njobs, pl.grid_z), kThreads, pl.smem_total, stream>>>(p);
+  unpp::launch(wgrad_kernel<TAPS, PPW>, dim3(pl.grid_x, pl.njobs, pl.grid_z), kThreads, pl.smem_total, stream, p);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("wgrad: launch");
   return UNPP_OK;
 }

@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  unpp::pdl_wait();  // see common.h: the set-up above overlaps the tail of the preceding kernel
+  unpp::pdl_trigger();
   const uint32_t tmem_base = tmem_slot;
   const int ntiles = p.ntiles, nx = p.nx, nz = p.nz, nsplit = p.nsplit, ncols = p.ncols;
   const int zspan = p.zspan, TR = p.TR;
@@ -404,7 +406,7 @@ int wgrad_tc_launch(const UnppWgradArgs* a, cudaStream_t stream) {
       return unpp::fail_cuda("wgrad_tc: cudaFuncSetAttribute");
     opted_in = true;
   }
-  wgrad_tc_kernel<<<dim3(pl.grid_x, pl.njobs), kThreads, pl.smem_total, stream>>>(p);
+  unpp::launch(wgrad_tc_kernel, dim3(pl.grid_x, pl.njobs), kThreads, pl.smem_total, stream, p);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("wgrad_tc: launch");
   return UNPP_OK;
 }
