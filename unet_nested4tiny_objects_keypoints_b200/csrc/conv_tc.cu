@@ -868,6 +868,10 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
     }
     // widest tile that leaves room for two stages: fewer tiles (less per-tile handshake), more sub-tiles (more issuers busy)
     int TW = a->W > 32 ? 64 : a->W > 16 ? 32 : 16;
+    if (const char* e = getenv("UNPP_B2_TW")) {  // experiment: cap the tile width (more, smaller stages)
+      const int cap = atoi(e);
+      if ((cap == 16 || cap == 32) && TW > cap) TW = cap;
+    }
     for (;; TW >>= 1) {
       pl->b2_P = TW / 2 + 2;
       pl->stage_bytes = (34 * pl->b2_P * 64 + 1023) / 1024 * 1024;
@@ -892,6 +896,10 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
   pl->w_bytes = a->taps * k8 * a->n_tile * 16;
   pl->w_smem_bytes = (pl->w_bytes + 1023) / 1024 * 1024;
   int TW = 64;
+  if (const char* e = getenv("UNPP_TW")) {  // experiment: cap the tile width (more, smaller stages)
+    const int cap = atoi(e);
+    if (cap == 16 || cap == 32) TW = cap;
+  }
   while (TW > 8 && (2 * (TW / 8) * a->n_tile > 512 || TW / 2 >= ((a->W + 7) / 8) * 8)) TW >>= 1;
   for (;; TW >>= 1) {
     pl->stage_bytes = ((16 + 2 * pad) * (TW + 2 * pad) * max_span + 1023) / 1024 * 1024;
