@@ -10,7 +10,7 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libunpp.so")
+LIB_PATH = os.environ.get("UNPP_LIB") or os.path.join(HERE, "libunpp.so")  # UNPP_LIB: an experimental build of the same library
 
 UNPP_MAX_SRC = 6
 MODE_CONV, MODE_DECONV = 0, 1

@@ -59,6 +59,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef UNPP_POLL_BACKOFF_NS
+    if (spins > 2) __nanosleep(UNPP_POLL_BACKOFF_NS);  // keep the pollers off the shared-memory pipe the tensor core reads through
+#endif
     if (++spins > (1u << 26)) {
       printf("mbar_wait timeout: block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x, (void*)bar, parity);
       __trap();

@@ -385,7 +385,7 @@ def adamw_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_counter, ste
 def dropout_mask(mask: torch.Tensor, p_drop: float, seed: int, step_counter: Optional[torch.Tensor] = None) -> None:
     assert mask.dtype == torch.uint8 and mask.is_cuda and mask.is_contiguous()
     _count()
-    with _Traced("create_heatmap", 0, 0):
+    with _Traced("dropout_mask", 0, 0):
         _lib.check(lib().unpp_dropout_mask(mask.data_ptr(), mask.numel(), float(p_drop), int(seed) & (2**64 - 1), _ptr(step_counter), _stream()),
                "unpp_dropout_mask")
 
