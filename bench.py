@@ -203,7 +203,7 @@ def cpu_reference(steps, warmup, sample_b=4, train=False):
     return sample_b * steps / dt, dt / steps * 1e3, torch.get_num_threads()
 
 
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, rank, world, out):
     if rank != 0:
         return
     train = args.workload == "train"
@@ -215,7 +215,7 @@ def run_reference_arm(args, rank, world):
             "data": "synthetic", "config": config_of(args.workload, world),
             "cpu_baseline": {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(ips, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 def metric_name(workload):
@@ -315,18 +315,21 @@ def bench_train(args, rank, world, local):
     ms = timed(step.step_device, args.steps, world)
     clk = clocks.stop() if rank == 0 else None
     value = b * world * args.steps / (ms * 1e-3)
-    loss_host = torch.empty(1).pin_memory()
+    # end to end through the public API (FusedTrainStep.step_many): every step its images and targets go H2D from pinned
+    # host memory and its loss comes back D2H; the copies of batch k+1 overlap the step of batch k
+    x_hosts = [x_host, torch.randn(b, 3, S, S, generator=g).pin_memory()]
+    t_hosts = [t_host, torch.rand(b, 4, S, S, generator=g).pin_memory()]
+    loss_hosts = [torch.empty(1).pin_memory() for _ in range(2)]
 
-    def e2e_step():
-        loss = step.step(x_host, t_host)
-        loss_host.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    def e2e_run(nsteps):
+        step.step_many([x_hosts[k & 1] for k in range(nsteps)], [t_hosts[k & 1] for k in range(nsteps)], [loss_hosts[k & 1] for k in range(nsteps)])
 
-    for _ in range(2):
-        e2e_step()
-    ms_e2e = timed(e2e_step, args.steps, world)
+    e2e_run(2)
+    torch.cuda.synchronize()
+    ms_e2e = timed(lambda: e2e_run(args.steps), 1, world)
     e2e = {"value": round(b * world * args.steps / (ms_e2e * 1e-3), 1), "unit": "images/s", "h2d_bytes_per_step": (x_host.numel() + t_host.numel()) * 4,
-           "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)}
+           "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3),
+           "pipelining": "H2D of batch k+1 (staging buffers, copy stream) overlaps the step of batch k"}
     line = None
     if rank == 0:
         pk = peaks()
@@ -350,6 +353,17 @@ def bench_train(args, rank, world, local):
 
 
 def main():
+    # Only the JSON line may reach stdout (NCCL and friends print banners there): everything else goes to stderr.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    try:
+        _main(real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -365,7 +379,7 @@ def main():
 
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
-        run_reference_arm(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
+        run_reference_arm(args, rank, int(os.environ.get("WORLD_SIZE", "1")), out)
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -390,7 +404,7 @@ def main():
             line["cpu_baseline"] = None
         if extra is not None:
             line["train_step"] = extra
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

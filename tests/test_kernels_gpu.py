@@ -196,8 +196,9 @@ def test_wgrad_conv3x3(N, H, W, cins, cout):
     close(dst.cpu(), ref, 2e-3, "wgrad")
 
 
-def test_wgrad_deconv_strided_dz():
-    N, H, W, cin, cout = 2, 8, 12, 32, 16
+@pytest.mark.parametrize("N,H,W,cin,cout", [(2, 8, 12, 32, 16), (1, 24, 40, 32, 16), (2, 16, 16, 64, 32), (3, 8, 8, 128, 64), (2, 40, 72, 64, 32),
+                                           (32, 32, 32, 128, 64)])
+def test_wgrad_deconv_strided_dz(N, H, W, cin, cout):
     x = bf(rnd(N, cin, H, W, seed=31))
     du = bf(rnd(N, cout, 2 * H, 2 * W, seed=32))
     w = torch.zeros(cin, cout, 2, 2, dtype=torch.double, requires_grad=True)

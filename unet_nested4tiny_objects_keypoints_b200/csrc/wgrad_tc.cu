@@ -38,6 +38,11 @@
 // 64-channel chunk has only two atoms in M = 128, so it takes two MMAs per K step: start shifts 0 (filter
 // columns 0, 1) and +2 pixels (column 2).
 //
+// Transposed conv k2s2 (taps = 1, dz = [N, 2H, 2W, Cout] read through a stride-2 relation): dW[ci][co][p][q] =
+// sum X[n,y,x,ci] * dU[n, 2y+p, 2x+q, co].  dU is viewed as [N, 2H, W, 2*Cout]: the K row of low-resolution pixel x is
+// the hi-res pixel pair (2x, 2x+1), so the N element inside an atom is (q, co) and the two atoms (leading offset =
+// one hi-res tile row) are p = 0, 1: one MMA per K step yields all four taps (Cout = 64: two boxes, one per q).
+//
 // Shared-memory operand traffic per MMA: 4 KB (A) + 96 * Cout B (B) for 16 K rows, i.e. 224 B per
 // pixel and 16-channel source in the pair view (352 B without it) against 64 B of HBM traffic.
 #include <cstdlib>
@@ -68,6 +73,12 @@ struct Params {
   int zspan;                 // bytes per K row of the dZ tile (= effective slice width * 2)
   int xslot, zslot, nx, nz;  // ring geometry: bytes per slot, slots
   int nsplit, ncols, tmem_cols;
+  // geometry that differs between the 3x3 conv and the transposed-conv form
+  int dc;                    // transposed-conv form
+  int xpx, xorg;             // X box: K rows per tile row (34 / 32), x origin relative to the tile (-1 / 0)
+  int zrows, zy_mul, zy_org; // dZ box: rows, y origin = zy_mul * ty * TR + zy_org
+  int zrow_mul;              // B start row of X row r = zrow_mul * r
+  int nq, zbox_bytes;        // dZ boxes per tile (q halves when 2*Cout > 64) and bytes per box
   float* partial;
 };
 
@@ -113,15 +124,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         {
           const int s = zi % nz;
           mbar_wait(&z_empty[s], ((zi / nz) & 1) ^ 1);
-          mbar_arrive_expect_tx(&z_full[s], uint32_t((TR + 2) * TW * zspan));
-          tma_load_4d(&p.zmap, &z_full[s], zring + size_t(s) * p.zslot, p.pair ? 0 : co0, tx * TW, ty * TR - 1, n);
+          mbar_arrive_expect_tx(&z_full[s], uint32_t(p.nq * p.zrows * TW * zspan));
+          for (int qb = 0; qb < p.nq; ++qb)
+            tma_load_4d(&p.zmap, &z_full[s], zring + size_t(s) * p.zslot + size_t(qb) * p.zbox_bytes, p.dc ? qb * (zspan >> 1) : (p.pair ? 0 : co0),
+                        tx * TW, p.zy_mul * ty * TR + p.zy_org, n);
           ++zi;
         }
         for (int k = 0; k < nch; ++k, ++xi) {
           const int s = xi % nx, c = ch0 + k;
           mbar_wait(&x_empty[s], ((xi / nx) & 1) ^ 1);
-          mbar_arrive_expect_tx(&x_full[s], uint32_t(TR * PX * p.ch_C[c] * 2));
-          tma_load_4d(&p.xmap[p.ch_map[c]], &x_full[s], xring + size_t(s) * p.xslot, p.ch_c0[c], tx * TW - 1, ty * TR, n);
+          mbar_arrive_expect_tx(&x_full[s], uint32_t(TR * p.xpx * p.ch_C[c] * 2));
+          tma_load_4d(&p.xmap[p.ch_map[c]], &x_full[s], xring + size_t(s) * p.xslot, p.ch_c0[c], tx * TW + p.xorg, ty * TR, n);
         }
       }
     }
@@ -136,7 +149,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     int spans[kMaxChunks];
 #pragma unroll
     for (int k = 0; k < kMaxChunks; ++k) spans[k] = ch0 + k < kMaxChunks ? p.ch_C[ch0 + k] * 2 : 0;
-    const uint32_t z_row = uint32_t(TW * zspan) >> 4, z_seg = uint32_t(16 * zspan) >> 4;
+    const uint32_t z_row = uint32_t(p.zrow_mul * TW * zspan) >> 4, z_seg = uint32_t(16 * zspan) >> 4;
+    const int dc = p.dc, xpx = p.xpx, nq = p.nq;
+    const uint32_t zbox16 = uint32_t(p.zbox_bytes) >> 4;
     int xi = 0, zi = 0, tile_it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it, ++zi) {
       const int zs = zi % nz;
@@ -151,22 +166,24 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
 #pragma unroll
         for (int kk = 1; kk < kMaxChunks; ++kk)
           if (kk == k) span = spans[kk];
-        const int nm = span == 128 ? 2 : 1;  // 64-channel chunk: two atoms per MMA, two MMAs per K step
+        // MMAs per K step: 3x3 with a 64-channel chunk = two atoms per MMA, so two start shifts; transposed conv = one per dZ box
+        const int nm = dc ? nq : (span == 128 ? 2 : 1);
         mbar_wait(&x_full[xs], (xi / nx) & 1);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t ad = make_sdesc(xring_a + uint32_t(xs) * xslot, uint32_t(span), uint32_t(8 * span), layout_of_span(span));
           const uint32_t a_hi = uint32_t(ad >> 32), a_lo = uint32_t(ad);
-          const uint32_t x_row = uint32_t(PX * span) >> 4, x_seg = uint32_t(16 * span) >> 4;
+          const uint32_t x_row = uint32_t(xpx * span) >> 4, x_seg = uint32_t(16 * span) >> 4;
           for (int mi = 0; mi < nm; ++mi) {
             for (int h = 0; h < nsplit; ++h) {
               const int a = (acc0 + mi) * nsplit + h;
               if (a % kIssuers != w) continue;
               const uint32_t acc = tmem_base + uint32_t(a * ncols);
-              const uint32_t a_mi = a_lo + (uint32_t(mi * 2 * span) >> 4);  // second MMA: the row shifted by two more pixels
+              const uint32_t a_mi = a_lo + (dc ? 0u : (uint32_t(mi * 2 * span) >> 4));  // 3x3, second MMA: the row shifted by two more pixels
+              const uint32_t b_mi = b_lo + (dc ? uint32_t(mi) * zbox16 : 0u);           // transposed conv: the dZ box of q = mi
               uint32_t accum = tile_it ? 1u : 0u;
               for (int row = h; row < TR; row += nsplit) {
-                const uint32_t ar = a_mi + uint32_t(row) * x_row, br = b_lo + uint32_t(row) * z_row;
+                const uint32_t ar = a_mi + uint32_t(row) * x_row, br = b_mi + uint32_t(row) * z_row;
 #pragma unroll
                 for (int seg = 0; seg < TW / 16; ++seg) {
                   umma_bf16(acc, (uint64_t(a_hi) << 32) | (ar + uint32_t(seg) * x_seg), (uint64_t(b_hi) << 32) | (br + uint32_t(seg) * z_seg), idesc,
@@ -205,11 +222,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     for (int k = 0; k < nch; ++k) {
       const int c = ch0 + k;
       const int C = p.ch_C[c];  // effective width of an atom
-      const int nm = C == 64 ? 2 : 1;
+      const int nm = p.dc ? p.nq : (C == 64 ? 2 : 1);
       for (int mi = 0; mi < nm; ++mi) {
         const int a0 = (acc0 + mi) * nsplit;
-        const int j = m / C + 2 * mi;   // filter column (pair view: pair shift)
-        const int lanes_used = nm == 2 ? (mi ? 64 : 128) : 3 * C;
+        const int j = p.dc ? (m / C ? 3 : 0) : m / C + 2 * mi;   // filter column (pair view: pair shift); transposed conv: atom 0 only
+        const int lanes_used = p.dc ? C : (nm == 2 ? (mi ? 64 : 128) : 3 * C);
         if (q * 32 >= lanes_used) continue;  // warp-uniform: this lane quadrant only holds discarded shifts
         const int e = pair ? ((m >> 4) & 1) : 0, ci = pair ? (m & 15) : m % C;
         for (int g = half; g < ngroups; g += 2) {
@@ -222,6 +239,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
             tmem_ld_wait16(raw);
 #pragma unroll
             for (int t = 0; t < 16; ++t) v[t] += __uint_as_float(raw[t]);
+          }
+          if (p.dc) {  // column = (p, q, co) [one box] or (p, co) with q = mi [two boxes]; partial is [4 (2p+q)][grid][cin][cout]
+            if (j == 0) {
+              const int pp = (g * 16) / ecout, within = (g * 16) % ecout;
+              const int qq = p.nq == 2 ? mi : within / cout, cc0 = p.nq == 2 ? within : within % cout;
+              float4* dst = reinterpret_cast<float4*>(p.partial + (size_t(2 * pp + qq) * gridDim.x + blockIdx.x) * p.cin_total * cout +
+                                                      size_t(p.ch_cioff[c] + ci) * cout + cc0);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) dst[t] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+            }
+            continue;
           }
           int i, col0, sft, slot = 0;
           if (pair) {  // column group = (dZ row shift i, parity e'); tap column = e - e' + 2j - 1
@@ -266,6 +294,7 @@ struct Plan {
   bool ok;
   int cin_total, xslot, zslot, nx, nz, nsplit, ncols, tmem_cols, smem_total, tiles_x, tiles_y, ntiles, grid_x;
   int TR, pair, ecout, We;  // tile rows; pixel-pair view; effective output slice width; K rows per image row
+  int dc, nq;               // transposed-conv form; dZ boxes per tile
   int nchunks, njobs;
   int box_C[UNPP_MAX_SRC];  // channels per TMA box of each source (effective)
   int ch_map[kMaxChunks], ch_c0[kMaxChunks], ch_C[kMaxChunks], ch_cioff[kMaxChunks];
@@ -276,8 +305,10 @@ CUtensorMapSwizzle swizzle_of(int channels) { return channels == 64 ? CU_TENSOR_
 
 void make_plan(const UnppWgradArgs* a, Plan* pl) {
   pl->ok = false;
-  if (a->taps != 9 || a->dz_step != 1) return;
+  const bool dc = a->taps == 1 && a->dz_step == 2 && a->dz_oy < 0;  // the four taps of a k2s2 transposed conv in one launch
+  if (!dc && (a->taps != 9 || a->dz_step != 1)) return;
   if (a->cout != 16 && a->cout != 32 && a->cout != 64 && a->cout != 128) return;
+  if (dc && (a->cout > 64 || a->nsrc != 1)) return;
   bool all16 = a->cout == 16, wide = a->cout > 32;
   for (int i = 0; i < a->nsrc; ++i) {
     const int C = a->src_C[i];
@@ -285,10 +316,17 @@ void make_plan(const UnppWgradArgs* a, Plan* pl) {
     all16 = all16 && C == 16;
     wide = wide || C > 32;
   }
-  pl->pair = (all16 && !(a->W & 1) && a->nsrc * 96 <= 512) ? 1 : 0;
-  pl->ecout = pl->pair ? 32 : (a->cout > 64 ? 64 : a->cout);
+  pl->dc = dc ? 1 : 0, pl->nq = 1;
+  pl->pair = (!dc && all16 && !(a->W & 1) && a->nsrc * 96 <= 512) ? 1 : 0;
+  if (dc) {  // dZ rows are hi-res pixel PAIRS: 2*Cout elements, at most 64 per box
+    pl->ecout = 2 * a->cout > 64 ? 64 : 2 * a->cout;
+    pl->nq = 2 * a->cout / pl->ecout;
+    pl->ncols = 2 * pl->ecout;
+  } else {
+    pl->ecout = pl->pair ? 32 : (a->cout > 64 ? 64 : a->cout);
+    pl->ncols = 3 * pl->ecout;
+  }
   pl->We = pl->pair ? a->W / 2 : a->W;
-  pl->ncols = 3 * pl->ecout;
   // chunks
   int off = 0, nchunks = 0, maxc = 0;
   for (int i = 0; i < a->nsrc; ++i) {
@@ -303,9 +341,12 @@ void make_plan(const UnppWgradArgs* a, Plan* pl) {
     off += C;
   }
   pl->cin_total = off, pl->nchunks = nchunks;
-  // jobs: narrow layers = one job with every chunk; wide layers = one job per (chunk, output slice)
+  // jobs: narrow 3x3 layers = one job with every chunk; wide layers = one job per (chunk, output slice); transposed conv = one per chunk
   int njobs = 0, max_acc = 0;
-  if (!wide) {
+  if (dc) {
+    for (int c = 0; c < nchunks; ++c) pl->job_ch0[njobs] = c, pl->job_nch[njobs] = 1, pl->job_co0[njobs] = 0, ++njobs;
+    max_acc = pl->nq;
+  } else if (!wide) {
     pl->job_ch0[0] = 0, pl->job_nch[0] = nchunks, pl->job_co0[0] = 0;
     njobs = 1, max_acc = nchunks;
   } else {
@@ -325,10 +366,12 @@ void make_plan(const UnppWgradArgs* a, Plan* pl) {
   int need = max_acc * pl->nsplit * pl->ncols, tc = 32;
   while (tc < need) tc <<= 1;
   pl->tmem_cols = tc;
-  const int TR = (maxc == 64 || pl->ecout == 64) ? 8 : 16;
+  int TR = (maxc == 64 || pl->ecout == 64) ? 8 : 16;
+  if (dc) TR = 16 / (pl->ecout / 32) / pl->nq;  // keeps the dZ slot (2*TR hi-res rows per box) at 64 KB
   pl->TR = TR;
-  pl->xslot = (TR * PX * maxc * 2 + 1023) / 1024 * 1024;
-  pl->zslot = ((TR + 2) * TW * pl->ecout * 2 + 1023) / 1024 * 1024;
+  const int xpx = dc ? TW : PX, zrows = dc ? 2 * TR : TR + 2;
+  pl->xslot = (TR * xpx * maxc * 2 + 1023) / 1024 * 1024;
+  pl->zslot = pl->nq * ((zrows * TW * pl->ecout * 2 + 1023) / 1024 * 1024);
   const int budget = 212 * 1024;
   pl->nz = pl->zslot <= 20 * 1024 ? 3 : 2;
   pl->nx = (budget - pl->nz * pl->zslot) / pl->xslot;
@@ -378,16 +421,18 @@ int wgrad_tc_launch(const UnppWgradArgs* a, cudaStream_t stream) {
     const cuuint64_t C = pl.pair ? 32 : a->src_C[i];  // channels per K row of the tensor as TMA sees it
     cuuint64_t gd[4] = {C, cuuint64_t(pl.We), cuuint64_t(a->H), cuuint64_t(a->N)};
     cuuint64_t gs[3] = {C * 2, cuuint64_t(pl.We) * C * 2, cuuint64_t(a->H) * pl.We * C * 2};
-    cuuint32_t box[4] = {cuuint32_t(pl.box_C[i]), cuuint32_t(PX), cuuint32_t(pl.TR), 1};
+    cuuint32_t box[4] = {cuuint32_t(pl.box_C[i]), cuuint32_t(pl.dc ? TW : PX), cuuint32_t(pl.TR), 1};
     CUresult r = enc(&p.xmap[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->src[i]), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swizzle_of(pl.box_C[i]), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled failed (CUresult %d) for source %d", int(r), i);
   }
   {
-    const cuuint64_t C = pl.pair ? 32 : a->cout;
-    cuuint64_t gd[4] = {C, cuuint64_t(pl.We), cuuint64_t(a->H), cuuint64_t(a->N)};
-    cuuint64_t gs[3] = {C * 2, cuuint64_t(pl.We) * C * 2, cuuint64_t(a->H) * pl.We * C * 2};
-    cuuint32_t box[4] = {cuuint32_t(pl.ecout), cuuint32_t(TW), cuuint32_t(pl.TR + 2), 1};
+    // 3x3: dZ [N,H,W,Cout] (pair view: [N,H,W/2,32]); transposed conv: dU [N,2H,2W,Cout] viewed as [N,2H,W,2*Cout]
+    const cuuint64_t C = pl.dc ? 2 * a->cout : (pl.pair ? 32 : a->cout);
+    const cuuint64_t Hz = pl.dc ? 2 * a->H : a->H;
+    cuuint64_t gd[4] = {C, cuuint64_t(pl.We), Hz, cuuint64_t(a->N)};
+    cuuint64_t gs[3] = {C * 2, cuuint64_t(pl.We) * C * 2, Hz * pl.We * C * 2};
+    cuuint32_t box[4] = {cuuint32_t(pl.ecout), cuuint32_t(TW), cuuint32_t(pl.dc ? 2 * pl.TR : pl.TR + 2), 1};
     CUresult r = enc(&p.zmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a->dz), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swizzle_of(pl.ecout), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled failed (CUresult %d) for dZ", int(r));
@@ -399,6 +444,10 @@ int wgrad_tc_launch(const UnppWgradArgs* a, cudaStream_t stream) {
   p.pair = pl.pair, p.zspan = pl.ecout * 2, p.TR = pl.TR;
   p.xslot = pl.xslot, p.zslot = pl.zslot, p.nx = pl.nx, p.nz = pl.nz;
   p.nsplit = pl.nsplit, p.ncols = pl.ncols, p.tmem_cols = pl.tmem_cols;
+  p.dc = pl.dc, p.nq = pl.nq;
+  p.xpx = pl.dc ? TW : PX, p.xorg = pl.dc ? 0 : -1;
+  p.zrows = pl.dc ? 2 * pl.TR : pl.TR + 2, p.zy_mul = pl.dc ? 2 : 1, p.zy_org = pl.dc ? 0 : -1, p.zrow_mul = pl.dc ? 2 : 1;
+  p.zbox_bytes = pl.zslot / pl.nq;
   p.partial = a->partial;
   static bool opted_in = false;  // the attribute is idempotent
   if (!opted_in) {

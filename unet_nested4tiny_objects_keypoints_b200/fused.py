@@ -269,6 +269,46 @@ class FusedTrainStep:
         self.target.copy_(target_host, non_blocking=True)
         return self.step_device()
 
+    def step_many(self, x_hosts, target_hosts, loss_hosts=None) -> int:
+        """Pipelined training over a list of pinned host batches: the H2D copy of batch k+1 (into staging buffers, on a
+        copy stream) overlaps the step of batch k; a device-to-device copy (~0.1 ms) moves the staged batch into the
+        fixed-address inputs the captured step reads.  ``loss_hosts``: optional pinned [1] tensors receiving each loss.
+        Returns after everything is enqueued; the caller synchronises the current stream."""
+        cur = torch.cuda.current_stream(self.dev)
+        if not hasattr(self, "_stage"):
+            self._stage = [(torch.empty_like(self.x), torch.empty_like(self.target)) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(self.dev)
+        cs = self._copy_stream
+        cs.wait_stream(cur)
+        h2d = [torch.cuda.Event(), torch.cuda.Event()]
+        taken = [None, None]
+        n = len(x_hosts)
+
+        def prefetch(k):
+            i = k & 1
+            with torch.cuda.stream(cs):
+                if taken[i] is not None:
+                    cs.wait_event(taken[i])  # the staged batch has been moved into the step's inputs
+                self._stage[i][0].copy_(x_hosts[k], non_blocking=True)
+                self._stage[i][1].copy_(target_hosts[k], non_blocking=True)
+                h2d[i].record(cs)
+
+        if n:
+            prefetch(0)
+        for k in range(n):
+            i = k & 1
+            cur.wait_event(h2d[i])
+            self.x.copy_(self._stage[i][0], non_blocking=True)
+            self.target.copy_(self._stage[i][1], non_blocking=True)
+            taken[i] = torch.cuda.Event()
+            taken[i].record(cur)
+            if k + 1 < n:
+                prefetch(k + 1)
+            loss = self.step_device()
+            if loss_hosts is not None:
+                loss_hosts[k].copy_(loss, non_blocking=True)
+        return n
+
     def step_keypoints(self, x_host: torch.Tensor, keypoints_host: torch.Tensor) -> torch.Tensor:
         """The trainer's step with its target synthesis on the device: where trainer/trainer.py:122-123 builds the
         heat-map targets on the CPU with numpy every iteration (helper.create_heatmap), the key points [B,7,2] go
