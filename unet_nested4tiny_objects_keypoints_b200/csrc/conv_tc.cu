@@ -275,56 +275,60 @@ __device__ __forceinline__ void epilogue_group(const EpiArgs& p, float (&v)[16],
 }
 
 // ---------------------------------------------------------------------------------------------
-// Epilogue of the 2x2 output-blocked path.  A thread owns one 2x2 block (accumulator row); the two warps of a lane
-// quadrant take the upper / lower pixel row of the blocks (dy), so one step = the 32 accumulator columns of the two
-// horizontally adjacent pixels (x0, x0 + 1) = 64 contiguous bytes of every NHWC16 operand and of the output.
-struct B2Operands {  // training-only operands of the two pixels, fetched BEFORE the TMEM load is waited for
-  uint4 a[4], m[4], x[4], d[2];
+// Lean epilogue step: G groups of 16 accumulator columns whose outputs (and training operands) are 32*G contiguous bytes.
+//   G = 2: the 2x2 output-blocked path.  A thread owns one 2x2 block (accumulator row); the two warps of a lane quadrant
+//          take the upper / lower pixel row of the blocks, so a step = the two horizontally adjacent pixels (x0, x0 + 1).
+//   G = 1: the classic path with <= 32 GEMM columns per CTA: a step = 16 channels of one pixel.
+// `eoff` = element offset of the step's first value in the NHWC output (and in every same-shaped operand).
+template <int G>
+struct EpiOperands {  // training-only operands of the step, fetched BEFORE the TMEM load is waited for
+  uint4 a[2 * G], m[2 * G], x[2 * G], d[G];
 };
-template <bool HEAD, bool TRAIN>
-__device__ __forceinline__ void b2_prefetch(const EpiArgs& p, B2Operands& t, size_t pix0, bool valid) {
+template <int G, bool HEAD, bool TRAIN>
+__device__ __forceinline__ void epi_prefetch(const EpiArgs& p, EpiOperands<G>& t, size_t eoff, bool valid) {
   if constexpr (TRAIN) {
     const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) t.a[i] = t.m[i] = t.x[i] = z;
-    t.d[0] = t.d[1] = z;
-    if (valid) {
-      const size_t off = pix0 * 16;
-      if (p.addend) {
-        const uint4* q = reinterpret_cast<const uint4*>(p.addend + off);
+    for (int i = 0; i < 2 * G; ++i) t.a[i] = t.m[i] = t.x[i] = z;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) t.a[i] = __ldg(q + i);
+    for (int i = 0; i < G; ++i) t.d[i] = z;
+    if (valid) {
+      if (p.addend) {
+        const uint4* q = reinterpret_cast<const uint4*>(p.addend + eoff);
+#pragma unroll
+        for (int i = 0; i < 2 * G; ++i) t.a[i] = __ldg(q + i);
       }
       if (p.relu_mask_src) {
-        const uint4* q = reinterpret_cast<const uint4*>(p.relu_mask_src + off);
+        const uint4* q = reinterpret_cast<const uint4*>(p.relu_mask_src + eoff);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) t.m[i] = __ldg(q + i);
+        for (int i = 0; i < 2 * G; ++i) t.m[i] = __ldg(q + i);
       }
       if (p.stats_aux) {
-        const uint4* q = reinterpret_cast<const uint4*>(p.stats_aux + off);
+        const uint4* q = reinterpret_cast<const uint4*>(p.stats_aux + eoff);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) t.x[i] = __ldg(q + i);
+        for (int i = 0; i < 2 * G; ++i) t.x[i] = __ldg(q + i);
       }
       if constexpr (HEAD) {
         if (p.drop_mask) {
-          const uint4* q = reinterpret_cast<const uint4*>(p.drop_mask + off);
-          t.d[0] = __ldg(q), t.d[1] = __ldg(q + 1);
+          const uint4* q = reinterpret_cast<const uint4*>(p.drop_mask + eoff);  // (the head conv has 16 channels: element offset = byte offset)
+#pragma unroll
+          for (int i = 0; i < G; ++i) t.d[i] = __ldg(q + i);
         }
       }
     }
   }
 }
 
-template <bool HEAD, bool TRAIN>
-__device__ __forceinline__ void b2_finish(const EpiArgs& p, const uint32_t (&raw)[32], const B2Operands& t, const float (&bias_r)[16], const float* s_bias,
-                                          const float* s_head, bool relu, size_t pix0, bool valid, int n, int yy, int x0, float (&sa1)[16],
-                                          float (&sa2)[16]) {
-  uint32_t words[16];
-  float hv[2][16];  // post-activation values of the two pixels (fused head only)
+template <int G, bool HEAD, bool TRAIN>
+__device__ __forceinline__ void epi_finish(const EpiArgs& p, const uint32_t (&raw)[16 * G], const EpiOperands<G>& t, const float (&bias_r)[16], const float* s_bias,
+                                           const float* s_head, bool relu, size_t eoff, bool valid, int n, int yy, int x0, float (&sa1)[16],
+                                           float (&sa2)[16]) {
+  uint32_t words[8 * G];
+  float hv[HEAD ? G : 1][16];  // post-activation values of the pixels (fused head only)
 #pragma unroll
-  for (int px = 0; px < 2; ++px) {
+  for (int px = 0; px < G; ++px) {
     float v[16];
-    if (p.bias9) {  // (row class, column class) bias table of the fused transposed conv
+    if (G == 2 && p.bias9) {  // (row class, column class) bias table of the fused transposed conv
       const int x = x0 + px;
       const int boff = (((yy == 0) ? 0 : (yy == p.H - 1 ? 2 : 1)) * 3 + ((x == 0) ? 0 : (x == p.W - 1 ? 2 : 1))) * 16;
       const float4* b4 = reinterpret_cast<const float4*>(s_bias + boff);
@@ -394,11 +398,11 @@ __device__ __forceinline__ void b2_finish(const EpiArgs& p, const uint32_t (&raw
   }
   if (!valid) return;
   if (p.out) {
-    uint8_t* op = reinterpret_cast<uint8_t*>(p.out + pix0 * 16);
-    st_global_v8(op, words);
-    st_global_v8(op + 32, words + 8);
+    uint8_t* op = reinterpret_cast<uint8_t*>(p.out + eoff);
+#pragma unroll
+    for (int px = 0; px < G; ++px) st_global_v8(op + 32 * px, words + 8 * px);
   }
-  if constexpr (HEAD) {
+  if constexpr (HEAD && G == 2) {
     const size_t plane = size_t(p.H) * p.W;
     size_t o = size_t(n) * p.head_classes * plane + size_t(yy) * p.W + x0;
     for (int cls = 0; cls < p.head_classes; ++cls, o += plane) {
@@ -408,12 +412,12 @@ __device__ __forceinline__ void b2_finish(const EpiArgs& p, const uint32_t (&raw
       for (int k = 0; k < 4; ++k) {
         const float4 w = w4[k];
         a0 = fmaf(w.x, hv[0][4 * k], a0), a0 = fmaf(w.y, hv[0][4 * k + 1], a0), a0 = fmaf(w.z, hv[0][4 * k + 2], a0), a0 = fmaf(w.w, hv[0][4 * k + 3], a0);
-        a1 = fmaf(w.x, hv[1][4 * k], a1), a1 = fmaf(w.y, hv[1][4 * k + 1], a1), a1 = fmaf(w.z, hv[1][4 * k + 2], a1), a1 = fmaf(w.w, hv[1][4 * k + 3], a1);
+        a1 = fmaf(w.x, hv[G - 1][4 * k], a1), a1 = fmaf(w.y, hv[G - 1][4 * k + 1], a1), a1 = fmaf(w.z, hv[G - 1][4 * k + 2], a1), a1 = fmaf(w.w, hv[G - 1][4 * k + 3], a1);
       }
       if constexpr (TRAIN) {
         if (p.logit) *reinterpret_cast<float2*>(p.logit + o) = make_float2(a0, a1);
       }
-      *reinterpret_cast<float2*>(p.heat + o) = make_float2(1.f / (1.f + __expf(-a0)), 1.f / (1.f + __expf(-a1)));
+      *reinterpret_cast<float2*>(p.heat + o) = make_float2(__fdividef(1.f, 1.f + __expf(-a0)), __fdividef(1.f, 1.f + __expf(-a1)));
     }
   }
 }
@@ -698,27 +702,73 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
             for (int j = 0; j < nsub; ++j) {
               const int x0 = xb + j * 16;
               const bool valid = row_ok && x0 < e.W;
-              B2Operands tops;
+              EpiOperands<2> tops;
               tmem_ld32(tcol + uint32_t(j * 64), A);
-              b2_prefetch<HEAD, TRAIN>(e, tops, rowpix + x0, valid);
+              epi_prefetch<2, HEAD, TRAIN>(e, tops, (rowpix + x0) * 16, valid);
               tmem_ld_wait32(A);
-              b2_finish<HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, rowpix + x0, valid, n, yy, x0, sa1, sa2);
+              epi_finish<2, HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix + x0) * 16, valid, n, yy, x0, sa1, sa2);
             }
           } else {  // two TMEM buffers: the load of the next step is in flight while this one is finished
             uint32_t A[32], B[32];
-            B2Operands tops;
+            EpiOperands<2> tops;
             tmem_ld32(tcol, A);
             for (int j = 0; j < nsub; j += 2) {
               const int x0 = xb + j * 16;
               tmem_ld_wait32(A);
               if (j + 1 < nsub) tmem_ld32(tcol + uint32_t((j + 1) * 64), B);
-              b2_finish<HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, rowpix + x0, row_ok && x0 < e.W, n, yy, x0, sa1, sa2);
+              epi_finish<2, HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix + x0) * 16, row_ok && x0 < e.W, n, yy, x0, sa1, sa2);
               if (j + 1 < nsub) {
                 tmem_ld_wait32(B);
                 if (j + 2 < nsub) tmem_ld32(tcol + uint32_t((j + 2) * 64), A);
-                b2_finish<HEAD, TRAIN>(e, B, tops, bias_r, s_bias, s_head, relu, rowpix + x0 + 16, row_ok && x0 + 16 < e.W, n, yy, x0 + 16, sa1, sa2);
+                epi_finish<2, HEAD, TRAIN>(e, B, tops, bias_r, s_bias, s_head, relu, (rowpix + x0 + 16) * 16, row_ok && x0 + 16 < e.W, n, yy, x0 + 16, sa1, sa2);
               }
             }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+      }
+    } else if (!DECONV && !HEAD && (ncb <= 2 || (!TRAIN && (ncb == 4 || ncb == 8)))) {
+      // classic path, a step = 16 channels of one pixel = 32 contiguous bytes.  With <= 32 GEMM columns per CTA (the
+      // 32-channel level, 16-channel dgrads) every unit of this warp has the same 16 channels, so bias and statistics
+      // live in registers; wider CTAs (inference only here) re-read the 16 bias values of the step from shared memory.
+      const bool fixed_c = ncb <= 2;
+      const int ncb_shift = ncb == 8 ? 3 : ncb == 4 ? 2 : ncb == 2 ? 1 : 0;  // ncols is 16 << ncb_shift on this path (see the guard below)
+      float bias_r[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) bias_r[k] = fixed_c ? s_bias[(half % ncb) * 16 + k] : 0.f;
+      const bool relu = p.relu != 0;
+      const int nit = (units - half + 1) / 2;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+        const int b = tile_it % nacc, aph = (tile_it / nacc) & 1;
+        const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+        mbar_wait(&bar_acc_full[b], aph);
+        tc_fence_after();
+        const int yy = ty * 16 + pi, xb = tx * TW + pj;
+        const bool row_ok = yy < e.H;
+        const size_t rowpix = (size_t(n) * e.H + yy) * e.W;
+        const uint32_t tcol = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * nsub * ncols);
+        if (!(dbg & 1)) {
+          uint32_t A[16];
+          EpiOperands<1> tops;
+          for (int it = 0; it < nit; ++it) {
+            const int u = half + 2 * it, j = u >> ncb_shift, c0 = (u & (ncb - 1)) * 16;  // unit = (sub-tile, 16-column group)
+            const int x0 = xb + j * 8;
+            const bool valid = row_ok && x0 < e.W;
+            const size_t eoff = (rowpix + x0) * e.cout + ntile_idx * ncols + c0;
+            tmem_ld16(tcol + uint32_t(j * ncols + c0), A);
+            epi_prefetch<1, false, TRAIN>(e, tops, eoff, valid);
+            if (!fixed_c) {
+              const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float4 bb = b4[k];
+                bias_r[4 * k] = bb.x, bias_r[4 * k + 1] = bb.y, bias_r[4 * k + 2] = bb.z, bias_r[4 * k + 3] = bb.w;
+              }
+            }
+            tmem_ld_wait16(A);
+            epi_finish<1, false, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, eoff, valid, n, yy, x0, sa1, sa2);
           }
         }
         tc_fence_before();
