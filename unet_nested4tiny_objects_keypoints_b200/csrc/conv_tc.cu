@@ -729,11 +729,11 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
       }
-    } else if (!DECONV && !HEAD && (ncb <= 2 || (!TRAIN && (ncb == 4 || ncb == 8)))) {
+    } else if (!HEAD && ((!DECONV && ncb <= 2) || (!TRAIN && (ncb == 1 || ncb == 2 || ncb == 4 || ncb == 8)))) {
       // classic path, a step = 16 channels of one pixel = 32 contiguous bytes.  With <= 32 GEMM columns per CTA (the
       // 32-channel level, 16-channel dgrads) every unit of this warp has the same 16 channels, so bias and statistics
       // live in registers; wider CTAs (inference only here) re-read the 16 bias values of the step from shared memory.
-      const bool fixed_c = ncb <= 2;
+      const bool fixed_c = !DECONV && ncb <= 2;
       const int ncb_shift = ncb == 8 ? 3 : ncb == 4 ? 2 : ncb == 2 ? 1 : 0;  // ncols is 16 << ncb_shift on this path (see the guard below)
       float bias_r[16];
 #pragma unroll
@@ -756,11 +756,19 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
             const int u = half + 2 * it, j = u >> ncb_shift, c0 = (u & (ncb - 1)) * 16;  // unit = (sub-tile, 16-column group)
             const int x0 = xb + j * 8;
             const bool valid = row_ok && x0 < e.W;
-            const size_t eoff = (rowpix + x0) * e.cout + ntile_idx * ncols + c0;
+            size_t eoff;
+            int boff = c0;
+            if constexpr (DECONV) {  // scatter: GEMM column = (2p + q) * Cout + co -> output pixel (2y + p, 2x + q) of the [N, 2H, 2W, Cout] tensor
+              const int gcol = ntile_idx * ncols + c0, pq = gcol / e.cout;
+              boff = gcol - pq * e.cout;
+              eoff = ((size_t(n) * (2 * e.H) + (2 * yy + (pq >> 1))) * (2 * e.W) + (2 * x0 + (pq & 1))) * e.cout + boff;
+            } else {
+              eoff = (rowpix + x0) * e.cout + ntile_idx * ncols + c0;
+            }
             tmem_ld16(tcol + uint32_t(j * ncols + c0), A);
             epi_prefetch<1, false, TRAIN>(e, tops, eoff, valid);
             if (!fixed_c) {
-              const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
+              const float4* b4 = reinterpret_cast<const float4*>(s_bias + boff);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const float4 bb = b4[k];
