@@ -142,3 +142,48 @@ def test_fused_train_step_from_keypoints_builds_targets_on_the_device():
     assert float((step.target.cpu() - target).abs().max()) <= 2e-6
     rl, _, _, _ = O.train_step_grads(sd, x, target, dropout_masks=None)
     assert abs(float(loss) - float(rl)) <= 1e-2 * float(rl)
+
+
+def test_pipelined_sessions_equal_the_sequential_calls():
+    """run_many / step_many overlap the H2D copy of batch k+1 with the kernels of batch k: same results, bit for bit."""
+    sd = O.synth_state_dict(seed=35)
+    g = torch.Generator().manual_seed(10)
+    B, H, W, K = 2, 32, 32, 5
+    xs = [torch.randn(B, 3, H, W, generator=g).pin_memory() for _ in range(K)]
+    ts = [torch.rand(B, 4, H, W, generator=g).pin_memory() for _ in range(K)]
+    # inference
+    m = pkg.UNet_Nested()
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    sess = fused.InferenceSession(m, B, H, W, head=2)
+    seq = []
+    for x in xs:
+        xy, val = sess.run(x)
+        torch.cuda.synchronize()
+        seq.append((xy.cpu().clone(), val.cpu().clone()))
+    xy_h = [torch.empty(B, 4, 2, dtype=torch.int32).pin_memory() for _ in range(K)]
+    val_h = [torch.empty(B, 4, dtype=torch.float32).pin_memory() for _ in range(K)]
+    assert sess.run_many(xs, xy_h, val_h) == K
+    torch.cuda.synchronize()
+    for k in range(K):
+        assert torch.equal(xy_h[k], seq[k][0]) and torch.equal(val_h[k], seq[k][1]), k
+    # training: two identical models, one stepped sequentially, one through the pipeline
+    losses = []
+    for mode in ("seq", "pipe"):
+        mt = pkg.UNet_Nested()
+        mt.load_state_dict(sd)
+        mt = mt.cuda().train()
+        mt.drop_out.p = 0.0
+        step = fused.FusedTrainStep(mt, B, H, W, lr=1e-3)
+        if mode == "seq":
+            out = []
+            for x, t in zip(xs, ts):
+                out.append(float(step.step(x, t)))
+        else:
+            lh = [torch.empty(1).pin_memory() for _ in range(K)]
+            assert step.step_many(xs, ts, lh) == K
+            torch.cuda.synchronize()
+            out = [float(l) for l in lh]
+        losses.append((out, step.flat_p.clone()))
+    assert losses[0][0] == losses[1][0]
+    assert torch.equal(losses[0][1], losses[1][1])
