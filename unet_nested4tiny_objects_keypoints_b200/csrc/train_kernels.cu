@@ -175,7 +175,22 @@ __global__ void bn_relu_kernel(const uint4* __restrict__ z, const float* __restr
                                long total, int C8) {
   unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
   unpp::pdl_trigger();
-  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+  const long stride = long(gridDim.x) * blockDim.x, i0 = blockIdx.x * long(blockDim.x) + threadIdx.x;
+  if (stride % C8 == 0) {  // the thread keeps its eight channels for the whole loop: their coefficients live in registers
+    const int c0 = int(i0 % C8) * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sc[k] = __ldg(scale + c0 + k), sh[k] = __ldg(shift + c0 + k);
+    for (long i = i0; i < total; i += stride) {
+      float f[8];
+      unpack8(__ldg(z + i), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
+      y[i] = pack8(f);
+    }
+    return;
+  }
+  for (long i = i0; i < total; i += stride) {
     const int c0 = int(i % C8) * 8;
     float f[8];
     unpack8(__ldg(z + i), f);
@@ -267,7 +282,29 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dyh, const uint4* 
   unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
   unpp::pdl_trigger();
   const int C = C8 * 8;
-  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+  const long stride = long(gridDim.x) * blockDim.x, i0 = blockIdx.x * long(blockDim.x) + threadIdx.x;
+  if (stride % C8 == 0) {
+    // The thread keeps its eight channels for the whole loop: dz = a*dyh + b*z + c with per-channel coefficients in registers
+    //   a = gamma*istd, b = -gamma*istd^2*s2/M, c = gamma*istd*(mean*istd*s2/M - s1/M).
+    const int c0 = int(i0 % C8) * 8;
+    float ca[8], cb[8], cc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c0 + k;
+      const float is = __ldg(istd + c), gm = __ldg(gamma + c) * is, s1 = __ldg(sums + c) * inv_count, s2 = __ldg(sums + C + c) * inv_count;
+      ca[k] = gm, cb[k] = -gm * is * s2, cc[k] = gm * (__ldg(mean + c) * is * s2 - s1);
+    }
+    for (long i = i0; i < total; i += stride) {
+      float g[8], zz[8], o[8];
+      unpack8(__ldg(dyh + i), g);
+      unpack8(__ldg(z + i), zz);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaf(cb[k], zz[k], fmaf(ca[k], g[k], cc[k]));
+      dz[i] = pack8(o);
+    }
+    return;
+  }
+  for (long i = i0; i < total; i += stride) {
     const int c0 = int(i % C8) * 8;
     float g[8], zz[8], o[8];
     unpack8(__ldg(dyh + i), g);
