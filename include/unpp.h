@@ -86,7 +86,7 @@ typedef struct UnppConvArgs {
   /* Fused transposed conv (inference, with block2x2): conv3x3(cat[ConvTranspose2d_k2s2(low), src...]) — the k2s2
    * upsample never overlaps, so its branch collapses into a 3x3 conv over the LOW-resolution tensor with
    * composed weights whose 64 GEMM columns are (pixel of the 2x2 block, co): one more K chunk of the same
-   * accumulators.  lowres_src: NHWC bf16 [N, H/2, W/2, lowres_C] (lowres_C = 32); lowres_wpacked: kind-0 packing
+   * accumulators.  lowres_src: NHWC bf16 [N, H/2, W/2, lowres_C] (lowres_C = 32); lowres_wpacked: kind-6 packing
    * of the composed [64][lowres_C][3][3] weight (taps 9, n_total = n_tile = 64).  The upsample bias reaches
    * fewer taps at the image border: bias is then a [9][16] table indexed by (row class, column class). */
   const void* lowres_src;
@@ -117,6 +117,11 @@ int unpp_conv_grid(const UnppConvArgs* a);
  *  kind 4: 2x2-blocked forward conv (taps = 16 window positions dy*4+dx, n = (2*jy+jx)*16 + co):
  *          B[n][pos][k=ci] = W[co][k_begin+ci][dy-jy][dx-jx] * scale[co] if both offsets are in 0..2, else 0
  *  kind 5: 2x2-blocked dgrad: B[n=(2*jy+jx)*16+ci][pos][k=co] = W[k_begin+co][n_begin+ci][2-(dy-jy)][2-(dx-jx)] or 0
+ *  kind 6: fused transposed conv of the 2x2-blocked path (taps = 9 low-resolution taps): src = composed weights
+ *          [4*16][Cin][3][3] whose output channel is (2*jy+jx)*16 + co
+ *          Kinds 4-6 store only the NON-ZERO (position, pixel) blocks: per 16 input channels 36 (kind 6: 16) blocks of
+ *          512 B = [2 k8][16 columns][8 channels], runs of adjacent pixels contiguous (csrc/b2_blocks.h): the kernel
+ *          issues one MMA (N = 16/32/64) per run.  Buffer size: (k8_total / 2) * 36 * 512 B (kind 6: * 16 * 512 B).
  * k_dst8 places the K range at 8-channel chunk offset k_dst8 inside a K/8 = k8_total wide buffer,
  * so that several sources (concat) or several consumers (dgrad gather) share one packed tensor. */
 typedef struct UnppPackArgs {

@@ -482,7 +482,7 @@ def test_fused_transposed_conv_into_block2x2_conv(N, H, W, nlows):
     ref = F.relu(F.conv2d(torch.cat([up] + [l.double() for l in lows], 1), w.double(), b.double(), padding=1))
     comp, table = compose_deconv_conv(w[:, :16].to(DEV), w_up.to(DEV), b_up.to(DEV), b.to(DEV))
     wp = ops.pack_weights_b2(w.to(DEV), False, 16 * nlows, k_begin=16)
-    lw = ops.pack_weights(comp, 0, 9, 64, 64, 32)
+    lw = ops.pack_weights(comp, 6, 9, 64, 64, 32)  # kind 6: only the non-zero (tap, pixel) blocks (csrc/b2_blocks.h)
     out = torch.empty(N, H, W, 16, dtype=torch.bfloat16, device=DEV)
     ops.conv([nhwc(l) for l in lows], N, H, W, wp, 16, ops.NTile(16, b2=True), 9, bias=table, bias_classes=9, relu=True, out=out,
              lowres=(nhwc(xlow), lw))

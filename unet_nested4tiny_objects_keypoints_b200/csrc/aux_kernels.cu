@@ -4,6 +4,7 @@
 // All are plain coalesced/vectorised CUDA-core kernels (HBM-bound byte movers).
 #include "common.h"
 #include "../../include/unpp.h"
+#include "b2_blocks.h"
 #include <cuda_bf16.h>
 #include <stdint.h>
 
@@ -11,7 +12,50 @@ namespace {
 
 // ------------------------------------------------------------------------------------------
 // weight packing: one thread per packed 8-element K group (16 B store)
+// kinds 4 / 5 / 6: only the non-zero (position, pixel) blocks of the 2x2-blocked layouts are stored (b2_blocks.h).
+// Per K = 16 slab: `units` 16-column blocks of 512 B; inside the run of an MMA: [2 k8][N = 16 * nblk columns][8 channels].
+__device__ __forceinline__ void pack_entry_b2(const UnppPackArgs& a) {
+  const bool low = a.kind == 6;
+  const int units = low ? b2::kLowUnits : b2::kMainUnits, nblks = low ? b2::kLowBlks : b2::kMainBlks;
+  const int k8_count = a.k_count / 8;
+  const long total = long(units) * 16 * k8_count;
+  for (long idx = blockIdx.x * long(blockDim.x) + threadIdx.x; idx < total; idx += long(gridDim.x) * blockDim.x) {
+    const int c = int(idx & 15), u = int((idx >> 4) % units), k8 = int((idx >> 4) / units);
+    b2::Blk blk = low ? b2::low_blk(0) : b2::main_blk(0);
+    for (int i = 1; i < nblks; ++i) {
+      const b2::Blk t = low ? b2::low_blk(i) : b2::main_blk(i);
+      if (u >= t.cum) blk = t;
+    }
+    const int q = blk.b0 + (u - blk.cum);  // pixel of the 2x2 block
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int k = k8 * 8 + kk;
+      float w;
+      if (low) {  // composed transposed-conv weights [4*16][Cin][3][3], output channel = q * 16 + co (engine.compose_deconv_conv)
+        w = a.src[(size_t(q * 16 + c) * a.src_I + (a.k_begin + k)) * 9 + blk.pos];
+      } else {
+        const int r = (blk.pos >> 2) - (q >> 1), s = (blk.pos & 3) - (q & 1);  // in [0, 2] by construction
+        if (a.kind == 4) {
+          w = (a.k_begin + k) < a.src_I ? a.src[(size_t(c) * a.src_I + (a.k_begin + k)) * 9 + r * 3 + s] : 0.f;
+          if (a.scale) w *= a.scale[c];
+        } else {
+          w = a.src[(size_t(a.k_begin + k) * a.src_I + (a.n_begin + c)) * 9 + (2 - r) * 3 + (2 - s)];
+        }
+      }
+      v[kk] = __float2bfloat16_rn(w);
+    }
+    const int kd = a.k_dst8 + k8, slab = kd >> 1, half = kd & 1, N = 16 * blk.nblk;
+    const size_t dst_bytes = size_t(slab) * units * b2::kUnitBytes + size_t(blk.cum) * b2::kUnitBytes + size_t(half) * N * 16 + size_t((u - blk.cum) * 16 + c) * 16;
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.dst) + dst_bytes) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
 __device__ __forceinline__ void pack_entry(const UnppPackArgs& a) {
+  if (a.kind >= 4) {
+    pack_entry_b2(a);
+    return;
+  }
   const int nt_count = a.n_total / a.n_tile;
   const int k8_count = a.k_count / 8;
   const long total = long(nt_count) * a.taps * k8_count * a.n_tile;
@@ -39,17 +83,6 @@ __device__ __forceinline__ void pack_entry(const UnppPackArgs& a) {
         w = a.src[(size_t(a.k_begin + k) * cout + co) * 4 + pq];
       } else if (a.kind == 3) {  // B[n=ci][tap=pq][k=co] = Wd[ci][co][pq]
         w = a.src[(size_t(a.n_begin + n) * a.src_I + (a.k_begin + k)) * 4 + tap];
-      } else {  // kinds 4 / 5: 2x2 output blocks; tap = window position dy*4+dx, n = (2*jy+jx)*16 + c
-        const int q = n >> 4, c = n & 15, r = (tap >> 2) - (q >> 1), s = (tap & 3) - (q & 1);
-        w = 0.f;
-        if (r >= 0 && r <= 2 && s >= 0 && s <= 2) {
-          if (a.kind == 4) {
-            w = (a.k_begin + k) < a.src_I ? a.src[(size_t(c) * a.src_I + (a.k_begin + k)) * 9 + r * 3 + s] : 0.f;
-            if (a.scale) w *= a.scale[c];
-          } else {
-            w = a.src[(size_t(a.k_begin + k) * a.src_I + (a.n_begin + c)) * 9 + (2 - r) * 3 + (2 - s)];
-          }
-        }
       }
       v[kk] = __float2bfloat16_rn(w);
     }
@@ -223,13 +256,13 @@ inline int grid_for(long total, int block) {
 
 extern "C" int unpp_pack_weights(const UnppPackArgs* a, unpp_stream_t stream) {
   if (!a || !a->src || !a->dst) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: null pointer");
-  if (a->kind < 0 || a->kind > 5) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: bad kind");
-  if (a->kind >= 4 && (a->taps != 16 || a->n_total != 64 || a->n_tile != 64))
-    return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: 2x2-blocked kinds need taps=16, n_total=n_tile=64");
+  if (a->kind < 0 || a->kind > 6) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: bad kind");
+  if (a->kind >= 4 && (a->taps != (a->kind == 6 ? 9 : 16) || a->n_total != 64 || a->n_tile != 64))
+    return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: 2x2-blocked kinds need taps=16 (kind 6: 9), n_total=n_tile=64");
   if (a->n_tile < 8 || a->n_total % a->n_tile || a->k_count % 8 || a->k_count < 8 || a->taps < 1)
     return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: n_total %% n_tile, k_count %% 8 must be 0");
   if (a->k_dst8 + a->k_count / 8 > a->k8_total) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: K range exceeds k8_total");
-  const long total = long(a->n_total) * a->taps * (a->k_count / 8);
+  const long total = a->kind >= 4 ? long(a->kind == 6 ? b2::kLowUnits : b2::kMainUnits) * 16 * (a->k_count / 8) : long(a->n_total) * a->taps * (a->k_count / 8);
   unpp::launch(pack_weights_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), *a);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("pack_weights: launch");
   return UNPP_OK;

@@ -25,6 +25,7 @@
 #include "sm100.cuh"
 #include "common.h"
 #include "../../include/unpp.h"
+#include "b2_blocks.h"
 
 using namespace sm100;
 
@@ -539,7 +540,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     const int ncols = p.ncols, nsub = p.nsub, taps = p.taps, k8_total = p.k8_total, nchunk = p.nchunk, nstage = p.nstage;
     const int ntiles = p.ntiles, stage_bytes = p.stage_bytes, dbg = p.dbg, b2 = p.b2, b2_P = p.b2_P, nacc = p.nacc;
     const int low_on = p.low_on, low_P = p.low_P, low_k8 = p.low_k8, low_w_off = p.low_w_off;
-    const uint32_t idesc = make_idesc_bf16(128, ncols);
+    const uint32_t idesc = make_idesc_bf16(128, ncols), idesc32 = make_idesc_bf16(128, 32), idesc16 = make_idesc_bf16(128, 16);
     const uint32_t w_addr = smem_u32(w_smem);
     const uint32_t stage_addr0 = smem_u32(stage0);
     int spans[kMaxChunks], wk8s[kMaxChunks];
@@ -569,23 +570,23 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
             // next row group one low-res row down); classic 3x3 taps over the low-res halo tile, two K=16 slabs per
             // tap (32 channels), the 64 columns are (pixel of the 2x2 block, co) with composed weights.
             const uint64_t ad = make_sdesc(stage_addr0 + uint32_t(s) * stage_bytes, 16, uint32_t(low_P * 64), 4);
-            const uint64_t bd = make_sdesc(w_addr + uint32_t(low_w_off), 64 * 16, 128, 0);
+            const uint64_t bd = make_sdesc(w_addr + uint32_t(low_w_off), 0, 128, 0);
             const uint32_t a_hi = uint32_t(ad >> 32), b_hi = uint32_t(bd >> 32), b_lo = uint32_t(bd);
             const uint32_t a_lo0 = uint32_t(ad) + uint32_t(mw * 32), a_lo1 = a_lo0 + uint32_t(kMmaWarps * 32);
             const uint32_t acc0 = acc + uint32_t(mw * 64), acc1 = acc + uint32_t((mw + kMmaWarps) * 64);
-            const uint32_t b_tap_step = uint32_t(low_k8 * 64 * 16) >> 4, b_ks_step = uint32_t(2 * 64 * 16) >> 4, row_step = uint32_t(low_P * 4);
+            const uint32_t row_step = uint32_t(low_P * 4);
             const int kslabs = low_k8 >> 1;
+            for (int ks = 0; ks < kslabs; ++ks) {
+              const uint32_t b_ks = b_lo + (uint32_t(ks * b2::kLowUnits * b2::kUnitBytes) >> 4);
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-#pragma unroll
-              for (int sft = 0; sft < 3; ++sft) {
-                for (int ks = 0; ks < kslabs; ++ks) {
-                  const uint32_t ao = uint32_t(r) * row_step + uint32_t(sft * 4 + ks * 2);
-                  const uint64_t bdesc = (uint64_t(b_hi) << 32) | (b_lo + uint32_t(r * 3 + sft) * b_tap_step + uint32_t(ks) * b_ks_step);
-                  const uint32_t accum = (c | r | sft | ks) ? 1u : 0u;
-                  if (has0) umma_bf16(acc0, (uint64_t(a_hi) << 32) | (a_lo0 + ao), bdesc, idesc, accum);
-                  if (has1) umma_bf16(acc1, (uint64_t(a_hi) << 32) | (a_lo1 + ao), bdesc, idesc, accum);
-                }
+              for (int i = 0; i < b2::kLowBlks; ++i) {  // one MMA per run of non-zero pixel blocks (b2_blocks.h); this chunk is never the first
+                const b2::Blk blk = b2::low_blk(i);
+                const uint32_t ao = uint32_t(blk.pos / 3) * row_step + uint32_t((blk.pos % 3) * 4 + ks * 2);
+                const uint32_t nb = uint32_t(blk.nblk);
+                const uint64_t bdesc = (uint64_t(b_hi) << 32) | (b_ks + (uint32_t(blk.cum * b2::kUnitBytes) >> 4) + (nb << 20));  // LBO = 16 * nblk * 16 B
+                const uint32_t idn = nb == 4 ? idesc : nb == 2 ? idesc32 : idesc16, dcol = uint32_t(blk.b0 * 16);
+                if (has0) umma_bf16(acc0 + dcol, (uint64_t(a_hi) << 32) | (a_lo0 + ao), bdesc, idn, 1u);
+                if (has1) umma_bf16(acc1 + dcol, (uint64_t(a_hi) << 32) | (a_lo1 + ao), bdesc, idn, 1u);
               }
             }
           }
@@ -595,22 +596,22 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
             // image rows down), K walks the 4x4 input window: pixel (dy, dx) of the window is 32 B into / past the
             // pair row, i.e. a start-address shift of (dy * pairs_per_row * 4 + (dx + 1) * 2) 16-byte units.
             const uint64_t ad = make_sdesc(stage_addr0 + uint32_t(s) * stage_bytes, 16, uint32_t(2 * b2_P * 64), 4);
-            const uint64_t bd = make_sdesc(w_addr + uint32_t(wk8 * 64 * 16), 64 * 16, 128, 0);
+            const uint64_t bd = make_sdesc(w_addr + uint32_t((wk8 >> 1) * b2::kMainUnits * b2::kUnitBytes), 0, 128, 0);
             const uint32_t a_hi = uint32_t(ad >> 32), b_hi = uint32_t(bd >> 32), b_lo = uint32_t(bd);
             const uint32_t a_lo0 = uint32_t(ad) + 2u + uint32_t(mw * 32), a_lo1 = a_lo0 + uint32_t(kMmaWarps * 32);
             const uint32_t acc0 = acc + uint32_t(mw * 64), acc1 = acc + uint32_t((mw + kMmaWarps) * 64);
-            const uint32_t b_pos_step = uint32_t(k8_total * 64 * 16) >> 4, row_step = uint32_t(b2_P * 4);
+            const uint32_t row_step = uint32_t(b2_P * 4);
             const uint32_t first = c ? 1u : 0u;
 #pragma unroll
-            for (int dy = 0; dy < 4; ++dy) {
-#pragma unroll
-              for (int dx = 0; dx < 4; ++dx) {
-                const uint32_t ao = uint32_t(dy) * row_step + uint32_t(dx * 2), bo = uint32_t(dy * 4 + dx) * b_pos_step;
-                const uint64_t bdesc = (uint64_t(b_hi) << 32) | (b_lo + bo);
-                const uint32_t accum = (dy | dx) ? 1u : first;
-                if (has0) umma_bf16(acc0, (uint64_t(a_hi) << 32) | (a_lo0 + ao), bdesc, idesc, accum);
-                if (has1) umma_bf16(acc1, (uint64_t(a_hi) << 32) | (a_lo1 + ao), bdesc, idesc, accum);
-              }
+            for (int i = 0; i < b2::kMainBlks; ++i) {  // one MMA per run of non-zero pixel blocks (b2_blocks.h); block 0 covers all 64 columns
+              const b2::Blk blk = b2::main_blk(i);
+              const uint32_t ao = uint32_t(blk.pos >> 2) * row_step + uint32_t((blk.pos & 3) * 2);
+              const uint32_t nb = uint32_t(blk.nblk);
+              const uint64_t bdesc = (uint64_t(b_hi) << 32) | (b_lo + (uint32_t(blk.cum * b2::kUnitBytes) >> 4) + (nb << 20));  // LBO = 16 * nblk * 16 B
+              const uint32_t idn = nb == 4 ? idesc : nb == 2 ? idesc32 : idesc16, dcol = uint32_t(blk.b0 * 16);
+              const uint32_t accum = i ? 1u : first;
+              if (has0) umma_bf16(acc0 + dcol, (uint64_t(a_hi) << 32) | (a_lo0 + ao), bdesc, idn, accum);
+              if (has1) umma_bf16(acc1 + dcol, (uint64_t(a_hi) << 32) | (a_lo1 + ao), bdesc, idn, accum);
             }
           }
         } else if (elect_one() && !(dbg & 2)) {
@@ -915,13 +916,13 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
       pl->ch_span[i] = 64, pl->ch_wk8[i] = 2 * i;
     }
     pl->b2 = 1, pl->ncols = 64;
-    pl->w_bytes = 16 * k8 * 64 * 16;
+    pl->w_bytes = (k8 / 2) * b2::kMainUnits * b2::kUnitBytes;  // only the non-zero (position, pixel) blocks are stored (b2_blocks.h)
     pl->w_smem_bytes = (pl->w_bytes + 1023) / 1024 * 1024;
     if (a->lowres_src) {
       if (a->lowres_C != 32 || !a->lowres_wpacked || (a->H & 3) || (a->W & 3) || is_train(a) || (reinterpret_cast<uintptr_t>(a->lowres_src) & 15))
         return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: fused transposed conv needs a 32-channel low-res source, its composed weights, H and W "
                                             "divisible by 4, and the inference epilogue");
-      pl->low_on = 1, pl->low_w_off = pl->w_smem_bytes, pl->low_w_bytes = 9 * (a->lowres_C / 8) * 64 * 16;
+      pl->low_on = 1, pl->low_w_off = pl->w_smem_bytes, pl->low_w_bytes = (a->lowres_C / 16) * b2::kLowUnits * b2::kUnitBytes;
       pl->w_smem_bytes += (pl->low_w_bytes + 1023) / 1024 * 1024;
     }
     // widest tile that leaves room for two stages: fewer tiles (less per-tile handshake), more sub-tiles (more issuers busy)

@@ -126,7 +126,7 @@ class Engine:
                                                       conv1.bias.detach().float())
                     klow = conv1.weight.shape[1] - cu
                     P[f"{name}.c1.fused"] = dict(w=ops.pack_weights_b2(conv1.weight.detach().float(), False, klow, k_begin=cu), bias=table,
-                                                 low_w=ops.pack_weights(comp, 0, 9, 64, 64, 32), n_total=16, n_tile=ops.NTile(16, b2=True))
+                                                 low_w=ops.pack_weights(comp, 6, 9, 64, 64, 32), n_total=16, n_tile=ops.NTile(16, b2=True))
                 cin, cout = up.up.weight.shape[0], up.up.weight.shape[1]
                 nt = pick_n_tile(4 * cout, cin, 1, deconv=True)
                 P[f"{name}.up"] = dict(w=ops.pack_weights(up.up.weight.float(), 2, 1, 4 * cout, nt, cin), bias=up.up.bias.detach().float().contiguous(),

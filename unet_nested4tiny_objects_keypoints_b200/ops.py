@@ -169,9 +169,10 @@ def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Te
     # algorithmic traffic: every source once, the output once, weights once; heat maps fp32
     k_total = sum(s.shape[-1] for s in srcs)
     px = N * H * W
-    nbytes = px * k_total * 2 + wpacked.numel() * 2
+    # (2x2-blocked layouts store only the non-zero blocks: 36 of 64 per 16 input channels, 16 of 36 for the fused transposed conv)
+    nbytes = px * k_total * 2 + ((k_total // 16) * 36 * 512 if a.block2x2 else wpacked.numel() * 2)
     if lowres is not None:
-        nbytes += lowres[0].numel() * 2 + lowres[1].numel() * 2
+        nbytes += lowres[0].numel() * 2 + (lowres[0].shape[-1] // 16) * 16 * 512
     if out is not None:
         nbytes += px * n_total * 2
     if head is not None:
