@@ -103,13 +103,36 @@ __global__ void pack_weights_batched_kernel(const UnppPackArgs* __restrict__ tab
 }
 
 // ------------------------------------------------------------------------------------------
-// NCHW fp32 -> NHWC bf16 with channel padding; one thread per pixel, reads coalesced per plane.
+// NCHW fp32 -> NHWC bf16 with channel padding.  A thread converts four consecutive pixels (one float4 per plane, 128
+// contiguous output bytes) when H*W is a multiple of 4; the generic path does one pixel per thread.
 template <int CPAD>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C, long HW) {
   unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
   unpp::pdl_trigger();
+  const long stride = long(gridDim.x) * blockDim.x, i0 = blockIdx.x * long(blockDim.x) + threadIdx.x;
+  if (!(HW & 3) && !(reinterpret_cast<uintptr_t>(x) & 15)) {
+    const long HW4 = HW >> 2, quads = long(N) * HW4;
+    long n = i0 / HW4, p4 = i0 % HW4;  // advanced incrementally: no 64-bit division in the loop
+    const long step_n = stride / HW4, step_p = stride % HW4;
+    for (long i = i0; i < quads; i += stride, n += step_n, p4 += step_p) {
+      if (p4 >= HW4) p4 -= HW4, ++n;
+      float4 f[CPAD];
+#pragma unroll
+      for (int c = 0; c < CPAD; ++c) f[c] = c < C ? __ldg(reinterpret_cast<const float4*>(x + (n * C + c) * HW) + p4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      uint4* o = reinterpret_cast<uint4*>(out + i * 4 * CPAD);
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        __align__(16) __nv_bfloat16 v[CPAD];
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) v[c] = __float2bfloat16_rn((&f[c].x)[px]);
+#pragma unroll
+        for (int k = 0; k < CPAD / 8; ++k) o[px * (CPAD / 8) + k] = reinterpret_cast<const uint4*>(v)[k];
+      }
+    }
+    return;
+  }
   const long total = long(N) * HW;
-  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
+  for (long i = i0; i < total; i += stride) {
     const long n = i / HW, p = i % HW;
     __align__(16) __nv_bfloat16 v[CPAD];
 #pragma unroll
@@ -278,7 +301,7 @@ extern "C" int unpp_pack_weights_batched(const UnppPackArgs* table_dev, int n, u
 extern "C" int unpp_nchw_to_nhwc(const float* x, void* out, int N, int C, int H, int W, int Cpad, unpp_stream_t stream) {
   if (!x || !out || N < 1 || C < 1 || H < 1 || W < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "nchw_to_nhwc: bad argument");
   if (Cpad != 16 || C > Cpad) return unpp::fail(UNPP_ERR_UNSUPPORTED, "nchw_to_nhwc: Cpad must be 16 and C <= 16");
-  const long total = long(N) * H * W;
+  const long total = (long(H) * W) % 4 ? long(N) * H * W : long(N) * H * W / 4;
   unpp::launch(nchw_to_nhwc_kernel<16>, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       x, reinterpret_cast<__nv_bfloat16*>(out), N, C, long(H) * W);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("nchw_to_nhwc: launch");

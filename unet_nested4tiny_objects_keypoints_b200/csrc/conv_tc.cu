@@ -320,6 +320,21 @@ __device__ __forceinline__ void epi_prefetch(const EpiArgs& p, EpiOperands<G>& t
   }
 }
 
+// Ask L2 for the step's training operands (issued for the whole tile while the warp would otherwise idle on the accumulator
+// barrier): the loads of epi_prefetch then find them in L2 instead of paying the DRAM latency once per step.
+template <int G, bool HEAD, bool TRAIN>
+__device__ __forceinline__ void epi_l2_prefetch(const EpiArgs& p, size_t eoff, bool valid) {
+  if constexpr (TRAIN) {
+    if (!valid) return;
+    if (p.addend) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.addend + eoff));
+    if (p.relu_mask_src) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.relu_mask_src + eoff));
+    if (p.stats_aux) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.stats_aux + eoff));
+    if constexpr (HEAD) {
+      if (p.drop_mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.drop_mask + eoff));
+    }
+  }
+}
+
 template <int G, bool HEAD, bool TRAIN>
 __device__ __forceinline__ void epi_finish(const EpiArgs& p, const uint32_t (&raw)[16 * G], const EpiOperands<G>& t, const float (&bias_r)[16], const float* s_bias,
                                            const float* s_head, bool relu, size_t eoff, bool valid, int n, int yy, int x0, float (&sa1)[16],
@@ -691,11 +706,14 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
         const int b = tile_it % nacc, aph = (tile_it / nacc) & 1;
         const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
-        mbar_wait(&bar_acc_full[b], aph);
-        tc_fence_after();
         const int yy = ty * 32 + 2 * pi + half, xb = tx * TW + 2 * pj;
         const bool row_ok = yy < e.H;
         const size_t rowpix = (size_t(n) * e.H + yy) * e.W;
+        if constexpr (TRAIN) {
+          for (int j = 0; j < nsub; ++j) epi_l2_prefetch<2, HEAD, TRAIN>(e, (rowpix + xb + j * 16) * 16, row_ok && xb + j * 16 < e.W);
+        }
+        mbar_wait(&bar_acc_full[b], aph);
+        tc_fence_after();
         const uint32_t tcol = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * nsub * 64 + half * 32);
         if (!(dbg & 1)) {
           if constexpr (TRAIN || HEAD) {  // one TMEM buffer (registers): operands of the step are in flight while the load is waited for
@@ -744,11 +762,17 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
         const int b = tile_it % nacc, aph = (tile_it / nacc) & 1;
         const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
-        mbar_wait(&bar_acc_full[b], aph);
-        tc_fence_after();
         const int yy = ty * 16 + pi, xb = tx * TW + pj;
         const bool row_ok = yy < e.H;
         const size_t rowpix = (size_t(n) * e.H + yy) * e.W;
+        if constexpr (TRAIN && !DECONV) {
+          for (int it = 0; it < nit; ++it) {
+            const int u = half + 2 * it, j = u >> ncb_shift, c0 = (u & (ncb - 1)) * 16;
+            epi_l2_prefetch<1, false, TRAIN>(e, (rowpix + xb + j * 8) * e.cout + ntile_idx * ncols + c0, row_ok && xb + j * 8 < e.W);
+          }
+        }
+        mbar_wait(&bar_acc_full[b], aph);
+        tc_fence_after();
         const uint32_t tcol = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * nsub * ncols);
         if (!(dbg & 1)) {
           uint32_t A[16];
