@@ -277,7 +277,7 @@ def bench_infer(args, rank, world, local):
         step_ms = ms / args.steps
         roof["share_of_step"] = round(roof["ms_per_step_in_kernel"] / step_ms, 3)
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+        if os.path.exists(tpath) and S == 256 and INFER_B == 128:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
             with open(tpath) as f:
                 tj = json.load(f)
             roof["traffic"] = round(tj["traffic_bytes_per_launch_avg"])

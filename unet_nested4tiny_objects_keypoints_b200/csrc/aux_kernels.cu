@@ -12,20 +12,19 @@ namespace {
 
 // ------------------------------------------------------------------------------------------
 // weight packing: one thread per packed 8-element K group (16 B store)
+__constant__ b2::UnitTable<b2::kMainUnits> c_main_units = b2::main_units();
+__constant__ b2::UnitTable<b2::kLowUnits> c_low_units = b2::low_units();
+
 // kinds 4 / 5 / 6: only the non-zero (position, pixel) blocks of the 2x2-blocked layouts are stored (b2_blocks.h).
 // Per K = 16 slab: `units` 16-column blocks of 512 B; inside the run of an MMA: [2 k8][N = 16 * nblk columns][8 channels].
 __device__ __forceinline__ void pack_entry_b2(const UnppPackArgs& a) {
   const bool low = a.kind == 6;
-  const int units = low ? b2::kLowUnits : b2::kMainUnits, nblks = low ? b2::kLowBlks : b2::kMainBlks;
+  const int units = low ? b2::kLowUnits : b2::kMainUnits;
   const int k8_count = a.k_count / 8;
   const long total = long(units) * 16 * k8_count;
   for (long idx = blockIdx.x * long(blockDim.x) + threadIdx.x; idx < total; idx += long(gridDim.x) * blockDim.x) {
     const int c = int(idx & 15), u = int((idx >> 4) % units), k8 = int((idx >> 4) / units);
-    b2::Blk blk = low ? b2::low_blk(0) : b2::main_blk(0);
-    for (int i = 1; i < nblks; ++i) {
-      const b2::Blk t = low ? b2::low_blk(i) : b2::main_blk(i);
-      if (u >= t.cum) blk = t;
-    }
+    const b2::Blk blk = low ? c_low_units.of[u] : c_main_units.of[u];
     const int q = blk.b0 + (u - blk.cum);  // pixel of the 2x2 block
     __align__(16) __nv_bfloat16 v[8];
 #pragma unroll

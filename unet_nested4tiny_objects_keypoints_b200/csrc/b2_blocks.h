@@ -35,4 +35,22 @@ __host__ __device__ constexpr Blk low_blk(int i) {
   return t[i];
 }
 
+// Per 16-column unit of the packed layout: the block it belongs to (for the weight packer, which walks units).
+template <int UNITS>
+struct UnitTable {
+  Blk of[UNITS];
+};
+__host__ __device__ constexpr UnitTable<kMainUnits> main_units() {
+  UnitTable<kMainUnits> t{};
+  for (int i = 0; i < kMainBlks; ++i)
+    for (int j = 0; j < main_blk(i).nblk; ++j) t.of[main_blk(i).cum + j] = main_blk(i);
+  return t;
+}
+__host__ __device__ constexpr UnitTable<kLowUnits> low_units() {
+  UnitTable<kLowUnits> t{};
+  for (int i = 0; i < kLowBlks; ++i)
+    for (int j = 0; j < low_blk(i).nblk; ++j) t.of[low_blk(i).cum + j] = low_blk(i);
+  return t;
+}
+
 }  // namespace b2
