@@ -93,6 +93,9 @@ typedef struct UnppConvArgs {
   const void* lowres_wpacked;
   int32_t lowres_C;
   int32_t bias_classes;         /* 0/1: bias[Cout]; 9: bias[3*rowclass+colclass][16], class 0 first, 1 interior, 2 last */
+  /* Fused nn.MaxPool2d(2) of the output (models/unet.py:219,258,260,262): NHWC bf16 [N, H/2, W/2, n_total], written next to
+   * `out` by the inference epilogue (conv mode, relu = 1, even H and W, no head, no training operand).  NULL = no pooling. */
+  void* pooled;
 } UnppConvArgs;
 
 const char* unpp_last_error(void);

@@ -467,6 +467,28 @@ def test_block2x2_dgrad_gather_mask_stats(ncons):
     close(sums[16:].cpu(), (got.double() * xhat).sum((0, 2, 3)), 2e-3, "sum v*xhat")
 
 
+@pytest.mark.parametrize("N,H,W,cin,cout,b2", [(2, 64, 96, 16, 16, True), (1, 24, 40, 16, 16, True), (2, 32, 48, 32, 32, False), (1, 16, 24, 64, 64, False),
+                                                (3, 8, 8, 16, 32, False), (1, 40, 72, 16, 16, False)])
+def test_conv_with_fused_maxpool(N, H, W, cin, cout, b2):
+    """conv3x3 + bias + ReLU with nn.MaxPool2d(2) of the result written by the same epilogue (unet.py:258-262): the pooled
+    tensor equals the pool of the stored bf16 output bit for bit."""
+    x = bf(rnd(N, cin, H, W, seed=300))
+    w = bf(rnd(cout, cin, 3, 3, seed=301, scale=(2.0 / (9 * cin)) ** 0.5))
+    b = rnd(cout, seed=302, scale=0.1)
+    if b2:
+        wp, nt = ops.pack_weights_b2(w.to(DEV), False, cin), ops.NTile(16, b2=True)
+    else:
+        nt = ops.pick_n_tile(cout, cin, 9)
+        wp = ops.pack_weights(w.to(DEV), 0, 9, cout, nt, cin)
+    out = torch.empty(N, H, W, cout, dtype=torch.bfloat16, device=DEV)
+    pooled = torch.full((N, H // 2, W // 2, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.conv([nhwc(x)], N, H, W, wp, cout, nt, 9, bias=b.to(DEV), relu=True, out=out, pooled=pooled)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1))
+    close(nchw(out), ref, 6e-3, "conv + relu")
+    assert torch.equal(nchw(pooled), F.max_pool2d(nchw(out), 2))
+
+
 @pytest.mark.parametrize("N,H,W,nlows", [(2, 32, 32, 1), (1, 24, 40, 2), (2, 64, 64, 3), (1, 8, 8, 1), (1, 128, 64, 2)])
 def test_fused_transposed_conv_into_block2x2_conv(N, H, W, nlows):
     """conv3x3(cat[ConvTranspose2d_k2s2(x_low), lows...]) + bias + ReLU in ONE launch, the upsampled tensor never exists."""

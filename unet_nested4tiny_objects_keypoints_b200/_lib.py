@@ -55,6 +55,7 @@ class ConvArgs(C.Structure):
         ("lowres_wpacked", C.c_void_p),
         ("lowres_C", C.c_int32),
         ("bias_classes", C.c_int32),
+        ("pooled", C.c_void_p),
     ]
 
 

@@ -77,6 +77,7 @@ struct ConvTcParams {
   int low_on, low_P, low_k8, low_w_off, low_w_bytes;  // low_P = low-res pixels per staged tile row (TW/2 + 2); offsets in bytes
   const __nv_bfloat16* low_wpacked;
   int bias9;     // bias is a [9][16] (row class, column class) table
+  __nv_bfloat16* pooled;  // fused 2x2 max pool of the output (inference epilogue), or null
   int dbg;  // UNPP_DBG experiment bits (0 in production): 1 = epilogue skips its work, 2 = no MMAs issued, 4 = no TMA tile loads,
             // 8 = epilogue does not store its bf16 output, 16 = epilogue does not read TMEM
 };
@@ -124,6 +125,7 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
 struct EpiArgs {
   int H, W, cout, head_classes, dbg, bias9;
   __nv_bfloat16* out;
+  __nv_bfloat16* pooled;
   float* heat;
   float* logit;
   const uint8_t* drop_mask;
@@ -320,6 +322,13 @@ __device__ __forceinline__ void epi_prefetch(const EpiArgs& p, EpiOperands<G>& t
   }
 }
 
+// element-wise max of two packed bf16x2 words (the 2x2 max pool works on the rounded values that are stored)
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
 // Ask L2 for the step's training operands (issued for the whole tile while the warp would otherwise idle on the accumulator
 // barrier): the loads of epi_prefetch then find them in L2 instead of paying the DRAM latency once per step.
 template <int G, bool HEAD, bool TRAIN>
@@ -338,8 +347,7 @@ __device__ __forceinline__ void epi_l2_prefetch(const EpiArgs& p, size_t eoff, b
 template <int G, bool HEAD, bool TRAIN>
 __device__ __forceinline__ void epi_finish(const EpiArgs& p, const uint32_t (&raw)[16 * G], const EpiOperands<G>& t, const float (&bias_r)[16], const float* s_bias,
                                            const float* s_head, bool relu, size_t eoff, bool valid, int n, int yy, int x0, float (&sa1)[16],
-                                           float (&sa2)[16]) {
-  uint32_t words[8 * G];
+                                           float (&sa2)[16], uint32_t (&words)[8 * G]) {
   float hv[HEAD ? G : 1][16];  // post-activation values of the pixels (fused head only)
 #pragma unroll
   for (int px = 0; px < G; ++px) {
@@ -684,7 +692,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     const int ncb = p.ncols >> 4, units = p.nsub * ncb;
     const float relu_floor = p.relu ? 0.f : -INFINITY;
     EpiArgs e;
-    e.dbg = p.dbg, e.bias9 = p.bias9;
+    e.dbg = p.dbg, e.bias9 = p.bias9, e.pooled = p.pooled;
     e.H = p.H, e.W = p.W, e.cout = p.cout, e.head_classes = p.head_classes, e.out = p.out, e.heat = p.heat, e.logit = p.logit;
     e.drop_mask = p.drop_mask, e.drop_scale = p.drop_scale, e.addend = p.addend, e.relu_mask_src = p.relu_mask_src;
     e.stats_partial = p.stats_partial, e.stats_aux = p.stats_aux, e.aux_mean = p.aux_mean, e.aux_istd = p.aux_istd;
@@ -703,9 +711,41 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
 #pragma unroll
       for (int k = 0; k < 16; ++k) bias_r[k] = e.bias9 ? 0.f : s_bias[k];
       const bool relu = p.relu != 0;
+      uint32_t wds[16];
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
         const int b = tile_it % nacc, aph = (tile_it / nacc) & 1;
         const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+        if constexpr (!TRAIN && !HEAD) {
+          if (e.pooled) {
+            // fused 2x2 max pool: this warp takes BOTH pixel rows of the blocks of sub-tiles half, half + 2, ...
+            mbar_wait(&bar_acc_full[b], aph);
+            tc_fence_after();
+            const int y0 = ty * 32 + 2 * pi, xb2 = tx * TW + 2 * pj;
+            const size_t rowpix0 = (size_t(n) * e.H + y0) * e.W;
+            const uint32_t tb = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * nsub * 64);
+            for (int jj = half; jj < nsub && !(dbg & 1); jj += 2) {
+              uint32_t A[32], pw[8];
+              EpiOperands<2> tops;
+              const int x0 = xb2 + jj * 16;
+              const bool valid = y0 < e.H && x0 < e.W;  // (even H, W: the whole 2x2 block is inside or outside)
+              tmem_ld32(tb + uint32_t(jj * 64), A);
+              tmem_ld_wait32(A);
+              epi_finish<2, HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix0 + x0) * 16, valid, n, y0, x0, sa1, sa2, wds);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) pw[k] = max_bf16x2(wds[k], wds[8 + k]);
+              tmem_ld32(tb + uint32_t(jj * 64 + 32), A);
+              tmem_ld_wait32(A);
+              epi_finish<2, HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix0 + e.W + x0) * 16, valid, n, y0 + 1, x0, sa1, sa2, wds);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) wds[k] = max_bf16x2(pw[k], max_bf16x2(wds[k], wds[8 + k]));
+              if (valid) st_global_v8(e.pooled + ((size_t(n) * (e.H >> 1) + (y0 >> 1)) * (e.W >> 1) + (x0 >> 1)) * 16, wds);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+            continue;
+          }
+        }
         const int yy = ty * 32 + 2 * pi + half, xb = tx * TW + 2 * pj;
         const bool row_ok = yy < e.H;
         const size_t rowpix = (size_t(n) * e.H + yy) * e.W;
@@ -725,7 +765,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
               tmem_ld32(tcol + uint32_t(j * 64), A);
               epi_prefetch<2, HEAD, TRAIN>(e, tops, (rowpix + x0) * 16, valid);
               tmem_ld_wait32(A);
-              epi_finish<2, HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix + x0) * 16, valid, n, yy, x0, sa1, sa2);
+              epi_finish<2, HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix + x0) * 16, valid, n, yy, x0, sa1, sa2, wds);
             }
           } else {  // two TMEM buffers: the load of the next step is in flight while this one is finished
             uint32_t A[32], B[32];
@@ -735,11 +775,11 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
               const int x0 = xb + j * 16;
               tmem_ld_wait32(A);
               if (j + 1 < nsub) tmem_ld32(tcol + uint32_t((j + 1) * 64), B);
-              epi_finish<2, HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix + x0) * 16, row_ok && x0 < e.W, n, yy, x0, sa1, sa2);
+              epi_finish<2, HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix + x0) * 16, row_ok && x0 < e.W, n, yy, x0, sa1, sa2, wds);
               if (j + 1 < nsub) {
                 tmem_ld_wait32(B);
                 if (j + 2 < nsub) tmem_ld32(tcol + uint32_t((j + 2) * 64), A);
-                epi_finish<2, HEAD, TRAIN>(e, B, tops, bias_r, s_bias, s_head, relu, (rowpix + x0 + 16) * 16, row_ok && x0 + 16 < e.W, n, yy, x0 + 16, sa1, sa2);
+                epi_finish<2, HEAD, TRAIN>(e, B, tops, bias_r, s_bias, s_head, relu, (rowpix + x0 + 16) * 16, row_ok && x0 + 16 < e.W, n, yy, x0 + 16, sa1, sa2, wds);
               }
             }
           }
@@ -775,7 +815,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
         tc_fence_after();
         const uint32_t tcol = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * nsub * ncols);
         if (!(dbg & 1)) {
-          uint32_t A[16];
+          uint32_t A[16], wds1[8];
           EpiOperands<1> tops;
           for (int it = 0; it < nit; ++it) {
             const int u = half + 2 * it, j = u >> ncb_shift, c0 = (u & (ncb - 1)) * 16;  // unit = (sub-tile, 16-column group)
@@ -801,7 +841,18 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
               }
             }
             tmem_ld_wait16(A);
-            epi_finish<1, false, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, eoff, valid, n, yy, x0, sa1, sa2);
+            epi_finish<1, false, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, eoff, valid, n, yy, x0, sa1, sa2, wds1);
+            if constexpr (!TRAIN && !DECONV) {
+              if (e.pooled) {  // 2x2 max pool across the four lanes that hold the window (pj ^ 1 = lane ^ 1, pi ^ 1 = lane ^ 8)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  wds1[k] = max_bf16x2(wds1[k], __shfl_xor_sync(0xffffffffu, wds1[k], 1));
+                  wds1[k] = max_bf16x2(wds1[k], __shfl_xor_sync(0xffffffffu, wds1[k], 8));
+                }
+                if (valid && !(lane & 9))
+                  st_global_v8(e.pooled + ((size_t(n) * (e.H >> 1) + (yy >> 1)) * (e.W >> 1) + (x0 >> 1)) * e.cout + ntile_idx * ncols + c0, wds1);
+              }
+            }
           }
         }
         tc_fence_before();
@@ -1028,6 +1079,9 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
                     a->head_classes > 8))
     return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: fused head needs conv mode, n_total=n_tile=16, heat/head_b and 1..8 classes");
   if (!a->out && !a->head_w) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: nothing to write");
+  if (a->pooled && (a->mode != UNPP_MODE_CONV || !a->relu || !a->out || a->head_w || is_train(a) || (a->H & 1) || (a->W & 1) ||
+                    (!a->block2x2 && a->n_tile != 16 && a->n_tile != 32 && a->n_tile != 64 && a->n_tile != 128)))
+    return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: the fused max pool needs conv mode with ReLU and an output, even H and W, no head / training operand");
   if (a->stats_partial && a->mode != UNPP_MODE_CONV) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: stats only in conv mode");
   if (a->stats_aux && (!a->aux_mean || !a->aux_istd)) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: stats_aux needs aux_mean/aux_istd");
 
@@ -1065,6 +1119,7 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   p.taps = a->taps, p.ncols = pl.ncols, p.k8_total = pl.k8_total;
   p.b2 = pl.b2, p.b2_P = pl.b2_P, p.nacc = pl.nacc;
   p.bias9 = a->bias_classes == 9;
+  p.pooled = reinterpret_cast<__nv_bfloat16*>(a->pooled);
   if (pl.low_on) {
     const cuuint64_t C = a->lowres_C, lw = a->W / 2, lh = a->H / 2;
     cuuint64_t gd[4] = {C, lw, lh, cuuint64_t(a->N)};

@@ -209,9 +209,10 @@ class Engine:
             h, w = H >> lvl, W >> lvl
             p1, p2 = P[f"{name}.c1"], P[f"{name}.c2"]
             ops.conv([src], B, h, w, p1["w"], p1["n_total"], p1["n_tile"], 9, bias=p1["bias"], relu=True, out=A[f"{name}.a"])
-            ops.conv([A[f"{name}.a"]], B, h, w, p2["w"], p2["n_total"], p2["n_tile"], 9, bias=p2["bias"], relu=True, out=A[f"X{lvl}0"])
+            # MaxPool2d(2) (unet.py:219,258,260,262) is written by the conv's own epilogue
+            ops.conv([A[f"{name}.a"]], B, h, w, p2["w"], p2["n_total"], p2["n_tile"], 9, bias=p2["bias"], relu=True, out=A[f"X{lvl}0"],
+                     pooled=A[f"P{lvl}0"] if lvl < 3 else None)
             if lvl < 3:
-                ops.maxpool(A[f"X{lvl}0"], A[f"P{lvl}0"])
                 src = A[f"P{lvl}0"]
         heats: List[Optional[torch.Tensor]] = [None, None, None]
         for name in DECODER_ORDER:

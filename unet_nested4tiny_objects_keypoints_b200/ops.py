@@ -144,7 +144,7 @@ def _conv_args(srcs, N, H, W, n_total, n_tile, taps, strided=None, b2=False) -> 
 
 def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Tensor, n_total: int, n_tile: int, taps: int, *, bias=None,
          relu=False, mode=MODE_CONV, out=None, head=None, addend=None, relu_mask_src=None, stats_partial=None, stats_aux=None, aux_mean=None,
-         aux_istd=None, strided=None, b2=False, lowres=None, bias_classes=0) -> None:
+         aux_istd=None, strided=None, b2=False, lowres=None, bias_classes=0, pooled=None) -> None:
     """One unpp_conv_tc launch.  ``srcs``: NHWC bf16 tensors (virtual concat along K).
     ``head`` = (w fp32 [cls,16], b fp32 [cls], heat fp32 NCHW, logit|None, drop_mask u8 NHWC|None, drop_scale).
     ``strided`` = [(oy, ox), ...]: every source is a [N,2H,2W,C] tensor read at (2y+oy, 2x+ox)."""
@@ -160,6 +160,7 @@ def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Te
     if lowres is not None:  # (low-resolution tensor [N,H/2,W/2,C], composed packed weights): fused transposed conv
         a.lowres_src, a.lowres_wpacked, a.lowres_C = lowres[0].data_ptr(), lowres[1].data_ptr(), lowres[0].shape[-1]
     a.bias_classes = bias_classes
+    a.pooled = _ptr(pooled)  # fused MaxPool2d(2) of the output (inference epilogue)
     a.addend, a.relu_mask_src = _ptr(addend), _ptr(relu_mask_src)
     a.stats_partial, a.stats_aux, a.aux_mean, a.aux_istd = _ptr(stats_partial), _ptr(stats_aux), _ptr(aux_mean), _ptr(aux_istd)
     _count()
@@ -175,6 +176,8 @@ def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Te
         nbytes += lowres[0].numel() * 2 + (lowres[0].shape[-1] // 16) * 16 * 512
     if out is not None:
         nbytes += px * n_total * 2
+    if pooled is not None:
+        nbytes += px * n_total * 2 // 4
     if head is not None:
         nbytes += px * head[0].shape[0] * 4 + (px * 16 if head[4] is not None else 0)
     for extra in (addend, relu_mask_src, stats_aux):
