@@ -66,8 +66,8 @@ typedef struct UnppConvArgs {
   float* heat;                  /* fp32 NCHW [N,classes,H,W]                                     */
   float* logit;                 /* optional fp32 NCHW pre-sigmoid output (training) or NULL       */
   int32_t head_classes;         /* <= 8                                                          */
-  /* head dropout (training): keep-mask u8 NHWC [N,H,W,16] or NULL; scale = 1/(1-p) */
-  const uint8_t* drop_mask;
+  /* head dropout (training): keep-mask (below) or NULL; scale = 1/(1-p) */
+  const uint16_t* drop_mask;    /* keep-mask of the head dropout, ONE 16-bit word per pixel [N,H,W]: bit c = keep channel c */
   float drop_scale;
   /* backward-only epilogue inputs, both NHWC bf16 shaped like `out` (conv mode) */
   const void* addend;           /* added to the accumulator before masking, or NULL              */
@@ -216,7 +216,7 @@ int unpp_bn_bwd_apply(const void* dyh, const void* z, const float* mean, const f
  *   loss_kind 1, FocalLoss_BCE_2d (tools/losses/focal_loss.py:264-301, the criterion the trainer ships, trainer.py:426):
  *                a = |heat-target|, e = 1-a+1e-20, loss partial = sum -a^gamma*log(e), dheat = coef * d/dheat of that term  dx is already multiplied by the ReLU mask [x > 0] of the conv that produced x.
  * partial: fp32 [unpp_head_bwd_grid()][classes*16 + classes + 1 + 16] = dW, db, loss, per-channel sum of dx. */
-int unpp_head_bwd(const float* heat, const float* dheat, const float* target, int loss_kind, float gamma, float coef, const void* x, const uint8_t* drop_mask,
+int unpp_head_bwd(const float* heat, const float* dheat, const float* target, int loss_kind, float gamma, float coef, const void* x, const uint16_t* drop_mask,
                   float drop_scale, const float* head_w, int classes, void* dx, float* partial, int N, int H, int W,
                   unpp_stream_t stream);
 int unpp_head_bwd_grid(int N, int H, int W);
@@ -228,9 +228,10 @@ int unpp_adamw(float* p, const float* g, float* m, float* v, long n, float lr, f
  * derives the bias-corrected step size from it into *step_size_scratch, then updates. */
 int unpp_adamw_dev(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, uint64_t* step_counter, float* step_size_scratch, float grad_scale, unpp_stream_t stream);
-/* u8 keep-mask for nn.Dropout(p): mask[i] = 1 with probability 1-p (counter-based hash of seed, i and,
- * when step_counter is not NULL, of the device step counter so that graph replays draw new masks). */
-int unpp_dropout_mask(uint8_t* mask, long n, float p_drop, uint64_t seed, const uint64_t* step_counter, unpp_stream_t stream);
+/* Keep-mask for the element-wise nn.Dropout(p) in front of the 16-channel heads (models/unet.py:254,283-286): one 16-bit
+ * word per pixel, bit c = 1 with probability 1-p (counter-based hash of seed, pixel, channel and, when step_counter is
+ * given, the device step counter: a captured training step draws fresh masks at every replay).  npix % 8 == 0. */
+int unpp_dropout_mask(uint16_t* mask, long npix, float p_drop, uint64_t seed, const uint64_t* step_counter, unpp_stream_t stream);
 
 /* Target heat maps from key points, the trainer's per-step CPU routine (tools/misc/helper.py:87-172, called at
  * trainer/trainer.py:122-123): keypoints fp32 [N][npts][2] as (x, y) -> out fp32 [N][4][H][W]; point groups

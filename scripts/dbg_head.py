@@ -6,7 +6,7 @@ dev = "cuda"
 N, H = 32, 256
 heat = torch.rand(N, 4, H, H, device=dev); target = torch.rand(N, 4, H, H, device=dev)
 x = torch.randn(N, H, H, 16, device=dev).relu().to(torch.bfloat16)
-mask = (torch.rand(N, H, H, 16, device=dev) > 0.4).to(torch.uint8)
+mask = torch.empty(N, H, H, dtype=torch.int16, device=dev); ops.dropout_mask(mask, 0.4, 7)
 hw = torch.randn(4, 16, device=dev)
 dx = torch.empty(N, H, H, 16, dtype=torch.bfloat16, device=dev)
 g = ops.head_bwd_grid(N, H, H)

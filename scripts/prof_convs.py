@@ -28,7 +28,7 @@ def level0():
     part = torch.empty(g, 2, 16, device=dev)
     hw, hb = torch.randn(4, 16, device=dev), torch.randn(4, device=dev)
     heat = torch.empty(N, 4, H, H, device=dev)
-    dmask = (torch.rand(N, H, H, 16, device=dev) > 0.4).to(torch.uint8)
+    dmask = torch.empty(N, H, H, dtype=torch.int16, device=dev); ops.dropout_mask(dmask, 0.4, 7)
     timeit("b2 K16 plain", lambda: ops.conv([src], N, H, H, w, 16, nt, 9, bias=bias, relu=True, out=out))
     timeit("b2 K16 +st", lambda: ops.conv([src], N, H, H, w, 16, nt, 9, bias=bias, out=out, stats_partial=part))
     timeit("b2 K16 +st+mask", lambda: ops.conv([src], N, H, H, w, 16, nt, 9, out=out, relu_mask_src=mask, stats_partial=part))

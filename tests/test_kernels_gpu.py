@@ -120,7 +120,7 @@ def test_fused_head_sigmoid_dropout(with_mask):
     out = torch.empty(N, H, W, 16, dtype=torch.bfloat16, device=DEV)
     heat = torch.empty(N, 4, H, W, device=DEV)
     lg = torch.empty(N, 4, H, W, device=DEV)
-    m8 = mask.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(DEV) if with_mask else None
+    m8 = ops.pack_keep_mask(mask.to(DEV)) if with_mask else None
     ops.conv([nhwc(x)], N, H, W, wp, 16, 16, 9, bias=b.to(DEV), relu=True, out=out,
              head=(hw.to(DEV), hb.to(DEV), heat, lg, m8, 1 / 0.6 if with_mask else 1.0))
     close(nchw(out), y, 6e-3, "head conv out")
@@ -353,7 +353,7 @@ def test_head_backward(mode):
     g = ops.head_bwd_grid(N, H, W)
     partial = torch.full((g, 4 * 16 + 4 + 1 + 16), float("nan"), device=DEV)
     dx = torch.empty(N, H, W, 16, dtype=torch.bfloat16, device=DEV)
-    m8 = mask.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(DEV)
+    m8 = ops.pack_keep_mask(mask.to(DEV))
     ops.head_bwd(heat.to(DEV), None if dheat is None else dheat.to(DEV), target.to(DEV) if mode != "upstream" else None, coef, nhwc(x), m8, 1 / 0.6,
                  hw.to(DEV), dx, partial, loss_kind=1 if mode == "focal" else 0, gamma=3.0)
     dx_ref = xx.grad * (x > 0)
@@ -383,12 +383,16 @@ def test_adamw_matches_reference_semantics(golden):
 
 
 def test_dropout_mask_rate_and_determinism():
-    m1 = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    m1 = torch.empty(4, 128, 128, dtype=torch.int16, device=DEV)  # one 16-bit keep word per pixel
     m2 = torch.empty_like(m1)
     ops.dropout_mask(m1, 0.4, 1234)
     ops.dropout_mask(m2, 0.4, 1234)
-    assert torch.equal(m1, m2) and int(m1.max()) == 1
-    assert abs(float(m1.float().mean()) - 0.6) < 5e-3
+    assert torch.equal(m1, m2)
+    keep = ops.unpack_keep_mask(m1)  # [N,16,H,W] bool
+    assert abs(float(keep.float().mean()) - 0.6) < 5e-3
+    per_channel = keep.float().mean((0, 2, 3))
+    assert float((per_channel - 0.6).abs().max()) < 2e-2  # every bit position is used and unbiased
+    assert torch.equal(ops.pack_keep_mask(keep), m1)
     ops.dropout_mask(m2, 0.4, 99)
     assert not torch.equal(m1, m2)
 

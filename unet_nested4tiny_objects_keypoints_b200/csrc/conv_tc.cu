@@ -62,7 +62,7 @@ struct ConvTcParams {
   float* heat;
   float* logit;
   int head_classes;
-  const uint8_t* drop_mask;
+  const uint16_t* drop_mask;
   float drop_scale;
   const __nv_bfloat16* addend;
   const __nv_bfloat16* relu_mask_src;
@@ -128,7 +128,7 @@ struct EpiArgs {
   __nv_bfloat16* pooled;
   float* heat;
   float* logit;
-  const uint8_t* drop_mask;
+  const uint16_t* drop_mask;
   float drop_scale;
   const __nv_bfloat16* addend;
   const __nv_bfloat16* relu_mask_src;
@@ -252,10 +252,9 @@ __device__ __forceinline__ void epilogue_group(const EpiArgs& p, float (&v)[16],
     if (valid) {
       if constexpr (TRAIN) {
         if (p.drop_mask) {
-          const uint4 dm = __ldg(reinterpret_cast<const uint4*>(p.drop_mask + pix * 16));
-          const uint32_t dw[4] = {dm.x, dm.y, dm.z, dm.w};
+          const uint32_t dm = __ldg(p.drop_mask + pix);  // 16 keep bits of this pixel
 #pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] = ((dw[k >> 2] >> (8 * (k & 3))) & 0xFF) ? v[k] * p.drop_scale : 0.f;
+          for (int k = 0; k < 16; ++k) v[k] = ((dm >> k) & 1u) ? v[k] * p.drop_scale : 0.f;
         }
       }
       const size_t plane = size_t(p.H) * p.W;
@@ -285,7 +284,8 @@ __device__ __forceinline__ void epilogue_group(const EpiArgs& p, float (&v)[16],
 // `eoff` = element offset of the step's first value in the NHWC output (and in every same-shaped operand).
 template <int G>
 struct EpiOperands {  // training-only operands of the step, fetched BEFORE the TMEM load is waited for
-  uint4 a[2 * G], m[2 * G], x[2 * G], d[G];
+  uint4 a[2 * G], m[2 * G], x[2 * G];
+  uint32_t dbits;  // head dropout: 16 keep bits per pixel, the (up to two) pixels of the step in one word
 };
 template <int G, bool HEAD, bool TRAIN>
 __device__ __forceinline__ void epi_prefetch(const EpiArgs& p, EpiOperands<G>& t, size_t eoff, bool valid) {
@@ -293,8 +293,7 @@ __device__ __forceinline__ void epi_prefetch(const EpiArgs& p, EpiOperands<G>& t
     const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int i = 0; i < 2 * G; ++i) t.a[i] = t.m[i] = t.x[i] = z;
-#pragma unroll
-    for (int i = 0; i < G; ++i) t.d[i] = z;
+    t.dbits = 0xFFFFFFFFu;
     if (valid) {
       if (p.addend) {
         const uint4* q = reinterpret_cast<const uint4*>(p.addend + eoff);
@@ -313,9 +312,8 @@ __device__ __forceinline__ void epi_prefetch(const EpiArgs& p, EpiOperands<G>& t
       }
       if constexpr (HEAD) {
         if (p.drop_mask) {
-          const uint4* q = reinterpret_cast<const uint4*>(p.drop_mask + eoff);  // (the head conv has 16 channels: element offset = byte offset)
-#pragma unroll
-          for (int i = 0; i < G; ++i) t.d[i] = __ldg(q + i);
+          // (the head conv has 16 channels: eoff / 16 = pixel index; two adjacent pixels, x0 even: one aligned 32-bit word)
+          t.dbits = G == 2 ? __ldg(reinterpret_cast<const uint32_t*>(p.drop_mask + (eoff >> 4))) : uint32_t(__ldg(p.drop_mask + (eoff >> 4)));
         }
       }
     }
@@ -338,9 +336,6 @@ __device__ __forceinline__ void epi_l2_prefetch(const EpiArgs& p, size_t eoff, b
     if (p.addend) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.addend + eoff));
     if (p.relu_mask_src) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.relu_mask_src + eoff));
     if (p.stats_aux) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.stats_aux + eoff));
-    if constexpr (HEAD) {
-      if (p.drop_mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.drop_mask + eoff));
-    }
   }
 }
 
@@ -412,9 +407,8 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, const uint32_t (&ra
         for (int k = 0; k < 16; ++k) hv[px][k] = v[k];
         if constexpr (TRAIN) {
           if (p.drop_mask) {
-            const uint32_t dw[4] = {t.d[px].x, t.d[px].y, t.d[px].z, t.d[px].w};
 #pragma unroll
-            for (int k = 0; k < 16; ++k) hv[px][k] = ((dw[k >> 2] >> (8 * (k & 3))) & 0xFF) ? v[k] * p.drop_scale : 0.f;
+            for (int k = 0; k < 16; ++k) hv[px][k] = ((t.dbits >> (16 * px + k)) & 1u) ? v[k] * p.drop_scale : 0.f;
           }
         }
       }

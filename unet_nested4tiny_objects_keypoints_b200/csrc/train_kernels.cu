@@ -333,7 +333,7 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dyh, const uint4* 
 // FOCAL is a compile-time switch: the powf/logf path costs registers and instructions the MSE / upstream path must not pay.
 template <int NCLS, bool FOCAL>
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ heat, const float* __restrict__ dheat, const float* __restrict__ target,
-                                                       float gamma, float coef, const uint2* __restrict__ x, const uint32_t* __restrict__ mask, float drop_scale,
+                                                       float gamma, float coef, const uint2* __restrict__ x, const uint16_t* __restrict__ mask, float drop_scale,
                                                        const float* __restrict__ head_w, uint2* __restrict__ dx, float* __restrict__ partial,
                                                        int N, long HW) {
   unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       xq[u] = __ldg(x + 4 * (4 * i4 + u) + sub);
-      mq[u] = mask ? __ldg(mask + 4 * (4 * i4 + u) + sub) : 0x01010101u;
+      mq[u] = mask ? uint32_t(__ldg(mask + 4 * i4 + u)) >> (4 * sub) : 0xFu;  // the keep bits of this lane's four channels
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       float g[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float keep = mask ? (((mw >> (8 * k)) & 0xFF) ? drop_scale : 0.f) : 1.f;
+        const float keep = mask ? (((mw >> k) & 1u) ? drop_scale : 0.f) : 1.f;
         const float xd = xv[k] * keep;
         float s = 0.f;
 #pragma unroll
@@ -496,7 +496,7 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16, x *= 0x7feb352du, x ^= x >> 15, x *= 0x846ca68bu, x ^= x >> 16;
   return x;
 }
-__global__ void dropout_mask_kernel(uint4* __restrict__ out, long n16, uint32_t seed_lo, uint32_t seed_hi, uint32_t thresh16,
+__global__ void dropout_mask_kernel(uint4* __restrict__ out, long n8, uint32_t seed_lo, uint32_t seed_hi, uint32_t thresh16,
                                     const unsigned long long* __restrict__ counter) {
   unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
   unpp::pdl_trigger();
@@ -504,20 +504,22 @@ __global__ void dropout_mask_kernel(uint4* __restrict__ out, long n16, uint32_t 
     const unsigned long long c = (*counter + 1ull) * 0x9E3779B97F4A7C15ull;
     seed_lo ^= uint32_t(c), seed_hi ^= uint32_t(c >> 32);
   }
-  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < n16; i += long(gridDim.x) * blockDim.x) {
-    uint32_t wds[4];
+  // one thread = eight pixels = eight 16-bit keep words (one 16-byte store); a hash yields two 16-bit uniforms
+  for (long t = blockIdx.x * long(blockDim.x) + threadIdx.x; t < n8; t += long(gridDim.x) * blockDim.x) {
+    uint32_t wds[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint32_t packed = 0;
+    for (int px = 0; px < 8; ++px) {
+      const long i = t * 8 + px;
+      uint32_t bits = 0;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint32_t r = mix32(mix32(uint32_t(i) * 8u + q * 2 + h + seed_lo) ^ (uint32_t(i >> 29) + seed_hi));
-        packed |= ((r & 0xFFFF) >= thresh16 ? 1u : 0u) << (16 * h);
-        packed |= ((r >> 16) >= thresh16 ? 1u : 0u) << (16 * h + 8);
+      for (int h = 0; h < 8; ++h) {
+        const uint32_t r = mix32(mix32(uint32_t(i) * 8u + h + seed_lo) ^ (uint32_t(i >> 29) + seed_hi));
+        bits |= ((r & 0xFFFF) >= thresh16 ? 1u : 0u) << (2 * h);
+        bits |= ((r >> 16) >= thresh16 ? 1u : 0u) << (2 * h + 1);
       }
-      wds[q] = packed;
+      wds[px >> 1] |= bits << (16 * (px & 1));
     }
-    out[i] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+    out[t] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
   }
 }
 
@@ -604,7 +606,7 @@ extern "C" int unpp_bn_bwd_apply(const void* dyh, const void* z, const float* me
 
 extern "C" int unpp_head_bwd_grid(int N, int H, int W) { return grid_for(long(N) * H * W, 256, 2); }
 
-extern "C" int unpp_head_bwd(const float* heat, const float* dheat, const float* target, int loss_kind, float gamma, float coef, const void* x, const uint8_t* drop_mask,
+extern "C" int unpp_head_bwd(const float* heat, const float* dheat, const float* target, int loss_kind, float gamma, float coef, const void* x, const uint16_t* drop_mask,
                              float drop_scale, const float* head_w, int classes, void* dx, float* partial, int N, int H, int W,
                              unpp_stream_t stream) {
   if (!heat || (!dheat && !target) || !x || !head_w || !dx || !partial || N < 1 || H < 1 || W < 1)
@@ -617,11 +619,11 @@ extern "C" int unpp_head_bwd(const float* heat, const float* dheat, const float*
 #define LAUNCH(NC)                                                                                                                        \
   if (loss_kind == 1)                                                                                                                     \
     unpp::launch(head_bwd_kernel<NC, true>, grid, 256, 0, STREAM(stream), heat, dheat, target, gamma, coef, reinterpret_cast<const uint2*>(x),           \
-                                                        reinterpret_cast<const uint32_t*>(drop_mask), drop_scale, head_w,                  \
+                                                        drop_mask, drop_scale, head_w,                  \
                                                         reinterpret_cast<uint2*>(dx), partial, N, HW);                                     \
   else                                                                                                                                    \
     unpp::launch(head_bwd_kernel<NC, false>, grid, 256, 0, STREAM(stream), heat, dheat, target, gamma, coef, reinterpret_cast<const uint2*>(x),          \
-                                                        reinterpret_cast<const uint32_t*>(drop_mask), drop_scale, head_w,                  \
+                                                        drop_mask, drop_scale, head_w,                  \
                                                         reinterpret_cast<uint2*>(dx), partial, N, HW)
   switch (classes) {
     case 1: LAUNCH(1); break;
@@ -654,11 +656,12 @@ extern "C" int unpp_adamw_dev(float* p, const float* g, float* m, float* v, long
   return UNPP_OK;
 }
 
-extern "C" int unpp_dropout_mask(uint8_t* mask, long n, float p_drop, uint64_t seed, const uint64_t* step_counter, unpp_stream_t stream) {
-  if (!mask || n < 16 || (n & 15) || !(p_drop >= 0.f) || !(p_drop < 1.f)) return unpp::fail(UNPP_ERR_BAD_ARG, "dropout_mask: n must be a positive multiple of 16, 0 <= p < 1");
+extern "C" int unpp_dropout_mask(uint16_t* mask, long npix, float p_drop, uint64_t seed, const uint64_t* step_counter, unpp_stream_t stream) {
+  if (!mask || npix < 8 || (npix & 7) || (reinterpret_cast<uintptr_t>(mask) & 15) || !(p_drop >= 0.f) || !(p_drop < 1.f))
+    return unpp::fail(UNPP_ERR_BAD_ARG, "dropout_mask: npix must be a positive multiple of 8, mask 16-byte aligned, 0 <= p < 1");
   const uint32_t thresh = uint32_t(double(p_drop) * 65536.0 + 0.5);
-  unpp::launch(dropout_mask_kernel, grid_for(n / 16, 256), 256, 0, STREAM(stream), reinterpret_cast<uint4*>(mask), n / 16, uint32_t(seed), uint32_t(seed >> 32),
-                                                                         thresh, reinterpret_cast<const unsigned long long*>(step_counter));
+  unpp::launch(dropout_mask_kernel, grid_for(npix / 8, 256), 256, 0, STREAM(stream), reinterpret_cast<uint4*>(mask), npix / 8, uint32_t(seed), uint32_t(seed >> 32),
+               thresh, reinterpret_cast<const unsigned long long*>(step_counter));
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("dropout_mask: launch");
   return UNPP_OK;
 }

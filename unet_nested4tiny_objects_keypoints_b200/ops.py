@@ -146,7 +146,7 @@ def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Te
          relu=False, mode=MODE_CONV, out=None, head=None, addend=None, relu_mask_src=None, stats_partial=None, stats_aux=None, aux_mean=None,
          aux_istd=None, strided=None, b2=False, lowres=None, bias_classes=0, pooled=None) -> None:
     """One unpp_conv_tc launch.  ``srcs``: NHWC bf16 tensors (virtual concat along K).
-    ``head`` = (w fp32 [cls,16], b fp32 [cls], heat fp32 NCHW, logit|None, drop_mask u8 NHWC|None, drop_scale).
+    ``head`` = (w fp32 [cls,16], b fp32 [cls], heat fp32 NCHW, logit|None, drop_mask int16 [N,H,W] keep bits|None, drop_scale).
     ``strided`` = [(oy, ox), ...]: every source is a [N,2H,2W,C] tensor read at (2y+oy, 2x+ox)."""
     a = _conv_args(srcs, N, H, W, n_total, n_tile, taps, strided, b2)
     a.wpacked, a.bias = wpacked.data_ptr(), _ptr(bias)
@@ -387,11 +387,27 @@ def adamw_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_counter, ste
 
 
 def dropout_mask(mask: torch.Tensor, p_drop: float, seed: int, step_counter: Optional[torch.Tensor] = None) -> None:
-    assert mask.dtype == torch.uint8 and mask.is_cuda and mask.is_contiguous()
+    """Fill ``mask`` (int16, one word per pixel: bit c = keep channel c of the 16-channel head input) for nn.Dropout(p_drop)."""
+    assert mask.dtype == torch.int16 and mask.is_cuda and mask.is_contiguous()
     _count()
     with _Traced("dropout_mask", 0, 0):
         _lib.check(lib().unpp_dropout_mask(mask.data_ptr(), mask.numel(), float(p_drop), int(seed) & (2**64 - 1), _ptr(step_counter), _stream()),
-               "unpp_dropout_mask")
+                   "unpp_dropout_mask")
+
+
+def pack_keep_mask(keep: torch.Tensor) -> torch.Tensor:
+    """Boolean / 0-1 keep-mask [N,16,H,W] (the layout nn.Dropout sees) -> the kernels' int16 [N,H,W] bit words."""
+    assert keep.dim() == 4 and keep.shape[1] == 16
+    w = torch.zeros(keep.shape[0], keep.shape[2], keep.shape[3], dtype=torch.int32, device=keep.device)
+    for c in range(16):
+        w |= (keep[:, c] != 0).to(torch.int32) << c
+    return (w - ((w >> 15) << 16)).to(torch.int16)  # two's-complement wrap of bit 15
+
+
+def unpack_keep_mask(words: torch.Tensor) -> torch.Tensor:
+    """int16 [N,H,W] bit words -> bool [N,16,H,W]."""
+    w = words.to(torch.int32) & 0xFFFF
+    return torch.stack([((w >> c) & 1).bool() for c in range(16)], 1)
 
 
 def create_heatmap(keypoints: torch.Tensor, H: int, W: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -86,7 +86,7 @@ class TrainState:
                 act(nm, lvl)
         act("tmpX11", 1)
         for k in range(3):
-            t[f"mask{k}"] = torch.ones(B, H, W, 16, dtype=torch.uint8, device=dev)
+            t[f"mask{k}"] = torch.full((B, H, W), -1, dtype=torch.int16, device=dev)  # dropout keep bits, one 16-bit word per pixel
             # head 3 is X03's only consumer: its (already ReLU-masked) input gradient IS dZ2 of up_concat03
             t[f"dXh{k}"] = t["dZ203"] if k == 2 else torch.empty(B, H, W, 16, **bf)
         self.head_grid = ops.head_bwd_grid(B, H, W)
@@ -472,7 +472,7 @@ def _prepare_dropout(ts: TrainState) -> None:
     forced = getattr(m, "_forced_dropout_masks", None)
     if forced is not None:  # parity runs: externally supplied keep-masks [B,16,H,W] (see tests)
         for k in range(3):
-            ts.t[f"mask{k}"].copy_(forced[k].to(ts.eng.device).permute(0, 2, 3, 1).to(torch.uint8))
+            ts.t[f"mask{k}"].copy_(ops.pack_keep_mask(forced[k].to(ts.eng.device)))
         ts.use_masks, ts.drop_scale = True, 1.0 / (1.0 - p)
     elif p > 0.0:
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # torch's CPU generator: torch.manual_seed() reproduces the run
