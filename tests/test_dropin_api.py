@@ -87,3 +87,27 @@ def test_struct_layouts_match_the_header():
     assert lib.unpp_sizeof_pack_args() == ctypes.sizeof(_lib.PackArgs)
     assert lib.unpp_sizeof_wgrad_args() == ctypes.sizeof(_lib.WgradArgs)
     assert lib.unpp_sizeof_reduce_job() == ctypes.sizeof(_lib.ReduceJob)
+
+
+def test_keep_mask_bit_words_round_trip_on_cpu():
+    """The head dropout keep-mask travels as one 16-bit word per pixel (bit c = keep channel c): pack/unpack are exact inverses."""
+    import torch
+    from unet_nested4tiny_objects_keypoints_b200 import ops
+    keep = torch.rand(2, 16, 5, 7, generator=torch.Generator().manual_seed(3)) >= 0.4
+    words = ops.pack_keep_mask(keep)
+    assert words.dtype == torch.int16 and words.shape == (2, 5, 7)
+    assert torch.equal(ops.unpack_keep_mask(words), keep)
+    assert int(ops.pack_keep_mask(torch.ones(1, 16, 1, 1, dtype=torch.bool)).item()) == -1  # all sixteen bits set
+
+
+def test_recording_state_is_per_thread():
+    """nn.DataParallel drives one host thread per replica: the deferred-reduction queue of one thread must not leak into another."""
+    import threading
+    from unet_nested4tiny_objects_keypoints_b200 import ops
+    ops.begin_reduce_queue()
+    seen = []
+    th = threading.Thread(target=lambda: seen.append(ops.reduce_queue_active()))
+    th.start()
+    th.join()
+    assert ops.reduce_queue_active() and seen == [False]
+    ops._tls.reduce_queue = None

@@ -69,7 +69,7 @@ def test_full_size_training_step_properties():
         loss = sum(torch.nn.functional.mse_loss(o, target.cuda()) for o in outs) / 3
         (loss * scale).backward()
         torch.cuda.synchronize()
-        return float(loss), {k: p.grad.clone() for k, p in m.named_parameters()}, m
+        return float(loss.detach()), {k: p.grad.clone() for k, p in m.named_parameters()}, m
 
     loss1, g1, m1 = grads_for(1.0)
     loss1b, g1b, _ = grads_for(1.0)

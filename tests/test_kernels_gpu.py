@@ -218,13 +218,13 @@ def test_wgrad_deconv_strided_dz(N, H, W, cin, cout):
     dst4 = torch.zeros(cin, cout, 2, 2, device=DEV)
     bias_part = torch.randn(7, 2 * cout, device=DEV)
     bias_out = torch.zeros(cout, device=DEV)
-    ops.reduce_queue = []
+    ops.begin_reduce_queue()
     for pq in range(4):
         ops.wgrad_reduce(partial4, g4, 1, cin, cout, dst4, 0, cin, 4, cout * 4, 0, dst_offset=pq, partial_offset=pq * g4 * cin * cout, defer=True)
     ops.reduce_partials(bias_part, 7, 2 * cout, cout, bias_out, scale=0.5, defer=True)
     assert float(dst4.abs().max()) == 0.0  # nothing ran yet
     ops.flush_reduce_queue({}, DEV)
-    assert ops.reduce_queue is None
+    assert not ops.reduce_queue_active()
     close(dst4.cpu(), w.grad, 2e-3, "deconv wgrad (4 taps, batched reduce)")
     close(bias_out.cpu(), 0.5 * bias_part[:, :cout].double().sum(0).cpu(), 1e-5, "batched flat reduce")
 

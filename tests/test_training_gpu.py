@@ -210,3 +210,41 @@ def test_gradient_noise_is_no_worse_than_torch_autocast_bf16():
         if _is_pre_bn_bias(k):
             continue
         assert ours[k][0] <= 1.5 * theirs[k][0] + 1e-2, (k, ours[k], theirs[k])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (nn.DataParallel, trainer/trainer.py:336-338)")
+def test_nn_dataparallel_like_the_reference_trainer():
+    """The reference's multi-GPU mode wraps the model in nn.DataParallel (trainer.py:338): replicas are rebuilt at every
+    forward with broadcast copies of the weights, every replica normalises with its own batch statistics, gradients are
+    summed onto the master parameters.  Two iterations with a weight update in between (a stale replica would show)."""
+    sd = O.synth_state_dict(seed=24)
+    g = torch.Generator().manual_seed(5)
+    B, H, W = 4, 32, 32
+    m = pkg.UNet_Nested()
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    m.drop_out.p = 0.0
+    dp = torch.nn.DataParallel(m, device_ids=[0, 1])
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running_" not in k}
+    for it in range(2):
+        x = torch.randn(B, 3, H, W, generator=g)
+        target = torch.rand(B, 4, H, W, generator=g)
+        m.zero_grad()
+        outs = dp(x.cuda())
+        loss = sum(F.mse_loss(o, target.cuda()) for o in outs) / 3
+        loss.backward()
+        # oracle: the two halves separately (own BatchNorm statistics), one loss over the gathered outputs
+        for p in params.values():
+            p.grad = None
+        full = dict(sd)
+        full.update(params)
+        halves = [O.forward(full, x[r * 2:(r + 1) * 2], training=True, dropout_masks=None) for r in range(2)]
+        routs = [torch.cat([h[k] for h in halves]) for k in range(3)]
+        rloss = sum(F.mse_loss(o, target) for o in routs) / 3
+        rloss.backward()
+        assert abs(float(loss.detach()) - float(rloss.detach())) <= 1e-2 * float(rloss.detach())
+        check_grads({k: p.grad for k, p in m.named_parameters()}, {k: p.grad for k, p in params.items()})
+        with torch.no_grad():  # the same SGD step on both sides
+            for k, p in m.named_parameters():
+                p -= 0.5 * params[k].grad.cuda()
+                params[k] -= 0.5 * params[k].grad

@@ -33,6 +33,18 @@ bool pdl_enabled() {
   return on != 0;
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  return dev;
+}
+
+int fail_cuda_err(const char* what, cudaError_t e) {
+  snprintf(last_error_buf(), 512, "%s: %s", what, cudaGetErrorString(e));
+  cudaGetLastError();  // clear the sticky-free error state
+  return UNPP_ERR_CUDA;
+}
+
 int num_sms() {
   // Immutable per-device cache (indexed by device ordinal; written once with the same value).
   static int cache[64] = {0};

@@ -12,6 +12,8 @@ char* last_error_buf();
 int fail(int code, const char* fmt, ...);
 int fail_cuda(const char* what);  // formats cudaGetLastError() and returns UNPP_ERR_CUDA
 int num_sms();
+int current_device();  // ordinal of the calling thread's device, clamped to [0, 63]
+int fail_cuda_err(const char* what, cudaError_t e);  // formats e and returns UNPP_ERR_CUDA
 bool pdl_enabled();  // programmatic dependent launch for every libunpp kernel (UNPP_PDL=1 switches it on)
 
 // With UNPP_PDL=1 every libunpp kernel is launched with the programmatic-stream-serialization attribute and runs
@@ -23,6 +25,17 @@ bool pdl_enabled();  // programmatic dependent launch for every libunpp kernel (
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel: in-process multi-GPU use
+// (nn.DataParallel) must opt in once on every device.  `done` is the kernel's own static flag array.
+template <typename K>
+inline cudaError_t opt_in_smem(K kernel, int bytes, unsigned char (&done)[64]) {
+  const int dev = current_device();
+  if (done[dev]) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[dev] = 1;  // idempotent: a race between replicas' threads only repeats the call
+  return e;
+}
 
 template <typename... P, typename... A>
 inline cudaError_t launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {

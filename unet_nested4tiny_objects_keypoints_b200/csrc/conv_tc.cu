@@ -1152,13 +1152,11 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   const dim3 grid(pl.grid_x, pl.grid_y);
 #define UNPP_LAUNCH(D, Hd, T)                                                                                                         \
   do {                                                                                                                                \
-    static int opted_in = 0; /* attribute is per-function, idempotent */                                                              \
-    if (!opted_in) {                                                                                                                  \
-      if (cudaFuncSetAttribute(conv_tc_kernel<D, Hd, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (T ? 204 : 224) * 1024) != cudaSuccess) \
-        return unpp::fail_cuda("conv_tc: cudaFuncSetAttribute");                                                                      \
-      opted_in = 1;                                                                                                                   \
-    }                                                                                                                                 \
-    unpp::launch(conv_tc_kernel<D, Hd, T>, grid, block_threads(T), pl.smem_total, stream, p);                                                           \
+    static unsigned char opted_in[64] = {0}; /* per variant and device */                                                             \
+    if (cudaError_t e = unpp::opt_in_smem(conv_tc_kernel<D, Hd, T>, (T ? 204 : 224) * 1024, opted_in))                                \
+      return unpp::fail_cuda_err("conv_tc: cudaFuncSetAttribute", e);                                                                 \
+    if (cudaError_t e = unpp::launch(conv_tc_kernel<D, Hd, T>, grid, block_threads(T), pl.smem_total, stream, p))                     \
+      return unpp::fail_cuda_err("conv_tc: launch", e);                                                                               \
   } while (0)
   if (deconv) UNPP_LAUNCH(true, false, false);
   else if (head && train) UNPP_LAUNCH(false, true, true);
@@ -1166,6 +1164,5 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   else if (train) UNPP_LAUNCH(false, false, true);
   else UNPP_LAUNCH(false, false, false);
 #undef UNPP_LAUNCH
-  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("conv_tc: launch");
   return UNPP_OK;
 }

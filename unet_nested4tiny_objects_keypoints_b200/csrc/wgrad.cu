@@ -260,14 +260,10 @@ int make_plan(const UnppWgradArgs* a, Plan* pl) {
 
 template <int TAPS, int PPW>
 int launch(const WgradParams& p, const Plan& pl, cudaStream_t stream) {
-  static bool opted_in = false;  // per instantiation; the attribute is idempotent
-  if (!opted_in) {
-    if (cudaFuncSetAttribute(wgrad_kernel<TAPS, PPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
-      return unpp::fail_cuda("wgrad: cudaFuncSetAttribute");
-    opted_in = true;
-  }
-  unpp::launch(wgrad_kernel<TAPS, PPW>, dim3(pl.grid_x, pl.njobs, pl.grid_z), kThreads, pl.smem_total, stream, p);
-  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("wgrad: launch");
+  static unsigned char opted_in[64] = {0};  // per instantiation and device
+  if (cudaError_t e = unpp::opt_in_smem(wgrad_kernel<TAPS, PPW>, 220 * 1024, opted_in)) return unpp::fail_cuda_err("wgrad: cudaFuncSetAttribute", e);
+  if (cudaError_t e = unpp::launch(wgrad_kernel<TAPS, PPW>, dim3(pl.grid_x, pl.njobs, pl.grid_z), kThreads, pl.smem_total, stream, p))
+    return unpp::fail_cuda_err("wgrad: launch", e);
   return UNPP_OK;
 }
 

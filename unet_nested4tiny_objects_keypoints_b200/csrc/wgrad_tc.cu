@@ -449,14 +449,9 @@ int wgrad_tc_launch(const UnppWgradArgs* a, cudaStream_t stream) {
   p.zrows = pl.dc ? 2 * pl.TR : pl.TR + 2, p.zy_mul = pl.dc ? 2 : 1, p.zy_org = pl.dc ? 0 : -1, p.zrow_mul = pl.dc ? 2 : 1;
   p.zbox_bytes = pl.zslot / pl.nq;
   p.partial = a->partial;
-  static bool opted_in = false;  // the attribute is idempotent
-  if (!opted_in) {
-    if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess)
-      return unpp::fail_cuda("wgrad_tc: cudaFuncSetAttribute");
-    opted_in = true;
-  }
-  unpp::launch(wgrad_tc_kernel, dim3(pl.grid_x, pl.njobs), kThreads, pl.smem_total, stream, p);
-  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("wgrad_tc: launch");
+  static unsigned char opted_in[64] = {0};  // per device
+  if (cudaError_t e = unpp::opt_in_smem(wgrad_tc_kernel, 224 * 1024, opted_in)) return unpp::fail_cuda_err("wgrad_tc: cudaFuncSetAttribute", e);
+  if (cudaError_t e = unpp::launch(wgrad_tc_kernel, dim3(pl.grid_x, pl.njobs), kThreads, pl.smem_total, stream, p)) return unpp::fail_cuda_err("wgrad_tc: launch", e);
   return UNPP_OK;
 }
 

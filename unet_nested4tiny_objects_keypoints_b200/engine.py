@@ -67,6 +67,16 @@ def compose_deconv_conv(w_conv_u: torch.Tensor, w_up: torch.Tensor, b_up: torch.
     return comp.float().contiguous(), table.float().contiguous()
 
 
+def named_params(model):
+    """``model.named_parameters()`` that also works on nn.DataParallel replicas: a replica's parameters are broadcast copies
+    kept as plain (non-leaf) tensors in ``_former_parameters`` and ``parameters()`` is empty there (torch/nn/parallel/replicate.py)."""
+    for prefix, mod in model.named_modules():
+        src = mod._former_parameters if getattr(mod, "_is_replica", False) else mod._parameters
+        for k, v in src.items():
+            if v is not None:
+                yield (prefix + "." + k if prefix else k), v
+
+
 class Engine:
     def __init__(self, model, device: torch.device):
         if device.type != "cuda":
@@ -90,7 +100,7 @@ class Engine:
 
     # ------------------------------------------------------------------------------ weights
     def _param_key(self):
-        return tuple((p.data_ptr(), p._version) for p in list(self.model.parameters()) + list(self.model.buffers()))
+        return tuple((p.data_ptr(), p._version) for p in [q for _, q in named_params(self.model)] + list(self.model.buffers()))
 
     def _conv_seq(self, name: str, n: int):
         m = self.model

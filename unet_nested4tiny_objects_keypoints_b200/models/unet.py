@@ -134,6 +134,9 @@ class UNet_Nested(nn.Module):
             eng = self._engines.get(key)
             if eng is None:
                 eng = self._engines[key] = Engine(self, device)
+            # nn.DataParallel re-creates its replicas (sharing this dict) at every forward: the cached engine of a device
+            # must read THIS module's parameters, not those of the replica it was built from
+            eng.model = self
         return eng
 
     def __getstate__(self):  # engines hold device buffers and a lock: never pickled / deep-copied

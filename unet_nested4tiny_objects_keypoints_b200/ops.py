@@ -8,6 +8,7 @@ never a fallback.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Optional, Sequence
 
 import torch
@@ -18,9 +19,11 @@ from ._lib import ConvArgs, PackArgs, ReduceJob, WgradArgs, MODE_CONV, MODE_DECO
 W_SMEM_BUDGET = 96 * 1024  # packed weights of one n_tile kept resident in shared memory
 
 
-pack_record = None  # when a list: pack_weights() appends its validated PackArgs instead of launching (see pack_batched)
+# Per-thread recording state (nn.DataParallel drives one host thread per GPU: module globals would be shared between replicas):
+#   _tls.pack_record  — when a list: pack_weights() appends its validated PackArgs instead of launching (see pack_batched)
+#   _tls.reduce_queue — when a list: reductions called with defer=True are queued for ONE unpp_reduce_batched launch
+_tls = threading.local()
 launch_count = 0   # kernels of libunpp.so enqueued through this module (bench.py reads it for "gpu_launches")
-reduce_queue = None  # when a list: reductions called with defer=True are queued for ONE unpp_reduce_batched launch (flush_reduce_queue)
 trace = None       # when a list: conv()/wgrad() append (label, start_event, end_event, algorithmic_bytes, flops)
 
 
@@ -104,13 +107,23 @@ def pack_weights(src: torch.Tensor, kind: int, taps: int, n_total: int, n_tile: 
     a.kind, a.src_O, a.src_I, a.taps = kind, src.shape[0], src.shape[1], taps
     a.n_total, a.n_tile, a.n_begin = n_total, n_tile, n_begin
     a.k_begin, a.k_count, a.k8_total, a.k_dst8 = k_begin, k_count, k8_total, k_dst8
-    if pack_record is not None:
-        pack_record.append((a, src))  # keep the source tensor alive with its job
+    rec = getattr(_tls, "pack_record", None)
+    if rec is not None:
+        rec.append((a, src))  # keep the source tensor alive with its job
         return dst
     _count()
     with _Traced("pack_weights", 0, 0):
         _lib.check(lib().unpp_pack_weights(C.byref(a), _stream()), "unpp_pack_weights")
     return dst
+
+
+def begin_pack_record() -> None:
+    _tls.pack_record = []
+
+
+def end_pack_record():
+    jobs, _tls.pack_record = getattr(_tls, "pack_record", None), None
+    return jobs
 
 
 def make_pack_table(jobs, device) -> torch.Tensor:
@@ -275,14 +288,22 @@ def _queue_reduce(partial_ptr, dst_ptr, stride, s_co, s_ci, s_tap, nparts, taps,
     j = ReduceJob()
     j.partial, j.dst, j.stride, j.s_co, j.s_ci, j.s_tap = partial_ptr, dst_ptr, stride, s_co, s_ci, s_tap
     j.nparts, j.taps, j.cin_total, j.cout, j.ci_begin, j.ci_count, j.scale = nparts, taps, cin_total, cout, ci_begin, ci_count, scale
-    reduce_queue.append((j, keep))
+    _tls.reduce_queue.append((j, keep))
+
+
+def begin_reduce_queue() -> None:
+    """From here until flush_reduce_queue() reductions called with defer=True on THIS thread are queued, not launched."""
+    _tls.reduce_queue = []
+
+
+def reduce_queue_active() -> bool:
+    return getattr(_tls, "reduce_queue", None) is not None
 
 
 def flush_reduce_queue(cache: dict, device) -> None:
     """Launch every queued reduction as one unpp_reduce_batched and switch queueing off.  The device-resident job
     table is cached by content (pointers are stable across steps), so a captured step replays without host work."""
-    global reduce_queue
-    jobs, reduce_queue = reduce_queue, None
+    jobs, _tls.reduce_queue = getattr(_tls, "reduce_queue", None), None
     if not jobs:
         return
     blocks = 0
@@ -302,7 +323,7 @@ def flush_reduce_queue(cache: dict, device) -> None:
 
 def wgrad_reduce(partial: torch.Tensor, nparts: int, taps: int, cin_total: int, cout: int, dst: torch.Tensor, ci_begin: int, ci_count: int,
                  s_co: int, s_ci: int, s_tap: int, scale: float = 1.0, dst_offset: int = 0, partial_offset: int = 0, defer: bool = False) -> None:
-    if defer and reduce_queue is not None:
+    if defer and reduce_queue_active():
         _queue_reduce(partial.data_ptr() + 4 * partial_offset, dst.data_ptr() + 4 * dst_offset, taps * cin_total * cout, s_co, s_ci, s_tap, nparts, taps,
                       cin_total, cout, ci_begin, ci_count, scale, (partial, dst))
         return
@@ -314,7 +335,7 @@ def wgrad_reduce(partial: torch.Tensor, nparts: int, taps: int, cin_total: int, 
 
 def reduce_partials(partial: torch.Tensor, nparts: int, stride: int, n: int, out: torch.Tensor, scale: float = 1.0, accumulate: bool = False,
                     partial_offset: int = 0, out_offset: int = 0, defer: bool = False) -> None:
-    if defer and reduce_queue is not None and not accumulate:
+    if defer and reduce_queue_active() and not accumulate:
         _queue_reduce(partial.data_ptr() + 4 * partial_offset, out.data_ptr() + 4 * out_offset, stride, 1, 0, 0, nparts, 1, 1, n, 0, 1, scale, (partial, out))
         return
     _count()

@@ -27,7 +27,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
-from .engine import DECODER, DECODER_ORDER, ENCODER, HEAD_OF, Engine
+from .engine import DECODER, DECODER_ORDER, ENCODER, HEAD_OF, Engine, named_params
 from .ops import MODE_DECONV, pick_n_tile
 
 PQ = [(0, 0), (0, 1), (1, 0), (1, 1)]
@@ -37,7 +37,7 @@ PQ = [(0, 0), (0, 1), (1, 0), (1, 1)]
 def flat_layout(model) -> Tuple[Dict[str, Tuple[int, int]], int]:
     """name -> (offset, numel) in ``model.named_parameters()`` order (74 tensors, 553 260 elements)."""
     lay, off = {}, 0
-    for name, p in model.named_parameters():
+    for name, p in named_params(model):
         lay[name] = (off, p.numel())
         off += p.numel()
     return lay, off
@@ -142,16 +142,15 @@ def pack_train(ts: TrainState) -> None:
     The ~60 pack jobs are recorded once into a device-resident table (source pointers are the
     parameters' storage, which stays put) and replayed with ONE launch per step."""
     m = ts.eng.model
-    key = tuple(p.data_ptr() for p in m.parameters())
+    key = tuple(p.data_ptr() for _, p in named_params(m))
     if getattr(ts, "_pack_key", None) == key:
         ops.pack_batched(ts._pack_table, ts._pack_n)
         return
-    ops.pack_record = []
+    ops.begin_pack_record()
     try:
         _pack_train_jobs(ts)
-        jobs = ops.pack_record
     finally:
-        ops.pack_record = None
+        jobs = ops.end_pack_record()
     ts._pack_jobs = jobs  # keeps the source views alive
     ts._pack_table, ts._pack_n, ts._pack_key = ops.make_pack_table(jobs, ts.eng.device), len(jobs), key
     ops.pack_batched(ts._pack_table, ts._pack_n)
@@ -288,7 +287,7 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
 
     # Reductions whose result only the optimizer reads (weight / bias gradients) are queued and run as ONE batched
     # launch at the end of the backward pass; each therefore owns its partial buffer (keyed by the parameter name).
-    ops.reduce_queue = []
+    ops.begin_reduce_queue()
 
     def stats_buf(srcs_C, n_total, nt, taps, h, w, key="stats"):
         g = ops.conv_grid(srcs_C, B, h, w, n_total, nt, taps)
@@ -508,14 +507,14 @@ class _UNetNestedFn(torch.autograd.Function):
         with torch.cuda.device(eng.device):
             backward_train(ts, G, dheats=dh)
         grads = []
-        for name, p in eng.model.named_parameters():
+        for name, p in named_params(eng.model):
             off, n = ts.lay[name]
             grads.append(G[off:off + n].view_as(p) if p.requires_grad else None)
         return (None, None, *grads)
 
 
 def run_autograd(eng: Engine, x: torch.Tensor):
-    params = [p for _, p in eng.model.named_parameters()]
+    params = [p for _, p in named_params(eng.model)]
     if torch.is_grad_enabled() and any(p.requires_grad for p in params):
         return _UNetNestedFn.apply(eng, x, *params)
     # train mode without a graph (e.g. a no_grad warm-up): still batch-stat BN + dropout
