@@ -996,8 +996,8 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
     }
     // widest tile that leaves room for two stages: fewer tiles (less per-tile handshake), more sub-tiles (more issuers busy)
     int TW = a->W > 32 ? 64 : a->W > 16 ? 32 : 16;
-    if (const char* e = getenv("UNPP_B2_TW")) {  // experiment: cap the tile width (more, smaller stages)
-      const int cap = atoi(e);
+    {
+      static const int cap = [] { const char* e = getenv("UNPP_B2_TW"); return e ? atoi(e) : 0; }();  // experiment knob: cap the tile width (read once)
       if ((cap == 16 || cap == 32) && TW > cap) TW = cap;
     }
     for (;; TW >>= 1) {
@@ -1024,8 +1024,8 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
   pl->w_bytes = a->taps * k8 * a->n_tile * 16;
   pl->w_smem_bytes = (pl->w_bytes + 1023) / 1024 * 1024;
   int TW = 64;
-  if (const char* e = getenv("UNPP_TW")) {  // experiment: cap the tile width (more, smaller stages)
-    const int cap = atoi(e);
+  {
+    static const int cap = [] { const char* e = getenv("UNPP_TW"); return e ? atoi(e) : 0; }();  // experiment knob: cap the tile width (read once)
     if (cap == 16 || cap == 32) TW = cap;
   }
   while (TW > 8 && (2 * (TW / 8) * a->n_tile > 512 || TW / 2 >= ((a->W + 7) / 8) * 8)) TW >>= 1;
@@ -1140,10 +1140,7 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   p.stats_partial = a->stats_partial;
   p.stats_aux = reinterpret_cast<const __nv_bfloat16*>(a->stats_aux);
   p.aux_mean = a->aux_mean, p.aux_istd = a->aux_istd;
-  {
-    const char* d = getenv("UNPP_DBG");
-    p.dbg = d ? atoi(d) : 0;
-  }
+  p.dbg = [] { const char* d = getenv("UNPP_DBG"); return d ? atoi(d) : 0; }();  // role-disabling experiment bits (scripts/dbg_conv*.py set it per process run)
 
   const bool deconv = a->mode == UNPP_MODE_DECONV, head = a->head_w != nullptr;
   const bool train = is_train(a);
