@@ -41,8 +41,12 @@ def filters(feature_scale: int = 2) -> List[int]:
 # --------------------------------------------------------------------------------------------
 # state_dict layout (models/unet.py:206-254)
 # --------------------------------------------------------------------------------------------
-def state_dict_spec(in_channels: int = 3, n_classes: int = 4, feature_scale: int = 2) -> "OrderedDict[str, Tuple[Tuple[int, ...], torch.dtype]]":
-    """Key -> (shape, dtype) in the exact registration order of the reference module."""
+def state_dict_spec(in_channels: int = 3, n_classes: int = 4, feature_scale: int = 2, is_deconv: bool = True,
+                    is_batchnorm: bool = True) -> "OrderedDict[str, Tuple[Tuple[int, ...], torch.dtype]]":
+    """Key -> (shape, dtype) in the exact registration order of the reference module.
+    ``is_batchnorm=False`` drops the BatchNorm entries of the encoder (unet.py:129-143: the Sequential is then conv, ReLU);
+    ``is_deconv=False`` replaces ``up.weight/up.bias`` by ``up.1.weight [Cout,Cin,1,1] / up.1.bias`` (unet.py:189-191:
+    Sequential(UpsamplingBilinear2d(2), Conv2d 1x1))."""
     f = filters(feature_scale)
     spec: "OrderedDict[str, Tuple[Tuple[int, ...], torch.dtype]]" = OrderedDict()
     cin = in_channels
@@ -52,11 +56,12 @@ def state_dict_spec(in_channels: int = 3, n_classes: int = 4, feature_scale: int
             p = f"{name}.conv{n}"
             spec[f"{p}.0.weight"] = ((cout, c, 3, 3), torch.float32)
             spec[f"{p}.0.bias"] = ((cout,), torch.float32)
-            spec[f"{p}.1.weight"] = ((cout,), torch.float32)
-            spec[f"{p}.1.bias"] = ((cout,), torch.float32)
-            spec[f"{p}.1.running_mean"] = ((cout,), torch.float32)
-            spec[f"{p}.1.running_var"] = ((cout,), torch.float32)
-            spec[f"{p}.1.num_batches_tracked"] = ((), torch.int64)
+            if is_batchnorm:
+                spec[f"{p}.1.weight"] = ((cout,), torch.float32)
+                spec[f"{p}.1.bias"] = ((cout,), torch.float32)
+                spec[f"{p}.1.running_mean"] = ((cout,), torch.float32)
+                spec[f"{p}.1.running_var"] = ((cout,), torch.float32)
+                spec[f"{p}.1.num_batches_tracked"] = ((), torch.int64)
             c = cout
         cin = cout
     # unetUp(in_size, out_size, is_deconv, n_concat) — unet.py:182-187, 226-236
@@ -69,8 +74,12 @@ def state_dict_spec(in_channels: int = 3, n_classes: int = 4, feature_scale: int
             spec[f"{name}.conv.conv{n}.0.weight"] = ((cout, c, 3, 3), torch.float32)
             spec[f"{name}.conv.conv{n}.0.bias"] = ((cout,), torch.float32)
             c = cout
-        spec[f"{name}.up.weight"] = ((cin_, cout, 2, 2), torch.float32)
-        spec[f"{name}.up.bias"] = ((cout,), torch.float32)
+        if is_deconv:
+            spec[f"{name}.up.weight"] = ((cin_, cout, 2, 2), torch.float32)
+            spec[f"{name}.up.bias"] = ((cout,), torch.float32)
+        else:
+            spec[f"{name}.up.1.weight"] = ((cout, cin_, 1, 1), torch.float32)
+            spec[f"{name}.up.1.bias"] = ((cout,), torch.float32)
     for h in HEADS:
         spec[f"{h}.weight"] = ((n_classes, f[0], 1, 1), torch.float32)
         spec[f"{h}.bias"] = ((n_classes,), torch.float32)
@@ -92,9 +101,9 @@ def synth_state_dict(seed: int, dtype=torch.float32, **kw) -> "OrderedDict[str, 
             sd[k] = (torch.rand(shape, generator=g) + 0.5).to(dtype)
         elif k.endswith("running_mean"):
             sd[k] = (torch.randn(shape, generator=g) * 0.2).to(dtype)
-        elif ".1.weight" in k:
+        elif ".1.weight" in k and ".up." not in k:
             sd[k] = (1 + 0.1 * torch.randn(shape, generator=g)).to(dtype)
-        elif ".1.bias" in k:
+        elif ".1.bias" in k and ".up." not in k:
             sd[k] = (0.1 * torch.randn(shape, generator=g)).to(dtype)
         elif k.endswith("bias"):
             sd[k] = (torch.rand(shape, generator=g) * 0.2 - 0.1).to(dtype)
@@ -130,8 +139,14 @@ def _unet_conv2(sd, prefix: str, x, bn: bool, training: bool, new_stats: Optiona
 
 
 def _unet_up(sd, prefix: str, high, lows: Sequence[torch.Tensor], inter: Optional[dict]):
-    """unetUp.forward (unet.py:198-202): cat([ConvTranspose2d(k2,s2)(high), *lows], 1) -> unetConv2 (no BN)."""
-    up = F.conv_transpose2d(high, sd[f"{prefix}.up.weight"], sd[f"{prefix}.up.bias"], stride=2)  # unet.py:187
+    """unetUp.forward (unet.py:198-202): cat([up(high), *lows], 1) -> unetConv2 (no BN); ``up`` is ConvTranspose2d(k2,s2)
+    (unet.py:187, is_deconv=True) or UpsamplingBilinear2d(2) [= bilinear, align_corners=True] + Conv2d 1x1 (unet.py:189-191);
+    which one is read off the state_dict keys."""
+    if f"{prefix}.up.weight" in sd:
+        up = F.conv_transpose2d(high, sd[f"{prefix}.up.weight"], sd[f"{prefix}.up.bias"], stride=2)  # unet.py:187
+    else:
+        up = F.interpolate(high, scale_factor=2, mode="bilinear", align_corners=True)  # nn.UpsamplingBilinear2d(scale_factor=2)
+        up = F.conv2d(up, sd[f"{prefix}.up.1.weight"], sd[f"{prefix}.up.1.bias"])
     if inter is not None:
         inter[f"{prefix}.up"] = up
     cat = torch.cat([up, *lows], 1)  # unet.py:200-201: order = [up, low_1, low_2, ...]
@@ -148,10 +163,11 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = False
     means "dropout disabled" (the documented parity policy: torch's RNG stream is not reproducible
     from a custom kernel, so parity runs pass explicit masks or none).  Eval: identity."""
     pool = lambda t: F.max_pool2d(t, 2)  # unet.py:219
-    X00 = _unet_conv2(sd, "conv00", x, True, training, new_stats, inter)
-    X10 = _unet_conv2(sd, "conv10", pool(X00), True, training, new_stats, inter)
-    X20 = _unet_conv2(sd, "conv20", pool(X10), True, training, new_stats, inter)
-    X30 = _unet_conv2(sd, "conv30", pool(X20), True, training, new_stats, inter)
+    bn = "conv00.conv1.1.weight" in sd  # is_batchnorm (unet.py:129-143), read off the state_dict keys
+    X00 = _unet_conv2(sd, "conv00", x, bn, training, new_stats, inter)
+    X10 = _unet_conv2(sd, "conv10", pool(X00), bn, training, new_stats, inter)
+    X20 = _unet_conv2(sd, "conv20", pool(X10), bn, training, new_stats, inter)
+    X30 = _unet_conv2(sd, "conv30", pool(X20), bn, training, new_stats, inter)
     X01 = _unet_up(sd, "up_concat01", X10, [X00], inter)
     X11 = _unet_up(sd, "up_concat11", X20, [X10], inter)
     X21 = _unet_up(sd, "up_concat21", X30, [X20], inter)
@@ -222,6 +238,62 @@ def adamw_reference_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: t
     if weight_decay != 0:
         p = p - decayed  # adamw.py:93
     return p, m, v
+
+
+def sgdw_reference_step(p: torch.Tensor, g: torch.Tensor, buf: Optional[torch.Tensor], lr: float, momentum: float = 0.0, dampening: float = 0.0,
+                        weight_decay: float = 0.0):
+    """The reference's SGDW.step AS SHIPPED (tools/optimizers/sgdw.py:77-110): the momentum buffer is maintained
+    (sgdw.py:95-102: first step ``buf = g``, later ``buf = momentum*buf + (1-dampening)*g``) but the descent direction
+    ``d_p`` is never applied to the parameter — the only write to ``p`` is the decoupled decay ``p -= weight_decay * p``
+    (sgdw.py:107-108), NOT scaled by ``lr``.  Returns new (p, buf); ``buf`` stays None when momentum == 0."""
+    if momentum != 0:
+        buf = g.clone() if buf is None else buf * momentum + (1 - dampening) * g
+    if weight_decay != 0:
+        p = p - weight_decay * p
+    return p, buf
+
+
+def adabound_reference_step(p, g, m, v, step: int, lr: float = 1e-3, betas=(0.9, 0.999), final_lr: float = 0.1, gamma: float = 1e-3,
+                            eps: float = 1e-8, weight_decay: float = 0.0, base_lr: Optional[float] = None):
+    """AdaBound.step without amsbound (tools/optimizers/adabound.py:57-122): L2 decay folded into the gradient (101-102),
+    Adam moments (105-106), per-element step ``clamp(step_size / (sqrt(v)+eps), lower, upper) * m`` with the bounds of
+    lines 119-121 (``final_lr`` scaled by lr/base_lr, base_lr = the lr at construction, adabound.py:49).  ``step`` is 1-based."""
+    b1, b2 = betas
+    base_lr = lr if base_lr is None else base_lr
+    if weight_decay != 0:
+        g = g + weight_decay * p
+    m = m * b1 + (1 - b1) * g
+    v = v * b2 + (1 - b2) * g * g
+    denom = v.sqrt() + eps
+    step_size = lr * math.sqrt(1 - b2 ** step) / (1 - b1 ** step)
+    flr = final_lr * lr / base_lr
+    lower = flr * (1 - 1 / (gamma * step + 1))
+    upper = flr * (1 + 1 / (gamma * step))
+    upd = (torch.full_like(denom, step_size) / denom).clamp(lower, upper) * m
+    return p - upd, m, v
+
+
+def sgd_reference_step(p, g, buf, lr: float, momentum: float = 0.0, weight_decay: float = 0.0):
+    """torch.optim.SGD as the trainer builds it (trainer/trainer.py:345-349: lr, momentum, weight_decay; dampening 0, no
+    Nesterov): g += wd*p; buf = g (first step) or momentum*buf + g; p -= lr*buf."""
+    if weight_decay != 0:
+        g = g + weight_decay * p
+    if momentum != 0:
+        buf = g.clone() if buf is None else buf * momentum + g
+        g = buf
+    return p - lr * g, buf
+
+
+def adam_reference_step(p, g, m, v, step: int, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+    """torch.optim.Adam as the trainer builds it (trainer/trainer.py:351-355: L2 weight decay folded into the gradient):
+    denom = sqrt(v)/sqrt(1-b2^t) + eps; p -= lr/(1-b1^t) * m/denom."""
+    b1, b2 = betas
+    if weight_decay != 0:
+        g = g + weight_decay * p
+    m = m * b1 + (1 - b1) * g
+    v = v * b2 + (1 - b2) * g * g
+    denom = v.sqrt() / math.sqrt(1 - b2 ** step) + eps
+    return p - (lr / (1 - b1 ** step)) * m / denom, m, v
 
 
 # --------------------------------------------------------------------------------------------

@@ -31,3 +31,15 @@ def golden():
     with open(os.path.join(g, "unetpp_golden.json")) as f:
         meta = json.load(f)
     return arrays, meta
+
+
+@pytest.fixture(scope="session")
+def variants_golden():
+    """Reference outputs for the constructor-flag variants and the extra optimizers (oracle/make_golden_variants.py)."""
+    import json
+    import numpy as np
+    g = os.path.join(ROOT, "tests", "golden")
+    arrays = dict(np.load(os.path.join(g, "unetpp_variants.npz")))
+    with open(os.path.join(g, "unetpp_variants.json")) as f:
+        meta = json.load(f)
+    return arrays, meta
