@@ -20,6 +20,9 @@
  *   unpp_wgrad, unpp_bn_*, unpp_maxpool2x2_bwd, unpp_head_bwd   the autograd backward of unet.py:255-300
  *   unpp_adamw          tools/optimizers/adamw.py:38-100 (AdamW.step) over one flat buffer
  *   unpp_create_heatmap tools/misc/helper.py:87-172 (target synthesis the trainer runs on the CPU every step)
+ *   unpp_bilinear_up2x(_bwd)  nn.UpsamplingBilinear2d(scale_factor=2) of unetUp with is_deconv=False (models/unet.py:189-191)
+ *   unpp_optim_step     every optimizer trainer/trainer.py:344-376 can select, over one flat buffer: tools/optimizers/adamw.py,
+ *                       tools/optimizers/sgdw.py, tools/optimizers/adabound.py, torch.optim.SGD, torch.optim.Adam
  */
 #ifndef UNPP_H_
 #define UNPP_H_
@@ -228,6 +231,35 @@ int unpp_adamw(float* p, const float* g, float* m, float* v, long n, float lr, f
  * derives the bias-corrected step size from it into *step_size_scratch, then updates. */
 int unpp_adamw_dev(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, uint64_t* step_counter, float* step_size_scratch, float grad_scale, unpp_stream_t stream);
+/* Every optimizer the reference trainer can select (trainer/trainer.py:344-376), one launch over a flat fp32 buffer. */
+#define UNPP_OPT_ADAMW 0     /* tools/optimizers/adamw.py:38-100 (decay = weight_decay * p_old, not scaled by lr)            */
+#define UNPP_OPT_ADAM 1      /* torch.optim.Adam(lr, weight_decay): L2 decay folded into the gradient                          */
+#define UNPP_OPT_ADABOUND 2  /* tools/optimizers/adabound.py:57-122 without amsbound                                           */
+#define UNPP_OPT_SGD 3       /* torch.optim.SGD(lr, momentum = beta1, weight_decay), dampening 0, no Nesterov                  */
+#define UNPP_OPT_SGDW 4      /* tools/optimizers/sgdw.py:77-110 AS SHIPPED: momentum buffer (beta1 = momentum, beta2 =
+                                dampening) is maintained but never applied; the parameter only decays: p -= weight_decay * p  */
+typedef struct UnppOptimArgs {
+  int32_t kind;
+  float lr;
+  float beta1, beta2;     /* Adam family: betas; SGD: beta1 = momentum; SGDW: beta1 = momentum, beta2 = dampening */
+  float eps;
+  float weight_decay;
+  float final_lr, gamma;  /* AdaBound */
+  float base_lr;          /* AdaBound: the learning rate at construction (adabound.py:49,119)                     */
+  float grad_scale;       /* gradients are multiplied by this first (1/world for data-parallel sums)              */
+} UnppOptimArgs;
+/* state1 / state2: first / second moment (Adam family) or the momentum buffer / unused (SGD, SGDW; may be NULL without
+ * momentum).  Either `step` (1-based, host) or `step_counter` (device; incremented by the call, CUDA-graph friendly; then
+ * scalars_scratch = fp32[4] device scratch and lr_dev may point to a device float that overrides a->lr at every launch,
+ * which is how an lr scheduler drives a captured step). */
+int unpp_optim_step(float* p, const float* g, float* state1, float* state2, long n, const UnppOptimArgs* a, int step, uint64_t* step_counter,
+                    const float* lr_dev, float* scalars_scratch, unpp_stream_t stream);
+int unpp_sizeof_optim_args(void);
+/* nn.UpsamplingBilinear2d(scale_factor=2) (= bilinear, align_corners=True; models/unet.py:190) on NHWC bf16:
+ * y[N,2H,2W,C] from x[N,H,W,C], C % 8 == 0, with ATen's float source-index arithmetic; and its exact adjoint
+ * dx[N,H,W,C] from dy[N,2H,2W,C] (a gather with the same weights: deterministic). */
+int unpp_bilinear_up2x(const void* x, void* y, int N, int H, int W, int C, unpp_stream_t stream);
+int unpp_bilinear_up2x_bwd(const void* dy, void* dx, int N, int H, int W, int C, unpp_stream_t stream);
 /* Keep-mask for the element-wise nn.Dropout(p) in front of the 16-channel heads (models/unet.py:254,283-286): one 16-bit
  * word per pixel, bit c = 1 with probability 1-p (counter-based hash of seed, pixel, channel and, when step_counter is
  * given, the device step counter: a captured training step draws fresh masks at every replay).  npix % 8 == 0. */

@@ -87,6 +87,32 @@ def test_struct_layouts_match_the_header():
     assert lib.unpp_sizeof_pack_args() == ctypes.sizeof(_lib.PackArgs)
     assert lib.unpp_sizeof_wgrad_args() == ctypes.sizeof(_lib.WgradArgs)
     assert lib.unpp_sizeof_reduce_job() == ctypes.sizeof(_lib.ReduceJob)
+    assert lib.unpp_sizeof_optim_args() == ctypes.sizeof(_lib.OptimArgs)
+
+
+@pytest.mark.parametrize("kw", [dict(is_deconv=False), dict(is_batchnorm=False), dict(is_deconv=False, is_batchnorm=False)])
+def test_constructor_flag_variants_keep_the_reference_state_dict_layout(variants_golden, kw):
+    """is_deconv=False -> up.1.weight [Cout,Cin,1,1] / up.1.bias (unet.py:189-191); is_batchnorm=False -> no BN entries (unet.py:137-143)."""
+    _, meta = variants_golden
+    tag = {(False, True): "bilinear", (True, False): "nobn", (False, False): "bilinear_nobn"}[(kw.get("is_deconv", True), kw.get("is_batchnorm", True))]
+    m = pkg.UNet_Nested(**kw)
+    assert [[k, list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()] == meta[tag]["state_dict_keys"]
+
+
+def test_optimizer_drop_ins_keep_the_reference_constructors():
+    from unet_nested4tiny_objects_keypoints_b200 import optimizers
+    p = [torch.nn.Parameter(torch.zeros(3))]
+    o = optimizers.SGDW(p, lr=0.1, weight_decay=1e-4)            # trainer/trainer.py:364-368
+    assert o.defaults == dict(lr=0.1, momentum=0, dampening=0, weight_decay=1e-4, nesterov=False)
+    o = optimizers.AdaBound(p, lr=1e-3, weight_decay=1e-4)        # trainer/trainer.py:371-375
+    assert o.defaults["final_lr"] == 0.1 and o.defaults["gamma"] == 1e-3 and o.base_lrs == [1e-3]
+    with pytest.raises(ValueError):
+        optimizers.SGDW(p, lr=0.1, nesterov=True)                 # sgdw.py:63-64
+    with pytest.raises(ValueError):
+        optimizers.AdaBound(p, gamma=1.5)                         # adabound.py:43-44
+    p[0].grad = torch.zeros(3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        o.step()
 
 
 def test_keep_mask_bit_words_round_trip_on_cpu():

@@ -89,6 +89,16 @@ class ReduceJob(C.Structure):
     ]
 
 
+class OptimArgs(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+        ("final_lr", C.c_float), ("gamma", C.c_float), ("base_lr", C.c_float), ("grad_scale", C.c_float),
+    ]
+
+
+OPT_ADAMW, OPT_ADAM, OPT_ADABOUND, OPT_SGD, OPT_SGDW = range(5)
+
+
 # Every symbol include/unpp.h declares, with its ctypes signature (tests check the export list).
 _SIGNATURES = {
     "unpp_last_error": (C.c_char_p, []),
@@ -123,6 +133,11 @@ _SIGNATURES = {
                                  C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     "unpp_dropout_mask": (C.c_int, [C.c_void_p, C.c_long, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p]),
     "unpp_create_heatmap": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "unpp_optim_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.POINTER(OptimArgs), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
+    "unpp_bilinear_up2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "unpp_bilinear_up2x_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "unpp_sizeof_optim_args": (C.c_int, []),
     "unpp_sizeof_conv_args": (C.c_int, []),
     "unpp_sizeof_pack_args": (C.c_int, []),
     "unpp_sizeof_wgrad_args": (C.c_int, []),

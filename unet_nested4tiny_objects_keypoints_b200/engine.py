@@ -81,10 +81,6 @@ class Engine:
     def __init__(self, model, device: torch.device):
         if device.type != "cuda":
             raise RuntimeError("the B200-native UNet_Nested engine needs a CUDA device")
-        if not model.is_deconv:
-            raise ValueError("is_deconv=False (bilinear upsample) is not implemented by the sm_100a engine yet")
-        if not model.is_batchnorm:
-            raise ValueError("is_batchnorm=False is not implemented by the sm_100a engine yet")
         f = [int(c / model.feature_scale) for c in (32, 64, 128, 256)]
         if f != [16, 32, 64, 128] or model.n_classes > 8 or model.in_channels > 16:
             raise ValueError("the sm_100a engine supports feature_scale=2, n_classes<=8, in_channels<=16")
@@ -119,15 +115,28 @@ class Engine:
             for name in ENCODER:
                 for n in (1, 2):
                     seq = self._conv_seq(name, n)
-                    conv, bn = seq[0], seq[1]
-                    scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
-                    bias = ((conv.bias - bn.running_mean) * scale + bn.bias).float().contiguous()
+                    conv = seq[0]
+                    if self.model.is_batchnorm:
+                        bn = seq[1]
+                        scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
+                        bias = ((conv.bias - bn.running_mean) * scale + bn.bias).float().contiguous()
+                    else:  # unet.py:137-143: conv + ReLU only
+                        scale, bias = None, conv.bias.detach().float().contiguous()
                     P[f"{name}.c{n}"] = self._pack_fwd_conv(conv.weight, scale, bias)
             for name in DECODER_ORDER:
                 up = getattr(self.model, name)
                 for n in (1, 2):
                     conv = self._conv_seq(name + ".conv", n)[0]
                     P[f"{name}.c{n}"] = self._pack_fwd_conv(conv.weight, None, conv.bias.detach().float().contiguous())
+                if not self.model.is_deconv:
+                    # unet.py:189-191: UpsamplingBilinear2d(2) + Conv2d 1x1.  Both are linear and the bilinear weights sum to one,
+                    # so the 1x1 conv (bias included) runs first, on the low-resolution tensor: a pointwise tensor-core GEMM
+                    pw = up.up[1]
+                    cout, cin = pw.weight.shape[0], pw.weight.shape[1]
+                    nt = pick_n_tile(cout, cin, 1)
+                    P[f"{name}.up"] = dict(w=ops.pack_weights(pw.weight.detach().float(), 0, 1, cout, nt, cin), bias=pw.bias.detach().float().contiguous(),
+                                           n_total=cout, n_tile=nt, cout=cout)
+                    continue
                 conv1 = self._conv_seq(name + ".conv", 1)[0]
                 cu = up.up.weight.shape[1]
                 if cu == 16 and up.up.weight.shape[0] == 32 and conv1.weight.shape[1] - cu <= 48:
@@ -177,6 +186,8 @@ class Engine:
                 h, w, c = H >> lvl, W >> lvl, f[lvl]
                 tag = name[-2:]
                 a[f"U{tag}"] = torch.empty(B, h, w, c, **bf)
+                if not self.model.is_deconv:
+                    a[f"V{tag}"] = torch.empty(B, h // 2, w // 2, c, **bf)  # 1x1 conv of the low-resolution source, before the x2 upsample
                 a[f"{name}.a"] = torch.empty(B, h, w, c, **bf)
                 a[f"X{tag}"] = torch.empty(B, h, w, c, **bf)
             if len(self._arena) >= 4:
@@ -235,7 +246,11 @@ class Engine:
                 ops.conv([A[l] for l in lows], B, h, w, pf["w"], 16, pf["n_tile"], 9, bias=pf["bias"], bias_classes=9, relu=True, out=A[f"{name}.a"],
                          lowres=(A[high], pf["low_w"]))
             else:
-                ops.conv([A[high]], B, h // 2, w // 2, pu["w"], pu["n_total"], pu["n_tile"], 1, bias=pu["bias"], mode=MODE_DECONV, out=A[f"U{tag}"])
+                if self.model.is_deconv:
+                    ops.conv([A[high]], B, h // 2, w // 2, pu["w"], pu["n_total"], pu["n_tile"], 1, bias=pu["bias"], mode=MODE_DECONV, out=A[f"U{tag}"])
+                else:
+                    ops.conv([A[high]], B, h // 2, w // 2, pu["w"], pu["n_total"], pu["n_tile"], 1, bias=pu["bias"], out=A[f"V{tag}"])
+                    ops.bilinear_up2x(A[f"V{tag}"], A[f"U{tag}"])
                 ops.conv([A[f"U{tag}"]] + [A[l] for l in lows], B, h, w, p1["w"], p1["n_total"], p1["n_tile"], 9, bias=p1["bias"], relu=True,
                           out=A[f"{name}.a"])
             head = None

@@ -152,14 +152,25 @@ class InferenceSession:
 class FusedTrainStep:
     def __init__(self, model, B: int, H: int, W: int, lr: float = 3e-6, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-4, device="cuda", use_graph: bool = True, process_group=None, seed: int = 0, loss: str = "mse",
-                 focal_gamma: float = 3.0):
-        """Defaults follow the reference CLI: ``--optimizer adamw --lr 3e-6 --weight-decay 1e-4`` (train.py:38-45)."""
+                 focal_gamma: float = 3.0, optimizer: str = "adamw", momentum: float = 0.9, dampening: float = 0.0, final_lr: float = 0.1,
+                 bound_gamma: float = 1e-3):
+        """Defaults follow the reference CLI: ``--optimizer adamw --lr 3e-6 --weight-decay 1e-4`` (train.py:38-45).
+        ``optimizer``: any of the trainer's choices (trainer.py:344-376) — "adamw" (tools/optimizers/adamw.py), "adam" / "sgd"
+        (torch.optim with the trainer's arguments; ``momentum`` = train.py:39), "sgdw" (tools/optimizers/sgdw.py as shipped, built by the
+        trainer without momentum: pass ``momentum=0`` for that), "adabound" (tools/optimizers/adabound.py).  The learning rate lives
+        on the device: ``set_lr`` is what an lr scheduler (MultiStepLR / ExponentialLR, trainer.py:383-388) calls between steps."""
         self.model = model
         self.dev = _device(device)
         if not model.training:
             raise RuntimeError("FusedTrainStep needs model.train()")
         self.eng = _engine(model, self.dev)
-        self.hyper = dict(lr=lr, b1=betas[0], b2=betas[1], eps=eps, wd=weight_decay)
+        if optimizer not in ops.OPTIMIZER_KINDS:
+            raise ValueError("optimizer must be one of %s" % sorted(ops.OPTIMIZER_KINDS))
+        self.optimizer = optimizer
+        if optimizer in ("sgd", "sgdw"):
+            self.hyper = dict(lr=lr, beta1=momentum, beta2=dampening if optimizer == "sgdw" else 0.0, eps=eps, weight_decay=weight_decay)
+        else:
+            self.hyper = dict(lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, weight_decay=weight_decay, final_lr=final_lr, gamma=bound_gamma, base_lr=lr)
         self.pg = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
@@ -181,7 +192,8 @@ class FusedTrainStep:
         self.flat_m = torch.zeros(n, dtype=torch.float32, device=self.dev)
         self.flat_v = torch.zeros(n, dtype=torch.float32, device=self.dev)
         self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)
-        self.step_size = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.step_size = torch.zeros(4, dtype=torch.float32, device=self.dev)  # per-step optimizer scalars (unpp_optim_step)
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.x = torch.zeros(B, model.in_channels, H, W, dtype=torch.float32, device=self.dev)
         self.target = torch.zeros(B, model.n_classes, H, W, dtype=torch.float32, device=self.dev)
@@ -242,9 +254,13 @@ class FusedTrainStep:
         ops.reduce_partials(ts.t["head_red"], 3, nacc, 1, self.loss, scale=self.loss_scale, partial_offset=ncls * 17)
 
     def _update(self):
-        h = self.hyper
-        ops.adamw_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, h["lr"], h["b1"], h["b2"], h["eps"], h["wd"], self.step_counter,
-                      self.step_size, grad_scale=1.0 / self.world)
+        ops.optim_step(self.optimizer, self.flat_p, self.flat_g, self.flat_m, self.flat_v, grad_scale=1.0 / self.world, step_counter=self.step_counter,
+                       lr_dev=self.lr_dev, scalars=self.step_size, **self.hyper)
+
+    def set_lr(self, lr: float) -> None:
+        """New learning rate for the following steps (the captured graph reads it from device memory)."""
+        self.hyper["lr"] = float(lr)
+        self.lr_dev.fill_(float(lr))
 
     def step_device(self) -> torch.Tensor:
         """Inputs already in ``self.x`` / ``self.target``.  Returns the (device) loss of this rank's batch."""

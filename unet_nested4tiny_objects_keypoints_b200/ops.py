@@ -442,3 +442,42 @@ def create_heatmap(keypoints: torch.Tensor, H: int, W: int, out: Optional[torch.
     _count()
     _lib.check(lib().unpp_create_heatmap(keypoints.data_ptr(), N, npts, H, W, out.data_ptr(), _stream()), "unpp_create_heatmap")
     return out
+
+
+# ---------------------------------------------------------------------------------------------- non-default constructor flags / optimizers
+OPTIMIZER_KINDS = {"adamw": _lib.OPT_ADAMW, "adam": _lib.OPT_ADAM, "adabound": _lib.OPT_ADABOUND, "sgd": _lib.OPT_SGD, "sgdw": _lib.OPT_SGDW}
+
+
+def bilinear_up2x(x: torch.Tensor, out: torch.Tensor) -> None:
+    """nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True, models/unet.py:190) on NHWC bf16: [N,H,W,C] -> [N,2H,2W,C]."""
+    N, H, W, Cc = x.shape
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and tuple(out.shape) == (N, 2 * H, 2 * W, Cc) and x.is_contiguous() and out.is_contiguous()
+    _count()
+    with _Traced("bilinear_up2x %dx%d C%d" % (H, W, Cc), x.numel() * 2 + out.numel() * 2, 0):
+        _lib.check(lib().unpp_bilinear_up2x(x.data_ptr(), out.data_ptr(), N, H, W, Cc, _stream()), "unpp_bilinear_up2x")
+
+
+def bilinear_up2x_bwd(dy: torch.Tensor, dx: torch.Tensor) -> None:
+    """Adjoint of bilinear_up2x: dy [N,2H,2W,C] -> dx [N,H,W,C]."""
+    N, H, W, Cc = dx.shape
+    assert dy.dtype == torch.bfloat16 and dx.dtype == torch.bfloat16 and tuple(dy.shape) == (N, 2 * H, 2 * W, Cc) and dy.is_contiguous() and dx.is_contiguous()
+    _count()
+    with _Traced("bilinear_up2x_bwd %dx%d C%d" % (H, W, Cc), dy.numel() * 2 + dx.numel() * 2, 0):
+        _lib.check(lib().unpp_bilinear_up2x_bwd(dy.data_ptr(), dx.data_ptr(), N, H, W, Cc, _stream()), "unpp_bilinear_up2x_bwd")
+
+
+def optim_step(kind: str, p, g, state1, state2, *, lr, beta1=0.0, beta2=0.0, eps=1e-8, weight_decay=0.0, final_lr=0.1, gamma=1e-3, base_lr=None,
+               grad_scale=1.0, step: int = 0, step_counter: Optional[torch.Tensor] = None, lr_dev: Optional[torch.Tensor] = None,
+               scalars: Optional[torch.Tensor] = None) -> None:
+    """One flat-buffer update of any optimizer trainer/trainer.py:344-376 can select (see UNPP_OPT_* in unpp.h).
+    Either ``step`` (1-based host count) or ``step_counter`` (int64 [1] on the device, incremented by the call; then ``scalars`` is
+    an fp32 [4] device scratch and ``lr_dev`` an optional fp32 [1] device learning rate that overrides ``lr``)."""
+    for t in (p, g, state1, state2):
+        assert t is None or (t.dtype == torch.float32 and t.is_cuda and t.is_contiguous() and t.numel() == p.numel())
+    a = _lib.OptimArgs()
+    a.kind, a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = OPTIMIZER_KINDS[kind], float(lr), float(beta1), float(beta2), float(eps), float(weight_decay)
+    a.final_lr, a.gamma, a.base_lr, a.grad_scale = float(final_lr), float(gamma), float(lr if base_lr is None else base_lr), float(grad_scale)
+    _count(2 if step_counter is not None else 1)
+    with _Traced("optim_step " + kind, 0, 0):
+        _lib.check(lib().unpp_optim_step(p.data_ptr(), g.data_ptr(), _ptr(state1), _ptr(state2), p.numel(), C.byref(a), int(step), _ptr(step_counter),
+                                         _ptr(lr_dev), _ptr(scalars), _stream()), "unpp_optim_step")

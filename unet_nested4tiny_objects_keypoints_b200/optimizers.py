@@ -6,6 +6,11 @@ one ``unpp_adamw`` launch per parameter tensor (the reference issues ~10 ATen ke
 or ONE launch for the whole model when the parameters are views of a flat buffer
 (``fused.FusedTrainStep`` lays them out that way).  CUDA fp32 parameters only; ``amsgrad`` is not
 implemented (the trainer never enables it).
+
+``SGDW`` and ``AdaBound`` are the drop-ins for ``tools/optimizers/sgdw.py`` / ``tools/optimizers/adabound.py``
+(``--optimizer sgdw|adabound``, trainer.py:364-376) on the same ``unpp_optim_step`` kernel; ``torch.optim.SGD`` /
+``torch.optim.Adam`` (trainer.py:344-355) keep working unchanged on this model's parameters, and their flat-buffer
+forms are ``FusedTrainStep(optimizer="sgd"|"adam")``.
 """
 from __future__ import annotations
 
@@ -54,4 +59,100 @@ class AdamW(Optimizer):
                 with torch.cuda.device(p.device):
                     ops.adamw(p.data.view(-1), g.view(-1), state["exp_avg"].view(-1), state["exp_avg_sq"].view(-1), group["lr"], b1, b2, group["eps"],
                               group["weight_decay"], state["step"])
+        return loss
+
+
+def _flat(t):
+    return t.view(-1)
+
+
+def _check(p):
+    if p.grad.is_sparse:
+        raise RuntimeError("sparse gradients are not supported")
+    if not p.is_cuda or p.dtype != torch.float32:
+        raise RuntimeError("the sm_100a optimizers update CUDA float32 parameters only (there is no CPU path)")
+    return p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+
+
+class SGDW(Optimizer):
+    """Drop-in for the reference's ``SGDW`` (tools/optimizers/sgdw.py:59-110), constructor and behaviour AS SHIPPED: ``step()``
+    maintains the momentum buffer (first step ``buf = g``, later ``buf = momentum*buf + (1-dampening)*g``, sgdw.py:95-102) but
+    never applies the descent direction — the only parameter update is the decoupled decay ``p -= weight_decay * p``
+    (sgdw.py:107-108).  Kept bug-for-bug so that a run switched over reproduces the reference's parameters."""
+
+    def __init__(self, params, lr, momentum=0, dampening=0, weight_decay=0, nesterov=False):
+        if nesterov and (momentum <= 0 or dampening != 0):
+            raise ValueError("Nesterov momentum requires a momentum and zero dampening")
+        super().__init__(params, dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay, nesterov=nesterov))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                g = _check(p)
+                state = self.state[p]
+                buf = None
+                if group["momentum"] != 0:
+                    if "momentum_buffer" not in state:
+                        state["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                        state["step"] = 0
+                    buf = _flat(state["momentum_buffer"])
+                state["step"] = state.get("step", 0) + 1
+                with torch.cuda.device(p.device):
+                    ops.optim_step("sgdw", _flat(p.data), _flat(g), buf, None, lr=group["lr"], beta1=group["momentum"], beta2=group["dampening"],
+                                   weight_decay=group["weight_decay"], step=state["step"])
+        return loss
+
+
+class AdaBound(Optimizer):
+    """Drop-in for the reference's ``AdaBound`` (tools/optimizers/adabound.py:10-122): Adam moments with the L2 decay folded
+    into the gradient, per-element rate ``clamp(step_size/(sqrt(v)+eps), lower(t), upper(t))`` with ``final_lr`` rescaled by
+    ``lr/base_lr`` so that lr schedulers act on the bounds too (adabound.py:117-121).  ``amsbound`` is not implemented."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), final_lr=0.1, gamma=1e-3, eps=1e-8, weight_decay=0, amsbound=False):
+        if not 0.0 <= lr:
+            raise ValueError("Invalid learning rate: {}".format(lr))
+        if not 0.0 <= eps:
+            raise ValueError("Invalid epsilon value: {}".format(eps))
+        if not 0.0 <= betas[0] < 1.0:
+            raise ValueError("Invalid beta parameter at index 0: {}".format(betas[0]))
+        if not 0.0 <= betas[1] < 1.0:
+            raise ValueError("Invalid beta parameter at index 1: {}".format(betas[1]))
+        if not 0.0 <= final_lr:
+            raise ValueError("Invalid final learning rate: {}".format(final_lr))
+        if not 0.0 <= gamma < 1.0:
+            raise ValueError("Invalid gamma parameter: {}".format(gamma))
+        if amsbound:
+            raise NotImplementedError("amsbound is not implemented by the sm_100a AdaBound")
+        super().__init__(params, dict(lr=lr, betas=betas, final_lr=final_lr, gamma=gamma, eps=eps, weight_decay=weight_decay, amsbound=amsbound))
+        self.base_lrs = [group["lr"] for group in self.param_groups]
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group, base_lr in zip(self.param_groups, self.base_lrs):
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                g = _check(p)
+                state = self.state[p]
+                if len(state) == 0:
+                    state["step"] = 0
+                    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                state["step"] += 1
+                with torch.cuda.device(p.device):
+                    ops.optim_step("adabound", _flat(p.data), _flat(g), _flat(state["exp_avg"]), _flat(state["exp_avg_sq"]), lr=group["lr"], beta1=b1,
+                                   beta2=b2, eps=group["eps"], weight_decay=group["weight_decay"], final_lr=group["final_lr"], gamma=group["gamma"],
+                                   base_lr=base_lr, step=state["step"])
         return loss

@@ -84,6 +84,9 @@ class TrainState:
             tag = name[-2:]
             for nm in (f"U{tag}", f"{name}.a", f"X{tag}", f"dZ2{tag}", f"dZ1{tag}", f"dU{tag}"):
                 act(nm, lvl)
+            if not eng.model.is_deconv:  # unet.py:189-191: the 1x1 conv runs on the low-resolution tensor, before the x2 bilinear upsample
+                for nm in (f"V{tag}", f"dV{tag}"):
+                    t[nm] = torch.empty(B, H >> (lvl + 1), W >> (lvl + 1), f[lvl], **bf)
         act("tmpX11", 1)
         for k in range(3):
             t[f"mask{k}"] = torch.full((B, H, W), -1, dtype=torch.int16, device=dev)  # dropout keep bits, one 16-bit word per pixel
@@ -196,10 +199,16 @@ def _pack_train_jobs(ts: TrainState) -> None:
             put(f"{name}.c1.dgrad", w1, 1, 9, cin, cout, n_tile=pick_n_tile(cin, cout, 9))
         for name in DECODER_ORDER:
             up = getattr(m, name).up
-            wd = up.weight.detach()
-            cin, cout = wd.shape[0], wd.shape[1]
-            put(f"{name}.up.fwd", wd, 2, 1, 4 * cout, cin, n_tile=pick_n_tile(4 * cout, cin, 1, deconv=True))
-            put(f"{name}.up.dgrad", wd, 3, 4, cin, cout, n_tile=pick_n_tile(cin, 4 * cout, 1))
+            if m.is_deconv:
+                wd = up.weight.detach()
+                cin, cout = wd.shape[0], wd.shape[1]
+                put(f"{name}.up.fwd", wd, 2, 1, 4 * cout, cin, n_tile=pick_n_tile(4 * cout, cin, 1, deconv=True))
+                put(f"{name}.up.dgrad", wd, 3, 4, cin, cout, n_tile=pick_n_tile(cin, 4 * cout, 1))
+            else:  # UpsamplingBilinear2d + Conv2d 1x1 (unet.py:189-191): pointwise GEMMs on the low-resolution grid
+                wp = up[1].weight.detach()  # [cout, cin, 1, 1]
+                cout, cin = wp.shape[0], wp.shape[1]
+                put(f"{name}.up.fwd", wp, 0, 1, cout, cin, n_tile=pick_n_tile(cout, cin, 1))
+                put(f"{name}.up.dgrad", wp, 1, 1, cin, cout, n_tile=pick_n_tile(cin, cout, 1))
             w1 = _w1(m, name).weight.detach()
             put(f"{name}.c1.dgradU", w1, 1, 9, cout, cout, n_tile=pick_n_tile(cout, cout, 9), n_begin=0)
         for node in ("X00", "X10", "X20", "X01", "X11", "X02"):
@@ -227,10 +236,19 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
         count = B * h * w
         for n in (1, 2):
             seq = _mod(m, f"{name}.conv{n}")
-            conv, bn = seq[0], seq[1]
-            z = t[f"{name}.z{n}"]
+            conv = seq[0]
             key = f"{name}.c{n}.fwd"
             nt = P[key + ".nt"]
+            if not m.is_batchnorm:  # unet.py:137-143: conv + ReLU (+ the 2x2 max pool of the level's output, written by the same epilogue)
+                if n == 1:
+                    ops.conv([src], B, h, w, P[key], c, nt, 9, bias=conv.bias, relu=True, out=t[f"{name}.a"])
+                    src = t[f"{name}.a"]
+                else:
+                    ops.conv([src], B, h, w, P[key], c, nt, 9, bias=conv.bias, relu=True, out=t[f"X{lvl}0"], pooled=t[f"P{lvl}0"] if lvl < 3 else None)
+                    src = t[f"P{lvl}0"] if lvl < 3 else None
+                continue
+            bn = seq[1]
+            z = t[f"{name}.z{n}"]
             cin = src.shape[-1]
             g = ops.conv_grid([cin], B, h, w, c, nt, 9)
             part = ts.scratch_f32("stats", g * 2 * c)
@@ -257,7 +275,11 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
         h, w, c = H >> lvl, W >> lvl, eng.filters[lvl]
         node = getattr(m, name)
         ku, k1, k2 = f"{name}.up.fwd", f"{name}.c1.fwd", f"{name}.c2.fwd"
-        ops.conv([t[high]], B, h // 2, w // 2, P[ku], 4 * c, P[ku + ".nt"], 1, bias=node.up.bias, mode=MODE_DECONV, out=t[f"U{tag}"])
+        if m.is_deconv:
+            ops.conv([t[high]], B, h // 2, w // 2, P[ku], 4 * c, P[ku + ".nt"], 1, bias=node.up.bias, mode=MODE_DECONV, out=t[f"U{tag}"])
+        else:
+            ops.conv([t[high]], B, h // 2, w // 2, P[ku], c, P[ku + ".nt"], 1, bias=node.up[1].bias, out=t[f"V{tag}"])
+            ops.bilinear_up2x(t[f"V{tag}"], t[f"U{tag}"])
         ops.conv([t[f"U{tag}"]] + [t[l] for l in lows], B, h, w, P[k1], c, P[k1 + ".nt"], 9, bias=_w1(m, name).bias, relu=True, out=t[f"{name}.a"])
         head = None
         if name in HEAD_OF:
@@ -313,13 +335,29 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
         for pq in range(4):
             ops.wgrad_reduce(part, g, 1, cin, cout, G, 0, cin, 4, cout * 4, 0, dst_offset=goff(pname) + pq, partial_offset=pq * g * cin * cout, defer=True)
 
+    def wgrad_up_bilinear(xhigh, tag, h2, w2, pname):
+        """is_deconv=False (unet.py:189-191): dV = bilinear_x2^T(dU) on the low-resolution grid, then the 1x1 conv's weight gradient."""
+        dV = t[f"dV{tag}"]
+        ops.bilinear_up2x_bwd(t[f"dU{tag}"], dV)
+        cin, cout = xhigh.shape[-1], dV.shape[-1]
+        g = ops.wgrad_grid([cin], B, h2, w2, cout, 1)
+        part = ts.scratch_f32("wgrad:" + pname, g * cin * cout)
+        ops.wgrad([xhigh], B, h2, w2, dV, cout, 1, part)
+        ops.wgrad_reduce(part, g, 1, cin, cout, G, 0, cin, cin, 1, 0, dst_offset=goff(pname), defer=True)
+
+    def up_dgrad_srcs_C(dname):
+        """Source channel list of the gradient GEMM toward the low-resolution input of decoder ``dname``'s upsample."""
+        c = t[f"dU{dname[-2:]}"].shape[-1]
+        return [c] * 4 if m.is_deconv else [c]
+
     def deconv_dgrad(dname, h2, w2, out, addend=None, mask=None, stats=None):
-        """grad wrt the high-resolution... rather LOW-resolution input of decoder ``dname``'s transposed conv."""
+        """grad wrt the LOW-resolution input of decoder ``dname``'s upsample (transposed conv, or bilinear + 1x1 conv)."""
         key = f"{dname}.up.dgrad"
-        dU = t[f"dU{dname[-2:]}"]
-        cout = dU.shape[-1]
         cin = out.shape[-1]
-        ops.conv([dU] * 4, B, h2, w2, P[key], cin, P[key + ".nt"], 1, out=out, addend=addend, relu_mask_src=mask, strided=PQ, **(stats or {}))
+        if m.is_deconv:
+            ops.conv([t[f"dU{dname[-2:]}"]] * 4, B, h2, w2, P[key], cin, P[key + ".nt"], 1, out=out, addend=addend, relu_mask_src=mask, strided=PQ, **(stats or {}))
+        else:
+            ops.conv([t[f"dV{dname[-2:]}"]], B, h2, w2, P[key], cin, P[key + ".nt"], 1, out=out, addend=addend, relu_mask_src=mask, **(stats or {}))
 
     # ---- heads: sigmoid' + 1x1 dgrad/wgrad + dropout mask (+ fused MSE); output already masked by X_0k > 0
     for name, hname in HEAD_OF.items():
@@ -351,10 +389,14 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
         bias_from_stats(part, g, c, f"{pre}.conv1.0.bias")
         wgrad_conv([t[f"U{tag}"]] + [t[l] for l in lows], dZ1, h, w, f"{pre}.conv1.0.weight")
         key = f"{name}.c1.dgradU"
-        g, part = stats_buf([c], c, P[key + ".nt"], 9, h, w, key=f"stats:{name}.up.bias")
+        up_bias = f"{name}.up.bias" if m.is_deconv else f"{name}.up.1.bias"
+        g, part = stats_buf([c], c, P[key + ".nt"], 9, h, w, key=f"stats:{up_bias}")
         ops.conv([dZ1], B, h, w, P[key], c, P[key + ".nt"], 9, out=dU, stats_partial=part)
-        bias_from_stats(part, g, c, f"{name}.up.bias")
-        wgrad_deconv(t[high], dU, h // 2, w // 2, f"{name}.up.weight")
+        bias_from_stats(part, g, c, up_bias)  # bilinear weights sum to one: sum(dV) == sum(dU)
+        if m.is_deconv:
+            wgrad_deconv(t[high], dU, h // 2, w // 2, f"{name}.up.weight")
+        else:
+            wgrad_up_bilinear(t[high], tag, h // 2, w // 2, f"{name}.up.1.weight")
 
     def gather(node, h, w, out, addend, mask, stats):
         cons = consumers_of(node)
@@ -383,8 +425,7 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
             g, part = stats_buf([c] * len(cons), c, P[key_for_stats + ".nt"], 9, h, w, key=f"stats:{dname}.conv.conv2.0.bias")
             gather(node, h, w, out, add, t[node], dict(stats_partial=part))
         else:
-            cin_up = t[f"dU{extra_deconv_from[-2:]}"].shape[-1]
-            g, part = stats_buf([cin_up] * 4, c, P[key_for_stats + ".nt"], 1, h, w, key=f"stats:{dname}.conv.conv2.0.bias")
+            g, part = stats_buf(up_dgrad_srcs_C(extra_deconv_from), c, P[key_for_stats + ".nt"], 1, h, w, key=f"stats:{dname}.conv.conv2.0.bias")
             deconv_dgrad(extra_deconv_from, h, w, out, addend=addend, mask=t[node], stats=dict(stats_partial=part))
         bias_from_stats(part, g, c, f"{dname}.conv.conv2.0.bias")
         decoder_node_backward(dname, True)
@@ -404,44 +445,55 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
         count = B * h * w
         bn2, bn1 = f"{name}.bn2", f"{name}.bn1"
         seq1, seq2 = _mod(m, f"{name}.conv1"), _mod(m, f"{name}.conv2")
-        aux2 = dict(stats_aux=t[f"{name}.z2"], aux_mean=t[bn2 + ".mean"], aux_istd=t[bn2 + ".istd"])
+        has_bn = m.is_batchnorm
+        # with BatchNorm the gather produces dyh2 (gradient at the BN output, ReLU-masked) plus the two BN-backward sums;
+        # without it (unet.py:137-143) the same launch produces dz2 directly and its per-channel sum is the conv bias gradient
+        aux2 = dict(stats_aux=t[f"{name}.z2"], aux_mean=t[bn2 + ".mean"], aux_istd=t[bn2 + ".istd"]) if has_bn else {}
         addend = t[f"dpool{lvl}"] if lvl < 3 else None
         cons = consumers_of(node)
-        dyh2 = t[f"{name}.dyh2"]
+        dz2 = t[f"{name}.dz2"]
+        dyh2 = t[f"{name}.dyh2"] if has_bn else dz2
+        skey = "stats" if has_bn else f"stats:{name}.conv2.0.bias"
         if lvl == 0:
             key = f"{node}.gather"
-            g, part = stats_buf([c] * len(cons), c, P[key + ".nt"], 9, h, w)
+            g, part = stats_buf([c] * len(cons), c, P[key + ".nt"], 9, h, w, key=skey)
             gather(node, h, w, dyh2, addend, t[node], dict(stats_partial=part, **aux2))
         elif cons:
             tmp = t[f"tmp{lvl}"]
             deconv_dgrad(deconv_into[lvl], h, w, tmp, addend=addend)
             key = f"{node}.gather"
-            g, part = stats_buf([c] * len(cons), c, P[key + ".nt"], 9, h, w)
+            g, part = stats_buf([c] * len(cons), c, P[key + ".nt"], 9, h, w, key=skey)
             gather(node, h, w, dyh2, tmp, t[node], dict(stats_partial=part, **aux2))
-        else:  # X30: the transposed conv of up_concat21 is its only consumer
+        else:  # X30: the upsample of up_concat21 is its only consumer
             key = f"{deconv_into[lvl]}.up.dgrad"
-            cin_up = t[f"dU{deconv_into[lvl][-2:]}"].shape[-1]
-            g, part = stats_buf([cin_up] * 4, c, P[key + ".nt"], 1, h, w)
+            g, part = stats_buf(up_dgrad_srcs_C(deconv_into[lvl]), c, P[key + ".nt"], 1, h, w, key=skey)
             deconv_dgrad(deconv_into[lvl], h, w, dyh2, addend=addend, mask=t[node], stats=dict(stats_partial=part, **aux2))
-        # BatchNorm 2 backward: sums = (dbeta, dgamma); dz = gamma*istd*(dyh - s1/M - xhat*s2/M)
-        ops.reduce_partials(part, g, 2 * c, 2 * c, t[bn2 + ".sums"])
-        ops.reduce_partials(t[bn2 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv2.1.bias"), defer=True)
-        ops.reduce_partials(t[bn2 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv2.1.weight"), partial_offset=c, defer=True)
-        # {name}.conv2.0.bias: a bias in front of BatchNorm has an exactly zero gradient; G is zero-initialised and never written there
-        dz2 = t[f"{name}.dz2"]
-        ops.bn_bwd_apply(dyh2, t[f"{name}.z2"], t[bn2 + ".mean"], t[bn2 + ".istd"], seq2[1].weight, t[bn2 + ".sums"], count, dz2)
+        if has_bn:
+            # BatchNorm 2 backward: sums = (dbeta, dgamma); dz = gamma*istd*(dyh - s1/M - xhat*s2/M)
+            ops.reduce_partials(part, g, 2 * c, 2 * c, t[bn2 + ".sums"])
+            ops.reduce_partials(t[bn2 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv2.1.bias"), defer=True)
+            ops.reduce_partials(t[bn2 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv2.1.weight"), partial_offset=c, defer=True)
+            # {name}.conv2.0.bias: a bias in front of BatchNorm has an exactly zero gradient; G is zero-initialised and never written there
+            ops.bn_bwd_apply(dyh2, t[f"{name}.z2"], t[bn2 + ".mean"], t[bn2 + ".istd"], seq2[1].weight, t[bn2 + ".sums"], count, dz2)
+        else:
+            bias_from_stats(part, g, c, f"{name}.conv2.0.bias")
         wgrad_conv([t[f"{name}.a"]], dz2, h, w, f"{name}.conv2.0.weight")
         # first conv of the level
         key = f"{name}.c2.dgrad"
-        g, part = stats_buf([c], c, P[key + ".nt"], 9, h, w)
-        dyh1 = t[f"{name}.dyh1"]
-        ops.conv([dz2], B, h, w, P[key], c, P[key + ".nt"], 9, out=dyh1, relu_mask_src=t[f"{name}.a"], stats_partial=part, stats_aux=t[f"{name}.z1"],
-                 aux_mean=t[bn1 + ".mean"], aux_istd=t[bn1 + ".istd"])
-        ops.reduce_partials(part, g, 2 * c, 2 * c, t[bn1 + ".sums"])
-        ops.reduce_partials(t[bn1 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv1.1.bias"), defer=True)
-        ops.reduce_partials(t[bn1 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv1.1.weight"), partial_offset=c, defer=True)
         dz1 = t[f"{name}.dz1"]
-        ops.bn_bwd_apply(dyh1, t[f"{name}.z1"], t[bn1 + ".mean"], t[bn1 + ".istd"], seq1[1].weight, t[bn1 + ".sums"], count, dz1)
+        if has_bn:
+            g, part = stats_buf([c], c, P[key + ".nt"], 9, h, w)
+            dyh1 = t[f"{name}.dyh1"]
+            ops.conv([dz2], B, h, w, P[key], c, P[key + ".nt"], 9, out=dyh1, relu_mask_src=t[f"{name}.a"], stats_partial=part, stats_aux=t[f"{name}.z1"],
+                     aux_mean=t[bn1 + ".mean"], aux_istd=t[bn1 + ".istd"])
+            ops.reduce_partials(part, g, 2 * c, 2 * c, t[bn1 + ".sums"])
+            ops.reduce_partials(t[bn1 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv1.1.bias"), defer=True)
+            ops.reduce_partials(t[bn1 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv1.1.weight"), partial_offset=c, defer=True)
+            ops.bn_bwd_apply(dyh1, t[f"{name}.z1"], t[bn1 + ".mean"], t[bn1 + ".istd"], seq1[1].weight, t[bn1 + ".sums"], count, dz1)
+        else:
+            g, part = stats_buf([c], c, P[key + ".nt"], 9, h, w, key=f"stats:{name}.conv1.0.bias")
+            ops.conv([dz2], B, h, w, P[key], c, P[key + ".nt"], 9, out=dz1, relu_mask_src=t[f"{name}.a"], stats_partial=part)
+            bias_from_stats(part, g, c, f"{name}.conv1.0.bias")
         if lvl == 0:
             wgrad_conv([t["x16"]], dz1, h, w, f"{name}.conv1.0.weight", ci_count=m.in_channels)
         else:
