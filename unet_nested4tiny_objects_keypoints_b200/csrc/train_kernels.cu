@@ -41,8 +41,17 @@ template <typename F>
 __device__ __forceinline__ float sliced_sum(int nparts, F load) {
   __shared__ float red[8][32];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  // eight loads in flight per thread, added in the original order (bit-identical to the plain loop, ~6x less latency)
   float s = 0.f;
-  for (int p = w; p < nparts; p += 8) s += load(p);
+  int p = w;
+  for (; p + 56 < nparts; p += 64) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = load(p + 8 * k);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+  }
+  for (; p < nparts; p += 8) s += load(p);
   red[w][l] = s;
   __syncthreads();
   float t = 0.f;
@@ -105,7 +114,15 @@ __global__ void __launch_bounds__(256) reduce_batched_kernel(const UnppReduceJob
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < n) {
       if (vec) {
-        for (int p = w; p < job.nparts; p += 8) {
+        int p = w;
+        for (; p + 56 < job.nparts; p += 64) {  // eight 16-byte loads in flight, added in the original order
+          float4 v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(q + (p + 8 * k) * job.stride));
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s.x += v[k].x, s.y += v[k].y, s.z += v[k].z, s.w += v[k].w;
+        }
+        for (; p < job.nparts; p += 8) {
           const float4 v = __ldg(reinterpret_cast<const float4*>(q + p * job.stride));
           s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
         }
@@ -143,11 +160,20 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
   __shared__ double r1[8][32], r2[8][32];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31, c = blockIdx.x * 32 + l;
   double s1 = 0.0, s2 = 0.0;
-  if (c < C)
-    for (int p = w; p < nparts; p += 8) {
+  if (c < C) {
+    int p = w;
+    for (; p + 56 < nparts; p += 64) {  // sixteen loads in flight, added in the original order
+      float a[8], b[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = __ldg(partial + (size_t(p + 8 * k) * 2 + 0) * C + c), b[k] = __ldg(partial + (size_t(p + 8 * k) * 2 + 1) * C + c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s1 += double(a[k]), s2 += double(b[k]);
+    }
+    for (; p < nparts; p += 8) {
       s1 += double(__ldg(partial + (size_t(p) * 2 + 0) * C + c));
       s2 += double(__ldg(partial + (size_t(p) * 2 + 1) * C + c));
     }
+  }
   r1[w][l] = s1, r2[w][l] = s2;
   __syncthreads();
   if (w != 0 || c >= C) return;

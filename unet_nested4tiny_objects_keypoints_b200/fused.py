@@ -207,6 +207,7 @@ class FusedTrainStep:
             raise ValueError("loss must be 'mse' or 'focal'")
         self.focal_gamma = focal_gamma
         self.graph_a = self.graph_b = None
+        self._side_stream = torch.cuda.Stream(self.dev)
         self.steps_done = 0
         with torch.cuda.device(self.dev):
             snapshot = (self.flat_p.clone(), [b.clone() for b in model.buffers()])
@@ -244,11 +245,19 @@ class FusedTrainStep:
     # num_batches_tracked increments of the eight BatchNorm layers
     def _fwd_bwd(self):
         ts = self.ts
-        pack_train(ts)
+        # The head dropout masks are not needed before the first decoder head: they are generated on a side stream (a parallel
+        # branch of the captured graph) next to the weight re-packing and the encoder; the CUDA-core mask kernel co-resides with
+        # the one-CTA-per-SM tensor-core convolutions (no shared memory, few registers) instead of serialising 3 launches.
+        cur = torch.cuda.current_stream(self.dev)
+        side = None
         if ts.use_masks:
-            for k in range(3):
-                ops.dropout_mask(ts.t[f"mask{k}"].view(-1), self.p_drop, self.seed * 7919 + k, self.step_counter)
-        forward_train(ts, self.x)
+            side = self._side_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for k in range(3):
+                    ops.dropout_mask(ts.t[f"mask{k}"].view(-1), self.p_drop, self.seed * 7919 + k, self.step_counter)
+        pack_train(ts)
+        forward_train(ts, self.x, before_decoder=(lambda: cur.wait_stream(side)) if side is not None else None)
         backward_train(ts, self.flat_g, target=self.target, coef=self.coef, loss_kind=self.loss_kind, gamma=self.focal_gamma)
         nacc, ncls = ts.head_nacc, self.model.n_classes
         ops.reduce_partials(ts.t["head_red"], 3, nacc, 1, self.loss, scale=self.loss_scale, partial_offset=ncls * 17)

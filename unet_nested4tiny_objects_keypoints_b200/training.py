@@ -222,7 +222,7 @@ def _pack_train_jobs(ts: TrainState) -> None:
 
 
 # ---------------------------------------------------------------------------------------------- forward (train mode)
-def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = True) -> Tuple[torch.Tensor, ...]:
+def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = True, before_decoder=None) -> Tuple[torch.Tensor, ...]:
     eng, t, P, m = ts.eng, ts.t, ts.packed, ts.eng.model
     B, H, W = ts.B, ts.H, ts.W
     ncls = m.n_classes
@@ -268,6 +268,8 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
                 src = t[f"P{lvl}0"] if lvl < 3 else None
     if tracked:
         torch._foreach_add_(tracked, 1)  # the eight int64 num_batches_tracked counters: one launch
+    if before_decoder is not None:
+        before_decoder()  # join point for work the caller put on a side stream (the head dropout masks)
     heats: List[torch.Tensor] = [None, None, None]
     for name in DECODER_ORDER:
         high, lows, lvl = DECODER[name]
