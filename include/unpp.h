@@ -84,7 +84,10 @@ typedef struct UnppConvArgs {
   const float* aux_istd;
   /* 2x2 output blocking (3x3 conv, every source C = 16, n_total = 16, even H and W): one GEMM row is a
    * 2x2 pixel block, N = 4*16, K walks the 4x4 input window -> 16 instead of 36 MMAs per 512 pixels.
-   * wpacked must then be packed with kind 4 (forward) or 5 (dgrad), taps = 16, n_total = n_tile = 64. */
+   * wpacked must then be packed with kind 4 (forward) or 5 (dgrad), taps = 16, n_total = n_tile = 64.
+   * block2x2 = 2: the same for the network's FIRST layer (inference epilogue): the one source is NHWC bf16 with 4 channels
+   * (8-byte pixels, unpp_nchw_to_nhwc with Cpad = 4), wpacked is kind 7; a K = 16 step is half a window row of 4-channel
+   * pixels, read through overlapping unswizzled K-major descriptors: 8 MMAs per 512 output pixels, 4x fewer input bytes. */
   int32_t block2x2;
   /* Fused transposed conv (inference, with block2x2): conv3x3(cat[ConvTranspose2d_k2s2(low), src...]) — the k2s2
    * upsample never overlaps, so its branch collapses into a 3x3 conv over the LOW-resolution tensor with
@@ -128,6 +131,9 @@ int unpp_conv_grid(const UnppConvArgs* a);
  *          Kinds 4-6 store only the NON-ZERO (position, pixel) blocks: per 16 input channels 36 (kind 6: 16) blocks of
  *          512 B = [2 k8][16 columns][8 channels], runs of adjacent pixels contiguous (csrc/b2_blocks.h): the kernel
  *          issues one MMA (N = 16/32/64) per run.  Buffer size: (k8_total / 2) * 36 * 512 B (kind 6: * 16 * 512 B).
+ *  kind 7: first layer of the 2x2-blocked path on 4-channel (8-byte) pixels (UnppConvArgs.block2x2 = 2): src [16][Cin <= 4][3][3],
+ *          taps = 4 window rows, n_total = n_tile = 64, k_count = 32: per window row dy the K axis is 4 chunks of 8 = (pixel pair,
+ *          4 channels) covering window columns -1 .. 6 (zero outside the 4x4 window): [dy][chunk][64 columns][8], 16 KB.
  * k_dst8 places the K range at 8-channel chunk offset k_dst8 inside a K/8 = k8_total wide buffer,
  * so that several sources (concat) or several consumers (dgrad gather) share one packed tensor. */
 typedef struct UnppPackArgs {
@@ -147,7 +153,7 @@ int unpp_pack_weights(const UnppPackArgs* a, unpp_stream_t stream);
  * re-packs every weight of a training step after the optimizer update. */
 int unpp_pack_weights_batched(const UnppPackArgs* table_dev, int n, unpp_stream_t stream);
 
-/* fp32 NCHW [N,C,H,W] -> bf16 NHWC [N,H,W,Cpad] (channels >= C zero-filled). */
+/* fp32 NCHW [N,C,H,W] -> bf16 NHWC [N,H,W,Cpad] (channels >= C zero-filled); Cpad = 16, or 4 for the first-layer mode. */
 int unpp_nchw_to_nhwc(const float* x, void* out, int N, int C, int H, int W, int Cpad, unpp_stream_t stream);
 /* bf16 NHWC 2x2/2 max pooling (H, W even). */
 int unpp_maxpool2x2(const void* x, void* out, int N, int H, int W, int C, unpp_stream_t stream);

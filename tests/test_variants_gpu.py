@@ -336,3 +336,43 @@ def test_fused_train_step_on_variants(tag):
             continue
         rel = float((got - r).abs().max()) / (float(r.abs().max()) + 1e-30)
         assert rel <= _bounds(k)[0], (tag, k, rel)
+
+
+# ---------------------------------------------------------------------------------------------- first-layer mode (4-channel input pixels)
+@pytest.mark.parametrize("N,H,W,cin", [(2, 32, 32, 3), (1, 8, 8, 3), (1, 24, 40, 3), (3, 64, 96, 1), (1, 16, 136, 4), (2, 256, 256, 3), (1, 72, 8, 2)])
+def test_first_layer_conv_on_4_channel_pixels(N, H, W, cin):
+    """conv00.conv1 (models/unet.py:132) in the first-layer mode: fp32 NCHW -> NHWC4 bf16 (8 B/pixel), 3x3 conv + folded-BN scale + bias +
+    ReLU through overlapping unswizzled K-major descriptors (block2x2 = 2, pack kind 7) vs torch fp64 on the same bf16-rounded operands."""
+    g = torch.Generator().manual_seed(N * 1000 + H + W + cin)
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = bf(torch.randn(16, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5)
+    b = torch.randn(16, generator=g) * 0.1
+    x4 = torch.empty(N, H, W, 4, dtype=torch.bfloat16, device=DEV)
+    ops.nchw_to_nhwc4(x.to(DEV), x4)
+    ref4 = torch.zeros(N, 4, H, W)
+    ref4[:, :cin] = bf(x)
+    assert torch.equal(nchw(x4), ref4)
+    out = torch.empty(N, H, W, 16, dtype=torch.bfloat16, device=DEV)
+    ops.conv([x4], N, H, W, ops.pack_weights_c4(w.to(DEV)), 16, ops.NTile(16, b2=2), 9, bias=b.to(DEV), relu=True, out=out)
+    ref = F.relu(F.conv2d(bf(x).double(), w.double(), b.double(), padding=1))
+    close(nchw(out), ref, 6e-3, "first-layer conv")
+    # folded BatchNorm scale (eval mode) and no ReLU
+    scale = torch.rand(16, generator=g) + 0.5
+    ops.conv([x4], N, H, W, ops.pack_weights_c4(w.to(DEV), scale=scale.to(DEV)), 16, ops.NTile(16, b2=2), 9, bias=b.to(DEV), out=out)
+    ref = F.conv2d(bf(x).double(), bf(w * scale.view(16, 1, 1, 1)).double(), b.double(), padding=1)
+    close(nchw(out), ref, 6e-3, "first-layer conv, folded scale")
+
+
+def test_first_layer_mode_equals_the_16_channel_path():
+    """Same bf16 operands, same fp32 accumulation, different MMA shapes: the two inference paths agree to output rounding."""
+    m = pkg.UNet_Nested()
+    m.load_state_dict(O.synth_state_dict(seed=3))
+    m = m.to(DEV).eval()
+    x = torch.randn(2, 3, 64, 96, generator=torch.Generator().manual_seed(1)).to(DEV)
+    with torch.no_grad():
+        a = [h.clone() for h in m(x)]
+        eng = m._engine(x.device)
+        eng.first_layer_c4, eng._packed_key = False, None
+        b = m(x)
+    for u, v in zip(a, b):
+        assert float((u - v).abs().max()) <= 2e-2

@@ -50,7 +50,33 @@ __device__ __forceinline__ void pack_entry_b2(const UnppPackArgs& a) {
   }
 }
 
+// kind 7: first layer of the 2x2-blocked path with 4-channel (8-byte) pixels.  One K = 16 step is half a window row: per
+// window row dy the K axis is 4 chunks of 8 = (pixel pair, 4 channels): chunk c holds window columns dx = 2c - 1, 2c
+// (dx = -1 and dx >= 4 lie outside the 4x4 window: zero), chunk 3 is all zero.  Layout [dy][chunk][64 columns][8] bf16.
+__device__ __forceinline__ void pack_entry_c4(const UnppPackArgs& a) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 4 * 4 * 64; idx += gridDim.x * blockDim.x) {
+    const int n = idx & 63, chunk = (idx >> 6) & 3, dy = idx >> 8;
+    const int q = n >> 4, co = n & 15, r = dy - (q >> 1);
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ci = e & 3, dx = 2 * chunk + (e >> 2) - 1, sft = dx - (q & 1);
+      float w = 0.f;
+      if (chunk < 3 && ci < a.src_I && r >= 0 && r <= 2 && sft >= 0 && sft <= 2) {
+        w = a.src[(size_t(co) * a.src_I + ci) * 9 + r * 3 + sft];
+        if (a.scale) w *= a.scale[co];
+      }
+      v[e] = __float2bfloat16_rn(w);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dst) + size_t(idx) * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
 __device__ __forceinline__ void pack_entry(const UnppPackArgs& a) {
+  if (a.kind == 7) {
+    pack_entry_c4(a);
+    return;
+  }
   if (a.kind >= 4) {
     pack_entry_b2(a);
     return;
@@ -139,6 +165,42 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
     uint4* o = reinterpret_cast<uint4*>(out + i * CPAD);
 #pragma unroll
     for (int k = 0; k < CPAD / 8; ++k) o[k] = reinterpret_cast<const uint4*>(v)[k];
+  }
+}
+
+// NCHW fp32 (C <= 4) -> NHWC bf16 with 4 channels per pixel (8 B): the input of the first-layer mode of conv_tc.  A thread
+// converts four consecutive pixels (one float4 per plane in, 32 contiguous bytes out) when H*W is a multiple of 4.
+__global__ void nchw_to_nhwc4_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C, long HW) {
+  unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
+  unpp::pdl_trigger();
+  const long stride = long(gridDim.x) * blockDim.x, i0 = blockIdx.x * long(blockDim.x) + threadIdx.x;
+  if (!(HW & 3) && !(reinterpret_cast<uintptr_t>(x) & 15)) {
+    const long HW4 = HW >> 2, quads = long(N) * HW4;
+    for (long i = i0; i < quads; i += stride) {
+      const long n = i / HW4, p4 = i % HW4;
+      float4 f[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) f[c] = c < C ? __ldg(reinterpret_cast<const float4*>(x + (n * C + c) * HW) + p4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      uint32_t w[8];
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn((&f[0].x)[px], (&f[1].x)[px]), hi = __floats2bfloat162_rn((&f[2].x)[px], (&f[3].x)[px]);
+        w[2 * px] = *reinterpret_cast<uint32_t*>(&lo), w[2 * px + 1] = *reinterpret_cast<uint32_t*>(&hi);
+      }
+      uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+      o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+    return;
+  }
+  const long total = long(N) * HW;
+  for (long i = i0; i < total; i += stride) {
+    const long n = i / HW, p = i % HW;
+    float f[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) f[c] = c < C ? __ldg(x + (n * C + c) * HW + p) : 0.f;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
+    *reinterpret_cast<uint2*>(out + i * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
   }
 }
 
@@ -278,13 +340,15 @@ inline int grid_for(long total, int block) {
 
 extern "C" int unpp_pack_weights(const UnppPackArgs* a, unpp_stream_t stream) {
   if (!a || !a->src || !a->dst) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: null pointer");
-  if (a->kind < 0 || a->kind > 6) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: bad kind");
-  if (a->kind >= 4 && (a->taps != (a->kind == 6 ? 9 : 16) || a->n_total != 64 || a->n_tile != 64))
+  if (a->kind < 0 || a->kind > 7) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: bad kind");
+  if (a->kind == 7 && (a->taps != 4 || a->n_total != 64 || a->n_tile != 64 || a->k_count != 32 || a->k8_total != 4 || a->k_dst8 || a->src_O != 16 || a->src_I > 4))
+    return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: kind 7 (first layer) needs taps=4, n_total=n_tile=64, k_count=32 and a [16][<=4][3][3] source");
+  if (a->kind >= 4 && a->kind < 7 && (a->taps != (a->kind == 6 ? 9 : 16) || a->n_total != 64 || a->n_tile != 64))
     return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: 2x2-blocked kinds need taps=16 (kind 6: 9), n_total=n_tile=64");
   if (a->n_tile < 8 || a->n_total % a->n_tile || a->k_count % 8 || a->k_count < 8 || a->taps < 1)
     return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: n_total %% n_tile, k_count %% 8 must be 0");
   if (a->k_dst8 + a->k_count / 8 > a->k8_total) return unpp::fail(UNPP_ERR_BAD_ARG, "pack_weights: K range exceeds k8_total");
-  const long total = a->kind >= 4 ? long(a->kind == 6 ? b2::kLowUnits : b2::kMainUnits) * 16 * (a->k_count / 8) : long(a->n_total) * a->taps * (a->k_count / 8);
+  const long total = a->kind == 7 ? 1024 : a->kind >= 4 ? long(a->kind == 6 ? b2::kLowUnits : b2::kMainUnits) * 16 * (a->k_count / 8) : long(a->n_total) * a->taps * (a->k_count / 8);
   unpp::launch(pack_weights_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), *a);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("pack_weights: launch");
   return UNPP_OK;
@@ -299,8 +363,13 @@ extern "C" int unpp_pack_weights_batched(const UnppPackArgs* table_dev, int n, u
 
 extern "C" int unpp_nchw_to_nhwc(const float* x, void* out, int N, int C, int H, int W, int Cpad, unpp_stream_t stream) {
   if (!x || !out || N < 1 || C < 1 || H < 1 || W < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "nchw_to_nhwc: bad argument");
-  if (Cpad != 16 || C > Cpad) return unpp::fail(UNPP_ERR_UNSUPPORTED, "nchw_to_nhwc: Cpad must be 16 and C <= 16");
+  if ((Cpad != 16 && Cpad != 4) || C > Cpad) return unpp::fail(UNPP_ERR_UNSUPPORTED, "nchw_to_nhwc: Cpad must be 16 or 4 and C <= Cpad");
   const long total = (long(H) * W) % 4 ? long(N) * H * W : long(N) * H * W / 4;
+  if (Cpad == 4) {
+    unpp::launch(nchw_to_nhwc4_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), x, reinterpret_cast<__nv_bfloat16*>(out), N, C, long(H) * W);
+    if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("nchw_to_nhwc: launch");
+    return UNPP_OK;
+  }
   unpp::launch(nchw_to_nhwc_kernel<16>, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       x, reinterpret_cast<__nv_bfloat16*>(out), N, C, long(H) * W);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("nchw_to_nhwc: launch");

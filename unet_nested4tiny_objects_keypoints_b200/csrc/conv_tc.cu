@@ -72,6 +72,7 @@ struct ConvTcParams {
   const float* aux_istd;
   int nacc;      // accumulator sets in TMEM (2 or 4): the epilogue of tile i overlaps the MMAs of tiles i+1 .. i+nacc-1
   int b2, b2_P;  // 2x2 output blocking: flag, pixel PAIRS per staged tile row (TW/2 + 2)
+  int c4;        // with b2: first-layer mode, the one source has 4 channels (8 B pixels, 16 B pair rows, no swizzle); b2_P = TW/2 + 3
   // fused transposed conv (with b2): one extra K chunk per tile read from the low-resolution tensor
   CUtensorMap lowmap;
   int low_on, low_P, low_k8, low_w_off, low_w_bytes;  // low_P = low-res pixels per staged tile row (TW/2 + 2); offsets in bytes
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
             continue;
           }
           if (p.b2) {  // pixel-pair rows (64 B), 34 image rows x (TW/2 + 2) pairs around a 32 x TW output tile
-            mbar_arrive_expect_tx(&bar_full[s], 34 * p.b2_P * 64);
+            mbar_arrive_expect_tx(&bar_full[s], 34 * p.b2_P * (p.c4 ? 16 : 64));
             tma_load_4d(&p.maps[p.ch_map[c]], &bar_full[s], stage0 + size_t(s) * p.stage_bytes, 0, tx * (p.TW >> 1) - 1, ty * 32 - 1, n);
             continue;
           }
@@ -556,7 +557,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     mbar_wait(&bar_w, 0);
     const int ncols = p.ncols, nsub = p.nsub, taps = p.taps, k8_total = p.k8_total, nchunk = p.nchunk, nstage = p.nstage;
     const int ntiles = p.ntiles, stage_bytes = p.stage_bytes, dbg = p.dbg, b2 = p.b2, b2_P = p.b2_P, nacc = p.nacc;
-    const int low_on = p.low_on, low_P = p.low_P, low_k8 = p.low_k8, low_w_off = p.low_w_off;
+    const int low_on = p.low_on, low_P = p.low_P, low_k8 = p.low_k8, low_w_off = p.low_w_off, c4 = p.c4;
     const uint32_t idesc = make_idesc_bf16(128, ncols), idesc32 = make_idesc_bf16(128, 32), idesc16 = make_idesc_bf16(128, 16);
     const uint32_t w_addr = smem_u32(w_smem);
     const uint32_t stage_addr0 = smem_u32(stage0);
@@ -604,6 +605,30 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
                 const uint32_t idn = nb == 4 ? idesc : nb == 2 ? idesc32 : idesc16, dcol = uint32_t(blk.b0 * 16);
                 if (has0) umma_bf16(acc0 + dcol, (uint64_t(a_hi) << 32) | (a_lo0 + ao), bdesc, idn, 1u);
                 if (has1) umma_bf16(acc1 + dcol, (uint64_t(a_hi) << 32) | (a_lo1 + ao), bdesc, idn, 1u);
+              }
+            }
+          }
+        } else if (c4) {
+          if (elect_one() && !(dbg & 2)) {
+            // First layer (<= 4 input channels, 8-byte pixels): 2x2 output blocks again, but one K = 16 step is a whole
+            // window ROW segment — the 16-byte pair rows are unswizzled K-major core-matrix rows, GEMM row j (block j) starts
+            // at pair j and its two 16-byte K chunks are pairs (j, j+1) resp. (j+2, j+3): LBO = 16 B makes consecutive GEMM
+            // rows overlapping windows of the same staged image row.  Window pixels -2 .. +5 around the block (weights are
+            // zero outside -1 .. +2): 2 MMAs of N = 64 per window row, 8 per 512 output pixels (20 on the 16-channel path).
+            const uint64_t ad = make_sdesc(stage_addr0 + uint32_t(s) * stage_bytes, 16, uint32_t(2 * b2_P * 16), 0);
+            const uint64_t bd = make_sdesc(w_addr, 1024, 128, 0);  // packed [dy][4 K chunks][64 columns][8] (pack kind 7)
+            const uint32_t a_hi = uint32_t(ad >> 32), b_hi = uint32_t(bd >> 32), b_lo = uint32_t(bd);
+            const uint32_t a_lo0 = uint32_t(ad) + uint32_t(mw * 8), a_lo1 = a_lo0 + uint32_t(kMmaWarps * 8);
+            const uint32_t acc0 = acc + uint32_t(mw * 64), acc1 = acc + uint32_t((mw + kMmaWarps) * 64);
+#pragma unroll
+            for (int dy = 0; dy < 4; ++dy) {
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                const uint32_t ao = uint32_t(dy * b2_P + 2 * hf);
+                const uint64_t bdesc = (uint64_t(b_hi) << 32) | (b_lo + uint32_t((dy * 4096 + hf * 2048) >> 4));
+                const uint32_t accum = (dy | hf) ? 1u : 0u;
+                if (has0) umma_bf16(acc0, (uint64_t(a_hi) << 32) | (a_lo0 + ao), bdesc, idesc, accum);
+                if (has1) umma_bf16(acc1, (uint64_t(a_hi) << 32) | (a_lo1 + ao), bdesc, idesc, accum);
               }
             }
           }
@@ -942,7 +967,7 @@ EncodeTiledFn get_encode() {
 
 struct Plan {
   int TW, nsub, nstage, stage_bytes, w_bytes, w_smem_bytes, tmem_cols, smem_total, grid_x, grid_y, tiles_x, tiles_y, ntiles;
-  int nchunk, k8_total, b2, b2_P, ncols, nacc, low_on, low_w_off, low_w_bytes;
+  int nchunk, k8_total, b2, b2_P, c4, ncols, nacc, low_on, low_w_off, low_w_bytes;
   int ch_map[kMaxChunks], ch_c0[kMaxChunks], ch_span[kMaxChunks], ch_wk8[kMaxChunks];
 };
 
@@ -957,7 +982,8 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
   int nchunk = 0, k8 = 0, max_span = 0;
   for (int i = 0; i < a->nsrc; ++i) {
     const int C = a->src_C[i];
-    if (C != 16 && C != 32 && C != 64 && C != 128) return unpp::fail(UNPP_ERR_UNSUPPORTED, "conv_tc: source channels must be 16/32/64/128");
+    const bool c4src = C == 4 && a->block2x2 == 2 && a->nsrc == 1;  // first-layer mode: one 4-channel source
+    if (C != 16 && C != 32 && C != 64 && C != 128 && !c4src) return unpp::fail(UNPP_ERR_UNSUPPORTED, "conv_tc: source channels must be 16/32/64/128");
     if (!a->src[i] || (reinterpret_cast<uintptr_t>(a->src[i]) & 15)) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: source pointer null or unaligned");
     if (a->src_step[i] < 0 || a->src_step[i] > 2 || (a->src_step[i] == 2 && (a->taps != 1 || (a->src_oy[i] & ~1) || (a->src_ox[i] & ~1))))
       return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: strided sources need taps=1 and offsets in {0,1}");
@@ -971,7 +997,7 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
     }
   }
   pl->nchunk = nchunk, pl->k8_total = k8;
-  pl->b2 = 0, pl->b2_P = 0, pl->ncols = a->n_tile, pl->low_on = 0, pl->low_w_off = 0, pl->low_w_bytes = 0;
+  pl->b2 = 0, pl->b2_P = 0, pl->c4 = 0, pl->ncols = a->n_tile, pl->low_on = 0, pl->low_w_off = 0, pl->low_w_bytes = 0;
   if (a->lowres_src && !a->block2x2) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: lowres_src (fused transposed conv) needs block2x2");
   if (a->bias_classes != 0 && a->bias_classes != 1 && a->bias_classes != 9) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: bias_classes must be 0, 1 or 9");
   // static shared memory: 18 KB in the training variants (statistics slots), 2 KB otherwise; 227 KB per CTA in total
@@ -980,12 +1006,15 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
     // 2x2 output blocking: every source is one 16-channel chunk staged as 64-byte pixel-pair rows; N = 4 x 16
     if (a->taps != 9 || a->mode != UNPP_MODE_CONV || a->n_total != 16 || a->n_tile != 16 || (a->H & 1) || (a->W & 1))
       return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: block2x2 needs a 3x3 conv with n_total = n_tile = 16 and even H, W");
-    for (int i = 0; i < a->nsrc; ++i) {
+    const bool c4 = a->block2x2 == 2;
+    if (c4 && (a->nsrc != 1 || a->src_C[0] != 4 || a->src_step[0] == 2 || a->lowres_src || is_train(a)))
+      return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: block2x2 = 2 (first layer) needs one dense 4-channel source and the inference epilogue");
+    for (int i = 0; i < a->nsrc && !c4; ++i) {
       if (a->src_C[i] != 16 || a->src_step[i] == 2) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: block2x2 needs dense 16-channel sources");
       pl->ch_span[i] = 64, pl->ch_wk8[i] = 2 * i;
     }
-    pl->b2 = 1, pl->ncols = 64;
-    pl->w_bytes = (k8 / 2) * b2::kMainUnits * b2::kUnitBytes;  // only the non-zero (position, pixel) blocks are stored (b2_blocks.h)
+    pl->b2 = 1, pl->c4 = c4, pl->ncols = 64;
+    pl->w_bytes = c4 ? 16384 : (k8 / 2) * b2::kMainUnits * b2::kUnitBytes;  // only the non-zero (position, pixel) blocks are stored (b2_blocks.h)
     pl->w_smem_bytes = (pl->w_bytes + 1023) / 1024 * 1024;
     if (a->lowres_src) {
       if (a->lowres_C != 32 || !a->lowres_wpacked || (a->H & 3) || (a->W & 3) || is_train(a) || (reinterpret_cast<uintptr_t>(a->lowres_src) & 15))
@@ -1001,8 +1030,8 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
       if ((cap == 16 || cap == 32) && TW > cap) TW = cap;
     }
     for (;; TW >>= 1) {
-      pl->b2_P = TW / 2 + 2;
-      pl->stage_bytes = (34 * pl->b2_P * 64 + 1023) / 1024 * 1024;
+      pl->b2_P = TW / 2 + (c4 ? 3 : 2);
+      pl->stage_bytes = (34 * pl->b2_P * (c4 ? 16 : 64) + 1023) / 1024 * 1024;
       pl->nstage = (smem_budget - pl->w_smem_bytes) / pl->stage_bytes;
       if (pl->nstage >= 2 || TW == 16) break;
     }
@@ -1102,6 +1131,10 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
       box[0] = 32, box[1] = cuuint32_t(pl.b2_P), box[2] = 34;
       sw = CU_TENSOR_MAP_SWIZZLE_64B;
     }
+    if (pl.c4) {  // first layer: [N,H,W,4] seen as [N,H,W/2,8], a pixel pair = 16 B, dense unswizzled rows in shared memory
+      gd[0] = 8, gs[0] = 16, box[0] = 8;
+      sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+    }
     CUresult r = enc(&p.maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<uint8_t*>(base), gd, gs, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return unpp::fail(UNPP_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled failed (CUresult %d) for source %d", int(r), i);
@@ -1111,7 +1144,7 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   p.N = a->N, p.H = a->H, p.W = a->W;
   p.TW = pl.TW, p.nsub = pl.nsub, p.tiles_x = pl.tiles_x, p.tiles_y = pl.tiles_y, p.ntiles = pl.ntiles;
   p.taps = a->taps, p.ncols = pl.ncols, p.k8_total = pl.k8_total;
-  p.b2 = pl.b2, p.b2_P = pl.b2_P, p.nacc = pl.nacc;
+  p.b2 = pl.b2, p.b2_P = pl.b2_P, p.c4 = pl.c4, p.nacc = pl.nacc;
   p.bias9 = a->bias_classes == 9;
   p.pooled = reinterpret_cast<__nv_bfloat16*>(a->pooled);
   if (pl.low_on) {

@@ -92,6 +92,7 @@ class Engine:
         self._packed_key = None
         self._arena: Dict[Tuple, Dict[str, torch.Tensor]] = {}
         self._keep: List = []
+        self.first_layer_c4 = True  # inference: conv00.conv1 reads a 4-channel NHWC input (8 B/pixel) through the first-layer MMA mode
         self.fuse_deconv = True  # inference: fold the k2s2 transposed conv of the full-resolution nodes into the consuming conv
 
     # ------------------------------------------------------------------------------ weights
@@ -122,6 +123,11 @@ class Engine:
                         bias = ((conv.bias - bn.running_mean) * scale + bn.bias).float().contiguous()
                     else:  # unet.py:137-143: conv + ReLU only
                         scale, bias = None, conv.bias.detach().float().contiguous()
+                    if name == "conv00" and n == 1 and self.first_layer_c4 and conv.weight.shape[1] <= 4:
+                        # first layer: 4-channel (8-byte) input pixels instead of the 16-channel zero-padded tensor
+                        P[f"{name}.c{n}"] = dict(w=ops.pack_weights_c4(conv.weight.detach().float(), scale=scale), bias=bias, n_total=16,
+                                                 n_tile=ops.NTile(16, b2=2), c4=True)
+                        continue
                     P[f"{name}.c{n}"] = self._pack_fwd_conv(conv.weight, scale, bias)
             for name in DECODER_ORDER:
                 up = getattr(self.model, name)
@@ -174,7 +180,7 @@ class Engine:
         if a is None:
             f = self.filters
             bf = dict(dtype=torch.bfloat16, device=self.device)
-            a = {"x16": torch.empty(B, H, W, 16, **bf)}
+            a = {"x16": torch.empty(B, H, W, 16, **bf)} if kind != "eval4" else {"x4": torch.empty(B, H, W, 4, **bf)}
             for lvl, (node, c) in enumerate(zip(ENCODER, f)):
                 h, w = H >> lvl, W >> lvl
                 a[f"{node}.a"] = torch.empty(B, h, w, c, **bf)
@@ -222,10 +228,15 @@ class Engine:
         B, H, W = self._check_input(x)
         x = x.contiguous()
         P = self.packed_eval()
-        A = self.arena(B, H, W, "eval")
+        c4 = bool(P["conv00.c1"].get("c4"))
+        A = self.arena(B, H, W, "eval4" if c4 else "eval")
         ncls = self.model.n_classes
-        ops.nchw_to_nhwc16(x, A["x16"])
-        src = A["x16"]
+        if c4:
+            ops.nchw_to_nhwc4(x, A["x4"])
+            src = A["x4"]
+        else:
+            ops.nchw_to_nhwc16(x, A["x16"])
+            src = A["x16"]
         for lvl, name in enumerate(ENCODER):
             h, w = H >> lvl, W >> lvl
             p1, p2 = P[f"{name}.c1"], P[f"{name}.c2"]

@@ -223,6 +223,20 @@ def nchw_to_nhwc16(x: torch.Tensor, out: torch.Tensor) -> None:
         _lib.check(lib().unpp_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, Cin, H, W, 16, _stream()), "unpp_nchw_to_nhwc")
 
 
+def nchw_to_nhwc4(x: torch.Tensor, out: torch.Tensor) -> None:
+    """fp32 NCHW (C <= 4) -> bf16 NHWC with 4 channels per pixel (8 B): the input of the first-layer conv mode (NTile(16, b2=2))."""
+    B, Cin, H, W = x.shape
+    assert tuple(out.shape) == (B, H, W, 4) and out.dtype == torch.bfloat16 and out.is_contiguous()
+    _count()
+    with _Traced("nchw_to_nhwc4", x.numel() * 4 + out.numel() * 2, 0):
+        _lib.check(lib().unpp_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, Cin, H, W, 4, _stream()), "unpp_nchw_to_nhwc")
+
+
+def pack_weights_c4(src: torch.Tensor, scale=None) -> torch.Tensor:
+    """Weights [16][Cin <= 4][3][3] of the network's first conv for the 4-channel first-layer mode (unpp.h kind 7)."""
+    return pack_weights(src, 7, 4, 64, 64, 32, scale=scale)
+
+
 def maxpool(x: torch.Tensor, out: torch.Tensor) -> None:
     B, H, W, Cc = x.shape
     _count()
