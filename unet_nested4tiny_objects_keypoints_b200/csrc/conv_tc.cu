@@ -967,13 +967,33 @@ EncodeTiledFn get_encode() {
 
 struct Plan {
   int TW, nsub, nstage, stage_bytes, w_bytes, w_smem_bytes, tmem_cols, smem_total, grid_x, grid_y, tiles_x, tiles_y, ntiles;
-  int nchunk, k8_total, b2, b2_P, c4, ncols, nacc, low_on, low_w_off, low_w_bytes;
+  int nchunk, k8_total, b2, b2_P, c4, cw, ncols, nacc, low_on, low_w_off, low_w_bytes;
   int ch_map[kMaxChunks], ch_c0[kMaxChunks], ch_span[kMaxChunks], ch_wk8[kMaxChunks];
 };
 
 inline bool is_train(const UnppConvArgs* a) { return a->addend || a->relu_mask_src || a->stats_partial || a->logit || a->drop_mask; }
 
+int make_plan_cw(const UnppConvArgs* a, Plan* pl, int cw);
+
+// K chunks are <= 64 channels wide (128-byte swizzled tile rows).  When the resident weights of a wide n_tile leave no room
+// for two 16-column-or-wider stages, 32-channel chunks (64-byte rows, half the stage size) are tried: an N = 64 MMA per
+// operand fetch instead of two N = 32 ones for the 128-channel layers of the deep levels.
 int make_plan(const UnppConvArgs* a, Plan* pl) {
+  int rc = make_plan_cw(a, pl, 64);
+  static const int prefer32 = [] { const char* e = getenv("UNPP_CW32"); return e ? atoi(e) : 0; }();  // experiment: 32-channel chunks whenever they give a wider tile
+  if (a && !a->block2x2 && a->taps == 9 && a->mode == UNPP_MODE_CONV && a->n_tile >= (prefer32 ? 32 : 64) && (rc != UNPP_OK || pl->TW < (prefer32 ? 64 : 16))) {
+    bool wide = true;
+    for (int i = 0; i < a->nsrc && i < UNPP_MAX_SRC; ++i) wide = wide && a->src_C[i] >= 64;
+    Plan alt;
+    if (wide && make_plan_cw(a, &alt, 32) == UNPP_OK && alt.TW >= 16 && (rc != UNPP_OK || alt.TW > pl->TW)) {
+      *pl = alt;
+      return UNPP_OK;
+    }
+  }
+  return rc;
+}
+
+int make_plan_cw(const UnppConvArgs* a, Plan* pl, int cw) {
   if (!a || a->nsrc < 1 || a->nsrc > UNPP_MAX_SRC) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: nsrc out of range");
   if (a->taps != 9 && a->taps != 1) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: taps must be 1 or 9");
   if (a->N < 1 || a->H < 1 || a->W < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: empty pixel grid");
@@ -987,16 +1007,16 @@ int make_plan(const UnppConvArgs* a, Plan* pl) {
     if (!a->src[i] || (reinterpret_cast<uintptr_t>(a->src[i]) & 15)) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: source pointer null or unaligned");
     if (a->src_step[i] < 0 || a->src_step[i] > 2 || (a->src_step[i] == 2 && (a->taps != 1 || (a->src_oy[i] & ~1) || (a->src_ox[i] & ~1))))
       return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: strided sources need taps=1 and offsets in {0,1}");
-    for (int c0 = 0; c0 < C; c0 += 64) {
+    for (int c0 = 0; c0 < C; c0 += cw) {
       if (nchunk >= kMaxChunks) return unpp::fail(UNPP_ERR_UNSUPPORTED, "conv_tc: too many K chunks");
-      const int w = C - c0 < 64 ? C - c0 : 64;
+      const int w = C - c0 < cw ? C - c0 : cw;
       pl->ch_map[nchunk] = i, pl->ch_c0[nchunk] = c0, pl->ch_span[nchunk] = w * 2, pl->ch_wk8[nchunk] = k8;
       k8 += w / 8;
       if (w * 2 > max_span) max_span = w * 2;
       ++nchunk;
     }
   }
-  pl->nchunk = nchunk, pl->k8_total = k8;
+  pl->nchunk = nchunk, pl->k8_total = k8, pl->cw = cw;
   pl->b2 = 0, pl->b2_P = 0, pl->c4 = 0, pl->ncols = a->n_tile, pl->low_on = 0, pl->low_w_off = 0, pl->low_w_bytes = 0;
   if (a->lowres_src && !a->block2x2) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: lowres_src (fused transposed conv) needs block2x2");
   if (a->bias_classes != 0 && a->bias_classes != 1 && a->bias_classes != 9) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: bias_classes must be 0, 1 or 9");
@@ -1116,7 +1136,7 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   const int pad = a->taps == 9 ? 1 : 0;
   for (int i = 0; i < a->nsrc; ++i) {
     const cuuint64_t C = a->src_C[i];
-    const int box_c = C < 64 ? int(C) : 64;
+    const int box_c = C < cuuint64_t(pl.cw) ? int(C) : pl.cw;
     const cuuint64_t st = a->src_step[i] == 2 ? 2 : 1, fullW = cuuint64_t(a->W) * st, fullH = cuuint64_t(a->H) * st;
     const uint8_t* base = reinterpret_cast<const uint8_t*>(a->src[i]);
     if (st == 2) base += (size_t(a->src_oy[i]) * fullW + a->src_ox[i]) * C * 2;
