@@ -79,6 +79,7 @@ struct ConvTcParams {
   const __nv_bfloat16* low_wpacked;
   int bias9;     // bias is a [9][16] (row class, column class) table
   __nv_bfloat16* pooled;  // fused 2x2 max pool of the output (inference epilogue), or null
+  int pf;   // L2 prefetch distance of the TMA producer in (tile, chunk) steps beyond the stage ring; 0 = off
   int dbg;  // UNPP_DBG experiment bits (0 in production): 1 = epilogue skips its work, 2 = no MMAs issued, 4 = no TMA tile loads,
             // 8 = epilogue does not store its bf16 output, 16 = epilogue does not read TMEM
 };
@@ -520,11 +521,33 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
           bulk_load(w_smem + p.low_w_off + off, lsrc + off, n, &bar_w);
         }
       }
+      // Box of step (tile, chunk): tensor map and coordinates, shared by the load and by the L2 prefetch that runs ahead of it.
+      auto box_of = [&](int tile, int c, const CUtensorMap*& map, int& c0, int& c1, int& c2, int& c3) {
+        const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y;
+        c3 = tile / (p.tiles_x * p.tiles_y);
+        if (c == p.nchunk) map = &p.lowmap, c0 = 0, c1 = tx * (p.TW >> 1) - 1, c2 = ty * 16 - 1;
+        else if (p.b2) map = &p.maps[p.ch_map[c]], c0 = 0, c1 = tx * (p.TW >> 1) - 1, c2 = ty * 32 - 1;
+        else map = &p.maps[p.ch_map[c]], c0 = p.ch_c0[c], c1 = tx * p.TW - pad, c2 = ty * 16 - pad;
+      };
+      const int nper = p.nchunk + p.low_on;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
         for (int c = 0; c < p.nchunk + p.low_on; ++c, ++it) {
           const int s = it % p.nstage, ph = (it / p.nstage) & 1;
+          if (p.pf && !(p.dbg & 4)) {
+            // The stage ring bounds the bytes a CTA has in flight (two 74 KB stages next to the resident weights of the
+            // many-source layers); pulling the boxes of later steps into L2 now decouples the DRAM fetch from that bound:
+            // the load issued when the stage frees is an L2 hit.
+            const int e = it + p.nstage - 1 + p.pf;
+            const int ptile = blockIdx.x + (e / nper) * gridDim.x;
+            if (ptile < p.ntiles) {
+              const CUtensorMap* m;
+              int c0, c1, c2, c3;
+              box_of(ptile, e % nper, m, c0, c1, c2, c3);
+              tma_prefetch_4d(m, c0, c1, c2, c3);
+            }
+          }
           mbar_wait(&bar_empty[s], ph ^ 1);
           if (p.dbg & 4) {
             mbar_arrive(&bar_full[s]);
@@ -1195,6 +1218,7 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   p.stats_partial = a->stats_partial;
   p.stats_aux = reinterpret_cast<const __nv_bfloat16*>(a->stats_aux);
   p.aux_mean = a->aux_mean, p.aux_istd = a->aux_istd;
+  p.pf = [] { const char* d = getenv("UNPP_PF"); return d ? atoi(d) : 0; }();  // L2 prefetch distance of the producer (experiment knob)
   p.dbg = [] { const char* d = getenv("UNPP_DBG"); return d ? atoi(d) : 0; }();  // role-disabling experiment bits (scripts/dbg_conv*.py set it per process run)
 
   const bool deconv = a->mode == UNPP_MODE_DECONV, head = a->head_w != nullptr;
