@@ -253,10 +253,11 @@ class FusedTrainStep:
         if ts.use_masks:
             side = self._side_stream
             side.wait_stream(cur)
+        pack_train(ts)
+        if side is not None:
             with torch.cuda.stream(side):
                 for k in range(3):
                     ops.dropout_mask(ts.t[f"mask{k}"].view(-1), self.p_drop, self.seed * 7919 + k, self.step_counter)
-        pack_train(ts)
         forward_train(ts, self.x, before_decoder=(lambda: cur.wait_stream(side)) if side is not None else None)
         backward_train(ts, self.flat_g, target=self.target, coef=self.coef, loss_kind=self.loss_kind, gamma=self.focal_gamma)
         nacc, ncls = ts.head_nacc, self.model.n_classes
