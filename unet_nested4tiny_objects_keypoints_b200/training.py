@@ -22,6 +22,7 @@ How it runs here (all NHWC bf16 activations / gradients, fp32 accumulation, fp32
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -31,6 +32,7 @@ from .engine import DECODER, DECODER_ORDER, ENCODER, HEAD_OF, Engine, named_para
 from .ops import MODE_DECONV, pick_n_tile
 
 PQ = [(0, 0), (0, 1), (1, 0), (1, 1)]
+WGRAD_SIDE_STREAM = os.environ.get("UNPP_WGRAD_STREAM", "1") != "0"  # weight gradients on a side stream (see backward_train)
 
 
 # ---------------------------------------------------------------------------------------------- flat parameter layout
@@ -102,6 +104,12 @@ class TrainState:
         self.lay, self.nflat = flat_layout(eng.model)
         self.drop_scale = 1.0
         self.use_masks = False
+
+    def wgrad_stream(self) -> torch.cuda.Stream:
+        s = getattr(self, "_wgrad_stream", None)
+        if s is None:
+            s = self._wgrad_stream = torch.cuda.Stream(self.eng.device)
+        return s
 
     def scratch_f32(self, key: str, numel: int) -> torch.Tensor:
         s = self.scratch.get(key)
@@ -320,12 +328,35 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
     def bias_from_stats(part, g, c, pname):
         ops.reduce_partials(part, g, 2 * c, c, G, out_offset=goff(pname), defer=True)
 
+    # Weight gradients only feed the optimizer: they run on a side stream (a parallel branch of the captured step), each one
+    # ordered after the kernel that produced its dZ.  The one-CTA-per-SM kernels of the two streams cannot share an SM, but the
+    # CTAs of a queued weight-gradient kernel take over the SMs a finishing dgrad kernel frees, instead of the whole GPU draining
+    # and re-filling between every pair of dependent launches.
+    cur = torch.cuda.current_stream(eng.device)
+    side = ts.wgrad_stream() if WGRAD_SIDE_STREAM else None
+    if side is not None:
+        side.wait_stream(cur)
+
+    class _on_side:
+        def __enter__(self_):
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                side.wait_event(ev)
+                self_.ctx = torch.cuda.stream(side)
+                self_.ctx.__enter__()
+
+        def __exit__(self_, *exc):
+            if side is not None:
+                self_.ctx.__exit__(*exc)
+
     def wgrad_conv(srcs, dz, h, w, pname, ci_count=None):
         cins = [s.shape[-1] for s in srcs]
         cin, cout = sum(cins), dz.shape[-1]
         g = ops.wgrad_grid(cins, B, h, w, cout, 9)
         part = ts.scratch_f32("wgrad:" + pname, g * 9 * cin * cout)
-        ops.wgrad(srcs, B, h, w, dz, cout, 9, part)
+        with _on_side():
+            ops.wgrad(srcs, B, h, w, dz, cout, 9, part)
         real = cin if ci_count is None else ci_count
         ops.wgrad_reduce(part, g, 9, cin, cout, G, 0, real, real * 9, 9, 1, dst_offset=goff(pname), defer=True)
 
@@ -333,7 +364,8 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
         cin, cout = xhigh.shape[-1], dU.shape[-1]
         g = ops.wgrad_grid([cin], B, h2, w2, cout, 1, dz_view="all4")
         part = ts.scratch_f32("wgrad:" + pname, 4 * g * cin * cout)
-        ops.wgrad([xhigh], B, h2, w2, dU, cout, 1, part, dz_view="all4")
+        with _on_side():
+            ops.wgrad([xhigh], B, h2, w2, dU, cout, 1, part, dz_view="all4")
         for pq in range(4):
             ops.wgrad_reduce(part, g, 1, cin, cout, G, 0, cin, 4, cout * 4, 0, dst_offset=goff(pname) + pq, partial_offset=pq * g * cin * cout, defer=True)
 
@@ -344,7 +376,8 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
         cin, cout = xhigh.shape[-1], dV.shape[-1]
         g = ops.wgrad_grid([cin], B, h2, w2, cout, 1)
         part = ts.scratch_f32("wgrad:" + pname, g * cin * cout)
-        ops.wgrad([xhigh], B, h2, w2, dV, cout, 1, part)
+        with _on_side():
+            ops.wgrad([xhigh], B, h2, w2, dV, cout, 1, part)
         ops.wgrad_reduce(part, g, 1, cin, cout, G, 0, cin, cin, 1, 0, dst_offset=goff(pname), defer=True)
 
     def up_dgrad_srcs_C(dname):
@@ -505,6 +538,8 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
             cprev = eng.filters[lvl - 1]
             ops.conv([dz1], B, h, w, P[key], cprev, P[key + ".nt"], 9, out=t[f"dP{lvl - 1}0"])
             ops.maxpool_bwd(t[f"X{lvl - 1}0"], t[f"dP{lvl - 1}0"], t[f"dpool{lvl - 1}"])
+    if side is not None:
+        cur.wait_stream(side)
     ops.flush_reduce_queue(ts.__dict__.setdefault("_reduce_tables", {}), eng.device)
 
 
