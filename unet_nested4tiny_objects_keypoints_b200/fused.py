@@ -249,16 +249,16 @@ class FusedTrainStep:
         # branch of the captured graph) next to the weight re-packing and the encoder; the CUDA-core mask kernel co-resides with
         # the one-CTA-per-SM tensor-core convolutions (no shared memory, few registers) instead of serialising 3 launches.
         cur = torch.cuda.current_stream(self.dev)
-        side = None
-        if ts.use_masks:
-            side = self._side_stream
-            side.wait_stream(cur)
-        pack_train(ts)
-        if side is not None:
-            with torch.cuda.stream(side):
+        side = self._side_stream
+        side.wait_stream(cur)
+        packed = torch.cuda.Event()
+        with torch.cuda.stream(side):  # the weight re-packing runs next to the input layout conversion, the masks next to the encoder
+            pack_train(ts)
+            packed.record(side)
+            if ts.use_masks:
                 for k in range(3):
                     ops.dropout_mask(ts.t[f"mask{k}"].view(-1), self.p_drop, self.seed * 7919 + k, self.step_counter)
-        forward_train(ts, self.x, before_decoder=(lambda: cur.wait_stream(side)) if side is not None else None)
+        forward_train(ts, self.x, after_input=lambda: cur.wait_event(packed), before_decoder=lambda: cur.wait_stream(side))
         backward_train(ts, self.flat_g, target=self.target, coef=self.coef, loss_kind=self.loss_kind, gamma=self.focal_gamma)
         nacc, ncls = ts.head_nacc, self.model.n_classes
         ops.reduce_partials(ts.t["head_red"], 3, nacc, 1, self.loss, scale=self.loss_scale, partial_offset=ncls * 17)

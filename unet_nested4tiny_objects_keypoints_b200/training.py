@@ -230,13 +230,15 @@ def _pack_train_jobs(ts: TrainState) -> None:
 
 
 # ---------------------------------------------------------------------------------------------- forward (train mode)
-def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = True, before_decoder=None) -> Tuple[torch.Tensor, ...]:
+def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = True, before_decoder=None, after_input=None) -> Tuple[torch.Tensor, ...]:
     eng, t, P, m = ts.eng, ts.t, ts.packed, ts.eng.model
     B, H, W = ts.B, ts.H, ts.W
     ncls = m.n_classes
     if update_running_stats:
         eng._packed_key = None  # running statistics change below without a torch version bump: drop the eval-mode fold cache
     ops.nchw_to_nhwc16(x, t["x16"])
+    if after_input is not None:
+        after_input()  # join point for the weight re-packing the caller put on a side stream
     src = t["x16"]
     tracked: List[torch.Tensor] = []
     for lvl, name in enumerate(ENCODER):
