@@ -337,7 +337,12 @@ def bench_train(args, rank, world, local):
         step._fwd_bwd()
         step._update()
         launches = ops.launch_count - n0
-        agg, reps = trace_kernels(lambda: (step._fwd_bwd(), step._update()))
+        from unet_nested4tiny_objects_keypoints_b200 import training as _tr
+        side_on, _tr.WGRAD_SIDE_STREAM = _tr.WGRAD_SIDE_STREAM, False  # per-kernel events: one kernel at a time (the timed steps above ran with the side stream)
+        try:
+            agg, reps = trace_kernels(lambda: (step._fwd_bwd(), step._update()))
+        finally:
+            _tr.WGRAD_SIDE_STREAM = side_on
         roof = roofline_from_trace(agg, reps, "conv_tc", pk)
         roof_w = roofline_from_trace(agg, reps, "wgrad taps", pk)
         step_ms = ms / args.steps

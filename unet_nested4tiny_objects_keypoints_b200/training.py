@@ -32,7 +32,9 @@ from .engine import DECODER, DECODER_ORDER, ENCODER, HEAD_OF, Engine, named_para
 from .ops import MODE_DECONV, pick_n_tile
 
 PQ = [(0, 0), (0, 1), (1, 0), (1, 1)]
-WGRAD_SIDE_STREAM = os.environ.get("UNPP_WGRAD_STREAM", "1") != "0"  # weight gradients on a side stream (see backward_train)
+# Side streams of the training step: weight gradients (see backward_train), weight re-packing and dropout masks (fused.FusedTrainStep).
+# bench.py switches them off for its per-kernel trace so that CUDA events bracket one kernel at a time.
+WGRAD_SIDE_STREAM = os.environ.get("UNPP_WGRAD_STREAM", "1") != "0"
 
 
 # ---------------------------------------------------------------------------------------------- flat parameter layout
