@@ -15,6 +15,7 @@ PyTorch owns all device memory (activation arena, packed weights); this module o
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -93,7 +94,7 @@ class Engine:
         self._arena: Dict[Tuple, Dict[str, torch.Tensor]] = {}
         self._keep: List = []
         self.first_layer_c4 = True  # inference: conv00.conv1 reads a 4-channel NHWC input (8 B/pixel) through the first-layer MMA mode
-        self.pair_level1 = True   # inference: the 32-channel level runs in pixel-pair mode (1x2 output blocking, ops.compose_pair_weights)
+        self.pair_level1 = os.environ.get("UNPP_PAIR", "0") == "1"   # (off: measured slower than the per-pixel path) inference: the 32-channel level runs in pixel-pair mode (1x2 output blocking, ops.compose_pair_weights)
         self.fuse_deconv = True  # inference: fold the k2s2 transposed conv of the full-resolution nodes into the consuming conv
 
     # ------------------------------------------------------------------------------ weights
