@@ -102,13 +102,6 @@ typedef struct UnppConvArgs {
   /* Fused nn.MaxPool2d(2) of the output (models/unet.py:219,258,260,262): NHWC bf16 [N, H/2, W/2, n_total], written next to
    * `out` by the inference epilogue (conv mode, relu = 1, even H and W, no head, no training operand).  NULL = no pooling. */
   void* pooled;
-  /* Pixel-pair mode (inference epilogue, 3x3 conv, n_total = n_tile = 64): every tensor is passed as its pair view
-   * [N,H,W/2,2c] (same memory), W = pairs per row; GEMM row = a horizontal pixel pair, column = (pixel of the pair, co).
-   * The composed weights are sparse — of the neighbouring pairs only one pixel reaches the block — and wpacked holds just
-   * the non-zero parts: 3 centre blocks [K/8][64][8] (tap row r), then 6 side blocks [K/16][32][8] (r, left/right), where K
-   * lists, per source, the left pixel's channels then the right pixel's (side blocks: the one contributing pixel).
-   * bias has 64 entries (the per-channel bias twice). */
-  int32_t pair_skip;
 } UnppConvArgs;
 
 const char* unpp_last_error(void);

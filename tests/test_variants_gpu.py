@@ -376,34 +376,3 @@ def test_first_layer_mode_equals_the_16_channel_path():
         b = m(x)
     for u, v in zip(a, b):
         assert float((u - v).abs().max()) <= 2e-2
-
-
-# ---------------------------------------------------------------------------------------------- pixel-pair mode (32-channel level)
-@pytest.mark.parametrize("N,H,W,srcs", [(2, 16, 16, [32]), (1, 8, 24, [32, 32]), (1, 32, 40, [32, 32, 32]), (2, 4, 4, [16]), (1, 128, 128, [32, 32]), (3, 64, 64, [16])])
-def test_conv3x3_pixel_pair_mode(N, H, W, srcs):
-    """3x3 conv -> 32 channels on the pair view [N,H,W/2,2c] of every tensor (conv(pair=True), ops.compose_pair_weights): dense centre
-    taps, half-K N = 32 side taps; vs torch fp64 on the same bf16-rounded operands."""
-    g = torch.Generator().manual_seed(H * 7 + W + len(srcs))
-    cin = sum(srcs)
-    xs = [bf(torch.randn(N, c, H, W, generator=g)) for c in srcs]
-    w = bf(torch.randn(32, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5)
-    b = torch.randn(32, generator=g) * 0.1
-    ref = F.relu(F.conv2d(torch.cat(xs, 1).double(), w.double(), b.double(), padding=1))
-    out = torch.empty(N, H, W, 32, dtype=torch.bfloat16, device=DEV)
-    pv = lambda t: t.view(N, H, W // 2, 2 * t.shape[-1])
-    ops.conv([pv(nhwc(x)) for x in xs], N, H, W // 2, ops.compose_pair_weights(w.to(DEV), srcs), 64, 64, 9, bias=b.repeat(2).to(DEV), relu=True, out=pv(out), pair=True)
-    close(nchw(out), ref, 6e-3, "pixel-pair conv")
-
-
-def test_pixel_pair_mode_equals_the_per_pixel_path():
-    m = pkg.UNet_Nested()
-    m.load_state_dict(O.synth_state_dict(seed=3))
-    m = m.to(DEV).eval()
-    x = torch.randn(2, 3, 64, 96, generator=torch.Generator().manual_seed(1)).to(DEV)
-    with torch.no_grad():
-        a = [h.clone() for h in m(x)]
-        eng = m._engine(x.device)
-        eng.pair_level1, eng._packed_key = not eng.pair_level1, None
-        b = m(x)
-    for u, v in zip(a, b):
-        assert float((u - v).abs().max()) <= 2e-2

@@ -56,7 +56,6 @@ class ConvArgs(C.Structure):
         ("lowres_C", C.c_int32),
         ("bias_classes", C.c_int32),
         ("pooled", C.c_void_p),
-        ("pair_skip", C.c_int32),
     ]
 
 

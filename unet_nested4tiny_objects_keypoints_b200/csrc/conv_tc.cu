@@ -72,7 +72,6 @@ struct ConvTcParams {
   const float* aux_istd;
   int nacc;      // accumulator sets in TMEM (2 or 4): the epilogue of tile i overlaps the MMAs of tiles i+1 .. i+nacc-1
   int b2, b2_P;  // 2x2 output blocking: flag, pixel PAIRS per staged tile row (TW/2 + 2)
-  int pair;      // pixel-pair mode of the classic path (see UnppConvArgs.pair_skip): side taps are half-K, N = 32 MMAs
   int c4;        // with b2: first-layer mode, the one source has 4 channels (8 B pixels, 16 B pair rows, no swizzle); b2_P = TW/2 + 3
   // fused transposed conv (with b2): one extra K chunk per tile read from the low-resolution tensor
   CUtensorMap lowmap;
@@ -581,7 +580,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     mbar_wait(&bar_w, 0);
     const int ncols = p.ncols, nsub = p.nsub, taps = p.taps, k8_total = p.k8_total, nchunk = p.nchunk, nstage = p.nstage;
     const int ntiles = p.ntiles, stage_bytes = p.stage_bytes, dbg = p.dbg, b2 = p.b2, b2_P = p.b2_P, nacc = p.nacc;
-    const int low_on = p.low_on, low_P = p.low_P, low_k8 = p.low_k8, low_w_off = p.low_w_off, c4 = p.c4, pair = p.pair;
+    const int low_on = p.low_on, low_P = p.low_P, low_k8 = p.low_k8, low_w_off = p.low_w_off, c4 = p.c4;
     const uint32_t idesc = make_idesc_bf16(128, ncols), idesc32 = make_idesc_bf16(128, 32), idesc16 = make_idesc_bf16(128, 16);
     const uint32_t w_addr = smem_u32(w_smem);
     const uint32_t stage_addr0 = smem_u32(stage0);
@@ -706,49 +705,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
               }
             }
           };
-          if (pair) {
-            // Pixel-pair mode (1x2 output blocking on the pair view [N,H,W/2,2c] of every tensor): GEMM row = a horizontal pixel
-            // pair, the 64 columns are (pixel of the pair, co), a K chunk = one pair-pixel of a source (first half: left pixel).
-            // The centre tap column is dense; of the pair to the left only its RIGHT pixel reaches the block (and only the left
-            // output pixel), of the pair to the right only its LEFT pixel (-> the right output pixel): those six taps are
-            // half-K, N = 32 MMAs on packed quarter blocks.  Per 256 pixels and 16 input channels: 3 x 48 + 3 x 40 cycles of
-            // operand fetch instead of 2 x 9 x 40 on the per-pixel path.
-            const int hk = kslabs >> 1;
-            const uint64_t bds = make_sdesc(w_addr, 512, 128, 0);  // side blocks: [k8][32 columns][8]
-            const uint32_t bs_hi = uint32_t(bds >> 32);
-            const uint32_t b_centre = uint32_t(bd) - ((uint32_t(wk8 * ncols * 16)) >> 4) + ((uint32_t(wk8) * 1024u) >> 4);
-            const uint32_t b_side = uint32_t(bds) + ((uint32_t(3 * k8_total) * 1024u + uint32_t(wk8 >> 1) * 512u) >> 4);
-            const uint32_t side_blk = (uint32_t(k8_total >> 1) * 512u) >> 4;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              const uint32_t ar = uint32_t(r) * row_step;
-#pragma unroll 4
-              for (int ks = 0; ks < kslabs; ++ks) {  // centre column: all of K, N = 64
-                const uint32_t aok = ar + px_step + uint32_t(ks * 2);
-                const uint64_t bdesc = (uint64_t(b_hi) << 32) | (b_centre + ((uint32_t(r * k8_total) * 1024u + uint32_t(ks) * 2048u) >> 4));
-                const uint32_t accum = (r == 0 && ks == 0) ? first : 1u;
-                if (has0) umma_bf16(acc0, (uint64_t(a_hi) << 32) | (a_lo0 + aok), bdesc, idesc, accum);
-                if (has1) umma_bf16(acc1, (uint64_t(a_hi) << 32) | (a_lo1 + aok), bdesc, idesc, accum);
-                if constexpr (kMmaWarps < 4) {
-                  if (has2) umma_bf16(acc2, (uint64_t(a_hi) << 32) | (a_lo2 + aok), bdesc, idesc, accum);
-                }
-              }
-#pragma unroll
-              for (int side = 0; side < 2; ++side) {  // 0: pair to the left (its right pixel -> left output pixel), 1: pair to the right
-#pragma unroll 2
-                for (int kq = 0; kq < hk; ++kq) {
-                  const uint32_t aok = ar + uint32_t(side ? 2 : 0) * px_step + uint32_t(((side ? 0 : hk) + kq) * 2);
-                  const uint64_t bdesc = (uint64_t(bs_hi) << 32) | (b_side + uint32_t(r * 2 + side) * side_blk + ((uint32_t(kq) * 1024u) >> 4));
-                  const uint32_t dcol = side ? 32u : 0u;
-                  if (has0) umma_bf16(acc0 + dcol, (uint64_t(a_hi) << 32) | (a_lo0 + aok), bdesc, idesc32, 1u);
-                  if (has1) umma_bf16(acc1 + dcol, (uint64_t(a_hi) << 32) | (a_lo1 + aok), bdesc, idesc32, 1u);
-                  if constexpr (kMmaWarps < 4) {
-                    if (has2) umma_bf16(acc2 + dcol, (uint64_t(a_hi) << 32) | (a_lo2 + aok), bdesc, idesc32, 1u);
-                  }
-                }
-              }
-            }
-          } else if (taps == 9) {
+          if (taps == 9) {
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -1033,7 +990,7 @@ EncodeTiledFn get_encode() {
 
 struct Plan {
   int TW, nsub, nstage, stage_bytes, w_bytes, w_smem_bytes, tmem_cols, smem_total, grid_x, grid_y, tiles_x, tiles_y, ntiles;
-  int nchunk, k8_total, b2, b2_P, c4, cw, pair, ncols, nacc, low_on, low_w_off, low_w_bytes;
+  int nchunk, k8_total, b2, b2_P, c4, cw, ncols, nacc, low_on, low_w_off, low_w_bytes;
   int ch_map[kMaxChunks], ch_c0[kMaxChunks], ch_span[kMaxChunks], ch_wk8[kMaxChunks];
 };
 
@@ -1049,7 +1006,7 @@ int make_plan_cw(const UnppConvArgs* a, Plan* pl, int cw);
 int make_plan(const UnppConvArgs* a, Plan* pl) {
   int rc = make_plan_cw(a, pl, 64);
   static const int prefer32 = [] { const char* e = getenv("UNPP_CW32"); return e ? atoi(e) : 1; }();  // 32-channel chunks whenever they give a wider tile (UNPP_CW32=0: only when 64-channel chunks leave < 16 columns)
-  if (a && !a->block2x2 && !a->pair_skip && a->taps == 9 && a->mode == UNPP_MODE_CONV && a->n_tile >= (prefer32 ? 32 : 64) && (rc != UNPP_OK || pl->TW < (prefer32 ? 64 : 16))) {
+  if (a && !a->block2x2 && a->taps == 9 && a->mode == UNPP_MODE_CONV && a->n_tile >= (prefer32 ? 32 : 64) && (rc != UNPP_OK || pl->TW < (prefer32 ? 64 : 16))) {
     bool wide = true;
     for (int i = 0; i < a->nsrc && i < UNPP_MAX_SRC; ++i) wide = wide && a->src_C[i] >= 64;
     Plan alt;
@@ -1138,15 +1095,7 @@ int make_plan_cw(const UnppConvArgs* a, Plan* pl, int cw) {
     return UNPP_OK;
   }
   const int pad = a->taps == 9 ? 1 : 0;
-  pl->pair = 0;
-  if (a->pair_skip) {
-    if (a->taps != 9 || a->mode != UNPP_MODE_CONV || a->n_total != 64 || a->n_tile != 64 || cw != 64 || a->pooled || a->head_w || is_train(a))
-      return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: pair_skip needs a 3x3 conv with n_total = n_tile = 64 and the plain inference epilogue");
-    for (int i = 0; i < a->nsrc; ++i)
-      if ((a->src_C[i] != 32 && a->src_C[i] != 64) || a->src_step[i] == 2) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: pair_skip sources are dense pair views with 32 or 64 channels");
-    pl->pair = 1;
-  }
-  pl->w_bytes = pl->pair ? k8 * 4608 : a->taps * k8 * a->n_tile * 16;  // pair mode: 3 dense centre blocks + 6 quarter blocks
+  pl->w_bytes = a->taps * k8 * a->n_tile * 16;
   pl->w_smem_bytes = (pl->w_bytes + 1023) / 1024 * 1024;
   int TW = 64;
   {
@@ -1240,7 +1189,7 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   p.N = a->N, p.H = a->H, p.W = a->W;
   p.TW = pl.TW, p.nsub = pl.nsub, p.tiles_x = pl.tiles_x, p.tiles_y = pl.tiles_y, p.ntiles = pl.ntiles;
   p.taps = a->taps, p.ncols = pl.ncols, p.k8_total = pl.k8_total;
-  p.b2 = pl.b2, p.b2_P = pl.b2_P, p.c4 = pl.c4, p.pair = pl.pair, p.nacc = pl.nacc;
+  p.b2 = pl.b2, p.b2_P = pl.b2_P, p.c4 = pl.c4, p.nacc = pl.nacc;
   p.bias9 = a->bias_classes == 9;
   p.pooled = reinterpret_cast<__nv_bfloat16*>(a->pooled);
   if (pl.low_on) {

@@ -15,7 +15,6 @@ PyTorch owns all device memory (activation arena, packed weights); this module o
 """
 from __future__ import annotations
 
-import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -94,7 +93,6 @@ class Engine:
         self._arena: Dict[Tuple, Dict[str, torch.Tensor]] = {}
         self._keep: List = []
         self.first_layer_c4 = True  # inference: conv00.conv1 reads a 4-channel NHWC input (8 B/pixel) through the first-layer MMA mode
-        self.pair_level1 = os.environ.get("UNPP_PAIR", "0") == "1"   # (off: measured slower than the per-pixel path) inference: the 32-channel level runs in pixel-pair mode (1x2 output blocking, ops.compose_pair_weights)
         self.fuse_deconv = True  # inference: fold the k2s2 transposed conv of the full-resolution nodes into the consuming conv
 
     # ------------------------------------------------------------------------------ weights
@@ -130,21 +128,11 @@ class Engine:
                         P[f"{name}.c{n}"] = dict(w=ops.pack_weights_c4(conv.weight.detach().float(), scale=scale), bias=bias, n_total=16,
                                                  n_tile=ops.NTile(16, b2=2), c4=True)
                         continue
-                    if name == "conv10" and self.pair_level1:
-                        cin = conv.weight.shape[1]
-                        P[f"{name}.c{n}"] = dict(w=ops.compose_pair_weights(conv.weight, [cin], scale=scale), bias=bias.repeat(2).contiguous(), n_total=64, n_tile=64,
-                                                 pair=True)
-                        continue
                     P[f"{name}.c{n}"] = self._pack_fwd_conv(conv.weight, scale, bias)
             for name in DECODER_ORDER:
                 up = getattr(self.model, name)
                 for n in (1, 2):
                     conv = self._conv_seq(name + ".conv", n)[0]
-                    if DECODER[name][2] == 1 and self.pair_level1:  # 32-channel level: pixel-pair mode, K = [up, lows...] (unet.py:199-201)
-                        nsrc = conv.weight.shape[1] // 32
-                        P[f"{name}.c{n}"] = dict(w=ops.compose_pair_weights(conv.weight, [32] * nsrc), bias=conv.bias.detach().float().repeat(2).contiguous(),
-                                                 n_total=64, n_tile=64, pair=True)
-                        continue
                     P[f"{name}.c{n}"] = self._pack_fwd_conv(conv.weight, None, conv.bias.detach().float().contiguous())
                 if not self.model.is_deconv:
                     # unet.py:189-191: UpsamplingBilinear2d(2) + Conv2d 1x1.  Both are linear and the bilinear weights sum to one,
@@ -234,17 +222,6 @@ class Engine:
         # eval mode (trainer/trainer.py:200-210 runs it under set_grad_enabled(False)): inference kernels, no graph
         return self.forward_eval(x)
 
-    @staticmethod
-    def _conv3x3(srcs, B, h, w, p, out, pooled=None):
-        """3x3 conv + bias + ReLU of packed layer ``p``; layers packed in pixel-pair mode see every tensor as [B,h,w/2,2c]."""
-        if p.get("pair"):
-            pv = lambda t: t.view(B, h, w // 2, 2 * t.shape[-1])
-            ops.conv([pv(t) for t in srcs], B, h, w // 2, p["w"], 64, 64, 9, bias=p["bias"], relu=True, out=pv(out), pair=True)
-            if pooled is not None:
-                ops.maxpool(out, pooled)
-            return
-        ops.conv(srcs, B, h, w, p["w"], p["n_total"], p["n_tile"], 9, bias=p["bias"], relu=True, out=out, pooled=pooled)
-
     def forward_eval(self, x: torch.Tensor, heads: Sequence[int] = (0, 1, 2)):
         """Inference forward (BN folded, dropout off).  Returns the three sigmoid heat maps
         (fp32 NCHW) — ``None`` for heads not requested."""
@@ -263,9 +240,10 @@ class Engine:
         for lvl, name in enumerate(ENCODER):
             h, w = H >> lvl, W >> lvl
             p1, p2 = P[f"{name}.c1"], P[f"{name}.c2"]
-            self._conv3x3([src], B, h, w, p1, A[f"{name}.a"])
-            # MaxPool2d(2) (unet.py:219,258,260,262) is written by the conv's own epilogue (pixel-pair mode: by the pool kernel)
-            self._conv3x3([A[f"{name}.a"]], B, h, w, p2, A[f"X{lvl}0"], pooled=A[f"P{lvl}0"] if lvl < 3 else None)
+            ops.conv([src], B, h, w, p1["w"], p1["n_total"], p1["n_tile"], 9, bias=p1["bias"], relu=True, out=A[f"{name}.a"])
+            # MaxPool2d(2) (unet.py:219,258,260,262) is written by the conv's own epilogue
+            ops.conv([A[f"{name}.a"]], B, h, w, p2["w"], p2["n_total"], p2["n_tile"], 9, bias=p2["bias"], relu=True, out=A[f"X{lvl}0"],
+                     pooled=A[f"P{lvl}0"] if lvl < 3 else None)
             if lvl < 3:
                 src = A[f"P{lvl}0"]
         heats: List[Optional[torch.Tensor]] = [None, None, None]
@@ -284,7 +262,8 @@ class Engine:
                 else:
                     ops.conv([A[high]], B, h // 2, w // 2, pu["w"], pu["n_total"], pu["n_tile"], 1, bias=pu["bias"], out=A[f"V{tag}"])
                     ops.bilinear_up2x(A[f"V{tag}"], A[f"U{tag}"])
-                self._conv3x3([A[f"U{tag}"]] + [A[l] for l in lows], B, h, w, p1, A[f"{name}.a"])
+                ops.conv([A[f"U{tag}"]] + [A[l] for l in lows], B, h, w, p1["w"], p1["n_total"], p1["n_tile"], 9, bias=p1["bias"], relu=True,
+                          out=A[f"{name}.a"])
             head = None
             out = A[f"X{tag}"]
             if name in HEAD_OF:
@@ -297,10 +276,7 @@ class Engine:
                     out = None  # X03 has no consumer besides its head
                     if head is None:
                         continue
-            if p2.get("pair"):
-                self._conv3x3([A[f"{name}.a"]], B, h, w, p2, out)
-            else:
-                ops.conv([A[f"{name}.a"]], B, h, w, p2["w"], p2["n_total"], p2["n_tile"], 9, bias=p2["bias"], relu=True, out=out, head=head)
+            ops.conv([A[f"{name}.a"]], B, h, w, p2["w"], p2["n_total"], p2["n_tile"], 9, bias=p2["bias"], relu=True, out=out, head=head)
         return tuple(heats)
 
     @torch.no_grad()

@@ -160,7 +160,7 @@ def _conv_args(srcs, N, H, W, n_total, n_tile, taps, strided=None, b2=False) -> 
 
 def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Tensor, n_total: int, n_tile: int, taps: int, *, bias=None,
          relu=False, mode=MODE_CONV, out=None, head=None, addend=None, relu_mask_src=None, stats_partial=None, stats_aux=None, aux_mean=None,
-         aux_istd=None, strided=None, b2=False, lowres=None, bias_classes=0, pooled=None, pair=False) -> None:
+         aux_istd=None, strided=None, b2=False, lowres=None, bias_classes=0, pooled=None) -> None:
     """One unpp_conv_tc launch.  ``srcs``: NHWC bf16 tensors (virtual concat along K).
     ``head`` = (w fp32 [cls,16], b fp32 [cls], heat fp32 NCHW, logit|None, drop_mask int16 [N,H,W] keep bits|None, drop_scale).
     ``strided`` = [(oy, ox), ...]: every source is a [N,2H,2W,C] tensor read at (2y+oy, 2x+ox)."""
@@ -177,7 +177,6 @@ def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Te
         a.lowres_src, a.lowres_wpacked, a.lowres_C = lowres[0].data_ptr(), lowres[1].data_ptr(), lowres[0].shape[-1]
     a.bias_classes = bias_classes
     a.pooled = _ptr(pooled)  # fused MaxPool2d(2) of the output (inference epilogue)
-    a.pair_skip = int(pair)  # pixel-pair mode: tensors are pair views [N,H,W/2,2c], weights from compose_pair_weights()
     a.addend, a.relu_mask_src = _ptr(addend), _ptr(relu_mask_src)
     a.stats_partial, a.stats_aux, a.aux_mean, a.aux_istd = _ptr(stats_partial), _ptr(stats_aux), _ptr(aux_mean), _ptr(aux_istd)
     _count()
@@ -201,12 +200,9 @@ def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Te
         if extra is not None:
             nbytes += extra.numel() * 2
     flops = 2 * px * k_total * n_total * taps
-    if pair:
-        flops //= 2  # the pair view doubles K and N for half as many GEMM rows: count the arithmetic of the real 3x3 conv
     if lowres is not None:  # count the unfused arithmetic it replaces: the k2s2 transposed conv + its 3x3 taps
         flops += 2 * px * lowres[0].shape[-1] * n_total + 2 * px * n_total * n_total * taps
-    label = "conv_tc %s taps%d K%d N%d %dx%d" % ("deconv" if mode == MODE_DECONV else ("conv2x2" if a.block2x2 else "conv1x2" if pair else "conv"), taps,
-                                                  k_total // 2 if pair else k_total, n_total // 2 if pair else n_total, H, 2 * W if pair else W)
+    label = "conv_tc %s taps%d K%d N%d %dx%d" % ("deconv" if mode == MODE_DECONV else ("conv2x2" if a.block2x2 else "conv"), taps, k_total, n_total, H, W)
     flags = [n for n, v in (("st", stats_partial), ("aux", stats_aux), ("mask", relu_mask_src), ("add", addend), ("head", head), ("s2", strided), ("low", lowres)) if v is not None]
     if flags:
         label += " +" + "+".join(flags)
@@ -502,43 +498,3 @@ def optim_step(kind: str, p, g, state1, state2, *, lr, beta1=0.0, beta2=0.0, eps
     with _Traced("optim_step " + kind, 0, 0):
         _lib.check(lib().unpp_optim_step(p.data_ptr(), g.data_ptr(), _ptr(state1), _ptr(state2), p.numel(), C.byref(a), int(step), _ptr(step_counter),
                                          _ptr(lr_dev), _ptr(scalars), _stream()), "unpp_optim_step")
-
-
-def compose_pair_weights(w: torch.Tensor, src_channels: Sequence[int], scale: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Packed bf16 weights of a 3x3 conv in pixel-pair mode (conv(..., pair=True); layout in unpp.h, UnppConvArgs.pair_skip).
-
-    w [Co=32, sum(src_channels), 3, 3] fp32 (the K axis is the virtual concat of the sources, models/unet.py:199-201); on the pair
-    view a GEMM column is (output pixel po of the pair, co) and a K index (source j, input pixel pi of the pair, ci); the pair at
-    offset d in {-1, 0, +1} contributes through the original tap column s = 2d + pi - po + 1 when 0 <= s <= 2."""
-    w = w.detach().float()
-    if scale is not None:
-        w = w * scale.view(-1, 1, 1, 1)
-    co, dev = w.shape[0], w.device
-    assert co == 32 and w.shape[1] == sum(src_channels) and all(c % 16 == 0 for c in src_channels)
-    kp = 2 * sum(src_channels)
-    wp = torch.zeros(2 * co, kp, 3, 3, dtype=torch.float32, device=dev)  # [(po, co), (j, pi, ci), r, d + 1]
-    left_k, right_k = [], []
-    kb = cb = 0
-    for c in src_channels:
-        for pi in range(2):
-            ks = slice(kb + pi * c, kb + (pi + 1) * c)
-            (left_k if pi == 0 else right_k).extend(range(ks.start, ks.stop))
-            for po in range(2):
-                for d in (-1, 0, 1):
-                    sft = 2 * d + pi - po + 1
-                    if 0 <= sft <= 2:
-                        wp[po * co:(po + 1) * co, ks, :, d + 1] = w[:, cb:cb + c, :, sft]
-        kb += 2 * c
-        cb += c
-    wp = wp.to(torch.bfloat16)
-
-    def block(m):  # [n, k] -> UMMA K-major operand [k/8][n][8]
-        n, k = m.shape
-        return m.reshape(n, k // 8, 8).permute(1, 0, 2).reshape(-1)
-
-    right_k, left_k = torch.tensor(right_k, device=dev), torch.tensor(left_k, device=dev)
-    parts = [block(wp[:, :, r, 1]) for r in range(3)]
-    for r in range(3):
-        parts.append(block(wp[:co, right_k, r, 0]))   # pair to the left: its right pixel -> left output pixel
-        parts.append(block(wp[co:, left_k, r, 2]))    # pair to the right: its left pixel -> right output pixel
-    return torch.cat(parts).contiguous()
