@@ -627,7 +627,9 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
                 const uint64_t bdesc = (uint64_t(b_hi) << 32) | (b_ks + (uint32_t(blk.cum * b2::kUnitBytes) >> 4) + (nb << 20));  // LBO = 16 * nblk * 16 B
                 const uint32_t idn = nb == 4 ? idesc : nb == 2 ? idesc32 : idesc16, dcol = uint32_t(blk.b0 * 16);
                 if (has0) umma_bf16(acc0 + dcol, (uint64_t(a_hi) << 32) | (a_lo0 + ao), bdesc, idn, 1u);
-                if (has1) umma_bf16(acc1 + dcol, (uint64_t(a_hi) << 32) | (a_lo1 + ao), bdesc, idn, 1u);
+                if constexpr (kMmaWarps < 4) {  // (b2 tiles have at most four sub-tiles: with four issuers nobody owns a second one)
+                  if (has1) umma_bf16(acc1 + dcol, (uint64_t(a_hi) << 32) | (a_lo1 + ao), bdesc, idn, 1u);
+                }
               }
             }
           }
@@ -651,7 +653,9 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
                 const uint64_t bdesc = (uint64_t(b_hi) << 32) | (b_lo + uint32_t((dy * 4096 + hf * 2048) >> 4));
                 const uint32_t accum = (dy | hf) ? 1u : 0u;
                 if (has0) umma_bf16(acc0, (uint64_t(a_hi) << 32) | (a_lo0 + ao), bdesc, idesc, accum);
-                if (has1) umma_bf16(acc1, (uint64_t(a_hi) << 32) | (a_lo1 + ao), bdesc, idesc, accum);
+                if constexpr (kMmaWarps < 4) {
+                  if (has1) umma_bf16(acc1, (uint64_t(a_hi) << 32) | (a_lo1 + ao), bdesc, idesc, accum);
+                }
               }
             }
           }
@@ -676,7 +680,9 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
               const uint32_t idn = nb == 4 ? idesc : nb == 2 ? idesc32 : idesc16, dcol = uint32_t(blk.b0 * 16);
               const uint32_t accum = i ? 1u : first;
               if (has0) umma_bf16(acc0 + dcol, (uint64_t(a_hi) << 32) | (a_lo0 + ao), bdesc, idn, accum);
-              if (has1) umma_bf16(acc1 + dcol, (uint64_t(a_hi) << 32) | (a_lo1 + ao), bdesc, idn, accum);
+              if constexpr (kMmaWarps < 4) {
+                if (has1) umma_bf16(acc1 + dcol, (uint64_t(a_hi) << 32) | (a_lo1 + ao), bdesc, idn, accum);
+              }
             }
           }
         } else if (elect_one() && !(dbg & 2)) {
@@ -692,6 +698,15 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
           const uint32_t acc0 = acc + uint32_t(mw * ncols), acc1 = acc + uint32_t((mw + kMmaWarps) * ncols),
                          acc2 = acc + uint32_t((mw + 2 * kMmaWarps) * ncols);
           const uint32_t first = c ? 1u : 0u;
+          // every MMA costs its issuing thread a handful of uniform-datapath instructions per (predicated) slot: when no issuer owns a
+          // second sub-tile (nsub <= issuers: the deep levels) the loop is issued without the dead slots
+          auto issue_tap1 = [&](uint32_t ao, uint32_t bo, bool first_tap) {
+#pragma unroll 4
+            for (int ks = 0; ks < kslabs; ++ks) {
+              const uint64_t bdesc = (uint64_t(b_hi) << 32) | (b_lo + bo + uint32_t(ks) * b_ks_step);
+              if (has0) umma_bf16(acc0, (uint64_t(a_hi) << 32) | (a_lo0 + ao + uint32_t(ks * 2)), bdesc, idesc, (first_tap && ks == 0) ? first : 1u);
+            }
+          };
           auto issue_tap = [&](uint32_t ao, uint32_t bo, bool first_tap) {
 #pragma unroll 4
             for (int ks = 0; ks < kslabs; ++ks) {
@@ -705,7 +720,13 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
               }
             }
           };
-          if (taps == 9) {
+          if (taps == 9 && nsub <= kMmaWarps) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+              for (int sft = 0; sft < 3; ++sft) issue_tap1(uint32_t(r) * row_step + uint32_t(sft) * px_step, uint32_t(r * 3 + sft) * b_tap_step, (r | sft) == 0);
+            }
+          } else if (taps == 9) {
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
 #pragma unroll
