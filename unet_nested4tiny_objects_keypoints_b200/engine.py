@@ -1,14 +1,18 @@
 """Host-side engine: drives libunpp.so (C ABI, include/unpp.h) for one UNet_Nested on one device.
 
 The reference executes ``UNet_Nested.forward`` (models/unet.py:255-300) as ~80 ATen/cuDNN launches
-on NCHW fp32 tensors.  Here the same DAG runs as 27 launches of hand-written sm_100a kernels on
+on NCHW fp32 tensors.  Here the same DAG runs as 25 launches of hand-written sm_100a kernels on
 NHWC bf16 tensors with fp32 accumulation:
 
+  * the fp32 NCHW input becomes a 4-channel NHWC bf16 tensor (8 B/pixel) that the first conv reads through the
+    first-layer MMA mode of ``unpp_conv_tc`` (include/unpp.h, block2x2 = 2);
   * every 3x3 conv (+bias / folded BatchNorm, + ReLU) is one ``unpp_conv_tc`` call whose K loop walks
     the list of source tensors, so ``torch.cat`` (unet.py:199-201) is never materialised;
   * ``ConvTranspose2d(k2,s2)`` (unet.py:187) is a pointwise tensor-core GEMM with a scatter epilogue;
   * the 1x1 heads + sigmoid (unet.py:242-244,283-286) ride in the epilogue of the node's second conv;
-  * eval-mode BatchNorm (unet.py:133) is folded into the packed bf16 weights and the fp32 bias.
+  * eval-mode BatchNorm (unet.py:133) is folded into the packed bf16 weights and the fp32 bias;
+  * ``is_deconv=False`` (unet.py:189-191): the 1x1 conv of the bilinear branch runs on the low-resolution tensor (pointwise
+    tensor-core GEMM), ``unpp_bilinear_up2x`` upsamples its output; ``is_batchnorm=False``: nothing to fold.
 
 PyTorch owns all device memory (activation arena, packed weights); this module only passes
 ``data_ptr()``s and the current CUDA stream across the C ABI.  There is no fallback path.
