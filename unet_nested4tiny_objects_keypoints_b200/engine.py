@@ -24,7 +24,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
-from .ops import MODE_CONV, MODE_DECONV, pick_n_tile
+from .ops import MODE_DECONV, pick_n_tile
 
 ENCODER = ("conv00", "conv10", "conv20", "conv30")
 # name -> (high-resolution source node, low sources in concat order, level)   (unet.py:268-277)

@@ -17,7 +17,7 @@ per-rank like ``nn.DataParallel`` (trainer.py:338) keeps them per replica.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 

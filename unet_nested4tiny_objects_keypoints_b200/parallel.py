@@ -10,7 +10,7 @@ gloo in the CPU tests); there is no data-path collective in inference.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 import torch.distributed as dist
