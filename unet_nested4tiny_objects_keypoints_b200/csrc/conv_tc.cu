@@ -37,10 +37,10 @@ constexpr int kEpiWarps = 8;
 // Issuing threads: each owns the sub-tile accumulators j = i, i+n, i+2n (disjoint TMEM columns).  The inference
 // variants (<= 108 registers) run four of them (416 threads); the training variants need up to 168 registers
 // and run three (384 threads).
-#ifndef UNPP_TRAIN_ISSUERS
-#define UNPP_TRAIN_ISSUERS 3  // 4: a fourth issuing thread for the training variants, registers capped at 152 by __maxnreg__ (13 warps x 152 fit)
-#endif
-constexpr int mma_warps(bool train) { return train ? UNPP_TRAIN_ISSUERS : 4; }
+// (A fourth issuer for the training variants does not pay: registers are allocated for a multiple of four warps, so a 13-warp
+// CTA is limited to 128 registers per thread whatever __maxnreg__ says — 152 or 144 fail to launch — and at 128 the training
+// epilogue spills ~600 bytes per thread: 3.51 -> 3.95 ms per step.)
+constexpr int mma_warps(bool train) { return train ? 3 : 4; }
 constexpr int block_threads(bool train) { return 64 + 32 * kEpiWarps + 32 * (mma_warps(train) - 1); }
 
 struct ConvTcParams {
@@ -446,11 +446,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, const uint32_t (&ra
 }
 
 template <bool DECONV, bool HEAD, bool TRAIN>
-#if UNPP_TRAIN_ISSUERS == 4
-__global__ void __maxnreg__(TRAIN ? 152 : 128) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-#else
 __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-#endif
   constexpr int kMmaWarps = mma_warps(TRAIN), kThreads = block_threads(TRAIN);
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_acc_full[4], bar_acc_empty[4], bar_w;
