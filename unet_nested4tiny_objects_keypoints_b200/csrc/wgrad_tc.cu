@@ -90,7 +90,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   __shared__ uint32_t tmem_slot;
   uint8_t* const zring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* const xring = zring + p.nz * p.zslot;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (the shuffle tells the compiler that the warp index is warp-uniform: the issuing threads' descriptor arithmetic then stays in
+  // uniform registers instead of one R2UR per MMA — the line where ncu showed their stalls; launch times did not change, though:
+  // the kernel is bound by the MN-major operand fetch / HBM, not by the issue rate)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int job = blockIdx.y;
   const int ch0 = p.job_ch0[job], nch = p.job_nch[job], co0 = p.job_co0[job];
 
@@ -182,8 +185,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
               const uint32_t a_mi = a_lo + (dc ? 0u : (uint32_t(mi * 2 * span) >> 4));  // 3x3, second MMA: the row shifted by two more pixels
               const uint32_t b_mi = b_lo + (dc ? uint32_t(mi) * zbox16 : 0u);           // transposed conv: the dZ box of q = mi
               uint32_t accum = tile_it ? 1u : 0u;
-              for (int row = h; row < TR; row += nsplit) {
-                const uint32_t ar = a_mi + uint32_t(row) * x_row, br = b_mi + uint32_t(row) * z_row;
+              uint32_t ar = a_mi + uint32_t(h) * x_row, br = b_mi + uint32_t(h) * z_row;
+              const uint32_t a_step = uint32_t(nsplit) * x_row, b_step = uint32_t(nsplit) * z_row;
+#pragma unroll 4
+              for (int row = h; row < TR; row += nsplit, ar += a_step, br += b_step) {
 #pragma unroll
                 for (int seg = 0; seg < TW / 16; ++seg) {
                   umma_bf16(acc, (uint64_t(a_hi) << 32) | (ar + uint32_t(seg) * x_seg), (uint64_t(b_hi) << 32) | (br + uint32_t(seg) * z_seg), idesc,
