@@ -402,9 +402,14 @@ def _main(out):
     if rank == 0:
         if world == 1 and not args.no_extra:
             train = args.workload == "train"
-            ips, ms_cpu, cores = cpu_reference(3, 1, 2 if train else 4, train)
+            # ~10 s of host work: 150 four-image inference batches (or 25 two-image training steps) of the same workload
+            nb, bs = (25, 2) if train else (150, 4)
+            ips, ms_cpu, cores = cpu_reference(nb, 2, bs, train)
             line["cpu_baseline"] = {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port",
-                                    "sample": f"{2 if train else 4}-image batches of the same workload, 1 warm-up + 3 timed, oracle/unetpp_oracle.py on torch-CPU fp32"}
+                                    "sample": f"{bs}-image batches of the same workload, 2 warm-up + {nb} timed, oracle/unetpp_oracle.py on torch-CPU fp32"}
+            if not train:  # BASELINE.json configs[0]: the reference's own CPU-runnable case, batch 1 (3 warm-up + 10 timed)
+                ips1, ms1, _ = cpu_reference(10, 3, 1, False)
+                line["cpu_baseline"]["configs0_batch1_images_per_s"] = round(ips1, 3)
         else:
             line["cpu_baseline"] = None
         if extra is not None:
