@@ -409,7 +409,8 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
         if True:
             ops.head_bwd(ts.heats[k], dh, target if dh is None else None, coef, t[f"X{name[-2:]}"], t[f"mask{k}"] if ts.use_masks else None,
                          ts.drop_scale, hm.weight.view(ncls, -1), t[f"dXh{k}"], part, loss_kind=loss_kind, gamma=gamma)
-            ops.reduce_partials(part, ts.head_grid, ts.head_nacc, ts.head_nacc, t["head_red"][k])
+            with _on_side():  # (only the optimizer and the loss read-out consume it)
+                ops.reduce_partials(part, ts.head_grid, ts.head_nacc, ts.head_nacc, t["head_red"][k])
         ops.reduce_partials(t["head_red"], 1, 0, ncls * 16, G, out_offset=goff(hname + ".weight"), partial_offset=k * ts.head_nacc, defer=True)
         ops.reduce_partials(t["head_red"], 1, 0, ncls, G, out_offset=goff(hname + ".bias"), partial_offset=k * ts.head_nacc + ncls * 16, defer=True)
 
