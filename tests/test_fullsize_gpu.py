@@ -18,7 +18,8 @@ pytestmark = pytest.mark.gpu
 import unet_nested4tiny_objects_keypoints_b200 as pkg  # noqa: E402
 from unet_nested4tiny_objects_keypoints_b200 import fused, ops  # noqa: E402
 from oracle import unetpp_oracle as O  # noqa: E402
-from test_training_gpu import check_grads  # noqa: E402
+from oracle import teacher_forced as T  # noqa: E402
+from test_training_gpu import check_grads, stored_tensors  # noqa: E402
 
 
 def _model(seed, train=False):
@@ -72,6 +73,15 @@ def test_full_size_training_step_properties():
         return float(loss.detach()), {k: p.grad.clone() for k, p in m.named_parameters()}, m
 
     loss1, g1, m1 = grads_for(1.0)
+    # teacher-forced parity at the full size (oracle/teacher_forced.py, fp64 on the GPU): every stored tensor of THIS step to
+    # one bf16 ulp, every one of the 74 parameter gradients to 1e-3
+    t, heats = stored_tensors(m1, B, S, S)
+    rep = T.verify_step(t, heats, g1, sd, x.cuda(), target=target)
+    assert not rep.check(), rep.check()
+    wb, wf = rep.worst("bf16"), rep.worst("f32")
+    print(f"teacher-forced B={B} {S}x{S}: worst bf16 tensor {wb['name']} {wb['max_rel']:.2e} (> 1 ulp: {wb['frac_gt_ulp']:.1e}); worst fp32 {wf['name']} {wf['max_rel']:.2e}")
+    del rep, t, heats
+    torch.cuda.empty_cache()
     loss1b, g1b, _ = grads_for(1.0)
     assert loss1 == loss1b
     for k in g1:  # determinism: fixed-order reductions everywhere

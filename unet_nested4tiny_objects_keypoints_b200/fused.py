@@ -172,14 +172,14 @@ class FusedTrainStep:
         else:
             self.hyper = dict(lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, weight_decay=weight_decay, final_lr=final_lr, gamma=bound_gamma, base_lr=lr)
         self.pg = process_group
-        self.world = 1
+        self.world, self.rank = 1, 0
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.world = torch.distributed.get_world_size(process_group)
+            self.world, self.rank = torch.distributed.get_world_size(process_group), torch.distributed.get_rank(process_group)
         self.ts = TrainState(self.eng, B, H, W)
         ts = self.ts
         p_drop = float(model.drop_out.p)
         ts.use_masks, ts.drop_scale = p_drop > 0.0, (1.0 / (1.0 - p_drop) if p_drop > 0 else 1.0)
-        self.p_drop, self.seed = p_drop, seed
+        self.p_drop, self.seed = p_drop, seed + self.rank  # every replica draws its own dropout masks (nn.DataParallel: one RNG stream per device)
         # flat fp32 parameter storage: every nn.Parameter becomes a view into one buffer (state_dict unchanged)
         lay, n = flat_layout(model)
         self.flat_p = torch.empty(n, dtype=torch.float32, device=self.dev)
