@@ -301,7 +301,8 @@ def bench_train(args, rank, world, local):
     if world > 1:
         fused.broadcast_parameters(model)
     b = TRAIN_B1 if world == 1 else TRAIN_GLOBAL // world
-    step = fused.FusedTrainStep(model, b, S, S, device=dev, seed=rank)
+    loss = getattr(args, "loss", "mse")  # BASELINE.json configs[2]/[3] name the MSE heat-map loss; "focal" = the trainer's shipped criterion
+    step = fused.FusedTrainStep(model, b, S, S, device=dev, seed=0, loss=loss)
     g = torch.Generator().manual_seed(99 + rank)
     x_host = torch.randn(b, 3, S, S, generator=g).pin_memory()
     t_host = torch.rand(b, 4, S, S, generator=g).pin_memory()

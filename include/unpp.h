@@ -160,6 +160,12 @@ int unpp_maxpool2x2(const void* x, void* out, int N, int H, int W, int C, unpp_s
 /* Per-plane arg-max of fp32 NCHW heatmaps: first maximum in row-major order -> xy[b][c] = {x, y},
  * val[b][c] = the maximum (val may be NULL). One CTA per plane, warp-shuffle reduction. */
 int unpp_argmax_peaks(const float* heat, int planes, int H, int W, int32_t* xy, float* val, unpp_stream_t stream);
+/* The same result (bit-identical: (value, first index) is a total order) for few, large planes — 1024x1024 at batch 16 is 64
+ * planes of 4 MB: every plane is cut into `splits` segments, one CTA each, and a second launch folds the per-segment pairs.
+ * workspace: planes * splits * 8 bytes of device memory owned by the caller; unpp_argmax_splits() proposes the split count
+ * (1 = one CTA per plane already fills the GPU; then the call is unpp_argmax_peaks and workspace may be NULL). */
+int unpp_argmax_peaks_split(const float* heat, int planes, int H, int W, int32_t* xy, float* val, void* workspace, int splits, unpp_stream_t stream);
+int unpp_argmax_splits(int planes, int H, int W);
 
 /* ---------------------------------------------------------------------------------------------
  * Training step.  Reference counterparts: autograd of models/unet.py:255-300 (cuDNN dgrad/wgrad,

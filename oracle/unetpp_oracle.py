@@ -319,8 +319,8 @@ def argmax_keypoints(heat: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
 
 def create_heatmap(target: np.ndarray, image_height: int, image_width: int) -> np.ndarray:
     """helper.create_heatmap (helper.py:87-172): 7 keypoints -> 4 channels, groups {0},{1,2,3},{4},{5,6};
-    per point ``exp(-0.5 * dist / 3)`` with dist the Euclidean DISTANCE (not squared); multi-point
-    channels are summed then divided by their max."""
+    per point ``exp(-0.5 * dist / 3)`` with dist the Euclidean DISTANCE (not squared); channels 1 and 3
+    are summed then divided by their max (also when channel 3 holds a single point, i.e. 6 key points)."""
     target = np.asarray(target, dtype=np.float64)
     N, C, _ = target.shape
     out = np.zeros((N, 4, image_height, image_width), dtype=np.float32)
@@ -333,12 +333,12 @@ def create_heatmap(target: np.ndarray, image_height: int, image_width: int) -> n
             for pt in pts:
                 d = np.sqrt((xs - target[n, pt, 0]) ** 2 + (ys - target[n, pt, 1]) ** 2)
                 g = np.exp(-0.5 * d / 3)
-                if len(pts) == 1:
+                if ch in (0, 2):
                     acc = g.astype(np.float32)  # helper.py:106,142: plain assignment
                 else:
                     acc = acc + g  # helper.py:122,158: float32 += float64 -> float32
                     acc = acc.astype(np.float32)
-            if len(pts) > 1:
-                acc = acc / np.max(acc)  # helper.py:123,159
+            if ch in (1, 3):
+                acc = acc / np.max(acc)  # helper.py:123,159: planes 1 and 3 are always divided by their maximum
             out[n, ch] = acc
     return out

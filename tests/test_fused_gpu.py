@@ -44,7 +44,7 @@ def test_fused_train_step_loss_grads_and_adamw_update(use_graph):
     m.drop_out.p = 0.0
     B, H, W = 2, 32, 32
     hyper = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
-    step = fused.FusedTrainStep(m, B, H, W, use_graph=use_graph, **hyper)
+    step = fused.FusedTrainStep(m, B, H, W, use_graph=use_graph, loss="mse", **hyper)
     # construction (warm-up + capture) must leave weights, buffers and optimizer state untouched
     for k, v in m.state_dict().items():
         assert torch.equal(v.cpu(), sd[k]), k
@@ -133,7 +133,7 @@ def test_fused_train_step_from_keypoints_builds_targets_on_the_device():
     m = m.cuda().train()
     m.drop_out.p = 0.0
     B, H, W = 2, 32, 32
-    step = fused.FusedTrainStep(m, B, H, W)
+    step = fused.FusedTrainStep(m, B, H, W, loss="mse")
     g = torch.Generator().manual_seed(9)
     x = torch.randn(B, 3, H, W, generator=g)
     kp = (torch.rand(B, 7, 2, generator=g) * 28 + 2).float()

@@ -1,0 +1,172 @@
+"""GPU: the cases where the reference (plain autograd / cuDNN) is robust by construction and a cached, raw-pointer engine
+must be made so — interleaved forwards, weights that change under a captured graph, optimizers that write through raw
+pointers, replicas, a current device other than the module's."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import unet_nested4tiny_objects_keypoints_b200 as pkg  # noqa: E402
+from unet_nested4tiny_objects_keypoints_b200 import fused, ops, optimizers  # noqa: E402
+from oracle import unetpp_oracle as O  # noqa: E402
+
+
+def _model(seed, train, dev="cuda"):
+    m = pkg.UNet_Nested()
+    m.load_state_dict(O.synth_state_dict(seed=seed))
+    m = m.to(dev)
+    return m.train() if train else m.eval()
+
+
+def test_two_forwards_before_one_backward_like_autograd():
+    """o1 = model(x1); o2 = model(x2); (l1 + l2).backward(): every forward keeps its own saved activations."""
+    g = torch.Generator().manual_seed(3)
+    x1, x2 = torch.randn(2, 3, 32, 32, generator=g).cuda(), torch.randn(2, 3, 32, 32, generator=g).cuda()
+    t = torch.rand(2, 4, 32, 32, generator=g).cuda()
+
+    def loss_of(m, x):
+        return sum(F.mse_loss(o, t) for o in m(x)) / 3
+
+    m = _model(61, True)
+    m.drop_out.p = 0.0
+    (loss_of(m, x1) + loss_of(m, x2)).backward()
+    both = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone()
+    sep = []
+    for x in (x1, x2):
+        ms = _model(61, True)
+        ms.drop_out.p = 0.0
+        loss_of(ms, x).backward()
+        sep.append(torch.cat([p.grad.reshape(-1) for p in ms.parameters()]))
+    assert torch.equal(both, sep[0] + sep[1])
+    # running statistics saw both batches, in order
+    ms = _model(61, True)
+    ms.drop_out.p = 0.0
+    with torch.no_grad():
+        ms(x1), ms(x2)
+    for (k, a), b in zip(m.state_dict().items(), ms.state_dict().values()):
+        assert torch.equal(a, b), k
+
+
+def test_backward_after_the_activations_were_overwritten_raises():
+    m = _model(62, True)
+    x = torch.randn(1, 3, 32, 32).cuda()
+    out = m(x)
+    out[0].sum().backward(retain_graph=True)
+    m(x)  # same shape: the state is free again (its backward ran) and is reused
+    with pytest.raises(RuntimeError, match="overwritten"):
+        out[0].sum().backward()
+
+
+def test_inference_session_follows_weight_changes_and_survives_arena_eviction():
+    m = _model(63, False)
+    x = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(1))
+    sess = fused.InferenceSession(m, 2, 32, 32, head=2)
+    sess.run(x.pin_memory())
+    torch.cuda.synchronize()
+    assert float((sess.heat.cpu() - O.forward(O.synth_state_dict(seed=63), x)[2]).abs().max()) <= 3e-2
+    # five other shapes evict this shape's arena from the engine's cache; the session keeps its own alive
+    with torch.no_grad():
+        for s in (16, 24, 40, 48, 56):
+            m(torch.randn(1, 3, s, s).cuda())
+    first = sess.heat.clone()
+    sess.run(x.pin_memory())
+    torch.cuda.synchronize()
+    assert torch.equal(sess.heat, first)
+    # new weights under the captured graph: the next run re-folds and re-captures
+    sd2 = O.synth_state_dict(seed=64)
+    m.load_state_dict(sd2)
+    sess.run(x.pin_memory())
+    torch.cuda.synchronize()
+    assert float((sess.heat.cpu() - O.forward(sd2, x)[2]).abs().max()) <= 3e-2
+    assert not torch.equal(sess.heat, first)
+
+
+@pytest.mark.parametrize("opt", ["adamw", "sgdw", "adabound"])
+def test_eval_after_a_dropin_optimizer_step_uses_the_new_weights(opt):
+    """The drop-in optimizers write through raw pointers; the eval-mode fold cache is keyed on tensor versions."""
+    m = _model(65, False)
+    x = torch.randn(1, 3, 32, 32, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        before = m(x.cuda())[2].clone()
+    o = {"adamw": lambda: optimizers.AdamW(m.parameters(), lr=5e-2, weight_decay=1e-2), "sgdw": lambda: optimizers.SGDW(m.parameters(), lr=0.1, weight_decay=0.2),
+         "adabound": lambda: optimizers.AdaBound(m.parameters(), lr=5e-2)}[opt]()
+    for p in m.parameters():
+        p.grad = torch.ones_like(p) * 0.1
+    o.step()
+    with torch.no_grad():
+        after = m(x.cuda())[2]
+    ref = O.forward({k: v.cpu() for k, v in m.state_dict().items()}, x)[2]
+    assert float((after.cpu() - ref).abs().max()) <= 3e-2
+    assert float((after - before).abs().max()) > 1e-3
+
+
+def test_eval_after_a_fused_train_step_uses_the_new_weights_and_statistics():
+    m = _model(66, True)
+    step = fused.FusedTrainStep(m, 2, 32, 32, lr=1e-2, loss="mse")
+    g = torch.Generator().manual_seed(4)
+    x, t = torch.randn(2, 3, 32, 32, generator=g), torch.rand(2, 4, 32, 32, generator=g)
+    m.eval()
+    with torch.no_grad():
+        before = m(x.cuda())[2].clone()
+    m.train()
+    step.step(x.pin_memory(), t.pin_memory())
+    m.eval()
+    with torch.no_grad():
+        after = m(x.cuda())[2]
+    ref = O.forward({k: v.cpu() for k, v in m.state_dict().items()}, x)[2]
+    assert float((after.cpu() - ref).abs().max()) <= 3e-2 and not torch.equal(after, before)
+
+
+def test_create_heatmap_with_six_points_normalises_plane_three():
+    """helper.py:148-159: planes 1 and 3 are ALWAYS divided by their maximum, also when plane 3 holds one point."""
+    kp = (torch.rand(3, 6, 2, generator=torch.Generator().manual_seed(6)) * 30 + 1.3).float()
+    got = ops.create_heatmap(kp.cuda(), 32, 40).cpu().numpy()
+    ref = O.create_heatmap(kp.numpy(), 32, 40)
+    assert np.abs(got - ref).max() <= 2e-6
+    assert np.allclose(got[:, 3].reshape(3, -1).max(1), 1.0) and got[:, 2].max() < 1.0
+
+
+@pytest.mark.parametrize("planes,H,W", [(3, 1024, 1024), (8, 512, 768), (64, 1024, 1024), (5, 250, 250)])
+def test_split_argmax_is_bit_identical_to_numpy(planes, H, W):
+    g = torch.Generator().manual_seed(planes)
+    heat = torch.rand(1, planes, H, W, generator=g)
+    heat[0, 0] = 0.5                       # a constant plane: the first index wins
+    heat[0, 1, H - 1, W - 1] = 2.0         # maximum in the very last element (last segment)
+    if planes > 2:
+        heat[0, 2, 7, 9] = heat[0, 2, H // 2, 3] = 3.0  # a tie across segments: the smaller index wins
+    assert ops.lib().unpp_argmax_splits(planes, H, W) > 1 or planes * H * W < 1 << 20
+    xy, val = ops.argmax_peaks(heat.cuda())
+    rxy, rval = O.argmax_keypoints(heat.numpy())
+    assert np.array_equal(xy.cpu().numpy(), rxy) and np.array_equal(val.cpu().numpy(), rval)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_module_on_device_one_while_the_current_device_is_zero():
+    torch.cuda.set_device(0)
+    sd = O.synth_state_dict(seed=67)
+    m = _model(67, False, "cuda:1")
+    x = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        out = m(x.to("cuda:1"))[2]
+    xy, val, _ = m.predict_keypoints(x.to("cuda:1"))
+    torch.cuda.synchronize(1)
+    assert out.device.index == 1 and float((out.cpu() - O.forward(sd, x)[2]).abs().max()) <= 3e-2
+    assert np.array_equal(xy.cpu().numpy(), O.argmax_keypoints(out.cpu().numpy())[0])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_dataparallel_eval_sees_a_load_state_dict_between_two_forwards():
+    """Replicas are fresh broadcast copies (version 0, recycled addresses): they must never be served cached folded weights."""
+    m = _model(68, False)
+    dp = torch.nn.DataParallel(m, device_ids=[0, 1])
+    x = torch.randn(4, 3, 32, 32, generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        a = dp(x.cuda())[2].cpu()
+    assert float((a - O.forward(O.synth_state_dict(seed=68), x)[2]).abs().max()) <= 3e-2
+    sd2 = O.synth_state_dict(seed=69)
+    m.load_state_dict(sd2)
+    with torch.no_grad():
+        b = dp(x.cuda())[2].cpu()
+    assert float((b - O.forward(sd2, x)[2]).abs().max()) <= 3e-2

@@ -322,7 +322,7 @@ def test_fused_train_step_on_variants(tag):
     B, H, W = 2, 32, 32
     m, sd = make(tag, seed=43, train=True)
     m.drop_out.p = 0.0
-    step = fused.FusedTrainStep(m, B, H, W)
+    step = fused.FusedTrainStep(m, B, H, W, loss="mse")
     g = torch.Generator().manual_seed(9)
     x, target = torch.randn(B, 3, H, W, generator=g), torch.rand(B, 4, H, W, generator=g)
     loss = step.step(x, target)

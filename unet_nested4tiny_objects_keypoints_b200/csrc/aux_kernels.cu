@@ -288,11 +288,88 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ h
   }
 }
 
+// The same arg-max for few, large planes (1024x1024 at batch 16 = 64 planes of 4 MB: one CTA per plane leaves 84 SMs idle and
+// streams at 0.8 TB/s): every plane is cut into `splits` contiguous segments, one CTA each, writing its (value, index) pair;
+// a second launch folds the pairs of a plane.  (value desc, index asc) is a strict total order, so the result does not depend
+// on the split count or on the folding order: bit-identical to the one-CTA kernel.
+__global__ void __launch_bounds__(256) argmax_split_kernel(const float* __restrict__ heat, int HW, int seg, float* __restrict__ pval, int* __restrict__ pidx) {
+  unpp::pdl_wait();
+  unpp::pdl_trigger();
+  const int plane = blockIdx.y, s = blockIdx.x;
+  const float* h = heat + size_t(plane) * HW;
+  const int b = s * seg, e = min(b + seg, HW);  // seg % 4 == 0
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  if ((HW & 3) == 0 && (reinterpret_cast<uintptr_t>(h) & 15) == 0) {
+    const float4* h4 = reinterpret_cast<const float4*>(h);
+    int i = b / 4 + threadIdx.x;
+    const int e4 = e / 4;
+    for (; i + 3 * 256 < e4; i += 4 * 256) {  // four 16-byte loads in flight per thread
+      const float4 v0 = __ldg(h4 + i), v1 = __ldg(h4 + i + 256), v2 = __ldg(h4 + i + 512), v3 = __ldg(h4 + i + 768);
+      take(bv, bi, v0.x, 4 * i), take(bv, bi, v0.y, 4 * i + 1), take(bv, bi, v0.z, 4 * i + 2), take(bv, bi, v0.w, 4 * i + 3);
+      take(bv, bi, v1.x, 4 * i + 1024), take(bv, bi, v1.y, 4 * i + 1025), take(bv, bi, v1.z, 4 * i + 1026), take(bv, bi, v1.w, 4 * i + 1027);
+      take(bv, bi, v2.x, 4 * i + 2048), take(bv, bi, v2.y, 4 * i + 2049), take(bv, bi, v2.z, 4 * i + 2050), take(bv, bi, v2.w, 4 * i + 2051);
+      take(bv, bi, v3.x, 4 * i + 3072), take(bv, bi, v3.y, 4 * i + 3073), take(bv, bi, v3.z, 4 * i + 3074), take(bv, bi, v3.w, 4 * i + 3075);
+    }
+    for (; i < e4; i += 256) {
+      const float4 v = __ldg(h4 + i);
+      take(bv, bi, v.x, 4 * i), take(bv, bi, v.y, 4 * i + 1), take(bv, bi, v.z, 4 * i + 2), take(bv, bi, v.w, 4 * i + 3);
+    }
+  } else {
+    for (int i = b + threadIdx.x; i < e; i += 256) take(bv, bi, __ldg(h + i), i);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    take(bv, bi, ov, oi);
+  }
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sv[warp] = bv, si[warp] = bi;
+  __syncthreads();
+  if (warp == 0) {
+    bv = lane < 8 ? sv[lane] : -INFINITY;
+    bi = lane < 8 ? si[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      take(bv, bi, ov, oi);
+    }
+    if (lane == 0) pval[size_t(plane) * gridDim.x + s] = bv, pidx[size_t(plane) * gridDim.x + s] = bi;
+  }
+}
+
+__global__ void __launch_bounds__(128) argmax_fold_kernel(const float* __restrict__ pval, const int* __restrict__ pidx, int planes, int splits, int W,
+                                                          int32_t* __restrict__ xy, float* __restrict__ val) {
+  unpp::pdl_wait();
+  unpp::pdl_trigger();
+  const int plane = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;  // one warp per plane
+  if (plane >= planes) return;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int s = lane; s < splits; s += 32) take(bv, bi, pval[size_t(plane) * splits + s], pidx[size_t(plane) * splits + s]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    take(bv, bi, ov, oi);
+  }
+  if (lane == 0) {
+    if (bi == 0x7fffffff) bi = 0;
+    xy[2 * plane] = bi % W, xy[2 * plane + 1] = bi / W;
+    if (val) val[plane] = bv;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Target heat-map synthesis of the reference trainer (tools/misc/helper.py:87-172, called on the CPU every
 // step at trainer/trainer.py:122-123): 7 key points -> 4 planes, point groups {0}, {1,2,3}, {4}, {5..};
-// per point exp(-0.5 * dist / 3) with the Euclidean DISTANCE (not squared) in float64; single-point
-// planes are assigned, multi-point planes are summed (float32 += float64) and divided by their maximum.
+// per point exp(-0.5 * dist / 3) with the Euclidean DISTANCE (not squared) in float64; planes 0 and 2 are
+// assigned (helper.py:106,142), planes 1 and 3 are summed (float32 += float64) and ALWAYS divided by their
+// maximum (helper.py:122-123,158-159) — also when plane 3 holds a single point (6 key points).
 // One CTA per (n, channel) plane: pass 1 writes the sums and reduces the plane maximum, pass 2 normalises.
 __global__ void __launch_bounds__(256) create_heatmap_kernel(const float* __restrict__ kp, int npts, int H, int W, float* __restrict__ out) {
   unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
@@ -306,6 +383,7 @@ __global__ void __launch_bounds__(256) create_heatmap_kernel(const float* __rest
     cx[i] = i < np ? double(kp[(size_t(n) * npts + p0 + i) * 2]) : 0.0;
     cy[i] = i < np ? double(kp[(size_t(n) * npts + p0 + i) * 2 + 1]) : 0.0;
   }
+  const bool summed = ch & 1;  // planes 1 and 3: "+=" then "/ max"
   float mx = 0.f;
   for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
     const double x = double(i % W), y = double(i / W);
@@ -313,12 +391,12 @@ __global__ void __launch_bounds__(256) create_heatmap_kernel(const float* __rest
     for (int k = 0; k < np && k < 4; ++k) {
       const double d = sqrt((x - cx[k]) * (x - cx[k]) + (y - cy[k]) * (y - cy[k]));
       const double g = exp(-0.5 * d / 3.0);
-      acc = np == 1 ? float(g) : float(double(acc) + g);
+      acc = summed ? float(double(acc) + g) : float(g);
     }
     plane[i] = acc;
     mx = fmaxf(mx, acc);
   }
-  if (np <= 1) return;
+  if (!summed) return;
   __shared__ float smax[8];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -390,6 +468,33 @@ extern "C" int unpp_create_heatmap(const float* keypoints, int N, int npts, int 
   if (npts < 6 || npts > 9) return unpp::fail(UNPP_ERR_UNSUPPORTED, "create_heatmap: the reference's grouping needs 6..9 key points (7 in the trainer)");
   unpp::launch(create_heatmap_kernel, N * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream), keypoints, npts, H, W, out);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("create_heatmap: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_argmax_splits(int planes, int H, int W) {
+  // enough CTAs for ~4 per SM, segments of at least 16 K values; 1 = the one-CTA-per-plane kernel is the better choice
+  if (planes < 1 || H < 1 || W < 1) return 1;
+  const long HW = long(H) * W;
+  long want = (4L * unpp::num_sms() + planes - 1) / planes, cap = HW / 16384;
+  if (want > cap) want = cap;
+  if (want > 256) want = 256;
+  return want < 2 ? 1 : int(want);
+}
+
+extern "C" int unpp_argmax_peaks_split(const float* heat, int planes, int H, int W, int32_t* xy, float* val, void* workspace, int splits, unpp_stream_t stream) {
+  if (!heat || !xy || planes < 0 || H < 1 || W < 1 || splits < 1 || splits > 1024) return unpp::fail(UNPP_ERR_BAD_ARG, "argmax_peaks_split: bad argument");
+  if (long(H) * W > 0x7ffffff0L || planes > 65535) return unpp::fail(UNPP_ERR_UNSUPPORTED, "argmax_peaks_split: plane too large / too many planes");
+  if (planes == 0) return UNPP_OK;
+  if (splits == 1) return unpp_argmax_peaks(heat, planes, H, W, xy, val, stream);
+  if (!workspace) return unpp::fail(UNPP_ERR_BAD_ARG, "argmax_peaks_split: workspace of planes * splits * 8 bytes needed");
+  const int HW = H * W;
+  const int seg = ((HW + splits - 1) / splits + 3) & ~3;
+  float* pval = static_cast<float*>(workspace);
+  int* pidx = reinterpret_cast<int*>(pval + size_t(planes) * splits);
+  unpp::launch(argmax_split_kernel, dim3(splits, planes), 256, 0, reinterpret_cast<cudaStream_t>(stream), heat, HW, seg, pval, pidx);
+  unpp::launch(argmax_fold_kernel, (planes + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream), static_cast<const float*>(pval), static_cast<const int*>(pidx), planes,
+               splits, W, xy, val);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("argmax_peaks_split: launch");
   return UNPP_OK;
 }
 

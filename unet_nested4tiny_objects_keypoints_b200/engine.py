@@ -112,11 +112,15 @@ class Engine:
     def packed_eval(self):
         """bf16 UMMA-layout weights with eval-mode BatchNorm folded in (unet.py:133), cached until a
         parameter or buffer changes."""
-        key = self._param_key()
-        if self._packed_eval is not None and self._packed_key == key:
+        # An nn.DataParallel replica holds fresh broadcast copies at every forward: their versions are always 0 and the caching
+        # allocator tends to hand out the same addresses again, so (data_ptr, _version) cannot tell new weights from old.
+        # Replicas are re-packed at every eval forward; the master module (and every single-device use) is cached.
+        replica = bool(getattr(self.model, "_is_replica", False))
+        key = None if replica else self._param_key()
+        if key is not None and self._packed_eval is not None and self._packed_key == key:
             return self._packed_eval
         P: Dict[str, Dict] = {}
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(self.device):
             for name in ENCODER:
                 for n in (1, 2):
                     seq = self._conv_seq(name, n)
@@ -231,6 +235,12 @@ class Engine:
         (fp32 NCHW) — ``None`` for heads not requested."""
         B, H, W = self._check_input(x)
         x = x.contiguous()
+        # the kernels, their TMA descriptors and the per-device shared-memory opt-in belong to the ENGINE's device, whatever the
+        # calling thread's current device is (the reference works regardless of it)
+        with torch.cuda.device(self.device):
+            return self._forward_eval(x, B, H, W, heads)
+
+    def _forward_eval(self, x: torch.Tensor, B: int, H: int, W: int, heads: Sequence[int]):
         P = self.packed_eval()
         c4 = bool(P["conv00.c1"].get("c4"))
         A = self.arena(B, H, W, "eval4" if c4 else "eval")
@@ -288,5 +298,6 @@ class Engine:
         if head not in (0, 1, 2):
             raise ValueError("head must be 0, 1 or 2")
         heats = self.forward_eval(x, heads=(head,))
-        xy, val = ops.argmax_peaks(heats[head])
+        with torch.cuda.device(self.device):
+            xy, val = ops.argmax_peaks(heats[head])
         return xy, val, heats

@@ -4,8 +4,8 @@ launch of a step captured in one CUDA graph.
   * ``InferenceSession``  — ``val_epoch_`` core (trainer/trainer.py:209-220): forward in eval mode +
     heat-map arg-max keypoints (tools/misc/heatmap.py:173-178), host tensors in, keypoints out.
   * ``FusedTrainStep``    — ``train_epoch_`` core (trainer/trainer.py:115-136): zero_grad, forward,
-    mean-of-three-heads MSE (nn.MSELoss, trainer.py:427) with its gradient fused into the head
-    backward, backward, [data-parallel all-reduce], the reference's AdamW (tools/optimizers/
+    mean-of-three-heads FocalLoss_BCE_2d (the trainer's heatmap_criterion, trainer.py:426) or nn.MSELoss
+    (BASELINE.json's configurations) with its gradient fused into the head backward, backward, [data-parallel all-reduce], the reference's AdamW (tools/optimizers/
     adamw.py:38-100) over one flat parameter buffer.  Where the reference makes three D2H copies, a
     CPU loss and one H2D gradient copy per step (trainer.py:127-135), nothing leaves the device here.
 
@@ -48,15 +48,24 @@ class InferenceSession:
         if model.training:
             raise RuntimeError("InferenceSession needs model.eval()")
         self.B = B
+        self.use_graph = use_graph
         self.xs = [torch.zeros(B, model.in_channels, H, W, dtype=torch.float32, device=self.dev) for _ in range(2)]
         self.out = [None, None]
+        self.graphs = [None, None]
+        self._capture()
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+
+    def _capture(self):
+        """(Re)build the captured passes.  The graphs hold raw pointers into the engine's activation arena and packed eval-mode
+        weights: the session keeps both alive itself (the engine evicts arenas of other shapes and replaces the packed weights
+        whenever a parameter changes) and remembers the parameter key the weights were folded from."""
         self.graphs = [None, None]
         with torch.no_grad(), torch.cuda.device(self.dev):
             n0 = ops.launch_count
             self._body(0)  # warm-up: packs weights, allocates the activation arena
             self.launches = ops.launch_count - n0 - self._pack_launches
             torch.cuda.synchronize()
-            if use_graph:
+            if self.use_graph:
                 s = torch.cuda.Stream()
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
@@ -69,7 +78,10 @@ class InferenceSession:
                     self.graphs[i] = g
             else:
                 self._body(1)
-        self.copy_stream = torch.cuda.Stream(device=self.dev)
+            self._key = self.eng._param_key()
+            self._P = self.eng.packed_eval()
+            H, W = self.xs[0].shape[2], self.xs[0].shape[3]
+            self._arena = self.eng.arena(self.B, H, W, "eval4" if self._P["conv00.c1"].get("c4") else "eval")
 
     # kernels per pass: nchw->nhwc, 8 encoder convs, 3 pools, 6 x (deconv + 2 convs), arg-max = 31
     def _body(self, i: int):
@@ -102,6 +114,8 @@ class InferenceSession:
 
     def run_device(self, i: int = 0):
         """Inputs already in ``self.xs[i]`` (device): one pass of the hot path."""
+        if self.eng._packed_key is None or self._key != self.eng._param_key():
+            self._capture()  # a parameter or BatchNorm buffer changed since the weights were folded: re-pack and re-capture
         if self.graphs[i] is not None:
             self.graphs[i].replay()
         else:
@@ -151,10 +165,15 @@ class InferenceSession:
 
 class FusedTrainStep:
     def __init__(self, model, B: int, H: int, W: int, lr: float = 3e-6, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-4, device="cuda", use_graph: bool = True, process_group=None, seed: int = 0, loss: str = "mse",
+                 weight_decay: float = 1e-4, device="cuda", use_graph: bool = True, process_group=None, seed: int = 0, loss: str = "focal",
                  focal_gamma: float = 3.0, optimizer: str = "adamw", momentum: float = 0.9, dampening: float = 0.0, final_lr: float = 0.1,
                  bound_gamma: float = 1e-3):
-        """Defaults follow the reference CLI: ``--optimizer adamw --lr 3e-6 --weight-decay 1e-4`` (train.py:38-45).
+        """Defaults follow the reference trainer: ``--optimizer adamw --lr 3e-6 --weight-decay 1e-4`` (train.py:38-45) and
+        ``loss="focal"``, the criterion its training loop optimises — ``heatmap_criterion = FocalLoss_BCE_2d(gamma=3,
+        size_average=False)`` (trainer.py:426, used at 125-135), mean over the three heads.  ``loss="mse"`` is the
+        ``nn.MSELoss`` heat-map loss BASELINE.json's configurations name (the reference itself only uses MSE for the
+        landmark criterion of validation, trainer.py:427,221).  In data-parallel runs every rank draws its own dropout
+        masks (``seed + rank``), like nn.DataParallel's replicas draw from their devices' generators.
         ``optimizer``: any of the trainer's choices (trainer.py:344-376) — "adamw" (tools/optimizers/adamw.py), "adam" / "sgd"
         (torch.optim with the trainer's arguments; ``momentum`` = train.py:39), "sgdw" (tools/optimizers/sgdw.py as shipped, built by the
         trainer without momentum: pass ``momentum=0`` for that), "adabound" (tools/optimizers/adabound.py).  The learning rate lives
@@ -188,6 +207,7 @@ class FusedTrainStep:
                 off, cnt = lay[name]
                 self.flat_p[off:off + cnt].copy_(p.detach().reshape(-1))
                 p.data = self.flat_p[off:off + cnt].view_as(p)
+        self._versioned = list(model.parameters()) + [b for b in model.buffers() if b.dtype.is_floating_point]
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=self.dev)
         self.flat_m = torch.zeros(n, dtype=torch.float32, device=self.dev)
         self.flat_v = torch.zeros(n, dtype=torch.float32, device=self.dev)
@@ -287,7 +307,9 @@ class FusedTrainStep:
             else:
                 self._update()
         self.steps_done += 1
-        self.eng._packed_key = None  # parameters changed through raw pointers: eval-mode packed weights are stale
+        # parameters (and BatchNorm running statistics) changed through raw pointers: tell every version-keyed cache
+        torch._C._increment_version(self._versioned)
+        self.eng._packed_key = None
         return self.loss
 
     def step(self, x_host: torch.Tensor, target_host: torch.Tensor) -> torch.Tensor:

@@ -255,8 +255,17 @@ def argmax_peaks(heat: torch.Tensor):
     B, Cc, H, W = heat.shape
     xy = torch.empty(B, Cc, 2, dtype=torch.int32, device=heat.device)
     val = torch.empty(B, Cc, dtype=torch.float32, device=heat.device)
+    splits = lib().unpp_argmax_splits(B * Cc, H, W)  # few large planes (1024x1024 at batch 16): several CTAs per plane + a fold launch
+    nbytes = heat.numel() * 4
+    if splits > 1:
+        ws = torch.empty(B * Cc * splits * 2, dtype=torch.float32, device=heat.device)
+        _count(2)
+        with _Traced("argmax_peaks_split", nbytes, 0):
+            _lib.check(lib().unpp_argmax_peaks_split(heat.data_ptr(), B * Cc, H, W, xy.data_ptr(), val.data_ptr(), ws.data_ptr(), splits, _stream()),
+                       "unpp_argmax_peaks_split")
+        return xy, val
     _count()
-    with _Traced("argmax_peaks", 0, 0):
+    with _Traced("argmax_peaks", nbytes, 0):
         _lib.check(lib().unpp_argmax_peaks(heat.data_ptr(), B * Cc, H, W, xy.data_ptr(), val.data_ptr(), _stream()), "unpp_argmax_peaks")
     return xy, val
 

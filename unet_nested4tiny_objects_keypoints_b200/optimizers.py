@@ -59,11 +59,18 @@ class AdamW(Optimizer):
                 with torch.cuda.device(p.device):
                     ops.adamw(p.data.view(-1), g.view(-1), state["exp_avg"].view(-1), state["exp_avg_sq"].view(-1), group["lr"], b1, b2, group["eps"],
                               group["weight_decay"], state["step"])
+                _written(p)
         return loss
 
 
 def _flat(t):
     return t.view(-1)
+
+
+def _written(p) -> None:
+    """The kernels update ``p`` through its raw pointer: tell autograd / every ``_version``-keyed cache (the engine's folded
+    eval-mode weights) that the tensor changed, like an in-place torch op would."""
+    torch._C._increment_version([p])
 
 
 def _check(p):
@@ -107,6 +114,7 @@ class SGDW(Optimizer):
                 with torch.cuda.device(p.device):
                     ops.optim_step("sgdw", _flat(p.data), _flat(g), buf, None, lr=group["lr"], beta1=group["momentum"], beta2=group["dampening"],
                                    weight_decay=group["weight_decay"], step=state["step"])
+                _written(p)
         return loss
 
 
@@ -155,4 +163,5 @@ class AdaBound(Optimizer):
                     ops.optim_step("adabound", _flat(p.data), _flat(g), _flat(state["exp_avg"]), _flat(state["exp_avg_sq"]), lr=group["lr"], beta1=b1,
                                    beta2=b2, eps=group["eps"], weight_decay=group["weight_decay"], final_lr=group["final_lr"], gamma=group["gamma"],
                                    base_lr=base_lr, step=state["step"])
+                _written(p)
         return loss

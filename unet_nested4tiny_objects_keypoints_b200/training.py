@@ -23,6 +23,7 @@ How it runs here (all NHWC bf16 activations / gradients, fp32 accumulation, fp32
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -106,6 +107,15 @@ class TrainState:
         self.lay, self.nflat = flat_layout(eng.model)
         self.drop_scale = 1.0
         self.use_masks = False
+        # Which forward the saved activations belong to: forward_train bumps `generation`; an autograd node remembers the value it
+        # ran at and refuses to run its backward on activations a later forward overwrote.  `owner` is a weak reference to the
+        # token of the autograd node whose backward is still outstanding (dead once the node is freed or its backward has run).
+        self.generation = 0
+        self.owner = None
+
+    def busy(self) -> bool:
+        tok = self.owner() if self.owner is not None else None
+        return tok is not None and not tok.done
 
     def wgrad_stream(self) -> torch.cuda.Stream:
         s = getattr(self, "_wgrad_stream", None)
@@ -236,6 +246,7 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
     eng, t, P, m = ts.eng, ts.t, ts.packed, ts.eng.model
     B, H, W = ts.B, ts.H, ts.W
     ncls = m.n_classes
+    ts.generation += 1  # the saved activations now belong to this forward
     if update_running_stats:
         eng._packed_key = None  # running statistics change below without a torch version bump: drop the eval-mode fold cache
     ops.nchw_to_nhwc16(x, t["x16"])
@@ -243,6 +254,7 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
         after_input()  # join point for the weight re-packing the caller put on a side stream
     src = t["x16"]
     tracked: List[torch.Tensor] = []
+    stat_buffers: List[torch.Tensor] = []
     for lvl, name in enumerate(ENCODER):
         h, w, c = H >> lvl, W >> lvl, eng.filters[lvl]
         count = B * h * w
@@ -272,6 +284,7 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
                             t[pre + ".shift"])
             if update_running_stats:
                 tracked.append(bn.num_batches_tracked)
+                stat_buffers += [bn.running_mean, bn.running_var]
             if n == 1:
                 ops.bn_relu(z, t[pre + ".scale"], t[pre + ".shift"], t[f"{name}.a"])
                 src = t[f"{name}.a"]
@@ -280,6 +293,8 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
                 src = t[f"P{lvl}0"] if lvl < 3 else None
     if tracked:
         torch._foreach_add_(tracked, 1)  # the eight int64 num_batches_tracked counters: one launch
+        if not torch.cuda.is_current_stream_capturing():  # (a captured step bumps the versions once per replay, fused.FusedTrainStep.step_device)
+            torch._C._increment_version(stat_buffers)  # running_mean / running_var were written through raw pointers
     if before_decoder is not None:
         before_decoder()  # join point for work the caller put on a side stream (the head dropout masks)
     heats: List[torch.Tensor] = [None, None, None]
@@ -550,13 +565,26 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
 
 # ---------------------------------------------------------------------------------------------- autograd boundary
 def _train_state(eng: Engine, B: int, H: int, W: int) -> TrainState:
+    """The cached state of this shape — or, while an earlier forward of the same shape still waits for its backward
+    (``o1 = model(x1); o2 = model(x2); (l1 + l2).backward()``, which autograd supports), a fresh one that lives as long as
+    the autograd node that owns it."""
     cache = eng.__dict__.setdefault("_train_states", {})
     ts = cache.get((B, H, W))
+    if ts is not None and ts.busy():
+        return TrainState(eng, B, H, W)
     if ts is None:
         if len(cache) >= 2:
             cache.pop(next(iter(cache)))
         ts = cache[(B, H, W)] = TrainState(eng, B, H, W)
     return ts
+
+
+class _Token:
+    """Lives exactly as long as the autograd node of one forward (ctx holds the only strong reference)."""
+    __slots__ = ("done", "__weakref__")
+
+    def __init__(self):
+        self.done = False
 
 
 def _prepare_dropout(ts: TrainState) -> None:
@@ -590,12 +618,17 @@ class _UNetNestedFn(torch.autograd.Function):
             pack_train(ts)
             _prepare_dropout(ts)
             heats = forward_train(ts, x)
-        ctx.eng, ctx.ts = eng, ts
+        ctx.eng, ctx.ts, ctx.generation, ctx.token = eng, ts, ts.generation, _Token()
+        ts.owner = weakref.ref(ctx.token)
         return heats
 
     @staticmethod
     def backward(ctx, *dheats):
         eng, ts = ctx.eng, ctx.ts
+        if ts.generation != ctx.generation:
+            raise RuntimeError("UNet_Nested backward: the activations saved by this forward were overwritten by a later train-mode forward of the "
+                               "same shape (a second backward through a retained graph after another forward is not supported)")
+        ctx.token.done = True
         G = torch.zeros(ts.nflat, dtype=torch.float32, device=eng.device)  # fresh buffer: p.grad may alias views of it
         dh = [None if d is None else d.contiguous().float() for d in dheats]
         with torch.cuda.device(eng.device):
