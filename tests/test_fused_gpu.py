@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 import unet_nested4tiny_objects_keypoints_b200 as pkg  # noqa: E402
 from unet_nested4tiny_objects_keypoints_b200 import fused  # noqa: E402
 from oracle import unetpp_oracle as O  # noqa: E402
-from test_training_gpu import check_grads  # noqa: E402
+from test_training_gpu import check_grads, emulation_bounds  # noqa: E402
 
 
 def test_inference_session_graph_equals_eager_and_oracle():
@@ -57,7 +57,7 @@ def test_fused_train_step_loss_grads_and_adamw_update(use_graph):
     rl, _, rg, rstats = O.train_step_grads(sd, x, target, dropout_masks=None)
     assert abs(float(loss) - float(rl)) <= 1e-2 * float(rl)
     grads = {k: step.flat_g[off:off + n].view_as(p) for (k, p), (off, n) in zip(m.named_parameters(), step.ts.lay.values())}
-    check_grads(grads, rg)
+    check_grads(grads, rg, emulation_bounds(sd, x, target, None, 0.0, rg, loss="focal"))
     # the update is the reference AdamW (decay = wd * p_old, not scaled by lr) applied to OUR gradient
     p_exp, _, _ = O.adamw_reference_step(p_old.cpu(), step.flat_g.cpu(), torch.zeros_like(p_old.cpu()), torch.zeros_like(p_old.cpu()), 1, **hyper)
     assert torch.allclose(step.flat_p.cpu(), p_exp, rtol=1e-5, atol=1e-7)
@@ -107,7 +107,7 @@ def test_fused_train_step_with_the_shipped_focal_criterion():
     rl, _, rg, _ = O.train_step_grads(sd, x, target, dropout_masks=None, loss="focal")
     assert abs(float(loss) - float(rl)) <= 2e-2 * abs(float(rl))
     grads = {k: step.flat_g[off:off + n].view_as(p) for (k, p), (off, n) in zip(m.named_parameters(), step.ts.lay.values())}
-    check_grads(grads, rg)
+    check_grads(grads, rg, emulation_bounds(sd, x, target, None, 0.0, rg, loss="focal"))
 
 
 def test_reference_adamw_dropin_optimizer_matches_reference_semantics(golden):

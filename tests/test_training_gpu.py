@@ -3,20 +3,21 @@ trainer drives it (trainer/trainer.py:115-136: zero_grad, model(inputs), loss on
 loss.backward(), optimizer.step()), against the reference outputs in tests/golden/ and the oracle's
 CPU autograd on the same seeded inputs, weights and dropout masks.
 
-Stated bf16 bounds for the training path (activations AND activation gradients are stored in bf16
-between the fused kernels; parameter gradients are accumulated and stored in fp32):
+Parity statements of the training path (activations AND activation gradients are stored in bf16 between the fused kernels;
+parameter gradients are accumulated and stored in fp32):
+  * TIGHT, per stored tensor (oracle/teacher_forced.py): every tensor a step stores equals the fp64 restatement of the
+    reference operation applied to the step's own stored inputs to ONE bf16 ulp, every parameter gradient to 1e-3 (measured
+    <= 1e-5).  A 10 % error in one dgrad slice fails it.
+  * End to end against the fp32 oracle the difference is the bf16 storage noise of this graph — the same for ANY exact
+    implementation of the storage scheme (profiles/r02_grad_errors_*.md: ours, the fp32 emulation of our storage points and
+    stock PyTorch autocast(bf16) all land on the same per-tensor figures; two exact emulations that differ only in
+    accumulation precision disagree by a third of it, because a bf16-storage network is chaotic at the rounding level).
+    Bounds are therefore per tensor and MEASURED: 2x the committed table at the shapes it covers (2x64x64 and 32x256x256),
+    and at other shapes 3x the error of oracle/bf16_emulation.py against the same fp32 oracle, computed in the test.
   * heat maps: max |err| <= 3e-2, mean |err| <= 3e-3;  loss: relative error <= 1e-2;
-  * parameter gradients g vs the fp32 reference g_ref, per group (err = max|g - g_ref| / max|g_ref|):
-        heads and full-resolution decoder nodes (up_concat01/02/03, final_*):  err <= 0.1,  cosine >= 0.995
-        deeper decoder nodes (up_concat11/12/21):                              err <= 0.5,  cosine >= 0.95
-        encoder (conv00..conv30, the end of the backward chain, tiny grads):   err <= 1.0,  cosine >= 0.85
-    (the small test shapes are the noisy end: few pixels per weight; at 256x256 the figures are 3-10x smaller)
-    These are the noise floor of bf16 storage on this network, not kernel error: stock PyTorch
-    autocast(bf16) (cuDNN) on the same inputs lands on the same figures, and
-    test_gradient_noise_is_no_worse_than_torch_autocast_bf16 pins ours to <= 1.5x its error;
   * BatchNorm running statistics: relative error <= 1e-2 of the tensor's max.
-The oracle (fp32, CPU) is the reference; conv biases in front of a BatchNorm have an exactly zero
-gradient analytically — the reference holds rounding noise there (|g| ~ 1e-9), we hold 0."""
+Conv biases in front of a BatchNorm have an exactly zero gradient analytically — the reference holds rounding noise there
+(|g| ~ 1e-9), we hold 0."""
 import numpy as np
 import pytest
 import torch
@@ -29,25 +30,39 @@ from oracle import bf16_emulation as E  # noqa: E402
 from oracle import teacher_forced as T  # noqa: E402
 from oracle import unetpp_oracle as O  # noqa: E402
 
-GRAD_REL = 5e-2  # full-resolution group; see the module docstring for the others
-
-
 def _is_pre_bn_bias(k):
     return k.startswith("conv") and k.endswith(".0.bias")
 
 
-def _bounds(k):
-    if k.startswith("conv"):
-        return 1.0, 0.85
-    if k.startswith(("up_concat11", "up_concat12", "up_concat21")):
-        return 0.5, 0.95
-    return 0.1, 0.995
+# (max err / max|g_ref|, min cosine) per module = 2x the worst figure of that module in profiles/r02_grad_errors_<shape>.md
+# (column "ours vs fp32"; the cosine bound is 1 - 2 (1 - measured)); regenerate with scripts/grad_error_table.py.
+TABLE_BOUNDS = {
+    "b32_256": {"conv00": (6.0e-2, 0.9992), "conv10": (9.4e-2, 0.9970), "conv20": (2.9e-1, 0.969), "conv30": (7.4e-1, 0.892),
+                "up_concat01": (1.1e-2, 0.9999), "up_concat11": (2.6e-2, 0.9999), "up_concat21": (6.3e-2, 0.9993), "up_concat02": (1.2e-2, 0.9999),
+                "up_concat12": (1.6e-2, 0.9999), "up_concat03": (9.0e-3, 0.9999), "final": (9.0e-3, 0.9999)},
+    "b2_64": {"conv00": (4.5e-1, 0.966), "conv10": (5.2e-1, 0.958), "conv20": (6.4e-1, 0.923), "conv30": (7.8e-1, 0.869),
+              "up_concat01": (5.1e-2, 0.9993), "up_concat11": (2.4e-1, 0.990), "up_concat21": (4.5e-1, 0.961), "up_concat02": (4.6e-2, 0.9995),
+              "up_concat12": (1.7e-1, 0.994), "up_concat03": (2.5e-2, 0.9996), "final": (7.0e-3, 0.9999)},
+}
+
+
+def table_bounds(shape):
+    tbl = TABLE_BOUNDS[shape]
+    return lambda k: tbl[k.split(".")[0] if not k.startswith("final") else "final"]
+
+
+def emulation_bounds(sd, x, target, masks=None, p_drop=0.4, ref=None, dheats=None, loss="mse"):
+    """Per-tensor bounds at an arbitrary shape: 3x what an exact fp32 emulation of our bf16 storage points (oracle/bf16_emulation.py)
+    deviates from the fp32 oracle on these very inputs (+ 5e-3 / 1e-3 floors for tensors it happens to hit exactly)."""
+    _, _, eg, _ = E.train_step_grads_bf16(sd, x, target, dropout_masks=masks, p_drop=p_drop, dheats=dheats, loss=loss)
+    errs = grad_errors(eg, ref)
+    return lambda k: (3.0 * errs[k][0] + 5e-3, 1.0 - 3.0 * (1.0 - errs[k][1]) - 1e-3)
 
 
 def grad_errors(named_grads, ref):
     out = {}
     for k, g in named_grads.items():
-        r = ref[k].double()
+        r = ref[k].double().cpu()
         g = g.detach().cpu().double()
         assert g.shape == r.shape, k
         scale = float(r.abs().max())
@@ -57,7 +72,7 @@ def grad_errors(named_grads, ref):
     return out
 
 
-def check_grads(named_grads, ref):
+def check_grads(named_grads, ref, bounds):
     worst = ("", 0.0)
     for k, (rel, cos, scale, gmax) in grad_errors(named_grads, ref).items():
         if _is_pre_bn_bias(k):
@@ -66,9 +81,9 @@ def check_grads(named_grads, ref):
         if scale == 0.0:  # e.g. a head that does not contribute to the loss: both must be exactly zero
             assert gmax == 0.0, k
             continue
-        max_rel, min_cos = _bounds(k)
-        assert rel <= max_rel, f"{k}: rel err {rel:.3e} > {max_rel} (scale {scale:.3e}, cos {cos:.5f})"
-        assert cos >= min_cos, f"{k}: cosine {cos:.5f} < {min_cos}"
+        max_rel, min_cos = bounds(k)
+        assert rel <= max_rel, f"{k}: rel err {rel:.3e} > {max_rel:.3e} (scale {scale:.3e}, cos {cos:.5f})"
+        assert cos >= min_cos, f"{k}: cosine {cos:.5f} < {min_cos:.5f}"
         if rel > worst[1]:
             worst = (k, rel)
     return worst
@@ -184,12 +199,13 @@ def test_train_step_matches_reference_golden(golden):
         assert err.max() <= 3e-2 and err.mean() <= 3e-3, (i, err.max(), err.mean())
     assert abs(float(loss) - meta["train_loss"]) <= 1e-2 * meta["train_loss"]
     # the three gradients stored in full in the fixture, then all 74 against the oracle
-    for k in ("final_3.weight", "conv00.conv1.0.weight", "up_concat01.up.weight"):
-        r = arr[f"train_grad_{k}"]
-        g = dict(m.named_parameters())[k].grad.cpu().numpy()
-        assert np.abs(g - r).max() <= _bounds(k)[0] * np.abs(r).max(), k
     _, _, rg, rstats = O.train_step_grads(sd, x, target, dropout_masks=masks)
-    worst = check_grads({k: p.grad for k, p in m.named_parameters()}, rg)
+    bounds = emulation_bounds(sd, x, target, masks, 0.4, rg)
+    for k in ("final_3.weight", "conv00.conv1.0.weight", "up_concat01.up.weight"):
+        r = arr[f"train_grad_{k}"]  # the gradients the real reference produced (oracle/make_golden.py)
+        g = dict(m.named_parameters())[k].grad.cpu().numpy()
+        assert np.abs(g - r).max() <= bounds(k)[0] * np.abs(r).max(), k
+    worst = check_grads({k: p.grad for k, p in m.named_parameters()}, rg, bounds)
     print("worst gradient", worst)
     new_sd = m.state_dict()
     for k, v in rstats.items():
@@ -213,7 +229,8 @@ def test_train_step_matches_oracle(B, H, W, p_drop):
         err = (o.detach().cpu() - r).abs()
         assert float(err.max()) <= 3e-2 and float(err.mean()) <= 3e-3
     assert abs(float(loss) - float(rl)) <= 1e-2 * float(rl)
-    check_grads({k: p.grad for k, p in m.named_parameters()}, rg)
+    bounds = table_bounds("b2_64") if (B, H, W) == (2, 64, 64) else emulation_bounds(sd, x, target, masks, p_drop, rg)
+    check_grads({k: p.grad for k, p in m.named_parameters()}, rg, bounds)
 
 
 def test_arbitrary_upstream_gradients_like_the_trainer_cpu_loss():
@@ -237,7 +254,9 @@ def test_arbitrary_upstream_gradients_like_the_trainer_cpu_loss():
     ro = O.forward(full, x, training=True, dropout_masks=None)
     (0.7 * F.mse_loss(ro[0], target) + 0.3 * F.l1_loss(ro[2], target)).backward()
     ref = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in params.items()}
-    check_grads({k: p.grad for k, p in m.named_parameters()}, ref)
+    with torch.no_grad():
+        dh = [0.7 * 2 * (ro[0] - target) / target.numel(), None, 0.3 * torch.sign(ro[2] - target) / target.numel()]
+    check_grads({k: p.grad for k, p in m.named_parameters()}, ref, emulation_bounds(sd, x, target, None, 0.0, ref, dheats=dh))
     assert float(m.final_2.weight.grad.abs().max()) == 0.0
 
 
@@ -331,7 +350,12 @@ def test_nn_dataparallel_like_the_reference_trainer():
         rloss = sum(F.mse_loss(o, target) for o in routs) / 3
         rloss.backward()
         assert abs(float(loss.detach()) - float(rloss.detach())) <= 1e-2 * float(rloss.detach())
-        check_grads({k: p.grad for k, p in m.named_parameters()}, {k: p.grad for k, p in params.items()})
+        refg = {k: p.grad.detach().clone() for k, p in params.items()}
+        sd_now = dict(sd)
+        sd_now.update({k: v.detach() for k, v in params.items()})
+        # the replicas' halves are independent steps: bound = the emulation's deviation on the first half (same size, same weights)
+        _, _, rg_half, _ = O.train_step_grads(sd_now, x[:2], target[:2], dropout_masks=None)
+        check_grads({k: p.grad for k, p in m.named_parameters()}, refg, emulation_bounds(sd_now, x[:2], target[:2], None, 0.0, rg_half))
         with torch.no_grad():  # the same SGD step on both sides
             for k, p in m.named_parameters():
                 p -= 0.5 * params[k].grad.cuda()
