@@ -155,6 +155,22 @@ int unpp_pack_weights_batched(const UnppPackArgs* table_dev, int n, unpp_stream_
 
 /* fp32 NCHW [N,C,H,W] -> bf16 NHWC [N,H,W,Cpad] (channels >= C zero-filled); Cpad = 16, or 4 for the first-layer mode. */
 int unpp_nchw_to_nhwc(const float* x, void* out, int N, int C, int H, int W, int Cpad, unpp_stream_t stream);
+/* Eval-mode BatchNorm2d (models/unet.py:133) folded into the conv in front of it: scale[c] = gamma[c] / sqrt(running_var[c] + eps)
+ * (unpp_pack_weights multiplies it into the weights), bias[c] = (conv_bias[c] - running_mean[c]) * scale[c] + beta[c]. */
+int unpp_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var, const float* conv_bias, float eps, int C,
+                 float* scale, float* bias, unpp_stream_t stream);
+/* Weight preparation of the fused transposed conv (UnppConvArgs.lowres_src): conv3x3(cat[ConvTranspose2d_k2s2(low), ...]) restricted to
+ * the upsampled slice is ONE 3x3 conv over the low-resolution tensor.  w_conv fp32 [Co][Ctot][3][3] (its first Cu input channels
+ * multiply the upsampled tensor, models/unet.py:199-201), w_up fp32 [Ci][Cu][2][2], b_up [Cu] (unet.py:187), b_conv [Co] ->
+ * comp fp32 [4*Co][Ci][3][3] (output channel (2*jy+jx)*Co + co, taps = low-resolution offsets -1..1; pack it with kind 6) and
+ * table fp32 [9][Co] = bias per (row class, column class) (UnppConvArgs.bias_classes = 9). */
+int unpp_compose_deconv_conv(const float* w_conv, int Ctot, int Cu, const float* w_up, const float* b_up, const float* b_conv, int Co, int Ci,
+                             float* comp, float* table, unpp_stream_t stream);
+/* 8-bit images -> bf16 NHWC [N,H,W,Cpad] with torchvision ToTensor's scaling fused in (value = byte / 255 in fp32, then the bf16
+ * rounding of the fp32 path): the reference converts PIL images on the CPU (datasets/datasets_base.py:71-72) and copies fp32
+ * tensors to the device (trainer/trainer.py:109); copying the bytes is 4x less host-to-device traffic.
+ * hwc = 1: x is [N,H,W,C] (PIL / OpenCV layout); hwc = 0: x is [N,C,H,W]. */
+int unpp_u8_to_nhwc(const uint8_t* x, void* out, int N, int C, int H, int W, int Cpad, int hwc, unpp_stream_t stream);
 /* bf16 NHWC 2x2/2 max pooling (H, W even). */
 int unpp_maxpool2x2(const void* x, void* out, int N, int H, int W, int C, unpp_stream_t stream);
 /* Per-plane arg-max of fp32 NCHW heatmaps: first maximum in row-major order -> xy[b][c] = {x, y},

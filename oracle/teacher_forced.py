@@ -44,6 +44,7 @@ class Report:
 
     def bf16(self, name: str, got: torch.Tensor, ref: torch.Tensor):
         """Stored bf16 tensor ``got`` against the fp64 recomputation ``ref`` (not yet rounded)."""
+        got, ref = got.detach(), ref.detach()
         refr = _r(ref)
         scale = float(ref.abs().max()) + 1e-30
         d = (got - refr).abs()
@@ -54,6 +55,7 @@ class Report:
                               frac_gt_ulp=float((d > ulp).double().mean()), scale=scale))
 
     def f32(self, name: str, got: torch.Tensor, ref: torch.Tensor):
+        got, ref = got.detach(), ref.detach()
         scale = float(ref.abs().max()) + 1e-30
         d = (got.to(ref.dtype) - ref).abs()
         self.rows.append(dict(name=name, kind="f32", max_rel=float(d.max()) / scale, scale=scale))

@@ -493,10 +493,51 @@ def test_conv_with_fused_maxpool(N, H, W, cin, cout, b2):
     assert torch.equal(nchw(pooled), F.max_pool2d(nchw(out), 2))
 
 
+def compose_deconv_conv_fp64(w_conv_u: torch.Tensor, w_up: torch.Tensor, b_up: torch.Tensor, b_conv: torch.Tensor):
+    """conv3x3(ConvTranspose2d_k2s2(x)) as ONE 3x3 conv over the low-resolution x (the k2s2 upsample never overlaps).
+
+    w_conv_u [Co, Cu, 3, 3]: the slice of the consuming conv's weight that multiplies the upsampled tensor (unet.py:199-201:
+    the first Cu input channels); w_up [Ci, Cu, 2, 2], b_up [Cu]: the transposed conv (unet.py:187); b_conv [Co].
+    Returns (composed weight [4*Co, Ci, 3, 3] whose output channel is (2*jy+jx)*Co + co for pixel (jy, jx) of the 2x2 output
+    block, and whose taps are offsets -1..1 on the low-res grid; bias table [9, Co] indexed by 3*rowclass + colclass,
+    class 0 = first row/column, 1 = interior, 2 = last: zero padding is applied AFTER the upsample, so border pixels see
+    fewer taps of the upsample bias)."""
+    co, cu = w_conv_u.shape[0], w_conv_u.shape[1]
+    ci = w_up.shape[0]
+    wc, wd = w_conv_u.double(), w_up.double()
+    comp = torch.zeros(4 * co, ci, 3, 3, dtype=torch.float64, device=wc.device)
+    for jy in range(2):
+        for jx in range(2):
+            for r in range(3):
+                for s in range(3):
+                    uy, ux = jy + r - 1, jx + s - 1          # position in the upsampled grid relative to the block origin
+                    dyl, p_ = uy // 2, uy % 2                # low-res row offset (-1, 0, 1) and row parity of that upsampled pixel
+                    dxl, q_ = ux // 2, ux % 2
+                    blk = (2 * jy + jx) * co
+                    comp[blk:blk + co, :, dyl + 1, dxl + 1] += wc[:, :, r, s] @ wd[:, :, p_, q_].t()
+    t = torch.einsum("ocrs,c->rso", wc, b_up.double())       # contribution of the upsample bias through tap (r, s)
+    valid = {0: (1, 2), 1: (0, 1, 2), 2: (0, 1)}              # taps that stay inside the image for first / interior / last row
+    table = torch.zeros(9, co, dtype=torch.float64, device=wc.device)
+    for rc in range(3):
+        for cc in range(3):
+            table[3 * rc + cc] = b_conv.double() + sum(t[r, s] for r in valid[rc] for s in valid[cc])
+    return comp.float().contiguous(), table.float().contiguous()
+
+
+def test_compose_kernel_matches_the_fp64_composition():
+    """unpp_compose_deconv_conv (fp32, one thread per element) against the fp64 torch restatement above."""
+    w = rnd(16, 48, 3, 3, seed=301, scale=0.1)
+    w_up, b_up, b = rnd(32, 16, 2, 2, seed=302, scale=0.2), rnd(16, seed=303, scale=0.3), rnd(16, seed=304, scale=0.1)
+    rc, rt = compose_deconv_conv_fp64(w[:, :16], w_up, b_up, b)
+    comp, table = ops.compose_deconv_conv(w.to(DEV), 16, w_up.to(DEV), b_up.to(DEV), b.to(DEV))
+    assert comp.shape == rc.shape and table.shape == rt.shape
+    assert float((comp.cpu() - rc).abs().max()) <= 1e-6 * float(rc.abs().max()) + 1e-7
+    assert float((table.cpu() - rt).abs().max()) <= 1e-6 * float(rt.abs().max()) + 1e-7
+
+
 @pytest.mark.parametrize("N,H,W,nlows", [(2, 32, 32, 1), (1, 24, 40, 2), (2, 64, 64, 3), (1, 8, 8, 1), (1, 128, 64, 2)])
 def test_fused_transposed_conv_into_block2x2_conv(N, H, W, nlows):
     """conv3x3(cat[ConvTranspose2d_k2s2(x_low), lows...]) + bias + ReLU in ONE launch, the upsampled tensor never exists."""
-    from unet_nested4tiny_objects_keypoints_b200.engine import compose_deconv_conv
     xlow = bf(rnd(N, 32, H // 2, W // 2, seed=200))
     lows = [bf(rnd(N, 16, H, W, seed=201 + i)) for i in range(nlows)]
     w_up = rnd(32, 16, 2, 2, seed=210, scale=0.2)
@@ -506,7 +547,7 @@ def test_fused_transposed_conv_into_block2x2_conv(N, H, W, nlows):
     b = rnd(16, seed=213, scale=0.1)
     up = F.conv_transpose2d(xlow.double(), w_up.double(), b_up.double(), stride=2)
     ref = F.relu(F.conv2d(torch.cat([up] + [l.double() for l in lows], 1), w.double(), b.double(), padding=1))
-    comp, table = compose_deconv_conv(w[:, :16].to(DEV), w_up.to(DEV), b_up.to(DEV), b.to(DEV))
+    comp, table = ops.compose_deconv_conv(w.to(DEV), 16, w_up.to(DEV), b_up.to(DEV), b.to(DEV))
     wp = ops.pack_weights_b2(w.to(DEV), False, 16 * nlows, k_begin=16)
     lw = ops.pack_weights(comp, 6, 9, 64, 64, 32)  # kind 6: only the non-zero (tap, pixel) blocks (csrc/b2_blocks.h)
     out = torch.empty(N, H, W, 16, dtype=torch.bfloat16, device=DEV)

@@ -53,10 +53,10 @@ def table_bounds(shape):
 
 def emulation_bounds(sd, x, target, masks=None, p_drop=0.4, ref=None, dheats=None, loss="mse"):
     """Per-tensor bounds at an arbitrary shape: 3x what an exact fp32 emulation of our bf16 storage points (oracle/bf16_emulation.py)
-    deviates from the fp32 oracle on these very inputs (+ 5e-3 / 1e-3 floors for tensors it happens to hit exactly)."""
+    deviates from the fp32 oracle on these very inputs (+ 1e-2 / 1e-3 floors for tensors it happens to hit exactly)."""
     _, _, eg, _ = E.train_step_grads_bf16(sd, x, target, dropout_masks=masks, p_drop=p_drop, dheats=dheats, loss=loss)
     errs = grad_errors(eg, ref)
-    return lambda k: (3.0 * errs[k][0] + 5e-3, 1.0 - 3.0 * (1.0 - errs[k][1]) - 1e-3)
+    return lambda k: (3.0 * errs[k][0] + 1e-2, 1.0 - 3.0 * (1.0 - errs[k][1]) - 1e-3)
 
 
 def grad_errors(named_grads, ref):

@@ -204,6 +204,35 @@ __global__ void nchw_to_nhwc4_kernel(const float* __restrict__ x, __nv_bfloat16*
   }
 }
 
+// 8-bit images -> NHWC bf16, torchvision ToTensor's scaling fused in: value = float(byte) / 255 (one fp32 division, like
+// ``img.float().div(255)``), then the same bf16 rounding the fp32 path applies.  The reference decodes 8-bit RGB with PIL and
+// converts on the CPU (datasets/datasets_base.py:71-72) before the H2D copy of fp32 tensors (trainer/trainer.py:109): moving
+// the bytes instead is 4x less PCIe traffic.  HWC = 1: x is [N,H,W,C] (what PIL / OpenCV hold); 0: [N,C,H,W].
+// One thread per pixel; the warp's reads are contiguous in either layout.
+template <int CPAD, bool HWC>
+__global__ void u8_to_nhwc_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C, long HW) {
+  unpp::pdl_wait();
+  unpp::pdl_trigger();
+  const long stride = long(gridDim.x) * blockDim.x, total = long(N) * HW;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += stride) {
+    const long n = i / HW, p = i % HW;
+    __align__(16) __nv_bfloat16 v[CPAD];
+#pragma unroll
+    for (int c = 0; c < CPAD; ++c) {
+      float f = 0.f;
+      if (c < C) f = float(HWC ? __ldg(x + i * C + c) : __ldg(x + (n * C + c) * HW + p)) / 255.f;
+      v[c] = __float2bfloat16_rn(f);
+    }
+    if constexpr (CPAD == 4) {
+      *reinterpret_cast<uint2*>(out + i * 4) = *reinterpret_cast<const uint2*>(v);
+    } else {
+      uint4* o = reinterpret_cast<uint4*>(out + i * CPAD);
+#pragma unroll
+      for (int k = 0; k < CPAD / 8; ++k) o[k] = reinterpret_cast<const uint4*>(v)[k];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // 2x2 max pool on NHWC bf16, 8 channels (16 B) per thread.
 __device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
@@ -408,6 +437,57 @@ __global__ void __launch_bounds__(256) create_heatmap_kernel(const float* __rest
   for (int i = threadIdx.x; i < H * W; i += blockDim.x) plane[i] = plane[i] / mx;  // each thread re-reads only what it wrote
 }
 
+// ------------------------------------------------------------------------------------------
+// conv3x3(ConvTranspose2d_k2s2(x)) as ONE 3x3 conv over the low-resolution x (models/unet.py:187,199-201: the k2s2 upsample
+// never overlaps).  comp[(2*jy+jx)*Co + co][ci][ty][tx] = sum over the conv taps (r, s) whose upsampled position
+// (jy + r - 1, jx + s - 1) lies in low-resolution cell (ty - 1, tx - 1), and over u, of Wc[co][u][r][s] * Wd[ci][u][p][q] with
+// (p, q) the parity of that position; table[3*rc + cc][co] = b_conv[co] + the upsample bias through the taps that stay inside
+// the image for a first / interior / last row (rc) and column (cc): zero padding is applied AFTER the upsample.
+// One thread per output element, fp32 accumulation of at most 4 * Cu products in a fixed order.
+__global__ void compose_deconv_conv_kernel(const float* __restrict__ wc, int Ctot, int Cu, const float* __restrict__ wd, const float* __restrict__ b_up,
+                                           const float* __restrict__ b_conv, int Co, int Ci, float* __restrict__ comp, float* __restrict__ table) {
+  unpp::pdl_wait();
+  unpp::pdl_trigger();
+  const int ncomp = 4 * Co * Ci * 9, total = ncomp + 9 * Co;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < ncomp) {
+      const int tx = i % 3, ty = (i / 3) % 3, ci = (i / 9) % Ci, row = i / (9 * Ci);
+      const int co = row % Co, jx = (row / Co) & 1, jy = (row / Co) >> 1;
+      float acc = 0.f;
+      for (int r = 0; r < 3; ++r) {
+        const int uy = jy + r - 1, dyl = uy < 0 ? -1 : uy >> 1, pp = uy - 2 * dyl;
+        if (dyl + 1 != ty) continue;
+        for (int sft = 0; sft < 3; ++sft) {
+          const int ux = jx + sft - 1, dxl = ux < 0 ? -1 : ux >> 1, qq = ux - 2 * dxl;
+          if (dxl + 1 != tx) continue;
+          for (int u = 0; u < Cu; ++u) acc = fmaf(__ldg(wc + ((size_t(co) * Ctot + u) * 3 + r) * 3 + sft), __ldg(wd + ((size_t(ci) * Cu + u) * 2 + pp) * 2 + qq), acc);
+        }
+      }
+      comp[i] = acc;
+    } else {
+      const int j = i - ncomp, co = j % Co, cls = j / Co, rc = cls / 3, cc = cls % 3;
+      float acc = __ldg(b_conv + co);
+      for (int r = (rc == 0 ? 1 : 0); r < (rc == 2 ? 2 : 3); ++r)
+        for (int sft = (cc == 0 ? 1 : 0); sft < (cc == 2 ? 2 : 3); ++sft)
+          for (int u = 0; u < Cu; ++u) acc = fmaf(__ldg(wc + ((size_t(co) * Ctot + u) * 3 + r) * 3 + sft), __ldg(b_up + u), acc);
+      table[j] = acc;
+    }
+  }
+}
+
+// Eval-mode BatchNorm2d folded into the preceding conv (models/unet.py:132-133): y = (conv + b - running_mean) * gamma / sqrt(running_var + eps) + beta
+//   scale[c] = gamma[c] / sqrt(running_var[c] + eps)  (multiplied into the packed weights),  bias[c] = (b[c] - running_mean[c]) * scale[c] + beta[c]
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rmean, const float* __restrict__ rvar,
+                               const float* __restrict__ cbias, float eps, int C, float* __restrict__ scale, float* __restrict__ bias) {
+  unpp::pdl_wait();
+  unpp::pdl_trigger();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] / sqrtf(rvar[c] + eps);
+  scale[c] = sc;
+  bias[c] = (cbias[c] - rmean[c]) * sc + beta[c];
+}
+
 inline int grid_for(long total, int block) {
   long g = (total + block - 1) / block;
   const long cap = long(unpp::num_sms()) * 16;
@@ -451,6 +531,38 @@ extern "C" int unpp_nchw_to_nhwc(const float* x, void* out, int N, int C, int H,
   unpp::launch(nchw_to_nhwc_kernel<16>, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       x, reinterpret_cast<__nv_bfloat16*>(out), N, C, long(H) * W);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("nchw_to_nhwc: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var, const float* conv_bias, float eps, int C,
+                            float* scale, float* bias, unpp_stream_t stream) {
+  if (!gamma || !beta || !running_mean || !running_var || !conv_bias || !scale || !bias || C < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "bn_fold: bad argument");
+  unpp::launch(bn_fold_kernel, (C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream), gamma, beta, running_mean, running_var, conv_bias, eps, C, scale, bias);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("bn_fold: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_compose_deconv_conv(const float* w_conv, int Ctot, int Cu, const float* w_up, const float* b_up, const float* b_conv, int Co, int Ci,
+                                        float* comp, float* table, unpp_stream_t stream) {
+  if (!w_conv || !w_up || !b_up || !b_conv || !comp || !table || Co < 1 || Ci < 1 || Cu < 1 || Cu > Ctot)
+    return unpp::fail(UNPP_ERR_BAD_ARG, "compose_deconv_conv: bad argument");
+  const long total = 4L * Co * Ci * 9 + 9L * Co;
+  unpp::launch(compose_deconv_conv_kernel, grid_for(total, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream), w_conv, Ctot, Cu, w_up, b_up, b_conv, Co, Ci, comp, table);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("compose_deconv_conv: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_u8_to_nhwc(const uint8_t* x, void* out, int N, int C, int H, int W, int Cpad, int hwc, unpp_stream_t stream) {
+  if (!x || !out || N < 1 || C < 1 || H < 1 || W < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "u8_to_nhwc: bad argument");
+  if ((Cpad != 16 && Cpad != 4) || C > Cpad) return unpp::fail(UNPP_ERR_UNSUPPORTED, "u8_to_nhwc: Cpad must be 16 or 4 and C <= Cpad");
+  const long total = long(N) * H * W;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (Cpad == 4 && hwc) unpp::launch(u8_to_nhwc_kernel<4, true>, grid_for(total, 256), 256, 0, st, x, o, N, C, long(H) * W);
+  else if (Cpad == 4) unpp::launch(u8_to_nhwc_kernel<4, false>, grid_for(total, 256), 256, 0, st, x, o, N, C, long(H) * W);
+  else if (hwc) unpp::launch(u8_to_nhwc_kernel<16, true>, grid_for(total, 256), 256, 0, st, x, o, N, C, long(H) * W);
+  else unpp::launch(u8_to_nhwc_kernel<16, false>, grid_for(total, 256), 256, 0, st, x, o, N, C, long(H) * W);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("u8_to_nhwc: launch");
   return UNPP_OK;
 }
 

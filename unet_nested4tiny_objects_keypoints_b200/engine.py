@@ -40,37 +40,6 @@ DECODER_ORDER = ("up_concat01", "up_concat11", "up_concat21", "up_concat02", "up
 HEAD_OF = {"up_concat01": "final_1", "up_concat02": "final_2", "up_concat03": "final_3"}
 
 
-def compose_deconv_conv(w_conv_u: torch.Tensor, w_up: torch.Tensor, b_up: torch.Tensor, b_conv: torch.Tensor):
-    """conv3x3(ConvTranspose2d_k2s2(x)) as ONE 3x3 conv over the low-resolution x (the k2s2 upsample never overlaps).
-
-    w_conv_u [Co, Cu, 3, 3]: the slice of the consuming conv's weight that multiplies the upsampled tensor (unet.py:199-201:
-    the first Cu input channels); w_up [Ci, Cu, 2, 2], b_up [Cu]: the transposed conv (unet.py:187); b_conv [Co].
-    Returns (composed weight [4*Co, Ci, 3, 3] whose output channel is (2*jy+jx)*Co + co for pixel (jy, jx) of the 2x2 output
-    block, and whose taps are offsets -1..1 on the low-res grid; bias table [9, Co] indexed by 3*rowclass + colclass,
-    class 0 = first row/column, 1 = interior, 2 = last: zero padding is applied AFTER the upsample, so border pixels see
-    fewer taps of the upsample bias)."""
-    co, cu = w_conv_u.shape[0], w_conv_u.shape[1]
-    ci = w_up.shape[0]
-    wc, wd = w_conv_u.double(), w_up.double()
-    comp = torch.zeros(4 * co, ci, 3, 3, dtype=torch.float64, device=wc.device)
-    for jy in range(2):
-        for jx in range(2):
-            for r in range(3):
-                for s in range(3):
-                    uy, ux = jy + r - 1, jx + s - 1          # position in the upsampled grid relative to the block origin
-                    dyl, p_ = uy // 2, uy % 2                # low-res row offset (-1, 0, 1) and row parity of that upsampled pixel
-                    dxl, q_ = ux // 2, ux % 2
-                    blk = (2 * jy + jx) * co
-                    comp[blk:blk + co, :, dyl + 1, dxl + 1] += wc[:, :, r, s] @ wd[:, :, p_, q_].t()
-    t = torch.einsum("ocrs,c->rso", wc, b_up.double())       # contribution of the upsample bias through tap (r, s)
-    valid = {0: (1, 2), 1: (0, 1, 2), 2: (0, 1)}              # taps that stay inside the image for first / interior / last row
-    table = torch.zeros(9, co, dtype=torch.float64, device=wc.device)
-    for rc in range(3):
-        for cc in range(3):
-            table[3 * rc + cc] = b_conv.double() + sum(t[r, s] for r in valid[rc] for s in valid[cc])
-    return comp.float().contiguous(), table.float().contiguous()
-
-
 def named_params(model):
     """``model.named_parameters()`` that also works on nn.DataParallel replicas: a replica's parameters are broadcast copies
     kept as plain (non-leaf) tensors in ``_former_parameters`` and ``parameters()`` is empty there (torch/nn/parallel/replicate.py)."""
@@ -126,9 +95,7 @@ class Engine:
                     seq = self._conv_seq(name, n)
                     conv = seq[0]
                     if self.model.is_batchnorm:
-                        bn = seq[1]
-                        scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
-                        bias = ((conv.bias - bn.running_mean) * scale + bn.bias).float().contiguous()
+                        scale, bias = ops.bn_fold(seq[1], conv.bias)
                     else:  # unet.py:137-143: conv + ReLU only
                         scale, bias = None, conv.bias.detach().float().contiguous()
                     if name == "conv00" and n == 1 and self.first_layer_c4 and conv.weight.shape[1] <= 4:
@@ -155,8 +122,7 @@ class Engine:
                 cu = up.up.weight.shape[1]
                 if cu == 16 and up.up.weight.shape[0] == 32 and conv1.weight.shape[1] - cu <= 48:
                     # full-resolution node: the transposed conv is folded into the consuming conv (no U tensor, no deconv launch)
-                    comp, table = compose_deconv_conv(conv1.weight.detach().float()[:, :cu], up.up.weight.detach().float(), up.up.bias.detach().float(),
-                                                      conv1.bias.detach().float())
+                    comp, table = ops.compose_deconv_conv(conv1.weight, cu, up.up.weight, up.up.bias, conv1.bias)
                     klow = conv1.weight.shape[1] - cu
                     P[f"{name}.c1.fused"] = dict(w=ops.pack_weights_b2(conv1.weight.detach().float(), False, klow, k_begin=cu), bias=table,
                                                  low_w=ops.pack_weights(comp, 6, 9, 64, 64, 32), n_total=16, n_tile=ops.NTile(16, b2=True))
@@ -210,10 +176,16 @@ class Engine:
         return a
 
     # ------------------------------------------------------------------------------ forward
-    def _check_input(self, x: torch.Tensor):
-        if x.dtype != torch.float32:
-            raise ValueError("UNet_Nested expects float32 input (the reference runs fp32 NCHW)")
-        B, Cin, H, W = x.shape
+    def _check_input(self, x: torch.Tensor, channels_last: bool = False):
+        if x.dtype != torch.float32 and not (x.dtype == torch.uint8 and not self.model.training):
+            raise ValueError("UNet_Nested expects float32 input (the reference runs fp32 NCHW); eval mode also takes uint8 images (scaled by 1/255 "
+                             "like torchvision's ToTensor)")
+        if channels_last and x.dtype != torch.uint8:
+            raise ValueError("channels_last input is the uint8 image layout [B,H,W,C]; float32 input is NCHW like the reference's")
+        if channels_last:
+            B, H, W, Cin = x.shape
+        else:
+            B, Cin, H, W = x.shape
         if Cin != self.model.in_channels:
             raise ValueError(f"expected {self.model.in_channels} input channels, got {Cin}")
         if H % 8 or W % 8 or H < 8 or W < 8:
@@ -230,27 +202,31 @@ class Engine:
         # eval mode (trainer/trainer.py:200-210 runs it under set_grad_enabled(False)): inference kernels, no graph
         return self.forward_eval(x)
 
-    def forward_eval(self, x: torch.Tensor, heads: Sequence[int] = (0, 1, 2)):
+    def forward_eval(self, x: torch.Tensor, heads: Sequence[int] = (0, 1, 2), channels_last: bool = False):
         """Inference forward (BN folded, dropout off).  Returns the three sigmoid heat maps
-        (fp32 NCHW) — ``None`` for heads not requested."""
-        B, H, W = self._check_input(x)
+        (fp32 NCHW) — ``None`` for heads not requested.  The requested heat maps are slices of ONE tensor
+        ``self.last_heats`` [len(heads), B, classes, H, W] (one arg-max launch covers them all).
+        ``x``: float32 [B,C,H,W] like the reference, or uint8 images ([B,C,H,W], or [B,H,W,C] with ``channels_last``) that are
+        scaled by 1/255 on the device — torchvision's ToTensor (datasets/datasets_base.py:71-72) fused into the layout change."""
+        B, H, W = self._check_input(x, channels_last)
         x = x.contiguous()
         # the kernels, their TMA descriptors and the per-device shared-memory opt-in belong to the ENGINE's device, whatever the
         # calling thread's current device is (the reference works regardless of it)
         with torch.cuda.device(self.device):
-            return self._forward_eval(x, B, H, W, heads)
+            return self._forward_eval(x, B, H, W, heads, channels_last)
 
-    def _forward_eval(self, x: torch.Tensor, B: int, H: int, W: int, heads: Sequence[int]):
+    def _forward_eval(self, x: torch.Tensor, B: int, H: int, W: int, heads: Sequence[int], channels_last: bool = False):
         P = self.packed_eval()
         c4 = bool(P["conv00.c1"].get("c4"))
         A = self.arena(B, H, W, "eval4" if c4 else "eval")
         ncls = self.model.n_classes
-        if c4:
-            ops.nchw_to_nhwc4(x, A["x4"])
-            src = A["x4"]
+        src = A["x4"] if c4 else A["x16"]
+        if x.dtype == torch.uint8:
+            ops.u8_to_nhwc(x, src, channels_last)
+        elif c4:
+            ops.nchw_to_nhwc4(x, src)
         else:
-            ops.nchw_to_nhwc16(x, A["x16"])
-            src = A["x16"]
+            ops.nchw_to_nhwc16(x, src)
         for lvl, name in enumerate(ENCODER):
             h, w = H >> lvl, W >> lvl
             p1, p2 = P[f"{name}.c1"], P[f"{name}.c2"]
@@ -261,6 +237,10 @@ class Engine:
             if lvl < 3:
                 src = A[f"P{lvl}0"]
         heats: List[Optional[torch.Tensor]] = [None, None, None]
+        want = sorted(set(int(k) for k in heads))
+        self.last_heats = torch.empty(len(want), B, ncls, H, W, dtype=torch.float32, device=self.device)
+        for i, k in enumerate(want):
+            heats[k] = self.last_heats[i]
         for name in DECODER_ORDER:
             high, lows, lvl = DECODER[name]
             tag = name[-2:]
@@ -282,9 +262,8 @@ class Engine:
             out = A[f"X{tag}"]
             if name in HEAD_OF:
                 k = int(HEAD_OF[name][-1]) - 1
-                if k in heads:
+                if heats[k] is not None:
                     ph = P[HEAD_OF[name]]
-                    heats[k] = torch.empty(B, ncls, H, W, dtype=torch.float32, device=self.device)
                     head = (ph["w"], ph["b"], heats[k], None, None, 1.0)
                 if name == "up_concat03":
                     out = None  # X03 has no consumer besides its head

@@ -39,17 +39,31 @@ class InferenceSession:
     replays the captured forward + arg-max and returns ``(xy int32 [B,C,2], peak fp32 [B,C])`` on the
     device; ``heat`` holds the heat maps of the selected head.  ``run_many`` streams a sequence of
     host batches through two input buffers so that the H2D copy of batch k+1 overlaps the kernels
-    of batch k (the activation arena is shared: compute is serial on one stream)."""
+    of batch k (the activation arena is shared: compute is serial on one stream).
 
-    def __init__(self, model, B: int, H: int, W: int, head: int = 2, device="cuda", use_graph: bool = True):
-        self.model, self.head = model, head
+    ``head``: one head index (results as above), or a tuple such as ``(0, 1, 2)`` — everything ``UNet_Nested.forward`` returns
+    (models/unet.py:300) and the validation loop consumes (trainer/trainer.py:212-221): results are then
+    ``xy [len(head),B,C,2]`` / ``peak [len(head),B,C]`` / ``heat [len(head),B,C,H,W]``, one arg-max launch for all.
+    ``input``: "float32" (the reference's [B,C,H,W] fp32 tensors), or "uint8_nchw" / "uint8_nhwc": 8-bit images copied as bytes
+    (4x less host-to-device traffic) and scaled by 1/255 on the device like torchvision's ToTensor, which the reference applies on
+    the CPU before its H2D copy (datasets/datasets_base.py:71-72, trainer/trainer.py:109)."""
+
+    def __init__(self, model, B: int, H: int, W: int, head=2, device="cuda", use_graph: bool = True, input: str = "float32"):
+        if input not in ("float32", "uint8_nchw", "uint8_nhwc"):
+            raise ValueError("input must be 'float32', 'uint8_nchw' or 'uint8_nhwc'")
+        self.model, self.head, self.input = model, head, input
+        self.heads = tuple(head) if isinstance(head, (tuple, list)) else (int(head),)
+        if not self.heads or any(k not in (0, 1, 2) for k in self.heads) or list(self.heads) != sorted(set(self.heads)):
+            raise ValueError("head must be 0, 1, 2 or an increasing tuple of them")
         self.dev = _device(device)
         self.eng = _engine(model, self.dev)
         if model.training:
             raise RuntimeError("InferenceSession needs model.eval()")
         self.B = B
         self.use_graph = use_graph
-        self.xs = [torch.zeros(B, model.in_channels, H, W, dtype=torch.float32, device=self.dev) for _ in range(2)]
+        shape = (B, H, W, model.in_channels) if input == "uint8_nhwc" else (B, model.in_channels, H, W)
+        self.xs = [torch.zeros(shape, dtype=torch.float32 if input == "float32" else torch.uint8, device=self.dev) for _ in range(2)]
+        self.H, self.W = H, W
         self.out = [None, None]
         self.graphs = [None, None]
         self._capture()
@@ -80,17 +94,20 @@ class InferenceSession:
                 self._body(1)
             self._key = self.eng._param_key()
             self._P = self.eng.packed_eval()
-            H, W = self.xs[0].shape[2], self.xs[0].shape[3]
-            self._arena = self.eng.arena(self.B, H, W, "eval4" if self._P["conv00.c1"].get("c4") else "eval")
+            self._arena = self.eng.arena(self.B, self.H, self.W, "eval4" if self._P["conv00.c1"].get("c4") else "eval")
 
     # kernels per pass: nchw->nhwc, 8 encoder convs, 3 pools, 6 x (deconv + 2 convs), arg-max = 31
     def _body(self, i: int):
         n0 = ops.launch_count
         P = self.eng.packed_eval()
         self._pack_launches = ops.launch_count - n0
-        heats = self.eng.forward_eval(self.xs[i], heads=(self.head,))
-        xy, val = ops.argmax_peaks(heats[self.head])
-        self.out[i] = (xy, val, heats[self.head])
+        self.eng.forward_eval(self.xs[i], heads=self.heads, channels_last=self.input == "uint8_nhwc")
+        heat = self.eng.last_heats  # [len(heads), B, C, H, W]
+        xy, val = ops.argmax_peaks(heat.view(-1, *heat.shape[2:]))
+        if isinstance(self.head, (tuple, list)):
+            self.out[i] = (xy.view(len(self.heads), self.B, -1, 2), val.view(len(self.heads), self.B, -1), heat)
+        else:
+            self.out[i] = (xy, val, heat[0])
 
     @property
     def x(self):

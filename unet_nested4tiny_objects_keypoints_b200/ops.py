@@ -235,6 +235,45 @@ def nchw_to_nhwc4(x: torch.Tensor, out: torch.Tensor) -> None:
         _lib.check(lib().unpp_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, Cin, H, W, 4, _stream()), "unpp_nchw_to_nhwc")
 
 
+def bn_fold(bn, conv_bias: torch.Tensor):
+    """Eval-mode nn.BatchNorm2d folded into the conv in front of it: (scale fp32 [C] for pack_weights, bias fp32 [C])."""
+    c = conv_bias.numel()
+    out = torch.empty(2, c, dtype=torch.float32, device=conv_bias.device)
+    _count()
+    _lib.check(lib().unpp_bn_fold(bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(), conv_bias.data_ptr(), float(bn.eps), c,
+                                  out[0].data_ptr(), out[1].data_ptr(), _stream()), "unpp_bn_fold")
+    return out[0], out[1]
+
+
+def compose_deconv_conv(w_conv: torch.Tensor, cu: int, w_up: torch.Tensor, b_up: torch.Tensor, b_conv: torch.Tensor):
+    """conv3x3(ConvTranspose2d_k2s2(x)) as one 3x3 conv over the low-resolution x (unpp_compose_deconv_conv): returns the composed
+    weight fp32 [4*Co, Ci, 3, 3] and the (row class, column class) bias table fp32 [9, Co]."""
+    w_conv, w_up, b_up, b_conv = (t.detach().float().contiguous() for t in (w_conv, w_up, b_up, b_conv))
+    co, ctot, ci = w_conv.shape[0], w_conv.shape[1], w_up.shape[0]
+    assert w_up.shape[1] == cu and b_up.numel() == cu and b_conv.numel() == co and w_conv.is_cuda
+    comp = torch.empty(4 * co, ci, 3, 3, dtype=torch.float32, device=w_conv.device)
+    table = torch.empty(9, co, dtype=torch.float32, device=w_conv.device)
+    _count()
+    _lib.check(lib().unpp_compose_deconv_conv(w_conv.data_ptr(), ctot, cu, w_up.data_ptr(), b_up.data_ptr(), b_conv.data_ptr(), co, ci, comp.data_ptr(),
+                                              table.data_ptr(), _stream()), "unpp_compose_deconv_conv")
+    return comp, table
+
+
+def u8_to_nhwc(x: torch.Tensor, out: torch.Tensor, channels_last: bool) -> None:
+    """uint8 images ([B,H,W,C] when ``channels_last`` else [B,C,H,W]) -> bf16 NHWC [B,H,W,Cpad] (Cpad = out.shape[-1] in {4,16}) scaled by 1/255
+    like torchvision's ToTensor (datasets/datasets_base.py:71-72)."""
+    assert x.dtype == torch.uint8 and x.is_cuda and x.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+    if channels_last:
+        B, H, W, Cin = x.shape
+    else:
+        B, Cin, H, W = x.shape
+    cpad = out.shape[-1]
+    assert tuple(out.shape) == (B, H, W, cpad)
+    _count()
+    with _Traced("u8_to_nhwc%d" % cpad, x.numel() + out.numel() * 2, 0):
+        _lib.check(lib().unpp_u8_to_nhwc(x.data_ptr(), out.data_ptr(), B, Cin, H, W, cpad, int(channels_last), _stream()), "unpp_u8_to_nhwc")
+
+
 def pack_weights_c4(src: torch.Tensor, scale=None) -> torch.Tensor:
     """Weights [16][Cin <= 4][3][3] of the network's first conv for the 4-channel first-layer mode (unpp.h kind 7)."""
     return pack_weights(src, 7, 4, 64, 64, 32, scale=scale)
