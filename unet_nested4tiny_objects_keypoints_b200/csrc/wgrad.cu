@@ -1,5 +1,11 @@
-// wgrad.cu — weight gradient of the 3x3 convs (and, with taps = 1 and a strided dZ view, of the
-// k2s2 transposed convs) as an implicit GEMM whose reduction dimension is the pixel grid:
+// wgrad.cu — unpp_wgrad entry point + the POINTWISE weight-gradient kernel.
+//
+// Every 3x3 conv and every transposed conv of the network goes to the tcgen05 kernel (wgrad_tc.cu).  The kernel of this file serves
+// what is left: taps = 1 shapes — the 1x1 conv of the is_deconv=False variant (models/unet.py:189-191) and single taps of a
+// transposed conv through a strided dZ view — HBM-bound GEMMs whose few hundred outputs live in registers; a 3x3 shape the
+// tcgen05 kernel cannot take is rejected (UNPP_ERR_UNSUPPORTED), never re-routed.  (The template still carries its 3x3
+// instantiation: tests/test_kernels_gpu.py uses none of it through the C ABI.)  The arithmetic, as an implicit GEMM whose
+// reduction dimension is the pixel grid:
 //
 //     dW[tap][ci][co] = sum_{n,y,x} X[n, y + r - 1, x + s - 1, ci] * dZ[n, y, x, co]
 //
@@ -271,6 +277,7 @@ int launch(const WgradParams& p, const Plan& pl, cudaStream_t stream) {
 
 extern "C" int unpp_wgrad_grid(const UnppWgradArgs* a) {
   if (a && a->nsrc >= 1 && a->nsrc <= UNPP_MAX_SRC && a->N >= 1 && a->H >= 1 && a->W >= 1 && unpp::wgrad_tc_eligible(a)) return unpp::wgrad_tc_grid(a);
+  if (a && a->taps != 1) return unpp::fail(UNPP_ERR_UNSUPPORTED, "wgrad: 3x3 shape not supported by the tcgen05 weight-gradient kernel (channels must be 16/32/64/128)");
   Plan pl;
   int rc = make_plan(a, &pl);
   return rc ? rc : pl.grid_x;
@@ -284,7 +291,11 @@ extern "C" int unpp_wgrad(const UnppWgradArgs* a, unpp_stream_t stream_) {
   if ((reinterpret_cast<uintptr_t>(a->dz) & 15)) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: dz pointer unaligned");
   for (int i = 0; i < a->nsrc; ++i)
     if (!a->src[i] || (reinterpret_cast<uintptr_t>(a->src[i]) & 15)) return unpp::fail(UNPP_ERR_BAD_ARG, "wgrad: source pointer null or unaligned");
-  if (unpp::wgrad_tc_eligible(a)) return unpp::wgrad_tc_launch(a, stream);  // tcgen05 path (every dense 3x3 shape of the network)
+  if (unpp::wgrad_tc_eligible(a)) return unpp::wgrad_tc_launch(a, stream);  // tcgen05 path: every 3x3 conv and every transposed conv of the network
+  // What is left for the kernel of this file: POINTWISE weight gradients (taps = 1: the 1x1 conv of the is_deconv=False variant,
+  // models/unet.py:189-191, and single taps of a transposed conv) — HBM-bound GEMMs with K = pixels and a few hundred outputs.
+  // A 3x3 shape the tcgen05 kernel rejects is an error, not a silent change of kernel.
+  if (a->taps != 1) return unpp::fail(UNPP_ERR_UNSUPPORTED, "wgrad: 3x3 shape not supported by the tcgen05 weight-gradient kernel (channels must be 16/32/64/128)");
   Plan pl;
   if (int rc = make_plan(a, &pl)) return rc;
   EncodeTiledFn enc = get_encode();

@@ -396,12 +396,6 @@ void make_plan(const UnppWgradArgs* a, Plan* pl) {
 namespace unpp {
 
 bool wgrad_tc_eligible(const UnppWgradArgs* a) {
-  static int legacy = -1;  // UNPP_WGRAD_LEGACY=1 forces the mma.sync kernel (A/B measurements); read once
-  if (legacy < 0) {
-    const char* e = getenv("UNPP_WGRAD_LEGACY");
-    legacy = (e && e[0] == '1') ? 1 : 0;
-  }
-  if (legacy) return false;
   Plan pl;
   make_plan(a, &pl);
   return pl.ok;

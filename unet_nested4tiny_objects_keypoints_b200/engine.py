@@ -221,6 +221,7 @@ class Engine:
         A = self.arena(B, H, W, "eval4" if c4 else "eval")
         ncls = self.model.n_classes
         src = A["x4"] if c4 else A["x16"]
+        ops.tag("input")
         if x.dtype == torch.uint8:
             ops.u8_to_nhwc(x, src, channels_last)
         elif c4:
@@ -230,8 +231,10 @@ class Engine:
         for lvl, name in enumerate(ENCODER):
             h, w = H >> lvl, W >> lvl
             p1, p2 = P[f"{name}.c1"], P[f"{name}.c2"]
+            ops.tag(f"{name}.c1")
             ops.conv([src], B, h, w, p1["w"], p1["n_total"], p1["n_tile"], 9, bias=p1["bias"], relu=True, out=A[f"{name}.a"])
             # MaxPool2d(2) (unet.py:219,258,260,262) is written by the conv's own epilogue
+            ops.tag(f"{name}.c2")
             ops.conv([A[f"{name}.a"]], B, h, w, p2["w"], p2["n_total"], p2["n_tile"], 9, bias=p2["bias"], relu=True, out=A[f"X{lvl}0"],
                      pooled=A[f"P{lvl}0"] if lvl < 3 else None)
             if lvl < 3:
@@ -247,6 +250,7 @@ class Engine:
             h, w = H >> lvl, W >> lvl
             pu, p1, p2 = P[f"{name}.up"], P[f"{name}.c1"], P[f"{name}.c2"]
             pf = P.get(f"{name}.c1.fused")
+            ops.tag(f"up{tag}.c1")
             if pf is not None and self.fuse_deconv:
                 ops.conv([A[l] for l in lows], B, h, w, pf["w"], 16, pf["n_tile"], 9, bias=pf["bias"], bias_classes=9, relu=True, out=A[f"{name}.a"],
                          lowres=(A[high], pf["low_w"]))
@@ -260,6 +264,7 @@ class Engine:
                           out=A[f"{name}.a"])
             head = None
             out = A[f"X{tag}"]
+            ops.tag(f"up{tag}.c2")
             if name in HEAD_OF:
                 k = int(HEAD_OF[name][-1]) - 1
                 if heats[k] is not None:
@@ -270,6 +275,7 @@ class Engine:
                     if head is None:
                         continue
             ops.conv([A[f"{name}.a"]], B, h, w, p2["w"], p2["n_total"], p2["n_tile"], 9, bias=p2["bias"], relu=True, out=out, head=head)
+        ops.tag("")
         return tuple(heats)
 
     @torch.no_grad()

@@ -318,7 +318,14 @@ class FusedTrainStep:
             if self.world == 1:
                 self._update()
         if self.world > 1:
+            ev = getattr(self, "allreduce_events", None)  # bench.py: a list that receives one (before, after) CUDA-event pair per step
+            if ev is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             parallel.allreduce_gradients(self.flat_g, self.pg)  # the step's only collective: 2.2 MB flat fp32 buffer
+            if ev is not None:
+                e1.record()
+                ev.append((e0, e1))
             if self.graph_b is not None:
                 self.graph_b.replay()
             else:

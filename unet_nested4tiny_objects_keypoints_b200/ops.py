@@ -27,7 +27,8 @@ W_SMEM_BUDGET = int(os.environ.get("UNPP_WBUDGET", 148 * 1024))
 #   _tls.reduce_queue — when a list: reductions called with defer=True are queued for ONE unpp_reduce_batched launch
 _tls = threading.local()
 launch_count = 0   # kernels of libunpp.so enqueued through this module (bench.py reads it for "gpu_launches")
-trace = None       # when a list: conv()/wgrad() append (label, start_event, end_event, algorithmic_bytes, flops)
+trace = None       # when a list: every wrapper appends (label, start_event, end_event, bytes the launch moves, flops, plan-row tag)
+trace_tag = ""     # row of the fused plan the following launches belong to, e.g. "up01.c1" (set by the engine; read by bench.py)
 
 
 def _stream() -> int:
@@ -53,7 +54,13 @@ class _Traced:
     def __exit__(self, *exc):
         if trace is not None:
             self.e1.record()
-            trace.append((self.label, self.e0, self.e1, self.nbytes, self.flops))
+            trace.append((self.label, self.e0, self.e1, self.nbytes, self.flops, trace_tag))
+
+
+def tag(name: str) -> None:
+    """Name the plan row of the launches that follow (only read while tracing; a plain global store otherwise)."""
+    global trace_tag
+    trace_tag = name
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:

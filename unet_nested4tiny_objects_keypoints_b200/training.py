@@ -247,6 +247,7 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
     B, H, W = ts.B, ts.H, ts.W
     ncls = m.n_classes
     ts.generation += 1  # the saved activations now belong to this forward
+    ops.tag("fwd")
     if update_running_stats:
         eng._packed_key = None  # running statistics change below without a torch version bump: drop the eval-mode fold cache
     ops.nchw_to_nhwc16(x, t["x16"])
@@ -339,6 +340,7 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
     # Reductions whose result only the optimizer reads (weight / bias gradients) are queued and run as ONE batched
     # launch at the end of the backward pass; each therefore owns its partial buffer (keyed by the parameter name).
     ops.begin_reduce_queue()
+    ops.tag("bwd")
 
     def stats_buf(srcs_C, n_total, nt, taps, h, w, key="stats"):
         g = ops.conv_grid(srcs_C, B, h, w, n_total, nt, taps)
