@@ -182,6 +182,12 @@ int unpp_argmax_peaks(const float* heat, int planes, int H, int W, int32_t* xy, 
  * (1 = one CTA per plane already fills the GPU; then the call is unpp_argmax_peaks and workspace may be NULL). */
 int unpp_argmax_peaks_split(const float* heat, int planes, int H, int W, int32_t* xy, float* val, void* workspace, int splits, unpp_stream_t stream);
 int unpp_argmax_splits(int planes, int H, int W);
+/* The multi-point form of Heatmap.extract_points_ (tools/misc/heatmap.py:148-208: threshold, regions, every region's maximum,
+ * brightest `num` first, one retry at 0.9 x threshold): the `num` best strict local maxima (8-neighbourhood, order = value
+ * descending then index ascending) of heat >= threshold per plane.  xy int32 [planes][num][2] as {x, y} (-1, -1 when a plane has
+ * fewer peaks), val fp32 [planes][num], count int32 [planes].  Equal to the reference's point set on separated blobs; the
+ * OpenCV watershed itself is host code outside the path. */
+int unpp_topk_peaks(const float* heat, int planes, int H, int W, int num, float threshold, int32_t* xy, float* val, int32_t* count, unpp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Training step.  Reference counterparts: autograd of models/unet.py:255-300 (cuDNN dgrad/wgrad,

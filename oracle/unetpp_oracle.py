@@ -317,6 +317,45 @@ def argmax_keypoints(heat: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     return xy, val
 
 
+def topk_peaks(heat: np.ndarray, num: int, threshold: float = 0.5):
+    """The multi-point form of Heatmap.extract_points_ (heatmap.py:148-208) with the OpenCV watershed replaced by its effect on
+    separated blobs: threshold the plane (heatmap.py:158), take the strict local maxima of the 8-neighbourhood under the order
+    (value descending, index ascending) as the regions' maxima (heatmap.py:165-166: ``np.max`` per region, first index, 173-176),
+    sort brightest first (heatmap.py:167) and keep ``num`` (heatmap.py:170); one retry at 0.9 x threshold (heatmap.py:187-190).
+    Returns (xy int32 [B,C,num,2] as [x,y], -1 padded; value [B,C,num]; count [B,C]).  tests/golden/unetpp_r2.* pins it against the
+    real ``Heatmap.extract_points_`` (cv2) on synthetic targets."""
+    heat = np.asarray(heat)
+    B, C, H, W = heat.shape
+    xy = -np.ones((B, C, num, 2), dtype=np.int32)
+    val = np.zeros((B, C, num), dtype=heat.dtype)
+    cnt = np.zeros((B, C), dtype=np.int32)
+    for b in range(B):
+        for c in range(C):
+            h = heat[b, c]
+            for thr in (threshold, np.float32(threshold) * np.float32(0.9)):
+                cands = []
+                ys, xs = np.where(h >= thr)
+                for y, x in zip(ys.tolist(), xs.tolist()):
+                    v, p, ok = h[y, x], y * W + x, True
+                    for dy in (-1, 0, 1):
+                        for dx in (-1, 0, 1):
+                            yy, xx = y + dy, x + dx
+                            if (dy or dx) and 0 <= yy < H and 0 <= xx < W:
+                                u, q = h[yy, xx], yy * W + xx
+                                if u > v or (u == v and q < p):
+                                    ok = False
+                    if ok:
+                        cands.append((-float(v), p))
+                if cands:
+                    cands.sort()
+                    for r, (nv, p) in enumerate(cands[:num]):
+                        xy[b, c, r] = (p % W, p // W)
+                        val[b, c, r] = h[p // W, p % W]
+                    cnt[b, c] = min(num, len(cands))
+                    break
+    return xy, val, cnt
+
+
 def create_heatmap(target: np.ndarray, image_height: int, image_width: int) -> np.ndarray:
     """helper.create_heatmap (helper.py:87-172): 7 keypoints -> 4 channels, groups {0},{1,2,3},{4},{5,6};
     per point ``exp(-0.5 * dist / 3)`` with dist the Euclidean DISTANCE (not squared); channels 1 and 3

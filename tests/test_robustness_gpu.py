@@ -170,3 +170,43 @@ def test_dataparallel_eval_sees_a_load_state_dict_between_two_forwards():
     with torch.no_grad():
         b = dp(x.cuda())[2].cpu()
     assert float((b - O.forward(sd2, x)[2]).abs().max()) <= 3e-2
+
+
+def test_topk_peaks_kernel_matches_the_oracle():
+    """unpp_topk_peaks (the multi-point form of Heatmap.extract_points_, tools/misc/heatmap.py:148-208) bit for bit against the oracle
+    restatement, which tests/test_oracle_golden.py pins against the real reference: fixture planes, noisy planes with hundreds of
+    local maxima, plateaus, empty planes, the retry threshold."""
+    import json, os
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    arr = dict(np.load(os.path.join(g, "unetpp_r2.npz")))
+    cases = [(torch.from_numpy(arr["peaks_planes"]), 3, 0.5), (torch.from_numpy(arr["peaks_low"]), 2, 0.5)]
+    gen = torch.Generator().manual_seed(4)
+    noisy = torch.rand(2, 3, 40, 56, generator=gen)          # ~ 1/9 of the pixels above 0.5 are local maxima
+    noisy[0, 0] = 0.25                                         # nothing above either threshold
+    noisy[0, 1] = 0.75                                         # one plateau: a single peak at index 0
+    noisy[1, 2, 5:9, 7:12] = 2.0                               # a rectangular plateau inside noise
+    cases += [(noisy, 5, 0.5), (noisy, 1, 0.9), (torch.rand(1, 2, 1024, 1024, generator=gen), 4, 0.99)]
+    for heat, num, thr in cases:
+        xy, val, cnt = ops.topk_peaks(heat.cuda(), num, thr)
+        rxy, rval, rcnt = O.topk_peaks(heat.numpy(), num, thr) if heat.shape[-1] <= 64 else (None, None, None)
+        if rxy is None:  # large planes: the python oracle is too slow; check against a torch restatement of the same definition
+            h = heat.cuda()
+            pad = torch.nn.functional.pad(h, (1, 1, 1, 1), value=-1.0)
+            idx = torch.arange(h.shape[2] * h.shape[3], device="cuda").view(1, 1, *h.shape[2:]).expand_as(h)
+            pidx = torch.nn.functional.pad(idx.float(), (1, 1, 1, 1), value=1e12)
+            ok = h >= thr
+            for dy in range(3):
+                for dx in range(3):
+                    if dy == 1 and dx == 1:
+                        continue
+                    u, q = pad[:, :, dy:dy + h.shape[2], dx:dx + h.shape[3]], pidx[:, :, dy:dy + h.shape[2], dx:dx + h.shape[3]]
+                    ok &= ~((u > h) | ((u == h) & (q < idx)))
+            for b in range(h.shape[0]):
+                for c in range(h.shape[1]):
+                    v = torch.where(ok[b, c], h[b, c], torch.full_like(h[b, c], -1.0)).flatten()
+                    order = torch.argsort(-v.double() * 1e7 + torch.arange(v.numel(), device="cuda").double() * 1e-3)[:num]  # value desc, index asc
+                    n = int((v[order] >= 0).sum())
+                    assert int(cnt[b, c]) == n
+                    assert torch.equal(xy[b, c, :n, 0].long(), order[:n] % h.shape[3]) and torch.equal(xy[b, c, :n, 1].long(), order[:n] // h.shape[3])
+            continue
+        assert np.array_equal(cnt.cpu().numpy(), rcnt) and np.array_equal(xy.cpu().numpy(), rxy) and np.array_equal(val.cpu().numpy(), rval)

@@ -116,6 +116,7 @@ _SIGNATURES = {
     "unpp_argmax_peaks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "unpp_argmax_peaks_split": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "unpp_argmax_splits": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "unpp_topk_peaks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "unpp_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "unpp_wgrad_grid": (C.c_int, [C.POINTER(WgradArgs)]),
     "unpp_wgrad_reduce": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_long, C.c_long, C.c_long,

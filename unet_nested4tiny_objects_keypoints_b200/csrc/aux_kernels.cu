@@ -394,6 +394,87 @@ __global__ void __launch_bounds__(128) argmax_fold_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------
+// Top-`num` peaks of a heat-map plane: the multi-point form of Heatmap.extract_points_ (tools/misc/heatmap.py:148-208), which
+// thresholds the plane at 0.5, splits it into regions (OpenCV watershed), takes every region's maximum (first index), sorts the
+// regions by that maximum, brightest first, and keeps `num` of them — retrying once at 0.9 x threshold when nothing is found.
+// Here a region's representative is a strict local maximum of the thresholded plane under the total order (value desc, index
+// asc) over its 8-neighbourhood: for separated blobs (what the targets of helper.create_heatmap look like) this is the same
+// point set in the same order; touching blobs that the watershed would cut and a plain maximum search would merge keep one
+// peak each as long as each has its own local maximum.  One CTA per plane, `num` selection rounds over the (L2-resident) plane:
+// round r takes the best peak that comes after the (r-1)-th in the order, so nothing is stored and nothing can overflow.
+__device__ __forceinline__ bool peak_at(const float* __restrict__ h, int H, int W, int p, float v) {
+  const int y = p / W, x = p - y * W;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      if (!dy && !dx) continue;
+      const int yy = y + dy, xx = x + dx;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const int q = yy * W + xx;
+      const float u = __ldg(h + q);
+      if (u > v || (u == v && q < p)) return false;
+    }
+  }
+  return true;
+}
+__global__ void __launch_bounds__(256) topk_peaks_kernel(const float* __restrict__ heat, int H, int W, int num, float threshold, int32_t* __restrict__ xy,
+                                                         float* __restrict__ val, int32_t* __restrict__ count) {
+  unpp::pdl_wait();
+  unpp::pdl_trigger();
+  const int HW = H * W;
+  const float* h = heat + size_t(blockIdx.x) * HW;
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  __shared__ float s_lastv;
+  __shared__ int s_lasti;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int found = 0;
+  for (int attempt = 0; attempt < 2 && found == 0; ++attempt) {
+    const float thr = attempt ? threshold * 0.9f : threshold;  // heatmap.py:187-190: one retry on a lower threshold
+    float lastv = INFINITY;
+    int lasti = -1;
+    for (int r = 0; r < num; ++r) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+        const float v = __ldg(h + p);
+        if (!(v >= thr)) continue;                                     // heatm[heatm < threshold] = 0 (heatmap.py:158)
+        if (!(v < lastv || (v == lastv && p > lasti))) continue;      // strictly after the previous pick in (value desc, index asc)
+        if (!(v > bv || (v == bv && p < bi))) continue;               // not better than what this thread already holds
+        if (peak_at(h, H, W, p, v)) bv = v, bi = p;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        take(bv, bi, ov, oi);
+      }
+      if (lane == 0) sv[warp] = bv, si[warp] = bi;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) take(bv, bi, sv[k], si[k]);
+        s_lastv = bv, s_lasti = bi;
+      }
+      __syncthreads();
+      lastv = s_lastv, lasti = s_lasti;
+      __syncthreads();
+      if (lasti == 0x7fffffff) break;  // no further peak
+      if (threadIdx.x == 0) {
+        xy[(size_t(blockIdx.x) * num + r) * 2] = lasti % W;      // x first (heatmap.py:178)
+        xy[(size_t(blockIdx.x) * num + r) * 2 + 1] = lasti / W;
+        val[size_t(blockIdx.x) * num + r] = lastv;
+      }
+      ++found;
+    }
+  }
+  if (threadIdx.x == 0) {
+    count[blockIdx.x] = found;
+    for (int r = found; r < num; ++r) xy[(size_t(blockIdx.x) * num + r) * 2] = xy[(size_t(blockIdx.x) * num + r) * 2 + 1] = -1, val[size_t(blockIdx.x) * num + r] = 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Target heat-map synthesis of the reference trainer (tools/misc/helper.py:87-172, called on the CPU every
 // step at trainer/trainer.py:122-123): 7 key points -> 4 planes, point groups {0}, {1,2,3}, {4}, {5..};
 // per point exp(-0.5 * dist / 3) with the Euclidean DISTANCE (not squared) in float64; planes 0 and 2 are
@@ -580,6 +661,15 @@ extern "C" int unpp_create_heatmap(const float* keypoints, int N, int npts, int 
   if (npts < 6 || npts > 9) return unpp::fail(UNPP_ERR_UNSUPPORTED, "create_heatmap: the reference's grouping needs 6..9 key points (7 in the trainer)");
   unpp::launch(create_heatmap_kernel, N * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream), keypoints, npts, H, W, out);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("create_heatmap: launch");
+  return UNPP_OK;
+}
+
+extern "C" int unpp_topk_peaks(const float* heat, int planes, int H, int W, int num, float threshold, int32_t* xy, float* val, int32_t* count, unpp_stream_t stream) {
+  if (!heat || !xy || !val || !count || planes < 0 || H < 1 || W < 1 || num < 1 || num > 64) return unpp::fail(UNPP_ERR_BAD_ARG, "topk_peaks: bad argument (1 <= num <= 64)");
+  if (long(H) * W > 0x7ffffff0L) return unpp::fail(UNPP_ERR_UNSUPPORTED, "topk_peaks: plane too large");
+  if (planes == 0) return UNPP_OK;
+  unpp::launch(topk_peaks_kernel, planes, 256, 0, reinterpret_cast<cudaStream_t>(stream), heat, H, W, num, threshold, xy, val, count);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("topk_peaks: launch");
   return UNPP_OK;
 }
 

@@ -656,7 +656,11 @@ extern "C" int unpp_head_bwd(const float* heat, const float* dheat, const float*
     case 2: LAUNCH(2); break;
     case 3: LAUNCH(3); break;
     case 4: LAUNCH(4); break;
-    default: return unpp::fail(UNPP_ERR_UNSUPPORTED, "head_bwd: 1..4 classes supported");
+    case 5: LAUNCH(5); break;
+    case 6: LAUNCH(6); break;
+    case 7: LAUNCH(7); break;
+    case 8: LAUNCH(8); break;
+    default: return unpp::fail(UNPP_ERR_UNSUPPORTED, "head_bwd: 1..8 classes supported");
   }
 #undef LAUNCH
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("head_bwd: launch");

@@ -316,6 +316,23 @@ def argmax_peaks(heat: torch.Tensor):
     return xy, val
 
 
+def topk_peaks(heat: torch.Tensor, num: int, threshold: float = 0.5):
+    """fp32 [B,C,H,W] -> (xy int32 [B,C,num,2] as [x,y] (-1 where a plane has fewer peaks), peak fp32 [B,C,num], count int32 [B,C]):
+    the ``num`` brightest local maxima above ``threshold`` per plane — Heatmap.extract_points_(pred, num) of tools/misc/heatmap.py:148-208."""
+    if heat.dtype != torch.float32 or not heat.is_cuda or heat.dim() != 4:
+        raise ValueError("topk_peaks expects an fp32 CUDA tensor [B,C,H,W]")
+    heat = heat.contiguous()
+    B, Cc, H, W = heat.shape
+    xy = torch.empty(B, Cc, num, 2, dtype=torch.int32, device=heat.device)
+    val = torch.empty(B, Cc, num, dtype=torch.float32, device=heat.device)
+    cnt = torch.empty(B, Cc, dtype=torch.int32, device=heat.device)
+    _count()
+    with _Traced("topk_peaks", heat.numel() * 4, 0):
+        _lib.check(lib().unpp_topk_peaks(heat.data_ptr(), B * Cc, H, W, int(num), float(threshold), xy.data_ptr(), val.data_ptr(), cnt.data_ptr(), _stream()),
+                   "unpp_topk_peaks")
+    return xy, val, cnt
+
+
 # ---------------------------------------------------------------------------------------------- training
 def _wgrad_args(srcs, N, H, W, dz, cout, taps, dz_view=None) -> WgradArgs:
     a = WgradArgs()
