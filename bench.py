@@ -429,12 +429,12 @@ def bench_eager_dropin(args, local, steps=5):
     moved to the CPU, FocalLoss_BCE_2d there, mean of three, backward (the upstream gradients travel back H2D), AdamW.step().
     Targets are precomputed (the trainer's numpy target synthesis, helper.create_heatmap, is host code outside the path).  Wall clock with
     a device synchronize per run — the loop is host-bound by construction.  Second figure: the same with the loss left on the device."""
-    import unet_nested4tiny_objects_keypoints_b200 as pkg
+    from unet_nested4tiny_objects_keypoints_b200 import optimizers
     dev = torch.device("cuda", local)
     res = {}
     for where in ("trainer_as_shipped_loss_on_cpu", "loss_on_device"):
         model = make_model(True, dev)
-        opt = pkg.optimizers.AdamW(model.parameters(), lr=3e-6, weight_decay=1e-4)  # train.py:38-45 defaults
+        opt = optimizers.AdamW(model.parameters(), lr=3e-6, weight_decay=1e-4)  # train.py:38-45 defaults
         g = torch.Generator().manual_seed(5)
         x_host = torch.randn(TRAIN_B1, 3, 256, 256, generator=g).pin_memory()
         t_host = torch.rand(TRAIN_B1, 4, 256, 256, generator=g)

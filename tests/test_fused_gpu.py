@@ -188,3 +188,54 @@ def test_pipelined_sessions_equal_the_sequential_calls():
         losses.append((out, step.flat_p.clone()))
     assert losses[0][0] == losses[1][0]
     assert torch.equal(losses[0][1], losses[1][1])
+
+
+@pytest.mark.parametrize("opt", ["adamw", "sgd"])
+def test_tar_checkpoint_resume_round_trip(tmp_path, opt):
+    """trainer/trainer.py:402-413: a ``.tar`` with model_state_dict / optimizer_state_dict / epoch.  Three uninterrupted fused steps ==
+    two steps, save, a NEW model + step restored from the file, one more step (bit for bit: weights, moments, step count, dropout
+    stream); and the optimizer state loads into the matching torch-style optimizer (the format the reference trainer expects)."""
+    sd = O.synth_state_dict(seed=71)
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 2, 32, 32
+    xs = [torch.randn(B, 3, H, W, generator=g).pin_memory() for _ in range(3)]
+    ts = [torch.rand(B, 4, H, W, generator=g).pin_memory() for _ in range(3)]
+
+    def fresh():
+        m = pkg.UNet_Nested()
+        m.load_state_dict(sd)
+        m = m.cuda().train()
+        return m, fused.FusedTrainStep(m, B, H, W, lr=1e-3, weight_decay=1e-2, optimizer=opt, momentum=0.9, loss="focal", seed=5)
+
+    m_a, st_a = fresh()
+    for k in range(3):
+        st_a.step(xs[k], ts[k])
+    m_b, st_b = fresh()
+    for k in range(2):
+        st_b.step(xs[k], ts[k])
+    path = str(tmp_path / "ck.tar")
+    st_b.save_checkpoint(path, epoch=7)
+    m_c, st_c = fresh()
+    assert st_c.load_checkpoint(path) == 8
+    st_c.step(xs[2], ts[2])
+    torch.cuda.synchronize()
+    assert torch.equal(st_c.flat_p, st_a.flat_p) and torch.equal(st_c.flat_m, st_a.flat_m) and torch.equal(st_c.flat_v, st_a.flat_v)
+    assert int(st_c.step_counter) == 3
+    for (k, a), b in zip(m_a.state_dict().items(), m_c.state_dict().values()):
+        assert torch.equal(a, b), k
+    # the file is what the reference trainer resumes from: plain keys, and the optimizer state loads into a torch-style optimizer
+    ck = torch.load(path)
+    assert set(ck) == {"epoch", "model_state_dict", "optimizer_state_dict"} and list(ck["model_state_dict"]) == list(sd)
+    from unet_nested4tiny_objects_keypoints_b200 import optimizers
+    m_d = pkg.UNet_Nested().cuda()
+    o = optimizers.AdamW(m_d.parameters(), lr=1e-3, weight_decay=1e-2) if opt == "adamw" else torch.optim.SGD(m_d.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-2)
+    o.load_state_dict(ck["optimizer_state_dict"])
+    st0 = o.state[next(iter(m_d.parameters()))]
+    if opt == "adamw":
+        assert st0["step"] == 2 and torch.equal(st0["exp_avg"].reshape(-1), st_b.flat_m[:st0["exp_avg"].numel()])
+    else:
+        assert torch.equal(st0["momentum_buffer"].reshape(-1), st_b.flat_m[:st0["momentum_buffer"].numel()])
+    # ... and the other way round: a state saved by that optimizer resumes in the fused step
+    st_e = fresh()[1]
+    st_e.load_optimizer_state_dict(o.state_dict())
+    assert torch.equal(st_e.flat_m, st_b.flat_m) and int(st_e.step_counter) >= 1

@@ -203,10 +203,11 @@ def test_topk_peaks_kernel_matches_the_oracle():
                     ok &= ~((u > h) | ((u == h) & (q < idx)))
             for b in range(h.shape[0]):
                 for c in range(h.shape[1]):
-                    v = torch.where(ok[b, c], h[b, c], torch.full_like(h[b, c], -1.0)).flatten()
-                    order = torch.argsort(-v.double() * 1e7 + torch.arange(v.numel(), device="cuda").double() * 1e-3)[:num]  # value desc, index asc
-                    n = int((v[order] >= 0).sum())
+                    cand = torch.nonzero(ok[b, c].flatten()).flatten()                     # candidates in index order
+                    _, o = torch.sort(h[b, c].flatten()[cand], descending=True, stable=True)  # value desc, ties keep the index order
+                    order = cand[o][:num]
+                    n = order.numel()
                     assert int(cnt[b, c]) == n
-                    assert torch.equal(xy[b, c, :n, 0].long(), order[:n] % h.shape[3]) and torch.equal(xy[b, c, :n, 1].long(), order[:n] // h.shape[3])
+                    assert torch.equal(xy[b, c, :n, 0].long(), order % h.shape[3]) and torch.equal(xy[b, c, :n, 1].long(), order // h.shape[3])
             continue
         assert np.array_equal(cnt.cpu().numpy(), rcnt) and np.array_equal(xy.cpu().numpy(), rxy) and np.array_equal(val.cpu().numpy(), rval)

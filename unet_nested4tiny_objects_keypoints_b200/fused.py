@@ -394,5 +394,72 @@ class FusedTrainStep:
     def heats(self):
         return self.ts.heats
 
+    # ------------------------------------------------------------------------------ checkpoint / resume (trainer/trainer.py:402-413)
+    def optimizer_state_dict(self) -> dict:
+        """The flat optimizer state in the layout ``torch.optim.Optimizer.state_dict()`` gives the reference's optimizers
+        (tools/optimizers/adamw.py:60-68: per parameter ``step`` / ``exp_avg`` / ``exp_avg_sq``; SGD-family: ``momentum_buffer``), so a
+        ``.tar`` written here resumes under the reference trainer (``optimizer.load_state_dict(checkpoint['optimizer_state_dict'])``,
+        trainer.py:411) and a ``.tar`` written by it resumes here."""
+        step = int(self.step_counter.item())
+        adam = self.optimizer in ("adamw", "adam", "adabound")
+        state = {}
+        for i, (name, p) in enumerate(self.model.named_parameters()):
+            off, n = self.ts.lay[name]
+            if adam:
+                state[i] = {"step": step, "exp_avg": self.flat_m[off:off + n].view_as(p).clone(), "exp_avg_sq": self.flat_v[off:off + n].view_as(p).clone()}
+            elif self.hyper["beta1"] != 0 and step > 0:
+                state[i] = {"momentum_buffer": self.flat_m[off:off + n].view_as(p).clone()}
+        h = self.hyper
+        if adam:
+            group = {"lr": h["lr"], "betas": (h["beta1"], h["beta2"]), "eps": h["eps"], "weight_decay": h["weight_decay"], "amsgrad": False}
+            if self.optimizer == "adabound":
+                group.update(final_lr=h["final_lr"], gamma=h["gamma"], amsbound=False)
+                del group["amsgrad"]
+        else:
+            group = {"lr": h["lr"], "momentum": h["beta1"], "dampening": h["beta2"], "weight_decay": h["weight_decay"], "nesterov": False}
+        group["params"] = list(range(len(self.ts.lay)))
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        """Inverse of ``optimizer_state_dict`` (also takes what the reference's / torch's optimizers saved for this model)."""
+        names = [k for k, _ in self.model.named_parameters()]
+        state = sd["state"]
+        step = 0
+        with torch.no_grad():
+            self.flat_m.zero_()
+            self.flat_v.zero_()
+            for i, name in enumerate(names):
+                st = state.get(i, state.get(str(i)))
+                if not st:
+                    continue
+                off, n = self.ts.lay[name]
+                if "exp_avg" in st:
+                    self.flat_m[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                    self.flat_v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                if "momentum_buffer" in st and st["momentum_buffer"] is not None:
+                    self.flat_m[off:off + n].copy_(st["momentum_buffer"].reshape(-1))
+                    step = max(step, 1)  # the buffer exists: not the first step any more
+                step = max(step, int(st.get("step", 0)))
+            self.step_counter.fill_(step)
+        if sd.get("param_groups"):
+            self.set_lr(float(sd["param_groups"][0]["lr"]))
+
+    def save_checkpoint(self, path: str, epoch: int) -> None:
+        """A ``.tar`` in the format the reference trainer resumes from (trainer.py:402-413): ``model_state_dict`` (the unchanged
+        98-key layout), ``optimizer_state_dict`` and ``epoch``."""
+        torch.save({"epoch": int(epoch), "model_state_dict": self.model.state_dict(), "optimizer_state_dict": self.optimizer_state_dict()}, path)
+
+    def load_checkpoint(self, path: str, resume_opt: bool = True) -> int:
+        """Resume like trainer.py:402-413: weights always, optimizer state and epoch with ``resume_opt``.  Returns the epoch to start from.
+        The parameters stay views of the flat buffer (``load_state_dict`` copies in place)."""
+        ck = torch.load(path, map_location=self.dev)
+        self.model.load_state_dict(ck["model_state_dict"])
+        torch._C._increment_version(self._versioned)
+        self.eng._packed_key = None
+        if resume_opt:
+            self.load_optimizer_state_dict(ck["optimizer_state_dict"])
+            return int(ck["epoch"]) + 1
+        return 0
+
 
 broadcast_parameters = parallel.broadcast_parameters
