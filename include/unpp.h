@@ -304,6 +304,28 @@ int unpp_dropout_mask(uint16_t* mask, long npix, float p_drop, uint64_t seed, co
  * {0}, {1,2,3}, {4}, {5..npts-1}; exp(-0.5*distance/3) in float64; multi-point planes divided by their maximum. */
 int unpp_create_heatmap(const float* keypoints, int N, int npts, int H, int W, float* out, unpp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * fp32 validation mode of the inference path (UNet_Nested.precision = "fp32"): the same fused plan on NCHW fp32 tensors with fp32
+ * FMAs on the CUDA cores, straight from the OIHW state_dict weights — BASELINE's "<= 1e-3 relative in fp32/TF32" tolerance; used
+ * to separate wiring errors from bf16 rounding, never benchmarked.  models/unet.py:121-156,182-202,242-244,283-286.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct UnppRefConvArgs {
+  int32_t N, H, W, nsrc;
+  const void* src[UNPP_MAX_SRC]; /* NCHW fp32 sources, concatenated along the channel axis in this order (unet.py:199-201) */
+  int32_t src_C[UNPP_MAX_SRC];
+  const float* weight;           /* fp32 [cout][sum src_C][k][k], k = 3 (taps 9, pad 1) or 1 (taps 1) */
+  const float* scale;            /* per output channel (eval-mode BatchNorm) or NULL */
+  const float* bias;             /* per output channel or NULL */
+  int32_t cout, taps, relu, sigmoid;
+  float* out;                    /* NCHW fp32 [N][cout][H][W] */
+} UnppRefConvArgs;
+int unpp_ref_conv(const UnppRefConvArgs* a, unpp_stream_t stream);
+/* nn.ConvTranspose2d(k=2, s=2) (unet.py:187): x [N,Cin,H,W], w [Cin,Cout,2,2], b [Cout] -> out [N,Cout,2H,2W], all fp32 */
+int unpp_ref_deconv2x2(const float* x, const float* w, const float* b, float* out, int N, int Cin, int Cout, int H, int W, unpp_stream_t stream);
+/* nn.MaxPool2d(2) on NCHW fp32 */
+int unpp_ref_maxpool2x2(const float* x, float* out, int N, int C, int H, int W, unpp_stream_t stream);
+int unpp_sizeof_ref_conv_args(void);
+
 /* sizeof() of the argument structs as the C compiler sees them (binding self-check). */
 int unpp_sizeof_conv_args(void);
 int unpp_sizeof_pack_args(void);

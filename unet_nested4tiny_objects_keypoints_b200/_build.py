@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libunpp.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["common.cu", "conv_tc.cu", "aux_kernels.cu", "train_kernels.cu", "wgrad.cu", "wgrad_tc.cu", "variant_kernels.cu"]
+SOURCES = ["common.cu", "conv_tc.cu", "aux_kernels.cu", "train_kernels.cu", "wgrad.cu", "wgrad_tc.cu", "variant_kernels.cu", "ref_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

@@ -89,6 +89,17 @@ class ReduceJob(C.Structure):
     ]
 
 
+class RefConvArgs(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("nsrc", C.c_int32),
+        ("src", C.c_void_p * UNPP_MAX_SRC),
+        ("src_C", C.c_int32 * UNPP_MAX_SRC),
+        ("weight", C.c_void_p), ("scale", C.c_void_p), ("bias", C.c_void_p),
+        ("cout", C.c_int32), ("taps", C.c_int32), ("relu", C.c_int32), ("sigmoid", C.c_int32),
+        ("out", C.c_void_p),
+    ]
+
+
 class OptimArgs(C.Structure):
     _fields_ = [
         ("kind", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
@@ -143,6 +154,10 @@ _SIGNATURES = {
                                   C.c_void_p]),
     "unpp_bilinear_up2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "unpp_bilinear_up2x_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "unpp_ref_conv": (C.c_int, [C.POINTER(RefConvArgs), C.c_void_p]),
+    "unpp_ref_deconv2x2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "unpp_ref_maxpool2x2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "unpp_sizeof_ref_conv_args": (C.c_int, []),
     "unpp_sizeof_optim_args": (C.c_int, []),
     "unpp_sizeof_conv_args": (C.c_int, []),
     "unpp_sizeof_pack_args": (C.c_int, []),

@@ -199,6 +199,8 @@ class Engine:
         if self.model.training:
             from .training import run_autograd
             return run_autograd(self, x)
+        if getattr(self.model, "precision", "bf16") == "fp32":
+            return self.forward_eval_fp32(x)
         # eval mode (trainer/trainer.py:200-210 runs it under set_grad_enabled(False)): inference kernels, no graph
         return self.forward_eval(x)
 
@@ -277,6 +279,47 @@ class Engine:
             ops.conv([A[f"{name}.a"]], B, h, w, p2["w"], p2["n_total"], p2["n_tile"], 9, bias=p2["bias"], relu=True, out=out, head=head)
         ops.tag("")
         return tuple(heats)
+
+    @torch.no_grad()
+    def forward_eval_fp32(self, x: torch.Tensor):
+        """The fp32 validation mode (``model.precision = "fp32"``, csrc/ref_kernels.cu): the same fused plan — virtual concat,
+        eval-mode BatchNorm as per-channel scale / bias, ReLU, k2s2 transposed conv, 2x2 max pool, 1x1 heads + sigmoid — on NCHW
+        fp32 tensors with fp32 FMAs, straight from the state_dict weights.  BASELINE's tolerance for this mode is <= 1e-3 relative
+        against the reference (tests: ~1e-6).  ~30x slower than the tensor-core path; it exists to tell wiring from rounding."""
+        B, H, W = self._check_input(x)
+        if x.dtype != torch.float32:
+            raise ValueError("the fp32 validation mode takes float32 input")
+        if not self.model.is_deconv:
+            raise ValueError("the fp32 validation mode covers the default is_deconv=True graph")
+        m = self.model
+        with torch.cuda.device(self.device):
+            def block(srcs, seq1, seq2):
+                for seq in (seq1, seq2):
+                    conv = seq[0]
+                    if m.is_batchnorm and len(seq) == 3:  # conv, BatchNorm, ReLU (unet.py:132-134)
+                        scale, bias = ops.bn_fold(seq[1], conv.bias)
+                    else:
+                        scale, bias = None, conv.bias.detach().float().contiguous()
+                    srcs = [ops.ref_conv(srcs, conv.weight, bias, scale=scale, relu=True)]
+                return srcs[0]
+
+            X = {}
+            src = x.contiguous()
+            for lvl, name in enumerate(ENCODER):
+                mod = getattr(m, name)
+                X[f"X{lvl}0"] = block([src], mod.conv1, mod.conv2)
+                if lvl < 3:
+                    src = ops.ref_maxpool2x2(X[f"X{lvl}0"])
+            for name in DECODER_ORDER:
+                high, lows, lvl = DECODER[name]
+                up = getattr(m, name)
+                U = ops.ref_deconv2x2(X[high], up.up.weight, up.up.bias)
+                X[f"X{name[-2:]}"] = block([U] + [X[l] for l in lows], up.conv.conv1, up.conv.conv2)
+            outs = []
+            for hname, node in (("final_1", "X01"), ("final_2", "X02"), ("final_3", "X03")):
+                hm = getattr(m, hname)
+                outs.append(ops.ref_conv([X[node]], hm.weight, hm.bias.detach().float().contiguous(), sigmoid=True))
+        return tuple(outs)
 
     @torch.no_grad()
     def predict_keypoints(self, x: torch.Tensor, head: int = 2):

@@ -123,6 +123,9 @@ class UNet_Nested(nn.Module):
                 init_weights(m, init_type="kaiming")
         self.drop_out = nn.Dropout(p=0.4)
 
+        # "bf16" = the tensor-core path (bf16 storage, fp32 accumulation); "fp32" = the validation mode of the eval forward
+        # (csrc/ref_kernels.cu: fp32 storage and arithmetic on the CUDA cores, <= 1e-3 of the reference by BASELINE's tolerance)
+        self.precision = "bf16"
         self._engines = {}
         self._engines_lock = threading.Lock()
 

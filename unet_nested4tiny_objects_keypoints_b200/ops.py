@@ -570,3 +570,42 @@ def optim_step(kind: str, p, g, state1, state2, *, lr, beta1=0.0, beta2=0.0, eps
     with _Traced("optim_step " + kind, 0, 0):
         _lib.check(lib().unpp_optim_step(p.data_ptr(), g.data_ptr(), _ptr(state1), _ptr(state2), p.numel(), C.byref(a), int(step), _ptr(step_counter),
                                          _ptr(lr_dev), _ptr(scalars), _stream()), "unpp_optim_step")
+
+
+# ---------------------------------------------------------------------------------------------- fp32 validation mode (csrc/ref_kernels.cu)
+def ref_conv(srcs: Sequence[torch.Tensor], weight: torch.Tensor, bias, *, scale=None, relu=False, sigmoid=False) -> torch.Tensor:
+    """conv (3x3 pad 1, or 1x1) of the channel-concatenation of NCHW fp32 ``srcs`` with the OIHW fp32 ``weight``, then
+    ``* scale + bias`` per output channel, ReLU and / or sigmoid: fp32 FMAs on the CUDA cores."""
+    N, _, H, W = srcs[0].shape
+    cout, ctot, k, _ = weight.shape
+    assert sum(s.shape[1] for s in srcs) == ctot and k in (1, 3)
+    out = torch.empty(N, cout, H, W, dtype=torch.float32, device=srcs[0].device)
+    a = _lib.RefConvArgs()
+    a.N, a.H, a.W, a.nsrc = N, H, W, len(srcs)
+    for i, s in enumerate(srcs):
+        assert s.dtype == torch.float32 and s.is_contiguous() and tuple(s.shape[2:]) == (H, W)
+        a.src[i], a.src_C[i] = s.data_ptr(), s.shape[1]
+    weight = weight.detach().float().contiguous()
+    a.weight, a.scale, a.bias = weight.data_ptr(), _ptr(scale), _ptr(bias)
+    a.cout, a.taps, a.relu, a.sigmoid, a.out = cout, k * k, int(relu), int(sigmoid), out.data_ptr()
+    _count()
+    _lib.check(lib().unpp_ref_conv(C.byref(a), _stream()), "unpp_ref_conv")
+    return out
+
+
+def ref_deconv2x2(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    N, cin, H, W = x.shape
+    cout = weight.shape[1]
+    out = torch.empty(N, cout, 2 * H, 2 * W, dtype=torch.float32, device=x.device)
+    weight, bias = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+    _count()
+    _lib.check(lib().unpp_ref_deconv2x2(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), N, cin, cout, H, W, _stream()), "unpp_ref_deconv2x2")
+    return out
+
+
+def ref_maxpool2x2(x: torch.Tensor) -> torch.Tensor:
+    N, Cc, H, W = x.shape
+    out = torch.empty(N, Cc, H // 2, W // 2, dtype=torch.float32, device=x.device)
+    _count()
+    _lib.check(lib().unpp_ref_maxpool2x2(x.data_ptr(), out.data_ptr(), N, Cc, H, W, _stream()), "unpp_ref_maxpool2x2")
+    return out
