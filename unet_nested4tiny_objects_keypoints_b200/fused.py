@@ -418,7 +418,8 @@ class FusedTrainStep:
         else:
             group = {"lr": h["lr"], "momentum": h["beta1"], "dampening": h["beta2"], "weight_decay": h["weight_decay"], "nesterov": False}
         group["params"] = list(range(len(self.ts.lay)))
-        return {"state": state, "param_groups": [group]}
+        # (torch's Optimizer.load_state_dict ignores extra top-level keys: the step count also seeds the dropout stream, and SGD's state has none)
+        return {"state": state, "param_groups": [group], "unpp_step": step}
 
     def load_optimizer_state_dict(self, sd: dict) -> None:
         """Inverse of ``optimizer_state_dict`` (also takes what the reference's / torch's optimizers saved for this model)."""
@@ -440,7 +441,7 @@ class FusedTrainStep:
                     self.flat_m[off:off + n].copy_(st["momentum_buffer"].reshape(-1))
                     step = max(step, 1)  # the buffer exists: not the first step any more
                 step = max(step, int(st.get("step", 0)))
-            self.step_counter.fill_(step)
+            self.step_counter.fill_(int(sd.get("unpp_step", step)))
         if sd.get("param_groups"):
             self.set_lr(float(sd["param_groups"][0]["lr"]))
 
