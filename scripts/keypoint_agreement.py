@@ -22,34 +22,36 @@ def batch(B, S, gen):
     kp = (torch.rand(B, 7, 2, generator=gen, device="cuda") * (S - 24) + 12).float()
     t = ops.create_heatmap(kp, S, S)
     x = torch.stack([t[:, 0] + 0.5 * t[:, 3], t[:, 1], t[:, 2] + 0.5 * t[:, 3]], 1)
-    x = x + 0.15 * torch.randn(x.shape, generator=gen, device="cuda")
+    x = x + 0.05 * torch.randn(x.shape, generator=gen, device="cuda")
     return x.contiguous(), t, kp
 
 
 def main():
     out = sys.argv[1]
-    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1500
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
     S = int(sys.argv[3]) if len(sys.argv) > 3 else 256
     B = 32
     torch.manual_seed(0)
     gen = torch.Generator(device="cuda").manual_seed(1)
     m = pkg.UNet_Nested().cuda().train()
     loss_kind = sys.argv[4] if len(sys.argv) > 4 else "focal"  # the trainer's criterion (trainer.py:426): MSE collapses to the all-zero heat map on these sparse targets
-    st = fused.FusedTrainStep(m, B, S, S, lr=1e-3, weight_decay=0.0, loss=loss_kind, seed=3)
+    st = fused.FusedTrainStep(m, B, S, S, lr=5e-4, weight_decay=0.0, loss=loss_kind, seed=3)
     losses = []
     for k in range(steps):
         x, t, _ = batch(B, S, gen)
         st.x.copy_(x)
         st.target.copy_(t)
         st.step_device()
-        if k % 50 == 0 or k == steps - 1:
+        if k == steps // 2:
+            st.set_lr(1e-4)  # one MultiStepLR-style drop (trainer.py:383-388)
+        if k % 250 == 0 or k == steps - 1:
             losses.append((k, float(st.loss)))
     m.eval()
     ident = {c: 0 for c in range(4)}
     within1 = {c: 0 for c in range(4)}
     total = {c: 0 for c in range(4)}
     maxd = {c: 0.0 for c in range(4)}
-    gt_err, heat_err, peak = [], [], []
+    gt_err, gt_err16, heat_err, peak = [], [], [], []
     nums = {0: 1, 1: 3, 2: 1, 3: 2}
     for _ in range(8):
         x, t, kp = batch(B, S, gen)
@@ -77,12 +79,14 @@ def main():
             total[c] += d.numel()
             maxd[c] = max(maxd[c], float(d.max()))
         a0, _ = ops.argmax_peaks(hf[:, 0:1].contiguous())
+        b0, _ = ops.argmax_peaks(hb[:, 0:1].contiguous())
         gt_err.append(float((a0.view(B, 2).float() - kp[:, 0]).norm(dim=1).mean()))
+        gt_err16.append(float((b0.view(B, 2).float() - kp[:, 0]).norm(dim=1).mean()))
     with open(out, "w") as f:
         f.write(f"# Key-point agreement of the bf16 tensor-core path with the fp32 validation mode ({S}x{S}, {steps} fused training steps at batch {B})\n\n")
         f.write(__doc__.split("usage")[0].strip() + "\n\n")
         f.write(f"training loss ({loss_kind}, mean of three heads): " + ", ".join(f"step {k}: {v:.5f}" for k, v in losses) + "\n\n")
-        f.write(f"mean distance of the fp32 key point of plane 0 from the drawn point: {sum(gt_err) / len(gt_err):.2f} px (the model is 'trained-looking')\n\n")
+        f.write(f"mean distance of the key point of plane 0 from the drawn point: fp32 mode {sum(gt_err) / len(gt_err):.2f} px, bf16 path {sum(gt_err16) / len(gt_err16):.2f} px\n\n")
         f.write(f"max |heat_bf16 - heat_fp32| over the evaluation batches: {max(heat_err):.3e}; mean plane maximum of the fp32 heat maps: {sum(peak) / len(peak):.3f}\n\n")
         f.write("| plane | points per plane | key points compared | identical | within 1 px (incl. diagonal) | largest distance (px) |\n|---|---|---|---|---|---|\n")
         for c in range(4):

@@ -40,8 +40,10 @@ constexpr int kEpiWarps = 8;
 // (A fourth issuer for the training variants does not pay: registers are allocated for a multiple of four warps, so a 13-warp
 // CTA is limited to 128 registers per thread whatever __maxnreg__ says — 152 or 144 fail to launch — and at 128 the training
 // epilogue spills ~600 bytes per thread: 3.51 -> 3.95 ms per step.)
-constexpr int mma_warps(bool train) { return train ? 3 : 4; }
-constexpr int block_threads(bool train) { return 64 + 32 * kEpiWarps + 32 * (mma_warps(train) - 1); }
+// The head conv of the training forward (HEAD && TRAIN: dropout keep bits, nothing else) is as light as the inference head: four issuers.
+constexpr bool heavy_epilogue(bool head, bool train) { return train && !head; }
+constexpr int mma_warps(bool heavy) { return heavy ? 3 : 4; }
+constexpr int block_threads(bool heavy) { return 64 + 32 * kEpiWarps + 32 * (mma_warps(heavy) - 1); }
 
 struct ConvTcParams {
   CUtensorMap maps[UNPP_MAX_SRC];
@@ -294,7 +296,12 @@ struct EpiOperands {  // training-only operands of the step, fetched BEFORE the 
 };
 template <int G, bool HEAD, bool TRAIN>
 __device__ __forceinline__ void epi_prefetch(const EpiArgs& p, EpiOperands<G>& t, size_t eoff, bool valid) {
-  if constexpr (TRAIN) {
+  if constexpr (TRAIN && HEAD) {
+    // the head conv of the training forward: bias + ReLU + dropout + 1x1 head, none of the backward operands (the launch rejects them)
+    t.dbits = 0xFFFFFFFFu;
+    if (valid && p.drop_mask)
+      t.dbits = G == 2 ? __ldg(reinterpret_cast<const uint32_t*>(p.drop_mask + (eoff >> 4))) : uint32_t(__ldg(p.drop_mask + (eoff >> 4)));
+  } else if constexpr (TRAIN) {
     const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int i = 0; i < 2 * G; ++i) t.a[i] = t.m[i] = t.x[i] = z;
@@ -336,7 +343,7 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
 // barrier): the loads of epi_prefetch then find them in L2 instead of paying the DRAM latency once per step.
 template <int G, bool HEAD, bool TRAIN>
 __device__ __forceinline__ void epi_l2_prefetch(const EpiArgs& p, size_t eoff, bool valid) {
-  if constexpr (TRAIN) {
+  if constexpr (TRAIN && !HEAD) {
     if (!valid) return;
     if (p.addend) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.addend + eoff));
     if (p.relu_mask_src) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.relu_mask_src + eoff));
@@ -371,7 +378,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, const uint32_t (&ra
 #pragma unroll
       for (int k = 0; k < 8; ++k) words[8 * px + k] = relu ? cvt_bf16x2_relu(v[2 * k], v[2 * k + 1]) : cvt_bf16x2(v[2 * k], v[2 * k + 1]);
     } else {
-      if constexpr (TRAIN) {
+      if constexpr (TRAIN && !HEAD) {
         if (p.addend) {
           const uint32_t aw[8] = {t.a[2 * px].x, t.a[2 * px].y, t.a[2 * px].z, t.a[2 * px].w, t.a[2 * px + 1].x, t.a[2 * px + 1].y, t.a[2 * px + 1].z, t.a[2 * px + 1].w};
 #pragma unroll
@@ -382,7 +389,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, const uint32_t (&ra
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
       }
-      if constexpr (TRAIN) {
+      if constexpr (TRAIN && !HEAD) {
         if (p.relu_mask_src) {
           const uint32_t mw[8] = {t.m[2 * px].x, t.m[2 * px].y, t.m[2 * px].z, t.m[2 * px].w, t.m[2 * px + 1].x, t.m[2 * px + 1].y, t.m[2 * px + 1].z, t.m[2 * px + 1].w};
 #pragma unroll
@@ -394,7 +401,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, const uint32_t (&ra
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) words[8 * px + k] = cvt_bf16x2(v[2 * k], v[2 * k + 1]);
-      if constexpr (TRAIN) {
+      if constexpr (TRAIN && !HEAD) {
         if (p.stats_partial && valid) {
           // statistics of the bf16-rounded values that are stored; second statistic v*v (BN batch variance) or v*aux (BN backward)
           const uint32_t xw[8] = {t.x[2 * px].x, t.x[2 * px].y, t.x[2 * px].z, t.x[2 * px].w, t.x[2 * px + 1].x, t.x[2 * px + 1].y, t.x[2 * px + 1].z, t.x[2 * px + 1].w};
@@ -446,14 +453,15 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, const uint32_t (&ra
 }
 
 template <bool DECONV, bool HEAD, bool TRAIN>
-__global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-  constexpr int kMmaWarps = mma_warps(TRAIN), kThreads = block_threads(TRAIN);
+__global__ void __launch_bounds__(block_threads(heavy_epilogue(HEAD, TRAIN)), 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  constexpr bool kHeavy = heavy_epilogue(HEAD, TRAIN);  // backward operands / statistics in the epilogue: 168 registers, three issuers
+  constexpr int kMmaWarps = mma_warps(kHeavy), kThreads = block_threads(kHeavy);
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_acc_full[4], bar_acc_empty[4], bar_w;
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_bias[256];
   __shared__ __align__(16) float s_head[8 * 16 + 8];
-  __shared__ float s_stats[TRAIN ? kEpiWarps : 1][2][TRAIN ? 256 : 1];  // per epilogue warp per-channel partial sums
+  __shared__ float s_stats[kHeavy ? kEpiWarps : 1][2][kHeavy ? 256 : 1];  // per epilogue warp per-channel partial sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntile_idx = blockIdx.y;  // which n_tile slice of the GEMM N axis this CTA owns
@@ -495,7 +503,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
       for (int i = threadIdx.x; i < p.head_classes * 16; i += kThreads) s_head[i] = __ldg(p.head_w + i);
       for (int i = threadIdx.x; i < p.head_classes; i += kThreads) s_head[8 * 16 + i] = __ldg(p.head_b + i);
     }
-    if constexpr (TRAIN) {
+    if constexpr (kHeavy) {
       for (int i = threadIdx.x; i < kEpiWarps * 2 * 256; i += kThreads) (&s_stats[0][0][0])[i] = 0.f;
     }
   }
@@ -763,10 +771,10 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
     e.drop_mask = p.drop_mask, e.drop_scale = p.drop_scale, e.addend = p.addend, e.relu_mask_src = p.relu_mask_src;
     e.stats_partial = p.stats_partial, e.stats_aux = p.stats_aux, e.aux_mean = p.aux_mean, e.aux_istd = p.aux_istd;
     const int TW = p.TW, ncols = p.ncols, nsub = p.nsub, ntiles = p.ntiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y, dbg = p.dbg, b2 = p.b2, nacc = p.nacc;
-    float* const st1 = TRAIN ? &s_stats[TRAIN ? ew : 0][0][0] : nullptr;
-    float* const st2 = TRAIN ? &s_stats[TRAIN ? ew : 0][1][0] : nullptr;
+    float* const st1 = kHeavy ? &s_stats[kHeavy ? ew : 0][0][0] : nullptr;
+    float* const st2 = kHeavy ? &s_stats[kHeavy ? ew : 0][1][0] : nullptr;
     // with <= 2 column groups every unit of this warp has the same 16 channels: keep the statistics in registers
-    const bool reg_stats = TRAIN && (ncb <= 2 || b2);  // (2x2 blocking: the four column groups are four pixels of the same 16 channels)
+    const bool reg_stats = kHeavy && (ncb <= 2 || b2);  // (2x2 blocking: the four column groups are four pixels of the same 16 channels)
     float sa1[16], sa2[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) sa1[k] = 0.f, sa2[k] = 0.f;
@@ -854,11 +862,16 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
       }
-    } else if (!HEAD && ((!DECONV && ncb <= 2) || (!TRAIN && (ncb == 1 || ncb == 2 || ncb == 4 || ncb == 8)))) {
+    } else if (!HEAD && !(TRAIN && DECONV) && (ncb == 1 || ncb == 2 || ncb == 4 || ncb == 8)) {
       // classic path, a step = 16 channels of one pixel = 32 contiguous bytes.  With <= 32 GEMM columns per CTA (the
       // 32-channel level, 16-channel dgrads) every unit of this warp has the same 16 channels, so bias and statistics
-      // live in registers; wider CTAs (inference only here) re-read the 16 bias values of the step from shared memory.
+      // live in registers; wider CTAs re-read the 16 bias values of the step from shared memory.
+      // Training variants of the 64 / 128-column layers (deep encoder levels, their dgrads) walk their units GROUP-MAJOR: all
+      // sub-tiles of one 16-channel group, then the next group, so that the statistics of a group stay in registers and are
+      // folded into the warp's shared-memory slots once per (tile, group) instead of once per unit (64 shuffles each).
       const bool fixed_c = !DECONV && ncb <= 2;
+      const bool gm = TRAIN && ncb > 2;
+      const int nsub_shift = nsub == 8 ? 3 : nsub == 4 ? 2 : nsub == 2 ? 1 : 0;  // nsub = TW / 8 is a power of two
       const int ncb_shift = ncb == 8 ? 3 : ncb == 4 ? 2 : ncb == 2 ? 1 : 0;  // ncols is 16 << ncb_shift on this path (see the guard below)
       float bias_r[16];
 #pragma unroll
@@ -873,7 +886,8 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
         const size_t rowpix = (size_t(n) * e.H + yy) * e.W;
         if constexpr (TRAIN && !DECONV) {
           for (int it = 0; it < nit; ++it) {
-            const int u = half + 2 * it, j = u >> ncb_shift, c0 = (u & (ncb - 1)) * 16;
+            const int u = half + 2 * it;
+            const int j = gm ? (it & (nsub - 1)) : (u >> ncb_shift), c0 = gm ? (half + 2 * (it >> nsub_shift)) * 16 : (u & (ncb - 1)) * 16;
             epi_l2_prefetch<1, false, TRAIN>(e, (rowpix + xb + j * 8) * e.cout + ntile_idx * ncols + c0, row_ok && xb + j * 8 < e.W);
           }
         }
@@ -884,7 +898,8 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
           uint32_t A[16], wds1[8];
           EpiOperands<1> tops;
           for (int it = 0; it < nit; ++it) {
-            const int u = half + 2 * it, j = u >> ncb_shift, c0 = (u & (ncb - 1)) * 16;  // unit = (sub-tile, 16-column group)
+            const int u = half + 2 * it;  // unit = (sub-tile, 16-column group)
+            const int j = gm ? (it & (nsub - 1)) : (u >> ncb_shift), c0 = gm ? (half + 2 * (it >> nsub_shift)) * 16 : (u & (ncb - 1)) * 16;
             const int x0 = xb + j * 8;
             const bool valid = row_ok && x0 < e.W;
             size_t eoff;
@@ -908,6 +923,14 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
             }
             tmem_ld_wait16(A);
             epi_finish<1, false, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, eoff, valid, n, yy, x0, sa1, sa2, wds1);
+            if constexpr (kHeavy) {
+              if (gm && j == nsub - 1 && e.stats_partial) {  // last sub-tile of this 16-channel group: fold its statistics into the warp's slots
+                const float r1 = warp_reduce16(sa1, lane), r2 = warp_reduce16(sa2, lane);
+                if ((lane & 1) == 0) st1[c0 + (lane >> 1)] += r1, st2[c0 + (lane >> 1)] += r2;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) sa1[k] = 0.f, sa2[k] = 0.f;
+              }
+            }
             if constexpr (!TRAIN && !DECONV) {
               if (e.pooled) {  // 2x2 max pool across the four lanes that hold the window (pj ^ 1 = lane ^ 1, pi ^ 1 = lane ^ 8)
 #pragma unroll
@@ -961,7 +984,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
     }
-    if constexpr (TRAIN) {
+    if constexpr (kHeavy) {
       if (reg_stats && e.stats_partial) {
         const int c0w = b2 ? 0 : (half % ncb) * 16;  // u = half + 2i  =>  u % ncb is constant for ncb in {1, 2}
         const float r1 = warp_reduce16(sa1, lane), r2 = warp_reduce16(sa2, lane);
@@ -973,7 +996,7 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
-  if constexpr (TRAIN) {
+  if constexpr (kHeavy) {
     if (p.stats_partial) {
       // partial layout [cta.x][2][n_total]; the warp slots are summed in a fixed order so the
       // result is deterministic for a given launch geometry.
@@ -982,11 +1005,11 @@ __global__ void __launch_bounds__(block_threads(TRAIN), 1) conv_tc_kernel(const 
         const int st = i / nch, ch = i % nch;
         float t = 0.f;
 #pragma unroll
-        for (int wv = 0; wv < kEpiWarps; ++wv) t += s_stats[TRAIN ? wv : 0][st][TRAIN ? ch : 0];
+        for (int wv = 0; wv < kEpiWarps; ++wv) t += s_stats[kHeavy ? wv : 0][st][kHeavy ? ch : 0];
         if (st == 1 && p.stats_aux) {  // sum dyh*xhat = istd * (sum dyh*z - mean * sum dyh)
           float t1 = 0.f;
 #pragma unroll
-          for (int wv = 0; wv < kEpiWarps; ++wv) t1 += s_stats[TRAIN ? wv : 0][0][TRAIN ? ch : 0];
+          for (int wv = 0; wv < kEpiWarps; ++wv) t1 += s_stats[kHeavy ? wv : 0][0][kHeavy ? ch : 0];
           const int gc = ntile_idx * nch + ch;
           t = __ldg(p.aux_istd + gc) * (t - __ldg(p.aux_mean + gc) * t1);
         }
@@ -1070,7 +1093,7 @@ int make_plan_cw(const UnppConvArgs* a, Plan* pl, int cw) {
   if (a->lowres_src && !a->block2x2) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: lowres_src (fused transposed conv) needs block2x2");
   if (a->bias_classes != 0 && a->bias_classes != 1 && a->bias_classes != 9) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: bias_classes must be 0, 1 or 9");
   // static shared memory: 18 KB in the training variants (statistics slots), 2 KB otherwise; 227 KB per CTA in total
-  const int smem_budget = (is_train(a) ? 196 : 220) * 1024;
+  const int smem_budget = ((is_train(a) && !a->head_w) ? 196 : 220) * 1024;
   if (a->block2x2) {
     // 2x2 output blocking: every source is one 16-channel chunk staged as 64-byte pixel-pair rows; N = 4 x 16
     if (a->taps != 9 || a->mode != UNPP_MODE_CONV || a->n_total != 16 || a->n_tile != 16 || (a->H & 1) || (a->W & 1))
@@ -1175,6 +1198,8 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
                     (!a->block2x2 && a->n_tile != 16 && a->n_tile != 32 && a->n_tile != 64 && a->n_tile != 128)))
     return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: the fused max pool needs conv mode with ReLU and an output, even H and W, no head / training operand");
   if (a->stats_partial && a->mode != UNPP_MODE_CONV) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: stats only in conv mode");
+  if (a->head_w && (a->addend || a->relu_mask_src || a->stats_partial))
+    return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: the fused head (a forward op) takes no addend / ReLU mask / statistics");
   if (a->stats_aux && (!a->aux_mean || !a->aux_istd)) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: stats_aux needs aux_mean/aux_istd");
 
   EncodeTiledFn enc = get_encode();
@@ -1253,9 +1278,9 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
 #define UNPP_LAUNCH(D, Hd, T)                                                                                                         \
   do {                                                                                                                                \
     static unsigned char opted_in[64] = {0}; /* per variant and device */                                                             \
-    if (cudaError_t e = unpp::opt_in_smem(conv_tc_kernel<D, Hd, T>, (T ? 204 : 224) * 1024, opted_in))                                \
+    if (cudaError_t e = unpp::opt_in_smem(conv_tc_kernel<D, Hd, T>, (heavy_epilogue(Hd, T) ? 204 : 224) * 1024, opted_in))            \
       return unpp::fail_cuda_err("conv_tc: cudaFuncSetAttribute", e);                                                                 \
-    if (cudaError_t e = unpp::launch(conv_tc_kernel<D, Hd, T>, grid, block_threads(T), pl.smem_total, stream, p))                     \
+    if (cudaError_t e = unpp::launch(conv_tc_kernel<D, Hd, T>, grid, block_threads(heavy_epilogue(Hd, T)), pl.smem_total, stream, p)) \
       return unpp::fail_cuda_err("conv_tc: launch", e);                                                                               \
   } while (0)
   if (deconv) UNPP_LAUNCH(true, false, false);
