@@ -180,15 +180,18 @@ def forward_bf16(sd: Dict[str, torch.Tensor], x: torch.Tensor, dropout_masks: Op
 
 
 def train_step_grads_bf16(sd: Dict[str, torch.Tensor], x, target, dropout_masks=None, loss: str = "mse", scale_grad=None, dheats=None, p_drop: float = 0.4,
-                          capture: Optional[dict] = None):
+                          capture: Optional[dict] = None, loss_fn=None):
     """Like unetpp_oracle.train_step_grads with the bf16 storage points of the CUDA path.
-    ``dheats``: optional upstream gradients of the three heat maps (then ``target`` / ``loss`` are ignored)."""
+    ``dheats``: optional upstream gradients of the three heat maps (then ``target`` / ``loss`` are ignored); ``loss_fn``: optional
+    callable mapping the three heat maps to a scalar loss (takes precedence)."""
     params = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in sd.items() if v.dtype.is_floating_point and "running_" not in k)
     full = dict(sd)
     full.update(params)
     new_stats: dict = {}
     outs = forward_bf16(full, x, dropout_masks=dropout_masks, p_drop=p_drop, new_stats=new_stats, scale_grad=scale_grad, capture=capture)
-    if dheats is not None:
+    if loss_fn is not None:  # any differentiable function of the three heat maps (the trainer builds its loss on them, trainer.py:125-135)
+        L = loss_fn(outs)
+    elif dheats is not None:
         L = sum((o * d).sum() for o, d in zip(outs, dheats) if d is not None)
     elif loss == "mse":
         L = O.mse_heatmap_loss(outs, target)

@@ -51,10 +51,10 @@ def table_bounds(shape):
     return lambda k: tbl[k.split(".")[0] if not k.startswith("final") else "final"]
 
 
-def emulation_bounds(sd, x, target, masks=None, p_drop=0.4, ref=None, dheats=None, loss="mse"):
+def emulation_bounds(sd, x, target, masks=None, p_drop=0.4, ref=None, dheats=None, loss="mse", loss_fn=None):
     """Per-tensor bounds at an arbitrary shape: 3x what an exact fp32 emulation of our bf16 storage points (oracle/bf16_emulation.py)
     deviates from the fp32 oracle on these very inputs (+ 1e-2 / 1e-3 floors for tensors it happens to hit exactly)."""
-    _, _, eg, _ = E.train_step_grads_bf16(sd, x, target, dropout_masks=masks, p_drop=p_drop, dheats=dheats, loss=loss)
+    _, _, eg, _ = E.train_step_grads_bf16(sd, x, target, dropout_masks=masks, p_drop=p_drop, dheats=dheats, loss=loss, loss_fn=loss_fn)
     errs = grad_errors(eg, ref)
     return lambda k: (3.0 * errs[k][0] + 1e-2, 1.0 - 3.0 * (1.0 - errs[k][1]) - 1e-3)
 
@@ -254,9 +254,10 @@ def test_arbitrary_upstream_gradients_like_the_trainer_cpu_loss():
     ro = O.forward(full, x, training=True, dropout_masks=None)
     (0.7 * F.mse_loss(ro[0], target) + 0.3 * F.l1_loss(ro[2], target)).backward()
     ref = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in params.items()}
-    with torch.no_grad():
-        dh = [0.7 * 2 * (ro[0] - target) / target.numel(), None, 0.3 * torch.sign(ro[2] - target) / target.numel()]
-    check_grads({k: p.grad for k, p in m.named_parameters()}, ref, emulation_bounds(sd, x, target, None, 0.0, ref, dheats=dh))
+    # (the L1 term is not smooth: where a heat map crosses its target the upstream gradient flips sign with the bf16 noise of the
+    # heat map itself — the emulation builds the same loss on ITS outputs, so its deviation includes that effect)
+    bounds = emulation_bounds(sd, x, target, None, 0.0, ref, loss_fn=lambda o: 0.7 * F.mse_loss(o[0], target) + 0.3 * F.l1_loss(o[2], target))
+    check_grads({k: p.grad for k, p in m.named_parameters()}, ref, bounds)
     assert float(m.final_2.weight.grad.abs().max()) == 0.0
 
 
