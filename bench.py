@@ -554,7 +554,10 @@ def bench_train(args, rank, world, local):
         line = {"metric": metric_name("train"), "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic", "config": config_of("train", world), "clocks": clk, "e2e": e2e, "gpu_launches": launches * args.steps,
-                "roofline": roof, "whole_step_roofline": whole, "per_kernel": per_kernel, "loss": float(step.loss.item()), "loss_kind": loss,
+                "roofline": roof, "whole_step_roofline": whole, "per_kernel": per_kernel,
+                "per_launch_label": [{"pass": tag, "label": label, "launches": agg[(tag, label)][1] // reps, "ms": round(t, 4)}
+                                     for (tag, label), t in sorted(times.items(), key=lambda kv: -kv[1])],
+                "loss": float(step.loss.item()), "loss_kind": loss,
                 "batch_per_gpu": b, "images_per_s_per_gpu": round(value / world, 1), "allreduce_us": round(ar_us, 1) if ar_us is not None else None}
     return line
 
