@@ -495,21 +495,36 @@ def bench_train(args, rank, world, local):
         ar_us = statistics.median(e0.elapsed_time(e1) for e0, e1 in step.allreduce_events) * 1e3
         step.allreduce_events = None
     value = b * world * args.steps / (ms * 1e-3)
-    # end to end through the public API (FusedTrainStep.step_many): every step its images and targets go H2D from pinned
-    # host memory and its loss comes back D2H; the copies of batch k+1 overlap the step of batch k
-    x_hosts = [x_host, torch.randn(b, 3, 256, 256, generator=g).pin_memory()]
-    t_hosts = [t_host, torch.rand(b, 4, 256, 256, generator=g).pin_memory()]
+    # end to end through the public API (FusedTrainStep.step_many): every step its batch goes H2D from pinned host memory and its loss
+    # comes back D2H; the copies of batch k+1 overlap the step of batch k.  Two forms of the same batch:
+    #   e2e             what the trainer's data loader delivers (trainer.py:106-109): 8-bit RGB images (as the dataset decodes them,
+    #                   datasets_base.py:71-72; ToTensor's 1/255 on the device) + the 7 key points per image; the targets of
+    #                   helper.create_heatmap (numpy on the CPU every iteration in the reference, trainer.py:122-123) are synthesised on the device
+    #   e2e_fp32_input  fp32 images + fp32 target heat maps built beforehand (58.7 MB per step at batch 32)
     loss_hosts = [torch.empty(1).pin_memory() for _ in range(2)]
 
-    def e2e_run(nsteps):
-        step.step_many([x_hosts[k & 1] for k in range(nsteps)], [t_hosts[k & 1] for k in range(nsteps)], [loss_hosts[k & 1] for k in range(nsteps)])
+    def e2e_of(st, xs, ts):
+        def run(nsteps):
+            st.step_many([xs[k & 1] for k in range(nsteps)], [ts[k & 1] for k in range(nsteps)], [loss_hosts[k & 1] for k in range(nsteps)])
 
-    e2e_run(2)
-    torch.cuda.synchronize()
-    ms_e2e = timed(lambda: e2e_run(args.steps), 1, world)
-    e2e = {"value": round(b * world * args.steps / (ms_e2e * 1e-3), 1), "unit": "images/s", "h2d_bytes_per_step": (x_host.numel() + t_host.numel()) * 4,
-           "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3),
-           "pipelining": "H2D of batch k+1 (staging buffers, copy stream) overlaps the step of batch k"}
+        run(2)
+        torch.cuda.synchronize()
+        ms_e = timed(lambda: run(args.steps), 1, world)
+        return {"value": round(b * world * args.steps / (ms_e * 1e-3), 1), "unit": "images/s",
+                "h2d_bytes_per_step": xs[0].numel() * xs[0].element_size() + ts[0].numel() * ts[0].element_size(), "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e / args.steps, 3), "pipelining": "H2D of batch k+1 (staging buffers, copy stream) overlaps the step of batch k"}
+
+    e2e_f32 = e2e_of(step, [x_host, torch.randn(b, 3, 256, 256, generator=g).pin_memory()], [t_host, torch.rand(b, 4, 256, 256, generator=g).pin_memory()])
+    e2e_f32["input"] = "float32 images [B,3,H,W] + float32 target heat maps [B,4,H,W]"
+    model8 = make_model(True, dev)
+    if world > 1:
+        fused.broadcast_parameters(model8)
+    step8 = fused.FusedTrainStep(model8, b, 256, 256, device=dev, seed=0, loss=loss, input="uint8_nhwc")
+    u8 = [torch.randint(0, 256, (b, 256, 256, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    kps = [(torch.rand(b, 7, 2, generator=g) * 240 + 8).pin_memory() for _ in range(2)]
+    e2e = e2e_of(step8, u8, kps)
+    e2e["input"] = "uint8 RGB images [B,H,W,3] + 7 key points per image (the trainer's (inputs, labels), trainer.py:106-109); ToTensor and helper.create_heatmap on the device"
+    del step8, model8
     line = None
     if rank == 0:
         pk = peaks()
@@ -553,7 +568,8 @@ def bench_train(args, rank, world, local):
                  "frac_of_hbm_peak_at_190MB": round(190e6 * b / (step_ms * 1e-3) / 1e9 / pk["hbm"], 4)}
         line = {"metric": metric_name("train"), "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
-                "dtype": "bf16", "data": "synthetic", "config": config_of("train", world), "clocks": clk, "e2e": e2e, "gpu_launches": launches * args.steps,
+                "dtype": "bf16", "data": "synthetic", "config": config_of("train", world), "clocks": clk, "e2e": e2e, "e2e_fp32_input": e2e_f32,
+                "gpu_launches": launches * args.steps,
                 "roofline": roof, "whole_step_roofline": whole, "per_kernel": per_kernel,
                 "per_launch_label": [{"pass": tag, "label": label, "launches": agg[(tag, label)][1] // reps, "ms": round(t, 4)}
                                      for (tag, label), t in sorted(times.items(), key=lambda kv: -kv[1])],
@@ -608,7 +624,7 @@ def _main(out):
         torch.cuda.empty_cache()
         t = bench_train(targs, rank, world, local)
         if t is not None:
-            extra = {k: t[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "e2e", "gpu_launches", "roofline", "whole_step_roofline", "per_kernel",
+            extra = {k: t[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "e2e", "e2e_fp32_input", "gpu_launches", "roofline", "whole_step_roofline", "per_kernel",
                                        "loss", "loss_kind", "batch_per_gpu", "images_per_s_per_gpu", "allreduce_us")}
         if world == 1:
             targs.loss = "focal"  # the criterion the trainer ships (trainer.py:426), next to BASELINE's MSE

@@ -239,3 +239,34 @@ def test_tar_checkpoint_resume_round_trip(tmp_path, opt):
     st_e = fresh()[1]
     st_e.load_optimizer_state_dict(o.state_dict())
     assert torch.equal(st_e.flat_m, st_b.flat_m) and int(st_e.step_counter) >= 1
+
+
+def test_fused_step_from_uint8_images_and_keypoints_like_the_trainers_loader():
+    """The trainer's loader delivers (inputs, labels) = images + key points (trainer.py:106-109).  step_many with 8-bit images and key
+    points: ToTensor's 1/255 and helper.create_heatmap run on the device; the result equals the step fed with the fp32 tensors the
+    reference would have built on the CPU (same x16 after the bf16 rounding, targets to 2e-6 -> same loss to 1e-6)."""
+    sd = O.synth_state_dict(seed=72)
+    g = torch.Generator().manual_seed(6)
+    B, H, W = 2, 32, 32
+    u8 = [torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    kps = [(torch.rand(B, 7, 2, generator=g) * 24 + 4).pin_memory() for _ in range(2)]
+    res = []
+    for mode in ("u8", "f32"):
+        m = pkg.UNet_Nested()
+        m.load_state_dict(sd)
+        m = m.cuda().train()
+        m.drop_out.p = 0.0
+        st = fused.FusedTrainStep(m, B, H, W, lr=1e-3, loss="mse", input="uint8_nhwc" if mode == "u8" else "float32")
+        lh = [torch.empty(1).pin_memory() for _ in range(2)]
+        if mode == "u8":
+            st.step_many(u8, kps, lh)
+        else:
+            xs = [(u.permute(0, 3, 1, 2).float() / 255).contiguous().pin_memory() for u in u8]          # torchvision ToTensor
+            ts = [torch.from_numpy(O.create_heatmap(k.numpy(), H, W)).pin_memory() for k in kps]       # trainer.py:122-123
+            st.step_many(xs, ts, lh)
+        torch.cuda.synchronize()
+        res.append(([float(l) for l in lh], st.ts.t["x16"].clone(), st.flat_g.clone()))
+    assert torch.equal(res[0][1], res[1][1])  # identical bf16 input tensor
+    for a, b in zip(res[0][0], res[1][0]):
+        assert abs(a - b) <= 1e-4 * abs(b)
+    assert float((res[0][2] - res[1][2]).abs().max()) <= 2e-2 * float(res[1][2].abs().max())  # (the second step starts from parameters that differ in the last bits)

@@ -184,7 +184,7 @@ class FusedTrainStep:
     def __init__(self, model, B: int, H: int, W: int, lr: float = 3e-6, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-4, device="cuda", use_graph: bool = True, process_group=None, seed: int = 0, loss: str = "focal",
                  focal_gamma: float = 3.0, optimizer: str = "adamw", momentum: float = 0.9, dampening: float = 0.0, final_lr: float = 0.1,
-                 bound_gamma: float = 1e-3):
+                 bound_gamma: float = 1e-3, input: str = "float32"):
         """Defaults follow the reference trainer: ``--optimizer adamw --lr 3e-6 --weight-decay 1e-4`` (train.py:38-45) and
         ``loss="focal"``, the criterion its training loop optimises — ``heatmap_criterion = FocalLoss_BCE_2d(gamma=3,
         size_average=False)`` (trainer.py:426, used at 125-135), mean over the three heads.  ``loss="mse"`` is the
@@ -195,7 +195,9 @@ class FusedTrainStep:
         (torch.optim with the trainer's arguments; ``momentum`` = train.py:39), "sgdw" (tools/optimizers/sgdw.py as shipped, built by the
         trainer without momentum: pass ``momentum=0`` for that), "adabound" (tools/optimizers/adabound.py).  The learning rate lives
         on the device: ``set_lr`` is what an lr scheduler (MultiStepLR / ExponentialLR, trainer.py:383-388) calls between steps."""
-        self.model = model
+        if input not in ("float32", "uint8_nchw", "uint8_nhwc"):
+            raise ValueError("input must be 'float32', 'uint8_nchw' or 'uint8_nhwc'")
+        self.model, self.input = model, input
         self.dev = _device(device)
         if not model.training:
             raise RuntimeError("FusedTrainStep needs model.train()")
@@ -232,7 +234,10 @@ class FusedTrainStep:
         self.step_size = torch.zeros(4, dtype=torch.float32, device=self.dev)  # per-step optimizer scalars (unpp_optim_step)
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
-        self.x = torch.zeros(B, model.in_channels, H, W, dtype=torch.float32, device=self.dev)
+        # ``input``: "float32" (the reference's [B,C,H,W] tensors, trainer.py:109) or 8-bit images copied as bytes and scaled by 1/255 on
+        # the device like torchvision's ToTensor (datasets/datasets_base.py:71-72): "uint8_nchw" / "uint8_nhwc" ([B,H,W,C], what PIL holds)
+        xshape = (B, H, W, model.in_channels) if input == "uint8_nhwc" else (B, model.in_channels, H, W)
+        self.x = torch.zeros(xshape, dtype=torch.float32 if input == "float32" else torch.uint8, device=self.dev)
         self.target = torch.zeros(B, model.n_classes, H, W, dtype=torch.float32, device=self.dev)
         self.numel_head = B * model.n_classes * H * W
         if loss == "mse":      # (1/3) sum_k mean((p_k - T)^2): nn.MSELoss per head (trainer.py:427), mean of the heads (trainer.py:125-134)
@@ -295,7 +300,8 @@ class FusedTrainStep:
             if ts.use_masks:
                 for k in range(3):
                     ops.dropout_mask(ts.t[f"mask{k}"].view(-1), self.p_drop, self.seed * 7919 + k, self.step_counter)
-        forward_train(ts, self.x, after_input=lambda: cur.wait_event(packed), before_decoder=lambda: cur.wait_stream(side))
+        forward_train(ts, self.x, after_input=lambda: cur.wait_event(packed), before_decoder=lambda: cur.wait_stream(side),
+                      channels_last=self.input == "uint8_nhwc")
         backward_train(ts, self.flat_g, target=self.target, coef=self.coef, loss_kind=self.loss_kind, gamma=self.focal_gamma)
         nacc, ncls = ts.head_nacc, self.model.n_classes
         ops.reduce_partials(ts.t["head_red"], 3, nacc, 1, self.loss, scale=self.loss_scale, partial_offset=ncls * 17)
@@ -345,10 +351,20 @@ class FusedTrainStep:
         """Pipelined training over a list of pinned host batches: the H2D copy of batch k+1 (into staging buffers, on a
         copy stream) overlaps the step of batch k; a device-to-device copy (~0.1 ms) moves the staged batch into the
         fixed-address inputs the captured step reads.  ``loss_hosts``: optional pinned [1] tensors receiving each loss.
+        ``target_hosts``: heat-map targets [B,C,H,W] fp32 — or KEY POINTS [B,points,2] fp32, what the trainer's data loader
+        actually delivers as labels (trainer.py:109): the targets of helper.create_heatmap (trainer.py:122-123, numpy on the CPU
+        every iteration in the reference) are then synthesised on the device, and a step moves 56 bytes of labels per image.
         Returns after everything is enqueued; the caller synchronises the current stream."""
         cur = torch.cuda.current_stream(self.dev)
-        if not hasattr(self, "_stage"):
-            self._stage = [(torch.empty_like(self.x), torch.empty_like(self.target)) for _ in range(2)]
+        kp_mode = n_kp = None
+        if len(target_hosts):
+            kp_mode = target_hosts[0].dim() == 3
+            n_kp = target_hosts[0].shape[1] if kp_mode else None
+        if getattr(self, "_stage_kind", None) != (kp_mode, n_kp):
+            tstage = (lambda: torch.empty(self.x.shape[0], n_kp, 2, dtype=torch.float32, device=self.dev)) if kp_mode else (lambda: torch.empty_like(self.target))
+            self._stage = [(torch.empty_like(self.x), tstage()) for _ in range(2)]
+            self._stage_kind = (kp_mode, n_kp)
+        if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(self.dev)
         cs = self._copy_stream
         cs.wait_stream(cur)
@@ -371,7 +387,10 @@ class FusedTrainStep:
             i = k & 1
             cur.wait_event(h2d[i])
             self.x.copy_(self._stage[i][0], non_blocking=True)
-            self.target.copy_(self._stage[i][1], non_blocking=True)
+            if kp_mode:
+                ops.create_heatmap(self._stage[i][1], self.target.shape[2], self.target.shape[3], out=self.target)
+            else:
+                self.target.copy_(self._stage[i][1], non_blocking=True)
             taken[i] = torch.cuda.Event()
             taken[i].record(cur)
             if k + 1 < n:

@@ -242,7 +242,8 @@ def _pack_train_jobs(ts: TrainState) -> None:
 
 
 # ---------------------------------------------------------------------------------------------- forward (train mode)
-def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = True, before_decoder=None, after_input=None) -> Tuple[torch.Tensor, ...]:
+def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = True, before_decoder=None, after_input=None,
+                  channels_last: bool = False) -> Tuple[torch.Tensor, ...]:
     eng, t, P, m = ts.eng, ts.t, ts.packed, ts.eng.model
     B, H, W = ts.B, ts.H, ts.W
     ncls = m.n_classes
@@ -250,7 +251,10 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
     ops.tag("fwd")
     if update_running_stats:
         eng._packed_key = None  # running statistics change below without a torch version bump: drop the eval-mode fold cache
-    ops.nchw_to_nhwc16(x, t["x16"])
+    if x.dtype == torch.uint8:  # 8-bit images ([B,C,H,W] or, with channels_last, [B,H,W,C]): ToTensor's 1/255 fused into the layout change
+        ops.u8_to_nhwc(x, t["x16"], channels_last)
+    else:
+        ops.nchw_to_nhwc16(x, t["x16"])
     if after_input is not None:
         after_input()  # join point for the weight re-packing the caller put on a side stream
     src = t["x16"]
