@@ -361,8 +361,9 @@ class FusedTrainStep:
             kp_mode = target_hosts[0].dim() == 3
             n_kp = target_hosts[0].shape[1] if kp_mode else None
         if getattr(self, "_stage_kind", None) != (kp_mode, n_kp):
-            tstage = (lambda: torch.empty(self.x.shape[0], n_kp, 2, dtype=torch.float32, device=self.dev)) if kp_mode else (lambda: torch.empty_like(self.target))
-            self._stage = [(torch.empty_like(self.x), tstage()) for _ in range(2)]
+            # staged images, staged targets and (key-point mode) the staged key points the targets are synthesised from
+            self._stage = [(torch.empty_like(self.x), torch.empty_like(self.target),
+                            torch.empty(self.x.shape[0], n_kp, 2, dtype=torch.float32, device=self.dev) if kp_mode else None) for _ in range(2)]
             self._stage_kind = (kp_mode, n_kp)
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(self.dev)
@@ -378,7 +379,11 @@ class FusedTrainStep:
                 if taken[i] is not None:
                     cs.wait_event(taken[i])  # the staged batch has been moved into the step's inputs
                 self._stage[i][0].copy_(x_hosts[k], non_blocking=True)
-                self._stage[i][1].copy_(target_hosts[k], non_blocking=True)
+                if kp_mode:  # the target synthesis of batch k+1 runs on the copy stream too, next to the step of batch k
+                    self._stage[i][2].copy_(target_hosts[k], non_blocking=True)
+                    ops.create_heatmap(self._stage[i][2], self.target.shape[2], self.target.shape[3], out=self._stage[i][1])
+                else:
+                    self._stage[i][1].copy_(target_hosts[k], non_blocking=True)
                 h2d[i].record(cs)
 
         if n:
@@ -387,10 +392,7 @@ class FusedTrainStep:
             i = k & 1
             cur.wait_event(h2d[i])
             self.x.copy_(self._stage[i][0], non_blocking=True)
-            if kp_mode:
-                ops.create_heatmap(self._stage[i][1], self.target.shape[2], self.target.shape[3], out=self.target)
-            else:
-                self.target.copy_(self._stage[i][1], non_blocking=True)
+            self.target.copy_(self._stage[i][1], non_blocking=True)
             taken[i] = torch.cuda.Event()
             taken[i].record(cur)
             if k + 1 < n:
