@@ -2,6 +2,7 @@
 //   weight packing (fp32 OIHW state_dict -> bf16 UMMA B-operand layout),
 //   NCHW fp32 -> NHWC bf16 input conversion, 2x2 max-pool, and heat-map peak extraction.
 // All are plain coalesced/vectorised CUDA-core kernels (HBM-bound byte movers).
+#include <cooperative_groups.h>
 #include "common.h"
 #include "../../include/unpp.h"
 #include "b2_blocks.h"
@@ -480,22 +481,29 @@ __global__ void __launch_bounds__(256) topk_peaks_kernel(const float* __restrict
 // per point exp(-0.5 * dist / 3) with the Euclidean DISTANCE (not squared) in float64; planes 0 and 2 are
 // assigned (helper.py:106,142), planes 1 and 3 are summed (float32 += float64) and ALWAYS divided by their
 // maximum (helper.py:122-123,158-159) — also when plane 3 holds a single point (6 key points).
-// One CTA per (n, channel) plane: pass 1 writes the sums and reduces the plane maximum, pass 2 normalises.
-__global__ void __launch_bounds__(256) create_heatmap_kernel(const float* __restrict__ kp, int npts, int H, int W, float* __restrict__ out) {
+// A thread-block CLUSTER of 8 CTAs per (n, channel) plane (1024 CTAs at batch 32: the fp64 sqrt / exp chains need ~50 warps per SM
+// in flight; one CTA per plane ran at 8): every CTA owns one eighth of the pixels, pass 1 writes the sums and reduces the CTA's
+// maximum, the eight maxima are exchanged through distributed shared memory, pass 2 normalises the CTA's own pixels.
+constexpr int kHmCluster = 8;
+__global__ void __cluster_dims__(kHmCluster, 1, 1) __launch_bounds__(256) create_heatmap_kernel(const float* __restrict__ kp, int npts, int H, int W, float* __restrict__ out) {
   unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
   unpp::pdl_trigger();
-  const int n = blockIdx.x >> 2, ch = blockIdx.x & 3;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int plane_idx = blockIdx.y, rank = blockIdx.x;  // gridDim.x == cluster size: blockIdx.x is the rank inside the cluster
+  const int n = plane_idx >> 2, ch = plane_idx & 3;
   const int p0 = ch == 0 ? 0 : ch == 1 ? 1 : ch == 2 ? 4 : 5, p1 = ch == 0 ? 1 : ch == 1 ? 4 : ch == 2 ? 5 : npts;
-  float* plane = out + size_t(blockIdx.x) * H * W;
+  float* plane = out + size_t(plane_idx) * H * W;
   double cx[4], cy[4];
   const int np = p1 - p0;
   for (int i = 0; i < 4; ++i) {
     cx[i] = i < np ? double(kp[(size_t(n) * npts + p0 + i) * 2]) : 0.0;
     cy[i] = i < np ? double(kp[(size_t(n) * npts + p0 + i) * 2 + 1]) : 0.0;
   }
+  const int HW = H * W, seg = (HW + kHmCluster - 1) / kHmCluster, b = rank * seg, e = min(b + seg, HW);
   const bool summed = ch & 1;  // planes 1 and 3: "+=" then "/ max"
   float mx = 0.f;
-  for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+  for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
     const double x = double(i % W), y = double(i / W);
     float acc = 0.f;
     for (int k = 0; k < np && k < 4; ++k) {
@@ -506,16 +514,24 @@ __global__ void __launch_bounds__(256) create_heatmap_kernel(const float* __rest
     plane[i] = acc;
     mx = fmaxf(mx, acc);
   }
-  if (!summed) return;
   __shared__ float smax[8];
+  __shared__ float cta_max;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mx;
   __syncthreads();
-  mx = smax[0];
+  if (threadIdx.x == 0) {
+    mx = smax[0];
 #pragma unroll
-  for (int k = 1; k < 8; ++k) mx = fmaxf(mx, smax[k]);
-  for (int i = threadIdx.x; i < H * W; i += blockDim.x) plane[i] = plane[i] / mx;  // each thread re-reads only what it wrote
+    for (int k = 1; k < 8; ++k) mx = fmaxf(mx, smax[k]);
+    cta_max = mx;
+  }
+  cluster.sync();  // every CTA's maximum is published
+  mx = 0.f;
+  for (int r = 0; r < kHmCluster; ++r) mx = fmaxf(mx, *cluster.map_shared_rank(&cta_max, r));
+  cluster.sync();  // nobody leaves (and frees its shared memory) while a peer still reads it
+  if (!summed) return;
+  for (int i = b + threadIdx.x; i < e; i += blockDim.x) plane[i] = plane[i] / mx;  // each thread re-reads only what it wrote
 }
 
 // ------------------------------------------------------------------------------------------
@@ -659,7 +675,8 @@ extern "C" int unpp_maxpool2x2(const void* x, void* out, int N, int H, int W, in
 extern "C" int unpp_create_heatmap(const float* keypoints, int N, int npts, int H, int W, float* out, unpp_stream_t stream) {
   if (!keypoints || !out || N < 1 || H < 1 || W < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "create_heatmap: bad argument");
   if (npts < 6 || npts > 9) return unpp::fail(UNPP_ERR_UNSUPPORTED, "create_heatmap: the reference's grouping needs 6..9 key points (7 in the trainer)");
-  unpp::launch(create_heatmap_kernel, N * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream), keypoints, npts, H, W, out);
+  if (N * 4 > 65535) return unpp::fail(UNPP_ERR_UNSUPPORTED, "create_heatmap: at most 16383 images per call");
+  unpp::launch(create_heatmap_kernel, dim3(kHmCluster, N * 4), 256, 0, reinterpret_cast<cudaStream_t>(stream), keypoints, npts, H, W, out);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("create_heatmap: launch");
   return UNPP_OK;
 }
