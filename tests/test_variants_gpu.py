@@ -372,3 +372,47 @@ def test_first_layer_mode_equals_the_16_channel_path():
         b = m(x)
     for u, v in zip(a, b):
         assert float((u - v).abs().max()) <= 2e-2
+
+
+# ---------------------------------------------------------------------------------------------- other constructor values (models/unet.py:206,242-244)
+@pytest.mark.parametrize("in_channels,n_classes", [(1, 1), (4, 8), (5, 2), (3, 3)])
+def test_other_in_channels_and_n_classes_inference_and_training(in_channels, n_classes):
+    """``UNet_Nested(in_channels=..., n_classes=...)``: the first conv reads 1..16 input channels (<= 4: the 8-byte-pixel first-layer mode,
+    above: the 16-channel padded tensor), the heads produce 1..8 classes.  Inference against the oracle, the training step through the
+    teacher-forced check (every stored tensor to one bf16 ulp, every gradient to 1e-3) and the key points bit-exact."""
+    from oracle import teacher_forced as T
+    kw = dict(in_channels=in_channels, n_classes=n_classes)
+    sd = O.synth_state_dict(seed=91, **kw)
+    m = pkg.UNet_Nested(**kw)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(v.shape)) for k, v in sd.items()]
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    g = torch.Generator().manual_seed(in_channels * 10 + n_classes)
+    B, H, W = 2, 32, 48
+    x = torch.randn(B, in_channels, H, W, generator=g)
+    with torch.no_grad():
+        outs = m(x.to(DEV))
+    ref = O.forward(sd, x)
+    for o, r in zip(outs, ref):
+        assert tuple(o.shape) == (B, n_classes, H, W)
+        assert float((o.cpu() - r).abs().max()) <= 3e-2
+    xy, val, heats = m.predict_keypoints(x.to(DEV))
+    rxy, _ = O.argmax_keypoints(heats[2].cpu().numpy())
+    assert np.array_equal(xy.cpu().numpy(), rxy)
+    m.train()
+    m.drop_out.p = 0.0
+    target = torch.rand(B, n_classes, H, W, generator=g)
+    outs = m(x.to(DEV))
+    (sum(F.mse_loss(o, target.to(DEV)) for o in outs) / 3).backward()
+    torch.cuda.synchronize()
+    ts = m._engine(torch.device("cuda", torch.cuda.current_device()))._train_states[(B, H, W)]
+    rep = T.verify_step(ts.t, ts.heats, {k: p.grad for k, p in m.named_parameters()}, sd, x.to(DEV), target=target)
+    assert not rep.check(), rep.check()
+
+
+def test_feature_scale_other_than_two_is_rejected_with_a_reason():
+    """feature_scale changes every channel count of the network (8- or 256-channel levels, a 32-channel head input): outside the kernels'
+    16..128-channel tiling.  The reference trainer never passes it (trainer.py:337,340 build the model with no arguments)."""
+    m = pkg.UNet_Nested(feature_scale=4).to(DEV).eval()
+    with pytest.raises(ValueError, match="feature_scale"):
+        m(torch.randn(1, 3, 32, 32, device=DEV))
