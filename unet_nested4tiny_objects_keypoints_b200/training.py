@@ -81,7 +81,7 @@ class TrainState:
                 act(f"dpool{lvl}", lvl)  # un-pooled gradient flowing into X_{lvl}0
                 act(f"tmp{lvl}", lvl)
             for n in (1, 2):
-                for nm in ("mean", "istd"):
+                for nm in ("mean", "istd", "scale", "shift"):
                     t[f"{node}.bn{n}.{nm}"] = torch.empty(f[lvl], **f32)
                 t[f"{node}.bn{n}.sums"] = torch.empty(2 * f[lvl], **f32)
         for name in DECODER_ORDER:
