@@ -242,20 +242,11 @@ int unpp_bn_finalize(const float* partial, int nparts, int C, float count, const
 /* y = relu(z*scale + shift) on NHWC bf16; pooled (optional) = 2x2/2 max pool of y. */
 int unpp_bn_relu(const void* z, const float* scale, const float* shift, void* y, void* pooled, int N, int H, int W, int C,
                  unpp_stream_t stream);
-/* unpp_bn_finalize + unpp_bn_relu in ONE launch: every block reduces the partials itself (same summation order, same bits), block 0
- * publishes mean / istd and updates the running statistics.  C <= 256. */
-int unpp_bn_relu_stats(const void* z, const float* partial, int nparts, float count, const float* gamma, const float* beta, float* running_mean,
-                       float* running_var, float momentum, float eps, float* mean, float* istd, void* y, void* pooled, int N, int H, int W, int C,
-                       unpp_stream_t stream);
 /* MaxPool2d(2) backward: dx[N,H,W,C] from dpooled[N,H/2,W/2,C] and the forward input x (first max wins). */
 int unpp_maxpool2x2_bwd(const void* x, const void* dpooled, void* dx, int N, int H, int W, int C, unpp_stream_t stream);
 /* BatchNorm backward apply: dz = gamma*istd*(dyh - sums[c]/count - xhat*sums[C+c]/count), xhat=(z-mean)*istd. */
 int unpp_bn_bwd_apply(const void* dyh, const void* z, const float* mean, const float* istd, const float* gamma, const float* sums,
                       float count, void* dz, int N, int H, int W, int C, unpp_stream_t stream);
-/* The same with the reduction of the dgrad epilogue's [nparts][2C] partials (sum dyh, sum dyh*xhat) as its prologue: one launch instead of
- * unpp_reduce_partials + unpp_bn_bwd_apply; block 0 writes the reduced sums to sums_out[2C] (= dbeta, dgamma).  C <= 256. */
-int unpp_bn_bwd_apply_stats(const void* dyh, const void* z, const float* mean, const float* istd, const float* gamma, const float* partial, int nparts,
-                            float* sums_out, float count, void* dz, int N, int H, int W, int C, unpp_stream_t stream);
 /* Head backward (sigmoid' + 1x1 conv dgrad/wgrad + dropout mask).  Exactly one of dheat (upstream
  * gradient, fp32 NCHW) and target is non-NULL.  With target the loss gradient is fused:
  *   loss_kind 0, nn.MSELoss (trainer/trainer.py:427): dheat = coef*(heat-target), loss partial = sum (heat-target)^2

@@ -196,89 +196,17 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
   }
 }
 
-// The statistics finalisation as the PROLOGUE of the kernel that applies them (one launch instead of two on the critical path of
-// every encoder conv): every block reduces the conv epilogue's partials for all C channels into shared memory with exactly the
-// summation order of bn_finalize_kernel (same bits in every block and as the stand-alone kernel); block 0 publishes mean / inverse
-// std (the backward pass reads them) and updates the running statistics.
-struct BnStats {
-  const float* partial;  // [nparts][2][C]
-  int nparts, C;
-  float count;
-  const float* gamma;
-  const float* beta;
-  float* running_mean;
-  float* running_var;
-  float momentum, eps;
-  float* mean;
-  float* istd;
-};
-__device__ __forceinline__ void bn_stats_prologue(const BnStats& a, float* s_scale, float* s_shift) {
-  __shared__ double r1[8][32], r2[8][32];
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  for (int cb = 0; cb < a.C; cb += 32) {
-    const int c = cb + l;
-    double s1 = 0.0, s2 = 0.0;
-    if (c < a.C) {
-      int p = w;
-      for (; p + 56 < a.nparts; p += 64) {
-        float x[8], y[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = __ldg(a.partial + (size_t(p + 8 * k) * 2 + 0) * a.C + c), y[k] = __ldg(a.partial + (size_t(p + 8 * k) * 2 + 1) * a.C + c);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s1 += double(x[k]), s2 += double(y[k]);
-      }
-      for (; p < a.nparts; p += 8) {
-        s1 += double(__ldg(a.partial + (size_t(p) * 2 + 0) * a.C + c));
-        s2 += double(__ldg(a.partial + (size_t(p) * 2 + 1) * a.C + c));
-      }
-    }
-    r1[w][l] = s1, r2[w][l] = s2;
-    __syncthreads();
-    if (w == 0 && c < a.C) {
-      s1 = 0.0, s2 = 0.0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s1 += r1[k][l], s2 += r2[k][l];
-      const double m = s1 / a.count;
-      double var = s2 / a.count - m * m;
-      if (var < 0.0) var = 0.0;
-      const float is = float(1.0 / sqrt(var + double(a.eps)));
-      const float sc = a.gamma[c] * is;
-      s_scale[c] = sc;
-      s_shift[c] = a.beta[c] - float(m) * sc;
-      if (blockIdx.x == 0) {
-        a.mean[c] = float(m);
-        a.istd[c] = is;
-        if (a.running_mean) {
-          const double unbiased = a.count > 1.f ? var * double(a.count) / double(a.count - 1.f) : var;
-          a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * float(m);
-          a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * float(unbiased);
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
-
 // y = relu(z * scale[c] + shift[c]) (bf16 NHWC, 8 channels per thread); optional 2x2 max-pooled copy.
-// FUSED: scale / shift come from bn_stats_prologue (shared memory) instead of a preceding bn_finalize launch.
-template <bool FUSED>
-__global__ void __launch_bounds__(256) bn_relu_kernel(const uint4* __restrict__ z, const float* __restrict__ scale_g, const float* __restrict__ shift_g, uint4* __restrict__ y,
-                                                      long total, int C8, BnStats st) {
+__global__ void bn_relu_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift, uint4* __restrict__ y,
+                               long total, int C8) {
   unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
   unpp::pdl_trigger();
-  __shared__ float s_scale[FUSED ? 256 : 1], s_shift[FUSED ? 256 : 1];
-  const float* scale = scale_g;
-  const float* shift = shift_g;
-  if constexpr (FUSED) {
-    bn_stats_prologue(st, s_scale, s_shift);
-    scale = s_scale, shift = s_shift;
-  }
   const long stride = long(gridDim.x) * blockDim.x, i0 = blockIdx.x * long(blockDim.x) + threadIdx.x;
   if (stride % C8 == 0) {  // the thread keeps its eight channels for the whole loop: their coefficients live in registers
     const int c0 = int(i0 % C8) * 8;
     float sc[8], sh[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) sc[k] = scale[c0 + k], sh[k] = shift[c0 + k];
+    for (int k = 0; k < 8; ++k) sc[k] = __ldg(scale + c0 + k), sh[k] = __ldg(shift + c0 + k);
     for (long i = i0; i < total; i += stride) {
       float f[8];
       unpack8(__ldg(z + i), f);
@@ -293,22 +221,14 @@ __global__ void __launch_bounds__(256) bn_relu_kernel(const uint4* __restrict__ 
     float f[8];
     unpack8(__ldg(z + i), f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], scale[c0 + k], shift[c0 + k]), 0.f);
+    for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], __ldg(scale + c0 + k), __ldg(shift + c0 + k)), 0.f);
     y[i] = pack8(f);
   }
 }
-template <bool FUSED>
-__global__ void __launch_bounds__(256) bn_relu_pool_kernel(const uint4* __restrict__ z, const float* __restrict__ scale_g, const float* __restrict__ shift_g,
-                                                           uint4* __restrict__ y, uint4* __restrict__ pooled, int N, int H, int W, int C8, BnStats st) {
+__global__ void bn_relu_pool_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                                    uint4* __restrict__ y, uint4* __restrict__ pooled, int N, int H, int W, int C8) {
   unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
   unpp::pdl_trigger();
-  __shared__ float s_scale[FUSED ? 256 : 1], s_shift[FUSED ? 256 : 1];
-  const float* scale = scale_g;
-  const float* shift = shift_g;
-  if constexpr (FUSED) {
-    bn_stats_prologue(st, s_scale, s_shift);
-    scale = s_scale, shift = s_shift;
-  }
   const int Ho = H / 2, Wo = W / 2;
   const long total = long(N) * Ho * Wo * C8;
   for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
@@ -321,7 +241,7 @@ __global__ void __launch_bounds__(256) bn_relu_pool_kernel(const uint4* __restri
     const long n = t / Ho;
     float sc[8], sh[8], mx[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) sc[k] = scale[c8 * 8 + k], sh[k] = shift[c8 * 8 + k], mx[k] = 0.f;
+    for (int k = 0; k < 8; ++k) sc[k] = __ldg(scale + c8 * 8 + k), sh[k] = __ldg(shift + c8 * 8 + k), mx[k] = 0.f;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const long idx = ((n * H + 2 * yo + (q >> 1)) * W + 2 * xo + (q & 1)) * C8 + c8;
@@ -382,30 +302,12 @@ __global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __r
 
 // BatchNorm backward, apply pass: dz = gamma*istd * (dyh - s1/M - xhat * s2/M), xhat = (z-mean)*istd,
 // with s1 = sum dyh (= dbeta), s2 = sum dyh*xhat (= dgamma) reduced beforehand (conv_tc epilogue stats).
-// FUSED: (s1, s2) are reduced here from the [nparts][2C] partials of the dgrad epilogue — every block with the summation order of
-// reduce_partials_kernel (same bits); block 0 publishes them to `sums_out` (the deferred dgamma / dbeta reductions read them).
-template <bool FUSED>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ dyh, const uint4* __restrict__ z, const float* __restrict__ mean,
-                                                           const float* __restrict__ istd, const float* __restrict__ gamma, const float* __restrict__ sums_g,
-                                                           float inv_count, uint4* __restrict__ dz, long total, int C8, const float* __restrict__ partial, int nparts,
-                                                           float* __restrict__ sums_out) {
+__global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dyh, const uint4* __restrict__ z, const float* __restrict__ mean,
+                                    const float* __restrict__ istd, const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count,
+                                    uint4* __restrict__ dz, long total, int C8) {
   unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
   unpp::pdl_trigger();
   const int C = C8 * 8;
-  __shared__ float s_sums[FUSED ? 512 : 1];
-  const float* sums = sums_g;
-  if constexpr (FUSED) {
-    for (int base = 0; base < 2 * C; base += 32) {
-      const int i = base + (threadIdx.x & 31);
-      const float t = sliced_sum(nparts, [&](int p) { return i < 2 * C ? __ldg(partial + size_t(p) * 2 * C + i) : 0.f; });
-      if (threadIdx.x < 32 && i < 2 * C) {
-        s_sums[i] = t;
-        if (blockIdx.x == 0) sums_out[i] = t;
-      }
-    }
-    __syncthreads();
-    sums = s_sums;
-  }
   const long stride = long(gridDim.x) * blockDim.x, i0 = blockIdx.x * long(blockDim.x) + threadIdx.x;
   if (stride % C8 == 0) {
     // The thread keeps its eight channels for the whole loop: dz = a*dyh + b*z + c with per-channel coefficients in registers
@@ -415,7 +317,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = c0 + k;
-      const float is = __ldg(istd + c), gm = __ldg(gamma + c) * is, s1 = sums[c] * inv_count, s2 = sums[C + c] * inv_count;
+      const float is = __ldg(istd + c), gm = __ldg(gamma + c) * is, s1 = __ldg(sums + c) * inv_count, s2 = __ldg(sums + C + c) * inv_count;
       ca[k] = gm, cb[k] = -gm * is * s2, cc[k] = gm * (__ldg(mean + c) * is * s2 - s1);
     }
     for (long i = i0; i < total; i += stride) {
@@ -438,7 +340,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
       const int c = c0 + k;
       const float is = __ldg(istd + c);
       const float xh = (zz[k] - __ldg(mean + c)) * is;
-      o[k] = __ldg(gamma + c) * is * (g[k] - sums[c] * inv_count - xh * sums[C + c] * inv_count);
+      o[k] = __ldg(gamma + c) * is * (g[k] - __ldg(sums + c) * inv_count - xh * __ldg(sums + C + c) * inv_count);
     }
     dz[i] = pack8(o);
   }
@@ -695,35 +597,15 @@ extern "C" int unpp_bn_relu(const void* z, const float* scale, const float* shif
   if (pooled) {
     if ((H & 1) || (W & 1)) return unpp::fail(UNPP_ERR_BAD_ARG, "bn_relu: pooling needs even H and W");
     const long total = long(N) * (H / 2) * (W / 2) * (C / 8);
-    unpp::launch(bn_relu_pool_kernel<false>, grid_for(total, 256), 256, 0, STREAM(stream), reinterpret_cast<const uint4*>(z), scale, shift,
+    unpp::launch(bn_relu_pool_kernel, grid_for(total, 256), 256, 0, STREAM(stream), reinterpret_cast<const uint4*>(z), scale, shift,
                                                                           reinterpret_cast<uint4*>(y), reinterpret_cast<uint4*>(pooled), N, H, W,
-                                                                          C / 8, BnStats{});
+                                                                          C / 8);
   } else {
     const long total = long(N) * H * W * (C / 8);
-    unpp::launch(bn_relu_kernel<false>, grid_for(total, 256), 256, 0, STREAM(stream), reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<uint4*>(y),
-                                                                     total, C / 8, BnStats{});
+    unpp::launch(bn_relu_kernel, grid_for(total, 256), 256, 0, STREAM(stream), reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<uint4*>(y),
+                                                                     total, C / 8);
   }
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("bn_relu: launch");
-  return UNPP_OK;
-}
-
-extern "C" int unpp_bn_relu_stats(const void* z, const float* partial, int nparts, float count, const float* gamma, const float* beta, float* running_mean,
-                                  float* running_var, float momentum, float eps, float* mean, float* istd, void* y, void* pooled, int N, int H, int W, int C,
-                                  unpp_stream_t stream) {
-  if (!z || !partial || !gamma || !beta || !mean || !istd || !y || nparts < 1 || N < 1 || H < 1 || W < 1 || C % 8 || C > 256 || !(count >= 1.f))
-    return unpp::fail(UNPP_ERR_BAD_ARG, "bn_relu_stats: bad argument (C %% 8 == 0, C <= 256)");
-  const BnStats st{partial, nparts, C, count, gamma, beta, running_mean, running_var, momentum, eps, mean, istd};
-  if (pooled) {
-    if ((H & 1) || (W & 1)) return unpp::fail(UNPP_ERR_BAD_ARG, "bn_relu_stats: pooling needs even H and W");
-    const long total = long(N) * (H / 2) * (W / 2) * (C / 8);
-    unpp::launch(bn_relu_pool_kernel<true>, grid_for(total, 256), 256, 0, STREAM(stream), reinterpret_cast<const uint4*>(z), static_cast<const float*>(nullptr),
-                 static_cast<const float*>(nullptr), reinterpret_cast<uint4*>(y), reinterpret_cast<uint4*>(pooled), N, H, W, C / 8, st);
-  } else {
-    const long total = long(N) * H * W * (C / 8);
-    unpp::launch(bn_relu_kernel<true>, grid_for(total, 256), 256, 0, STREAM(stream), reinterpret_cast<const uint4*>(z), static_cast<const float*>(nullptr),
-                 static_cast<const float*>(nullptr), reinterpret_cast<uint4*>(y), total, C / 8, st);
-  }
-  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("bn_relu_stats: launch");
   return UNPP_OK;
 }
 
@@ -742,20 +624,9 @@ extern "C" int unpp_bn_bwd_apply(const void* dyh, const void* z, const float* me
   if (!dyh || !z || !mean || !istd || !gamma || !sums || !dz || N < 1 || H < 1 || W < 1 || C % 8 || !(count >= 1.f))
     return unpp::fail(UNPP_ERR_BAD_ARG, "bn_bwd_apply: bad argument");
   const long total = long(N) * H * W * (C / 8);
-  unpp::launch(bn_bwd_apply_kernel<false>, grid_for(total, 256), 256, 0, STREAM(stream), reinterpret_cast<const uint4*>(dyh), reinterpret_cast<const uint4*>(z), mean,
-               istd, gamma, sums, 1.f / count, reinterpret_cast<uint4*>(dz), total, C / 8, static_cast<const float*>(nullptr), 0, static_cast<float*>(nullptr));
+  unpp::launch(bn_bwd_apply_kernel, grid_for(total, 256), 256, 0, STREAM(stream), reinterpret_cast<const uint4*>(dyh), reinterpret_cast<const uint4*>(z), mean,
+                                                                        istd, gamma, sums, 1.f / count, reinterpret_cast<uint4*>(dz), total, C / 8);
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("bn_bwd_apply: launch");
-  return UNPP_OK;
-}
-
-extern "C" int unpp_bn_bwd_apply_stats(const void* dyh, const void* z, const float* mean, const float* istd, const float* gamma, const float* partial, int nparts,
-                                       float* sums_out, float count, void* dz, int N, int H, int W, int C, unpp_stream_t stream) {
-  if (!dyh || !z || !mean || !istd || !gamma || !partial || !sums_out || !dz || nparts < 1 || N < 1 || H < 1 || W < 1 || C % 8 || C > 256 || !(count >= 1.f))
-    return unpp::fail(UNPP_ERR_BAD_ARG, "bn_bwd_apply_stats: bad argument (C %% 8 == 0, C <= 256)");
-  const long total = long(N) * H * W * (C / 8);
-  unpp::launch(bn_bwd_apply_kernel<true>, grid_for(total, 256), 256, 0, STREAM(stream), reinterpret_cast<const uint4*>(dyh), reinterpret_cast<const uint4*>(z), mean,
-               istd, gamma, static_cast<const float*>(nullptr), 1.f / count, reinterpret_cast<uint4*>(dz), total, C / 8, partial, nparts, sums_out);
-  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("bn_bwd_apply_stats: launch");
   return UNPP_OK;
 }
 

@@ -448,25 +448,6 @@ def bn_relu(z, scale, shift, y, pooled=None) -> None:
         _lib.check(lib().unpp_bn_relu(z.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), _ptr(pooled), N, H, W, Cc, _stream()), "unpp_bn_relu")
 
 
-def bn_relu_stats(z, partial, nparts, count, gamma, beta, running_mean, running_var, momentum, eps, mean, istd, y, pooled=None) -> None:
-    """bn_finalize + bn_relu in one launch (the statistics reduction is the prologue of the apply kernel)."""
-    N, H, W, Cc = z.shape
-    _count()
-    with _Traced("bn_relu_stats", 0, 0):
-        _lib.check(lib().unpp_bn_relu_stats(z.data_ptr(), partial.data_ptr(), nparts, float(count), gamma.data_ptr(), beta.data_ptr(), _ptr(running_mean), _ptr(running_var),
-                                            float(momentum), float(eps), mean.data_ptr(), istd.data_ptr(), y.data_ptr(), _ptr(pooled), N, H, W, Cc, _stream()),
-                   "unpp_bn_relu_stats")
-
-
-def bn_bwd_apply_stats(dyh, z, mean, istd, gamma, partial, nparts, sums_out, count, dz) -> None:
-    """reduce_partials (sum dyh, sum dyh*xhat) + bn_bwd_apply in one launch."""
-    N, H, W, Cc = z.shape
-    _count()
-    with _Traced("bn_bwd_apply_stats", 0, 0):
-        _lib.check(lib().unpp_bn_bwd_apply_stats(dyh.data_ptr(), z.data_ptr(), mean.data_ptr(), istd.data_ptr(), gamma.data_ptr(), partial.data_ptr(), nparts,
-                                                 sums_out.data_ptr(), float(count), dz.data_ptr(), N, H, W, Cc, _stream()), "unpp_bn_bwd_apply_stats")
-
-
 def maxpool_bwd(x, dpooled, dx) -> None:
     N, H, W, Cc = x.shape
     _count()

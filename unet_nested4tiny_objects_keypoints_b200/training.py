@@ -284,14 +284,18 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
             ops.conv([src], B, h, w, P[key], c, nt, 9, bias=conv.bias, out=z, stats_partial=part)
             pre = f"{name}.bn{n}"
             mom = 0.1 if bn.momentum is None else bn.momentum
+            ops.bn_finalize(part, g, c, count, bn.weight, bn.bias, bn.running_mean if update_running_stats else None,
+                            bn.running_var if update_running_stats else None, mom, bn.eps, t[pre + ".mean"], t[pre + ".istd"], t[pre + ".scale"],
+                            t[pre + ".shift"])
             if update_running_stats:
                 tracked.append(bn.num_batches_tracked)
                 stat_buffers += [bn.running_mean, bn.running_var]
-            # statistics finalisation (mean, inverse std, running-stat update) + normalise + ReLU (+ 2x2 max pool): ONE launch
-            y, pooled = (t[f"{name}.a"], None) if n == 1 else (t[f"X{lvl}0"], t[f"P{lvl}0"] if lvl < 3 else None)
-            ops.bn_relu_stats(z, part, g, count, bn.weight, bn.bias, bn.running_mean if update_running_stats else None,
-                              bn.running_var if update_running_stats else None, mom, bn.eps, t[pre + ".mean"], t[pre + ".istd"], y, pooled)
-            src = y if n == 1 else pooled
+            if n == 1:
+                ops.bn_relu(z, t[pre + ".scale"], t[pre + ".shift"], t[f"{name}.a"])
+                src = t[f"{name}.a"]
+            else:
+                ops.bn_relu(z, t[pre + ".scale"], t[pre + ".shift"], t[f"X{lvl}0"], t[f"P{lvl}0"] if lvl < 3 else None)
+                src = t[f"P{lvl}0"] if lvl < 3 else None
     if tracked:
         torch._foreach_add_(tracked, 1)  # the eight int64 num_batches_tracked counters: one launch
         if not torch.cuda.is_current_stream_capturing():  # (a captured step bumps the versions once per replay, fused.FusedTrainStep.step_device)
@@ -527,11 +531,11 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
             deconv_dgrad(deconv_into[lvl], h, w, dyh2, addend=addend, mask=t[node], stats=dict(stats_partial=part, **aux2))
         if has_bn:
             # BatchNorm 2 backward: sums = (dbeta, dgamma); dz = gamma*istd*(dyh - s1/M - xhat*s2/M)
-            # (the reduction of the dgrad epilogue's partials is the prologue of the apply kernel, which publishes the sums = dbeta, dgamma)
-            ops.bn_bwd_apply_stats(dyh2, t[f"{name}.z2"], t[bn2 + ".mean"], t[bn2 + ".istd"], seq2[1].weight, part, g, t[bn2 + ".sums"], count, dz2)
+            ops.reduce_partials(part, g, 2 * c, 2 * c, t[bn2 + ".sums"])
             ops.reduce_partials(t[bn2 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv2.1.bias"), defer=True)
             ops.reduce_partials(t[bn2 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv2.1.weight"), partial_offset=c, defer=True)
             # {name}.conv2.0.bias: a bias in front of BatchNorm has an exactly zero gradient; G is zero-initialised and never written there
+            ops.bn_bwd_apply(dyh2, t[f"{name}.z2"], t[bn2 + ".mean"], t[bn2 + ".istd"], seq2[1].weight, t[bn2 + ".sums"], count, dz2)
         else:
             bias_from_stats(part, g, c, f"{name}.conv2.0.bias")
         wgrad_conv([t[f"{name}.a"]], dz2, h, w, f"{name}.conv2.0.weight")
@@ -543,9 +547,10 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
             dyh1 = t[f"{name}.dyh1"]
             ops.conv([dz2], B, h, w, P[key], c, P[key + ".nt"], 9, out=dyh1, relu_mask_src=t[f"{name}.a"], stats_partial=part, stats_aux=t[f"{name}.z1"],
                      aux_mean=t[bn1 + ".mean"], aux_istd=t[bn1 + ".istd"])
-            ops.bn_bwd_apply_stats(dyh1, t[f"{name}.z1"], t[bn1 + ".mean"], t[bn1 + ".istd"], seq1[1].weight, part, g, t[bn1 + ".sums"], count, dz1)
+            ops.reduce_partials(part, g, 2 * c, 2 * c, t[bn1 + ".sums"])
             ops.reduce_partials(t[bn1 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv1.1.bias"), defer=True)
             ops.reduce_partials(t[bn1 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv1.1.weight"), partial_offset=c, defer=True)
+            ops.bn_bwd_apply(dyh1, t[f"{name}.z1"], t[bn1 + ".mean"], t[bn1 + ".istd"], seq1[1].weight, t[bn1 + ".sums"], count, dz1)
         else:
             g, part = stats_buf([c], c, P[key + ".nt"], 9, h, w, key=f"stats:{name}.conv1.0.bias")
             ops.conv([dz2], B, h, w, P[key], c, P[key + ".nt"], 9, out=dz1, relu_mask_src=t[f"{name}.a"], stats_partial=part)
