@@ -102,11 +102,6 @@ typedef struct UnppConvArgs {
   /* Fused nn.MaxPool2d(2) of the output (models/unet.py:219,258,260,262): NHWC bf16 [N, H/2, W/2, n_total], written next to
    * `out` by the inference epilogue (conv mode, relu = 1, even H and W, no head, no training operand).  NULL = no pooling. */
   void* pooled;
-  /* The ReLU mask of a training step as BITS: one 16-bit word per (pixel, 16-channel group) of an NHWC tensor, bit k = (y[16g + k] > 0),
-   * i.e. uint16 [N, H, W, C/16].  relu_bits_out: written by a forward launch (relu = 1) for its output; relu_bits: read by the dgrad
-   * launch instead of relu_mask_src (2 bytes instead of 32 per pixel and 16 channels).  Conv mode; not with the generic deconv epilogue. */
-  const uint16_t* relu_bits;
-  uint16_t* relu_bits_out;
 } UnppConvArgs;
 
 const char* unpp_last_error(void);
@@ -244,9 +239,8 @@ int unpp_reduce_partials(const float* partial, int nparts, long stride, int n, f
 int unpp_bn_finalize(const float* partial, int nparts, int C, float count, const float* gamma, const float* beta, float* running_mean,
                      float* running_var, float momentum, float eps, float* mean, float* istd, float* scale, float* shift,
                      unpp_stream_t stream);
-/* y = relu(z*scale + shift) on NHWC bf16; pooled (optional) = 2x2/2 max pool of y; relu_bits (optional) = the mask y > 0 as bits, one byte
- * per (pixel, 8 channels) = the uint16 [N,H,W,C/16] words of UnppConvArgs.relu_bits (C % 16 == 0 then). */
-int unpp_bn_relu(const void* z, const float* scale, const float* shift, void* y, void* pooled, void* relu_bits, int N, int H, int W, int C,
+/* y = relu(z*scale + shift) on NHWC bf16; pooled (optional) = 2x2/2 max pool of y. */
+int unpp_bn_relu(const void* z, const float* scale, const float* shift, void* y, void* pooled, int N, int H, int W, int C,
                  unpp_stream_t stream);
 /* MaxPool2d(2) backward: dx[N,H,W,C] from dpooled[N,H/2,W/2,C] and the forward input x (first max wins). */
 int unpp_maxpool2x2_bwd(const void* x, const void* dpooled, void* dx, int N, int H, int W, int C, unpp_stream_t stream);

@@ -568,62 +568,3 @@ def test_target_heatmap_synthesis_matches_reference(golden):
     ref = O.create_heatmap(kp.numpy(), 40, 72)
     assert got.shape == ref.shape == (3, 4, 40, 72) and np.allclose(got, ref, rtol=0, atol=2e-6)
     assert np.allclose(got[:, [1, 3]].max(axis=(2, 3)), 1.0)  # multi-point planes are max-normalised
-
-
-def _bits_of(y_nhwc):
-    """uint16 [N,H,W,C/16] ReLU-mask words of an NHWC tensor: bit k of word g = (y[..., 16g + k] > 0)."""
-    N, H, W, C = y_nhwc.shape
-    pos = (y_nhwc.float() > 0).to(torch.int32).view(N, H, W, C // 16, 16)
-    w = (pos << torch.arange(16, device=y_nhwc.device, dtype=torch.int32)).sum(-1)
-    return (w - ((w >> 15) << 16)).to(torch.int16)
-
-
-@pytest.mark.parametrize("N,H,W,cin,cout", [(2, 32, 32, 16, 16), (1, 16, 24, 32, 32), (2, 16, 16, 64, 64), (1, 16, 16, 64, 128), (1, 8, 8, 128, 32)])
-def test_relu_mask_as_bits_producer_and_consumer(N, H, W, cin, cout):
-    """The ReLU mask of a training step travels as one bit per element (UnppConvArgs.relu_bits / relu_bits_out): the forward launch writes
-    exactly (stored value > 0); a dgrad launch masking with the bits is bit-identical — output and statistics — to masking with the
-    32-byte activation; unpp_bn_relu writes the same words for the encoder."""
-    x = nhwc(rnd(N, cin, H, W, seed=1))
-    w = rnd(cout, cin, 3, 3, seed=2, scale=(2.0 / (9 * cin)) ** 0.5).to(DEV)
-    b2 = cin == 16 and cout == 16
-    nt = ops.NTile(16, b2=True) if b2 else ops.pick_n_tile(cout, cin, 9)
-    wp = ops.pack_weights_b2(w, False, cin) if b2 else ops.pack_weights(w, 0, 9, cout, nt, cin)
-    bias = rnd(cout, seed=3, scale=0.1).to(DEV)
-    y = torch.empty(N, H, W, cout, dtype=torch.bfloat16, device=DEV)
-    bits = torch.zeros(N, H, W, cout // 16, dtype=torch.int16, device=DEV)
-    ops.conv([x], N, H, W, wp, cout, nt, 9, bias=bias, relu=True, out=y, relu_bits_out=bits)
-    y_plain = torch.empty_like(y)
-    ops.conv([x], N, H, W, wp, cout, nt, 9, bias=bias, relu=True, out=y_plain)
-    torch.cuda.synchronize()
-    assert torch.equal(y, y_plain)
-    assert torch.equal(bits, _bits_of(y))
-    assert 0.2 < float((y > 0).float().mean()) < 0.8
-    # consumer: a dgrad-style launch (another conv cout -> cout) masked by y, with statistics
-    dz = nhwc(rnd(N, cout, H, W, seed=4, scale=0.3))
-    w2 = rnd(cout, cout, 3, 3, seed=5, scale=(2.0 / (9 * cout)) ** 0.5).to(DEV)
-    b2b = cout == 16
-    nt2 = ops.NTile(16, b2=True) if b2b else ops.pick_n_tile(cout, cout, 9)
-    wp2 = ops.pack_weights_b2(w2, True, cout) if b2b else ops.pack_weights(w2, 1, 9, cout, nt2, cout)
-    g = ops.conv_grid([cout], N, H, W, cout, nt2, 9)
-    outs = []
-    for kw in (dict(relu_mask_src=y), dict(relu_bits=bits)):
-        o = torch.empty(N, H, W, cout, dtype=torch.bfloat16, device=DEV)
-        part = torch.zeros(g, 2, cout, device=DEV)
-        ops.conv([dz], N, H, W, wp2, cout, nt2, 9, out=o, stats_partial=part, **kw)
-        outs.append((o, part))
-    torch.cuda.synchronize()
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
-    assert float((outs[0][0].float().abs() > 0).float().mean()) > 0.1
-    # bn_relu writes the same words
-    scale, shift = (rnd(cout, seed=6).abs() + 0.5).to(DEV), rnd(cout, seed=7, scale=0.3).to(DEV)
-    z = nhwc(rnd(N, cout, H, W, seed=8))
-    a = torch.empty_like(z)
-    abits = torch.zeros(N, H, W, cout // 16, dtype=torch.int16, device=DEV)
-    pooled = torch.empty(N, H // 2, W // 2, cout, dtype=torch.bfloat16, device=DEV)
-    ops.bn_relu(z, scale, shift, a, relu_bits=abits)
-    torch.cuda.synchronize()
-    assert torch.equal(abits, _bits_of(a))
-    abits.zero_()
-    ops.bn_relu(z, scale, shift, a, pooled, relu_bits=abits)
-    torch.cuda.synchronize()
-    assert torch.equal(abits, _bits_of(a))

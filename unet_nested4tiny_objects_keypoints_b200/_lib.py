@@ -56,8 +56,6 @@ class ConvArgs(C.Structure):
         ("lowres_C", C.c_int32),
         ("bias_classes", C.c_int32),
         ("pooled", C.c_void_p),
-        ("relu_bits", C.c_void_p),
-        ("relu_bits_out", C.c_void_p),
     ]
 
 
@@ -139,7 +137,7 @@ _SIGNATURES = {
     "unpp_reduce_partials": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "unpp_bn_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "unpp_bn_relu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "unpp_bn_relu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "unpp_maxpool2x2_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "unpp_bn_bwd_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_void_p]),

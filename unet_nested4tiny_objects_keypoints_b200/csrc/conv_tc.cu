@@ -71,8 +71,6 @@ struct ConvTcParams {
   float drop_scale;
   const __nv_bfloat16* addend;
   const __nv_bfloat16* relu_mask_src;
-  const uint16_t* relu_bits;  // backward: 1 bit per element of the forward activation (y > 0), one 16-bit word per (pixel, 16-channel group)
-  uint16_t* relu_bits_out;    // forward: write those words for the output of this launch
   float* stats_partial;
   const __nv_bfloat16* stats_aux;
   const float* aux_mean;
@@ -141,8 +139,6 @@ struct EpiArgs {
   float drop_scale;
   const __nv_bfloat16* addend;
   const __nv_bfloat16* relu_mask_src;
-  const uint16_t* relu_bits;
-  uint16_t* relu_bits_out;
   float* stats_partial;
   const __nv_bfloat16* stats_aux;
   const float* aux_mean;
@@ -297,7 +293,6 @@ template <int G>
 struct EpiOperands {  // training-only operands of the step, fetched BEFORE the TMEM load is waited for
   uint4 a[2 * G], m[2 * G], x[2 * G];
   uint32_t dbits;  // head dropout: 16 keep bits per pixel, the (up to two) pixels of the step in one word
-  uint32_t rbits;  // ReLU mask as bits (relu_bits): 16 bits per pixel, the (up to two) pixels of the step in one word
 };
 template <int G, bool HEAD, bool TRAIN>
 __device__ __forceinline__ void epi_prefetch(const EpiArgs& p, EpiOperands<G>& t, size_t eoff, bool valid) {
@@ -311,7 +306,6 @@ __device__ __forceinline__ void epi_prefetch(const EpiArgs& p, EpiOperands<G>& t
 #pragma unroll
     for (int i = 0; i < 2 * G; ++i) t.a[i] = t.m[i] = t.x[i] = z;
     t.dbits = 0xFFFFFFFFu;
-    t.rbits = 0u;
     if (valid) {
       if (p.addend) {
         const uint4* q = reinterpret_cast<const uint4*>(p.addend + eoff);
@@ -322,10 +316,6 @@ __device__ __forceinline__ void epi_prefetch(const EpiArgs& p, EpiOperands<G>& t
         const uint4* q = reinterpret_cast<const uint4*>(p.relu_mask_src + eoff);
 #pragma unroll
         for (int i = 0; i < 2 * G; ++i) t.m[i] = __ldg(q + i);
-      }
-      if (p.relu_bits) {
-        // eoff / 16 = index of the step's first (pixel, 16-channel group) word; G = 2: 16-channel tensors, two adjacent pixels (x0 even) = one aligned 32-bit word
-        t.rbits = G == 2 ? __ldg(reinterpret_cast<const uint32_t*>(p.relu_bits + (eoff >> 4))) : uint32_t(__ldg(p.relu_bits + (eoff >> 4)));
       }
       if (p.stats_aux) {
         const uint4* q = reinterpret_cast<const uint4*>(p.stats_aux + eoff);
@@ -361,7 +351,7 @@ __device__ __forceinline__ void epi_l2_prefetch(const EpiArgs& p, size_t eoff, b
   }
 }
 
-template <int G, bool HEAD, bool TRAIN, bool BITS = false>
+template <int G, bool HEAD, bool TRAIN>
 __device__ __forceinline__ void epi_finish(const EpiArgs& p, const uint32_t (&raw)[16 * G], const EpiOperands<G>& t, const float (&bias_r)[16], const float* s_bias,
                                            const float* s_head, bool relu, size_t eoff, bool valid, int n, int yy, int x0, float (&sa1)[16],
                                            float (&sa2)[16], uint32_t (&words)[8 * G]) {
@@ -408,11 +398,6 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, const uint32_t (&ra
             if (!(bf16_hi(mw[k]) > 0.f)) v[2 * k + 1] = 0.f;
           }
         }
-        if (p.relu_bits) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k)
-            if (!((t.rbits >> (16 * px + k)) & 1u)) v[k] = 0.f;
-        }
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) words[8 * px + k] = cvt_bf16x2(v[2 * k], v[2 * k + 1]);
@@ -447,24 +432,6 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, const uint32_t (&ra
 #pragma unroll
     for (int px = 0; px < G; ++px) st_global_v8(op + 32 * px, words + 8 * px);
   }
-  if constexpr (BITS) {
-    if (p.relu_bits_out) {
-      // forward of a training step: the ReLU mask of the stored (bf16, >= 0) values as bits — the backward pass reads 2 bytes per
-      // (pixel, 16 channels) instead of the 32-byte activation
-      uint32_t mb = 0;
-#pragma unroll
-      for (int px = 0; px < G; ++px) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t w = words[8 * px + k];
-          mb |= ((w & 0xFFFFu) ? 1u : 0u) << (16 * px + 2 * k);
-          mb |= ((w >> 16) ? 1u : 0u) << (16 * px + 2 * k + 1);
-        }
-      }
-      if constexpr (G == 2) *reinterpret_cast<uint32_t*>(p.relu_bits_out + (eoff >> 4)) = mb;
-      else p.relu_bits_out[eoff >> 4] = uint16_t(mb);
-    }
-  }
   if constexpr (HEAD && G == 2) {
     const size_t plane = size_t(p.H) * p.W;
     size_t o = size_t(n) * p.head_classes * plane + size_t(yy) * p.W + x0;
@@ -485,9 +452,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, const uint32_t (&ra
   }
 }
 
-// BITS: the forward launches of a training step that also write the ReLU mask of their output as bits (relu_bits_out); a separate
-// instantiation so that the inference kernels carry neither the code nor its registers.
-template <bool DECONV, bool HEAD, bool TRAIN, bool BITS = false>
+template <bool DECONV, bool HEAD, bool TRAIN>
 __global__ void __launch_bounds__(block_threads(heavy_epilogue(HEAD, TRAIN)), 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   constexpr bool kHeavy = heavy_epilogue(HEAD, TRAIN);  // backward operands / statistics in the epilogue: 168 registers, three issuers
   constexpr int kMmaWarps = mma_warps(kHeavy), kThreads = block_threads(kHeavy);
@@ -804,7 +769,6 @@ __global__ void __launch_bounds__(block_threads(heavy_epilogue(HEAD, TRAIN)), 1)
     e.dbg = p.dbg, e.bias9 = p.bias9, e.pooled = p.pooled;
     e.H = p.H, e.W = p.W, e.cout = p.cout, e.head_classes = p.head_classes, e.out = p.out, e.heat = p.heat, e.logit = p.logit;
     e.drop_mask = p.drop_mask, e.drop_scale = p.drop_scale, e.addend = p.addend, e.relu_mask_src = p.relu_mask_src;
-    e.relu_bits = p.relu_bits, e.relu_bits_out = p.relu_bits_out;
     e.stats_partial = p.stats_partial, e.stats_aux = p.stats_aux, e.aux_mean = p.aux_mean, e.aux_istd = p.aux_istd;
     const int TW = p.TW, ncols = p.ncols, nsub = p.nsub, ntiles = p.ntiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y, dbg = p.dbg, b2 = p.b2, nacc = p.nacc;
     float* const st1 = kHeavy ? &s_stats[kHeavy ? ew : 0][0][0] : nullptr;
@@ -840,12 +804,12 @@ __global__ void __launch_bounds__(block_threads(heavy_epilogue(HEAD, TRAIN)), 1)
               const bool valid = y0 < e.H && x0 < e.W;  // (even H, W: the whole 2x2 block is inside or outside)
               tmem_ld32(tb + uint32_t(jj * 64), A);
               tmem_ld_wait32(A);
-              epi_finish<2, HEAD, TRAIN, BITS>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix0 + x0) * 16, valid, n, y0, x0, sa1, sa2, wds);
+              epi_finish<2, HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix0 + x0) * 16, valid, n, y0, x0, sa1, sa2, wds);
 #pragma unroll
               for (int k = 0; k < 8; ++k) pw[k] = max_bf16x2(wds[k], wds[8 + k]);
               tmem_ld32(tb + uint32_t(jj * 64 + 32), A);
               tmem_ld_wait32(A);
-              epi_finish<2, HEAD, TRAIN, BITS>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix0 + e.W + x0) * 16, valid, n, y0 + 1, x0, sa1, sa2, wds);
+              epi_finish<2, HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix0 + e.W + x0) * 16, valid, n, y0 + 1, x0, sa1, sa2, wds);
 #pragma unroll
               for (int k = 0; k < 8; ++k) wds[k] = max_bf16x2(pw[k], max_bf16x2(wds[k], wds[8 + k]));
               if (valid) st_global_v8(e.pooled + ((size_t(n) * (e.H >> 1) + (y0 >> 1)) * (e.W >> 1) + (x0 >> 1)) * 16, wds);
@@ -875,7 +839,7 @@ __global__ void __launch_bounds__(block_threads(heavy_epilogue(HEAD, TRAIN)), 1)
               tmem_ld32(tcol + uint32_t(j * 64), A);
               epi_prefetch<2, HEAD, TRAIN>(e, tops, (rowpix + x0) * 16, valid);
               tmem_ld_wait32(A);
-              epi_finish<2, HEAD, TRAIN, BITS>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix + x0) * 16, valid, n, yy, x0, sa1, sa2, wds);
+              epi_finish<2, HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix + x0) * 16, valid, n, yy, x0, sa1, sa2, wds);
             }
           } else {  // two TMEM buffers: the load of the next step is in flight while this one is finished
             uint32_t A[32], B[32];
@@ -885,11 +849,11 @@ __global__ void __launch_bounds__(block_threads(heavy_epilogue(HEAD, TRAIN)), 1)
               const int x0 = xb + j * 16;
               tmem_ld_wait32(A);
               if (j + 1 < nsub) tmem_ld32(tcol + uint32_t((j + 1) * 64), B);
-              epi_finish<2, HEAD, TRAIN, BITS>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix + x0) * 16, row_ok && x0 < e.W, n, yy, x0, sa1, sa2, wds);
+              epi_finish<2, HEAD, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, (rowpix + x0) * 16, row_ok && x0 < e.W, n, yy, x0, sa1, sa2, wds);
               if (j + 1 < nsub) {
                 tmem_ld_wait32(B);
                 if (j + 2 < nsub) tmem_ld32(tcol + uint32_t((j + 2) * 64), A);
-                epi_finish<2, HEAD, TRAIN, BITS>(e, B, tops, bias_r, s_bias, s_head, relu, (rowpix + x0 + 16) * 16, row_ok && x0 + 16 < e.W, n, yy, x0 + 16, sa1, sa2, wds);
+                epi_finish<2, HEAD, TRAIN>(e, B, tops, bias_r, s_bias, s_head, relu, (rowpix + x0 + 16) * 16, row_ok && x0 + 16 < e.W, n, yy, x0 + 16, sa1, sa2, wds);
               }
             }
           }
@@ -958,7 +922,7 @@ __global__ void __launch_bounds__(block_threads(heavy_epilogue(HEAD, TRAIN)), 1)
               }
             }
             tmem_ld_wait16(A);
-            epi_finish<1, false, TRAIN, BITS>(e, A, tops, bias_r, s_bias, s_head, relu, eoff, valid, n, yy, x0, sa1, sa2, wds1);
+            epi_finish<1, false, TRAIN>(e, A, tops, bias_r, s_bias, s_head, relu, eoff, valid, n, yy, x0, sa1, sa2, wds1);
             if constexpr (kHeavy) {
               if (gm && j == nsub - 1 && e.stats_partial) {  // last sub-tile of this 16-channel group: fold its statistics into the warp's slots
                 const float r1 = warp_reduce16(sa1, lane), r2 = warp_reduce16(sa2, lane);
@@ -1077,7 +1041,7 @@ struct Plan {
   int ch_map[kMaxChunks], ch_c0[kMaxChunks], ch_span[kMaxChunks], ch_wk8[kMaxChunks];
 };
 
-inline bool is_train(const UnppConvArgs* a) { return a->addend || a->relu_mask_src || a->relu_bits || a->stats_partial || a->logit || a->drop_mask; }
+inline bool is_train(const UnppConvArgs* a) { return a->addend || a->relu_mask_src || a->stats_partial || a->logit || a->drop_mask; }
 
 int make_plan_cw(const UnppConvArgs* a, Plan* pl, int cw);
 
@@ -1234,12 +1198,8 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
                     (!a->block2x2 && a->n_tile != 16 && a->n_tile != 32 && a->n_tile != 64 && a->n_tile != 128)))
     return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: the fused max pool needs conv mode with ReLU and an output, even H and W, no head / training operand");
   if (a->stats_partial && a->mode != UNPP_MODE_CONV) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: stats only in conv mode");
-  if (a->head_w && (a->addend || a->relu_mask_src || a->relu_bits || a->stats_partial))
+  if (a->head_w && (a->addend || a->relu_mask_src || a->stats_partial))
     return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: the fused head (a forward op) takes no addend / ReLU mask / statistics");
-  if ((a->relu_bits || a->relu_bits_out) && a->mode != UNPP_MODE_CONV) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: ReLU bit masks only in conv mode");
-  if (a->relu_bits && a->relu_mask_src) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: pass the ReLU mask either as the activation or as bits");
-  if (a->relu_bits_out && (!a->relu || !a->out || (is_train(a) && !a->head_w)))
-    return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: relu_bits_out belongs to a forward launch with ReLU and an output");
   if (a->stats_aux && (!a->aux_mean || !a->aux_istd)) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: stats_aux needs aux_mean/aux_istd");
 
   EncodeTiledFn enc = get_encode();
@@ -1304,7 +1264,6 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   p.drop_mask = a->drop_mask, p.drop_scale = a->drop_scale;
   p.addend = reinterpret_cast<const __nv_bfloat16*>(a->addend);
   p.relu_mask_src = reinterpret_cast<const __nv_bfloat16*>(a->relu_mask_src);
-  p.relu_bits = a->relu_bits, p.relu_bits_out = a->relu_bits_out;
   p.stats_partial = a->stats_partial;
   p.stats_aux = reinterpret_cast<const __nv_bfloat16*>(a->stats_aux);
   p.aux_mean = a->aux_mean, p.aux_istd = a->aux_istd;
@@ -1316,21 +1275,19 @@ extern "C" int unpp_conv_tc(const UnppConvArgs* a, unpp_stream_t stream_) {
   if (deconv && train) return unpp::fail(UNPP_ERR_BAD_ARG, "conv_tc: deconv mode has no training epilogue");
   if (deconv && a->n_total / 4 > 256) return unpp::fail(UNPP_ERR_UNSUPPORTED, "conv_tc: deconv Cout > 256");
   const dim3 grid(pl.grid_x, pl.grid_y);
-#define UNPP_LAUNCH(D, Hd, T, Bt)                                                                                                         \
-  do {                                                                                                                                    \
-    static unsigned char opted_in[64] = {0}; /* per variant and device */                                                                 \
-    if (cudaError_t e = unpp::opt_in_smem(conv_tc_kernel<D, Hd, T, Bt>, (heavy_epilogue(Hd, T) ? 204 : 224) * 1024, opted_in))            \
-      return unpp::fail_cuda_err("conv_tc: cudaFuncSetAttribute", e);                                                                     \
-    if (cudaError_t e = unpp::launch(conv_tc_kernel<D, Hd, T, Bt>, grid, block_threads(heavy_epilogue(Hd, T)), pl.smem_total, stream, p)) \
-      return unpp::fail_cuda_err("conv_tc: launch", e);                                                                                   \
+#define UNPP_LAUNCH(D, Hd, T)                                                                                                         \
+  do {                                                                                                                                \
+    static unsigned char opted_in[64] = {0}; /* per variant and device */                                                             \
+    if (cudaError_t e = unpp::opt_in_smem(conv_tc_kernel<D, Hd, T>, (heavy_epilogue(Hd, T) ? 204 : 224) * 1024, opted_in))            \
+      return unpp::fail_cuda_err("conv_tc: cudaFuncSetAttribute", e);                                                                 \
+    if (cudaError_t e = unpp::launch(conv_tc_kernel<D, Hd, T>, grid, block_threads(heavy_epilogue(Hd, T)), pl.smem_total, stream, p)) \
+      return unpp::fail_cuda_err("conv_tc: launch", e);                                                                               \
   } while (0)
-  const bool bits_out = a->relu_bits_out != nullptr;
-  if (deconv) UNPP_LAUNCH(true, false, false, false);
-  else if (head && (train || bits_out)) UNPP_LAUNCH(false, true, true, true);  // the head convs of a training forward (dropout bits and / or mask bits)
-  else if (head) UNPP_LAUNCH(false, true, false, false);
-  else if (train) UNPP_LAUNCH(false, false, true, false);
-  else if (bits_out) UNPP_LAUNCH(false, false, false, true);
-  else UNPP_LAUNCH(false, false, false, false);
+  if (deconv) UNPP_LAUNCH(true, false, false);
+  else if (head && train) UNPP_LAUNCH(false, true, true);
+  else if (head) UNPP_LAUNCH(false, true, false);
+  else if (train) UNPP_LAUNCH(false, false, true);
+  else UNPP_LAUNCH(false, false, false);
 #undef UNPP_LAUNCH
   return UNPP_OK;
 }

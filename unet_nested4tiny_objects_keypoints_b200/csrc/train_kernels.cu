@@ -196,19 +196,9 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
   }
 }
 
-// ReLU mask of eight stored (bf16, >= 0) values as one byte: bit k = (value k > 0).  Two such bytes are the 16-bit word per (pixel,
-// 16-channel group) that the dgrad epilogue of conv_tc reads instead of the activation itself (UnppConvArgs.relu_bits).
-__device__ __forceinline__ uint8_t relu_bits8(const uint4& u) {
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-  uint32_t b = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) b |= ((w[k] & 0xFFFFu) ? 1u : 0u) << (2 * k), b |= ((w[k] >> 16) ? 1u : 0u) << (2 * k + 1);
-  return uint8_t(b);
-}
-
-// y = relu(z * scale[c] + shift[c]) (bf16 NHWC, 8 channels per thread); optional 2x2 max-pooled copy; optional ReLU mask bits of y.
+// y = relu(z * scale[c] + shift[c]) (bf16 NHWC, 8 channels per thread); optional 2x2 max-pooled copy.
 __global__ void bn_relu_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift, uint4* __restrict__ y,
-                               uint8_t* __restrict__ bits, long total, int C8) {
+                               long total, int C8) {
   unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
   unpp::pdl_trigger();
   const long stride = long(gridDim.x) * blockDim.x, i0 = blockIdx.x * long(blockDim.x) + threadIdx.x;
@@ -222,9 +212,7 @@ __global__ void bn_relu_kernel(const uint4* __restrict__ z, const float* __restr
       unpack8(__ldg(z + i), f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
-      const uint4 packed = pack8(f);
-      y[i] = packed;
-      if (bits) bits[i] = relu_bits8(packed);
+      y[i] = pack8(f);
     }
     return;
   }
@@ -234,13 +222,11 @@ __global__ void bn_relu_kernel(const uint4* __restrict__ z, const float* __restr
     unpack8(__ldg(z + i), f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], __ldg(scale + c0 + k), __ldg(shift + c0 + k)), 0.f);
-    const uint4 packed = pack8(f);
-    y[i] = packed;
-    if (bits) bits[i] = relu_bits8(packed);
+    y[i] = pack8(f);
   }
 }
 __global__ void bn_relu_pool_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
-                                    uint4* __restrict__ y, uint4* __restrict__ pooled, uint8_t* __restrict__ bits, int N, int H, int W, int C8) {
+                                    uint4* __restrict__ y, uint4* __restrict__ pooled, int N, int H, int W, int C8) {
   unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
   unpp::pdl_trigger();
   const int Ho = H / 2, Wo = W / 2;
@@ -265,7 +251,6 @@ __global__ void bn_relu_pool_kernel(const uint4* __restrict__ z, const float* __
       for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
       const uint4 packed = pack8(f);
       y[idx] = packed;
-      if (bits) bits[idx] = relu_bits8(packed);
       float r[8];
       unpack8(packed, r);  // pool the bf16-rounded values, exactly what a pool over the stored y would see
 #pragma unroll
@@ -606,19 +591,19 @@ extern "C" int unpp_bn_finalize(const float* partial, int nparts, int C, float c
   return UNPP_OK;
 }
 
-extern "C" int unpp_bn_relu(const void* z, const float* scale, const float* shift, void* y, void* pooled, void* relu_bits, int N, int H, int W, int C,
+extern "C" int unpp_bn_relu(const void* z, const float* scale, const float* shift, void* y, void* pooled, int N, int H, int W, int C,
                             unpp_stream_t stream) {
   if (!z || !scale || !shift || !y || N < 1 || H < 1 || W < 1 || C % 8) return unpp::fail(UNPP_ERR_BAD_ARG, "bn_relu: bad argument");
   if (pooled) {
     if ((H & 1) || (W & 1)) return unpp::fail(UNPP_ERR_BAD_ARG, "bn_relu: pooling needs even H and W");
     const long total = long(N) * (H / 2) * (W / 2) * (C / 8);
     unpp::launch(bn_relu_pool_kernel, grid_for(total, 256), 256, 0, STREAM(stream), reinterpret_cast<const uint4*>(z), scale, shift,
-                                                                          reinterpret_cast<uint4*>(y), reinterpret_cast<uint4*>(pooled),
-                                                                          static_cast<uint8_t*>(relu_bits), N, H, W, C / 8);
+                                                                          reinterpret_cast<uint4*>(y), reinterpret_cast<uint4*>(pooled), N, H, W,
+                                                                          C / 8);
   } else {
     const long total = long(N) * H * W * (C / 8);
     unpp::launch(bn_relu_kernel, grid_for(total, 256), 256, 0, STREAM(stream), reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<uint4*>(y),
-                                                                     static_cast<uint8_t*>(relu_bits), total, C / 8);
+                                                                     total, C / 8);
   }
   if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("bn_relu: launch");
   return UNPP_OK;

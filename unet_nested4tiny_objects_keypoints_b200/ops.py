@@ -167,7 +167,7 @@ def _conv_args(srcs, N, H, W, n_total, n_tile, taps, strided=None, b2=False) -> 
 
 def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Tensor, n_total: int, n_tile: int, taps: int, *, bias=None,
          relu=False, mode=MODE_CONV, out=None, head=None, addend=None, relu_mask_src=None, stats_partial=None, stats_aux=None, aux_mean=None,
-         aux_istd=None, strided=None, b2=False, lowres=None, bias_classes=0, pooled=None, relu_bits=None, relu_bits_out=None) -> None:
+         aux_istd=None, strided=None, b2=False, lowres=None, bias_classes=0, pooled=None) -> None:
     """One unpp_conv_tc launch.  ``srcs``: NHWC bf16 tensors (virtual concat along K).
     ``head`` = (w fp32 [cls,16], b fp32 [cls], heat fp32 NCHW, logit|None, drop_mask int16 [N,H,W] keep bits|None, drop_scale).
     ``strided`` = [(oy, ox), ...]: every source is a [N,2H,2W,C] tensor read at (2y+oy, 2x+ox)."""
@@ -184,8 +184,6 @@ def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Te
         a.lowres_src, a.lowres_wpacked, a.lowres_C = lowres[0].data_ptr(), lowres[1].data_ptr(), lowres[0].shape[-1]
     a.bias_classes = bias_classes
     a.pooled = _ptr(pooled)  # fused MaxPool2d(2) of the output (inference epilogue)
-    # ReLU masks of a training step as bits, uint16 [N,H,W,C/16] (unpp.h): written by the forward launch, read by the dgrad launch
-    a.relu_bits, a.relu_bits_out = _ptr(relu_bits), _ptr(relu_bits_out)
     a.addend, a.relu_mask_src = _ptr(addend), _ptr(relu_mask_src)
     a.stats_partial, a.stats_aux, a.aux_mean, a.aux_istd = _ptr(stats_partial), _ptr(stats_aux), _ptr(aux_mean), _ptr(aux_istd)
     _count()
@@ -205,15 +203,14 @@ def conv(srcs: Sequence[torch.Tensor], N: int, H: int, W: int, wpacked: torch.Te
         nbytes += px * n_total * 2 // 4
     if head is not None:
         nbytes += px * head[0].shape[0] * 4 + (px * 16 if head[4] is not None else 0)
-    for extra in (addend, relu_mask_src, stats_aux, relu_bits, relu_bits_out):
+    for extra in (addend, relu_mask_src, stats_aux):
         if extra is not None:
             nbytes += extra.numel() * 2
     flops = 2 * px * k_total * n_total * taps
     if lowres is not None:  # count the unfused arithmetic it replaces: the k2s2 transposed conv + its 3x3 taps
         flops += 2 * px * lowres[0].shape[-1] * n_total + 2 * px * n_total * n_total * taps
     label = "conv_tc %s taps%d K%d N%d %dx%d" % ("deconv" if mode == MODE_DECONV else ("conv2x2" if a.block2x2 else "conv"), taps, k_total, n_total, H, W)
-    flags = [n for n, v in (("st", stats_partial), ("aux", stats_aux), ("mask", relu_mask_src), ("bits", relu_bits), ("add", addend), ("head", head), ("s2", strided),
-                            ("low", lowres), ("bitsout", relu_bits_out)) if v is not None]
+    flags = [n for n, v in (("st", stats_partial), ("aux", stats_aux), ("mask", relu_mask_src), ("add", addend), ("head", head), ("s2", strided), ("low", lowres)) if v is not None]
     if flags:
         label += " +" + "+".join(flags)
     with _Traced(label, nbytes, flops):
@@ -444,11 +441,11 @@ def bn_finalize(partial, nparts, Cc, count, gamma, beta, running_mean, running_v
                                       shift.data_ptr(), _stream()), "unpp_bn_finalize")
 
 
-def bn_relu(z, scale, shift, y, pooled=None, relu_bits=None) -> None:
+def bn_relu(z, scale, shift, y, pooled=None) -> None:
     N, H, W, Cc = z.shape
     _count()
     with _Traced("bn_relu", 0, 0):
-        _lib.check(lib().unpp_bn_relu(z.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), _ptr(pooled), _ptr(relu_bits), N, H, W, Cc, _stream()), "unpp_bn_relu")
+        _lib.check(lib().unpp_bn_relu(z.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), _ptr(pooled), N, H, W, Cc, _stream()), "unpp_bn_relu")
 
 
 def maxpool_bwd(x, dpooled, dx) -> None:

@@ -66,18 +66,11 @@ class TrainState:
         def act(name, lvl, c=None):
             t[name] = torch.empty(B, H >> lvl, W >> lvl, f[lvl] if c is None else c, **bf)
 
-        def bits(name, lvl):
-            # ReLU mask of activation `name` as bits: one 16-bit word per (pixel, 16-channel group), written by the forward launch that
-            # produces the activation, read by the dgrad launch that masks with it (2 bytes instead of the 32-byte activation)
-            t["bits:" + name] = torch.empty(B, H >> lvl, W >> lvl, f[lvl] // 16, dtype=torch.int16, device=dev)
-
         t["x16"] = torch.empty(B, H, W, 16, **bf)
         for lvl, node in enumerate(ENCODER):
             for nm in ("z1", "a", "z2"):
                 act(f"{node}.{nm}", lvl)
             act(f"X{lvl}0", lvl)
-            bits(f"{node}.a", lvl)
-            bits(f"X{lvl}0", lvl)
             if lvl < 3:
                 t[f"P{lvl}0"] = torch.empty(B, H >> (lvl + 1), W >> (lvl + 1), f[lvl], **bf)
             for nm in ("dyh2", "dz2", "dyh1", "dz1"):
@@ -96,8 +89,6 @@ class TrainState:
             tag = name[-2:]
             for nm in (f"U{tag}", f"{name}.a", f"X{tag}", f"dZ2{tag}", f"dZ1{tag}", f"dU{tag}"):
                 act(nm, lvl)
-            bits(f"{name}.a", lvl)
-            bits(f"X{tag}", lvl)
             if not eng.model.is_deconv:  # unet.py:189-191: the 1x1 conv runs on the low-resolution tensor, before the x2 bilinear upsample
                 for nm in (f"V{tag}", f"dV{tag}"):
                     t[nm] = torch.empty(B, H >> (lvl + 1), W >> (lvl + 1), f[lvl], **bf)
@@ -279,11 +270,10 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
             nt = P[key + ".nt"]
             if not m.is_batchnorm:  # unet.py:137-143: conv + ReLU (+ the 2x2 max pool of the level's output, written by the same epilogue)
                 if n == 1:
-                    ops.conv([src], B, h, w, P[key], c, nt, 9, bias=conv.bias, relu=True, out=t[f"{name}.a"], relu_bits_out=t[f"bits:{name}.a"])
+                    ops.conv([src], B, h, w, P[key], c, nt, 9, bias=conv.bias, relu=True, out=t[f"{name}.a"])
                     src = t[f"{name}.a"]
                 else:
-                    ops.conv([src], B, h, w, P[key], c, nt, 9, bias=conv.bias, relu=True, out=t[f"X{lvl}0"], pooled=t[f"P{lvl}0"] if lvl < 3 else None,
-                             relu_bits_out=t[f"bits:X{lvl}0"])
+                    ops.conv([src], B, h, w, P[key], c, nt, 9, bias=conv.bias, relu=True, out=t[f"X{lvl}0"], pooled=t[f"P{lvl}0"] if lvl < 3 else None)
                     src = t[f"P{lvl}0"] if lvl < 3 else None
                 continue
             bn = seq[1]
@@ -301,10 +291,10 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
                 tracked.append(bn.num_batches_tracked)
                 stat_buffers += [bn.running_mean, bn.running_var]
             if n == 1:
-                ops.bn_relu(z, t[pre + ".scale"], t[pre + ".shift"], t[f"{name}.a"], relu_bits=t[f"bits:{name}.a"])
+                ops.bn_relu(z, t[pre + ".scale"], t[pre + ".shift"], t[f"{name}.a"])
                 src = t[f"{name}.a"]
             else:
-                ops.bn_relu(z, t[pre + ".scale"], t[pre + ".shift"], t[f"X{lvl}0"], t[f"P{lvl}0"] if lvl < 3 else None, relu_bits=t[f"bits:X{lvl}0"])
+                ops.bn_relu(z, t[pre + ".scale"], t[pre + ".shift"], t[f"X{lvl}0"], t[f"P{lvl}0"] if lvl < 3 else None)
                 src = t[f"P{lvl}0"] if lvl < 3 else None
     if tracked:
         torch._foreach_add_(tracked, 1)  # the eight int64 num_batches_tracked counters: one launch
@@ -324,16 +314,14 @@ def forward_train(ts: TrainState, x: torch.Tensor, update_running_stats: bool = 
         else:
             ops.conv([t[high]], B, h // 2, w // 2, P[ku], c, P[ku + ".nt"], 1, bias=node.up[1].bias, out=t[f"V{tag}"])
             ops.bilinear_up2x(t[f"V{tag}"], t[f"U{tag}"])
-        ops.conv([t[f"U{tag}"]] + [t[l] for l in lows], B, h, w, P[k1], c, P[k1 + ".nt"], 9, bias=_w1(m, name).bias, relu=True, out=t[f"{name}.a"],
-                 relu_bits_out=t[f"bits:{name}.a"])
+        ops.conv([t[f"U{tag}"]] + [t[l] for l in lows], B, h, w, P[k1], c, P[k1 + ".nt"], 9, bias=_w1(m, name).bias, relu=True, out=t[f"{name}.a"])
         head = None
         if name in HEAD_OF:
             k = int(HEAD_OF[name][-1]) - 1
             hm = getattr(m, HEAD_OF[name])
             heats[k] = torch.empty(B, ncls, H, W, dtype=torch.float32, device=eng.device)
             head = (hm.weight.view(ncls, -1), hm.bias, heats[k], None, t[f"mask{k}"] if ts.use_masks else None, ts.drop_scale)
-        ops.conv([t[f"{name}.a"]], B, h, w, P[k2], c, P[k2 + ".nt"], 9, bias=_w2(m, name).bias, relu=True, out=t[f"X{tag}"], head=head,
-                 relu_bits_out=t[f"bits:X{tag}"])
+        ops.conv([t[f"{name}.a"]], B, h, w, P[k2], c, P[k2 + ".nt"], 9, bias=_w2(m, name).bias, relu=True, out=t[f"X{tag}"], head=head)
     ts.heats = heats
     return tuple(heats)
 
@@ -427,9 +415,9 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
         key = f"{dname}.up.dgrad"
         cin = out.shape[-1]
         if m.is_deconv:
-            ops.conv([t[f"dU{dname[-2:]}"]] * 4, B, h2, w2, P[key], cin, P[key + ".nt"], 1, out=out, addend=addend, relu_bits=mask, strided=PQ, **(stats or {}))
+            ops.conv([t[f"dU{dname[-2:]}"]] * 4, B, h2, w2, P[key], cin, P[key + ".nt"], 1, out=out, addend=addend, relu_mask_src=mask, strided=PQ, **(stats or {}))
         else:
-            ops.conv([t[f"dV{dname[-2:]}"]], B, h2, w2, P[key], cin, P[key + ".nt"], 1, out=out, addend=addend, relu_bits=mask, **(stats or {}))
+            ops.conv([t[f"dV{dname[-2:]}"]], B, h2, w2, P[key], cin, P[key + ".nt"], 1, out=out, addend=addend, relu_mask_src=mask, **(stats or {}))
 
     # ---- heads: sigmoid' + 1x1 dgrad/wgrad + dropout mask (+ fused MSE); output already masked by X_0k > 0
     for name, hname in HEAD_OF.items():
@@ -458,7 +446,7 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
         wgrad_conv([t[f"{name}.a"]], dZ2, h, w, f"{pre}.conv2.0.weight")
         key = f"{name}.c2.dgrad"
         g, part = stats_buf([c], c, P[key + ".nt"], 9, h, w, key=f"stats:{pre}.conv1.0.bias")
-        ops.conv([dZ2], B, h, w, P[key], c, P[key + ".nt"], 9, out=dZ1, relu_bits=t[f"bits:{name}.a"], stats_partial=part)
+        ops.conv([dZ2], B, h, w, P[key], c, P[key + ".nt"], 9, out=dZ1, relu_mask_src=t[f"{name}.a"], stats_partial=part)
         bias_from_stats(part, g, c, f"{pre}.conv1.0.bias")
         wgrad_conv([t[f"U{tag}"]] + [t[l] for l in lows], dZ1, h, w, f"{pre}.conv1.0.weight")
         key = f"{name}.c1.dgradU"
@@ -475,7 +463,7 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
         cons = consumers_of(node)
         key = f"{node}.gather"
         c = out.shape[-1]
-        ops.conv([t[f"dZ1{cn[-2:]}"] for cn, _ in cons], B, h, w, P[key], c, P[key + ".nt"], 9, out=out, addend=addend, relu_bits=mask, **stats)
+        ops.conv([t[f"dZ1{cn[-2:]}"] for cn, _ in cons], B, h, w, P[key], c, P[key + ".nt"], 9, out=out, addend=addend, relu_mask_src=mask, **stats)
 
     # ---- decoder, deepest nesting first.  X03's only consumer is head 3: dZ2_03 = dXh2 (already masked)
     c0 = eng.filters[0]
@@ -496,10 +484,10 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
                 deconv_dgrad(extra_deconv_from, h, w, tmp, addend=addend)
                 add = tmp
             g, part = stats_buf([c] * len(cons), c, P[key_for_stats + ".nt"], 9, h, w, key=f"stats:{dname}.conv.conv2.0.bias")
-            gather(node, h, w, out, add, t["bits:" + node], dict(stats_partial=part))
+            gather(node, h, w, out, add, t[node], dict(stats_partial=part))
         else:
             g, part = stats_buf(up_dgrad_srcs_C(extra_deconv_from), c, P[key_for_stats + ".nt"], 1, h, w, key=f"stats:{dname}.conv.conv2.0.bias")
-            deconv_dgrad(extra_deconv_from, h, w, out, addend=addend, mask=t["bits:" + node], stats=dict(stats_partial=part))
+            deconv_dgrad(extra_deconv_from, h, w, out, addend=addend, mask=t[node], stats=dict(stats_partial=part))
         bias_from_stats(part, g, c, f"{dname}.conv.conv2.0.bias")
         decoder_node_backward(dname, True)
 
@@ -530,17 +518,17 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
         if lvl == 0:
             key = f"{node}.gather"
             g, part = stats_buf([c] * len(cons), c, P[key + ".nt"], 9, h, w, key=skey)
-            gather(node, h, w, dyh2, addend, t["bits:" + node], dict(stats_partial=part, **aux2))
+            gather(node, h, w, dyh2, addend, t[node], dict(stats_partial=part, **aux2))
         elif cons:
             tmp = t[f"tmp{lvl}"]
             deconv_dgrad(deconv_into[lvl], h, w, tmp, addend=addend)
             key = f"{node}.gather"
             g, part = stats_buf([c] * len(cons), c, P[key + ".nt"], 9, h, w, key=skey)
-            gather(node, h, w, dyh2, tmp, t["bits:" + node], dict(stats_partial=part, **aux2))
+            gather(node, h, w, dyh2, tmp, t[node], dict(stats_partial=part, **aux2))
         else:  # X30: the upsample of up_concat21 is its only consumer
             key = f"{deconv_into[lvl]}.up.dgrad"
             g, part = stats_buf(up_dgrad_srcs_C(deconv_into[lvl]), c, P[key + ".nt"], 1, h, w, key=skey)
-            deconv_dgrad(deconv_into[lvl], h, w, dyh2, addend=addend, mask=t["bits:" + node], stats=dict(stats_partial=part, **aux2))
+            deconv_dgrad(deconv_into[lvl], h, w, dyh2, addend=addend, mask=t[node], stats=dict(stats_partial=part, **aux2))
         if has_bn:
             # BatchNorm 2 backward: sums = (dbeta, dgamma); dz = gamma*istd*(dyh - s1/M - xhat*s2/M)
             ops.reduce_partials(part, g, 2 * c, 2 * c, t[bn2 + ".sums"])
@@ -557,7 +545,7 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
         if has_bn:
             g, part = stats_buf([c], c, P[key + ".nt"], 9, h, w)
             dyh1 = t[f"{name}.dyh1"]
-            ops.conv([dz2], B, h, w, P[key], c, P[key + ".nt"], 9, out=dyh1, relu_bits=t[f"bits:{name}.a"], stats_partial=part, stats_aux=t[f"{name}.z1"],
+            ops.conv([dz2], B, h, w, P[key], c, P[key + ".nt"], 9, out=dyh1, relu_mask_src=t[f"{name}.a"], stats_partial=part, stats_aux=t[f"{name}.z1"],
                      aux_mean=t[bn1 + ".mean"], aux_istd=t[bn1 + ".istd"])
             ops.reduce_partials(part, g, 2 * c, 2 * c, t[bn1 + ".sums"])
             ops.reduce_partials(t[bn1 + ".sums"], 1, 0, c, G, out_offset=goff(f"{name}.conv1.1.bias"), defer=True)
@@ -565,7 +553,7 @@ def backward_train(ts: TrainState, G: torch.Tensor, dheats: Optional[Sequence[Op
             ops.bn_bwd_apply(dyh1, t[f"{name}.z1"], t[bn1 + ".mean"], t[bn1 + ".istd"], seq1[1].weight, t[bn1 + ".sums"], count, dz1)
         else:
             g, part = stats_buf([c], c, P[key + ".nt"], 9, h, w, key=f"stats:{name}.conv1.0.bias")
-            ops.conv([dz2], B, h, w, P[key], c, P[key + ".nt"], 9, out=dz1, relu_bits=t[f"bits:{name}.a"], stats_partial=part)
+            ops.conv([dz2], B, h, w, P[key], c, P[key + ".nt"], 9, out=dz1, relu_mask_src=t[f"{name}.a"], stats_partial=part)
             bias_from_stats(part, g, c, f"{name}.conv1.0.bias")
         if lvl == 0:
             wgrad_conv([t["x16"]], dz1, h, w, f"{name}.conv1.0.weight", ci_count=m.in_channels)
