@@ -89,7 +89,7 @@ class Engine:
         if key is not None and self._packed_eval is not None and self._packed_key == key:
             return self._packed_eval
         P: Dict[str, Dict] = {}
-        with torch.no_grad(), torch.cuda.device(self.device):
+        with torch.no_grad(), torch.cuda.device(self.device), ops.pack_arena(self.device):
             for name in ENCODER:
                 for n in (1, 2):
                     seq = self._conv_seq(name, n)

@@ -111,7 +111,7 @@ def pack_weights(src: torch.Tensor, kind: int, taps: int, n_total: int, n_tile: 
     assert src.dtype == torch.float32 and src.is_cuda
     k8_total = k_count // 8 if k8_total is None else k8_total
     if dst is None:
-        dst = torch.zeros(n_total * taps * k8_total * 8, dtype=torch.bfloat16, device=src.device)
+        dst = _zeros_bf16(n_total * taps * k8_total * 8, src.device)
     a = PackArgs()
     a.src, a.dst, a.scale = src.data_ptr(), dst.data_ptr(), _ptr(scale)
     a.kind, a.src_O, a.src_I, a.taps = kind, src.shape[0], src.shape[1], taps
@@ -125,6 +125,34 @@ def pack_weights(src: torch.Tensor, kind: int, taps: int, n_total: int, n_tile: 
     with _Traced("pack_weights", 0, 0):
         _lib.check(lib().unpp_pack_weights(C.byref(a), _stream()), "unpp_pack_weights")
     return dst
+
+
+def _zeros_bf16(n: int, device) -> torch.Tensor:
+    """Zero-filled bf16 buffer for one packed weight: a slice of the thread's pack arena when one is open (ONE fill launch for all the
+    packed weights of a model instead of one per tensor), else its own allocation."""
+    arena = getattr(_tls, "pack_arena", None)
+    if arena is not None:
+        buf, used = arena
+        n_al = (n + 127) // 128 * 128  # 256-byte alignment of every slice (TMA bulk copies need 16)
+        if used + n_al <= buf.numel() and buf.device == torch.device(device):
+            arena[1] = used + n_al
+            return buf[used:used + n]
+    return torch.zeros(n, dtype=torch.bfloat16, device=device)
+
+
+class pack_arena:
+    """``with ops.pack_arena(device, elems): ...`` — packed-weight buffers allocated inside are slices of one zero-filled tensor."""
+
+    def __init__(self, device, elems: int = 4 << 20):
+        self.device, self.elems = device, elems
+
+    def __enter__(self):
+        self.prev = getattr(_tls, "pack_arena", None)
+        _tls.pack_arena = [torch.zeros(self.elems, dtype=torch.bfloat16, device=self.device), 0]
+        return self
+
+    def __exit__(self, *exc):
+        _tls.pack_arena = self.prev
 
 
 def begin_pack_record() -> None:

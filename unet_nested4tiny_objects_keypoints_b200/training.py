@@ -171,7 +171,8 @@ def pack_train(ts: TrainState) -> None:
         return
     ops.begin_pack_record()
     try:
-        _pack_train_jobs(ts)
+        with ops.pack_arena(ts.eng.device, 8 << 20):
+            _pack_train_jobs(ts)
     finally:
         jobs = ops.end_pack_record()
     ts._pack_jobs = jobs  # keeps the source views alive
@@ -190,13 +191,13 @@ def _pack_train_jobs(ts: TrainState) -> None:
         b2 = kind in (0, 1) and taps == 9 and n_total == 16 and k_count % 16 == 0 and src.shape[0] == 16 and k8_total <= 8
         if b2:  # 16-channel full-resolution level: 2x2 output-blocked kernel path (unpp.h kinds 4 / 5)
             if dst is None:
-                dst = P[key] = torch.zeros(64 * 16 * k8_total * 8, dtype=torch.bfloat16, device=dev)
+                dst = P[key] = ops._zeros_bf16(64 * 16 * k8_total * 8, dev)
                 P[key + ".nt"] = ops.NTile(16, b2=True)
             kw.pop("k8_total", None)
             ops.pack_weights_b2(src, kind == 1, k_count, dst=dst, k8_total=k8_total, **kw)
             return
         if dst is None:
-            dst = P[key] = torch.zeros(n_total * taps * k8_total * 8, dtype=torch.bfloat16, device=dev)
+            dst = P[key] = ops._zeros_bf16(n_total * taps * k8_total * 8, dev)
             P[key + ".nt"] = nt
         ops.pack_weights(src, kind, taps, n_total, nt, k_count, dst=dst, **kw)
 
