@@ -288,6 +288,20 @@ typedef struct UnppOptimArgs {
  * which is how an lr scheduler drives a captured step). */
 int unpp_optim_step(float* p, const float* g, float* state1, float* state2, long n, const UnppOptimArgs* a, int step, uint64_t* step_counter,
                     const float* lr_dev, float* scalars_scratch, unpp_stream_t stream);
+/* The same update for many tensors in ONE launch (the drop-in optimizers on a model whose parameters are separate allocations: the 74
+ * tensors of UNet_Nested; tools/optimizers/adamw.py:49-98 loops over them with ~10 launches each).  `table_dev`: DEVICE array of
+ * ntensors entries; block_end = exclusive running total of ceil(n / 1024) blocks; all tensors share the step count `step` (1-based). */
+typedef struct UnppOptimTensor {
+  float* p;
+  const float* g;
+  float* state1;
+  float* state2;
+  int64_t n;
+  int32_t block_end;
+  int32_t reserved;
+} UnppOptimTensor;
+int unpp_optim_step_multi(const UnppOptimTensor* table_dev, int ntensors, int total_blocks, const UnppOptimArgs* a, int step, unpp_stream_t stream);
+int unpp_sizeof_optim_tensor(void);
 int unpp_sizeof_optim_args(void);
 /* nn.UpsamplingBilinear2d(scale_factor=2) (= bilinear, align_corners=True; models/unet.py:190) on NHWC bf16:
  * y[N,2H,2W,C] from x[N,H,W,C], C % 8 == 0, with ATen's float source-index arithmetic; and its exact adjoint

@@ -107,6 +107,10 @@ class OptimArgs(C.Structure):
     ]
 
 
+class OptimTensor(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("state1", C.c_void_p), ("state2", C.c_void_p), ("n", C.c_int64), ("block_end", C.c_int32), ("reserved", C.c_int32)]
+
+
 OPT_ADAMW, OPT_ADAM, OPT_ADABOUND, OPT_SGD, OPT_SGDW = range(5)
 
 
@@ -158,6 +162,8 @@ _SIGNATURES = {
     "unpp_ref_deconv2x2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "unpp_ref_maxpool2x2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "unpp_sizeof_ref_conv_args": (C.c_int, []),
+    "unpp_optim_step_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(OptimArgs), C.c_int, C.c_void_p]),
+    "unpp_sizeof_optim_tensor": (C.c_int, []),
     "unpp_sizeof_optim_args": (C.c_int, []),
     "unpp_sizeof_conv_args": (C.c_int, []),
     "unpp_sizeof_pack_args": (C.c_int, []),

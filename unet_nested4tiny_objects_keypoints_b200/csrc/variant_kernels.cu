@@ -153,6 +153,55 @@ __global__ void optim_prep_kernel(UnppOptimArgs a, unsigned long long* counter, 
   optim_scalars(a, double(lr_dev ? *lr_dev : a.lr), t, sc);
 }
 
+// One element of any optimizer (see UnppOptimArgs): shared by the flat-buffer kernel and the multi-tensor kernel.
+__device__ __forceinline__ void optim_update(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ s1, float* __restrict__ s2, long i,
+                                             const UnppOptimArgs& a, const float (&sc)[4]) {
+  const float wd = a.weight_decay, b1 = a.beta1, b2 = a.beta2, eps = a.eps;
+  const float po = p[i];
+  float gr = g[i] * a.grad_scale;
+  float pn = po;
+  switch (a.kind) {
+    case UNPP_OPT_ADAMW: {  // tools/optimizers/adamw.py:38-100: decay = wd * p_old, NOT scaled by lr
+      const float mm = s1[i] * b1 + (1.f - b1) * gr, vv = s2[i] * b2 + (1.f - b2) * gr * gr;
+      s1[i] = mm, s2[i] = vv;
+      pn = po - sc[0] * (mm / (sqrtf(vv) + eps));
+      if (wd != 0.f) pn -= po * wd;
+      break;
+    }
+    case UNPP_OPT_ADAM: {  // torch.optim.Adam (trainer.py:351-355): L2 decay folded into the gradient
+      if (wd != 0.f) gr = fmaf(wd, po, gr);
+      const float mm = s1[i] * b1 + (1.f - b1) * gr, vv = s2[i] * b2 + (1.f - b2) * gr * gr;
+      s1[i] = mm, s2[i] = vv;
+      pn = po - sc[0] * (mm / (sqrtf(vv) / sc[1] + eps));
+      break;
+    }
+    case UNPP_OPT_ADABOUND: {  // tools/optimizers/adabound.py:57-122 (amsbound = False)
+      if (wd != 0.f) gr = fmaf(wd, po, gr);
+      const float mm = s1[i] * b1 + (1.f - b1) * gr, vv = s2[i] * b2 + (1.f - b2) * gr * gr;
+      s1[i] = mm, s2[i] = vv;
+      const float rate = fminf(fmaxf(sc[0] / (sqrtf(vv) + eps), sc[1]), sc[2]);
+      pn = po - rate * mm;
+      break;
+    }
+    case UNPP_OPT_SGD: {  // torch.optim.SGD (trainer.py:345-349): beta1 = momentum, dampening 0, no Nesterov
+      if (wd != 0.f) gr = fmaf(wd, po, gr);
+      if (b1 != 0.f) {
+        gr = sc[3] != 0.f ? gr : s1[i] * b1 + gr;
+        s1[i] = gr;
+      }
+      pn = po - sc[0] * gr;
+      break;
+    }
+    default: {  // UNPP_OPT_SGDW — tools/optimizers/sgdw.py:77-110 AS SHIPPED: the momentum buffer is maintained
+      // (beta1 = momentum, beta2 = dampening) but the step direction is never applied; p only decays by wd * p.
+      if (b1 != 0.f) s1[i] = sc[3] != 0.f ? gr : s1[i] * b1 + (1.f - b2) * gr;
+      if (wd != 0.f) pn = po - wd * po;
+      break;
+    }
+  }
+  p[i] = pn;
+}
+
 __global__ void optim_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ s1, float* __restrict__ s2, long n,
                                   UnppOptimArgs a, OptimScalars host_sc, const float* __restrict__ sc_dev) {
   unpp::pdl_wait();  // see common.h: everything below may read what earlier kernels of the stream wrote
@@ -160,51 +209,23 @@ __global__ void optim_step_kernel(float* __restrict__ p, const float* __restrict
   float sc[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) sc[k] = sc_dev ? sc_dev[k] : host_sc.v[k];
-  const float wd = a.weight_decay, b1 = a.beta1, b2 = a.beta2, eps = a.eps;
-  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < n; i += long(gridDim.x) * blockDim.x) {
-    const float po = p[i];
-    float gr = g[i] * a.grad_scale;
-    float pn = po;
-    switch (a.kind) {
-      case UNPP_OPT_ADAMW: {  // tools/optimizers/adamw.py:38-100: decay = wd * p_old, NOT scaled by lr
-        const float mm = s1[i] * b1 + (1.f - b1) * gr, vv = s2[i] * b2 + (1.f - b2) * gr * gr;
-        s1[i] = mm, s2[i] = vv;
-        pn = po - sc[0] * (mm / (sqrtf(vv) + eps));
-        if (wd != 0.f) pn -= po * wd;
-        break;
-      }
-      case UNPP_OPT_ADAM: {  // torch.optim.Adam (trainer.py:351-355): L2 decay folded into the gradient
-        if (wd != 0.f) gr = fmaf(wd, po, gr);
-        const float mm = s1[i] * b1 + (1.f - b1) * gr, vv = s2[i] * b2 + (1.f - b2) * gr * gr;
-        s1[i] = mm, s2[i] = vv;
-        pn = po - sc[0] * (mm / (sqrtf(vv) / sc[1] + eps));
-        break;
-      }
-      case UNPP_OPT_ADABOUND: {  // tools/optimizers/adabound.py:57-122 (amsbound = False)
-        if (wd != 0.f) gr = fmaf(wd, po, gr);
-        const float mm = s1[i] * b1 + (1.f - b1) * gr, vv = s2[i] * b2 + (1.f - b2) * gr * gr;
-        s1[i] = mm, s2[i] = vv;
-        const float rate = fminf(fmaxf(sc[0] / (sqrtf(vv) + eps), sc[1]), sc[2]);
-        pn = po - rate * mm;
-        break;
-      }
-      case UNPP_OPT_SGD: {  // torch.optim.SGD (trainer.py:345-349): beta1 = momentum, dampening 0, no Nesterov
-        if (wd != 0.f) gr = fmaf(wd, po, gr);
-        if (b1 != 0.f) {
-          gr = sc[3] != 0.f ? gr : s1[i] * b1 + gr;
-          s1[i] = gr;
-        }
-        pn = po - sc[0] * gr;
-        break;
-      }
-      default: {  // UNPP_OPT_SGDW — tools/optimizers/sgdw.py:77-110 AS SHIPPED: the momentum buffer is maintained
-        // (beta1 = momentum, beta2 = dampening) but the step direction is never applied; p only decays by wd * p.
-        if (b1 != 0.f) s1[i] = sc[3] != 0.f ? gr : s1[i] * b1 + (1.f - b2) * gr;
-        if (wd != 0.f) pn = po - wd * po;
-        break;
-      }
-    }
-    p[i] = pn;
+  for (long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < n; i += long(gridDim.x) * blockDim.x) optim_update(p, g, s1, s2, i, a, sc);
+}
+
+// The same update for MANY tensors in one launch (the drop-in optimizers on a model whose parameters are separate allocations: 74 tensors,
+// the reference issues ~10 launches per tensor): block b owns 1024 consecutive elements of the tensor whose block range contains b.
+__global__ void __launch_bounds__(256) optim_step_multi_kernel(const UnppOptimTensor* __restrict__ table, int ntensors, UnppOptimArgs a, OptimScalars host_sc) {
+  unpp::pdl_wait();
+  unpp::pdl_trigger();
+  int t = 0;
+  while (t < ntensors - 1 && int(blockIdx.x) >= __ldg(&table[t].block_end)) ++t;
+  const UnppOptimTensor e = table[t];
+  const int first = t ? __ldg(&table[t - 1].block_end) : 0;
+  const long base = long(int(blockIdx.x) - first) * 1024;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long i = base + k * 256 + threadIdx.x;
+    if (i < e.n) optim_update(e.p, e.g, e.state1, e.state2, i, a, host_sc.v);
   }
 }
 
@@ -258,4 +279,16 @@ extern "C" int unpp_optim_step(float* p, const float* g, float* state1, float* s
   return UNPP_OK;
 }
 
+extern "C" int unpp_optim_step_multi(const UnppOptimTensor* table_dev, int ntensors, int total_blocks, const UnppOptimArgs* a, int step, unpp_stream_t stream) {
+  if (!table_dev || ntensors < 1 || total_blocks < 1 || !a || step < 1) return unpp::fail(UNPP_ERR_BAD_ARG, "optim_step_multi: bad argument");
+  if (a->kind < UNPP_OPT_ADAMW || a->kind > UNPP_OPT_SGDW) return unpp::fail(UNPP_ERR_BAD_ARG, "optim_step_multi: unknown optimizer kind %d", a->kind);
+  if (a->kind == UNPP_OPT_ADABOUND && !(a->base_lr > 0.f)) return unpp::fail(UNPP_ERR_BAD_ARG, "optim_step_multi: AdaBound needs base_lr > 0");
+  OptimScalars hs = {};
+  optim_scalars(*a, double(a->lr), (unsigned long long)step, hs.v);
+  unpp::launch(optim_step_multi_kernel, total_blocks, 256, 0, STREAM(stream), table_dev, ntensors, *a, hs);
+  if (cudaGetLastError() != cudaSuccess) return unpp::fail_cuda("optim_step_multi: launch");
+  return UNPP_OK;
+}
+
 extern "C" int unpp_sizeof_optim_args(void) { return int(sizeof(UnppOptimArgs)); }
+extern "C" int unpp_sizeof_optim_tensor(void) { return int(sizeof(UnppOptimTensor)); }

@@ -600,6 +600,28 @@ def optim_step(kind: str, p, g, state1, state2, *, lr, beta1=0.0, beta2=0.0, eps
                                          _ptr(lr_dev), _ptr(scalars), _stream()), "unpp_optim_step")
 
 
+def optim_step_multi(kind: str, tensors, *, step: int, lr, beta1=0.0, beta2=0.0, eps=1e-8, weight_decay=0.0, final_lr=0.1, gamma=1e-3, base_lr=None,
+                     grad_scale=1.0) -> None:
+    """One launch updating many tensors: ``tensors`` = [(p, g, state1 | None, state2 | None), ...], contiguous fp32 CUDA tensors on one device,
+    all at the same (1-based) ``step``.  The 3 KB pointer table travels host -> device with the call."""
+    raw, blocks = [], 0
+    for p, g, s1, s2 in tensors:
+        for t in (p, g, s1, s2):
+            assert t is None or (t.dtype == torch.float32 and t.is_cuda and t.is_contiguous() and t.numel() == p.numel())
+        e = _lib.OptimTensor()
+        e.p, e.g, e.state1, e.state2, e.n = p.data_ptr(), g.data_ptr(), _ptr(s1), _ptr(s2), p.numel()
+        blocks += (p.numel() + 1023) // 1024
+        e.block_end = blocks
+        raw.append(bytes(e))
+    table = torch.frombuffer(bytearray(b"".join(raw)), dtype=torch.uint8).to(tensors[0][0].device)
+    a = _lib.OptimArgs()
+    a.kind, a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = OPTIMIZER_KINDS[kind], float(lr), float(beta1), float(beta2), float(eps), float(weight_decay)
+    a.final_lr, a.gamma, a.base_lr, a.grad_scale = float(final_lr), float(gamma), float(lr if base_lr is None else base_lr), float(grad_scale)
+    _count()
+    with _Traced("optim_step_multi " + kind, 0, 0):
+        _lib.check(lib().unpp_optim_step_multi(table.data_ptr(), len(tensors), blocks, C.byref(a), int(step), _stream()), "unpp_optim_step_multi")
+
+
 # ---------------------------------------------------------------------------------------------- fp32 validation mode (csrc/ref_kernels.cu)
 def ref_conv(srcs: Sequence[torch.Tensor], weight: torch.Tensor, bias, *, scale=None, relu=False, sigmoid=False) -> torch.Tensor:
     """conv (3x3 pad 1, or 1x1) of the channel-concatenation of NCHW fp32 ``srcs`` with the OIHW fp32 ``weight``, then

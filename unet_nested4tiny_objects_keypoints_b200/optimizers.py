@@ -2,9 +2,9 @@
 train.py:38 / trainer.py:344-379): same constructor, same ``step()`` arithmetic — decoupled decay
 ``weight_decay * p_old`` that is NOT multiplied by the learning rate (adamw.py:91-96), denominator
 ``sqrt(v) + eps`` with both bias corrections folded into the step size (adamw.py:84-90) — executed by
-one ``unpp_adamw`` launch per parameter tensor (the reference issues ~10 ATen kernels per tensor),
-or ONE launch for the whole model when the parameters are views of a flat buffer
-(``fused.FusedTrainStep`` lays them out that way).  CUDA fp32 parameters only; ``amsgrad`` is not
+ONE multi-tensor launch per parameter group (``unpp_optim_step_multi``: a pointer table of the group's tensors; the reference issues ~10
+ATen kernels per tensor, 74 tensors), one launch per tensor only when the tensors of a group are at different step counts or on
+different devices.  ``fused.FusedTrainStep`` goes further and keeps parameters, gradients and moments in flat buffers.  CUDA fp32 parameters only; ``amsgrad`` is not
 implemented (the trainer never enables it).
 
 ``SGDW`` and ``AdaBound`` are the drop-ins for ``tools/optimizers/sgdw.py`` / ``tools/optimizers/adabound.py``
@@ -42,6 +42,7 @@ class AdamW(Optimizer):
                 loss = closure()
         for group in self.param_groups:
             b1, b2 = group["betas"]
+            entries = []
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -56,10 +57,8 @@ class AdamW(Optimizer):
                     state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 state["step"] += 1
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                with torch.cuda.device(p.device):
-                    ops.adamw(p.data.view(-1), g.view(-1), state["exp_avg"].view(-1), state["exp_avg_sq"].view(-1), group["lr"], b1, b2, group["eps"],
-                              group["weight_decay"], state["step"])
-                _written(p)
+                entries.append((p, g, state["exp_avg"], state["exp_avg_sq"], int(state["step"])))
+            _launch_group("adamw", entries, dict(lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"], weight_decay=group["weight_decay"]))
         return loss
 
 
@@ -67,10 +66,21 @@ def _flat(t):
     return t.view(-1)
 
 
-def _written(p) -> None:
-    """The kernels update ``p`` through its raw pointer: tell autograd / every ``_version``-keyed cache (the engine's folded
-    eval-mode weights) that the tensor changed, like an in-place torch op would."""
-    torch._C._increment_version([p])
+def _launch_group(kind, entries, hyper) -> None:
+    """``entries``: [(p, grad, state1 | None, state2 | None, step)] of one parameter group.  One multi-tensor launch when they share the
+    step count and the device, else one launch per tensor (same kernel arithmetic either way)."""
+    if not entries:
+        return
+    same = len({e[4] for e in entries}) == 1 and len({e[0].device for e in entries}) == 1
+    if same and len(entries) > 1:
+        with torch.cuda.device(entries[0][0].device):
+            ops.optim_step_multi(kind, [(_flat(p.data), _flat(g), None if a is None else _flat(a), None if b is None else _flat(b)) for p, g, a, b, _ in entries],
+                                 step=entries[0][4], **hyper)
+    else:
+        for p, g, a, b, step in entries:
+            with torch.cuda.device(p.device):
+                ops.optim_step(kind, _flat(p.data), _flat(g), None if a is None else _flat(a), None if b is None else _flat(b), step=step, **hyper)
+    torch._C._increment_version([e[0] for e in entries])
 
 
 def _check(p):
@@ -99,6 +109,7 @@ class SGDW(Optimizer):
             with torch.enable_grad():
                 loss = closure()
         for group in self.param_groups:
+            entries = []
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -109,12 +120,10 @@ class SGDW(Optimizer):
                     if "momentum_buffer" not in state:
                         state["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                         state["step"] = 0
-                    buf = _flat(state["momentum_buffer"])
+                    buf = state["momentum_buffer"]
                 state["step"] = state.get("step", 0) + 1
-                with torch.cuda.device(p.device):
-                    ops.optim_step("sgdw", _flat(p.data), _flat(g), buf, None, lr=group["lr"], beta1=group["momentum"], beta2=group["dampening"],
-                                   weight_decay=group["weight_decay"], step=state["step"])
-                _written(p)
+                entries.append((p, g, buf, None, int(state["step"])))
+            _launch_group("sgdw", entries, dict(lr=group["lr"], beta1=group["momentum"], beta2=group["dampening"], weight_decay=group["weight_decay"]))
         return loss
 
 
@@ -149,6 +158,7 @@ class AdaBound(Optimizer):
                 loss = closure()
         for group, base_lr in zip(self.param_groups, self.base_lrs):
             b1, b2 = group["betas"]
+            entries = []
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -159,9 +169,7 @@ class AdaBound(Optimizer):
                     state["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 state["step"] += 1
-                with torch.cuda.device(p.device):
-                    ops.optim_step("adabound", _flat(p.data), _flat(g), _flat(state["exp_avg"]), _flat(state["exp_avg_sq"]), lr=group["lr"], beta1=b1,
-                                   beta2=b2, eps=group["eps"], weight_decay=group["weight_decay"], final_lr=group["final_lr"], gamma=group["gamma"],
-                                   base_lr=base_lr, step=state["step"])
-                _written(p)
+                entries.append((p, g, state["exp_avg"], state["exp_avg_sq"], int(state["step"])))
+            _launch_group("adabound", entries, dict(lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"], weight_decay=group["weight_decay"],
+                                                    final_lr=group["final_lr"], gamma=group["gamma"], base_lr=base_lr))
         return loss
