@@ -45,10 +45,10 @@ if n:
     md += f"""
 ### Multi-GPU (`torchrun`, one rank per GPU, same box)
 
-| GPUs | inference img/s (device) | e2e from 8-bit images | e2e from fp32 tensors (pinned-copy GB/s per GPU) | DP train img/s, global batch 256 | per GPU (batch) | all-reduce us | DP e2e (fp32 images + targets) |
+| GPUs | inference img/s (device) | e2e from 8-bit images | e2e from fp32 tensors (pinned-copy GB/s per GPU) | DP train img/s, global batch 256 | per GPU (batch) | all-reduce us | DP e2e (8-bit images + key points / fp32 images + targets) |
 |---|---|---|---|---|---|---|---|
-| 1 | {d['value']:.0f} | {d['e2e']['value']:.0f} | {d['e2e_fp32_input']['value']:.0f} ({d['e2e']['h2d_gbs_measured']}) | {t['value']:.0f} (batch 32) | {t['value']:.0f} (32) | - | {t['e2e_fp32_input']['value']:.0f} |
-""" + "\n".join(f"| {k} | {n[k]['value']:.0f} | {n[k]['e2e']['value']:.0f} | {n[k]['e2e_fp32_input']['value']:.0f} ({n[k]['e2e']['h2d_gbs_measured']}) | {n[k]['train_step']['value']:.0f} | {n[k]['train_step']['images_per_s_per_gpu']:.0f} ({n[k]['train_step']['batch_per_gpu']}) | {n[k]['train_step']['allreduce_us']} | {n[k]['train_step'].get('e2e_fp32_input', n[k]['train_step']['e2e'])['value']:.0f} |" for k in sorted(n)) + f"""
+| 1 | {d['value']:.0f} | {d['e2e']['value']:.0f} | {d['e2e_fp32_input']['value']:.0f} ({d['e2e']['h2d_gbs_measured']}) | {t['value']:.0f} (batch 32) | {t['value']:.0f} (32) | - | {t['e2e']['value']:.0f} / {t['e2e_fp32_input']['value']:.0f} |
+""" + "\n".join(f"| {k} | {n[k]['value']:.0f} | {n[k]['e2e']['value']:.0f} | {n[k]['e2e_fp32_input']['value']:.0f} ({n[k]['e2e']['h2d_gbs_measured']}) | {n[k]['train_step']['value']:.0f} | {n[k]['train_step']['images_per_s_per_gpu']:.0f} ({n[k]['train_step']['batch_per_gpu']}) | {n[k]['train_step']['allreduce_us']} | {n[k]['train_step']['e2e']['value']:.0f} / {n[k]['train_step']['e2e_fp32_input']['value']:.0f} |" for k in sorted(n)) + f"""
 
 End-to-end inference from 8-bit images scales {n[8]['e2e']['value'] / d['e2e']['value']:.2f}x on 8 GPUs ({n[8]['e2e']['value'] / d['e2e']['value'] / 8:.3f} of linear); from fp32 tensors it is bound by the host: the
 pinned-copy bandwidth per GPU drops from {d['e2e']['h2d_gbs_measured']} GB/s (1 GPU) to {n[8]['e2e']['h2d_gbs_measured']} GB/s (8 GPUs copying at once, ~{8 * n[8]['e2e']['h2d_gbs_measured']:.0f} GB/s for the box).  Data-parallel training at
