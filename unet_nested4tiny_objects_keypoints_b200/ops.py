@@ -32,7 +32,9 @@ trace_tag = ""     # row of the fused plan the following launches
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    # (the raw handle of the calling thread's current stream on its current device: ~10x cheaper than torch.cuda.current_stream(),
+    # which every launch of an eager step used to pay — 130 launches per training step)
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _count(n: int = 1) -> None:
