@@ -22,4 +22,4 @@ pr.enable()
 for _ in range(20): one()
 torch.cuda.synchronize()
 pr.disable()
-st = pstats.Stats(pr); st.sort_stats("cumulative").print_stats(28)
+st = pstats.Stats(pr); st.sort_stats("tottime").print_stats(22)

@@ -40,14 +40,39 @@ DECODER_ORDER = ("up_concat01", "up_concat11", "up_concat21", "up_concat02", "up
 HEAD_OF = {"up_concat01": "final_1", "up_concat02": "final_2", "up_concat03": "final_3"}
 
 
-def named_params(model):
-    """``model.named_parameters()`` that also works on nn.DataParallel replicas: a replica's parameters are broadcast copies
-    kept as plain (non-leaf) tensors in ``_former_parameters`` and ``parameters()`` is empty there (torch/nn/parallel/replicate.py)."""
+def _named_params_walk(model):
     for prefix, mod in model.named_modules():
         src = mod._former_parameters if getattr(mod, "_is_replica", False) else mod._parameters
         for k, v in src.items():
             if v is not None:
                 yield (prefix + "." + k if prefix else k), v
+
+
+def named_params(model):
+    """``model.named_parameters()`` that also works on nn.DataParallel replicas: a replica's parameters are broadcast copies
+    kept as plain (non-leaf) tensors in ``_former_parameters`` and ``parameters()`` is empty there (torch/nn/parallel/replicate.py).
+    The walk over the module tree (~40 modules, three times per eager training step) is cached on the module: parameters are updated
+    in place (optimizers, load_state_dict, .to()), so the list stays valid as long as the module keeps its Parameter OBJECTS — checked
+    on the first and last one; replicas are fresh objects at every forward and are walked every time."""
+    if getattr(model, "_is_replica", False):
+        return list(_named_params_walk(model))
+    cache = model.__dict__.get("_unpp_named_params")
+    if cache is not None:
+        first_owner, first_key, last_owner, last_key, lst = cache
+        if first_owner._parameters.get(first_key) is lst[0][1] and last_owner._parameters.get(last_key) is lst[-1][1]:
+            return lst
+    lst = list(_named_params_walk(model))
+    if lst:
+        def owner(name):
+            mod = model
+            parts = name.split(".")
+            for part in parts[:-1]:
+                mod = getattr(mod, part)
+            return mod, parts[-1]
+        fo, fk = owner(lst[0][0])
+        lo, lk = owner(lst[-1][0])
+        model.__dict__["_unpp_named_params"] = (fo, fk, lo, lk, lst)
+    return lst
 
 
 class Engine:

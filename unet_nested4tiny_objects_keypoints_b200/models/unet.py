@@ -146,6 +146,7 @@ class UNet_Nested(nn.Module):
         state = self.__dict__.copy()
         state["_engines"] = {}
         state["_engines_lock"] = None
+        state.pop("_unpp_named_params", None)  # (engine.named_params' cache: rebuilt on demand)
         return state
 
     def __setstate__(self, state):
