@@ -211,3 +211,13 @@ def test_topk_peaks_kernel_matches_the_oracle():
                     assert torch.equal(xy[b, c, :n, 0].long(), order % h.shape[3]) and torch.equal(xy[b, c, :n, 1].long(), order // h.shape[3])
             continue
         assert np.array_equal(cnt.cpu().numpy(), rcnt) and np.array_equal(xy.cpu().numpy(), rxy) and np.array_equal(val.cpu().numpy(), rval)
+
+
+def test_extract_points_api_on_model_outputs():
+    m = _model(70, False)
+    x = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        heats = m(x.cuda())
+    xy, val, cnt = m.extract_points(heats[2], 2, threshold=0.3)
+    rxy, rval, rcnt = O.topk_peaks(heats[2].cpu().numpy(), 2, 0.3)
+    assert np.array_equal(xy.cpu().numpy(), rxy) and np.array_equal(val.cpu().numpy(), rval) and np.array_equal(cnt.cpu().numpy(), rcnt)

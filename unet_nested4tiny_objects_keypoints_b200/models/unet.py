@@ -168,3 +168,16 @@ class UNet_Nested(nn.Module):
         for head index ``head`` (0..2; default the deepest, final_3).  The arg-max follows
         tools/misc/heatmap.py:173-178 (first maximum in row-major order, x first)."""
         return self._engine(inputs.device).predict_keypoints(inputs, head)
+
+    @staticmethod
+    @torch.no_grad()
+    def extract_points(heatmaps, num: int, threshold: float = 0.5):
+        """The multi-point form of ``Heatmap.extract_points_(pred, num)`` (tools/misc/heatmap.py:148-208), for all planes of a heat-map
+        tensor ``[B, C, H, W]`` at once: the ``num`` brightest regions above ``threshold`` (one retry at 0.9 x threshold), brightest
+        first, as ``(xy int32 [B, C, num, 2] as [x, y], -1 where a plane has fewer; peak fp32 [B, C, num]; count int32 [B, C])``.
+        Regions are strict local maxima instead of the OpenCV watershed: the same points on separated blobs (tests/golden/unetpp_r2.*)."""
+        from .. import ops
+        if not heatmaps.is_cuda:
+            raise RuntimeError("extract_points runs on the device: pass the CUDA heat maps the model returned")
+        with torch.cuda.device(heatmaps.device):
+            return ops.topk_peaks(heatmaps.float(), num, threshold)
