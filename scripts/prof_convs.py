@@ -51,4 +51,3 @@ def level1():
 
 level0()
 level1()
-exec(open(os.path.join(os.path.dirname(__file__), "dbg_head.py")).read()) if os.environ.get("PROF_HEAD") else None
