@@ -221,3 +221,32 @@ def test_extract_points_api_on_model_outputs():
     xy, val, cnt = m.extract_points(heats[2], 2, threshold=0.3)
     rxy, rval, rcnt = O.topk_peaks(heats[2].cpu().numpy(), 2, 0.3)
     assert np.array_equal(xy.cpu().numpy(), rxy) and np.array_equal(val.cpu().numpy(), rval) and np.array_equal(cnt.cpu().numpy(), rcnt)
+
+
+def test_edge_shapes_empty_batch_smallest_and_ragged():
+    """Edge cases of the reference's layers: an empty batch gives empty outputs in eval mode; the smallest legal image is 8x8 (one pixel at
+    the deepest level); extreme aspect ratios; a single value per channel at the deepest level is an error in train mode, like
+    nn.BatchNorm2d's ("Expected more than 1 value per channel when training")."""
+    sd = O.synth_state_dict(seed=73)
+    m = _model(73, False)
+    with torch.no_grad():
+        outs = m(torch.empty(0, 3, 32, 32, device="cuda"))
+    assert all(tuple(o.shape) == (0, 4, 32, 32) for o in outs)
+    xy, val, _ = m.predict_keypoints(torch.empty(0, 3, 32, 32, device="cuda"))
+    assert tuple(xy.shape) == (0, 4, 2) and tuple(val.shape) == (0, 4)
+    for shape in [(1, 3, 8, 8), (3, 3, 8, 8), (1, 3, 8, 2048), (1, 3, 1024, 8), (2, 3, 24, 8)]:
+        x = torch.randn(*shape, generator=torch.Generator().manual_seed(shape[3]))
+        with torch.no_grad():
+            outs = m(x.cuda())
+        for o, r in zip(outs, O.forward(sd, x)):
+            assert float((o.cpu() - r).abs().max()) <= 3e-2, shape
+        xy, _, heats = m.predict_keypoints(x.cuda())
+        assert np.array_equal(xy.cpu().numpy(), O.argmax_keypoints(heats[2].cpu().numpy())[0])
+    m.train()
+    with pytest.raises(ValueError, match="more than 1 value per channel"):
+        m(torch.randn(1, 3, 8, 8, device="cuda"))
+    with pytest.raises(ValueError, match="divisible by 8"):
+        m(torch.randn(1, 3, 12, 16, device="cuda"))
+    out = m(torch.randn(2, 3, 8, 8, device="cuda"))  # two values per channel at the deepest level: legal
+    sum(o.sum() for o in out).backward()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters())

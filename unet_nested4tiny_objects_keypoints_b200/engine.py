@@ -236,6 +236,10 @@ class Engine:
         ``x``: float32 [B,C,H,W] like the reference, or uint8 images ([B,C,H,W], or [B,H,W,C] with ``channels_last``) that are
         scaled by 1/255 on the device — torchvision's ToTensor (datasets/datasets_base.py:71-72) fused into the layout change."""
         B, H, W = self._check_input(x, channels_last)
+        if B == 0:  # an empty batch: the reference's layers return empty tensors in eval mode
+            self.last_heats = torch.empty(len(set(heads)), 0, self.model.n_classes, H, W, dtype=torch.float32, device=self.device)
+            want = sorted(set(int(k) for k in heads))
+            return tuple(self.last_heats[want.index(k)] if k in want else None for k in range(3))
         x = x.contiguous()
         # the kernels, their TMA descriptors and the per-device shared-memory opt-in belong to the ENGINE's device, whatever the
         # calling thread's current device is (the reference works regardless of it)
@@ -351,6 +355,9 @@ class Engine:
         if head not in (0, 1, 2):
             raise ValueError("head must be 0, 1 or 2")
         heats = self.forward_eval(x, heads=(head,))
+        if x.shape[0] == 0:
+            return (torch.empty(0, self.model.n_classes, 2, dtype=torch.int32, device=self.device),
+                    torch.empty(0, self.model.n_classes, dtype=torch.float32, device=self.device), heats)
         with torch.cuda.device(self.device):
             xy, val = ops.argmax_peaks(heats[head])
         return xy, val, heats

@@ -648,6 +648,10 @@ class _UNetNestedFn(torch.autograd.Function):
 
 
 def run_autograd(eng: Engine, x: torch.Tensor):
+    if eng.model.is_batchnorm and x.dim() == 4 and x.shape[0] * (x.shape[2] >> 3) * (x.shape[3] >> 3) <= 1:
+        # nn.BatchNorm2d refuses batch statistics of a single value (torch/nn/functional.py:_verify_batch_size): the deepest level
+        # (models/unet.py:262-263) sees B x H/8 x W/8 values per channel — mirror the reference's error instead of dividing by zero variance
+        raise ValueError(f"Expected more than 1 value per channel when training, got input size {[x.shape[0], eng.filters[3], x.shape[2] >> 3, x.shape[3] >> 3]}")
     params = [p for _, p in named_params(eng.model)]
     if torch.is_grad_enabled() and any(p.requires_grad for p in params):
         return _UNetNestedFn.apply(eng, x, *params)
